@@ -1,0 +1,218 @@
+/*
+ * flecsph_b200.h — C ABI of the B200-native FleCSPH per-step particle hot path.
+ *
+ * This is the drop-in boundary: one `fsph_system`
+ * replaces one `body_system<double,D>` of the reference
+ * (mpisph/bodies_system.h:38-379).  All particle state lives on the device as
+ * fp64 / int64 SoA columns; the host sees it only through fsph_set_column /
+ * fsph_get_column (or the AoS marshalling calls) at the points where the
+ * reference touches `std::vector<body>` (read_bodies, write_bodies,
+ * getLocalbodies, analysis).  Every entry point below cites the reference
+ * interface it replaces.
+ *
+ * Error convention: every call returns 0 on success, non-zero on failure
+ * (fsph_last_error gives the text).  The reference aborts (assert /
+ * mpi_assert -> MPI_Abort, mpisph/utils.h:34-38); the C++ facade on top of
+ * this ABI turns a non-zero code into the same abort.
+ *
+ * The same ABI is implemented three times, which is what makes the parity
+ * tests read like one another:
+ *   flecsph_b200/csrc  -> libflecsph_b200.so   the product (sm_100a CUDA, no CPU path)
+ *   oracle/            -> liboracle_port.so    CPU restatement (test infrastructure)
+ *   oracle/_ref        -> libflecsph_ref_Dd.so the unmodified reference headers behind
+ *                                              this ABI (test infrastructure)
+ */
+#ifndef FLECSPH_B200_H
+#define FLECSPH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fsph_system fsph_system;
+
+/* sph_kernel keyword, same order as include/params.h:124-133 */
+enum fsph_kernel {
+  FSPH_KERNEL_CUBIC_SPLINE = 0,
+  FSPH_KERNEL_QUINTIC_SPLINE = 1,
+  FSPH_KERNEL_WENDLAND_C2 = 2,
+  FSPH_KERNEL_WENDLAND_C4 = 3,
+  FSPH_KERNEL_WENDLAND_C6 = 4,
+  FSPH_KERNEL_GAUSSIAN = 5,
+  FSPH_KERNEL_SUPER_GAUSSIAN = 6,
+  FSPH_KERNEL_SINC = 7
+};
+/* eos_type keyword, include/params.h:135-141 */
+enum fsph_eos { FSPH_EOS_IDEAL = 0, FSPH_EOS_POLYTROPIC = 1 };
+/* sph_viscosity keyword, include/params.h:145-148 */
+enum fsph_viscosity { FSPH_VISC_CONSTANT = 0, FSPH_VISC_CULLEN = 1 };
+
+/* POD snapshot of the `param::` globals the hot path reads
+ * (include/params.h:160-628) plus the `physics::` time globals
+ * (include/physics/default_physics.h:31-40). */
+typedef struct fsph_params {
+  int32_t dim;                    /* gdimension (app/drivers/include/user.h:36) */
+  int32_t sph_kernel;             /* params.h:227 */
+  int32_t eos_type;               /* params.h:468 */
+  int32_t sph_viscosity;          /* params.h:495 */
+  double sph_eta;                 /* params.h:212 */
+  double sph_sinc_index;          /* params.h:232 */
+  double poly_gamma;              /* params.h:478 */
+  double sph_viscosity_alpha;     /* params.h:501 */
+  double sph_viscosity_beta;      /* params.h:506 */
+  double sph_viscosity_epsilon;   /* params.h:511 */
+  double timestep_cfl_factor;     /* params.h:183 */
+  double initial_dt;              /* params.h:178 */
+  double out_screen_dt;           /* params.h:339 */
+  double out_scalar_dt;           /* params.h:350 */
+  double out_h5data_dt;           /* params.h:366 */
+  double fmm_macangle;            /* params.h:542 */
+  double gravitational_constant;  /* params.h:628 */
+  double box_length, box_width, box_height; /* params.h:258-266 */
+  int32_t adaptive_timestep;      /* params.h:188 */
+  int32_t sph_variable_h;         /* params.h:244 */
+  int32_t sph_update_uniform_h;   /* params.h:238 */
+  int32_t evolve_internal_energy; /* params.h:584 */
+  int32_t thermokinetic_formulation; /* params.h:591 */
+  int32_t enable_fmm;             /* params.h:537 */
+  int32_t relaxation_steps;       /* params.h:563 */
+  int32_t pressure_updates_number;/* params.h:194 */
+  int32_t periodic_boundary_x, periodic_boundary_y, periodic_boundary_z; /* params.h:292-300 */
+  int32_t reserved_;
+} fsph_params;
+
+/* Fill `p` with the reference's defaults (include/params.h) for `dim`. */
+void fsph_default_params(fsph_params * p, int32_t dim);
+
+/* Particle columns (fields of body_u, include/physics/body.h:221-251, and of
+ * entity, include/tree_topology/tree_types.h:376-381).  Vector fields are
+ * stored as `dim` separate contiguous columns; fsph_set/get_column move them
+ * as an [n][dim] row-major host array. */
+enum fsph_column {
+  FSPH_COL_POS = 0,     /* coordinates_      [n][dim] f64 */
+  FSPH_COL_VEL,         /* velocity_         [n][dim] f64 */
+  FSPH_COL_VELHALF,     /* velocityhalf_     [n][dim] f64 */
+  FSPH_COL_ACC,         /* acceleration_     [n][dim] f64 */
+  FSPH_COL_GACC,        /* g_acceleration_   [n][dim] f64 */
+  FSPH_COL_MASS,        /* mass_             [n] f64 */
+  FSPH_COL_H,           /* radius_ = full kernel support radius [n] f64 */
+  FSPH_COL_RHO,         /* density_          */
+  FSPH_COL_P,           /* pressure_         */
+  FSPH_COL_U,           /* internalenergy_   */
+  FSPH_COL_E,           /* totalenergy_      */
+  FSPH_COL_CS,          /* soundspeed_       */
+  FSPH_COL_DUDT,        /* dudt_             */
+  FSPH_COL_DEDT,        /* dedt_             */
+  FSPH_COL_DT,          /* dt_               */
+  FSPH_COL_ALPHA,       /* alpha_            */
+  FSPH_COL_VSIG,        /* signalspeed_      */
+  FSPH_COL_GPOT,        /* g_potential_      */
+  FSPH_COL_ADIABATIC,   /* adiabatic_        */
+  FSPH_COL_ID,          /* id_               [n] i64 */
+  FSPH_COL_KEY,         /* key_              [n] u64 (read-only: written by update_iteration) */
+  FSPH_COL_TYPE,        /* type_ (0 NORMAL, 1 WALL) [n] i32 */
+  FSPH_COL_NNEIGH,      /* neighbour count of the last sweep [n] i32 (read-only) */
+  FSPH_COL_COUNT_
+};
+
+/* apply_in_smoothinglength(f) callables (mpisph/bodies_system.h:304) the
+ * in-scope drivers pass (app/drivers/hydro/main_driver.cc:118-233). */
+enum fsph_sweep_op {
+  FSPH_SWEEP_DENSITY_PRESSURE_SOUNDSPEED = 0, /* physics::compute_density_pressure_soundspeed, default_physics.h:309 */
+  FSPH_SWEEP_ACCELERATION = 1,                /* physics::compute_acceleration, default_physics.h:348 */
+  FSPH_SWEEP_DUDT = 2,                        /* physics::compute_dudt, default_physics.h:421 */
+  FSPH_SWEEP_DEDT = 3,                        /* physics::compute_dedt, default_physics.h:502 */
+  FSPH_SWEEP_NEIGHBORS_ONLY = 4               /* empty functor: neighbour search only (app/drivers/tree/main_driver.cc:103) */
+};
+
+/* apply_all(f) callables (mpisph/bodies_system.h:318). */
+enum fsph_apply_op {
+  FSPH_APPLY_EOS_INIT = 0,                 /* eos::init, eos/eos.h:157 */
+  FSPH_APPLY_SET_TOTAL_ENERGY,             /* physics::set_total_energy, default_physics.h:327 */
+  FSPH_APPLY_SAVE_VELOCITYHALF,            /* integration::save_velocityhalf, integration.h:52 */
+  FSPH_APPLY_LEAPFROG_KICK_V,              /* integration::leapfrog_kick_v, integration.h:65 */
+  FSPH_APPLY_LEAPFROG_KICK_U,              /* integration::leapfrog_kick_u, integration.h:80 */
+  FSPH_APPLY_LEAPFROG_KICK_E,              /* integration::leapfrog_kick_e, integration.h:94 */
+  FSPH_APPLY_LEAPFROG_DRIFT,               /* integration::leapfrog_drift, integration.h:106 */
+  FSPH_APPLY_RECOMPUTE_P_CS,               /* physics::recompute_pressure_soundspeed, default_physics.h:153 */
+  FSPH_APPLY_RECOMPUTE_P_CS_THERMOKINETIC, /* physics::recompute_pressure_soundspeed_thermokinetic, default_physics.h:169 */
+  FSPH_APPLY_COMPUTE_DT,                   /* physics::compute_dt, default_physics.h:602 */
+  FSPH_APPLY_CHECK_NANS,                   /* physics::check_nans, default_physics.h:918 */
+  FSPH_APPLY_CHECK_NEGATIVITY              /* physics::check_negativity, default_physics.h:962 */
+};
+
+/* get_all(f) callables (mpisph/bodies_system.h:335). */
+enum fsph_reduce_op {
+  FSPH_GET_SET_ADAPTIVE_TIMESTEP = 0,      /* physics::set_adaptive_timestep, default_physics.h:761; out[0] = new dt */
+  FSPH_GET_COMPUTE_SMOOTHINGLENGTH,        /* physics::compute_smoothinglength, default_physics.h:825 */
+  FSPH_GET_COMPUTE_AVERAGE_SMOOTHINGLENGTH,/* physics::compute_average_smoothinglength, default_physics.h:879 */
+  FSPH_GET_TOTAL_MASS,                     /* analysis::compute_total_mass, analysis.h:69; out[0] */
+  FSPH_GET_TOTAL_ENERGY,                   /* analysis::compute_total_energy, analysis.h:113; out[0] */
+  FSPH_GET_TOTAL_MOMENTUM                  /* analysis::compute_total_momentum, analysis.h:56; out[0..dim) */
+};
+
+/* --- life cycle ---------------------------------------------------------- */
+/* body_system<double,D>::body_system() (bodies_system.h:45).  `device` is the
+ * CUDA ordinal.  Returns NULL on failure (no CUDA device => failure; there is
+ * no CPU path in the product library). */
+fsph_system * fsph_create(const fsph_params * p, int32_t device);
+void fsph_destroy(fsph_system * s);
+const char * fsph_last_error(const fsph_system * s);
+/* "cuda-sm100a" for the product, "oracle-port" / "reference" for the checkers. */
+const char * fsph_backend(void);
+
+/* --- particle storage: read_bodies / getLocalbodies (bodies_system.h:83,345) */
+int32_t fsph_resize(fsph_system * s, int64_t n);
+int64_t fsph_nbodies(const fsph_system * s);                      /* bodies_system.h:349 */
+int32_t fsph_set_column(fsph_system * s, int32_t col, const void * host);
+int32_t fsph_get_column(fsph_system * s, int32_t col, void * host);
+/* AoS marshalling of the reference's 368-byte `body` records: offsets[col]
+ * is offsetof(body, field) obtained in the C++ facade, -1 to skip a column. */
+int32_t fsph_upload_aos(fsph_system * s, const void * bodies, int64_t n, int64_t stride, const int64_t * offsets);
+int32_t fsph_download_aos(fsph_system * s, void * bodies, int64_t stride, const int64_t * offsets);
+
+/* --- time globals: physics::dt / totaltime / iteration (default_physics.h:31-40) */
+int32_t fsph_set_time(fsph_system * s, double dt, double totaltime, int64_t iteration);
+int32_t fsph_get_time(const fsph_system * s, double * dt, double * totaltime, int64_t * iteration);
+int32_t fsph_advance_time(fsph_system * s);                       /* physics::advance_time, default_physics.h:853 */
+
+/* --- the hot path --------------------------------------------------------- */
+int32_t fsph_update_iteration(fsph_system * s);                   /* bodies_system.h:152: range, keys, sort, tree */
+int32_t fsph_reset_ghosts(fsph_system * s);                       /* bodies_system.h:273 */
+int32_t fsph_sweep(fsph_system * s, int32_t sweep_op);            /* apply_in_smoothinglength, bodies_system.h:304 */
+int32_t fsph_apply(fsph_system * s, int32_t apply_op);            /* apply_all, bodies_system.h:318 */
+int32_t fsph_reduce(fsph_system * s, int32_t reduce_op, double * out, int32_t nout); /* get_all, bodies_system.h:335 */
+int32_t fsph_gravitation_fmm(fsph_system * s);                    /* bodies_system.h:282 */
+int32_t fsph_get_range(fsph_system * s, double * lo, double * hi);/* getRange, bodies_system.h:131 */
+double fsph_get_smoothinglength(fsph_system * s);                 /* getSmoothinglength, bodies_system.h:112 */
+
+/* One whole non-initial iteration of the hydro / newtonian driver loop
+ * (app/drivers/hydro/main_driver.cc:175-277, newtonian/main_driver.cc:184-296)
+ * issued as one call so the element-wise passes can be fused between the
+ * sweeps; result identical to issuing the individual calls in driver order.
+ * `initial` != 0 runs the first-iteration branch (hydro/main_driver.cc:102-173). */
+int32_t fsph_step(fsph_system * s, int32_t initial);
+
+/* --- introspection used by the parity tests ------------------------------- */
+/* Octree node table, sorted by key: tree_topology::cofm_ (tree_topology.h:2103)
+ * with node fields of cofm_u (tree_types.h:51-141). */
+int64_t fsph_tree_num_nodes(fsph_system * s);
+int32_t fsph_tree_get_nodes(fsph_system * s, uint64_t * key, double * mass, double * com /*[nn][dim]*/,
+  double * radius, double * lap, double * bmin /*[nn][dim]*/, double * bmax /*[nn][dim]*/, int64_t * sub_entities);
+/* Depth of every particle's leaf cell in the tree (in storage order). */
+int32_t fsph_tree_get_leaf_depth(fsph_system * s, int32_t * depth);
+/* Neighbour lists of the last sweep in CSR form, neighbour *ids* sorted
+ * ascending per particle; rows in storage (key-sorted) order.
+ * offsets has n+1 entries; call with ids == NULL to get only offsets. */
+int32_t fsph_neighbor_lists(fsph_system * s, int64_t * offsets, int64_t * ids);
+
+/* Per-phase device times of the last fsph_step in milliseconds (CUDA events);
+ * names is a ';'-separated list, returns the number of phases. */
+int32_t fsph_phase_times(fsph_system * s, double * ms, int32_t cap, const char ** names);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLECSPH_B200_H */
