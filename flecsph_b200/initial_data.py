@@ -1,0 +1,170 @@
+"""Synthetic initial data for the benchmark / parity configurations.
+
+Restates (does not copy) what the reference's single-rank initial-data
+generators produce, so that no HDF5 file is needed:
+  * lattices: include/lattice.h:224-293 (rectangular / HCP / FCC rules, loops
+    `for(p = min; p < max; p += d)` -> sequential accumulation = np.cumsum) and
+    in_domain_{1,3}d (lattice.h:74-133, b_tol = 1e-6);
+  * Sedov blast:  app/id_generators/sedov/main.cc:68-312 with data/sedov_nx20.par;
+  * Noh implosion: app/id_generators/noh/main.cc:236-292 with data/noh_nx20.par;
+  * Sod tube 1-D: app/id_generators/sodtube/main.cc with data/sodtube_t1_n100.par
+    (equal-mass variant, test #1).
+Every function returns (fields, params_overrides): a dict of column-name ->
+numpy array in generation order (ids 0..N-1) and the `.par` values of the run.
+"""
+import math
+import numpy as np
+
+B_TOL = 1e-6  # lattice.h: particle_lattice::b_tol
+
+
+def _axis(lo, hi, step, offset=0.0):
+    """Values of `for(p = lo + offset; p < hi; p += step)` with the loop's own rounding."""
+    n = int(math.ceil((hi - lo - offset) / step)) + 2
+    steps = np.full(n, step)
+    steps[0] = lo + offset
+    p = np.cumsum(steps)
+    return p[p < hi]
+
+
+def lattice_3d(lattice_type, domain_type, bmin, bmax, sep):
+    """generator_lattice_3d (lattice.h:224-293). Returns [n,3] positions in generation order."""
+    xmin, ymin, zmin = bmin
+    xmax, ymax, zmax = bmax
+    dx, dy, dz = sep, sep * math.sqrt(3.0) / 2.0, sep * math.sqrt(2.0 / 3.0)
+    tol = B_TOL * (xmax - xmin)
+    out = []
+    zs = _axis(zmin, zmax, dx if lattice_type == 0 else dz)
+    zl = 0
+    for z in zs:
+        if lattice_type == 0:
+            ys = _axis(ymin, ymax, dx)
+            xs = _axis(xmin, xmax, dx)
+            X, Y = np.meshgrid(xs, ys)
+        else:
+            ys = _axis(ymin - zl * dy / 3, ymax, dy)
+            yo = (np.arange(len(ys)) % 2).astype(np.float64)
+            x0 = _axis(xmin, xmax + 2 * dx, dx)  # row template, shifted per row below
+            # rows start at xmin + (yo - zl)*dx/2 and run while x < xmax
+            X = x0[None, :] + ((yo - zl) * dx / 2.0)[:, None]
+            Y = np.broadcast_to(ys[:, None], X.shape)
+        Z = np.full(X.shape, z)
+        m = (X > xmin - tol) & (X < xmax - tol) & (Y > ymin - tol) & (Y < ymax - tol) & (z > zmin - tol) & (z < zmax - tol)
+        if lattice_type != 0:
+            m &= X < xmax
+        if domain_type == 1:
+            r = 0.5 * min(xmax - xmin, ymax - ymin, zmax - zmin)
+            x0c, y0c, z0c = 0.5 * (xmin + xmax) - tol, 0.5 * (ymin + ymax) - tol, 0.5 * (zmin + zmax) - tol
+            m &= (X - x0c) ** 2 + (Y - y0c) ** 2 + (z - z0c) ** 2 < r * r
+        out.append(np.stack([X[m], Y[m], Z[m]], 1))
+        if lattice_type == 1:
+            zl = 1 - zl
+        elif lattice_type == 2:
+            zl = (zl + 1) * (1 if zl < 3 else 0)
+    return np.concatenate(out, 0)
+
+
+def _sphere_common(nx, rho0, P0, gamma, eta, kernel_width, R=1.0, lattice_type=2):
+    sep = 2.0 * R / (nx - 1)
+    pos = lattice_3d(lattice_type, 1, (-R,) * 3, (R,) * 3, sep)
+    n = len(pos)
+    total_mass = rho0 * (4.0 * math.pi / 3.0) * R ** 3  # constant profile normalisation (sedov/main.cc:126-133)
+    m = total_mass / n
+    h = eta * kernel_width * (m / rho0) ** (1.0 / 3.0)
+    K0 = P0 / rho0 ** gamma
+    u = K0 * rho0 ** (gamma - 1) / (gamma - 1)
+    f = dict(pos=pos, vel=np.zeros((n, 3)), mass=np.full(n, m), h=np.full(n, h), rho=np.full(n, rho0),
+             u=np.full(n, u), id=np.arange(n, dtype=np.int64))
+    return f, m
+
+
+def sedov_3d(nx=20, eta=1.2, blast_energy=2e-7, blast_radius=0.06, P0=1e-7, gamma=1.4):
+    """Sedov blast wave, data/sedov_nx20.par semantics; nx scales the particle count (~0.74 nx^3)."""
+    f, m = _sphere_common(nx, 1.0, P0, gamma, eta, 2.0)
+    r = np.sqrt((f["pos"] ** 2).sum(1))
+    blast = r < blast_radius
+    if blast.any():
+        f["u"] = f["u"] + np.where(blast, blast_energy / (m * blast.sum()), 0.0)
+    f["P"] = f["rho"] * f["u"] * (gamma - 1)
+    f["dt"] = np.full(len(r), 1e-4)
+    par = dict(sph_kernel="wendland c4", sph_eta=eta, poly_gamma=gamma, initial_dt=1e-4, sph_variable_h=1,
+               adaptive_timestep=1, timestep_cfl_factor=0.01)
+    return f, par
+
+
+def noh_3d(nx=20, eta=1.2, P0=1e-6, gamma=1.6666667, infall=0.1):
+    """Noh implosion, data/noh_nx20.par semantics (noh/main.cc:236-292): radial inflow v = -0.1 r/|r|."""
+    f, m = _sphere_common(nx, 1.0, P0, gamma, eta, 2.0)
+    r = np.sqrt((f["pos"] ** 2).sum(1))
+    rr = np.where(r > 0, r, 1.0)
+    f["vel"] = -infall * f["pos"] / rr[:, None] * (r > 0)[:, None]
+    f["P"] = f["rho"] * f["u"] * (gamma - 1)
+    f["dt"] = np.full(len(r), 2e-3)
+    par = dict(sph_kernel="wendland c4", sph_eta=eta, poly_gamma=gamma, initial_dt=2e-3, sph_variable_h=1,
+               adaptive_timestep=1, timestep_cfl_factor=0.25)
+    return f, par
+
+
+def collapse_3d(nx=10, eta=1.2, P0=1e-10, gamma=1.4):
+    """Self-gravitating cold sphere, data/collapse_nx10.par semantics: quintic spline, du/dt path, FMM gravity."""
+    f, m = _sphere_common(nx, 1.0, P0, gamma, eta, 3.0)
+    f["P"] = f["rho"] * f["u"] * (gamma - 1)
+    f["dt"] = np.full(len(f["mass"]), 5e-4)
+    par = dict(sph_kernel="quintic spline", sph_eta=eta, poly_gamma=gamma, initial_dt=5e-4, sph_variable_h=0,
+               adaptive_timestep=0, thermokinetic_formulation=0, enable_fmm=1, fmm_macangle=0.8,
+               gravitational_constant=1.0)
+    return f, par
+
+
+def sodtube_1d(nx=100, eta=1.2, gamma=1.4, box_length=3.0):
+    """Sod shock tube test #1, 1-D, equal-mass particles (data/sodtube_t1_n100.par)."""
+    nx = ((nx - 1) // 3) * 3 + 1  # sodtube/main.cc:124
+    sep = box_length / (nx - 1)
+    rho1, rho2, P1, P2 = 1.0, 0.125, 1.0, 0.1
+    m = rho1 * sep
+    sep_lr = m / rho2
+    tol = B_TOL
+    # in_domain_1d (lattice.h:74-83): keep xmin - tol*L < x < xmax - tol*L
+    c = _axis(-box_length / 6.0, box_length / 6.0 - tol * box_length / 3.0, sep)
+    rgt = _axis(box_length / 6.0, box_length / 2.0 - tol * box_length / 3.0, sep_lr)
+    lft = _axis(-box_length / 2.0, -box_length / 6.0 - tol, sep_lr)
+    x = np.concatenate([c, rgt, lft])
+    mid = np.concatenate([np.ones(len(c), bool), np.zeros(len(rgt) + len(lft), bool)])
+    n = len(x)
+    rho = np.where(mid, rho1, rho2)
+    P = np.where(mid, P1, P2)
+    u = P / ((gamma - 1) * rho)
+    h = eta * 2.0 * m / rho
+    f = dict(pos=x[:, None], vel=np.zeros((n, 1)), mass=np.full(n, m), h=h, rho=rho, P=P, u=u,
+             id=np.arange(n, dtype=np.int64), dt=np.full(n, 1e-3))
+    par = dict(sph_kernel="wendland c4", sph_eta=eta, poly_gamma=gamma, initial_dt=1e-3, sph_variable_h=1,
+               adaptive_timestep=1, timestep_cfl_factor=0.25)
+    return f, par
+
+
+def random_box(n, dim=3, seed=0, h_jitter=0.0, eta=1.2, vel_amp=0.1):
+    """Uniform random particles in the unit box (the reference's own tree tests use this:
+    mpisph/test/tree3d.cc:48-111), optionally with +-h_jitter relative scatter in h."""
+    rng = np.random.default_rng(seed)
+    pos = rng.random((n, dim))
+    m = np.full(n, 1.0 / n)
+    h0 = eta * 2.0 * (1.0 / n) ** (1.0 / dim)
+    h = h0 * (1.0 + h_jitter * (2.0 * rng.random(n) - 1.0))
+    vel = vel_amp * (2.0 * rng.random((n, dim)) - 1.0)
+    f = dict(pos=pos, vel=vel, mass=m, h=h, rho=np.ones(n), u=1.0 + 0.1 * rng.random(n), P=np.full(n, 0.4),
+             id=rng.permutation(n).astype(np.int64), dt=np.full(n, 1e-3))
+    par = dict(sph_kernel="wendland c4", sph_eta=eta, poly_gamma=1.4, initial_dt=1e-3, sph_variable_h=1,
+               adaptive_timestep=1, timestep_cfl_factor=0.25)
+    return f, par
+
+
+def nx_for_particles(target, lo=8, hi=2000):
+    """Smallest lattice_nx whose FCC unit sphere holds >= target particles (count ~ (4pi/3)/(s^3/sqrt2))."""
+    est = lambda nx: (4.0 * math.pi / 3.0) / ((2.0 / (nx - 1)) ** 3 / math.sqrt(2.0))
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if est(mid) >= target:
+            hi = mid
+        else:
+            lo = mid + 1
+    return lo
