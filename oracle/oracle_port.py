@@ -1,0 +1,679 @@
+"""oracle_port.py -- TEST INFRASTRUCTURE ONLY (never imported by the product).
+
+A numpy restatement of the reference's per-step particle hot path, independent
+of the CUDA code, exposing the same host-side interface as
+flecsph_b200.capi.BodySystem so that parity tests can drive either.  Only
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import it.
+
+Parity status: PINNED.  tests/test_oracle.py checks every function below
+against the UNMODIFIED reference headers compiled behind the C ABI
+(oracle/_ref/libflecsph_ref_{1,2,3}d.so, built by oracle/Makefile from
+/root/reference) on seeded inputs, and against the golden vectors committed
+under tests/golden/ (generated from that same reference build by
+tests/golden/make_golden.py).  The reference's own tests hold no numeric
+golden vectors for this path; its behavioural pins
+(neighbour set == brute force for uniform h, mpisph/test/tree3d.cc:87-108;
+self in neighbours, app/drivers/tree/main_driver.cc:108-113; root mass == sum m,
+tree3d.cc:85; key round trip, tree_topology/test/filling_curves.cc:202-241)
+are asserted in tests/test_oracle.py as well.
+
+Each function cites the reference file:line it follows (paths relative to
+/root/reference).  Bit-exact parts (range, keys, order, tree, node summaries,
+neighbour sets) use strictly the reference's operation order in IEEE fp64;
+physics sums are only required to agree to 1e-10 and are vectorised.
+"""
+import math
+import numpy as np
+
+TINY = 1e10 * np.finfo(np.float64).tiny  # kernels.h:64, viscosity.h:36
+SUB_ENTITIES = 128                       # tree_topology.h:2121
+TOL = np.finfo(np.float64).eps * 10.0    # tree_geometry.h:57
+
+VEC = ("pos", "vel", "velhalf", "acc", "gacc")
+SCAL = ("mass", "h", "rho", "P", "u", "e", "cs", "dudt", "dedt", "dt", "alpha", "vsig", "gpot", "adiabatic")
+
+# sigma tables, kernels.h:40-47
+SIGMA = {
+    0: [4. / 3., 40. / (7. * math.pi), 8. / math.pi],
+    1: [1. / 40., 63. / (478. * math.pi), 81. / (359. * math.pi)],
+    2: [1.25, 7. / math.pi, 21. / (2. * math.pi)],
+    3: [1.5, 9. / math.pi, 495. / (32. * math.pi)],
+    4: [55. / 32., 78. / (7. * math.pi), 1365. / (64. * math.pi)],
+}
+
+
+def kernel_width(k):
+    """kernels::select, kernels.h:753-764."""
+    return 3.0 if k in (1, 5, 6) else 2.0
+
+
+def _clz64(x):
+    """count leading zeros of uint64 array (x != 0)."""
+    x = x.astype(np.uint64)
+    n = np.zeros(x.shape, np.int64)
+    for s in (32, 16, 8, 4, 2, 1):
+        m = (x >> np.uint64(64 - s)) == 0
+        n += np.where(m, s, 0)
+        x = np.where(m, x << np.uint64(s), x)
+    return n
+
+
+class PortSystem:
+    backend = "oracle-port"
+
+    def __init__(self, params, backend=None, device=0):
+        self.par = params
+        self.dim = D = params.dim
+        self.B = 63 // D  # filling_curve.h:45-47
+        self.n = 0
+        self.c = {}
+        self.dt_ = params.initial_dt
+        self.totaltime = 0.0
+        self.iteration = 0
+        self.dt_saved = 0.0
+        self.totaltime_next = 0.0
+        self.t_out = [0.0, 0.0, 0.0]
+        self.nbr_off = None
+        self.kw = kernel_width(params.sph_kernel)
+
+    def close(self):
+        pass
+
+    # ---- storage ------------------------------------------------------
+    def resize(self, n):
+        D = self.dim
+        self.n = n
+        for k in VEC:
+            self.c[k] = np.zeros((n, D))
+        for k in SCAL:
+            self.c[k] = np.zeros(n)
+        self.c["id"] = np.arange(n, dtype=np.int64)
+        self.c["key"] = np.zeros(n, np.uint64)
+        self.c["type"] = np.zeros(n, np.int32)
+        self.c["nneigh"] = np.zeros(n, np.int32)
+
+    def nbodies(self):
+        return self.n
+
+    def load_bodies(self, fields):
+        self.resize(len(fields["mass"]))
+        for k, v in fields.items():
+            self.c[k] = np.array(v, dtype=self.c[k].dtype).reshape(self.c[k].shape)
+
+    def set(self, col, arr):
+        from flecsph_b200.capi import COL_NAMES
+        k = COL_NAMES[col]
+        self.c[k] = np.array(arr, dtype=self.c[k].dtype).reshape(self.c[k].shape)
+
+    def get(self, col):
+        from flecsph_b200.capi import COL_NAMES
+        return self.c[COL_NAMES[col]].copy()
+
+    def snapshot(self, names=None):
+        names = names or [k for k in self.c if k != "nneigh"]
+        return {k: self.c[k].copy() for k in names}
+
+    def set_time(self, dt, totaltime=0.0, iteration=0):
+        self.dt_, self.totaltime, self.iteration = dt, totaltime, iteration
+
+    def get_time(self):
+        return self.dt_, self.totaltime, self.iteration
+
+    def advance_time(self):
+        """physics::advance_time, default_physics.h:853-860."""
+        self.iteration += 1
+        if self.par.adaptive_timestep:
+            self.totaltime = self.totaltime_next
+        else:
+            self.totaltime = self.totaltime + self.dt_
+
+    # ---- range, keys, sort ---------------------------------------------
+    def compute_range(self):
+        """body_system::mpi_compute_range, mpisph/bodies_system.h:231-268."""
+        x, h = self.c["pos"], self.c["h"]
+        self.lo = (x - h[:, None]).min(0)
+        self.hi = (x + h[:, None]).max(0)
+
+    def get_range(self):
+        return self.lo.copy(), self.hi.copy()
+
+    def compute_keys(self):
+        """morton_curve_u(range, p), filling_curve.h:503-525; compute_keys, tree_topology.h:828-832."""
+        D, B = self.dim, self.B
+        x = self.c["pos"]
+        scale = self.hi - self.lo
+        two_b = float(1 << B)
+        t = (x - self.lo[None, :]) / scale[None, :] * two_b   # sub, div, mul in this order
+        maxv = (1 << B) - 1
+        key = np.full(self.n, 1 << (D * B), dtype=np.uint64)
+        coords = []
+        for d in range(D):
+            # static_cast<uint64_t>(double): truncation; values reach 2^B at most
+            cd = np.minimum(t[:, d], two_b)
+            ci = np.array([min(maxv, int(v)) for v in cd], dtype=np.uint64) if B > 52 else \
+                np.minimum(np.uint64(maxv), cd.astype(np.uint64))
+            coords.append(ci)
+        for i in range(B):
+            for d in range(D):
+                bit = (coords[d] >> np.uint64(i)) & np.uint64(1)
+                key |= bit << np.uint64(i * D + d)
+        self.c["key"] = key
+
+    def sort_bodies(self):
+        """psort::psort with the (key, id) comparator, bodies_system.h:195-206."""
+        order = np.lexsort((self.c["id"], self.c["key"]))
+        for k in self.c:
+            self.c[k] = self.c[k][order]
+        self.nbr_off = None
+
+    # ---- tree -----------------------------------------------------------
+    def build_tree(self):
+        """tree_topology::build_tree, tree_topology.h:878-997 (result: the canonical octree of
+        SURVEY.md 3.4) and physics::compute_cofm, default_physics.h:59-119."""
+        D, B, n = self.dim, self.B, self.n
+        key = self.c["key"]
+        if n > 1:
+            x = key[:-1] ^ key[1:]
+            if (x == 0).any():
+                raise RuntimeError("duplicate keys")
+            p = 63 - _clz64(x)
+            d = B - 1 - p // D
+        else:
+            d = np.zeros(0, np.int64)
+        dprev = np.concatenate([[-1], d])
+        dcur = np.concatenate([d, [-1]])
+        if n == 1:
+            dcur[0] = 0  # the root always exists (tree_topology.h:893)
+        # cells in pre-order: nodes (dprev, dcur] then the leaf
+        cd, cs, cl = [], [], []
+        for i in range(n):
+            for k in range(dprev[i] + 1, dcur[i] + 1):
+                cd.append(k); cs.append(i); cl.append(0)
+            cd.append(max(dprev[i], dcur[i]) + 1); cs.append(i); cl.append(1)
+        cd, cs, cl = np.array(cd), np.array(cs), np.array(cl)
+        order = np.lexsort((cs, cd))
+        cd, cs, cl = cd[order], cs[order], cl[order]
+        nc = len(cd)
+        isnode = cl == 0
+        noderank = np.cumsum(isnode) - isnode
+        nn = int(isnode.sum())
+        # parent prefix of each cell
+        shift = (D * (B - (cd - 1))).astype(np.uint64)
+        ppref = np.where(cd > 0, key[cs] >> np.minimum(shift, np.uint64(63)), np.uint64(0))
+        head = np.zeros(nc, bool)
+        head[1:] = (cd[1:] != cd[:-1]) | (ppref[1:] != ppref[:-1])
+        head[0] = False
+        H = np.cumsum(head)
+        parent = H - 1  # node rank of the parent (root cell: -1)
+        cell_of_node = np.nonzero(isnode)[0]
+        child_begin = np.zeros(nn, np.int64)
+        child_end = np.zeros(nn, np.int64)
+        hb = np.nonzero(head)[0]
+        child_begin[parent[hb]] = hb
+        last = np.ones(nc, bool)
+        last[:-1] = head[1:]
+        last[0] = False
+        le = np.nonzero(last)[0]
+        child_end[parent[le]] = le + 1
+        self.t = t = dict(cell_depth=cd, cell_start=cs, cell_isleaf=cl.astype(bool), cell_node=np.where(isnode, noderank, -1),
+                          cell_parent=parent, child_begin=child_begin, child_end=child_end, nn=nn,
+                          node_cell=cell_of_node, node_depth=cd[cell_of_node], node_start=cs[cell_of_node])
+        t["node_key"] = key[t["node_start"]] >> (D * (B - t["node_depth"])).astype(np.uint64)
+        self.leaf_depth_ = np.zeros(n, np.int32)
+        lf = np.nonzero(cl == 1)[0]
+        self.leaf_depth_[cs[lf]] = cd[lf]
+        # upward pass, deepest nodes first (node ranks are in level order)
+        pos, m, h = self.c["pos"], self.c["mass"], self.c["h"]
+        mass = np.zeros(nn); com = np.zeros((nn, D)); radius = np.zeros(nn); lap = np.zeros(nn)
+        bmin = np.zeros((nn, D)); bmax = np.zeros((nn, D)); sub = np.zeros(nn, np.int64)
+        for nd in range(nn - 1, -1, -1):
+            ch = range(child_begin[nd], child_end[nd])
+            ents = [cs[c] for c in ch if cl[c] == 1]
+            nods = [noderank[c] for c in ch if cl[c] == 0]
+            X = np.zeros(D); M = 0.0; S = 0
+            mn = np.full(D, np.finfo(np.float64).max); mx = -mn
+            for e in ents:
+                X = X + m[e] * pos[e]; M = M + m[e]; S += 1
+                mn = np.minimum(mn, pos[e] - h[e] / 2.); mx = np.maximum(mx, pos[e] + h[e] / 2.)
+            for c in nods:
+                X = X + mass[c] * com[c]; M = M + mass[c]; S += sub[c]
+                mn = np.minimum(mn, bmin[c]); mx = np.maximum(mx, bmax[c])
+            X = X / M
+            r = 0.0; lp = 0.0
+            for e in ents:
+                dist = self._distance(X, pos[e])
+                r = max(r, dist); lp = max(lp, dist + h[e])
+            for c in nods:
+                dist = self._distance(X, com[c])
+                r = max(r, dist + radius[c]); lp = max(lp, dist + radius[c] + lap[c])
+            mass[nd] = M; com[nd] = X; radius[nd] = r; lap[nd] = lp; bmin[nd] = mn; bmax[nd] = mx; sub[nd] = S
+        t.update(mass=mass, com=com, radius=radius, lap=lap, bmin=bmin, bmax=bmax, sub=sub)
+
+    def _distance(self, a, b):
+        """flecsi::distance, space_vector.h:46-58."""
+        if self.dim == 1:
+            return abs(a[0] - b[0])
+        s = 0.0
+        for d in range(self.dim):
+            s = s + (a[d] - b[d]) * (a[d] - b[d])
+        return math.sqrt(s)
+
+    def tree_nodes(self):
+        t = self.t
+        o = np.argsort(t["node_key"], kind="stable")
+        return dict(key=t["node_key"][o], mass=t["mass"][o], com=t["com"][o], radius=t["radius"][o], lap=t["lap"][o],
+                    bmin=t["bmin"][o], bmax=t["bmax"][o], sub_entities=t["sub"][o])
+
+    def leaf_depth(self):
+        return self.leaf_depth_.copy()
+
+    def update_iteration(self):
+        """body_system::update_iteration, bodies_system.h:152-229 (non-periodic, one rank)."""
+        self.compute_range()
+        self.compute_keys()
+        self.sort_bodies()
+        self.build_tree()
+
+    def reset_ghosts(self):
+        """bodies_system.h:273 -> tree clean + rebuild (tree_topology.h:153-157): same tree."""
+        self.build_tree()
+
+    # ---- neighbour search -------------------------------------------------
+    def work_cells(self):
+        """traversal_sph work-cell collection, tree_topology.h:221-235."""
+        t = self.t
+        out = []
+        stack = [0]
+        while stack:
+            c = stack.pop()
+            if not t["cell_isleaf"][c]:
+                nd = t["cell_node"][c]
+                if t["sub"][nd] > SUB_ENTITIES:
+                    stack.extend(range(t["child_begin"][nd], t["child_end"][nd]))
+                    continue
+            out.append(c)
+        return out
+
+    def _sphere_box(self, mn, mx, c, r):
+        """tree_geometry::intersects_sphere_box: 3-D tree_geometry.h:329-341; 1-D :107-114; 2-D :219-227."""
+        x = np.maximum(mn, np.minimum(c, mx))
+        if self.dim == 3:
+            d2 = (x[:, 0] - c[:, 0]) * (x[:, 0] - c[:, 0]) + (x[:, 1] - c[:, 1]) * (x[:, 1] - c[:, 1]) \
+                + (x[:, 2] - c[:, 2]) * (x[:, 2] - c[:, 2])
+            return d2 <= r * r
+        if self.dim == 2:
+            dist = np.sqrt((x[:, 0] - c[:, 0]) * (x[:, 0] - c[:, 0]) + (x[:, 1] - c[:, 1]) * (x[:, 1] - c[:, 1]))
+        else:
+            dist = np.abs(x[:, 0] - c[:, 0])
+        return dist - r <= TOL
+
+    def _dist2(self, a, b):
+        """tree_geometry::distance2, tree_geometry.h:60,161,265."""
+        s = (a[..., 0] - b[..., 0]) * (a[..., 0] - b[..., 0])
+        for d in range(1, self.dim):
+            s = s + (a[..., d] - b[..., d]) * (a[..., d] - b[..., d])
+        return s
+
+    def find_neighbors(self):
+        """tree_topology::traversal_sph, tree_topology.h:212-442 (one rank): per work cell a
+        breadth-first walk from the root with the three predicates of SURVEY.md A7."""
+        if self.nbr_off is not None:
+            return
+        t = self.t
+        pos, h = self.c["pos"], self.c["h"]
+        lists = [None] * self.n
+        for wc in self.work_cells():
+            if t["cell_isleaf"][wc]:
+                grp = np.array([t["cell_start"][wc]]); gnode = -1
+            else:
+                gnode = t["cell_node"][wc]
+                s = t["node_start"][gnode]
+                grp = np.arange(s, s + t["sub"][gnode])
+            gp, gh = pos[grp], h[grp]
+            cands = []
+            queue = [0]
+            while queue:
+                nq = []
+                for c in queue:
+                    if not t["cell_isleaf"][c]:
+                        nd = t["cell_node"][c]
+                        if gnode >= 0:
+                            # intersects_box_box, tree_geometry.h:306-314
+                            if (t["bmax"][nd] < t["bmin"][gnode]).any() or (t["bmax"][gnode] < t["bmin"][nd]).any():
+                                continue
+                        if self._sphere_box(t["bmin"][nd][None, :], t["bmax"][nd][None, :], gp, gh).any():
+                            nq.extend(range(t["child_begin"][nd], t["child_end"][nd]))
+                    else:
+                        e = t["cell_start"][c]
+                        if gnode >= 0:
+                            ext = max(h[e], t["lap"][gnode]) + t["radius"][gnode]
+                            if not (self._dist2(pos[e], t["com"][gnode]) <= ext * ext):
+                                continue
+                        cands.append(e)
+                queue = nq
+            cands = np.array(cands, dtype=np.int64)
+            cp, chh = pos[cands], h[cands]
+            for k, g in enumerate(grp):
+                r = np.maximum(gh[k], chh)
+                ok = self._dist2(gp[k][None, :], cp) <= r * r
+                lists[g] = np.sort(cands[ok])
+        cnt = np.array([len(l) for l in lists])
+        self.nbr_off = np.concatenate([[0], np.cumsum(cnt)])
+        self.nbr_idx = np.concatenate(lists) if self.n else np.zeros(0, np.int64)
+        self.nbr_a = np.repeat(np.arange(self.n), cnt)
+        self.c["nneigh"] = cnt.astype(np.int32)
+
+    def neighbor_lists(self):
+        self.find_neighbors()
+        ids = self.c["id"][self.nbr_idx]
+        out = np.empty_like(ids)
+        for i in range(self.n):
+            s, e = self.nbr_off[i], self.nbr_off[i + 1]
+            out[s:e] = np.sort(ids[s:e])
+        return self.nbr_off.copy(), out
+
+    # ---- SPH kernels (kernels.h) -------------------------------------------
+    def W(self, r, h):
+        D, k = self.dim, self.par.sph_kernel
+        sg = SIGMA[k][D - 1]
+        if k == 3:  # Wendland C4, kernels.h:375-410
+            q = r / h
+            if D == 1:
+                return np.where(q < 1, sg / h * (1 - q) ** 5 * (1 + q * (5 + q * 8)), 0.0)
+            return np.where(q < 1, sg / h ** D * (1 - q) ** 6 * (1 + q * (6 + q * 35 / 3)), 0.0)
+        if k == 2:  # Wendland C2, kernels.h:282-320
+            q = r / h
+            if D == 1:
+                return np.where(q < 1, sg / h * (1 - q) ** 3 * (1 + 3 * q), 0.0)
+            return np.where(q < 1, sg / h ** D * (1 - q) ** 4 * (1 + 4 * q), 0.0)
+        if k == 4:  # Wendland C6, kernels.h:480-520
+            q = r / h
+            if D == 1:
+                return np.where(q < 1, sg / h * (1 - q) ** 7 * (1 + q * (7 + q * (19 + q * 21))), 0.0)
+            return np.where(q < 1, sg / h ** D * (1 - q) ** 8 * (1 + q * (8 + q * (25 + q * 32))), 0.0)
+        if k == 0:  # cubic spline, kernels.h:106-121
+            q = 2. * r / h
+            w = np.where(q < 1, 1 - 1.5 * q * q + .75 * q * q * q, .25 * (2 - q) ** 3)
+            return np.where(q < 2, w * sg / h ** D, 0.0)
+        if k == 1:  # quintic spline, kernels.h:217-234
+            q = 3. * r / h
+            w = (3 - q) ** 5 + np.where(q < 2, -6 * (2 - q) ** 5, 0.0) + np.where(q < 1, 15 * (1 - q) ** 5, 0.0)
+            return np.where(q < 3, w * sg / h ** D, 0.0)
+        raise NotImplementedError("kernel %d" % k)
+
+    def gradW_over_r(self, r, h):
+        """Scalar factor F such that grad W = r_ab * F (kernels.h gradients)."""
+        D, k = self.dim, self.par.sph_kernel
+        sg = SIGMA[k][D - 1]
+        if k == 3:  # kernels.h:420-463
+            q = r / h
+            if D == 1:
+                dW = -q * (1 - q) ** 4 * (1 + 4 * q)
+            else:
+                dW = -4. / 3. * q * (1 - q) ** 5 * (1 + 5 * q)
+            return np.where(q < 1, 14. * sg / h ** (D + 1) * dW / (r + TINY), 0.0)
+        if k == 2:  # kernels.h:330-365
+            q = r / h
+            if D == 1:
+                return np.where(q < 1, 12. * sg / h ** 2 * (-q * (1 - q) ** 2) / (r + TINY), 0.0)
+            return np.where(q < 1, 20. * sg / h ** (D + 1) * (-q * (1 - q) ** 3) / (r + TINY), 0.0)
+        if k == 4:  # kernels.h:530-566
+            q = r / h
+            if D == 1:
+                dW = -q * (1 - q) ** 6 * (3 + q * (18 + q * 35))
+                return np.where(q < 1, 6. * sg / h ** 2 * dW / (r + TINY), 0.0)
+            dW = -q * (1 - q) ** 7 * (1 + q * (7 + q * 16))
+            return np.where(q < 1, 22. * sg / h ** (D + 1) * dW / (r + TINY), 0.0)
+        if k == 0:  # kernels.h:133-153
+            q = 2. * r / h
+            dW = np.where(q < 1, -3.0 * q + 2.25 * q * q, -.75 * (2 - q) * (2 - q))
+            return np.where(q < 2, 2. * sg / h ** (D + 1) * dW / (r + TINY), 0.0)
+        if k == 1:  # kernels.h:246-268
+            q = 3. * r / h
+            dW = -5. * (3 - q) ** 4 + np.where(q < 2, 30. * (2 - q) ** 4, 0.0) + np.where(q < 1, -75. * (1 - q) ** 4, 0.0)
+            return np.where(q < 3, 3. * sg / h ** (D + 1) * dW / (r + TINY), 0.0)
+        raise NotImplementedError("kernel %d" % k)
+
+    # ---- sweeps (default_physics.h) ------------------------------------------
+    def _pairs(self):
+        self.find_neighbors()
+        a, b = self.nbr_a, self.nbr_idx
+        c = self.c
+        rab = c["pos"][a] - c["pos"][b]
+        r = np.sqrt((rab * rab).sum(1)) if self.dim > 1 else np.abs(rab[:, 0])
+        hab = .5 * (c["h"][a] + c["h"][b])
+        return a, b, rab, r, hab
+
+    def _sum(self, a, w):
+        return np.bincount(a, weights=w, minlength=self.n)
+
+    def _visc(self, a, b, rab, hab):
+        """viscosity::mu, viscosity.h:81-93 and viscosity_function<visc_constant>, :128-137."""
+        c, p = self.c, self.par
+        v12 = c["velhalf"][a] - c["velhalf"][b]
+        dot = (v12 * rab).sum(1)
+        d2 = (rab * rab).sum(1)
+        mu = hab * dot / (d2 + p.sph_viscosity_epsilon * hab * hab + TINY) * (dot < 0.0)
+        rho_ab = .5 * (c["rho"][a] + c["rho"][b])
+        c_ab = .5 * (c["cs"][a] + c["cs"][b])
+        return (-p.sph_viscosity_alpha * c_ab + p.sph_viscosity_beta * mu) * mu / rho_ab
+
+    def _eos(self, idx=slice(None)):
+        """eos_t<eos_ideal>::compute_pressure / compute_soundspeed, eos/eos.h:166-183."""
+        c, g = self.c, self.par.poly_gamma
+        c["P"][idx] = (g - 1.) * c["rho"][idx] * c["u"][idx]
+        c["cs"][idx] = np.sqrt(g * (g - 1.) * c["u"][idx])
+
+    def _recover_u(self):
+        """physics::recover_internal_energy, default_physics.h:126-145 (no external potential)."""
+        c = self.c
+        eint = c["e"] - .5 * (c["vel"] * c["vel"]).sum(1) - 0.0
+        if not (eint > 0).all():
+            raise RuntimeError("internal energy non-positive")
+        c["u"] = eint
+
+    def apply_in_smoothinglength(self, op):
+        c, p = self.c, self.par
+        if op == 4:
+            self.find_neighbors(); return
+        a, b, rab, r, hab = self._pairs()
+        if op == 0:
+            # compute_density_pressure_soundspeed, default_physics.h:309-320
+            rho = self._sum(a, c["mass"][b] * self.W(r, hab))
+            if not (rho > 0).all():
+                raise RuntimeError("density not positive")
+            c["rho"] = rho
+            cs_old = c["cs"].copy()
+            if p.evolve_internal_energy and p.thermokinetic_formulation:
+                self._recover_u()
+            self._eos()
+            # compute_signalspeed, default_physics.h:236-265; particles are processed in descending
+            # key order, so b contributes its new cs iff index b > index a
+            csb = np.where(b > a, c["cs"][b], cs_old[b])
+            cab = np.maximum(c["cs"][a], csb)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                n_ab = rab / r[:, None]
+                vr = ((c["vel"][a] - c["vel"][b]) * n_ab).sum(1)
+                val = cab - np.minimum(vr, 0.0)
+            val = np.where(np.isnan(val), 0.0, val)
+            vs = np.zeros(self.n)
+            np.maximum.at(vs, a, val)
+            c["vsig"] = vs
+            return
+        F = self.gradW_over_r(r, hab)
+        mt = c["mass"][b] * (rab != 0).any(1)
+        Pi = self._visc(a, b, rab, hab)
+        Pa = c["P"] / (c["rho"] * c["rho"])
+        if op == 1:
+            # compute_acceleration, default_physics.h:348-408
+            coef = -mt * (Pa[a] + Pa[b] + Pi) * F
+            acc = np.stack([self._sum(a, coef * rab[:, d]) for d in range(self.dim)], 1)
+            c["acc"] = acc
+            c["gacc"] = np.zeros_like(acc)
+            c["gpot"] = np.zeros(self.n)
+        elif op == 2:
+            # compute_dudt, default_physics.h:421-487
+            if self.iteration < p.relaxation_steps:
+                c["dudt"] = np.zeros(self.n); return
+            vdw = ((c["vel"][a] - c["vel"][b]) * rab).sum(1) * F
+            c["dudt"] = Pa * self._sum(a, mt * vdw) + .5 * self._sum(a, mt * vdw * Pi)
+        elif op == 3:
+            # compute_dedt, default_physics.h:502-566
+            va = (c["vel"][a] * rab).sum(1) * F
+            vb = (c["vel"][b] * rab).sum(1) * F
+            s = self._sum(a, mt * (Pa[a] * vb + va * Pa[b] + .5 * Pi * (vb + va)))
+            c["dedt"] = -s + (c["gacc"] * c["vel"]).sum(1)
+        else:
+            raise ValueError(op)
+
+    # ---- apply_all / get_all ---------------------------------------------------
+    def apply_all(self, op):
+        c, p, dt = self.c, self.par, self.dt_
+        if op == 0:    # eos::init -> compute_adiabatic, eos/eos.h:68-83,157-159
+            c["adiabatic"] = c["P"] / np.power(c["rho"], p.poly_gamma)
+        elif op == 1:  # set_total_energy, default_physics.h:327-335
+            c["e"] = .5 * (c["vel"] * c["vel"]).sum(1) + c["u"] + 0.0
+        elif op == 2:  # save_velocityhalf, integration.h:52
+            c["velhalf"] = c["vel"].copy()
+        elif op == 3:  # leapfrog_kick_v, integration.h:65
+            c["vel"] = c["vel"] + 0.5 * dt * (c["acc"] + c["gacc"])
+        elif op == 4:  # leapfrog_kick_u, integration.h:80
+            c["u"] = c["u"] + 0.5 * dt * c["dudt"]
+        elif op == 5:  # leapfrog_kick_e, integration.h:94
+            c["e"] = c["e"] + 0.5 * dt * c["dedt"]
+        elif op == 6:  # leapfrog_drift, integration.h:106
+            c["pos"] = c["pos"] + dt * c["vel"]
+        elif op == 7:  # recompute_pressure_soundspeed, default_physics.h:153-161
+            u = c["u"].copy()
+            c["u"] = u + 0.5 * dt * c["dudt"]
+            self._eos()
+            c["u"] = u
+        elif op == 8:  # recompute_pressure_soundspeed_thermokinetic, default_physics.h:169-182
+            self._recover_u()
+            u = c["u"].copy()
+            c["u"] = u + 0.5 * dt * (c["dedt"] - (c["vel"] * c["acc"]).sum(1))
+            self._eos()
+            c["u"] = u
+        elif op == 9:  # compute_dt, default_physics.h:602-695
+            tiny, mc = 1e-24, 0.6
+            dx = c["h"] / (p.sph_eta * self.kw)
+            vn = self._mag(c["vel"])
+            dt_v = dx / (vn + tiny)
+            acc = self._mag(c["acc"] + c["gacc"])
+            dt_a = np.sqrt(dx / (acc + tiny))
+            dt_c = dx / (tiny + c["vsig"] * (1 + mc * p.sph_viscosity_alpha))
+            dtmin = p.timestep_cfl_factor * np.minimum(np.minimum(dt_v, dt_a), dt_c)
+            if p.evolve_internal_energy and p.thermokinetic_formulation:
+                if not (c["u"] > 0).all():
+                    raise RuntimeError("internal energy non-positive")
+                vg = (c["vel"] * c["gacc"]).sum(1)
+                done = np.zeros(self.n, bool)
+                for _ in range(20):
+                    done |= (0.0 + (-dtmin * vg)) < c["u"] * 0.5
+                    dtmin = np.where(done, dtmin, dtmin * 0.25)
+                if not done.all():
+                    raise RuntimeError("eint-based dt estimator did not converge")
+            c["dt"] = dtmin
+        elif op == 10:  # check_nans, default_physics.h:918-958
+            for k in VEC + SCAL:
+                if np.isnan(c[k]).any():
+                    raise RuntimeError("NaN in " + k)
+        elif op == 11:  # check_negativity, default_physics.h:962-979
+            if (c["rho"] < 0).any() or (c["P"] < 0).any() or (p.evolve_internal_energy and (c["u"] < 0).any()):
+                raise RuntimeError("negative quantity")
+        else:
+            raise ValueError(op)
+
+    def _mag(self, v):
+        return np.sqrt((v * v).sum(1)) if self.dim > 1 else np.abs(v[:, 0])
+
+    def get_all(self, op, nout=3):
+        c, p = self.c, self.par
+        out = np.zeros(max(nout, 1))
+        if op == 0:    # set_adaptive_timestep, default_physics.h:761-823
+            dtmin = min(1e24, c["dt"].min())
+            dt = self.dt_
+            if dtmin < dt:
+                dt = min(dtmin, dt / 2.0)
+            if dtmin > 2.0 * dt:
+                dt = dt * 2.0
+            self.totaltime_next = self.totaltime + dt
+            for j, odt in enumerate((p.out_screen_dt, p.out_scalar_dt, p.out_h5data_dt)):
+                if odt > 0:
+                    if self.totaltime == self.t_out[j]:
+                        if self.dt_saved > 0:
+                            dt = self.dt_saved
+                        self.t_out[j] += odt
+                    if self.totaltime + dt > self.t_out[j] - 0.1 * odt:
+                        self.dt_saved = dt
+                        self.totaltime_next = self.t_out[j] if j == 0 else min(self.totaltime_next, self.t_out[j])
+            self.dt_ = self.totaltime_next - self.totaltime
+            out[0] = self.dt_
+        elif op in (1, 2):  # compute_smoothinglength, default_physics.h:825-848; average :879-898
+            q = c["mass"] / c["rho"]
+            r = q if self.dim == 1 else (np.sqrt(q) if self.dim == 2 else np.cbrt(q))
+            c["h"] = r * p.sph_eta * self.kw
+            if op == 2:
+                c["h"] = np.full(self.n, 1. / self.n * c["h"].sum())
+        elif op == 3:  # analysis::compute_total_mass, analysis.h:69-80 (NORMAL particles)
+            out[0] = c["mass"][c["type"] == 0].sum()
+        elif op == 4:  # analysis::compute_total_energy, analysis.h:113-150
+            m = c["type"] == 0
+            if p.thermokinetic_formulation:
+                out[0] = (c["mass"] * c["e"])[m].sum()
+            else:
+                out[0] = (c["mass"] * (c["u"] + .5 * (c["vel"] * c["vel"]).sum(1)))[m].sum()
+            if p.enable_fmm:
+                out[0] += .5 * (c["mass"] * c["gpot"])[m].sum()
+        elif op == 5:  # analysis::compute_total_momentum, analysis.h:56-67
+            m = c["type"] == 0
+            out[:self.dim] = (c["mass"][:, None] * c["vel"])[m].sum(0)
+        else:
+            raise ValueError(op)
+        return out
+
+    def get_smoothinglength(self):
+        """body_system::getSmoothinglength, bodies_system.h:112-127."""
+        return float(self.c["h"].max())
+
+    def step(self, initial=False):
+        """One iteration of app/drivers/hydro/main_driver.cc:102-277 (no FMM in the port)."""
+        p = self.par
+        S, A, G = self.apply_in_smoothinglength, self.apply_all, self.get_all
+
+        def energy():
+            for m in range(1, p.pressure_updates_number + 1):
+                if p.thermokinetic_formulation:
+                    S(3); A(8)
+                else:
+                    S(2); A(7)
+                if m < p.pressure_updates_number:
+                    self.reset_ghosts()
+        if initial:
+            self.update_iteration()
+            A(0)
+            if p.thermokinetic_formulation:
+                A(1)
+            S(0); A(2); self.reset_ghosts(); S(1)
+            if p.adaptive_timestep:
+                A(9); G(0)
+            if p.evolve_internal_energy:
+                energy()
+        else:
+            if p.evolve_internal_energy:
+                A(5 if p.thermokinetic_formulation else 4)
+            A(3); A(2); A(6)
+            self.update_iteration()
+            S(0); self.reset_ghosts(); S(1)
+            A(3); self.reset_ghosts()
+            if p.evolve_internal_energy:
+                energy()
+                A(5 if p.thermokinetic_formulation else 4)
+        if p.sph_variable_h:
+            G(1)
+        elif p.sph_update_uniform_h:
+            G(2)
+        A(10); A(11)
+        if p.adaptive_timestep:
+            A(9); G(0)
+        self.advance_time()

@@ -1,0 +1,73 @@
+"""CPU tests: the numpy oracle port against the reference headers compiled behind the C ABI
+(oracle/_ref, built from /root/reference by oracle/Makefile) and the reference's own behavioural pins."""
+import numpy as np
+import pytest
+from flecsph_b200 import capi
+from common import have_ref, make_system, case, assert_tree_equal, assert_neighbors_equal, assert_fields_close
+
+needs_ref = pytest.mark.skipif(not have_ref(3), reason="oracle/_ref not built (needs /root/reference)")
+
+CASES = [("sedov", dict(nx=10)), ("random", dict(n=1500, h_jitter=0.2, seed=3)), ("random", dict(n=700, dim=2, seed=4, h_jitter=0.1)),
+         ("sod", dict(nx=100)), ("random", dict(n=300, dim=1, seed=5))]
+
+
+@needs_ref
+@pytest.mark.parametrize("name,kw", CASES)
+def test_port_tree_and_neighbors_match_reference(name, kw):
+    f, par, dim = case(name, **kw)
+    R, P = make_system("ref", f, par, dim), make_system("port", f, par, dim)
+    R.update_iteration(); P.update_iteration()
+    assert_tree_equal(P, R)
+    R.apply_in_smoothinglength(capi.SWEEP_NEIGHBORS_ONLY); P.apply_in_smoothinglength(capi.SWEEP_NEIGHBORS_ONLY)
+    assert_neighbors_equal(P, R)
+
+
+@needs_ref
+@pytest.mark.parametrize("name,kw", [("sedov", dict(nx=10)), ("noh", dict(nx=9)), ("sod", dict(nx=100)),
+                                     ("random", dict(n=600, dim=2, seed=7)), ("collapse", dict(nx=8))])
+def test_port_steps_match_reference(name, kw):
+    f, par, dim = case(name, **kw)
+    R, P = make_system("ref", f, par, dim), make_system("port", f, par, dim)
+    names = ["pos", "vel", "rho", "P", "u", "cs", "acc", "h", "vsig", "dt"] + (["dedt", "e"] if par.get("thermokinetic_formulation", 1) else ["dudt"])
+    for it in range(3):
+        R.step(initial=(it == 0)); P.step(initial=(it == 0))
+        assert_fields_close(P, R, names, 1e-10)
+        assert abs(P.get_time()[0] - R.get_time()[0]) <= 1e-10 * abs(R.get_time()[0])
+
+
+def test_neighbors_equal_brute_force_uniform_h():
+    """mpisph/test/tree3d.cc:87-108: uniform h => tree search == brute force; self is a neighbour
+    (app/drivers/tree/main_driver.cc:108-113); root mass == sum of masses (tree3d.cc:85)."""
+    f, par, dim = case("random", n=800, seed=11)
+    P = make_system("port", f, par, dim)
+    P.update_iteration()
+    P.apply_in_smoothinglength(capi.SWEEP_NEIGHBORS_ONLY)
+    off, ids = P.neighbor_lists()
+    pos, h, pid = P.get(capi.COL_POS), P.get(capi.COL_H), P.get(capi.COL_ID)
+    for i in range(0, len(pos), 7):
+        d2 = ((pos - pos[i]) ** 2).sum(1)
+        want = np.sort(pid[d2 <= h[i] * h[i]])
+        got = ids[off[i]:off[i + 1]]
+        assert np.array_equal(got, want)
+        assert pid[i] in got
+    t = P.tree_nodes()
+    assert t["key"][0] == 1 and abs(t["mass"][0] - f["mass"].sum()) < 1e-14
+
+
+def test_key_round_trip():
+    """tree_topology/test/filling_curves.cc:202-241: key -> coordinates within 1e-4 of the point."""
+    f, par, dim = case("random", n=64, seed=2)
+    P = make_system("port", f, par, dim)
+    P.compute_range(); P.compute_keys()
+    lo, hi = P.get_range()
+    key = P.get(capi.COL_KEY)
+    B = 21
+    for i in range(len(key)):
+        k = int(key[i])
+        assert k >> 63 == 1
+        c = [0, 0, 0]
+        for b in range(B):
+            for d in range(3):
+                c[d] |= ((k >> (b * 3 + d)) & 1) << b
+        x = lo + (np.array(c) + 0.5) / (1 << B) * (hi - lo)
+        assert np.abs(x - f["pos"][i]).max() < 1e-4
