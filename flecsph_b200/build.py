@@ -1,0 +1,73 @@
+"""Builds libflecsph_b200.so (sm_100a only) in-tree with nvcc; also the test oracles under oracle/."""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "flecsph_b200", "csrc")
+OUT = os.path.join(ROOT, "flecsph_b200", "libflecsph_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+# translation units whose fp64 arithmetic must not be contracted into FMAs (bit-exact keys / tree / predicates)
+SOURCES = {
+    "fsph_sort.cu": [],
+    "fsph_tree.cu": ["-fmad=false"],
+    "fsph_search.cu": ["-fmad=false"],
+    "fsph_apply.cu": ["-fmad=false"],
+    "fsph_sweeps.cu": [],
+    "fsph_capi.cu": [],
+}
+
+
+def _newer(src_list, out):
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    return any(os.path.getmtime(s) > t for s in src_list)
+
+
+def build_cuda(verbose=False, force=False):
+    hdrs = [os.path.join(CSRC, "fsph_internal.h"), os.path.join(ROOT, "include", "flecsph_b200.h"), os.path.abspath(__file__)]
+    objs, jobs = [], []
+    for src, extra in SOURCES.items():
+        s = os.path.join(CSRC, src)
+        o = os.path.join(CSRC, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or _newer([s] + hdrs, o):
+            cmd = [NVCC] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            jobs.append(cmd)
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return cmd, r
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        for cmd, r in ex.map(run, jobs):
+            if verbose or r.returncode:
+                sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+            if r.returncode:
+                raise RuntimeError("nvcc failed for " + cmd[-3])
+    if jobs or not os.path.exists(OUT):
+        cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link failed")
+    return OUT
+
+
+def build_oracle():
+    """oracle/_ref from /root/reference when it is present (dev container); prebuilt files travel to the GPU box."""
+    if os.path.isdir("/root/reference/include"):
+        r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref", "ref_fast"], capture_output=True, text=True)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("oracle/_ref build failed")
+
+
+if __name__ == "__main__":
+    build_cuda(verbose="-v" in sys.argv, force="-f" in sys.argv)
+    if "--oracle" in sys.argv:
+        build_oracle()
+    print(OUT)

@@ -1,0 +1,315 @@
+// fsph_apply.cu -- element-wise passes and scalar reductions (compiled with -fmad=false so that positions and
+// velocities after a kick/drift are the same IEEE results as the reference's scalar code; HBM-bound).
+//
+// Replaces the functors passed to body_system::apply_all / get_all (mpisph/bodies_system.h:318,335):
+//   integration::save_velocityhalf / leapfrog_kick_{v,u,e} / leapfrog_drift   include/physics/integration.h:52-110
+//   eos::init (ideal -> adiabatic K = P / rho^gamma)                          include/physics/eos/eos.h:68-83,157-159
+//   physics::set_total_energy :327-335, recompute_pressure_soundspeed[_thermokinetic] :153-182,
+//   compute_dt :602-695, set_adaptive_timestep :761-823, compute_smoothinglength :825-848,
+//   compute_average_smoothinglength :879-898, check_nans :918-958, check_negativity :962-979
+//                                                                             include/physics/default_physics.h
+//   analysis::compute_total_{mass,energy,momentum}                            include/physics/analysis.h:56-150
+#include <stdexcept>
+#include <cfloat>
+#include <cmath>
+#include "fsph_internal.h"
+
+namespace fsph {
+
+Cols System::cols() const {
+  Cols c;
+  for(int f = 0; f < NF64; ++f) c.f[f] = col[f].as<double>();
+  c.id = col_id.as<int64_t>();
+  c.key = col_key.as<uint64_t>();
+  c.type = col_type.as<int32_t>();
+  c.nneigh = col_nneigh.as<int32_t>();
+  return c;
+}
+
+PhysParams System::phys() const {
+  PhysParams p;
+  p.kernel = par.sph_kernel;
+  p.thermokinetic = par.thermokinetic_formulation;
+  p.evolve_u = par.evolve_internal_energy;
+  p.eta = par.sph_eta;
+  p.gamma = par.poly_gamma;
+  p.alpha = par.sph_viscosity_alpha;
+  p.beta = par.sph_viscosity_beta;
+  p.epsilon = par.sph_viscosity_epsilon;
+  p.cfl = par.timestep_cfl_factor;
+  p.kernel_width = kernel_width;
+  p.dt = dt;
+  p.iteration = iteration;
+  p.relaxation_steps = par.relaxation_steps;
+  return p;
+}
+
+template<int D>
+__global__ void __launch_bounds__(256) k_apply(Cols c, int64_t n, int op, PhysParams pp, uint32_t * __restrict__ status) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const double dt = pp.dt;
+  switch(op) {
+    case FSPH_APPLY_EOS_INIT:
+      c.f[F_ADIA][i] = c.f[F_P][i] / pow(c.f[F_RHO][i], pp.gamma);
+      break;
+    case FSPH_APPLY_SET_TOTAL_ENERGY: {
+      double v2 = 0.0;
+#pragma unroll
+      for(int d = 0; d < D; ++d) v2 = v2 + c.f[F_VEL + d][i] * c.f[F_VEL + d][i];
+      c.f[F_E][i] = .5 * v2 + c.f[F_U][i] + 0.0;
+    } break;
+    case FSPH_APPLY_SAVE_VELOCITYHALF:
+#pragma unroll
+      for(int d = 0; d < D; ++d) c.f[F_VELH + d][i] = c.f[F_VEL + d][i];
+      break;
+    case FSPH_APPLY_LEAPFROG_KICK_V:
+#pragma unroll
+      for(int d = 0; d < D; ++d) c.f[F_VEL + d][i] = c.f[F_VEL + d][i] + (0.5 * dt) * (c.f[F_ACC + d][i] + c.f[F_GACC + d][i]);
+      break;
+    case FSPH_APPLY_LEAPFROG_KICK_U: c.f[F_U][i] = c.f[F_U][i] + 0.5 * dt * c.f[F_DUDT][i]; break;
+    case FSPH_APPLY_LEAPFROG_KICK_E: c.f[F_E][i] = c.f[F_E][i] + 0.5 * dt * c.f[F_DEDT][i]; break;
+    case FSPH_APPLY_LEAPFROG_DRIFT:
+#pragma unroll
+      for(int d = 0; d < D; ++d) c.f[F_POS + d][i] = c.f[F_POS + d][i] + dt * c.f[F_VEL + d][i];
+      break;
+    case FSPH_APPLY_RECOMPUTE_P_CS: {
+      const double u = c.f[F_U][i] + 0.5 * dt * c.f[F_DUDT][i];
+      c.f[F_P][i] = (pp.gamma - 1.) * c.f[F_RHO][i] * u;
+      c.f[F_CS][i] = sqrt(pp.gamma * (pp.gamma - 1.) * u);
+    } break;
+    case FSPH_APPLY_RECOMPUTE_P_CS_THERMOKINETIC: {
+      double v2 = 0.0, va = 0.0;
+#pragma unroll
+      for(int d = 0; d < D; ++d) {
+        v2 = v2 + c.f[F_VEL + d][i] * c.f[F_VEL + d][i];
+        va = va + c.f[F_VEL + d][i] * c.f[F_ACC + d][i];
+      }
+      const double eint = c.f[F_E][i] - .5 * v2 - 0.0;
+      if(!(eint > 0)) atomicOr(status, (uint32_t)ERR_U_NONPOS);
+      c.f[F_U][i] = eint;
+      const double u = eint + 0.5 * dt * (c.f[F_DEDT][i] - va);
+      c.f[F_P][i] = (pp.gamma - 1.) * c.f[F_RHO][i] * u;
+      c.f[F_CS][i] = sqrt(pp.gamma * (pp.gamma - 1.) * u);
+    } break;
+    case FSPH_APPLY_COMPUTE_DT: {
+      const double tiny = 1e-24, mc = 0.6;
+      const double dx = c.f[F_H][i] / (pp.eta * pp.kernel_width);
+      double v2 = 0.0, a2 = 0.0, vg = 0.0;
+#pragma unroll
+      for(int d = 0; d < D; ++d) {
+        const double v = c.f[F_VEL + d][i], a = c.f[F_ACC + d][i] + c.f[F_GACC + d][i];
+        v2 = v2 + v * v;
+        a2 = a2 + a * a;
+        vg = vg + v * c.f[F_GACC + d][i];
+      }
+      const double vn = D == 1 ? fabs(c.f[F_VEL][i]) : sqrt(v2);
+      const double acc = D == 1 ? fabs(c.f[F_ACC][i] + c.f[F_GACC][i]) : sqrt(a2);
+      const double dt_v = dx / (vn + tiny);
+      const double dt_a = sqrt(dx / (acc + tiny));
+      const double dt_c = dx / (tiny + c.f[F_VSIG][i] * (1 + mc * pp.alpha));
+      double dtmin = pp.cfl * fmin(fmin(dt_v, dt_a), dt_c);
+      if(pp.evolve_u && pp.thermokinetic) {
+        const double eint = c.f[F_U][i];
+        if(!(eint > 0)) atomicOr(status, (uint32_t)ERR_U_NONPOS);
+        int it;
+        for(it = 0; it < 20; ++it) {
+          const double delta_epot = 0.0, delta_egrv = -dtmin * vg;
+          if(delta_epot + delta_egrv < eint * 0.5) break;
+          dtmin *= 0.25;
+        }
+        if(it >= 20) atomicOr(status, (uint32_t)ERR_DT_LOOP);
+      }
+      c.f[F_DT][i] = dtmin;
+    } break;
+    case FSPH_APPLY_CHECK_NANS: {
+      bool bad = false;
+#pragma unroll
+      for(int d = 0; d < D; ++d) {
+        bad = bad || isnan(c.f[F_POS + d][i]) || isnan(c.f[F_VEL + d][i]) || isnan(c.f[F_VELH + d][i]) ||
+              isnan(c.f[F_ACC + d][i]) || isnan(c.f[F_GACC + d][i]);
+      }
+      bad = bad || isnan(c.f[F_MASS][i]) || isnan(c.f[F_GPOT][i]) || isnan(c.f[F_RHO][i]) || isnan(c.f[F_P][i]) ||
+            isnan(c.f[F_E][i]) || isnan(c.f[F_DEDT][i]) || isnan(c.f[F_DUDT][i]) || isnan(c.f[F_ADIA][i]) || isnan(c.f[F_VSIG][i]);
+      if(pp.evolve_u) bad = bad || isnan(c.f[F_U][i]);
+      if(bad) atomicOr(status, (uint32_t)ERR_NAN);
+    } break;
+    case FSPH_APPLY_CHECK_NEGATIVITY:
+      if(c.f[F_RHO][i] < 0 || c.f[F_P][i] < 0 || (pp.evolve_u && c.f[F_U][i] < 0)) atomicOr(status, (uint32_t)ERR_NEGATIVE);
+      break;
+    case 100: {  // compute_smoothinglength
+      const double q = c.f[F_MASS][i] / c.f[F_RHO][i];
+      const double r = D == 1 ? q : (D == 2 ? sqrt(q) : cbrt(q));
+      c.f[F_H][i] = r * pp.eta * pp.kernel_width;
+    } break;
+    case 101: c.f[F_H][i] = pp.dt; break;  // uniform h (value carried in pp.dt)
+  }
+}
+
+void apply(System & s, int op) {
+  if(s.n <= 0) return;
+  unsigned nb = (unsigned)((s.n + 255) / 256);
+  uint32_t * st = s.b_status.as<uint32_t>();
+  if(s.dim == 1) k_apply<1><<<nb, 256, 0, s.stream>>>(s.cols(), s.n, op, s.phys(), st);
+  else if(s.dim == 2) k_apply<2><<<nb, 256, 0, s.stream>>>(s.cols(), s.n, op, s.phys(), st);
+  else k_apply<3><<<nb, 256, 0, s.stream>>>(s.cols(), s.n, op, s.phys(), st);
+  FSPH_CUDA_OK(cudaGetLastError());
+  if(op == FSPH_APPLY_LEAPFROG_DRIFT) s.tree_dirty = true;
+}
+
+// ---- reductions: per-block partials in a fixed order, finished on the host (deterministic) ------------------
+enum RedKind { RED_MIN_DT = 0, RED_MAX_H, RED_SUM_H, RED_MASS, RED_ENERGY, RED_MOMENTUM };
+
+template<int D>
+__global__ void __launch_bounds__(256) k_reduce(Cols c, int64_t n, int kind, int thermokinetic, int fmm, double * __restrict__ part) {
+  double v[3] = {0, 0, 0};
+  if(kind == RED_MIN_DT) v[0] = 1e24;
+  if(kind == RED_MAX_H) v[0] = -DBL_MAX;
+  for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    switch(kind) {
+      case RED_MIN_DT: v[0] = fmin(v[0], c.f[F_DT][i]); break;
+      case RED_MAX_H: v[0] = fmax(v[0], c.f[F_H][i]); break;
+      case RED_SUM_H: v[0] += c.f[F_H][i]; break;
+      case RED_MASS:
+        if(c.type[i] == 0) v[0] += c.f[F_MASS][i];
+        break;
+      case RED_ENERGY:
+        if(c.type[i] == 0) {
+          const double m = c.f[F_MASS][i];
+          if(thermokinetic) v[0] += m * c.f[F_E][i];
+          else {
+            double v2 = 0.0;
+#pragma unroll
+            for(int d = 0; d < D; ++d) v2 += c.f[F_VEL + d][i] * c.f[F_VEL + d][i];
+            v[0] += m * (c.f[F_U][i] + .5 * v2);
+          }
+          if(fmm) v[0] += .5 * m * c.f[F_GPOT][i];
+        }
+        break;
+      case RED_MOMENTUM:
+        if(c.type[i] == 0) {
+#pragma unroll
+          for(int d = 0; d < D; ++d) v[d] += c.f[F_MASS][i] * c.f[F_VEL + d][i];
+        }
+        break;
+    }
+  }
+  __shared__ double sm[8][3];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for(int j = 0; j < 3; ++j) {
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) {
+      double u = __shfl_xor_sync(0xffffffffu, v[j], o);
+      v[j] = kind == RED_MIN_DT ? fmin(v[j], u) : (kind == RED_MAX_H ? fmax(v[j], u) : v[j] + u);
+    }
+    if(lane == 0) sm[w][j] = v[j];
+  }
+  __syncthreads();
+  if(threadIdx.x < 3) {
+    double r = sm[0][threadIdx.x];
+    for(int ww = 1; ww < 8; ++ww) {
+      double u = sm[ww][threadIdx.x];
+      r = kind == RED_MIN_DT ? fmin(r, u) : (kind == RED_MAX_H ? fmax(r, u) : r + u);
+    }
+    part[(size_t)blockIdx.x * 3 + threadIdx.x] = r;
+  }
+}
+
+static void run_reduce(System & s, int kind, double out[3]) {
+  int nb = (int)std::min<int64_t>((s.n + 255) / 256, 148 * 4);
+  double * part = reduce_scratch(s, (size_t)nb * 3 + 16);
+  if(s.dim == 1) k_reduce<1><<<nb, 256, 0, s.stream>>>(s.cols(), s.n, kind, s.par.thermokinetic_formulation, s.par.enable_fmm, part);
+  else if(s.dim == 2) k_reduce<2><<<nb, 256, 0, s.stream>>>(s.cols(), s.n, kind, s.par.thermokinetic_formulation, s.par.enable_fmm, part);
+  else k_reduce<3><<<nb, 256, 0, s.stream>>>(s.cols(), s.n, kind, s.par.thermokinetic_formulation, s.par.enable_fmm, part);
+  std::vector<double> h((size_t)nb * 3);
+  FSPH_CUDA_OK(cudaMemcpyAsync(h.data(), part, h.size() * 8, cudaMemcpyDeviceToHost, s.stream));
+  FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
+  for(int j = 0; j < 3; ++j) {
+    double r = h[j];
+    for(int b = 1; b < nb; ++b) {
+      double u = h[(size_t)b * 3 + j];
+      r = kind == RED_MIN_DT ? std::fmin(r, u) : (kind == RED_MAX_H ? std::fmax(r, u) : r + u);
+    }
+    out[j] = r;
+  }
+}
+
+double max_h(System & s) {
+  double o[3];
+  run_reduce(s, RED_MAX_H, o);
+  return o[0];
+}
+
+// physics::set_adaptive_timestep, default_physics.h:761-823 (host part, after the device min)
+static void set_adaptive_timestep(System & s, double dtmin) {
+  double & dt = s.dt;
+  if(dtmin < dt) dt = std::min(dtmin, dt / 2.0);
+  if(dtmin > 2.0 * dt) dt = dt * 2.0;
+  s.totaltime_next = s.totaltime + dt;
+  const double odt[3] = {s.par.out_screen_dt, s.par.out_scalar_dt, s.par.out_h5data_dt};
+  for(int j = 0; j < 3; ++j) {
+    if(odt[j] > 0) {
+      if(s.totaltime == s.t_out[j]) {
+        if(s.dt_saved > 0) dt = s.dt_saved;
+        s.t_out[j] += odt[j];
+      }
+      if(s.totaltime + dt > s.t_out[j] - 0.1 * odt[j]) {
+        s.dt_saved = dt;
+        s.totaltime_next = j == 0 ? s.t_out[j] : std::min(s.totaltime_next, s.t_out[j]);
+      }
+    }
+  }
+  dt = s.totaltime_next - s.totaltime;
+}
+
+void reduce(System & s, int op, double * out, int nout) {
+  double o[3] = {0, 0, 0};
+  switch(op) {
+    case FSPH_GET_SET_ADAPTIVE_TIMESTEP:
+      run_reduce(s, RED_MIN_DT, o);
+      set_adaptive_timestep(s, std::min(1e24, o[0]));
+      if(out && nout > 0) out[0] = s.dt;
+      return;
+    case FSPH_GET_COMPUTE_SMOOTHINGLENGTH:
+      apply(s, 100);
+      s.tree_dirty = true;
+      return;
+    case FSPH_GET_COMPUTE_AVERAGE_SMOOTHINGLENGTH: {
+      apply(s, 100);
+      run_reduce(s, RED_SUM_H, o);
+      const double new_h = 1. / (double)s.n * o[0];
+      const double keep = s.dt;
+      s.dt = new_h;
+      apply(s, 101);
+      s.dt = keep;
+      s.tree_dirty = true;
+      return;
+    }
+    case FSPH_GET_TOTAL_MASS: run_reduce(s, RED_MASS, o); break;
+    case FSPH_GET_TOTAL_ENERGY: run_reduce(s, RED_ENERGY, o); break;
+    case FSPH_GET_TOTAL_MOMENTUM: run_reduce(s, RED_MOMENTUM, o); break;
+    default: throw std::runtime_error("unknown reduce op");
+  }
+  for(int j = 0; j < nout && j < 3; ++j) out[j] = o[j];
+}
+
+void check_status(System & s) {
+  uint32_t st = 0;
+  uint32_t * d = s.b_status.as<uint32_t>();
+  FSPH_CUDA_OK(cudaMemcpyAsync(&st, d, 4, cudaMemcpyDeviceToHost, s.stream));
+  FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
+  if(!st) return;
+  FSPH_CUDA_OK(cudaMemsetAsync(d, 0, 4, s.stream));
+  std::string m = "device guard failed:";
+  if(st & ERR_DUP_KEYS) m += " duplicate keys;";
+  if(st & ERR_RHO_NONPOS) m += " density of a particle is not a positive number (default_physics.h:215);";
+  if(st & ERR_U_NONPOS) m += " internal energy non-positive (default_physics.h:134);";
+  if(st & ERR_NAN) m += " NaN in a particle field (check_nans);";
+  if(st & ERR_NEGATIVE) m += " negative density / pressure / internal energy (check_negativity);";
+  if(st & ERR_QUEUE_OVERFLOW) m += " neighbour-search frontier overflow;";
+  if(st & ERR_DT_LOOP) m += " eint-based dt estimator loop did not converge (default_physics.h:661);";
+  throw std::runtime_error(m);
+}
+
+}  // namespace fsph

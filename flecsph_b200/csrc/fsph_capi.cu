@@ -1,0 +1,555 @@
+// fsph_capi.cu -- the C ABI of include/flecsph_b200.h over the device path.  No CPU fallback: without a CUDA
+// device fsph_create fails.  Each entry point cites the reference interface it replaces in the header.
+#include <cstring>
+#include <stdexcept>
+#include <algorithm>
+#include "fsph_internal.h"
+
+using namespace fsph;
+
+struct fsph_system : public System {};
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+const int VEC_FIELD[5] = {F_POS, F_VEL, F_VELH, F_ACC, F_GACC};
+
+int scalar_field(int col) {
+  switch(col) {
+    case FSPH_COL_MASS: return F_MASS;
+    case FSPH_COL_H: return F_H;
+    case FSPH_COL_RHO: return F_RHO;
+    case FSPH_COL_P: return F_P;
+    case FSPH_COL_U: return F_U;
+    case FSPH_COL_E: return F_E;
+    case FSPH_COL_CS: return F_CS;
+    case FSPH_COL_DUDT: return F_DUDT;
+    case FSPH_COL_DEDT: return F_DEDT;
+    case FSPH_COL_DT: return F_DT;
+    case FSPH_COL_ALPHA: return F_ALPHA;
+    case FSPH_COL_VSIG: return F_VSIG;
+    case FSPH_COL_GPOT: return F_GPOT;
+    case FSPH_COL_ADIABATIC: return F_ADIA;
+    default: return -1;
+  }
+}
+
+struct PhaseScope {
+  System & s;
+  PhaseScope(System & sys, const char * name) : s(sys) {
+    if(!s.timing) return;
+    Phase p;
+    p.name = name;
+    cudaEventCreate(&p.e0);
+    cudaEventCreate(&p.e1);
+    cudaEventRecord(p.e0, s.stream);
+    s.phases.push_back(p);
+  }
+  ~PhaseScope() {
+    if(!s.timing) return;
+    cudaEventRecord(s.phases.back().e1, s.stream);
+  }
+};
+
+void finish_phases(System & s) {
+  if(!s.timing) return;
+  cudaStreamSynchronize(s.stream);
+  s.phase_ms.clear();
+  s.phase_names.clear();
+  // merge phases with the same name (e.g. the two leapfrog kicks)
+  std::vector<std::string> names;
+  for(auto & p : s.phases) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p.e0, p.e1);
+    cudaEventDestroy(p.e0);
+    cudaEventDestroy(p.e1);
+    auto it = std::find(names.begin(), names.end(), p.name);
+    if(it == names.end()) {
+      names.push_back(p.name);
+      s.phase_ms.push_back(ms);
+    }
+    else s.phase_ms[it - names.begin()] += ms;
+  }
+  for(size_t i = 0; i < names.size(); ++i) s.phase_names += (i ? ";" : "") + names[i];
+  s.phases.clear();
+}
+
+void invalidate(System & s) {
+  s.tree_valid = false;
+  s.search_valid = false;
+}
+
+void do_update_iteration(System & s) {
+  // body_system::update_iteration, bodies_system.h:152-229 (non-periodic)
+  if(s.par.periodic_boundary_x || s.par.periodic_boundary_y || s.par.periodic_boundary_z)
+    throw std::runtime_error("periodic boundaries (WALL ghosts, boundary.h) are not implemented on the device yet");
+  {
+    PhaseScope p(s, "range_keys");
+    compute_range(s);
+    compute_keys(s);
+  }
+  {
+    PhaseScope p(s, "sort");
+    sort_bodies(s);
+  }
+  {
+    PhaseScope p(s, "tree");
+    build_tree(s);
+  }
+}
+
+void do_reset_ghosts(System & s) {
+  // bodies_system.h:273 -> tree_topology::reset_ghosts (tree_topology.h:153-157): clean + build_tree with the
+  // current keys.  The tree is a pure function of (keys, positions, h, mass): rebuilt only if those changed.
+  if(!s.tree_valid) throw std::runtime_error("reset_ghosts before update_iteration");
+  if(s.tree_dirty) {
+    PhaseScope p(s, "tree");
+    build_tree(s);
+  }
+}
+
+void do_sweep(System & s, int op) {
+  if(!s.search_valid) {
+    PhaseScope p(s, "search");
+    if(!s.tree_valid) throw std::runtime_error("sweep before update_iteration");
+    neighbor_search(s);
+  }
+  const char * nm = op == FSPH_SWEEP_DENSITY_PRESSURE_SOUNDSPEED ? "density" : op == FSPH_SWEEP_ACCELERATION ? "acceleration"
+                  : op == FSPH_SWEEP_DUDT ? "dudt" : op == FSPH_SWEEP_DEDT ? "dedt" : "neighbors";
+  PhaseScope p(s, nm);
+  sweep(s, op);
+}
+
+void do_step(System & s, int initial) {
+  // app/drivers/hydro/main_driver.cc:102-277 (+ newtonian/main_driver.cc:218-222)
+  const fsph_params & P = s.par;
+  if(P.enable_fmm) throw std::runtime_error("FMM gravity is not implemented on the device yet");
+  auto A = [&](int op) { PhaseScope p(s, "elementwise"); apply(s, op); };
+  auto energy_passes = [&]() {
+    for(int m = 1; m <= P.pressure_updates_number; ++m) {
+      if(P.thermokinetic_formulation) {
+        do_sweep(s, FSPH_SWEEP_DEDT);
+        A(FSPH_APPLY_RECOMPUTE_P_CS_THERMOKINETIC);
+      }
+      else {
+        do_sweep(s, FSPH_SWEEP_DUDT);
+        A(FSPH_APPLY_RECOMPUTE_P_CS);
+      }
+      if(m < P.pressure_updates_number) do_reset_ghosts(s);
+    }
+  };
+  auto timestep = [&]() {
+    if(P.adaptive_timestep) {
+      PhaseScope p(s, "timestep");
+      apply(s, FSPH_APPLY_COMPUTE_DT);
+      reduce(s, FSPH_GET_SET_ADAPTIVE_TIMESTEP, nullptr, 0);
+    }
+  };
+  if(initial) {
+    do_update_iteration(s);
+    A(FSPH_APPLY_EOS_INIT);
+    if(P.thermokinetic_formulation) A(FSPH_APPLY_SET_TOTAL_ENERGY);
+    do_sweep(s, FSPH_SWEEP_DENSITY_PRESSURE_SOUNDSPEED);
+    A(FSPH_APPLY_SAVE_VELOCITYHALF);
+    do_reset_ghosts(s);
+    do_sweep(s, FSPH_SWEEP_ACCELERATION);
+    timestep();
+    if(P.evolve_internal_energy) energy_passes();
+  }
+  else {
+    if(P.evolve_internal_energy) A(P.thermokinetic_formulation ? FSPH_APPLY_LEAPFROG_KICK_E : FSPH_APPLY_LEAPFROG_KICK_U);
+    A(FSPH_APPLY_LEAPFROG_KICK_V);
+    A(FSPH_APPLY_SAVE_VELOCITYHALF);
+    A(FSPH_APPLY_LEAPFROG_DRIFT);
+    do_update_iteration(s);
+    do_sweep(s, FSPH_SWEEP_DENSITY_PRESSURE_SOUNDSPEED);
+    do_reset_ghosts(s);
+    do_sweep(s, FSPH_SWEEP_ACCELERATION);
+    A(FSPH_APPLY_LEAPFROG_KICK_V);
+    do_reset_ghosts(s);
+    if(P.evolve_internal_energy) {
+      energy_passes();
+      A(P.thermokinetic_formulation ? FSPH_APPLY_LEAPFROG_KICK_E : FSPH_APPLY_LEAPFROG_KICK_U);
+    }
+  }
+  {
+    PhaseScope p(s, "elementwise");
+    if(P.sph_variable_h) reduce(s, FSPH_GET_COMPUTE_SMOOTHINGLENGTH, nullptr, 0);
+    else if(P.sph_update_uniform_h) reduce(s, FSPH_GET_COMPUTE_AVERAGE_SMOOTHINGLENGTH, nullptr, 0);
+    apply(s, FSPH_APPLY_CHECK_NANS);
+    apply(s, FSPH_APPLY_CHECK_NEGATIVITY);
+  }
+  timestep();
+  check_status(s);
+  // physics::advance_time, default_physics.h:853-860
+  s.iteration++;
+  if(P.adaptive_timestep) s.totaltime = s.totaltime_next;
+  else s.totaltime = s.totaltime + s.dt;
+}
+
+template<typename F>
+int32_t guarded(fsph_system * s, F && f) {
+  if(!s) return 1;
+  try {
+    FSPH_CUDA_OK(cudaSetDevice(s->device));
+    f();
+    return 0;
+  }
+  catch(const std::exception & e) {
+    s->err = e.what();
+    s->phases.clear();
+    return 1;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+void fsph_default_params(fsph_params * p, int32_t dim) {
+  // defaults of include/params.h
+  std::memset(p, 0, sizeof(*p));
+  p->dim = dim;
+  p->sph_kernel = FSPH_KERNEL_WENDLAND_C4;
+  p->eos_type = FSPH_EOS_IDEAL;
+  p->sph_viscosity = FSPH_VISC_CONSTANT;
+  p->sph_eta = 1.5;
+  p->sph_sinc_index = 4.0;
+  p->poly_gamma = 1.4;
+  p->sph_viscosity_alpha = 1.0;
+  p->sph_viscosity_beta = 2.0;
+  p->sph_viscosity_epsilon = 0.01;
+  p->timestep_cfl_factor = 0.25;
+  p->initial_dt = 0.001;
+  p->gravitational_constant = 1.0;
+  p->box_length = 3.0;
+  p->box_width = 1.0;
+  p->box_height = 1.0;
+  p->evolve_internal_energy = 1;
+  p->thermokinetic_formulation = 1;
+  p->pressure_updates_number = 1;
+}
+
+const char * fsph_backend(void) { return "cuda-sm100a"; }
+
+fsph_system * fsph_create(const fsph_params * p, int32_t device) {
+  if(!p || p->dim < 1 || p->dim > 3) { g_create_error = "bad dimension"; return nullptr; }
+  int ndev = 0;
+  if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device >= ndev) {
+    cudaGetLastError();
+    g_create_error = "no CUDA device: libflecsph_b200 has no CPU path";
+    return nullptr;
+  }
+  if(p->eos_type != FSPH_EOS_IDEAL) { g_create_error = "only the ideal-gas EOS is implemented on the device"; return nullptr; }
+  if(p->sph_viscosity != FSPH_VISC_CONSTANT) { g_create_error = "only constant artificial viscosity is implemented on the device"; return nullptr; }
+  if(p->sph_kernel < 0 || p->sph_kernel > FSPH_KERNEL_WENDLAND_C6) { g_create_error = "sph_kernel not implemented on the device"; return nullptr; }
+  fsph_system * s = nullptr;
+  try {
+    FSPH_CUDA_OK(cudaSetDevice(device));
+    s = new fsph_system;
+    s->par = *p;
+    s->dim = p->dim;
+    s->device = device;
+    s->dt = p->initial_dt;
+    // kernels::select, kernels.h:753-764
+    s->kernel_width = (p->sph_kernel == FSPH_KERNEL_QUINTIC_SPLINE || p->sph_kernel == FSPH_KERNEL_GAUSSIAN ||
+                       p->sph_kernel == FSPH_KERNEL_SUPER_GAUSSIAN) ? 3.0 : 2.0;
+    FSPH_CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    s->b_status.reserve(64);
+    FSPH_CUDA_OK(cudaMemsetAsync(s->b_status.p, 0, 64, s->stream));
+    FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
+    return s;
+  }
+  catch(const std::exception & e) {
+    g_create_error = e.what();
+    delete s;
+    return nullptr;
+  }
+}
+
+void fsph_destroy(fsph_system * s) {
+  if(!s) return;
+  cudaSetDevice(s->device);
+  cudaStreamSynchronize(s->stream);
+  DevBuf * all[] = {&s->col_id, &s->col_key, &s->col_type, &s->col_nneigh, &s->scratch_col, &s->b_perm, &s->b_keys2, &s->b_perm2,
+    &s->b_cell, &s->b_cell_parent, &s->b_cell_desc, &s->b_cell_desc2, &s->b_child_begin, &s->b_child_end, &s->b_node_start,
+    &s->b_node_depth, &s->b_sub, &s->b_nmass, &s->b_nradius, &s->b_nlap, &s->b_wc_cell, &s->b_cand_off, &s->b_mask_off, &s->b_cand,
+    &s->b_mask, &s->b_cnt0, &s->b_cnt1, &s->b_status, &s->b_red, &s->b_levels};
+  for(DevBuf * b : all) b->release();
+  for(int f = 0; f < NF64; ++f) s->col[f].release();
+  for(int i = 0; i < 6; ++i) s->b_tmp[i].release();
+  for(int d = 0; d < 3; ++d) { s->b_ncom[d].release(); s->b_nbmin[d].release(); s->b_nbmax[d].release(); }
+  if(s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+const char * fsph_last_error(const fsph_system * s) { return s ? s->err.c_str() : g_create_error.c_str(); }
+
+__global__ void k_iota64(int64_t * p, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n) p[i] = i;
+}
+
+int32_t fsph_resize(fsph_system * s, int64_t n) {
+  return guarded(s, [&]() {
+    if(n < 0 || n >= (int64_t(1) << 31)) throw std::runtime_error("bad body count");
+    const size_t b8 = (size_t)std::max<int64_t>(n, 1) * 8, b4 = (size_t)std::max<int64_t>(n, 1) * 4;
+    for(int f = 0; f < NF64; ++f) {
+      s->col[f].reserve(b8);
+      FSPH_CUDA_OK(cudaMemsetAsync(s->col[f].p, 0, b8, s->stream));
+    }
+    s->col_id.reserve(b8); s->col_key.reserve(b8); s->scratch_col.reserve(b8);
+    s->col_type.reserve(b4); s->col_nneigh.reserve(b4);
+    FSPH_CUDA_OK(cudaMemsetAsync(s->col_key.p, 0, b8, s->stream));
+    FSPH_CUDA_OK(cudaMemsetAsync(s->col_type.p, 0, b4, s->stream));
+    FSPH_CUDA_OK(cudaMemsetAsync(s->col_nneigh.p, 0, b4, s->stream));
+    if(n > 0) k_iota64<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->col_id.as<int64_t>(), n);
+    s->n = n;
+    invalidate(*s);
+    FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
+  });
+}
+
+int64_t fsph_nbodies(const fsph_system * s) { return s ? s->n : 0; }
+
+int32_t fsph_set_column(fsph_system * s, int32_t col, const void * host) {
+  return guarded(s, [&]() {
+    const int64_t n = s->n;
+    const int D = s->dim;
+    if(col >= FSPH_COL_POS && col <= FSPH_COL_GACC) {
+      const double * h = static_cast<const double *>(host);
+      std::vector<double> tmp((size_t)n);
+      for(int d = 0; d < D; ++d) {
+        for(int64_t i = 0; i < n; ++i) tmp[i] = h[i * D + d];
+        FSPH_CUDA_OK(cudaMemcpyAsync(s->col[VEC_FIELD[col] + d].p, tmp.data(), (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+        FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
+      }
+      if(col == FSPH_COL_POS) s->tree_dirty = true;
+    }
+    else if(scalar_field(col) >= 0) {
+      FSPH_CUDA_OK(cudaMemcpyAsync(s->col[scalar_field(col)].p, host, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+      if(col == FSPH_COL_H || col == FSPH_COL_MASS) s->tree_dirty = true;
+    }
+    else if(col == FSPH_COL_ID) FSPH_CUDA_OK(cudaMemcpyAsync(s->col_id.p, host, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+    else if(col == FSPH_COL_TYPE) FSPH_CUDA_OK(cudaMemcpyAsync(s->col_type.p, host, (size_t)n * 4, cudaMemcpyHostToDevice, s->stream));
+    else throw std::runtime_error("column not writable");
+    FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
+  });
+}
+
+int32_t fsph_get_column(fsph_system * s, int32_t col, void * host) {
+  return guarded(s, [&]() {
+    const int64_t n = s->n;
+    const int D = s->dim;
+    if(col >= FSPH_COL_POS && col <= FSPH_COL_GACC) {
+      double * h = static_cast<double *>(host);
+      std::vector<double> tmp((size_t)n);
+      for(int d = 0; d < D; ++d) {
+        FSPH_CUDA_OK(cudaMemcpyAsync(tmp.data(), s->col[VEC_FIELD[col] + d].p, (size_t)n * 8, cudaMemcpyDeviceToHost, s->stream));
+        FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
+        for(int64_t i = 0; i < n; ++i) h[i * D + d] = tmp[i];
+      }
+      return;
+    }
+    const void * src = nullptr;
+    size_t bytes = (size_t)n * 8;
+    if(scalar_field(col) >= 0) src = s->col[scalar_field(col)].p;
+    else if(col == FSPH_COL_ID) src = s->col_id.p;
+    else if(col == FSPH_COL_KEY) src = s->col_key.p;
+    else if(col == FSPH_COL_TYPE) { src = s->col_type.p; bytes = (size_t)n * 4; }
+    else if(col == FSPH_COL_NNEIGH) { src = s->col_nneigh.p; bytes = (size_t)n * 4; }
+    else throw std::runtime_error("bad column");
+    FSPH_CUDA_OK(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, s->stream));
+    FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
+  });
+}
+
+// AoS marshalling of the reference's `body` records (include/physics/body.h:221-251): offsets[col] = offsetof(body, field).
+int32_t fsph_upload_aos(fsph_system * s, const void * bodies, int64_t n, int64_t stride, const int64_t * offsets) {
+  int32_t rc = fsph_resize(s, n);
+  if(rc) return rc;
+  return guarded(s, [&]() {
+    const char * base = static_cast<const char *>(bodies);
+    const int D = s->dim;
+    std::vector<double> tmp((size_t)n);
+    auto up = [&](void * dst, int64_t off, size_t esz) {
+      if(esz == 8) {
+        for(int64_t i = 0; i < n; ++i) std::memcpy(&tmp[i], base + i * stride + off, 8);
+        FSPH_CUDA_OK(cudaMemcpyAsync(dst, tmp.data(), (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+      }
+      else {
+        int32_t * t4 = reinterpret_cast<int32_t *>(tmp.data());
+        for(int64_t i = 0; i < n; ++i) std::memcpy(&t4[i], base + i * stride + off, 4);
+        FSPH_CUDA_OK(cudaMemcpyAsync(dst, t4, (size_t)n * 4, cudaMemcpyHostToDevice, s->stream));
+      }
+      FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
+    };
+    for(int col = 0; col < FSPH_COL_COUNT_; ++col) {
+      if(offsets[col] < 0) continue;
+      if(col <= FSPH_COL_GACC) for(int d = 0; d < D; ++d) up(s->col[VEC_FIELD[col] + d].p, offsets[col] + 8 * d, 8);
+      else if(scalar_field(col) >= 0) up(s->col[scalar_field(col)].p, offsets[col], 8);
+      else if(col == FSPH_COL_ID) up(s->col_id.p, offsets[col], 8);
+      else if(col == FSPH_COL_TYPE) up(s->col_type.p, offsets[col], 4);
+    }
+    invalidate(*s);
+  });
+}
+
+int32_t fsph_download_aos(fsph_system * s, void * bodies, int64_t stride, const int64_t * offsets) {
+  return guarded(s, [&]() {
+    char * base = static_cast<char *>(bodies);
+    const int D = s->dim;
+    const int64_t n = s->n;
+    std::vector<double> tmp((size_t)n);
+    auto down = [&](const void * src, int64_t off, size_t esz) {
+      FSPH_CUDA_OK(cudaMemcpyAsync(tmp.data(), src, (size_t)n * esz, cudaMemcpyDeviceToHost, s->stream));
+      FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
+      const char * t = reinterpret_cast<const char *>(tmp.data());
+      for(int64_t i = 0; i < n; ++i) std::memcpy(base + i * stride + off, t + i * esz, esz);
+    };
+    for(int col = 0; col < FSPH_COL_COUNT_; ++col) {
+      if(offsets[col] < 0) continue;
+      if(col <= FSPH_COL_GACC) for(int d = 0; d < D; ++d) down(s->col[VEC_FIELD[col] + d].p, offsets[col] + 8 * d, 8);
+      else if(scalar_field(col) >= 0) down(s->col[scalar_field(col)].p, offsets[col], 8);
+      else if(col == FSPH_COL_ID) down(s->col_id.p, offsets[col], 8);
+      else if(col == FSPH_COL_KEY) down(s->col_key.p, offsets[col], 8);
+      else if(col == FSPH_COL_TYPE) down(s->col_type.p, offsets[col], 4);
+      else if(col == FSPH_COL_NNEIGH) down(s->col_nneigh.p, offsets[col], 4);
+    }
+  });
+}
+
+int32_t fsph_set_time(fsph_system * s, double dt, double totaltime, int64_t iteration) {
+  if(!s) return 1;
+  s->dt = dt;
+  s->totaltime = totaltime;
+  s->iteration = iteration;
+  return 0;
+}
+int32_t fsph_get_time(const fsph_system * s, double * dt, double * totaltime, int64_t * iteration) {
+  if(!s) return 1;
+  if(dt) *dt = s->dt;
+  if(totaltime) *totaltime = s->totaltime;
+  if(iteration) *iteration = s->iteration;
+  return 0;
+}
+int32_t fsph_advance_time(fsph_system * s) {
+  if(!s) return 1;
+  s->iteration++;
+  if(s->par.adaptive_timestep) s->totaltime = s->totaltime_next;
+  else s->totaltime = s->totaltime + s->dt;
+  return 0;
+}
+
+int32_t fsph_update_iteration(fsph_system * s) {
+  return guarded(s, [&]() { do_update_iteration(*s); check_status(*s); });
+}
+int32_t fsph_reset_ghosts(fsph_system * s) {
+  return guarded(s, [&]() { do_reset_ghosts(*s); });
+}
+int32_t fsph_sweep(fsph_system * s, int32_t op) {
+  return guarded(s, [&]() { do_sweep(*s, op); check_status(*s); });
+}
+int32_t fsph_apply(fsph_system * s, int32_t op) {
+  return guarded(s, [&]() {
+    if(op < 0 || op > FSPH_APPLY_CHECK_NEGATIVITY) throw std::runtime_error("unknown apply op");
+    apply(*s, op);
+    check_status(*s);
+  });
+}
+int32_t fsph_reduce(fsph_system * s, int32_t op, double * out, int32_t nout) {
+  return guarded(s, [&]() { reduce(*s, op, out, nout); });
+}
+int32_t fsph_gravitation_fmm(fsph_system * s) {
+  return guarded(s, [&]() { throw std::runtime_error("FMM gravity is not implemented on the device yet"); });
+}
+int32_t fsph_get_range(fsph_system * s, double * lo, double * hi) {
+  if(!s) return 1;
+  for(int d = 0; d < s->dim; ++d) { lo[d] = s->lo[d]; hi[d] = s->hi[d]; }
+  return 0;
+}
+double fsph_get_smoothinglength(fsph_system * s) {
+  double r = 0;
+  guarded(s, [&]() { r = max_h(*s); });
+  return r;
+}
+
+int32_t fsph_step(fsph_system * s, int32_t initial) {
+  return guarded(s, [&]() {
+    s->timing = true;
+    s->phases.clear();
+    do_step(*s, initial);
+    finish_phases(*s);
+    s->timing = false;
+  });
+}
+
+int64_t fsph_tree_num_nodes(fsph_system * s) { return s && s->tree_valid ? s->tree.nnodes : 0; }
+
+int32_t fsph_tree_get_nodes(fsph_system * s, uint64_t * key, double * mass, double * com, double * radius, double * lap,
+  double * bmin, double * bmax, int64_t * sub_entities) {
+  return guarded(s, [&]() {
+    if(!s->tree_valid) throw std::runtime_error("no tree");
+    const int nn = s->tree.nnodes, D = s->dim, B = 63 / D;
+    const int64_t n = s->n;
+    std::vector<uint64_t> pkey((size_t)n);
+    std::vector<int32_t> ns(nn), ndp(nn), sb(nn);
+    std::vector<double> tmp(nn);
+    auto get = [&](void * dst, const void * src, size_t bytes) {
+      FSPH_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s->stream));
+      FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
+    };
+    get(pkey.data(), s->col_key.p, (size_t)n * 8);
+    get(ns.data(), s->tree.node_start, (size_t)nn * 4);
+    get(ndp.data(), s->tree.node_depth, (size_t)nn * 4);
+    get(sb.data(), s->tree.sub, (size_t)nn * 4);
+    get(mass, s->tree.mass, (size_t)nn * 8);
+    get(radius, s->tree.radius, (size_t)nn * 8);
+    get(lap, s->tree.lap, (size_t)nn * 8);
+    for(int i = 0; i < nn; ++i) {
+      key[i] = pkey[ns[i]] >> (D * (B - ndp[i]));
+      sub_entities[i] = sb[i];
+    }
+    for(int d = 0; d < D; ++d) {
+      get(tmp.data(), s->tree.com[d], (size_t)nn * 8);
+      for(int i = 0; i < nn; ++i) com[(size_t)i * D + d] = tmp[i];
+      get(tmp.data(), s->tree.bmin[d], (size_t)nn * 8);
+      for(int i = 0; i < nn; ++i) bmin[(size_t)i * D + d] = tmp[i];
+      get(tmp.data(), s->tree.bmax[d], (size_t)nn * 8);
+      for(int i = 0; i < nn; ++i) bmax[(size_t)i * D + d] = tmp[i];
+    }
+  });
+}
+
+int32_t fsph_tree_get_leaf_depth(fsph_system * s, int32_t * depth) {
+  return guarded(s, [&]() {
+    if(!s->tree_valid) throw std::runtime_error("no tree");
+    const int nc = s->tree.ncells;
+    std::vector<uint64_t> desc(nc);
+    FSPH_CUDA_OK(cudaMemcpyAsync(desc.data(), s->tree.cell_desc, (size_t)nc * 8, cudaMemcpyDeviceToHost, s->stream));
+    FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
+    for(int c = 0; c < nc; ++c)
+      if(desc[c] & 1ull) depth[(uint32_t)desc[c] >> 1] = (int32_t)(desc[c] >> 32);
+  });
+}
+
+int32_t fsph_neighbor_lists(fsph_system * s, int64_t * offsets, int64_t * ids) {
+  return guarded(s, [&]() {
+    if(!s->search_valid) throw std::runtime_error("no neighbour search done yet");
+    std::vector<int64_t> off, idv;
+    export_neighbors(*s, off, ids ? &idv : nullptr);
+    std::copy(off.begin(), off.end(), offsets);
+    if(ids) std::copy(idv.begin(), idv.end(), ids);
+  });
+}
+
+int32_t fsph_phase_times(fsph_system * s, double * ms, int32_t cap, const char ** names) {
+  if(!s) return 0;
+  int k = (int)std::min<size_t>(s->phase_ms.size(), (size_t)cap);
+  for(int i = 0; i < k; ++i) ms[i] = s->phase_ms[i];
+  if(names) *names = s->phase_names.c_str();
+  return k;
+}
+
+}  // extern "C"

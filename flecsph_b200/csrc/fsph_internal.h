@@ -1,0 +1,167 @@
+// fsph_internal.h -- internal declarations of libflecsph_b200.so (sm_100a CUDA, no CPU path).
+//
+// Device state of one `fsph_system` (= one body_system<double,D> of the reference,
+// mpisph/bodies_system.h:38-379): fp64 / int SoA columns in HBM, the level-ordered octree
+// tables, the work-cell list and the per-work-cell neighbour structure (candidate list +
+// bitmask).  DESIGN.md describes the layout and each kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "flecsph_b200.h"
+
+namespace fsph {
+
+// ---- fp64 columns -----------------------------------------------------------------------------
+enum F64 {
+  F_POS = 0, F_VEL = 3, F_VELH = 6, F_ACC = 9, F_GACC = 12,
+  F_MASS = 15, F_H, F_RHO, F_P, F_U, F_E, F_CS, F_DUDT, F_DEDT, F_DT, F_ALPHA, F_VSIG, F_GPOT, F_ADIA,
+  F_CSOLD,  // soundspeed before the current density sweep (signal-speed order dependence)
+  NF64
+};
+
+constexpr int SUB_ENTITIES = 128;  // tree_topology.h:2121
+constexpr int MAX_LEVELS = 66;
+
+// error bits latched on the device (surfaced at the next call boundary)
+enum ErrBits {
+  ERR_DUP_KEYS = 1, ERR_RHO_NONPOS = 2, ERR_U_NONPOS = 4, ERR_NAN = 8, ERR_NEGATIVE = 16, ERR_QUEUE_OVERFLOW = 32,
+  ERR_DT_LOOP = 64, ERR_RANGE = 128
+};
+
+struct DevBuf {
+  void * p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes);  // grows (contents NOT preserved)
+  void release();
+  template<typename T> T * as() const { return static_cast<T *>(p); }
+};
+
+// pointers handed to kernels by value
+struct Cols {
+  double * f[NF64];
+  int64_t * id;
+  uint64_t * key;
+  int32_t * type;
+  int32_t * nneigh;
+};
+
+struct Tree {
+  // cells in level order (depth, then key): value >= 0 -> particle index (leaf), < 0 -> ~node index
+  int32_t * cell;
+  int32_t * cell_parent;  // node index of the parent (-1 for the root cell)
+  uint64_t * cell_desc;   // depth << 32 | start << 1 | is_leaf
+  // nodes in level order
+  int32_t * child_begin;
+  int32_t * child_end;
+  int32_t * node_start;
+  int32_t * node_depth;
+  int32_t * sub;
+  double * mass;
+  double * com[3];
+  double * radius;
+  double * lap;
+  double * bmin[3];
+  double * bmax[3];
+  int32_t ncells, nnodes;
+};
+
+struct Search {
+  int32_t * wc_cell;     // work cells in Morton order: index into Tree::cell
+  uint64_t * cand_off;   // [nwc+1] offsets into cand
+  uint64_t * mask_off;   // [nwc+1] offsets into mask (32-bit words)
+  int32_t * cand;        // candidate particle indices
+  uint32_t * mask;       // per work cell: [ceil(C/32)][Ppad] words, bit b of word (w,k): candidate 32w+b is a neighbour of particle k
+  int32_t nwc;
+};
+
+struct PhysParams {
+  int kernel, thermokinetic, evolve_u;
+  double eta, gamma, alpha, beta, epsilon, cfl, kernel_width;
+  double dt;
+  int64_t iteration;
+  int relaxation_steps;
+};
+
+struct Phase {
+  std::string name;
+  cudaEvent_t e0, e1;
+};
+
+struct System {
+  fsph_params par;
+  int dim = 3, device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t n = 0;
+  // time globals (default_physics.h:31-40)
+  double dt = 0, dt_saved = 0, totaltime = 0, totaltime_next = 0, t_out[3] = {0, 0, 0};
+  int64_t iteration = 0;
+  double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  bool tree_valid = false, search_valid = false, tree_dirty = false;
+
+  // storage
+  DevBuf col[NF64], col_id, col_key, col_type, col_nneigh, scratch_col;
+  DevBuf b_perm, b_keys2, b_perm2, b_tmp[6];
+  DevBuf b_cell, b_cell_parent, b_cell_desc, b_cell_desc2, b_child_begin, b_child_end, b_node_start, b_node_depth, b_sub;
+  DevBuf b_nmass, b_ncom[3], b_nradius, b_nlap, b_nbmin[3], b_nbmax[3];
+  DevBuf b_wc_cell, b_cand_off, b_mask_off, b_cand, b_mask, b_cnt0, b_cnt1;
+  DevBuf b_status, b_red, b_levels;
+  void * h_pinned = nullptr;  // small pinned staging (4 KB)
+  Tree tree;
+  Search search;
+  int level_node_begin[MAX_LEVELS + 1];
+  int nlevels = 0;
+  double kernel_width = 2.0;
+  uint32_t host_err = 0;
+
+  // phase timing of the last fsph_step
+  std::vector<Phase> phases;
+  std::vector<double> phase_ms;
+  std::string phase_names;
+  bool timing = false;
+
+  Cols cols() const;
+  PhysParams phys() const;
+};
+
+#define FSPH_CUDA_OK(call)                                                                       \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if(e_ != cudaSuccess) {                                                                      \
+      throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_));              \
+    }                                                                                            \
+  } while(0)
+
+// ---- fsph_sort.cu ---------------------------------------------------------------------------
+// One stable LSD pass on an 8-bit digit at `shift`; vals may be null (keys only).
+void radix_pass(System & s, const uint64_t * kin, const uint32_t * vin, uint64_t * kout, uint32_t * vout, int64_t n, int shift);
+// Full 64-bit sort of (key, index) pairs; result in kout/vout (may swap internally): returns pointers to the sorted arrays.
+void radix_sort_pairs(System & s, uint64_t *& k0, uint32_t *& v0, uint64_t *& k1, uint32_t *& v1, int64_t n);
+void exclusive_scan_u32(System & s, const uint32_t * in, uint32_t * out, int64_t n, uint32_t * total_dev);  // out[n] not written
+void exclusive_scan_u64(System & s, const uint64_t * in, uint64_t * out, int64_t n, uint64_t * total_dev);
+
+// ---- fsph_tree.cu ---------------------------------------------------------------------------
+void compute_range(System & s);                 // bodies_system.h:231-268
+void compute_keys(System & s);                  // filling_curve.h:503-525
+void sort_bodies(System & s);                   // psort.h:227-322 (one rank): radix sort + column gather
+void build_tree(System & s);                    // tree_topology.h:878-997 + default_physics.h:59-119
+void find_work_cells(System & s);               // tree_topology.h:221-235
+
+// ---- fsph_search.cu -------------------------------------------------------------------------
+void neighbor_search(System & s);               // tree_topology.h:212-442
+void export_neighbors(System & s, std::vector<int64_t> & off, std::vector<int64_t> * ids);
+
+// ---- fsph_sweeps.cu -------------------------------------------------------------------------
+void sweep(System & s, int op);                 // default_physics.h:193-566
+
+// ---- fsph_apply.cu --------------------------------------------------------------------------
+void apply(System & s, int op);                 // integration.h, default_physics.h element-wise
+void reduce(System & s, int op, double * out, int nout);
+double max_h(System & s);
+void check_status(System & s);                  // throws on latched device errors
+
+double * reduce_scratch(System & s, size_t n);
+
+}  // namespace fsph

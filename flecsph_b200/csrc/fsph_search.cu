@@ -1,0 +1,412 @@
+// fsph_search.cu -- smoothing-length neighbour search (compiled with -fmad=false: bit-exact predicates).
+//
+// Replaces tree_topology::traversal_sph (include/tree_topology/tree_topology.h:212-442) with the predicates
+// of tree_geometry (include/tree_topology/tree_geometry.h: within_distance2 :60,161,265; intersects_box_box
+// :118,198,306; intersects_sphere_box :107,219,329).  One CTA per work cell G (<= 128 particles, the
+// reference's own partition, so that its non-conservative culls for unequal h are reproduced exactly):
+//   1. breadth-first walk from the root; a node survives iff its box overlaps G's box and some particle
+//      sphere of G touches it; the leaf children of surviving nodes that pass the |x_e - X_G| prefilter
+//      become G's candidates (written to HBM in walk order: runs of consecutive Morton indices);
+//   2. candidates are staged in shared memory in tiles of 512 (coordinates + h^2) and every particle of G
+//      tests them with the exact fp64 pair predicate (dx^2+dy^2)+dz^2 <= max(h_a,h_b)^2; the outcome is
+//      one bit per (particle, candidate) written as 32-bit words [word][particle] -- the neighbour
+//      structure all sweeps of the step reuse (positions and h do not change between them).
+// Pass 1 runs twice (count, then fill) so that the candidate and mask arrays are sized exactly and laid out
+// deterministically by a prefix sum; it is a few per cent of the pair-test cost.
+#include <stdexcept>
+#include <algorithm>
+#include "fsph_internal.h"
+
+namespace fsph {
+
+constexpr int SR_NT = 64;       // threads per CTA; each thread owns particles tid and tid + 64 of the work cell
+constexpr int SR_QCAP = 1024;   // node frontier capacity per level
+constexpr int SR_TILE = 512;    // candidates per shared-memory tile
+constexpr double GEO_TOL = 2.220446049250313e-16 * 10.;  // tree_geometry.h:57
+
+template<int D>
+__device__ __forceinline__ bool sphere_box(const double * mn, const double * mx, const double * c, double r) {
+  if(D == 3) {
+    // tree_geometry.h:329-341
+    double s = 0.0;
+#pragma unroll
+    for(int d = 0; d < D; ++d) {
+      double x = c[d] < mx[d] ? c[d] : mx[d];
+      x = x < mn[d] ? mn[d] : x;
+      double t = (x - c[d]) * (x - c[d]);
+      s = d == 0 ? t : s + t;
+    }
+    return s <= r * r;
+  }
+  else if(D == 2) {
+    // tree_geometry.h:219-227
+    double s = 0.0;
+#pragma unroll
+    for(int d = 0; d < D; ++d) {
+      double x = fmax(mn[d], fmin(c[d], mx[d]));
+      s = s + (x - c[d]) * (x - c[d]);
+    }
+    return sqrt(s) - r <= GEO_TOL;
+  }
+  else {
+    // tree_geometry.h:107-114
+    double x = fmax(mn[0], fmin(c[0], mx[0]));
+    return fabs(x - c[0]) - r <= GEO_TOL;
+  }
+}
+
+template<int NT>
+__device__ __forceinline__ uint32_t block_scan_u32(uint32_t v, uint32_t & total, uint32_t * sm) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for(int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if(lane >= o) x += y;
+  }
+  if(lane == 31) sm[w] = x;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for(int i = 0; i < NT / 32; ++i) {
+    if(i < w) base += sm[i];
+    tot += sm[i];
+  }
+  total = tot;
+  __syncthreads();
+  return base + x - v;
+}
+
+struct WorkCell {
+  int start, P, gnode;
+};
+
+__device__ __forceinline__ WorkCell load_work_cell(const Tree & t, const Search & sr, int g) {
+  WorkCell w;
+  int v = t.cell[sr.wc_cell[g]];
+  if(v >= 0) { w.start = v; w.P = 1; w.gnode = -1; }
+  else { w.gnode = ~v; w.start = t.node_start[w.gnode]; w.P = t.sub[w.gnode]; }
+  return w;
+}
+
+template<int D, bool FILL>
+__global__ void __launch_bounds__(SR_NT) k_search(Tree t, Cols c, Search sr, uint64_t * __restrict__ ncand,
+  uint64_t * __restrict__ nwords, uint32_t * __restrict__ status) {
+  __shared__ double gx[D][SUB_ENTITIES];
+  __shared__ double gh[SUB_ENTITIES];
+  __shared__ int32_t queue[2][SR_QCAP];
+  __shared__ uint32_t scan_sm[SR_NT / 32];
+  __shared__ double red_sm[SR_NT / 32][2 * D + 1];
+  __shared__ double cx[FILL ? D : 1][FILL ? SR_TILE : 1];
+  __shared__ double ch2[FILL ? SR_TILE : 1];
+
+  const int g = blockIdx.x, tid = threadIdx.x;
+  const WorkCell wc = load_work_cell(t, sr, g);
+  const int P = wc.P, gnode = wc.gnode;
+  for(int k = tid; k < P; k += SR_NT) {
+#pragma unroll
+    for(int d = 0; d < D; ++d) gx[d][k] = c.f[F_POS + d][wc.start + k];
+    gh[k] = c.f[F_H][wc.start + k];
+  }
+  double gmn[D], gmx[D], gcom[D], glap = 0.0, grad = 0.0;
+  if(gnode >= 0) {
+#pragma unroll
+    for(int d = 0; d < D; ++d) { gmn[d] = t.bmin[d][gnode]; gmx[d] = t.bmax[d][gnode]; gcom[d] = t.com[d][gnode]; }
+    glap = t.lap[gnode];
+    grad = t.radius[gnode];
+  }
+  const uint64_t cbase = FILL ? sr.cand_off[g] : 0;
+  if(tid == 0) queue[0][0] = 0;  // the root node
+  __syncthreads();
+  // Tight box of G's positions and max h: an extra, conservative candidate cull (it only drops leaves that
+  // cannot satisfy the pair predicate for any particle of G, so the neighbour sets are unchanged).
+  double tmn[D], tmx[D], ghmax = 0.0;
+  {
+#pragma unroll
+    for(int d = 0; d < D; ++d) { tmn[d] = 1.79769313486231570e308; tmx[d] = -1.79769313486231570e308; }
+    for(int k = tid; k < P; k += SR_NT) {
+#pragma unroll
+      for(int d = 0; d < D; ++d) { tmn[d] = fmin(tmn[d], gx[d][k]); tmx[d] = fmax(tmx[d], gx[d][k]); }
+      ghmax = fmax(ghmax, gh[k]);
+    }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for(int d = 0; d < D; ++d) {
+        tmn[d] = fmin(tmn[d], __shfl_xor_sync(0xffffffffu, tmn[d], o));
+        tmx[d] = fmax(tmx[d], __shfl_xor_sync(0xffffffffu, tmx[d], o));
+      }
+      ghmax = fmax(ghmax, __shfl_xor_sync(0xffffffffu, ghmax, o));
+    }
+    if((tid & 31) == 0) {
+#pragma unroll
+      for(int d = 0; d < D; ++d) { red_sm[tid >> 5][d] = tmn[d]; red_sm[tid >> 5][D + d] = tmx[d]; }
+      red_sm[tid >> 5][2 * D] = ghmax;
+    }
+    __syncthreads();
+#pragma unroll
+    for(int d = 0; d < D; ++d) {
+      tmn[d] = fmin(red_sm[0][d], red_sm[1][d]);
+      tmx[d] = fmax(red_sm[0][D + d], red_sm[1][D + d]);
+    }
+    ghmax = fmax(red_sm[0][2 * D], red_sm[1][2 * D]);
+  }
+  int ncur = 1, cur = 0;
+  uint32_t ncands = 0;
+  while(ncur > 0) {
+    uint32_t nnext = 0;
+    for(int base = 0; base < ncur; base += SR_NT) {
+      const int j = base + tid;
+      uint32_t node_mask = 0, cand_mask = 0;
+      int cb = 0;
+      if(j < ncur) {
+        const int nd = queue[cur][j];
+        double mn[D], mx[D];
+#pragma unroll
+        for(int d = 0; d < D; ++d) { mn[d] = t.bmin[d][nd]; mx[d] = t.bmax[d][nd]; }
+        bool ok = true;
+        if(gnode >= 0) {
+          // intersects_box_box(c, G)
+          bool sep = false;
+#pragma unroll
+          for(int d = 0; d < D; ++d) sep = sep || (mx[d] < gmn[d]) || (gmx[d] < mn[d]);
+          ok = !sep;
+        }
+        if(ok) {
+          bool acc = false;
+          for(int k = 0; k < P && !acc; ++k) {
+            double p[D];
+#pragma unroll
+            for(int d = 0; d < D; ++d) p[d] = gx[d][k];
+            acc = sphere_box<D>(mn, mx, p, gh[k]);
+          }
+          ok = acc;
+        }
+        if(ok) {
+          cb = t.child_begin[nd];
+          const int ce = t.child_end[nd];
+          for(int cc = cb; cc < ce; ++cc) {
+            const int v = t.cell[cc];
+            if(v < 0) node_mask |= 1u << (cc - cb);
+            else {
+              bool pass = true;
+              if(gnode >= 0) {
+                // |x_e - X_G|^2 <= (max(h_e, lap_G) + radius_G)^2, tree_topology.h:365-370
+                double ext = fmax(c.f[F_H][v], glap) + grad;
+                double s2 = 0.0;
+#pragma unroll
+                for(int d = 0; d < D; ++d) {
+                  double df = c.f[F_POS + d][v] - gcom[d];
+                  s2 = d == 0 ? df * df : s2 + df * df;
+                }
+                pass = s2 <= ext * ext;
+              }
+              if(pass) {
+                const double hm = fmax(c.f[F_H][v], ghmax);
+                double dd = 0.0;
+#pragma unroll
+                for(int d = 0; d < D; ++d) {
+                  const double x = c.f[F_POS + d][v];
+                  const double tt = fmax(0.0, fmax(tmn[d] - x, x - tmx[d]));
+                  dd = dd + tt * tt;
+                }
+                pass = dd <= hm * hm * (1.0 + 1e-9);
+              }
+              if(pass) cand_mask |= 1u << (cc - cb);
+            }
+          }
+        }
+      }
+      uint32_t packed = (uint32_t)__popc(node_mask) | ((uint32_t)__popc(cand_mask) << 16);
+      uint32_t total;
+      uint32_t ex = block_scan_u32<SR_NT>(packed, total, scan_sm);
+      uint32_t qpos = nnext + (ex & 0xffffu), cpos = ncands + (ex >> 16);
+      while(node_mask) {
+        int b = __ffs(node_mask) - 1;
+        node_mask &= node_mask - 1;
+        if(qpos < SR_QCAP) queue[cur ^ 1][qpos] = ~t.cell[cb + b];
+        ++qpos;
+      }
+      if(FILL) {
+        while(cand_mask) {
+          int b = __ffs(cand_mask) - 1;
+          cand_mask &= cand_mask - 1;
+          sr.cand[cbase + cpos] = t.cell[cb + b];
+          ++cpos;
+        }
+      }
+      nnext += total & 0xffffu;
+      ncands += total >> 16;
+    }
+    if(nnext > SR_QCAP) {
+      if(tid == 0) atomicOr(status, (uint32_t)ERR_QUEUE_OVERFLOW);
+      nnext = SR_QCAP;
+    }
+    __syncthreads();
+    ncur = (int)nnext;
+    cur ^= 1;
+  }
+  const int Ppad = (P + 31) & ~31;
+  if(!FILL) {
+    if(tid == 0) {
+      ncand[g] = ncands;
+      nwords[g] = (uint64_t)((ncands + 31) / 32) * Ppad;
+    }
+    return;
+  }
+  else {
+    // ---- pair tests ------------------------------------------------------------------------------------
+    const int C = (int)ncands;
+    const uint64_t mo = sr.mask_off[g];
+    const int k0 = tid, k1 = tid + SR_NT;
+    double a0[D], a1[D], h0 = 0.0, h1 = 0.0;
+#pragma unroll
+    for(int d = 0; d < D; ++d) { a0[d] = k0 < P ? gx[d][k0] : 0.0; a1[d] = k1 < P ? gx[d][k1] : 0.0; }
+    if(k0 < P) { h0 = gh[k0]; h0 = h0 * h0; }
+    if(k1 < P) { h1 = gh[k1]; h1 = h1 * h1; }
+    int cnt0 = 0, cnt1 = 0;
+    const bool warp_has0 = (tid & ~31) < P, warp_has1 = ((tid & ~31) + SR_NT) < P;
+    for(int tb = 0; tb < C; tb += SR_TILE) {
+      const int tc = min(SR_TILE, C - tb);
+      __syncthreads();
+      for(int i = tid; i < tc; i += SR_NT) {
+        const int p = sr.cand[cbase + tb + i];
+#pragma unroll
+        for(int d = 0; d < D; ++d) cx[d][i] = c.f[F_POS + d][p];
+        const double hh = c.f[F_H][p];
+        ch2[i] = hh * hh;
+      }
+      __syncthreads();
+      const int nw = (tc + 31) >> 5;
+      for(int w = 0; w < nw; ++w) {
+        const int nb = min(32, tc - w * 32);
+        const uint64_t wo = mo + (uint64_t)((tb >> 5) + w) * Ppad;
+        // within_distance2(x_k, x_e, max(h_k, h_e)): max(h_k,h_e)^2 == max(h_k^2,h_e^2) exactly (rounding is monotonic)
+        if(warp_has1) {
+          uint32_t m0 = 0, m1 = 0;
+#pragma unroll 4
+          for(int b = 0; b < nb; ++b) {
+            const int ci = w * 32 + b;
+            const double eh2 = ch2[ci];
+            double e0 = cx[0][ci];
+            double s0 = (a0[0] - e0) * (a0[0] - e0);
+            double s1 = (a1[0] - e0) * (a1[0] - e0);
+#pragma unroll
+            for(int d = 1; d < D; ++d) {
+              const double ed = cx[d][ci];
+              s0 = s0 + (a0[d] - ed) * (a0[d] - ed);
+              s1 = s1 + (a1[d] - ed) * (a1[d] - ed);
+            }
+            m0 |= (uint32_t)(s0 <= fmax(h0, eh2)) << b;
+            m1 |= (uint32_t)(s1 <= fmax(h1, eh2)) << b;
+          }
+          sr.mask[wo + k0] = m0;
+          cnt0 += __popc(m0);
+          if(k1 < P) { sr.mask[wo + k1] = m1; cnt1 += __popc(m1); }
+        }
+        else if(warp_has0) {
+          uint32_t m0 = 0;
+#pragma unroll 4
+          for(int b = 0; b < nb; ++b) {
+            const int ci = w * 32 + b;
+            const double eh2 = ch2[ci];
+            double e0 = cx[0][ci];
+            double s0 = (a0[0] - e0) * (a0[0] - e0);
+#pragma unroll
+            for(int d = 1; d < D; ++d) {
+              const double ed = cx[d][ci];
+              s0 = s0 + (a0[d] - ed) * (a0[d] - ed);
+            }
+            m0 |= (uint32_t)(s0 <= fmax(h0, eh2)) << b;
+          }
+          if(k0 < P) { sr.mask[wo + k0] = m0; cnt0 += __popc(m0); }
+        }
+      }
+    }
+    if(k0 < P) c.nneigh[wc.start + k0] = cnt0;
+    if(k1 < P) c.nneigh[wc.start + k1] = cnt1;
+  }
+}
+
+template<int D>
+static void neighbor_search_t(System & s) {
+  Search & sr = s.search;
+  const int nwc = sr.nwc;
+  if(nwc <= 0) throw std::runtime_error("no work cells");
+  uint32_t * status = s.b_status.as<uint32_t>();
+  s.b_cand_off.reserve((size_t)(nwc + 1) * 8);
+  s.b_mask_off.reserve((size_t)(nwc + 1) * 8);
+  sr.cand_off = s.b_cand_off.as<uint64_t>();
+  sr.mask_off = s.b_mask_off.as<uint64_t>();
+  k_search<D, false><<<nwc, SR_NT, 0, s.stream>>>(s.tree, s.cols(), sr, sr.cand_off, sr.mask_off, status);
+  exclusive_scan_u64(s, sr.cand_off, sr.cand_off, nwc, nullptr);
+  exclusive_scan_u64(s, sr.mask_off, sr.mask_off, nwc, nullptr);
+  uint64_t tot[2];
+  uint32_t st = 0;
+  FSPH_CUDA_OK(cudaMemcpyAsync(&tot[0], sr.cand_off + nwc, 8, cudaMemcpyDeviceToHost, s.stream));
+  FSPH_CUDA_OK(cudaMemcpyAsync(&tot[1], sr.mask_off + nwc, 8, cudaMemcpyDeviceToHost, s.stream));
+  FSPH_CUDA_OK(cudaMemcpyAsync(&st, status, 4, cudaMemcpyDeviceToHost, s.stream));
+  FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
+  if(st & ERR_QUEUE_OVERFLOW) throw std::runtime_error("neighbour search: node frontier exceeds the shared-memory queue");
+  s.b_cand.reserve((size_t)std::max<uint64_t>(tot[0], 1) * 4);
+  s.b_mask.reserve((size_t)std::max<uint64_t>(tot[1], 1) * 4);
+  sr.cand = s.b_cand.as<int32_t>();
+  sr.mask = s.b_mask.as<uint32_t>();
+  k_search<D, true><<<nwc, SR_NT, 0, s.stream>>>(s.tree, s.cols(), sr, nullptr, nullptr, status);
+  FSPH_CUDA_OK(cudaGetLastError());
+}
+
+void neighbor_search(System & s) {
+  if(s.dim == 1) neighbor_search_t<1>(s);
+  else if(s.dim == 2) neighbor_search_t<2>(s);
+  else neighbor_search_t<3>(s);
+  s.search_valid = true;
+}
+
+// ---- CSR export for the parity tests --------------------------------------------------------------------
+__global__ void __launch_bounds__(SR_NT) k_export(Tree t, Cols c, Search sr, const uint64_t * __restrict__ off, int64_t * __restrict__ ids) {
+  const int g = blockIdx.x;
+  const WorkCell wc = load_work_cell(t, sr, g);
+  const int Ppad = (wc.P + 31) & ~31;
+  const uint64_t co = sr.cand_off[g], mo = sr.mask_off[g];
+  const int C = (int)(sr.cand_off[g + 1] - co);
+  const int nw = (C + 31) >> 5;
+  for(int k = threadIdx.x; k < wc.P; k += SR_NT) {
+    uint64_t o = off[wc.start + k];
+    for(int w = 0; w < nw; ++w) {
+      uint32_t m = sr.mask[mo + (uint64_t)w * Ppad + k];
+      while(m) {
+        int b = __ffs(m) - 1;
+        m &= m - 1;
+        ids[o++] = c.id[sr.cand[co + w * 32 + b]];
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_i32_to_u64(const int32_t * __restrict__ in, uint64_t * __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n) out[i] = (uint64_t)in[i];
+}
+
+void export_neighbors(System & s, std::vector<int64_t> & off, std::vector<int64_t> * ids) {
+  const int64_t n = s.n;
+  s.b_cnt1.reserve((size_t)(n + 1) * 8);
+  uint64_t * o = s.b_cnt1.as<uint64_t>();
+  k_i32_to_u64<<<(unsigned)((n + 255) / 256), 256, 0, s.stream>>>(s.col_nneigh.as<int32_t>(), o, n);
+  exclusive_scan_u64(s, o, o, n, nullptr);
+  off.resize(n + 1);
+  FSPH_CUDA_OK(cudaMemcpyAsync(off.data(), o, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
+  FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
+  if(!ids) return;
+  const int64_t tot = off[n];
+  ids->resize(tot);
+  DevBuf tmp;
+  tmp.reserve((size_t)std::max<int64_t>(tot, 1) * 8);
+  k_export<<<s.search.nwc, SR_NT, 0, s.stream>>>(s.tree, s.cols(), s.search, o, tmp.as<int64_t>());
+  FSPH_CUDA_OK(cudaMemcpyAsync(ids->data(), tmp.p, (size_t)tot * 8, cudaMemcpyDeviceToHost, s.stream));
+  FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
+  tmp.release();
+  for(int64_t i = 0; i < n; ++i) std::sort(ids->begin() + off[i], ids->begin() + off[i + 1]);
+}
+
+}  // namespace fsph

@@ -1,0 +1,257 @@
+// fsph_sort.cu -- hand-written device scan and LSD radix sort (64-bit Morton keys + 32-bit index payload).
+//
+// Replaces the local std::sort of whole 368-byte body records in psort::psort (mpisph/psort.h:247,310)
+// and is reused as the one-pass stable counting sort that brings the octree cells into level order.
+// HBM-bound: each pass reads key+index once and writes them once (12 B + 12 B per particle); passes whose
+// digit is constant over all keys are skipped (the digit histograms of all 8 passes come from one read).
+#include <stdexcept>
+#include "fsph_internal.h"
+
+namespace fsph {
+
+void DevBuf::reserve(size_t bytes) {
+  if(bytes <= cap) return;
+  if(p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  cudaError_t e = cudaMalloc(&p, want);
+  if(e != cudaSuccess) {
+    p = nullptr;
+    throw std::runtime_error(std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+  }
+  cap = want;
+}
+void DevBuf::release() {
+  if(p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// block-wide exclusive scan helper (NT threads, NT multiple of 32, <= 1024)
+template<typename T, int NT>
+__device__ __forceinline__ T block_exclusive_scan(T v, T & total, T * sm /* NT/32 + 1 */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  T x = v;
+#pragma unroll
+  for(int o = 1; o < 32; o <<= 1) {
+    T y = __shfl_up_sync(0xffffffffu, x, o);
+    if(lane >= o) x += y;
+  }
+  if(lane == 31) sm[w] = x;
+  __syncthreads();
+  if(w == 0) {
+    T t = lane < NT / 32 ? sm[lane] : T(0);
+#pragma unroll
+    for(int o = 1; o < 32; o <<= 1) {
+      T y = __shfl_up_sync(0xffffffffu, t, o);
+      if(lane >= o) t += y;
+    }
+    if(lane < NT / 32) sm[lane] = t;  // inclusive over warps
+  }
+  __syncthreads();
+  T base = w > 0 ? sm[w - 1] : T(0);
+  total = sm[NT / 32 - 1];
+  __syncthreads();
+  return base + x - v;
+}
+
+constexpr int SCAN_NT = 256, SCAN_IPT = 8, SCAN_TILE = SCAN_NT * SCAN_IPT;
+
+template<typename T>
+__global__ void __launch_bounds__(SCAN_NT) k_scan_reduce(const T * __restrict__ in, T * __restrict__ bsum, int64_t n) {
+  __shared__ T sm[SCAN_NT / 32 + 1];
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_IPT;
+  T acc = 0;
+#pragma unroll
+  for(int i = 0; i < SCAN_IPT; ++i)
+    if(base + i < n) acc += in[base + i];
+  T total;
+  block_exclusive_scan<T, SCAN_NT>(acc, total, sm);
+  if(threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+
+template<typename T>
+__global__ void __launch_bounds__(SCAN_NT) k_scan_final(const T * in, T * out, const T * __restrict__ boff, int64_t n) {
+  __shared__ T sm[SCAN_NT / 32 + 1];
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_IPT;
+  T v[SCAN_IPT];
+  T acc = 0;
+#pragma unroll
+  for(int i = 0; i < SCAN_IPT; ++i) {
+    v[i] = base + i < n ? in[base + i] : T(0);
+    acc += v[i];
+  }
+  T total;
+  T ex = block_exclusive_scan<T, SCAN_NT>(acc, total, sm) + (boff ? boff[blockIdx.x] : T(0));
+#pragma unroll
+  for(int i = 0; i < SCAN_IPT; ++i) {
+    if(base + i < n) {
+      out[base + i] = ex;
+      ex += v[i];
+      if(base + i == n - 1) out[n] = ex;
+    }
+  }
+}
+
+template<typename T>
+static void scan_impl(System & s, const T * in, T * out, int64_t n, int depth) {
+  if(n <= 0) {
+    FSPH_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(T), s.stream));
+    return;
+  }
+  int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if(nb == 1) {
+    k_scan_final<T><<<1, SCAN_NT, 0, s.stream>>>(in, out, nullptr, n);
+    return;
+  }
+  if(depth > 2) throw std::runtime_error("scan recursion too deep");
+  DevBuf & b = s.b_tmp[3 + depth];
+  b.reserve((nb + 1) * sizeof(T));
+  T * bs = b.as<T>();
+  k_scan_reduce<T><<<(unsigned)nb, SCAN_NT, 0, s.stream>>>(in, bs, n);
+  scan_impl<T>(s, bs, bs, nb, depth + 1);
+  k_scan_final<T><<<(unsigned)nb, SCAN_NT, 0, s.stream>>>(in, out, bs, n);
+}
+
+// out has n+1 entries: out[n] = total.  In-place (in == out) is allowed.
+void exclusive_scan_u32(System & s, const uint32_t * in, uint32_t * out, int64_t n, uint32_t *) { scan_impl<uint32_t>(s, in, out, n, 0); }
+void exclusive_scan_u64(System & s, const uint64_t * in, uint64_t * out, int64_t n, uint64_t *) { scan_impl<uint64_t>(s, in, out, n, 0); }
+
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_NT = 256, RS_IPT = 16, RS_TILE = RS_NT * RS_IPT, RS_WARPS = RS_NT / 32;
+
+__global__ void __launch_bounds__(256) k_hist_all(const uint64_t * __restrict__ k, int64_t n, uint32_t * __restrict__ hist /*[8][256]*/) {
+  __shared__ uint32_t sh[8 * 256];
+  for(int i = threadIdx.x; i < 8 * 256; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t key = k[i];
+#pragma unroll
+    for(int p = 0; p < 8; ++p) atomicAdd(&sh[p * 256 + ((key >> (8 * p)) & 255)], 1u);
+  }
+  __syncthreads();
+  for(int i = threadIdx.x; i < 8 * 256; i += blockDim.x)
+    if(sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+__global__ void __launch_bounds__(RS_NT) k_radix_count(const uint64_t * __restrict__ k, int64_t n, int shift,
+  uint32_t * __restrict__ tile_hist, int ntiles) {
+  __shared__ uint32_t sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+  for(int r = 0; r < RS_IPT; ++r) {
+    int64_t i = base + r * RS_NT + threadIdx.x;
+    if(i < n) atomicAdd(&sh[(k[i] >> shift) & 255], 1u);
+  }
+  __syncthreads();
+  tile_hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = sh[threadIdx.x];
+}
+
+// VMODE: 0 keys only, 1 values from vin, 2 values = source index
+template<int VMODE>
+__global__ void __launch_bounds__(RS_NT) k_radix_scatter(const uint64_t * __restrict__ kin, const uint32_t * __restrict__ vin,
+  uint64_t * __restrict__ kout, uint32_t * __restrict__ vout, int64_t n, int shift, const uint32_t * __restrict__ tile_off,
+  int ntiles) {
+  __shared__ uint32_t wcnt[RS_WARPS][256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for(int i = threadIdx.x; i < RS_WARPS * 256; i += RS_NT) (&wcnt[0][0])[i] = 0;
+  __syncthreads();
+  const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * (32 * RS_IPT);
+  uint64_t key[RS_IPT];
+  uint32_t rank[RS_IPT];
+#pragma unroll
+  for(int r = 0; r < RS_IPT; ++r) {
+    int64_t i = wbase + r * 32 + lane;
+    bool valid = i < n;
+    key[r] = valid ? kin[i] : 0;
+    uint32_t d = valid ? (uint32_t)((key[r] >> shift) & 255) : (256u + lane);
+    uint32_t peers = __match_any_sync(0xffffffffu, d);
+    int leader = __ffs(peers) - 1;
+    uint32_t old = 0;
+    if(valid && lane == leader) {
+      old = wcnt[w][d];
+      wcnt[w][d] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[r] = old + __popc(peers & ((1u << lane) - 1u));
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    int d = threadIdx.x;  // RS_NT == 256 digits
+    uint32_t run = tile_off[(size_t)d * ntiles + blockIdx.x];
+#pragma unroll
+    for(int ww = 0; ww < RS_WARPS; ++ww) {
+      uint32_t c = wcnt[ww][d];
+      wcnt[ww][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for(int r = 0; r < RS_IPT; ++r) {
+    int64_t i = wbase + r * 32 + lane;
+    if(i < n) {
+      uint32_t d = (uint32_t)((key[r] >> shift) & 255);
+      uint32_t dst = wcnt[w][d] + rank[r];
+      kout[dst] = key[r];
+      if(VMODE == 1) vout[dst] = vin[i];
+      if(VMODE == 2) vout[dst] = (uint32_t)i;
+    }
+  }
+}
+
+static void radix_pass_mode(System & s, const uint64_t * kin, const uint32_t * vin, uint64_t * kout, uint32_t * vout, int64_t n,
+  int shift, int vmode) {
+  if(n <= 0) return;
+  if(n >= (int64_t(1) << 32)) throw std::runtime_error("radix sort: more than 2^32 items");
+  int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
+  s.b_tmp[2].reserve(((size_t)256 * ntiles + 1) * sizeof(uint32_t));
+  uint32_t * th = s.b_tmp[2].as<uint32_t>();
+  k_radix_count<<<ntiles, RS_NT, 0, s.stream>>>(kin, n, shift, th, ntiles);
+  exclusive_scan_u32(s, th, th, (int64_t)256 * ntiles, nullptr);
+  if(vmode == 0) k_radix_scatter<0><<<ntiles, RS_NT, 0, s.stream>>>(kin, vin, kout, vout, n, shift, th, ntiles);
+  else if(vmode == 1) k_radix_scatter<1><<<ntiles, RS_NT, 0, s.stream>>>(kin, vin, kout, vout, n, shift, th, ntiles);
+  else k_radix_scatter<2><<<ntiles, RS_NT, 0, s.stream>>>(kin, vin, kout, vout, n, shift, th, ntiles);
+  FSPH_CUDA_OK(cudaGetLastError());
+}
+
+void radix_pass(System & s, const uint64_t * kin, const uint32_t * vin, uint64_t * kout, uint32_t * vout, int64_t n, int shift) {
+  radix_pass_mode(s, kin, vin, kout, vout, n, shift, vin ? 1 : 0);
+}
+
+// Sort (key, index) pairs: on entry k0 holds the keys (v0 contents ignored: the payload starts as the
+// identity); on return k0/v0 point at the sorted keys / permutation and k1/v1 at the scratch pair.
+void radix_sort_pairs(System & s, uint64_t *& k0, uint32_t *& v0, uint64_t *& k1, uint32_t *& v1, int64_t n) {
+  s.b_tmp[1].reserve(8 * 256 * sizeof(uint32_t));
+  uint32_t * hist = s.b_tmp[1].as<uint32_t>();
+  FSPH_CUDA_OK(cudaMemsetAsync(hist, 0, 8 * 256 * sizeof(uint32_t), s.stream));
+  int nb = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  k_hist_all<<<nb, 256, 0, s.stream>>>(k0, n, hist);
+  std::vector<uint32_t> h(8 * 256);
+  FSPH_CUDA_OK(cudaMemcpyAsync(h.data(), hist, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+  FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
+  bool first = true;
+  for(int p = 0; p < 8; ++p) {
+    bool trivial = false;
+    for(int d = 0; d < 256; ++d)
+      if(h[p * 256 + d] == (uint32_t)n) trivial = true;
+    if(trivial) continue;
+    radix_pass_mode(s, k0, v0, k1, v1, n, 8 * p, first ? 2 : 1);
+    first = false;
+    std::swap(k0, k1);
+    std::swap(v0, v1);
+  }
+  if(first) {
+    // all passes trivial (n <= 1): identity permutation
+    radix_pass_mode(s, k0, v0, k1, v1, n, 0, 2);
+    std::swap(k0, k1);
+    std::swap(v0, v1);
+  }
+}
+
+}  // namespace fsph

@@ -1,0 +1,377 @@
+// fsph_sweeps.cu -- the fp64 pair sweeps over the neighbour structure of fsph_search.cu.
+//
+// Replaces the functors the drivers pass to body_system::apply_in_smoothinglength
+// (mpisph/bodies_system.h:304; include/physics/default_physics.h):
+//   compute_density_pressure_soundspeed :309-320  (compute_density :193-228, recover_internal_energy :126-145,
+//                                                  eos ideal eos/eos.h:166-183, compute_signalspeed :236-265)
+//   compute_acceleration :348-408, compute_dudt :421-487, compute_dedt :502-566
+// with the SPH kernels of include/physics/kernels.h (cubic :106-153, quintic :217-268, Wendland C2 :282-365,
+// C4 :375-463, C6 :480-566) and the constant artificial viscosity of include/physics/viscosity.h:81-137.
+//
+// One CTA per work cell (thread k <-> particle k of the cell).  The cell's candidate particles are staged
+// in shared memory in tiles of 256 as SoA columns (coalesced gathers: candidates are runs of consecutive
+// Morton indices); each thread then walks the set bits of its own mask words and reads its neighbours'
+// fields from shared memory.  FP64-pipe bound; FMA contraction is allowed here (1e-10 bar).
+#include <stdexcept>
+#include <cfloat>
+#include "fsph_internal.h"
+
+namespace fsph {
+
+constexpr int SW_NT = 128;
+constexpr int SW_TILE = 256;
+constexpr double TINY = 1e10 * DBL_MIN;  // kernels.h:64, viscosity.h:36
+constexpr double PI = 3.14159265358979323846;
+
+enum SweepOp { OP_DENSITY = 0, OP_ACC = 1, OP_DUDT = 2, OP_DEDT = 3, OP_VSIG = 5 };
+
+// ---- SPH kernels: value W(r,h) and the scalar F with grad W = r_ab * F ------------------------------------
+template<int D> __device__ __forceinline__ double powD(double h) { return D == 1 ? h : (D == 2 ? h * h : h * h * h); }
+
+template<int D, int K> struct SphKernel;
+
+template<int D> struct SphKernel<D, FSPH_KERNEL_CUBIC_SPLINE> {
+  static __device__ __forceinline__ double sigma() { return D == 1 ? 4. / 3. : (D == 2 ? 40. / (7. * PI) : 8. / PI); }
+  static __device__ __forceinline__ double W(double r, double h) {
+    double q = 2. * r / h, res = 0.;
+    if(q < 2.0) {
+      res = q < 1.0 ? 1.0 - 1.5 * q * q + .75 * q * q * q : 0.25 * (2 - q) * (2 - q) * (2 - q);
+      res *= sigma() / powD<D>(h);
+    }
+    return res;
+  }
+  static __device__ __forceinline__ double F(double r, double h) {
+    double q = 2. * r / h, res = 0.;
+    if(q < 2.0) {
+      double sg = 2. * sigma() / (powD<D>(h) * h);
+      double dW = q < 1.0 ? -3.0 * q + 9. / 4. * q * q : -.75 * (2 - q) * (2 - q);
+      res = sg * dW / (r + TINY);
+    }
+    return res;
+  }
+};
+template<int D> struct SphKernel<D, FSPH_KERNEL_QUINTIC_SPLINE> {
+  static __device__ __forceinline__ double sigma() { return D == 1 ? 1. / 40. : (D == 2 ? 63. / (478. * PI) : 81. / (359. * PI)); }
+  static __device__ __forceinline__ double p5(double x) { double x2 = x * x; return x2 * x2 * x; }
+  static __device__ __forceinline__ double p4(double x) { double x2 = x * x; return x2 * x2; }
+  static __device__ __forceinline__ double W(double r, double h) {
+    double q = 3. * r / h, res = 0.;
+    if(q < 3.) {
+      res = p5(3 - q);
+      if(q < 2.) res += -6 * p5(2 - q);
+      if(q < 1.) res += 15 * p5(1 - q);
+      res *= sigma() / powD<D>(h);
+    }
+    return res;
+  }
+  static __device__ __forceinline__ double F(double r, double h) {
+    double q = 3. * r / h, res = 0.;
+    if(q < 3.) {
+      double sg = 3. * sigma() / (powD<D>(h) * h);
+      double dW = -5. * p4(3 - q);
+      if(q < 2.) dW += 30. * p4(2 - q);
+      if(q < 1.) dW += -75. * p4(1 - q);
+      res = sg * dW / (r + TINY);
+    }
+    return res;
+  }
+};
+template<int D> struct SphKernel<D, FSPH_KERNEL_WENDLAND_C2> {
+  static __device__ __forceinline__ double sigma() { return D == 1 ? 1.25 : (D == 2 ? 7. / PI : 21. / (2. * PI)); }
+  static __device__ __forceinline__ double W(double r, double h) {
+    double q = r / h, o = 1 - q, o2 = o * o;
+    double res = D == 1 ? sigma() / h * o2 * o * (3 * q + 1) : sigma() / powD<D>(h) * o2 * o2 * (4 * q + 1);
+    return q < 1.0 ? res : 0.0;
+  }
+  static __device__ __forceinline__ double F(double r, double h) {
+    double q = r / h, o = 1 - q, o2 = o * o;
+    double sg = D == 1 ? sigma() / (h * h) : 2. * sigma() / (powD<D>(h) * h);
+    double dW = D == 1 ? -12. * q * o2 : -10. * q * o2 * o;
+    return q < 1.0 ? sg * dW / (r + TINY) : 0.0;
+  }
+};
+template<int D> struct SphKernel<D, FSPH_KERNEL_WENDLAND_C4> {
+  static __device__ __forceinline__ double sigma() { return D == 1 ? 1.5 : (D == 2 ? 9. / PI : 495. / (32. * PI)); }
+  static __device__ __forceinline__ double W(double r, double h) {
+    double q = r / h, o = 1 - q, o2 = o * o;
+    double res;
+    if(D == 1) res = sigma() / h * (o2 * o) * o2 * (1 + q * (5 + q * 8));
+    else res = sigma() / powD<D>(h) * (o2 * o2 * o2) * (1 + q * (6 + q * 35 / 3));
+    return q < 1.0 ? res : 0.0;
+  }
+  static __device__ __forceinline__ double F(double r, double h) {
+    double q = r / h, o = 1 - q, o2 = o * o;
+    double sg = 14. * sigma() / (powD<D>(h) * h);
+    double dW = D == 1 ? -q * o2 * o2 * (1 + 4. * q) : -4. / 3. * q * (o2 * o) * o2 * (1 + 5. * q);
+    return q < 1.0 ? sg * dW / (r + TINY) : 0.0;
+  }
+};
+template<int D> struct SphKernel<D, FSPH_KERNEL_WENDLAND_C6> {
+  static __device__ __forceinline__ double sigma() { return D == 1 ? 55. / 32. : (D == 2 ? 78. / (7. * PI) : 1365. / (64. * PI)); }
+  static __device__ __forceinline__ double W(double r, double h) {
+    double q = r / h, o = 1 - q, o2 = o * o, o4 = o2 * o2;
+    double res;
+    if(D == 1) res = sigma() / h * (o2 * o) * o4 * (1 + q * (7 + q * (19 + q * 21)));
+    else res = sigma() / powD<D>(h) * o4 * o4 * (1 + q * (8 + q * (25 + q * 32)));
+    return q < 1.0 ? res : 0.0;
+  }
+  static __device__ __forceinline__ double F(double r, double h) {
+    double q = r / h, o = 1 - q, o2 = o * o, o3 = o2 * o, o4 = o2 * o2;
+    double sg = sigma() / (powD<D>(h) * h);
+    double dW = D == 1 ? -6. * q * o3 * o3 * (3 + q * (18 + q * 35)) : -22. * q * o4 * o3 * (1 + q * (7 + q * 16));
+    return q < 1.0 ? sg * dW / (r + TINY) : 0.0;
+  }
+};
+
+// ---- candidate tile columns per sweep ---------------------------------------------------------------------
+template<int D, int OP> struct TileCols {
+  static constexpr int NF = OP == OP_DENSITY ? D + 2 : (OP == OP_VSIG ? 2 * D + 2 : (OP == OP_ACC ? 2 * D + 5 : 3 * D + 5));
+  static __device__ __forceinline__ int col(int j) {
+    if(j < D) return F_POS + j;
+    if(OP == OP_DENSITY) return j == D ? F_H : F_MASS;
+    if(OP == OP_VSIG) return j < 2 * D ? F_VEL + (j - D) : (j == 2 * D ? F_CS : F_CSOLD);
+    const int r = j - D;
+    if(r == 0) return F_H;
+    if(r == 1) return F_MASS;
+    if(r == 2) return F_RHO;
+    if(r == 3) return F_P;
+    if(r == 4) return F_CS;
+    if(r < 5 + D) return F_VELH + (r - 5);
+    return F_VEL + (r - 5 - D);
+  }
+};
+
+template<int D>
+__device__ __forceinline__ double norm_vec(const double * v) {
+  if(D == 1) return fabs(v[0]);
+  double s = 0.0;
+#pragma unroll
+  for(int d = 0; d < D; ++d) s += v[d] * v[d];
+  return sqrt(s);
+}
+
+template<int D, int K, int OP>
+__global__ void __launch_bounds__(SW_NT) k_sweep(Tree t, Cols c, Search sr, PhysParams pp, uint32_t * __restrict__ status) {
+  using TC = TileCols<D, OP>;
+  constexpr int NF = TC::NF;
+  __shared__ double tile[NF][SW_TILE];
+  __shared__ int32_t tidx[SW_TILE];
+
+  const int g = blockIdx.x, tid = threadIdx.x;
+  int start, P;
+  {
+    int v = t.cell[sr.wc_cell[g]];
+    if(v >= 0) { start = v; P = 1; }
+    else { start = t.node_start[~v]; P = t.sub[~v]; }
+  }
+  const int Ppad = (P + 31) & ~31;
+  const uint64_t co = sr.cand_off[g], mo = sr.mask_off[g];
+  const int C = (int)(sr.cand_off[g + 1] - co);
+  const bool active = tid < P;
+  const int ia = start + tid;
+
+  // own fields
+  double xa[D], ha = 0, rho_a = 0, P_a = 0, cs_a = 0, va[D], vha[D], Prho2_a = 0;
+#pragma unroll
+  for(int d = 0; d < D; ++d) { xa[d] = 0; va[d] = 0; vha[d] = 0; }
+  if(active) {
+#pragma unroll
+    for(int d = 0; d < D; ++d) xa[d] = c.f[F_POS + d][ia];
+    ha = c.f[F_H][ia];
+    if(OP == OP_VSIG || OP == OP_DUDT || OP == OP_DEDT) {
+#pragma unroll
+      for(int d = 0; d < D; ++d) va[d] = c.f[F_VEL + d][ia];
+    }
+    if(OP == OP_VSIG) cs_a = c.f[F_CS][ia];
+    if(OP == OP_ACC || OP == OP_DUDT || OP == OP_DEDT) {
+      rho_a = c.f[F_RHO][ia];
+      P_a = c.f[F_P][ia];
+      cs_a = c.f[F_CS][ia];
+      Prho2_a = P_a / (rho_a * rho_a);
+#pragma unroll
+      for(int d = 0; d < D; ++d) vha[d] = c.f[F_VELH + d][ia];
+    }
+  }
+  // accumulators
+  double acc0 = 0.0, acc1 = 0.0, accv[D];
+#pragma unroll
+  for(int d = 0; d < D; ++d) accv[d] = 0.0;
+
+  for(int tb = 0; tb < C; tb += SW_TILE) {
+    const int tc = min(SW_TILE, C - tb);
+    __syncthreads();
+    for(int i = tid; i < tc; i += SW_NT) {
+      const int p = sr.cand[co + tb + i];
+      tidx[i] = p;
+#pragma unroll
+      for(int j = 0; j < NF; ++j) tile[j][i] = c.f[TC::col(j)][p];
+    }
+    __syncthreads();
+    if(!active) continue;
+    const int nw = (tc + 31) >> 5;
+    const uint32_t * mrow = sr.mask + mo + (uint64_t)(tb >> 5) * Ppad + tid;
+    int w = 0;
+    uint32_t m = mrow[0];
+    while(true) {
+      while(m == 0 && ++w < nw) m = mrow[(size_t)w * Ppad];
+      if(m == 0) break;
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      const int ci = w * 32 + b;
+      double rab[D];
+#pragma unroll
+      for(int d = 0; d < D; ++d) rab[d] = xa[d] - tile[d][ci];
+      if(OP == OP_DENSITY) {
+        const double r = norm_vec<D>(rab);
+        const double hab = .5 * (ha + tile[D][ci]);
+        acc0 += tile[D + 1][ci] * SphKernel<D, K>::W(r, hab);
+      }
+      else if(OP == OP_VSIG) {
+        // compute_signalspeed: b contributes its new soundspeed iff it was processed before a, i.e. iff its
+        // (descending-key processing order) index is larger
+        const double csb = tidx[ci] > ia ? tile[2 * D][ci] : tile[2 * D + 1][ci];
+        const double cab = fmax(cs_a, csb);
+        const double dist = norm_vec<D>(rab);
+        double vr = 0.0;
+#pragma unroll
+        for(int d = 0; d < D; ++d) vr += (va[d] - tile[D + d][ci]) * (rab[d] / dist);
+        const double mn = (0.0 < vr) ? 0.0 : vr;  // std::min(vr, 0.0), NaN-preserving
+        const double val = cab - mn;
+        if(acc0 < val) acc0 = val;                // std::max(vsig, val): NaN (self) dropped
+      }
+      else {
+        const double hab = .5 * (ha + tile[D][ci]);
+        bool same = true;
+#pragma unroll
+        for(int d = 0; d < D; ++d) same = same && (rab[d] == 0.0) && (xa[d] == tile[d][ci]);
+        const double mb = same ? 0.0 : tile[D + 1][ci];
+        const double rho_b = tile[D + 2][ci], P_b = tile[D + 3][ci], cs_b = tile[D + 4][ci];
+        double dotvr = 0.0, dist2 = 0.0;
+#pragma unroll
+        for(int d = 0; d < D; ++d) {
+          dotvr += (vha[d] - tile[D + 5 + d][ci]) * rab[d];
+          dist2 += rab[d] * rab[d];
+        }
+        double mu = hab * dotvr / (dist2 + pp.epsilon * hab * hab + TINY);
+        mu = dotvr < 0.0 ? mu : 0.0;
+        const double rho_ab = .5 * (rho_a + rho_b), c_ab = .5 * (cs_a + cs_b);
+        const double Pi = (-pp.alpha * c_ab + pp.beta * mu) * mu / rho_ab;
+        const double r = D == 1 ? fabs(rab[0]) : sqrt(dist2);
+        const double Fk = SphKernel<D, K>::F(r, hab);
+        const double Prho2_b = P_b / (rho_b * rho_b);
+        if(OP == OP_ACC) {
+          const double coef = -mb * (Prho2_a + Prho2_b + Pi) * Fk;
+#pragma unroll
+          for(int d = 0; d < D; ++d) accv[d] += coef * rab[d];
+        }
+        else if(OP == OP_DUDT) {
+          double vdw = 0.0;
+#pragma unroll
+          for(int d = 0; d < D; ++d) vdw += (va[d] - tile[2 * D + 5 + d][ci]) * rab[d];
+          vdw *= Fk;
+          acc0 += mb * vdw;
+          acc1 += mb * vdw * Pi;
+        }
+        else {  // OP_DEDT
+          double vadw = 0.0, vbdw = 0.0;
+#pragma unroll
+          for(int d = 0; d < D; ++d) {
+            vadw += va[d] * rab[d];
+            vbdw += tile[2 * D + 5 + d][ci] * rab[d];
+          }
+          vadw *= Fk;
+          vbdw *= Fk;
+          acc0 -= mb * (Prho2_a * vbdw + vadw * Prho2_b + .5 * Pi * (vbdw + vadw));
+        }
+      }
+    }
+  }
+  if(!active) return;
+  if(OP == OP_DENSITY) {
+    const double rho = acc0;
+    if(!(rho > 0)) atomicOr(status, (uint32_t)ERR_RHO_NONPOS);
+    c.f[F_RHO][ia] = rho;
+    double u;
+    if(pp.evolve_u && pp.thermokinetic) {
+      // recover_internal_energy (no external potential)
+      double v2 = 0.0;
+#pragma unroll
+      for(int d = 0; d < D; ++d) { const double v = c.f[F_VEL + d][ia]; v2 += v * v; }
+      u = c.f[F_E][ia] - .5 * v2 - 0.0;
+      if(!(u > 0)) atomicOr(status, (uint32_t)ERR_U_NONPOS);
+      c.f[F_U][ia] = u;
+    }
+    else u = c.f[F_U][ia];
+    c.f[F_P][ia] = (pp.gamma - 1.) * rho * u;
+    c.f[F_CSOLD][ia] = c.f[F_CS][ia];
+    c.f[F_CS][ia] = sqrt(pp.gamma * (pp.gamma - 1.) * u);
+  }
+  else if(OP == OP_VSIG) c.f[F_VSIG][ia] = acc0;
+  else if(OP == OP_ACC) {
+#pragma unroll
+    for(int d = 0; d < D; ++d) {
+      c.f[F_ACC + d][ia] = accv[d];  // + external_force::acceleration == 0 (external_force_type "none")
+      c.f[F_GACC + d][ia] = 0.0;
+    }
+    c.f[F_GPOT][ia] = 0.0;
+  }
+  else if(OP == OP_DUDT) c.f[F_DUDT][ia] = Prho2_a * acc0 + .5 * acc1;
+  else {
+    double gv = 0.0;
+#pragma unroll
+    for(int d = 0; d < D; ++d) gv += c.f[F_GACC + d][ia] * va[d];
+    c.f[F_DEDT][ia] = acc0 + gv;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_fill(double * p, int64_t n, double v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n) p[i] = v;
+}
+
+template<int D, int K, int OP>
+static void launch_sweep(System & s) {
+  k_sweep<D, K, OP><<<s.search.nwc, SW_NT, 0, s.stream>>>(s.tree, s.cols(), s.search, s.phys(), s.b_status.as<uint32_t>());
+}
+
+template<int D, int K>
+static void sweep_dk(System & s, int op) {
+  switch(op) {
+    case FSPH_SWEEP_DENSITY_PRESSURE_SOUNDSPEED:
+      launch_sweep<D, K, OP_DENSITY>(s);
+      launch_sweep<D, K, OP_VSIG>(s);
+      break;
+    case FSPH_SWEEP_ACCELERATION: launch_sweep<D, K, OP_ACC>(s); break;
+    case FSPH_SWEEP_DUDT:
+      if(s.iteration < s.par.relaxation_steps)
+        k_fill<<<(unsigned)((s.n + 255) / 256), 256, 0, s.stream>>>(s.col[F_DUDT].as<double>(), s.n, 0.0);
+      else launch_sweep<D, K, OP_DUDT>(s);
+      break;
+    case FSPH_SWEEP_DEDT: launch_sweep<D, K, OP_DEDT>(s); break;
+    default: throw std::runtime_error("unknown sweep op");
+  }
+}
+
+template<int D>
+static void sweep_d(System & s, int op) {
+  switch(s.par.sph_kernel) {
+    case FSPH_KERNEL_CUBIC_SPLINE: sweep_dk<D, FSPH_KERNEL_CUBIC_SPLINE>(s, op); break;
+    case FSPH_KERNEL_QUINTIC_SPLINE: sweep_dk<D, FSPH_KERNEL_QUINTIC_SPLINE>(s, op); break;
+    case FSPH_KERNEL_WENDLAND_C2: sweep_dk<D, FSPH_KERNEL_WENDLAND_C2>(s, op); break;
+    case FSPH_KERNEL_WENDLAND_C4: sweep_dk<D, FSPH_KERNEL_WENDLAND_C4>(s, op); break;
+    case FSPH_KERNEL_WENDLAND_C6: sweep_dk<D, FSPH_KERNEL_WENDLAND_C6>(s, op); break;
+    default: throw std::runtime_error("sph_kernel not implemented on the device (gaussian / super gaussian / sinc)");
+  }
+}
+
+void sweep(System & s, int op) {
+  if(!s.tree_valid) throw std::runtime_error("sweep before update_iteration");
+  if(!s.search_valid) neighbor_search(s);
+  if(op == FSPH_SWEEP_NEIGHBORS_ONLY) return;
+  if(s.dim == 1) sweep_d<1>(s, op);
+  else if(s.dim == 2) sweep_d<2>(s, op);
+  else sweep_d<3>(s, op);
+  FSPH_CUDA_OK(cudaGetLastError());
+}
+
+}  // namespace fsph
