@@ -59,7 +59,7 @@ class Params(C.Structure):
 # every symbol include/flecsph_b200.h declares
 SYMBOLS = [
     "fsph_default_params", "fsph_create", "fsph_destroy", "fsph_last_error", "fsph_backend", "fsph_resize",
-    "fsph_nbodies", "fsph_set_column", "fsph_get_column", "fsph_upload_aos", "fsph_download_aos", "fsph_set_time",
+    "fsph_nbodies", "fsph_set_column", "fsph_get_column", "fsph_set_component", "fsph_get_component", "fsph_launch_count", "fsph_upload_aos", "fsph_download_aos", "fsph_set_time",
     "fsph_get_time", "fsph_advance_time", "fsph_update_iteration", "fsph_reset_ghosts", "fsph_sweep", "fsph_apply",
     "fsph_reduce", "fsph_gravitation_fmm", "fsph_get_range", "fsph_get_smoothinglength", "fsph_step",
     "fsph_tree_num_nodes", "fsph_tree_get_nodes", "fsph_tree_get_leaf_depth", "fsph_neighbor_lists",
@@ -103,6 +103,9 @@ def load(path):
         "fsph_nbodies": (i64, [vp]),
         "fsph_set_column": (i32, [vp, i32, vp]),
         "fsph_get_column": (i32, [vp, i32, vp]),
+        "fsph_set_component": (i32, [vp, i32, i32, vp]),
+        "fsph_get_component": (i32, [vp, i32, i32, vp]),
+        "fsph_launch_count": (C.c_uint64, []),
         "fsph_upload_aos": (i32, [vp, vp, i64, i64, vp]),
         "fsph_download_aos": (i32, [vp, vp, i64, vp]),
         "fsph_set_time": (i32, [vp, dbl, dbl, i64]),
@@ -204,6 +207,16 @@ class BodySystem:
         a = np.empty(self._shape(col), dtype=COL_DTYPE.get(col, np.float64))
         self._ck(self.lib.fsph_get_column(self.h, col, a.ctypes.data))
         return a
+
+    def set_component(self, col, comp, ptr):
+        """Contiguous [n] component from a raw host pointer (e.g. a pinned torch tensor's data_ptr())."""
+        self._ck(self.lib.fsph_set_component(self.h, col, comp, ptr))
+
+    def get_component(self, col, comp, ptr):
+        self._ck(self.lib.fsph_get_component(self.h, col, comp, ptr))
+
+    def launch_count(self):
+        return int(self.lib.fsph_launch_count())
 
     def load_bodies(self, fields):
         """read_bodies (bodies_system.h:83) from a dict of column-name -> array."""

@@ -150,9 +150,9 @@ void apply(System & s, int op) {
   if(s.n <= 0) return;
   unsigned nb = (unsigned)((s.n + 255) / 256);
   uint32_t * st = s.b_status.as<uint32_t>();
-  if(s.dim == 1) k_apply<1><<<nb, 256, 0, s.stream>>>(s.cols(), s.n, op, s.phys(), st);
-  else if(s.dim == 2) k_apply<2><<<nb, 256, 0, s.stream>>>(s.cols(), s.n, op, s.phys(), st);
-  else k_apply<3><<<nb, 256, 0, s.stream>>>(s.cols(), s.n, op, s.phys(), st);
+  if(s.dim == 1) FSPH_LAUNCH((k_apply<1>), nb, 256, s.stream, s.cols(), s.n, op, s.phys(), st);
+  else if(s.dim == 2) FSPH_LAUNCH((k_apply<2>), nb, 256, s.stream, s.cols(), s.n, op, s.phys(), st);
+  else FSPH_LAUNCH((k_apply<3>), nb, 256, s.stream, s.cols(), s.n, op, s.phys(), st);
   FSPH_CUDA_OK(cudaGetLastError());
   if(op == FSPH_APPLY_LEAPFROG_DRIFT) s.tree_dirty = true;
 }
@@ -219,9 +219,9 @@ __global__ void __launch_bounds__(256) k_reduce(Cols c, int64_t n, int kind, int
 static void run_reduce(System & s, int kind, double out[3]) {
   int nb = (int)std::min<int64_t>((s.n + 255) / 256, 148 * 4);
   double * part = reduce_scratch(s, (size_t)nb * 3 + 16);
-  if(s.dim == 1) k_reduce<1><<<nb, 256, 0, s.stream>>>(s.cols(), s.n, kind, s.par.thermokinetic_formulation, s.par.enable_fmm, part);
-  else if(s.dim == 2) k_reduce<2><<<nb, 256, 0, s.stream>>>(s.cols(), s.n, kind, s.par.thermokinetic_formulation, s.par.enable_fmm, part);
-  else k_reduce<3><<<nb, 256, 0, s.stream>>>(s.cols(), s.n, kind, s.par.thermokinetic_formulation, s.par.enable_fmm, part);
+  if(s.dim == 1) FSPH_LAUNCH((k_reduce<1>), nb, 256, s.stream, s.cols(), s.n, kind, s.par.thermokinetic_formulation, s.par.enable_fmm, part);
+  else if(s.dim == 2) FSPH_LAUNCH((k_reduce<2>), nb, 256, s.stream, s.cols(), s.n, kind, s.par.thermokinetic_formulation, s.par.enable_fmm, part);
+  else FSPH_LAUNCH((k_reduce<3>), nb, 256, s.stream, s.cols(), s.n, kind, s.par.thermokinetic_formulation, s.par.enable_fmm, part);
   std::vector<double> h((size_t)nb * 3);
   FSPH_CUDA_OK(cudaMemcpyAsync(h.data(), part, h.size() * 8, cudaMemcpyDeviceToHost, s.stream));
   FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));

@@ -304,7 +304,7 @@ int32_t fsph_resize(fsph_system * s, int64_t n) {
     FSPH_CUDA_OK(cudaMemsetAsync(s->col_key.p, 0, b8, s->stream));
     FSPH_CUDA_OK(cudaMemsetAsync(s->col_type.p, 0, b4, s->stream));
     FSPH_CUDA_OK(cudaMemsetAsync(s->col_nneigh.p, 0, b4, s->stream));
-    if(n > 0) k_iota64<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->col_id.as<int64_t>(), n);
+    if(n > 0) FSPH_LAUNCH(k_iota64, (unsigned)((n + 255) / 256), 256, s->stream, s->col_id.as<int64_t>(), n);
     s->n = n;
     invalidate(*s);
     FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
@@ -361,6 +361,43 @@ int32_t fsph_get_column(fsph_system * s, int32_t col, void * host) {
     else if(col == FSPH_COL_NNEIGH) { src = s->col_nneigh.p; bytes = (size_t)n * 4; }
     else throw std::runtime_error("bad column");
     FSPH_CUDA_OK(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, s->stream));
+    FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
+  });
+}
+
+int32_t fsph_set_component(fsph_system * s, int32_t col, int32_t comp, const void * host) {
+  return guarded(s, [&]() {
+    void * dst = nullptr;
+    size_t esz = 8;
+    if(col >= FSPH_COL_POS && col <= FSPH_COL_GACC) {
+      if(comp < 0 || comp >= s->dim) throw std::runtime_error("bad component");
+      dst = s->col[VEC_FIELD[col] + comp].p;
+    }
+    else if(scalar_field(col) >= 0) dst = s->col[scalar_field(col)].p;
+    else if(col == FSPH_COL_ID) dst = s->col_id.p;
+    else if(col == FSPH_COL_TYPE) { dst = s->col_type.p; esz = 4; }
+    else throw std::runtime_error("column not writable");
+    FSPH_CUDA_OK(cudaMemcpyAsync(dst, host, (size_t)s->n * esz, cudaMemcpyHostToDevice, s->stream));
+    FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
+    if(col == FSPH_COL_POS || col == FSPH_COL_H || col == FSPH_COL_MASS) s->tree_dirty = true;
+  });
+}
+
+int32_t fsph_get_component(fsph_system * s, int32_t col, int32_t comp, void * host) {
+  return guarded(s, [&]() {
+    const void * src = nullptr;
+    size_t esz = 8;
+    if(col >= FSPH_COL_POS && col <= FSPH_COL_GACC) {
+      if(comp < 0 || comp >= s->dim) throw std::runtime_error("bad component");
+      src = s->col[VEC_FIELD[col] + comp].p;
+    }
+    else if(scalar_field(col) >= 0) src = s->col[scalar_field(col)].p;
+    else if(col == FSPH_COL_ID) src = s->col_id.p;
+    else if(col == FSPH_COL_KEY) src = s->col_key.p;
+    else if(col == FSPH_COL_TYPE) { src = s->col_type.p; esz = 4; }
+    else if(col == FSPH_COL_NNEIGH) { src = s->col_nneigh.p; esz = 4; }
+    else throw std::runtime_error("bad column");
+    FSPH_CUDA_OK(cudaMemcpyAsync(host, src, (size_t)s->n * esz, cudaMemcpyDeviceToHost, s->stream));
     FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
   });
 }
@@ -479,7 +516,24 @@ int32_t fsph_step(fsph_system * s, int32_t initial) {
   return guarded(s, [&]() {
     s->timing = true;
     s->phases.clear();
-    do_step(*s, initial);
+    Phase tot;
+    tot.name = "total";
+    cudaEventCreate(&tot.e0);
+    cudaEventCreate(&tot.e1);
+    cudaEventRecord(tot.e0, s->stream);
+    try {
+      do_step(*s, initial);
+    }
+    catch(...) {
+      cudaEventDestroy(tot.e0);
+      cudaEventDestroy(tot.e1);
+      for(auto & p : s->phases) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+      s->phases.clear();
+      s->timing = false;
+      throw;
+    }
+    cudaEventRecord(tot.e1, s->stream);
+    s->phases.push_back(tot);
     finish_phases(*s);
     s->timing = false;
   });
@@ -543,6 +597,8 @@ int32_t fsph_neighbor_lists(fsph_system * s, int64_t * offsets, int64_t * ids) {
     if(ids) std::copy(idv.begin(), idv.end(), ids);
   });
 }
+
+uint64_t fsph_launch_count(void) { return fsph::g_launches; }
 
 int32_t fsph_phase_times(fsph_system * s, double * ms, int32_t cap, const char ** names) {
   if(!s) return 0;

@@ -134,6 +134,14 @@ struct System {
     }                                                                                            \
   } while(0)
 
+// every kernel launch of the library goes through this macro (bench.py reports the count as gpu_launches)
+extern unsigned long long g_launches;
+#define FSPH_LAUNCH(kernel, grid, block, stream, ...)            \
+  do {                                                           \
+    ++fsph::g_launches;                                          \
+    kernel<<<grid, block, 0, stream>>>(__VA_ARGS__);             \
+  } while(0)
+
 // ---- fsph_sort.cu ---------------------------------------------------------------------------
 // One stable LSD pass on an 8-bit digit at `shift`; vals may be null (keys only).
 void radix_pass(System & s, const uint64_t * kin, const uint32_t * vin, uint64_t * kout, uint32_t * vout, int64_t n, int shift);

@@ -338,7 +338,7 @@ static void neighbor_search_t(System & s) {
   s.b_mask_off.reserve((size_t)(nwc + 1) * 8);
   sr.cand_off = s.b_cand_off.as<uint64_t>();
   sr.mask_off = s.b_mask_off.as<uint64_t>();
-  k_search<D, false><<<nwc, SR_NT, 0, s.stream>>>(s.tree, s.cols(), sr, sr.cand_off, sr.mask_off, status);
+  FSPH_LAUNCH((k_search<D, false>), nwc, SR_NT, s.stream, s.tree, s.cols(), sr, sr.cand_off, sr.mask_off, status);
   exclusive_scan_u64(s, sr.cand_off, sr.cand_off, nwc, nullptr);
   exclusive_scan_u64(s, sr.mask_off, sr.mask_off, nwc, nullptr);
   uint64_t tot[2];
@@ -352,7 +352,7 @@ static void neighbor_search_t(System & s) {
   s.b_mask.reserve((size_t)std::max<uint64_t>(tot[1], 1) * 4);
   sr.cand = s.b_cand.as<int32_t>();
   sr.mask = s.b_mask.as<uint32_t>();
-  k_search<D, true><<<nwc, SR_NT, 0, s.stream>>>(s.tree, s.cols(), sr, nullptr, nullptr, status);
+  FSPH_LAUNCH((k_search<D, true>), nwc, SR_NT, s.stream, s.tree, s.cols(), sr, nullptr, nullptr, status);
   FSPH_CUDA_OK(cudaGetLastError());
 }
 
@@ -392,7 +392,7 @@ void export_neighbors(System & s, std::vector<int64_t> & off, std::vector<int64_
   const int64_t n = s.n;
   s.b_cnt1.reserve((size_t)(n + 1) * 8);
   uint64_t * o = s.b_cnt1.as<uint64_t>();
-  k_i32_to_u64<<<(unsigned)((n + 255) / 256), 256, 0, s.stream>>>(s.col_nneigh.as<int32_t>(), o, n);
+  FSPH_LAUNCH(k_i32_to_u64, (unsigned)((n + 255) / 256), 256, s.stream, s.col_nneigh.as<int32_t>(), o, n);
   exclusive_scan_u64(s, o, o, n, nullptr);
   off.resize(n + 1);
   FSPH_CUDA_OK(cudaMemcpyAsync(off.data(), o, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
@@ -402,7 +402,7 @@ void export_neighbors(System & s, std::vector<int64_t> & off, std::vector<int64_
   ids->resize(tot);
   DevBuf tmp;
   tmp.reserve((size_t)std::max<int64_t>(tot, 1) * 8);
-  k_export<<<s.search.nwc, SR_NT, 0, s.stream>>>(s.tree, s.cols(), s.search, o, tmp.as<int64_t>());
+  FSPH_LAUNCH(k_export, s.search.nwc, SR_NT, s.stream, s.tree, s.cols(), s.search, o, tmp.as<int64_t>());
   FSPH_CUDA_OK(cudaMemcpyAsync(ids->data(), tmp.p, (size_t)tot * 8, cudaMemcpyDeviceToHost, s.stream));
   FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
   tmp.release();

@@ -9,6 +9,8 @@
 
 namespace fsph {
 
+unsigned long long g_launches = 0;
+
 void DevBuf::reserve(size_t bytes) {
   if(bytes <= cap) return;
   if(p) cudaFree(p);
@@ -103,16 +105,16 @@ static void scan_impl(System & s, const T * in, T * out, int64_t n, int depth) {
   }
   int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
   if(nb == 1) {
-    k_scan_final<T><<<1, SCAN_NT, 0, s.stream>>>(in, out, nullptr, n);
+    FSPH_LAUNCH((k_scan_final<T>), 1, SCAN_NT, s.stream, in, out, nullptr, n);
     return;
   }
   if(depth > 2) throw std::runtime_error("scan recursion too deep");
   DevBuf & b = s.b_tmp[3 + depth];
   b.reserve((nb + 1) * sizeof(T));
   T * bs = b.as<T>();
-  k_scan_reduce<T><<<(unsigned)nb, SCAN_NT, 0, s.stream>>>(in, bs, n);
+  FSPH_LAUNCH((k_scan_reduce<T>), (unsigned)nb, SCAN_NT, s.stream, in, bs, n);
   scan_impl<T>(s, bs, bs, nb, depth + 1);
-  k_scan_final<T><<<(unsigned)nb, SCAN_NT, 0, s.stream>>>(in, out, bs, n);
+  FSPH_LAUNCH((k_scan_final<T>), (unsigned)nb, SCAN_NT, s.stream, in, out, bs, n);
 }
 
 // out has n+1 entries: out[n] = total.  In-place (in == out) is allowed.
@@ -212,11 +214,11 @@ static void radix_pass_mode(System & s, const uint64_t * kin, const uint32_t * v
   int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
   s.b_tmp[2].reserve(((size_t)256 * ntiles + 1) * sizeof(uint32_t));
   uint32_t * th = s.b_tmp[2].as<uint32_t>();
-  k_radix_count<<<ntiles, RS_NT, 0, s.stream>>>(kin, n, shift, th, ntiles);
+  FSPH_LAUNCH(k_radix_count, ntiles, RS_NT, s.stream, kin, n, shift, th, ntiles);
   exclusive_scan_u32(s, th, th, (int64_t)256 * ntiles, nullptr);
-  if(vmode == 0) k_radix_scatter<0><<<ntiles, RS_NT, 0, s.stream>>>(kin, vin, kout, vout, n, shift, th, ntiles);
-  else if(vmode == 1) k_radix_scatter<1><<<ntiles, RS_NT, 0, s.stream>>>(kin, vin, kout, vout, n, shift, th, ntiles);
-  else k_radix_scatter<2><<<ntiles, RS_NT, 0, s.stream>>>(kin, vin, kout, vout, n, shift, th, ntiles);
+  if(vmode == 0) FSPH_LAUNCH((k_radix_scatter<0>), ntiles, RS_NT, s.stream, kin, vin, kout, vout, n, shift, th, ntiles);
+  else if(vmode == 1) FSPH_LAUNCH((k_radix_scatter<1>), ntiles, RS_NT, s.stream, kin, vin, kout, vout, n, shift, th, ntiles);
+  else FSPH_LAUNCH((k_radix_scatter<2>), ntiles, RS_NT, s.stream, kin, vin, kout, vout, n, shift, th, ntiles);
   FSPH_CUDA_OK(cudaGetLastError());
 }
 
@@ -231,7 +233,7 @@ void radix_sort_pairs(System & s, uint64_t *& k0, uint32_t *& v0, uint64_t *& k1
   uint32_t * hist = s.b_tmp[1].as<uint32_t>();
   FSPH_CUDA_OK(cudaMemsetAsync(hist, 0, 8 * 256 * sizeof(uint32_t), s.stream));
   int nb = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
-  k_hist_all<<<nb, 256, 0, s.stream>>>(k0, n, hist);
+  FSPH_LAUNCH(k_hist_all, nb, 256, s.stream, k0, n, hist);
   std::vector<uint32_t> h(8 * 256);
   FSPH_CUDA_OK(cudaMemcpyAsync(h.data(), hist, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
   FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));

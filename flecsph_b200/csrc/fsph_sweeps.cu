@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256) k_fill(double * p, int64_t n, double v) {
 
 template<int D, int K, int OP>
 static void launch_sweep(System & s) {
-  k_sweep<D, K, OP><<<s.search.nwc, SW_NT, 0, s.stream>>>(s.tree, s.cols(), s.search, s.phys(), s.b_status.as<uint32_t>());
+  FSPH_LAUNCH((k_sweep<D, K, OP>), s.search.nwc, SW_NT, s.stream, s.tree, s.cols(), s.search, s.phys(), s.b_status.as<uint32_t>());
 }
 
 template<int D, int K>
@@ -344,7 +344,7 @@ static void sweep_dk(System & s, int op) {
     case FSPH_SWEEP_ACCELERATION: launch_sweep<D, K, OP_ACC>(s); break;
     case FSPH_SWEEP_DUDT:
       if(s.iteration < s.par.relaxation_steps)
-        k_fill<<<(unsigned)((s.n + 255) / 256), 256, 0, s.stream>>>(s.col[F_DUDT].as<double>(), s.n, 0.0);
+        FSPH_LAUNCH(k_fill, (unsigned)((s.n + 255) / 256), 256, s.stream, s.col[F_DUDT].as<double>(), s.n, 0.0);
       else launch_sweep<D, K, OP_DUDT>(s);
       break;
     case FSPH_SWEEP_DEDT: launch_sweep<D, K, OP_DEDT>(s); break;

@@ -82,8 +82,8 @@ static void compute_range_t(System & s) {
   int nb = (int)std::min<int64_t>((s.n + 255) / 256, 148 * 4);
   double * part = reduce_scratch(s, (size_t)(nb + 1) * 2 * D + 16);
   double * out = part + (size_t)nb * 2 * D;
-  k_range_partial<D><<<nb, 256, 0, s.stream>>>(s.cols(), s.n, part);
-  k_range_final<D><<<1, 32, 0, s.stream>>>(part, nb, out);
+  FSPH_LAUNCH((k_range_partial<D>), nb, 256, s.stream, s.cols(), s.n, part);
+  FSPH_LAUNCH((k_range_final<D>), 1, 32, s.stream, part, nb, out);
   double h[2 * D];
   FSPH_CUDA_OK(cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, s.stream));
   FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
@@ -133,9 +133,9 @@ void compute_keys(System & s) {
   Range3 r;
   for(int d = 0; d < 3; ++d) { r.lo[d] = s.lo[d]; r.hi[d] = s.hi[d]; }
   unsigned nb = (unsigned)((s.n + 255) / 256);
-  if(s.dim == 1) k_keys<1><<<nb, 256, 0, s.stream>>>(s.cols(), s.n, r);
-  else if(s.dim == 2) k_keys<2><<<nb, 256, 0, s.stream>>>(s.cols(), s.n, r);
-  else k_keys<3><<<nb, 256, 0, s.stream>>>(s.cols(), s.n, r);
+  if(s.dim == 1) FSPH_LAUNCH((k_keys<1>), nb, 256, s.stream, s.cols(), s.n, r);
+  else if(s.dim == 2) FSPH_LAUNCH((k_keys<2>), nb, 256, s.stream, s.cols(), s.n, r);
+  else FSPH_LAUNCH((k_keys<3>), nb, 256, s.stream, s.cols(), s.n, r);
   FSPH_CUDA_OK(cudaGetLastError());
 }
 
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256) k_is_identity(const uint32_t * __restrict
 static void gather8(System & s, DevBuf & colbuf, const uint32_t * perm) {
   s.scratch_col.reserve((size_t)s.n * 8);
   unsigned nb = (unsigned)((s.n + 255) / 256);
-  k_gather<uint64_t><<<nb, 256, 0, s.stream>>>(colbuf.as<uint64_t>(), s.scratch_col.as<uint64_t>(), perm, s.n);
+  FSPH_LAUNCH((k_gather<uint64_t>), nb, 256, s.stream, colbuf.as<uint64_t>(), s.scratch_col.as<uint64_t>(), perm, s.n);
   std::swap(colbuf.p, s.scratch_col.p);
   std::swap(colbuf.cap, s.scratch_col.cap);
 }
@@ -178,7 +178,7 @@ void sort_bodies(System & s) {
   uint32_t * flag = s.b_status.as<uint32_t>() + 1;
   FSPH_CUDA_OK(cudaMemsetAsync(flag, 0, 4, s.stream));
   unsigned nb = (unsigned)((n + 255) / 256);
-  k_is_identity<<<nb, 256, 0, s.stream>>>(perm, n, flag);
+  FSPH_LAUNCH(k_is_identity, nb, 256, s.stream, perm, n, flag);
   uint32_t moved = 0;
   FSPH_CUDA_OK(cudaMemcpyAsync(&moved, flag, 4, cudaMemcpyDeviceToHost, s.stream));
   FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
@@ -190,7 +190,7 @@ void sort_bodies(System & s) {
     gather8(s, s.col_id, perm);
     gather8(s, s.col_key, perm);
     s.b_tmp[0].reserve((size_t)n * 4);
-    k_gather<uint32_t><<<nb, 256, 0, s.stream>>>(s.col_type.as<uint32_t>(), s.b_tmp[0].as<uint32_t>(), perm, n);
+    FSPH_LAUNCH((k_gather<uint32_t>), nb, 256, s.stream, s.col_type.as<uint32_t>(), s.b_tmp[0].as<uint32_t>(), perm, n);
     std::swap(s.col_type.p, s.b_tmp[0].p);
     std::swap(s.col_type.cap, s.b_tmp[0].cap);
   }
@@ -382,8 +382,8 @@ static void build_tree_t(System & s) {
   s.b_cnt0.reserve((size_t)(n + 1) * sizeof(uint32_t));
   int8_t * lcp = s.b_tmp[0].as<int8_t>();
   uint32_t * cnt = s.b_cnt0.as<uint32_t>();
-  k_lcp<D><<<nbp, 256, 0, s.stream>>>(s.col_key.as<uint64_t>(), n, lcp, status);
-  k_cell_count<<<nbp, 256, 0, s.stream>>>(lcp, n, cnt);
+  FSPH_LAUNCH((k_lcp<D>), nbp, 256, s.stream, s.col_key.as<uint64_t>(), n, lcp, status);
+  FSPH_LAUNCH(k_cell_count, nbp, 256, s.stream, lcp, n, cnt);
   exclusive_scan_u32(s, cnt, cnt, n, nullptr);
   uint32_t h2[2];
   FSPH_CUDA_OK(cudaMemcpyAsync(&h2[0], cnt + n, 4, cudaMemcpyDeviceToHost, s.stream));
@@ -397,14 +397,14 @@ static void build_tree_t(System & s) {
   s.b_cell_desc2.reserve((size_t)nc * 8);
   uint64_t * desc0 = s.b_cell_desc2.as<uint64_t>();
   uint64_t * desc = s.b_cell_desc.as<uint64_t>();
-  k_cell_emit<<<nbp, 256, 0, s.stream>>>(lcp, n, cnt, desc0);
+  FSPH_LAUNCH(k_cell_emit, nbp, 256, s.stream, lcp, n, cnt, desc0);
   radix_pass(s, desc0, nullptr, desc, nullptr, nc, 32);  // stable counting sort by depth -> level order
   // flags + scan (node rank in the low word, number of first-children in the high word)
   uint64_t * flags = desc0;  // reuse
   s.b_cnt1.reserve((size_t)(nc + 1) * 8);
   uint64_t * ex = s.b_cnt1.as<uint64_t>();
   unsigned nbc = (unsigned)((nc + 255) / 256);
-  k_cell_flags<D><<<nbc, 256, 0, s.stream>>>(desc, nc, s.col_key.as<uint64_t>(), flags);
+  FSPH_LAUNCH((k_cell_flags<D>), nbc, 256, s.stream, desc, nc, s.col_key.as<uint64_t>(), flags);
   exclusive_scan_u64(s, flags, ex, nc, nullptr);
   // allocate the tables
   s.b_cell.reserve((size_t)nc * 4);
@@ -424,7 +424,7 @@ static void build_tree_t(System & s) {
   s.b_levels.reserve(MAX_LEVELS * sizeof(int32_t));
   int32_t * lv = s.b_levels.as<int32_t>();
   FSPH_CUDA_OK(cudaMemsetAsync(lv, 0xff, MAX_LEVELS * sizeof(int32_t), s.stream));
-  k_cell_link<<<nbc, 256, 0, s.stream>>>(desc, flags, ex, nc, t, lv);
+  FSPH_LAUNCH(k_cell_link, nbc, 256, s.stream, desc, flags, ex, nc, t, lv);
   int32_t hl[MAX_LEVELS];
   FSPH_CUDA_OK(cudaMemcpyAsync(hl, lv, sizeof(hl), cudaMemcpyDeviceToHost, s.stream));
   FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
@@ -438,7 +438,7 @@ static void build_tree_t(System & s) {
   for(int k = maxlev; k >= 0; --k) {
     int b = s.level_node_begin[k], e = s.level_node_begin[k + 1];
     if(e <= b) continue;
-    k_cofm<D><<<(e - b + 127) / 128, 128, 0, s.stream>>>(t, s.cols(), b, e);
+    FSPH_LAUNCH((k_cofm<D>), (e - b + 127) / 128, 128, s.stream, t, s.cols(), b, e);
   }
   FSPH_CUDA_OK(cudaGetLastError());
 }
@@ -485,9 +485,9 @@ void find_work_cells(System & s) {
   uint32_t * wc_at = s.b_cnt0.as<uint32_t>();
   uint32_t * ex = s.b_tmp[0].as<uint32_t>();
   FSPH_CUDA_OK(cudaMemsetAsync(wc_at, 0, (size_t)n * 4, s.stream));
-  k_wc_mark<<<(unsigned)((nc + 255) / 256), 256, 0, s.stream>>>(s.tree, nc, wc_at);
+  FSPH_LAUNCH(k_wc_mark, (unsigned)((nc + 255) / 256), 256, s.stream, s.tree, nc, wc_at);
   unsigned nbp = (unsigned)((n + 255) / 256);
-  k_flag_nonzero<<<nbp, 256, 0, s.stream>>>(wc_at, ex, n);
+  FSPH_LAUNCH(k_flag_nonzero, nbp, 256, s.stream, wc_at, ex, n);
   exclusive_scan_u32(s, ex, ex, n, nullptr);
   uint32_t nwc = 0;
   FSPH_CUDA_OK(cudaMemcpyAsync(&nwc, ex + n, 4, cudaMemcpyDeviceToHost, s.stream));
@@ -495,7 +495,7 @@ void find_work_cells(System & s) {
   s.b_wc_cell.reserve((size_t)std::max<uint32_t>(nwc, 1) * 4);
   s.search.wc_cell = s.b_wc_cell.as<int32_t>();
   s.search.nwc = (int)nwc;
-  k_wc_compact<<<nbp, 256, 0, s.stream>>>(wc_at, ex, n, s.search.wc_cell);
+  FSPH_LAUNCH(k_wc_compact, nbp, 256, s.stream, wc_at, ex, n, s.search.wc_cell);
   FSPH_CUDA_OK(cudaGetLastError());
 }
 

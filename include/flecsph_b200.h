@@ -168,6 +168,10 @@ int32_t fsph_resize(fsph_system * s, int64_t n);
 int64_t fsph_nbodies(const fsph_system * s);                      /* bodies_system.h:349 */
 int32_t fsph_set_column(fsph_system * s, int32_t col, const void * host);
 int32_t fsph_get_column(fsph_system * s, int32_t col, void * host);
+/* One contiguous component of a column ([n] values; comp = 0 for scalar columns): the zero-staging path the
+ * C++ facade uses for SoA host buffers (pinned memory makes it a straight DMA). */
+int32_t fsph_set_component(fsph_system * s, int32_t col, int32_t comp, const void * host);
+int32_t fsph_get_component(fsph_system * s, int32_t col, int32_t comp, void * host);
 /* AoS marshalling of the reference's 368-byte `body` records: offsets[col]
  * is offsetof(body, field) obtained in the C++ facade, -1 to skip a column. */
 int32_t fsph_upload_aos(fsph_system * s, const void * bodies, int64_t n, int64_t stride, const int64_t * offsets);
@@ -211,6 +215,9 @@ int32_t fsph_neighbor_lists(fsph_system * s, int64_t * offsets, int64_t * ids);
 /* Per-phase device times of the last fsph_step in milliseconds (CUDA events);
  * names is a ';'-separated list, returns the number of phases. */
 int32_t fsph_phase_times(fsph_system * s, double * ms, int32_t cap, const char ** names);
+
+/* Number of device kernels this library has launched in the calling process (0 for the CPU checkers). */
+uint64_t fsph_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -269,6 +269,21 @@ fsph_get_column(fsph_system * s, int32_t col, void * host) {
 }
 
 int32_t
+fsph_set_component(fsph_system * s, int32_t, int32_t, const void *) {
+  s->err = "component transfers are a product-library entry point";
+  return 1;
+}
+int32_t
+fsph_get_component(fsph_system * s, int32_t, int32_t, void *) {
+  s->err = "component transfers are a product-library entry point";
+  return 1;
+}
+uint64_t
+fsph_launch_count(void) {
+  return 0;
+}
+
+int32_t
 fsph_upload_aos(fsph_system * s, const void *, int64_t, int64_t, const int64_t *) {
   s->err = "AoS marshalling is a product-library entry point";
   return 1;

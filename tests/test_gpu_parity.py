@@ -119,6 +119,7 @@ def test_large_properties():
     t = G.tree_nodes()
     assert t["key"][0] == 1 and t["sub_entities"][0] == n
     assert abs(t["mass"][0] - f["mass"].sum()) <= 1e-12 * f["mass"].sum()
+    G.apply_all(capi.APPLY_SET_TOTAL_ENERGY)
     G.apply_in_smoothinglength(capi.SWEEP_DENSITY)
     nn = G.get(capi.COL_NNEIGH)
     pos, h = G.get(capi.COL_POS), G.get(capi.COL_H)
