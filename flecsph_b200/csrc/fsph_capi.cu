@@ -256,8 +256,8 @@ fsph_system * fsph_create(const fsph_params * p, int32_t device) {
     s->kernel_width = (p->sph_kernel == FSPH_KERNEL_QUINTIC_SPLINE || p->sph_kernel == FSPH_KERNEL_GAUSSIAN ||
                        p->sph_kernel == FSPH_KERNEL_SUPER_GAUSSIAN) ? 3.0 : 2.0;
     FSPH_CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    s->b_status.reserve(64);
-    FSPH_CUDA_OK(cudaMemsetAsync(s->b_status.p, 0, 64, s->stream));
+    s->b_status.reserve(128);
+    FSPH_CUDA_OK(cudaMemsetAsync(s->b_status.p, 0, 128, s->stream));
     FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
     return s;
   }
@@ -275,7 +275,7 @@ void fsph_destroy(fsph_system * s) {
   DevBuf * all[] = {&s->col_id, &s->col_key, &s->col_type, &s->col_nneigh, &s->scratch_col, &s->b_perm, &s->b_keys2, &s->b_perm2,
     &s->b_cell, &s->b_cell_parent, &s->b_cell_desc, &s->b_cell_desc2, &s->b_child_begin, &s->b_child_end, &s->b_node_start,
     &s->b_node_depth, &s->b_sub, &s->b_nmass, &s->b_nradius, &s->b_nlap, &s->b_wc_cell, &s->b_cand_off, &s->b_mask_off, &s->b_cand,
-    &s->b_mask, &s->b_cnt0, &s->b_cnt1, &s->b_status, &s->b_red, &s->b_levels};
+    &s->b_mask, &s->b_cnt0, &s->b_cnt1, &s->b_status, &s->b_red, &s->b_levels, &s->b_ncand, &s->b_search_scratch};
   for(DevBuf * b : all) b->release();
   for(int f = 0; f < NF64; ++f) s->col[f].release();
   for(int i = 0; i < 6; ++i) s->b_tmp[i].release();

@@ -27,7 +27,7 @@ constexpr int MAX_LEVELS = 66;
 // error bits latched on the device (surfaced at the next call boundary)
 enum ErrBits {
   ERR_DUP_KEYS = 1, ERR_RHO_NONPOS = 2, ERR_U_NONPOS = 4, ERR_NAN = 8, ERR_NEGATIVE = 16, ERR_QUEUE_OVERFLOW = 32,
-  ERR_DT_LOOP = 64, ERR_RANGE = 128
+  ERR_DT_LOOP = 64, ERR_RANGE = 128, ERR_SEARCH_CAPACITY = 256
 };
 
 struct DevBuf {
@@ -69,11 +69,15 @@ struct Tree {
 
 struct Search {
   int32_t * wc_cell;     // work cells in Morton order: index into Tree::cell
+  int32_t * ncand;       // [nwc] number of candidates of each work cell
   uint64_t * cand_off;   // [nwc+1] offsets into cand
   uint64_t * mask_off;   // [nwc+1] offsets into mask (32-bit words)
   int32_t * cand;        // candidate particle indices
   uint32_t * mask;       // per work cell: [ceil(C/32)][Ppad] words, bit b of word (w,k): candidate 32w+b is a neighbour of particle k
   int32_t nwc;
+  // work cells are grouped by size class (ceil(P/32) = 1..4 warps) so that every warp of a CTA owns live
+  // particles; within a class they stay in Morton order.  class c occupies [class_off[c], class_off[c+1]).
+  int32_t class_off[5];
 };
 
 struct PhysParams {
@@ -107,7 +111,9 @@ struct System {
   DevBuf b_cell, b_cell_parent, b_cell_desc, b_cell_desc2, b_child_begin, b_child_end, b_node_start, b_node_depth, b_sub;
   DevBuf b_nmass, b_ncom[3], b_nradius, b_nlap, b_nbmin[3], b_nbmax[3];
   DevBuf b_wc_cell, b_cand_off, b_mask_off, b_cand, b_mask, b_cnt0, b_cnt1;
-  DevBuf b_status, b_red, b_levels;
+  DevBuf b_status, b_red, b_levels, b_ncand, b_search_scratch;
+  unsigned long long est_cand = 0, est_mask = 0;  // sizes of the previous neighbour structure (capacity estimate)
+  int64_t est_n = 0;
   void * h_pinned = nullptr;  // small pinned staging (4 KB)
   Tree tree;
   Search search;

@@ -19,7 +19,7 @@
 
 namespace fsph {
 
-constexpr int SR_NT = 64;       // threads per CTA; each thread owns particles tid and tid + 64 of the work cell
+constexpr int SR_NT = 64;       // threads per CTA of the export kernel
 constexpr int SR_QCAP = 1024;   // node frontier capacity per level
 constexpr int SR_TILE = 512;    // candidates per shared-memory tile
 constexpr double GEO_TOL = 2.220446049250313e-16 * 10.;  // tree_geometry.h:57
@@ -89,243 +89,278 @@ __device__ __forceinline__ WorkCell load_work_cell(const Tree & t, const Search 
   return w;
 }
 
-template<int D, bool FILL>
-__global__ void __launch_bounds__(SR_NT) k_search(Tree t, Cols c, Search sr, uint64_t * __restrict__ ncand,
-  uint64_t * __restrict__ nwords, uint32_t * __restrict__ status) {
-  __shared__ double gx[D][SUB_ENTITIES];
-  __shared__ double gh[SUB_ENTITIES];
+// MODE 0: count candidates only (exact sizes for the two-pass path)
+// MODE 1: fill with offsets from a prefix sum over the counts of MODE 0 (deterministic layout)
+// MODE 2: single pass: persistent CTAs, candidates go to a per-CTA scratch strip during the walk, then the
+//         CTA reserves its exact share of the candidate / mask arrays with one atomicAdd each (capacity is
+//         estimated from the previous step; on overflow the host falls back to MODE 0 + 1)
+template<int D, int NW, int MODE>
+__global__ void __launch_bounds__(32 * NW) k_search(Tree t, Cols c, Search sr, int g_begin, int g_end, int32_t * __restrict__ scratch,
+  int scratch_cap, unsigned long long * __restrict__ cursors, unsigned long long cand_cap, unsigned long long mask_cap,
+  uint32_t * __restrict__ status) {
+  constexpr int NT = 32 * NW;
+  constexpr bool FILL = MODE != 0;
+  __shared__ double gx[D][32 * NW];
+  __shared__ double gh[32 * NW];
   __shared__ int32_t queue[2][SR_QCAP];
-  __shared__ uint32_t scan_sm[SR_NT / 32];
-  __shared__ double red_sm[SR_NT / 32][2 * D + 1];
+  __shared__ uint32_t scan_sm[NW];
+  __shared__ double red_sm[NW][2 * D + 1];
+  __shared__ unsigned long long base_sm[2];
   __shared__ double cx[FILL ? D : 1][FILL ? SR_TILE : 1];
   __shared__ double ch2[FILL ? SR_TILE : 1];
 
-  const int g = blockIdx.x, tid = threadIdx.x;
-  const WorkCell wc = load_work_cell(t, sr, g);
-  const int P = wc.P, gnode = wc.gnode;
-  for(int k = tid; k < P; k += SR_NT) {
-#pragma unroll
-    for(int d = 0; d < D; ++d) gx[d][k] = c.f[F_POS + d][wc.start + k];
-    gh[k] = c.f[F_H][wc.start + k];
-  }
-  double gmn[D], gmx[D], gcom[D], glap = 0.0, grad = 0.0;
-  if(gnode >= 0) {
-#pragma unroll
-    for(int d = 0; d < D; ++d) { gmn[d] = t.bmin[d][gnode]; gmx[d] = t.bmax[d][gnode]; gcom[d] = t.com[d][gnode]; }
-    glap = t.lap[gnode];
-    grad = t.radius[gnode];
-  }
-  const uint64_t cbase = FILL ? sr.cand_off[g] : 0;
-  if(tid == 0) queue[0][0] = 0;  // the root node
-  __syncthreads();
-  // Tight box of G's positions and max h: an extra, conservative candidate cull (it only drops leaves that
-  // cannot satisfy the pair predicate for any particle of G, so the neighbour sets are unchanged).
-  double tmn[D], tmx[D], ghmax = 0.0;
-  {
-#pragma unroll
-    for(int d = 0; d < D; ++d) { tmn[d] = 1.79769313486231570e308; tmx[d] = -1.79769313486231570e308; }
-    for(int k = tid; k < P; k += SR_NT) {
-#pragma unroll
-      for(int d = 0; d < D; ++d) { tmn[d] = fmin(tmn[d], gx[d][k]); tmx[d] = fmax(tmx[d], gx[d][k]); }
-      ghmax = fmax(ghmax, gh[k]);
-    }
-#pragma unroll
-    for(int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for(int d = 0; d < D; ++d) {
-        tmn[d] = fmin(tmn[d], __shfl_xor_sync(0xffffffffu, tmn[d], o));
-        tmx[d] = fmax(tmx[d], __shfl_xor_sync(0xffffffffu, tmx[d], o));
-      }
-      ghmax = fmax(ghmax, __shfl_xor_sync(0xffffffffu, ghmax, o));
-    }
-    if((tid & 31) == 0) {
-#pragma unroll
-      for(int d = 0; d < D; ++d) { red_sm[tid >> 5][d] = tmn[d]; red_sm[tid >> 5][D + d] = tmx[d]; }
-      red_sm[tid >> 5][2 * D] = ghmax;
-    }
+  const int tid = threadIdx.x;
+  for(int g = g_begin + blockIdx.x; g < g_end; g += gridDim.x) {
+    const WorkCell wc = load_work_cell(t, sr, g);
+    const int P = wc.P, gnode = wc.gnode;
     __syncthreads();
+    if(tid < P) {
 #pragma unroll
-    for(int d = 0; d < D; ++d) {
-      tmn[d] = fmin(red_sm[0][d], red_sm[1][d]);
-      tmx[d] = fmax(red_sm[0][D + d], red_sm[1][D + d]);
+      for(int d = 0; d < D; ++d) gx[d][tid] = c.f[F_POS + d][wc.start + tid];
+      gh[tid] = c.f[F_H][wc.start + tid];
     }
-    ghmax = fmax(red_sm[0][2 * D], red_sm[1][2 * D]);
-  }
-  int ncur = 1, cur = 0;
-  uint32_t ncands = 0;
-  while(ncur > 0) {
-    uint32_t nnext = 0;
-    for(int base = 0; base < ncur; base += SR_NT) {
-      const int j = base + tid;
-      uint32_t node_mask = 0, cand_mask = 0;
-      int cb = 0;
-      if(j < ncur) {
-        const int nd = queue[cur][j];
-        double mn[D], mx[D];
+    double gmn[D], gmx[D], gcom[D], glap = 0.0, grad = 0.0;
+    if(gnode >= 0) {
 #pragma unroll
-        for(int d = 0; d < D; ++d) { mn[d] = t.bmin[d][nd]; mx[d] = t.bmax[d][nd]; }
-        bool ok = true;
-        if(gnode >= 0) {
-          // intersects_box_box(c, G)
-          bool sep = false;
+      for(int d = 0; d < D; ++d) { gmn[d] = t.bmin[d][gnode]; gmx[d] = t.bmax[d][gnode]; gcom[d] = t.com[d][gnode]; }
+      glap = t.lap[gnode];
+      grad = t.radius[gnode];
+    }
+    int32_t * cout = MODE == 1 ? sr.cand + sr.cand_off[g] : (MODE == 2 ? scratch + (size_t)blockIdx.x * scratch_cap : nullptr);
+    if(tid == 0) queue[0][0] = 0;  // the root node
+    // Tight box of G's positions and max h: an extra, conservative candidate cull (it only drops leaves that
+    // cannot satisfy the pair predicate for any particle of G, so the neighbour sets are unchanged).
+    double tmn[D], tmx[D], ghmax = 0.0;
+    {
 #pragma unroll
-          for(int d = 0; d < D; ++d) sep = sep || (mx[d] < gmn[d]) || (gmx[d] < mn[d]);
-          ok = !sep;
+      for(int d = 0; d < D; ++d) { tmn[d] = 1.79769313486231570e308; tmx[d] = -1.79769313486231570e308; }
+      if(tid < P) {
+#pragma unroll
+        for(int d = 0; d < D; ++d) { tmn[d] = c.f[F_POS + d][wc.start + tid]; tmx[d] = tmn[d]; }
+        ghmax = c.f[F_H][wc.start + tid];
+      }
+#pragma unroll
+      for(int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for(int d = 0; d < D; ++d) {
+          tmn[d] = fmin(tmn[d], __shfl_xor_sync(0xffffffffu, tmn[d], o));
+          tmx[d] = fmax(tmx[d], __shfl_xor_sync(0xffffffffu, tmx[d], o));
         }
-        if(ok) {
-          bool acc = false;
-          for(int k = 0; k < P && !acc; ++k) {
-            double p[D];
+        ghmax = fmax(ghmax, __shfl_xor_sync(0xffffffffu, ghmax, o));
+      }
+      if((tid & 31) == 0) {
 #pragma unroll
-            for(int d = 0; d < D; ++d) p[d] = gx[d][k];
-            acc = sphere_box<D>(mn, mx, p, gh[k]);
+        for(int d = 0; d < D; ++d) { red_sm[tid >> 5][d] = tmn[d]; red_sm[tid >> 5][D + d] = tmx[d]; }
+        red_sm[tid >> 5][2 * D] = ghmax;
+      }
+      __syncthreads();
+#pragma unroll
+      for(int ww = 0; ww < NW; ++ww) {
+#pragma unroll
+        for(int d = 0; d < D; ++d) {
+          tmn[d] = fmin(tmn[d], red_sm[ww][d]);
+          tmx[d] = fmax(tmx[d], red_sm[ww][D + d]);
+        }
+        ghmax = fmax(ghmax, red_sm[ww][2 * D]);
+      }
+    }
+    int ncur = 1, cur = 0;
+    uint32_t ncands = 0;
+    bool overflow = false;
+    while(ncur > 0) {
+      uint32_t nnext = 0;
+      for(int base = 0; base < ncur; base += NT) {
+        const int j = base + tid;
+        uint32_t node_mask = 0, cand_mask = 0;
+        int cb = 0;
+        if(j < ncur) {
+          const int nd = queue[cur][j];
+          double mn[D], mx[D];
+#pragma unroll
+          for(int d = 0; d < D; ++d) { mn[d] = t.bmin[d][nd]; mx[d] = t.bmax[d][nd]; }
+          bool ok = true;
+          if(gnode >= 0) {
+            // intersects_box_box(c, G)
+            bool sep = false;
+#pragma unroll
+            for(int d = 0; d < D; ++d) sep = sep || (mx[d] < gmn[d]) || (gmx[d] < mn[d]);
+            ok = !sep;
           }
-          ok = acc;
-        }
-        if(ok) {
-          cb = t.child_begin[nd];
-          const int ce = t.child_end[nd];
-          for(int cc = cb; cc < ce; ++cc) {
-            const int v = t.cell[cc];
-            if(v < 0) node_mask |= 1u << (cc - cb);
-            else {
-              bool pass = true;
-              if(gnode >= 0) {
-                // |x_e - X_G|^2 <= (max(h_e, lap_G) + radius_G)^2, tree_topology.h:365-370
-                double ext = fmax(c.f[F_H][v], glap) + grad;
-                double s2 = 0.0;
+          if(ok) {
+            bool acc = false;
+            for(int k = 0; k < P && !acc; ++k) {
+              double p[D];
 #pragma unroll
-                for(int d = 0; d < D; ++d) {
-                  double df = c.f[F_POS + d][v] - gcom[d];
-                  s2 = d == 0 ? df * df : s2 + df * df;
-                }
-                pass = s2 <= ext * ext;
-              }
-              if(pass) {
-                const double hm = fmax(c.f[F_H][v], ghmax);
-                double dd = 0.0;
+              for(int d = 0; d < D; ++d) p[d] = gx[d][k];
+              acc = sphere_box<D>(mn, mx, p, gh[k]);
+            }
+            ok = acc;
+          }
+          if(ok) {
+            cb = t.child_begin[nd];
+            const int ce = t.child_end[nd];
+            for(int cc = cb; cc < ce; ++cc) {
+              const int v = t.cell[cc];
+              if(v < 0) node_mask |= 1u << (cc - cb);
+              else {
+                bool pass = true;
+                const double he = c.f[F_H][v];
+                double xe[D];
 #pragma unroll
-                for(int d = 0; d < D; ++d) {
-                  const double x = c.f[F_POS + d][v];
-                  const double tt = fmax(0.0, fmax(tmn[d] - x, x - tmx[d]));
-                  dd = dd + tt * tt;
+                for(int d = 0; d < D; ++d) xe[d] = c.f[F_POS + d][v];
+                if(gnode >= 0) {
+                  // |x_e - X_G|^2 <= (max(h_e, lap_G) + radius_G)^2, tree_topology.h:365-370
+                  const double ext = fmax(he, glap) + grad;
+                  double s2 = 0.0;
+#pragma unroll
+                  for(int d = 0; d < D; ++d) {
+                    const double df = xe[d] - gcom[d];
+                    s2 = d == 0 ? df * df : s2 + df * df;
+                  }
+                  pass = s2 <= ext * ext;
                 }
-                pass = dd <= hm * hm * (1.0 + 1e-9);
+                if(pass) {
+                  const double hm = fmax(he, ghmax);
+                  double dd = 0.0;
+#pragma unroll
+                  for(int d = 0; d < D; ++d) {
+                    const double tt = fmax(0.0, fmax(tmn[d] - xe[d], xe[d] - tmx[d]));
+                    dd = dd + tt * tt;
+                  }
+                  pass = dd <= hm * hm * (1.0 + 1e-9);
+                }
+                if(pass) cand_mask |= 1u << (cc - cb);
               }
-              if(pass) cand_mask |= 1u << (cc - cb);
             }
           }
         }
-      }
-      uint32_t packed = (uint32_t)__popc(node_mask) | ((uint32_t)__popc(cand_mask) << 16);
-      uint32_t total;
-      uint32_t ex = block_scan_u32<SR_NT>(packed, total, scan_sm);
-      uint32_t qpos = nnext + (ex & 0xffffu), cpos = ncands + (ex >> 16);
-      while(node_mask) {
-        int b = __ffs(node_mask) - 1;
-        node_mask &= node_mask - 1;
-        if(qpos < SR_QCAP) queue[cur ^ 1][qpos] = ~t.cell[cb + b];
-        ++qpos;
-      }
-      if(FILL) {
-        while(cand_mask) {
-          int b = __ffs(cand_mask) - 1;
-          cand_mask &= cand_mask - 1;
-          sr.cand[cbase + cpos] = t.cell[cb + b];
-          ++cpos;
+        uint32_t packed = (uint32_t)__popc(node_mask) | ((uint32_t)__popc(cand_mask) << 16);
+        uint32_t total;
+        uint32_t ex = block_scan_u32<NT>(packed, total, scan_sm);
+        uint32_t qpos = nnext + (ex & 0xffffu), cpos = ncands + (ex >> 16);
+        while(node_mask) {
+          int b = __ffs(node_mask) - 1;
+          node_mask &= node_mask - 1;
+          if(qpos < SR_QCAP) queue[cur ^ 1][qpos] = ~t.cell[cb + b];
+          ++qpos;
         }
+        if(FILL) {
+          while(cand_mask) {
+            int b = __ffs(cand_mask) - 1;
+            cand_mask &= cand_mask - 1;
+            if(MODE == 1 || cpos < (uint32_t)scratch_cap) cout[cpos] = t.cell[cb + b];
+            ++cpos;
+          }
+        }
+        nnext += total & 0xffffu;
+        ncands += total >> 16;
       }
-      nnext += total & 0xffffu;
-      ncands += total >> 16;
+      if(nnext > SR_QCAP) {
+        if(tid == 0) atomicOr(status, (uint32_t)ERR_QUEUE_OVERFLOW);
+        nnext = SR_QCAP;
+      }
+      __syncthreads();
+      ncur = (int)nnext;
+      cur ^= 1;
     }
-    if(nnext > SR_QCAP) {
-      if(tid == 0) atomicOr(status, (uint32_t)ERR_QUEUE_OVERFLOW);
-      nnext = SR_QCAP;
+    const int Ppad = (P + 31) & ~31;
+    const uint64_t nwords = (uint64_t)((ncands + 31) / 32) * Ppad;
+    if(MODE == 0) {
+      if(tid == 0) {
+        sr.ncand[g] = (int32_t)ncands;
+        sr.cand_off[g] = ncands;
+        sr.mask_off[g] = nwords;
+      }
+      continue;
     }
-    __syncthreads();
-    ncur = (int)nnext;
-    cur ^= 1;
-  }
-  const int Ppad = (P + 31) & ~31;
-  if(!FILL) {
-    if(tid == 0) {
-      ncand[g] = ncands;
-      nwords[g] = (uint64_t)((ncands + 31) / 32) * Ppad;
+    uint64_t co, mo;
+    if(MODE == 2) {
+      if(ncands > (uint32_t)scratch_cap) overflow = true;
+      if(tid == 0) {
+        base_sm[0] = atomicAdd(&cursors[0], (unsigned long long)ncands);
+        base_sm[1] = atomicAdd(&cursors[1], (unsigned long long)nwords);
+      }
+      __syncthreads();
+      co = base_sm[0];
+      mo = base_sm[1];
+      if(co + ncands > cand_cap || mo + nwords > mask_cap) overflow = true;
+      if(overflow) {
+        if(tid == 0) atomicOr(status, (uint32_t)ERR_SEARCH_CAPACITY);
+        continue;
+      }
+      if(tid == 0) {
+        sr.ncand[g] = (int32_t)ncands;
+        sr.cand_off[g] = co;
+        sr.mask_off[g] = mo;
+      }
+      for(uint32_t i = tid; i < ncands; i += NT) sr.cand[co + i] = cout[i];
     }
-    return;
-  }
-  else {
+    else {
+      co = sr.cand_off[g];
+      mo = sr.mask_off[g];
+    }
     // ---- pair tests ------------------------------------------------------------------------------------
     const int C = (int)ncands;
-    const uint64_t mo = sr.mask_off[g];
-    const int k0 = tid, k1 = tid + SR_NT;
-    double a0[D], a1[D], h0 = 0.0, h1 = 0.0;
+    const bool active = tid < P;
+    double a0[D], h0 = 0.0;
 #pragma unroll
-    for(int d = 0; d < D; ++d) { a0[d] = k0 < P ? gx[d][k0] : 0.0; a1[d] = k1 < P ? gx[d][k1] : 0.0; }
-    if(k0 < P) { h0 = gh[k0]; h0 = h0 * h0; }
-    if(k1 < P) { h1 = gh[k1]; h1 = h1 * h1; }
-    int cnt0 = 0, cnt1 = 0;
-    const bool warp_has0 = (tid & ~31) < P, warp_has1 = ((tid & ~31) + SR_NT) < P;
+    for(int d = 0; d < D; ++d) a0[d] = active ? gx[d][tid] : 0.0;
+    if(active) { h0 = gh[tid]; h0 = h0 * h0; }
+    int cnt0 = 0;
     for(int tb = 0; tb < C; tb += SR_TILE) {
       const int tc = min(SR_TILE, C - tb);
       __syncthreads();
-      for(int i = tid; i < tc; i += SR_NT) {
-        const int p = sr.cand[cbase + tb + i];
+      for(int i = tid; i < tc; i += NT) {
+        const int p = MODE == 2 ? cout[tb + i] : sr.cand[co + tb + i];
 #pragma unroll
         for(int d = 0; d < D; ++d) cx[d][i] = c.f[F_POS + d][p];
         const double hh = c.f[F_H][p];
         ch2[i] = hh * hh;
       }
       __syncthreads();
+      if(!active) continue;
       const int nw = (tc + 31) >> 5;
       for(int w = 0; w < nw; ++w) {
         const int nb = min(32, tc - w * 32);
-        const uint64_t wo = mo + (uint64_t)((tb >> 5) + w) * Ppad;
         // within_distance2(x_k, x_e, max(h_k, h_e)): max(h_k,h_e)^2 == max(h_k^2,h_e^2) exactly (rounding is monotonic)
-        if(warp_has1) {
-          uint32_t m0 = 0, m1 = 0;
-#pragma unroll 4
-          for(int b = 0; b < nb; ++b) {
-            const int ci = w * 32 + b;
-            const double eh2 = ch2[ci];
-            double e0 = cx[0][ci];
-            double s0 = (a0[0] - e0) * (a0[0] - e0);
-            double s1 = (a1[0] - e0) * (a1[0] - e0);
+        uint32_t m0 = 0;
+#pragma unroll 8
+        for(int b = 0; b < nb; ++b) {
+          const int ci = w * 32 + b;
+          const double e0 = cx[0][ci];
+          double s0 = (a0[0] - e0) * (a0[0] - e0);
 #pragma unroll
-            for(int d = 1; d < D; ++d) {
-              const double ed = cx[d][ci];
-              s0 = s0 + (a0[d] - ed) * (a0[d] - ed);
-              s1 = s1 + (a1[d] - ed) * (a1[d] - ed);
-            }
-            m0 |= (uint32_t)(s0 <= fmax(h0, eh2)) << b;
-            m1 |= (uint32_t)(s1 <= fmax(h1, eh2)) << b;
+          for(int d = 1; d < D; ++d) {
+            const double ed = cx[d][ci];
+            s0 = s0 + (a0[d] - ed) * (a0[d] - ed);
           }
-          sr.mask[wo + k0] = m0;
-          cnt0 += __popc(m0);
-          if(k1 < P) { sr.mask[wo + k1] = m1; cnt1 += __popc(m1); }
+          m0 |= (uint32_t)(s0 <= fmax(h0, ch2[ci])) << b;
         }
-        else if(warp_has0) {
-          uint32_t m0 = 0;
-#pragma unroll 4
-          for(int b = 0; b < nb; ++b) {
-            const int ci = w * 32 + b;
-            const double eh2 = ch2[ci];
-            double e0 = cx[0][ci];
-            double s0 = (a0[0] - e0) * (a0[0] - e0);
-#pragma unroll
-            for(int d = 1; d < D; ++d) {
-              const double ed = cx[d][ci];
-              s0 = s0 + (a0[d] - ed) * (a0[d] - ed);
-            }
-            m0 |= (uint32_t)(s0 <= fmax(h0, eh2)) << b;
-          }
-          if(k0 < P) { sr.mask[wo + k0] = m0; cnt0 += __popc(m0); }
-        }
+        sr.mask[mo + (uint64_t)((tb >> 5) + w) * Ppad + tid] = m0;
+        cnt0 += __popc(m0);
       }
     }
-    if(k0 < P) c.nneigh[wc.start + k0] = cnt0;
-    if(k1 < P) c.nneigh[wc.start + k1] = cnt1;
+    if(active) c.nneigh[wc.start + tid] = cnt0;
   }
+}
+
+template<int D, int MODE>
+static void launch_search(System & s, int32_t * scratch, int scratch_cap, int grid_cap, unsigned long long * cursors,
+  unsigned long long cand_cap, unsigned long long mask_cap) {
+  Search & sr = s.search;
+  uint32_t * status = s.b_status.as<uint32_t>();
+  for(int cls = 0; cls < 4; ++cls) {
+    const int b = sr.class_off[cls], e = sr.class_off[cls + 1];
+    if(e <= b) continue;
+    const int grid = MODE == 2 ? std::min(e - b, grid_cap) : e - b;
+    switch(cls) {
+      case 0: FSPH_LAUNCH((k_search<D, 1, MODE>), grid, 32, s.stream, s.tree, s.cols(), sr, b, e, scratch, scratch_cap, cursors, cand_cap, mask_cap, status); break;
+      case 1: FSPH_LAUNCH((k_search<D, 2, MODE>), grid, 64, s.stream, s.tree, s.cols(), sr, b, e, scratch, scratch_cap, cursors, cand_cap, mask_cap, status); break;
+      case 2: FSPH_LAUNCH((k_search<D, 3, MODE>), grid, 96, s.stream, s.tree, s.cols(), sr, b, e, scratch, scratch_cap, cursors, cand_cap, mask_cap, status); break;
+      default: FSPH_LAUNCH((k_search<D, 4, MODE>), grid, 128, s.stream, s.tree, s.cols(), sr, b, e, scratch, scratch_cap, cursors, cand_cap, mask_cap, status); break;
+    }
+  }
+  FSPH_CUDA_OK(cudaGetLastError());
 }
 
 template<int D>
@@ -336,9 +371,39 @@ static void neighbor_search_t(System & s) {
   uint32_t * status = s.b_status.as<uint32_t>();
   s.b_cand_off.reserve((size_t)(nwc + 1) * 8);
   s.b_mask_off.reserve((size_t)(nwc + 1) * 8);
+  s.b_ncand.reserve((size_t)(nwc + 1) * 4);
   sr.cand_off = s.b_cand_off.as<uint64_t>();
   sr.mask_off = s.b_mask_off.as<uint64_t>();
-  FSPH_LAUNCH((k_search<D, false>), nwc, SR_NT, s.stream, s.tree, s.cols(), sr, sr.cand_off, sr.mask_off, status);
+  sr.ncand = s.b_ncand.as<int32_t>();
+  unsigned long long * cursors = reinterpret_cast<unsigned long long *>(s.b_status.as<uint32_t>() + 8);
+  // single pass when the previous search on this system gives a capacity estimate
+  if(s.est_cand > 0 && s.est_n == s.n) {
+    const int grid_cap = 148 * 8, scratch_cap = 16384;
+    const unsigned long long cand_cap = s.est_cand + s.est_cand / 4 + 65536, mask_cap = s.est_mask + s.est_mask / 4 + 65536;
+    s.b_cand.reserve((size_t)cand_cap * 4);
+    s.b_mask.reserve((size_t)mask_cap * 4);
+    s.b_search_scratch.reserve((size_t)grid_cap * scratch_cap * 4);
+    sr.cand = s.b_cand.as<int32_t>();
+    sr.mask = s.b_mask.as<uint32_t>();
+    FSPH_CUDA_OK(cudaMemsetAsync(cursors, 0, 16, s.stream));
+    launch_search<D, 2>(s, s.b_search_scratch.as<int32_t>(), scratch_cap, grid_cap, cursors, cand_cap, mask_cap);
+    unsigned long long tot[2];
+    uint32_t st = 0;
+    FSPH_CUDA_OK(cudaMemcpyAsync(tot, cursors, 16, cudaMemcpyDeviceToHost, s.stream));
+    FSPH_CUDA_OK(cudaMemcpyAsync(&st, status, 4, cudaMemcpyDeviceToHost, s.stream));
+    FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
+    if(st & ERR_QUEUE_OVERFLOW) throw std::runtime_error("neighbour search: node frontier exceeds the shared-memory queue");
+    if(!(st & ERR_SEARCH_CAPACITY)) {
+      s.est_cand = tot[0];
+      s.est_mask = tot[1];
+      return;
+    }
+    // capacity estimate too small: clear the flag and fall through to the exact two-pass path
+    uint32_t cleared = st & ~(uint32_t)ERR_SEARCH_CAPACITY;
+    FSPH_CUDA_OK(cudaMemcpyAsync(status, &cleared, 4, cudaMemcpyHostToDevice, s.stream));
+    FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
+  }
+  launch_search<D, 0>(s, nullptr, 0, 0, nullptr, 0, 0);
   exclusive_scan_u64(s, sr.cand_off, sr.cand_off, nwc, nullptr);
   exclusive_scan_u64(s, sr.mask_off, sr.mask_off, nwc, nullptr);
   uint64_t tot[2];
@@ -352,8 +417,10 @@ static void neighbor_search_t(System & s) {
   s.b_mask.reserve((size_t)std::max<uint64_t>(tot[1], 1) * 4);
   sr.cand = s.b_cand.as<int32_t>();
   sr.mask = s.b_mask.as<uint32_t>();
-  FSPH_LAUNCH((k_search<D, true>), nwc, SR_NT, s.stream, s.tree, s.cols(), sr, nullptr, nullptr, status);
-  FSPH_CUDA_OK(cudaGetLastError());
+  launch_search<D, 1>(s, nullptr, 0, 0, nullptr, 0, 0);
+  s.est_cand = tot[0];
+  s.est_mask = tot[1];
+  s.est_n = s.n;
 }
 
 void neighbor_search(System & s) {
@@ -369,7 +436,7 @@ __global__ void __launch_bounds__(SR_NT) k_export(Tree t, Cols c, Search sr, con
   const WorkCell wc = load_work_cell(t, sr, g);
   const int Ppad = (wc.P + 31) & ~31;
   const uint64_t co = sr.cand_off[g], mo = sr.mask_off[g];
-  const int C = (int)(sr.cand_off[g + 1] - co);
+  const int C = sr.ncand[g];
   const int nw = (C + 31) >> 5;
   for(int k = threadIdx.x; k < wc.P; k += SR_NT) {
     uint64_t o = off[wc.start + k];

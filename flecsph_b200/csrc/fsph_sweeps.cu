@@ -18,7 +18,6 @@
 
 namespace fsph {
 
-constexpr int SW_NT = 128;
 constexpr int SW_TILE = 256;
 constexpr double TINY = 1e10 * DBL_MIN;  // kernels.h:64, viscosity.h:36
 constexpr double PI = 3.14159265358979323846;
@@ -26,26 +25,39 @@ constexpr double PI = 3.14159265358979323846;
 enum SweepOp { OP_DENSITY = 0, OP_ACC = 1, OP_DUDT = 2, OP_DEDT = 3, OP_VSIG = 5 };
 
 // ---- SPH kernels: value W(r,h) and the scalar F with grad W = r_ab * F ------------------------------------
-template<int D> __device__ __forceinline__ double powD(double h) { return D == 1 ? h : (D == 2 ? h * h : h * h * h); }
+
+template<int D> __device__ __forceinline__ double ipowD(double ih) { return D == 1 ? ih : (D == 2 ? ih * ih : ih * ih * ih); }
+// 1/h and 1/(r + TINY) from a single fp64 division
+__device__ __forceinline__ void inv_h_r(double h, double r, double & ih, double & ir) {
+  const double rt = r + TINY;
+  const double inv = 1.0 / (h * rt);
+  ih = inv * rt;
+  ir = inv * h;
+}
 
 template<int D, int K> struct SphKernel;
 
 template<int D> struct SphKernel<D, FSPH_KERNEL_CUBIC_SPLINE> {
   static __device__ __forceinline__ double sigma() { return D == 1 ? 4. / 3. : (D == 2 ? 40. / (7. * PI) : 8. / PI); }
   static __device__ __forceinline__ double W(double r, double h) {
-    double q = 2. * r / h, res = 0.;
+    const double ih = 1.0 / h;
+    const double q = 2. * r * ih;
+    double res = 0.;
     if(q < 2.0) {
       res = q < 1.0 ? 1.0 - 1.5 * q * q + .75 * q * q * q : 0.25 * (2 - q) * (2 - q) * (2 - q);
-      res *= sigma() / powD<D>(h);
+      res *= sigma() * ipowD<D>(ih);
     }
     return res;
   }
   static __device__ __forceinline__ double F(double r, double h) {
-    double q = 2. * r / h, res = 0.;
+    double ih, ir;
+    inv_h_r(h, r, ih, ir);
+    const double q = 2. * r * ih;
+    double res = 0.;
     if(q < 2.0) {
-      double sg = 2. * sigma() / (powD<D>(h) * h);
-      double dW = q < 1.0 ? -3.0 * q + 9. / 4. * q * q : -.75 * (2 - q) * (2 - q);
-      res = sg * dW / (r + TINY);
+      const double sg = 2. * sigma() * ipowD<D>(ih) * ih;
+      const double dW = q < 1.0 ? -3.0 * q + 9. / 4. * q * q : -.75 * (2 - q) * (2 - q);
+      res = sg * dW * ir;
     }
     return res;
   }
@@ -55,23 +67,28 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_QUINTIC_SPLINE> {
   static __device__ __forceinline__ double p5(double x) { double x2 = x * x; return x2 * x2 * x; }
   static __device__ __forceinline__ double p4(double x) { double x2 = x * x; return x2 * x2; }
   static __device__ __forceinline__ double W(double r, double h) {
-    double q = 3. * r / h, res = 0.;
+    const double ih = 1.0 / h;
+    const double q = 3. * r * ih;
+    double res = 0.;
     if(q < 3.) {
       res = p5(3 - q);
       if(q < 2.) res += -6 * p5(2 - q);
       if(q < 1.) res += 15 * p5(1 - q);
-      res *= sigma() / powD<D>(h);
+      res *= sigma() * ipowD<D>(ih);
     }
     return res;
   }
   static __device__ __forceinline__ double F(double r, double h) {
-    double q = 3. * r / h, res = 0.;
+    double ih, ir;
+    inv_h_r(h, r, ih, ir);
+    const double q = 3. * r * ih;
+    double res = 0.;
     if(q < 3.) {
-      double sg = 3. * sigma() / (powD<D>(h) * h);
+      const double sg = 3. * sigma() * ipowD<D>(ih) * ih;
       double dW = -5. * p4(3 - q);
       if(q < 2.) dW += 30. * p4(2 - q);
       if(q < 1.) dW += -75. * p4(1 - q);
-      res = sg * dW / (r + TINY);
+      res = sg * dW * ir;
     }
     return res;
   }
@@ -79,47 +96,56 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_QUINTIC_SPLINE> {
 template<int D> struct SphKernel<D, FSPH_KERNEL_WENDLAND_C2> {
   static __device__ __forceinline__ double sigma() { return D == 1 ? 1.25 : (D == 2 ? 7. / PI : 21. / (2. * PI)); }
   static __device__ __forceinline__ double W(double r, double h) {
-    double q = r / h, o = 1 - q, o2 = o * o;
-    double res = D == 1 ? sigma() / h * o2 * o * (3 * q + 1) : sigma() / powD<D>(h) * o2 * o2 * (4 * q + 1);
+    const double ih = 1.0 / h;
+    const double q = r * ih, o = 1 - q, o2 = o * o;
+    const double res = D == 1 ? sigma() * ih * o2 * o * (3 * q + 1) : sigma() * ipowD<D>(ih) * o2 * o2 * (4 * q + 1);
     return q < 1.0 ? res : 0.0;
   }
   static __device__ __forceinline__ double F(double r, double h) {
-    double q = r / h, o = 1 - q, o2 = o * o;
-    double sg = D == 1 ? sigma() / (h * h) : 2. * sigma() / (powD<D>(h) * h);
-    double dW = D == 1 ? -12. * q * o2 : -10. * q * o2 * o;
-    return q < 1.0 ? sg * dW / (r + TINY) : 0.0;
+    double ih, ir;
+    inv_h_r(h, r, ih, ir);
+    const double q = r * ih, o = 1 - q, o2 = o * o;
+    const double sg = D == 1 ? sigma() * ih * ih : 2. * sigma() * ipowD<D>(ih) * ih;
+    const double dW = D == 1 ? -12. * q * o2 : -10. * q * o2 * o;
+    return q < 1.0 ? sg * dW * ir : 0.0;
   }
 };
 template<int D> struct SphKernel<D, FSPH_KERNEL_WENDLAND_C4> {
   static __device__ __forceinline__ double sigma() { return D == 1 ? 1.5 : (D == 2 ? 9. / PI : 495. / (32. * PI)); }
   static __device__ __forceinline__ double W(double r, double h) {
-    double q = r / h, o = 1 - q, o2 = o * o;
+    const double ih = 1.0 / h;
+    const double q = r * ih, o = 1 - q, o2 = o * o;
     double res;
-    if(D == 1) res = sigma() / h * (o2 * o) * o2 * (1 + q * (5 + q * 8));
-    else res = sigma() / powD<D>(h) * (o2 * o2 * o2) * (1 + q * (6 + q * 35 / 3));
+    if(D == 1) res = sigma() * ih * (o2 * o) * o2 * (1 + q * (5 + q * 8));
+    else res = sigma() * ipowD<D>(ih) * (o2 * o2 * o2) * (1 + q * (6 + q * (35. / 3.)));
     return q < 1.0 ? res : 0.0;
   }
   static __device__ __forceinline__ double F(double r, double h) {
-    double q = r / h, o = 1 - q, o2 = o * o;
-    double sg = 14. * sigma() / (powD<D>(h) * h);
-    double dW = D == 1 ? -q * o2 * o2 * (1 + 4. * q) : -4. / 3. * q * (o2 * o) * o2 * (1 + 5. * q);
-    return q < 1.0 ? sg * dW / (r + TINY) : 0.0;
+    double ih, ir;
+    inv_h_r(h, r, ih, ir);
+    const double q = r * ih, o = 1 - q, o2 = o * o;
+    const double sg = 14. * sigma() * ipowD<D>(ih) * ih;
+    const double dW = D == 1 ? -q * o2 * o2 * (1 + 4. * q) : -4. / 3. * q * (o2 * o) * o2 * (1 + 5. * q);
+    return q < 1.0 ? sg * dW * ir : 0.0;
   }
 };
 template<int D> struct SphKernel<D, FSPH_KERNEL_WENDLAND_C6> {
   static __device__ __forceinline__ double sigma() { return D == 1 ? 55. / 32. : (D == 2 ? 78. / (7. * PI) : 1365. / (64. * PI)); }
   static __device__ __forceinline__ double W(double r, double h) {
-    double q = r / h, o = 1 - q, o2 = o * o, o4 = o2 * o2;
+    const double ih = 1.0 / h;
+    const double q = r * ih, o = 1 - q, o2 = o * o, o4 = o2 * o2;
     double res;
-    if(D == 1) res = sigma() / h * (o2 * o) * o4 * (1 + q * (7 + q * (19 + q * 21)));
-    else res = sigma() / powD<D>(h) * o4 * o4 * (1 + q * (8 + q * (25 + q * 32)));
+    if(D == 1) res = sigma() * ih * (o2 * o) * o4 * (1 + q * (7 + q * (19 + q * 21)));
+    else res = sigma() * ipowD<D>(ih) * o4 * o4 * (1 + q * (8 + q * (25 + q * 32)));
     return q < 1.0 ? res : 0.0;
   }
   static __device__ __forceinline__ double F(double r, double h) {
-    double q = r / h, o = 1 - q, o2 = o * o, o3 = o2 * o, o4 = o2 * o2;
-    double sg = sigma() / (powD<D>(h) * h);
-    double dW = D == 1 ? -6. * q * o3 * o3 * (3 + q * (18 + q * 35)) : -22. * q * o4 * o3 * (1 + q * (7 + q * 16));
-    return q < 1.0 ? sg * dW / (r + TINY) : 0.0;
+    double ih, ir;
+    inv_h_r(h, r, ih, ir);
+    const double q = r * ih, o = 1 - q, o2 = o * o, o3 = o2 * o, o4 = o2 * o2;
+    const double sg = sigma() * ipowD<D>(ih) * ih;
+    const double dW = D == 1 ? -6. * q * o3 * o3 * (3 + q * (18 + q * 35)) : -22. * q * o4 * o3 * (1 + q * (7 + q * 16));
+    return q < 1.0 ? sg * dW * ir : 0.0;
   }
 };
 
@@ -150,14 +176,15 @@ __device__ __forceinline__ double norm_vec(const double * v) {
   return sqrt(s);
 }
 
-template<int D, int K, int OP>
-__global__ void __launch_bounds__(SW_NT) k_sweep(Tree t, Cols c, Search sr, PhysParams pp, uint32_t * __restrict__ status) {
+template<int D, int K, int OP, int NW>
+__global__ void __launch_bounds__(32 * NW) k_sweep(Tree t, Cols c, Search sr, PhysParams pp, int g_begin, uint32_t * __restrict__ status) {
   using TC = TileCols<D, OP>;
   constexpr int NF = TC::NF;
+  constexpr int NT = 32 * NW;
   __shared__ double tile[NF][SW_TILE];
-  __shared__ int32_t tidx[SW_TILE];
+  __shared__ int32_t tidx[OP == OP_VSIG ? SW_TILE : 1];
 
-  const int g = blockIdx.x, tid = threadIdx.x;
+  const int g = g_begin + blockIdx.x, tid = threadIdx.x;
   int start, P;
   {
     int v = t.cell[sr.wc_cell[g]];
@@ -166,12 +193,12 @@ __global__ void __launch_bounds__(SW_NT) k_sweep(Tree t, Cols c, Search sr, Phys
   }
   const int Ppad = (P + 31) & ~31;
   const uint64_t co = sr.cand_off[g], mo = sr.mask_off[g];
-  const int C = (int)(sr.cand_off[g + 1] - co);
+  const int C = sr.ncand[g];
   const bool active = tid < P;
   const int ia = start + tid;
 
   // own fields
-  double xa[D], ha = 0, rho_a = 0, P_a = 0, cs_a = 0, va[D], vha[D], Prho2_a = 0;
+  double xa[D], ha = 0, rho_a = 0, cs_a = 0, va[D], vha[D], Prho2_a = 0;
 #pragma unroll
   for(int d = 0; d < D; ++d) { xa[d] = 0; va[d] = 0; vha[d] = 0; }
   if(active) {
@@ -185,9 +212,8 @@ __global__ void __launch_bounds__(SW_NT) k_sweep(Tree t, Cols c, Search sr, Phys
     if(OP == OP_VSIG) cs_a = c.f[F_CS][ia];
     if(OP == OP_ACC || OP == OP_DUDT || OP == OP_DEDT) {
       rho_a = c.f[F_RHO][ia];
-      P_a = c.f[F_P][ia];
       cs_a = c.f[F_CS][ia];
-      Prho2_a = P_a / (rho_a * rho_a);
+      Prho2_a = c.f[F_P][ia] / (rho_a * rho_a);
 #pragma unroll
       for(int d = 0; d < D; ++d) vha[d] = c.f[F_VELH + d][ia];
     }
@@ -200,21 +226,28 @@ __global__ void __launch_bounds__(SW_NT) k_sweep(Tree t, Cols c, Search sr, Phys
   for(int tb = 0; tb < C; tb += SW_TILE) {
     const int tc = min(SW_TILE, C - tb);
     __syncthreads();
-    for(int i = tid; i < tc; i += SW_NT) {
+    for(int i = tid; i < tc; i += NT) {
       const int p = sr.cand[co + tb + i];
-      tidx[i] = p;
+      if(OP == OP_VSIG) tidx[i] = p;
 #pragma unroll
       for(int j = 0; j < NF; ++j) tile[j][i] = c.f[TC::col(j)][p];
+      // the pair loops need P_b / rho_b^2 only: one division per candidate instead of one per pair
+      if(OP == OP_ACC || OP == OP_DUDT || OP == OP_DEDT) tile[D + 3][i] = tile[D + 3][i] / (tile[D + 2][i] * tile[D + 2][i]);
     }
     __syncthreads();
-    if(!active) continue;
-    const int nw = (tc + 31) >> 5;
+    const int nw = active ? (tc + 31) >> 5 : 0;
     const uint32_t * mrow = sr.mask + mo + (uint64_t)(tb >> 5) * Ppad + tid;
-    int w = 0;
-    uint32_t m = mrow[0];
-    while(true) {
-      while(m == 0 && ++w < nw) m = mrow[(size_t)w * Ppad];
-      if(m == 0) break;
+    int w = -1;
+    uint32_t m = 0;
+    for(;;) {
+      while(m == 0 && w + 1 < nw) {
+        ++w;
+        m = mrow[(size_t)w * Ppad];
+      }
+      const bool has = m != 0;
+      // warp-uniform exit; the vote also reconverges the lanes before the fp64 body
+      if(!__any_sync(0xffffffffu, has)) break;
+      if(!has) continue;
       const int b = __ffs(m) - 1;
       m &= m - 1;
       const int ci = w * 32 + b;
@@ -234,31 +267,34 @@ __global__ void __launch_bounds__(SW_NT) k_sweep(Tree t, Cols c, Search sr, Phys
         const double dist = norm_vec<D>(rab);
         double vr = 0.0;
 #pragma unroll
-        for(int d = 0; d < D; ++d) vr += (va[d] - tile[D + d][ci]) * (rab[d] / dist);
+        for(int d = 0; d < D; ++d) vr += (va[d] - tile[D + d][ci]) * rab[d];
+        vr = vr / dist;                            // 0/0 = NaN for the particle itself
         const double mn = (0.0 < vr) ? 0.0 : vr;  // std::min(vr, 0.0), NaN-preserving
         const double val = cab - mn;
         if(acc0 < val) acc0 = val;                // std::max(vsig, val): NaN (self) dropped
       }
       else {
         const double hab = .5 * (ha + tile[D][ci]);
-        bool same = true;
-#pragma unroll
-        for(int d = 0; d < D; ++d) same = same && (rab[d] == 0.0) && (xa[d] == tile[d][ci]);
-        const double mb = same ? 0.0 : tile[D + 1][ci];
-        const double rho_b = tile[D + 2][ci], P_b = tile[D + 3][ci], cs_b = tile[D + 4][ci];
         double dotvr = 0.0, dist2 = 0.0;
 #pragma unroll
         for(int d = 0; d < D; ++d) {
           dotvr += (vha[d] - tile[D + 5 + d][ci]) * rab[d];
           dist2 += rab[d] * rab[d];
         }
-        double mu = hab * dotvr / (dist2 + pp.epsilon * hab * hab + TINY);
-        mu = dotvr < 0.0 ? mu : 0.0;
-        const double rho_ab = .5 * (rho_a + rho_b), c_ab = .5 * (cs_a + cs_b);
-        const double Pi = (-pp.alpha * c_ab + pp.beta * mu) * mu / rho_ab;
+        const double mb = dist2 == 0.0 ? 0.0 : tile[D + 1][ci];   // m_b * (pos_b != pos_a)
+        const double rho_ab = .5 * (rho_a + tile[D + 2][ci]);
+        double Pi = 0.0;
+        if(dotvr < 0.0) {
+          // mu = h dot / (r^2 + eps h^2 + TINY);  Pi = (-alpha c + beta mu) mu / rho  -- one division for both
+          const double den = dist2 + pp.epsilon * hab * hab + TINY;
+          const double inv = 1.0 / (den * rho_ab);
+          const double mu = hab * dotvr * (inv * rho_ab);
+          const double c_ab = .5 * (cs_a + tile[D + 4][ci]);
+          Pi = (-pp.alpha * c_ab + pp.beta * mu) * mu * (inv * den);
+        }
         const double r = D == 1 ? fabs(rab[0]) : sqrt(dist2);
         const double Fk = SphKernel<D, K>::F(r, hab);
-        const double Prho2_b = P_b / (rho_b * rho_b);
+        const double Prho2_b = tile[D + 3][ci];
         if(OP == OP_ACC) {
           const double coef = -mb * (Prho2_a + Prho2_b + Pi) * Fk;
 #pragma unroll
@@ -331,7 +367,18 @@ __global__ void __launch_bounds__(256) k_fill(double * p, int64_t n, double v) {
 
 template<int D, int K, int OP>
 static void launch_sweep(System & s) {
-  FSPH_LAUNCH((k_sweep<D, K, OP>), s.search.nwc, SW_NT, s.stream, s.tree, s.cols(), s.search, s.phys(), s.b_status.as<uint32_t>());
+  const Search & sr = s.search;
+  uint32_t * st = s.b_status.as<uint32_t>();
+  for(int cls = 0; cls < 4; ++cls) {
+    const int b = sr.class_off[cls], n = sr.class_off[cls + 1] - b;
+    if(n <= 0) continue;
+    switch(cls) {
+      case 0: FSPH_LAUNCH((k_sweep<D, K, OP, 1>), n, 32, s.stream, s.tree, s.cols(), sr, s.phys(), b, st); break;
+      case 1: FSPH_LAUNCH((k_sweep<D, K, OP, 2>), n, 64, s.stream, s.tree, s.cols(), sr, s.phys(), b, st); break;
+      case 2: FSPH_LAUNCH((k_sweep<D, K, OP, 3>), n, 96, s.stream, s.tree, s.cols(), sr, s.phys(), b, st); break;
+      default: FSPH_LAUNCH((k_sweep<D, K, OP, 4>), n, 128, s.stream, s.tree, s.cols(), sr, s.phys(), b, st); break;
+    }
+  }
 }
 
 template<int D, int K>
