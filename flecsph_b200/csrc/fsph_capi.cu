@@ -115,7 +115,7 @@ void do_sweep(System & s, int op) {
     if(!s.tree_valid) throw std::runtime_error("sweep before update_iteration");
     neighbor_search(s);
   }
-  const char * nm = op == FSPH_SWEEP_DENSITY_PRESSURE_SOUNDSPEED ? "density" : op == FSPH_SWEEP_ACCELERATION ? "acceleration"
+  const char * nm = (op == FSPH_SWEEP_DENSITY_PRESSURE_SOUNDSPEED || op == 100) ? "density" : (op == FSPH_SWEEP_ACCELERATION || op == 101) ? "acceleration"
                   : op == FSPH_SWEEP_DUDT ? "dudt" : op == FSPH_SWEEP_DEDT ? "dedt" : "neighbors";
   PhaseScope p(s, nm);
   sweep(s, op);
@@ -150,10 +150,10 @@ void do_step(System & s, int initial) {
     do_update_iteration(s);
     A(FSPH_APPLY_EOS_INIT);
     if(P.thermokinetic_formulation) A(FSPH_APPLY_SET_TOTAL_ENERGY);
-    do_sweep(s, FSPH_SWEEP_DENSITY_PRESSURE_SOUNDSPEED);
+    do_sweep(s, 100);
     A(FSPH_APPLY_SAVE_VELOCITYHALF);
     do_reset_ghosts(s);
-    do_sweep(s, FSPH_SWEEP_ACCELERATION);
+    do_sweep(s, 101);
     timestep();
     if(P.evolve_internal_energy) energy_passes();
   }
@@ -163,9 +163,9 @@ void do_step(System & s, int initial) {
     A(FSPH_APPLY_SAVE_VELOCITYHALF);
     A(FSPH_APPLY_LEAPFROG_DRIFT);
     do_update_iteration(s);
-    do_sweep(s, FSPH_SWEEP_DENSITY_PRESSURE_SOUNDSPEED);
+    do_sweep(s, 100);
     do_reset_ghosts(s);
-    do_sweep(s, FSPH_SWEEP_ACCELERATION);
+    do_sweep(s, 101);
     A(FSPH_APPLY_LEAPFROG_KICK_V);
     do_reset_ghosts(s);
     if(P.evolve_internal_energy) {

@@ -18,6 +18,7 @@ enum F64 {
   F_POS = 0, F_VEL = 3, F_VELH = 6, F_ACC = 9, F_GACC = 12,
   F_MASS = 15, F_H, F_RHO, F_P, F_U, F_E, F_CS, F_DUDT, F_DEDT, F_DT, F_ALPHA, F_VSIG, F_GPOT, F_ADIA,
   F_CSOLD,  // soundspeed before the current density sweep (signal-speed order dependence)
+  F_PRHO2,  // P / rho^2, derived right before each pair sweep that needs it (not permuted by the sort)
   NF64
 };
 

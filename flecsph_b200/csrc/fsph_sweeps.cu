@@ -19,18 +19,39 @@
 namespace fsph {
 
 constexpr int SW_TILE = 256;
+constexpr int SW_LCAP = 32;   // neighbour-list entries decoded per round and thread
 constexpr double TINY = 1e10 * DBL_MIN;  // kernels.h:64, viscosity.h:36
 constexpr double PI = 3.14159265358979323846;
 
-enum SweepOp { OP_DENSITY = 0, OP_ACC = 1, OP_DUDT = 2, OP_DEDT = 3, OP_VSIG = 5 };
+enum SweepOp { OP_DENSITY = 0, OP_ACC = 1, OP_DUDT = 2, OP_DEDT = 3, OP_VSIG = 5, OP_ACCV = 6 };
 
 // ---- SPH kernels: value W(r,h) and the scalar F with grad W = r_ab * F ------------------------------------
 
 template<int D> __device__ __forceinline__ double ipowD(double ih) { return D == 1 ? ih : (D == 2 ? ih * ih : ih * ih * ih); }
-// 1/h and 1/(r + TINY) from a single fp64 division
+// Reciprocal and reciprocal square root from the MUFU seeds (~20 bits) plus two Newton steps (error ~1e-16
+// relative, far inside the 1e-10 bar) -- several times cheaper than the IEEE division / sqrt sequences with
+// their special-case branches.  Arguments are positive normal numbers here.
+__device__ __forceinline__ double rcp_nr(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double rsqrt_nr(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  return fma(y, e, y);
+}
+// 1/h and 1/(r + TINY) from a single fp64 reciprocal
 __device__ __forceinline__ void inv_h_r(double h, double r, double & ih, double & ir) {
   const double rt = r + TINY;
-  const double inv = 1.0 / (h * rt);
+  const double inv = rcp_nr(h * rt);
   ih = inv * rt;
   ir = inv * h;
 }
@@ -40,7 +61,7 @@ template<int D, int K> struct SphKernel;
 template<int D> struct SphKernel<D, FSPH_KERNEL_CUBIC_SPLINE> {
   static __device__ __forceinline__ double sigma() { return D == 1 ? 4. / 3. : (D == 2 ? 40. / (7. * PI) : 8. / PI); }
   static __device__ __forceinline__ double W(double r, double h) {
-    const double ih = 1.0 / h;
+    const double ih = rcp_nr(h);
     const double q = 2. * r * ih;
     double res = 0.;
     if(q < 2.0) {
@@ -61,13 +82,23 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_CUBIC_SPLINE> {
     }
     return res;
   }
+  static __device__ __forceinline__ double Fi(double r, double ih, double ir) {
+    const double q = 2. * r * ih;
+    double res = 0.;
+    if(q < 2.0) {
+      const double sg = 2. * sigma() * ipowD<D>(ih) * ih;
+      const double dW = q < 1.0 ? -3.0 * q + 9. / 4. * q * q : -.75 * (2 - q) * (2 - q);
+      res = sg * dW * ir;
+    }
+    return res;
+  }
 };
 template<int D> struct SphKernel<D, FSPH_KERNEL_QUINTIC_SPLINE> {
   static __device__ __forceinline__ double sigma() { return D == 1 ? 1. / 40. : (D == 2 ? 63. / (478. * PI) : 81. / (359. * PI)); }
   static __device__ __forceinline__ double p5(double x) { double x2 = x * x; return x2 * x2 * x; }
   static __device__ __forceinline__ double p4(double x) { double x2 = x * x; return x2 * x2; }
   static __device__ __forceinline__ double W(double r, double h) {
-    const double ih = 1.0 / h;
+    const double ih = rcp_nr(h);
     const double q = 3. * r * ih;
     double res = 0.;
     if(q < 3.) {
@@ -92,11 +123,23 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_QUINTIC_SPLINE> {
     }
     return res;
   }
+  static __device__ __forceinline__ double Fi(double r, double ih, double ir) {
+    const double q = 3. * r * ih;
+    double res = 0.;
+    if(q < 3.) {
+      const double sg = 3. * sigma() * ipowD<D>(ih) * ih;
+      double dW = -5. * p4(3 - q);
+      if(q < 2.) dW += 30. * p4(2 - q);
+      if(q < 1.) dW += -75. * p4(1 - q);
+      res = sg * dW * ir;
+    }
+    return res;
+  }
 };
 template<int D> struct SphKernel<D, FSPH_KERNEL_WENDLAND_C2> {
   static __device__ __forceinline__ double sigma() { return D == 1 ? 1.25 : (D == 2 ? 7. / PI : 21. / (2. * PI)); }
   static __device__ __forceinline__ double W(double r, double h) {
-    const double ih = 1.0 / h;
+    const double ih = rcp_nr(h);
     const double q = r * ih, o = 1 - q, o2 = o * o;
     const double res = D == 1 ? sigma() * ih * o2 * o * (3 * q + 1) : sigma() * ipowD<D>(ih) * o2 * o2 * (4 * q + 1);
     return q < 1.0 ? res : 0.0;
@@ -109,11 +152,17 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_WENDLAND_C2> {
     const double dW = D == 1 ? -12. * q * o2 : -10. * q * o2 * o;
     return q < 1.0 ? sg * dW * ir : 0.0;
   }
+  static __device__ __forceinline__ double Fi(double r, double ih, double ir) {
+    const double q = r * ih, o = 1 - q, o2 = o * o;
+    const double sg = D == 1 ? sigma() * ih * ih : 2. * sigma() * ipowD<D>(ih) * ih;
+    const double dW = D == 1 ? -12. * q * o2 : -10. * q * o2 * o;
+    return q < 1.0 ? sg * dW * ir : 0.0;
+  }
 };
 template<int D> struct SphKernel<D, FSPH_KERNEL_WENDLAND_C4> {
   static __device__ __forceinline__ double sigma() { return D == 1 ? 1.5 : (D == 2 ? 9. / PI : 495. / (32. * PI)); }
   static __device__ __forceinline__ double W(double r, double h) {
-    const double ih = 1.0 / h;
+    const double ih = rcp_nr(h);
     const double q = r * ih, o = 1 - q, o2 = o * o;
     double res;
     if(D == 1) res = sigma() * ih * (o2 * o) * o2 * (1 + q * (5 + q * 8));
@@ -128,11 +177,17 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_WENDLAND_C4> {
     const double dW = D == 1 ? -q * o2 * o2 * (1 + 4. * q) : -4. / 3. * q * (o2 * o) * o2 * (1 + 5. * q);
     return q < 1.0 ? sg * dW * ir : 0.0;
   }
+  static __device__ __forceinline__ double Fi(double r, double ih, double ir) {
+    const double q = r * ih, o = 1 - q, o2 = o * o;
+    const double sg = 14. * sigma() * ipowD<D>(ih) * ih;
+    const double dW = D == 1 ? -q * o2 * o2 * (1 + 4. * q) : -4. / 3. * q * (o2 * o) * o2 * (1 + 5. * q);
+    return q < 1.0 ? sg * dW * ir : 0.0;
+  }
 };
 template<int D> struct SphKernel<D, FSPH_KERNEL_WENDLAND_C6> {
   static __device__ __forceinline__ double sigma() { return D == 1 ? 55. / 32. : (D == 2 ? 78. / (7. * PI) : 1365. / (64. * PI)); }
   static __device__ __forceinline__ double W(double r, double h) {
-    const double ih = 1.0 / h;
+    const double ih = rcp_nr(h);
     const double q = r * ih, o = 1 - q, o2 = o * o, o4 = o2 * o2;
     double res;
     if(D == 1) res = sigma() * ih * (o2 * o) * o4 * (1 + q * (7 + q * (19 + q * 21)));
@@ -147,11 +202,18 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_WENDLAND_C6> {
     const double dW = D == 1 ? -6. * q * o3 * o3 * (3 + q * (18 + q * 35)) : -22. * q * o4 * o3 * (1 + q * (7 + q * 16));
     return q < 1.0 ? sg * dW * ir : 0.0;
   }
+  static __device__ __forceinline__ double Fi(double r, double ih, double ir) {
+    const double q = r * ih, o = 1 - q, o2 = o * o, o3 = o2 * o, o4 = o2 * o2;
+    const double sg = sigma() * ipowD<D>(ih) * ih;
+    const double dW = D == 1 ? -6. * q * o3 * o3 * (3 + q * (18 + q * 35)) : -22. * q * o4 * o3 * (1 + q * (7 + q * 16));
+    return q < 1.0 ? sg * dW * ir : 0.0;
+  }
 };
 
 // ---- candidate tile columns per sweep ---------------------------------------------------------------------
 template<int D, int OP> struct TileCols {
-  static constexpr int NF = OP == OP_DENSITY ? D + 2 : (OP == OP_VSIG ? 2 * D + 2 : (OP == OP_ACC ? 2 * D + 5 : 3 * D + 5));
+  // ACCV = acceleration + signal speed: ACC's columns + velocity + previous soundspeed
+  static constexpr int NF = OP == OP_DENSITY ? D + 2 : (OP == OP_VSIG ? 2 * D + 2 : (OP == OP_ACC ? 2 * D + 5 : (OP == OP_ACCV ? 3 * D + 6 : 3 * D + 5)));
   static __device__ __forceinline__ int col(int j) {
     if(j < D) return F_POS + j;
     if(OP == OP_DENSITY) return j == D ? F_H : F_MASS;
@@ -160,10 +222,11 @@ template<int D, int OP> struct TileCols {
     if(r == 0) return F_H;
     if(r == 1) return F_MASS;
     if(r == 2) return F_RHO;
-    if(r == 3) return F_P;
+    if(r == 3) return F_PRHO2;   // P / rho^2, refreshed by k_prho2 right before the sweep
     if(r == 4) return F_CS;
     if(r < 5 + D) return F_VELH + (r - 5);
-    return F_VEL + (r - 5 - D);
+    if(r < 5 + 2 * D) return F_VEL + (r - 5 - D);
+    return F_CSOLD;
   }
 };
 
@@ -176,13 +239,120 @@ __device__ __forceinline__ double norm_vec(const double * v) {
   return sqrt(s);
 }
 
+// state of the particle a thread owns + its accumulators
+template<int D> struct Own {
+  double xa[D], va[D], vha[D];
+  double ha, rho_a, cs_a, Prho2_a;
+  double acc0, acc1, accv[D], vsig;
+  int ia;
+};
+
+// one neighbour pair (a, candidate ci of the current tile); `valid` = false makes it a no-op (padding slot of
+// the two-pairs-per-iteration loop)
+template<int D, int K, int OP>
+__device__ __forceinline__ void pair_body(Own<D> & o, const double (*tile)[SW_TILE], const int32_t * tidx, const PhysParams & pp,
+  const int ci, const bool valid) {
+  double rab[D];
+#pragma unroll
+  for(int d = 0; d < D; ++d) rab[d] = o.xa[d] - tile[d][ci];
+  if(OP == OP_DENSITY) {
+    double d2 = 0.0;
+#pragma unroll
+    for(int d = 0; d < D; ++d) d2 += rab[d] * rab[d];
+    const double r = D == 1 ? fabs(rab[0]) : d2 * rsqrt_nr(fmax(d2, 1e-280));
+    const double hab = .5 * (o.ha + tile[D][ci]);
+    const double t = tile[D + 1][ci] * SphKernel<D, K>::W(r, hab);
+    o.acc0 += valid ? t : 0.0;
+  }
+  else if(OP == OP_VSIG) {
+    // compute_signalspeed: b contributes its new soundspeed iff it was processed before a, i.e. iff its
+    // (descending-key processing order) index is larger
+    const double csb = tidx[ci] > o.ia ? tile[2 * D][ci] : tile[2 * D + 1][ci];
+    const double cab = fmax(o.cs_a, csb);
+    const double dist = norm_vec<D>(rab);
+    double vr = 0.0;
+#pragma unroll
+    for(int d = 0; d < D; ++d) vr += (o.va[d] - tile[D + d][ci]) * rab[d];
+    vr = vr / dist;                            // 0/0 = NaN for the particle itself
+    const double mn = (0.0 < vr) ? 0.0 : vr;  // std::min(vr, 0.0), NaN-preserving
+    const double val = cab - mn;
+    if(valid && o.vsig < val) o.vsig = val;   // std::max(vsig, val): NaN (self) dropped
+  }
+  else {
+    const double hab = .5 * (o.ha + tile[D][ci]);
+    double dotvr = 0.0, dist2 = 0.0;
+#pragma unroll
+    for(int d = 0; d < D; ++d) {
+      dotvr += (o.vha[d] - tile[D + 5 + d][ci]) * rab[d];
+      dist2 += rab[d] * rab[d];
+    }
+    const double mb = (dist2 == 0.0 || !valid) ? 0.0 : tile[D + 1][ci];   // m_b * (pos_b != pos_a)
+    const double rho_ab = .5 * (o.rho_a + tile[D + 2][ci]);
+    double Pi = 0.0;
+    if(dotvr < 0.0) {
+      // mu = h dot / (r^2 + eps h^2 + TINY);  Pi = (-alpha c + beta mu) mu / rho  -- one division for both
+      const double den = dist2 + pp.epsilon * hab * hab + TINY;
+      const double inv = rcp_nr(den * rho_ab);
+      const double mu = hab * dotvr * (inv * rho_ab);
+      const double c_ab = .5 * (o.cs_a + tile[D + 4][ci]);
+      Pi = (-pp.alpha * c_ab + pp.beta * mu) * mu * (inv * den);
+    }
+    // r, 1/r and 1/h_ab: one reciprocal square root + one reciprocal (dist2 clamped away from 0: the particle
+    // itself / coincident particles carry m_b = 0 and the kernel gradient is 0 at r = 0 anyway)
+    const double ir = rsqrt_nr(fmax(dist2, 1e-280));
+    const double r = dist2 * ir;
+    const double ih = rcp_nr(hab);
+    const double Fk = SphKernel<D, K>::Fi(r, ih, ir);
+    const double Prho2_b = tile[D + 3][ci];
+    if(OP == OP_ACC || OP == OP_ACCV) {
+      const double coef = -mb * (o.Prho2_a + Prho2_b + Pi) * Fk;
+#pragma unroll
+      for(int d = 0; d < D; ++d) o.accv[d] += coef * rab[d];
+      if(OP == OP_ACCV) {
+        // compute_signalspeed fused into the acceleration sweep (fsph_step only): all new soundspeeds exist by now
+        const double csb = tidx[ci] > o.ia ? tile[D + 4][ci] : tile[3 * D + 5][ci];
+        const double cab = fmax(o.cs_a, csb);
+        double vr = 0.0;
+#pragma unroll
+        for(int d = 0; d < D; ++d) vr += (o.va[d] - tile[2 * D + 5 + d][ci]) * rab[d];
+        vr = vr * ir;                              // dist2 == 0 (self) is excluded below instead of via NaN
+        const double mn = (0.0 < vr) ? 0.0 : vr;
+        const double val = cab - mn;
+        if(valid && dist2 != 0.0 && o.vsig < val) o.vsig = val;
+      }
+    }
+    else if(OP == OP_DUDT) {
+      double vdw = 0.0;
+#pragma unroll
+      for(int d = 0; d < D; ++d) vdw += (o.va[d] - tile[2 * D + 5 + d][ci]) * rab[d];
+      vdw *= Fk;
+      o.acc0 += mb * vdw;
+      o.acc1 += mb * vdw * Pi;
+    }
+    else {  // OP_DEDT
+      double vadw = 0.0, vbdw = 0.0;
+#pragma unroll
+      for(int d = 0; d < D; ++d) {
+        vadw += o.va[d] * rab[d];
+        vbdw += tile[2 * D + 5 + d][ci] * rab[d];
+      }
+      vadw *= Fk;
+      vbdw *= Fk;
+      o.acc0 -= mb * (o.Prho2_a * vbdw + vadw * Prho2_b + .5 * Pi * (vbdw + vadw));
+    }
+  }
+}
+
 template<int D, int K, int OP, int NW>
 __global__ void __launch_bounds__(32 * NW) k_sweep(Tree t, Cols c, Search sr, PhysParams pp, int g_begin, uint32_t * __restrict__ status) {
   using TC = TileCols<D, OP>;
   constexpr int NF = TC::NF;
   constexpr int NT = 32 * NW;
+  constexpr bool NEED_IDX = OP == OP_VSIG || OP == OP_ACCV;
   __shared__ double tile[NF][SW_TILE];
-  __shared__ int32_t tidx[OP == OP_VSIG ? SW_TILE : 1];
+  __shared__ int32_t tidx[NEED_IDX ? SW_TILE : 1];
+  __shared__ uint32_t mtile[SW_TILE / 32][NT];   // this tile's mask words, [word][particle]
+  __shared__ uint8_t nlist[SW_LCAP][NT];         // decoded neighbour lists of one round, [entry][particle]
 
   const int g = g_begin + blockIdx.x, tid = threadIdx.x;
   int start, P;
@@ -195,136 +365,90 @@ __global__ void __launch_bounds__(32 * NW) k_sweep(Tree t, Cols c, Search sr, Ph
   const uint64_t co = sr.cand_off[g], mo = sr.mask_off[g];
   const int C = sr.ncand[g];
   const bool active = tid < P;
-  const int ia = start + tid;
 
-  // own fields
-  double xa[D], ha = 0, rho_a = 0, cs_a = 0, va[D], vha[D], Prho2_a = 0;
+  Own<D> o;
+  o.ia = start + tid;
+  o.ha = o.rho_a = o.cs_a = o.Prho2_a = 0.0;
+  o.acc0 = o.acc1 = o.vsig = 0.0;
 #pragma unroll
-  for(int d = 0; d < D; ++d) { xa[d] = 0; va[d] = 0; vha[d] = 0; }
+  for(int d = 0; d < D; ++d) { o.xa[d] = 0; o.va[d] = 0; o.vha[d] = 0; o.accv[d] = 0; }
   if(active) {
+    const int ia = o.ia;
 #pragma unroll
-    for(int d = 0; d < D; ++d) xa[d] = c.f[F_POS + d][ia];
-    ha = c.f[F_H][ia];
-    if(OP == OP_VSIG || OP == OP_DUDT || OP == OP_DEDT) {
+    for(int d = 0; d < D; ++d) o.xa[d] = c.f[F_POS + d][ia];
+    o.ha = c.f[F_H][ia];
+    if(OP == OP_VSIG || OP == OP_DUDT || OP == OP_DEDT || OP == OP_ACCV) {
 #pragma unroll
-      for(int d = 0; d < D; ++d) va[d] = c.f[F_VEL + d][ia];
+      for(int d = 0; d < D; ++d) o.va[d] = c.f[F_VEL + d][ia];
     }
-    if(OP == OP_VSIG) cs_a = c.f[F_CS][ia];
-    if(OP == OP_ACC || OP == OP_DUDT || OP == OP_DEDT) {
-      rho_a = c.f[F_RHO][ia];
-      cs_a = c.f[F_CS][ia];
-      Prho2_a = c.f[F_P][ia] / (rho_a * rho_a);
+    if(OP == OP_VSIG) o.cs_a = c.f[F_CS][ia];
+    if(OP == OP_ACC || OP == OP_DUDT || OP == OP_DEDT || OP == OP_ACCV) {
+      o.rho_a = c.f[F_RHO][ia];
+      o.cs_a = c.f[F_CS][ia];
+      o.Prho2_a = c.f[F_PRHO2][ia];
 #pragma unroll
-      for(int d = 0; d < D; ++d) vha[d] = c.f[F_VELH + d][ia];
+      for(int d = 0; d < D; ++d) o.vha[d] = c.f[F_VELH + d][ia];
     }
   }
-  // accumulators
-  double acc0 = 0.0, acc1 = 0.0, accv[D];
-#pragma unroll
-  for(int d = 0; d < D; ++d) accv[d] = 0.0;
 
   for(int tb = 0; tb < C; tb += SW_TILE) {
     const int tc = min(SW_TILE, C - tb);
     __syncthreads();
-    for(int i = tid; i < tc; i += NT) {
-      const int p = sr.cand[co + tb + i];
-      if(OP == OP_VSIG) tidx[i] = p;
+    {
+      // all candidate indices of this thread first, then the column gathers: (SW_TILE / NT) x NF loads in flight
+      constexpr int LPT = (SW_TILE + NT - 1) / NT;
+      int pidx[LPT];
 #pragma unroll
-      for(int j = 0; j < NF; ++j) tile[j][i] = c.f[TC::col(j)][p];
-      // the pair loops need P_b / rho_b^2 only: one division per candidate instead of one per pair
-      if(OP == OP_ACC || OP == OP_DUDT || OP == OP_DEDT) tile[D + 3][i] = tile[D + 3][i] / (tile[D + 2][i] * tile[D + 2][i]);
+      for(int u = 0; u < LPT; ++u) {
+        const int i = tid + u * NT;
+        pidx[u] = i < tc ? sr.cand[co + tb + i] : -1;
+      }
+#pragma unroll
+      for(int u = 0; u < LPT; ++u) {
+        const int i = tid + u * NT;
+        if(pidx[u] >= 0) {
+          if(NEED_IDX) tidx[i] = pidx[u];
+#pragma unroll
+          for(int j = 0; j < NF; ++j) tile[j][i] = c.f[TC::col(j)][pidx[u]];
+        }
+      }
+    }
+    {
+      const int nwt = (tc + 31) >> 5;
+      const uint32_t * mrow = sr.mask + mo + (uint64_t)(tb >> 5) * Ppad;
+      for(int i = tid; i < nwt * Ppad; i += NT) mtile[i / Ppad][i % Ppad] = mrow[i];
     }
     __syncthreads();
+    // Decode this thread's mask bits into a short list of tile-local candidate indices (<= SW_LCAP per round),
+    // then run a uniform, branch-free pair loop over the lists: two pairs per iteration (independent fp64
+    // dependency chains), trip count = the warp's longest list.
     const int nw = active ? (tc + 31) >> 5 : 0;
-    const uint32_t * mrow = sr.mask + mo + (uint64_t)(tb >> 5) * Ppad + tid;
-    int w = -1;
-    uint32_t m = 0;
+    int w = 0;
+    uint32_t m = nw > 0 ? mtile[0][tid] : 0u;
     for(;;) {
-      while(m == 0 && w + 1 < nw) {
-        ++w;
-        m = mrow[(size_t)w * Ppad];
+      int cnt = 0;
+      while(cnt < SW_LCAP) {
+        while(m == 0 && w + 1 < nw) m = mtile[++w][tid];
+        if(m == 0) break;
+        nlist[cnt++][tid] = (uint8_t)(w * 32 + __ffs(m) - 1);
+        m &= m - 1;
       }
-      const bool has = m != 0;
-      // warp-uniform exit; the vote also reconverges the lanes before the fp64 body
-      if(!__any_sync(0xffffffffu, has)) break;
-      if(!has) continue;
-      const int b = __ffs(m) - 1;
-      m &= m - 1;
-      const int ci = w * 32 + b;
-      double rab[D];
-#pragma unroll
-      for(int d = 0; d < D; ++d) rab[d] = xa[d] - tile[d][ci];
-      if(OP == OP_DENSITY) {
-        const double r = norm_vec<D>(rab);
-        const double hab = .5 * (ha + tile[D][ci]);
-        acc0 += tile[D + 1][ci] * SphKernel<D, K>::W(r, hab);
+      const int jmax = __reduce_max_sync(0xffffffffu, cnt);
+      if(jmax == 0) break;
+      for(int j = 0; j < jmax; j += 2) {
+        const bool v0 = j < cnt, v1 = j + 1 < cnt;
+        const int ci0 = v0 ? nlist[j][tid] : 0;
+        const int ci1 = v1 ? nlist[j + 1][tid] : ci0;
+        pair_body<D, K, OP>(o, tile, tidx, pp, ci0, v0);
+        pair_body<D, K, OP>(o, tile, tidx, pp, ci1, v1);
       }
-      else if(OP == OP_VSIG) {
-        // compute_signalspeed: b contributes its new soundspeed iff it was processed before a, i.e. iff its
-        // (descending-key processing order) index is larger
-        const double csb = tidx[ci] > ia ? tile[2 * D][ci] : tile[2 * D + 1][ci];
-        const double cab = fmax(cs_a, csb);
-        const double dist = norm_vec<D>(rab);
-        double vr = 0.0;
-#pragma unroll
-        for(int d = 0; d < D; ++d) vr += (va[d] - tile[D + d][ci]) * rab[d];
-        vr = vr / dist;                            // 0/0 = NaN for the particle itself
-        const double mn = (0.0 < vr) ? 0.0 : vr;  // std::min(vr, 0.0), NaN-preserving
-        const double val = cab - mn;
-        if(acc0 < val) acc0 = val;                // std::max(vsig, val): NaN (self) dropped
-      }
-      else {
-        const double hab = .5 * (ha + tile[D][ci]);
-        double dotvr = 0.0, dist2 = 0.0;
-#pragma unroll
-        for(int d = 0; d < D; ++d) {
-          dotvr += (vha[d] - tile[D + 5 + d][ci]) * rab[d];
-          dist2 += rab[d] * rab[d];
-        }
-        const double mb = dist2 == 0.0 ? 0.0 : tile[D + 1][ci];   // m_b * (pos_b != pos_a)
-        const double rho_ab = .5 * (rho_a + tile[D + 2][ci]);
-        double Pi = 0.0;
-        if(dotvr < 0.0) {
-          // mu = h dot / (r^2 + eps h^2 + TINY);  Pi = (-alpha c + beta mu) mu / rho  -- one division for both
-          const double den = dist2 + pp.epsilon * hab * hab + TINY;
-          const double inv = 1.0 / (den * rho_ab);
-          const double mu = hab * dotvr * (inv * rho_ab);
-          const double c_ab = .5 * (cs_a + tile[D + 4][ci]);
-          Pi = (-pp.alpha * c_ab + pp.beta * mu) * mu * (inv * den);
-        }
-        const double r = D == 1 ? fabs(rab[0]) : sqrt(dist2);
-        const double Fk = SphKernel<D, K>::F(r, hab);
-        const double Prho2_b = tile[D + 3][ci];
-        if(OP == OP_ACC) {
-          const double coef = -mb * (Prho2_a + Prho2_b + Pi) * Fk;
-#pragma unroll
-          for(int d = 0; d < D; ++d) accv[d] += coef * rab[d];
-        }
-        else if(OP == OP_DUDT) {
-          double vdw = 0.0;
-#pragma unroll
-          for(int d = 0; d < D; ++d) vdw += (va[d] - tile[2 * D + 5 + d][ci]) * rab[d];
-          vdw *= Fk;
-          acc0 += mb * vdw;
-          acc1 += mb * vdw * Pi;
-        }
-        else {  // OP_DEDT
-          double vadw = 0.0, vbdw = 0.0;
-#pragma unroll
-          for(int d = 0; d < D; ++d) {
-            vadw += va[d] * rab[d];
-            vbdw += tile[2 * D + 5 + d][ci] * rab[d];
-          }
-          vadw *= Fk;
-          vbdw *= Fk;
-          acc0 -= mb * (Prho2_a * vbdw + vadw * Prho2_b + .5 * Pi * (vbdw + vadw));
-        }
-      }
+      if(jmax < SW_LCAP) break;
     }
   }
   if(!active) return;
+  const int ia = o.ia;
   if(OP == OP_DENSITY) {
-    const double rho = acc0;
+    const double rho = o.acc0;
     if(!(rho > 0)) atomicOr(status, (uint32_t)ERR_RHO_NONPOS);
     c.f[F_RHO][ia] = rho;
     double u;
@@ -342,21 +466,30 @@ __global__ void __launch_bounds__(32 * NW) k_sweep(Tree t, Cols c, Search sr, Ph
     c.f[F_CSOLD][ia] = c.f[F_CS][ia];
     c.f[F_CS][ia] = sqrt(pp.gamma * (pp.gamma - 1.) * u);
   }
-  else if(OP == OP_VSIG) c.f[F_VSIG][ia] = acc0;
-  else if(OP == OP_ACC) {
+  else if(OP == OP_VSIG) c.f[F_VSIG][ia] = o.vsig;
+  else if(OP == OP_ACC || OP == OP_ACCV) {
 #pragma unroll
     for(int d = 0; d < D; ++d) {
-      c.f[F_ACC + d][ia] = accv[d];  // + external_force::acceleration == 0 (external_force_type "none")
+      c.f[F_ACC + d][ia] = o.accv[d];  // + external_force::acceleration == 0 (external_force_type "none")
       c.f[F_GACC + d][ia] = 0.0;
     }
     c.f[F_GPOT][ia] = 0.0;
+    if(OP == OP_ACCV) c.f[F_VSIG][ia] = o.vsig;
   }
-  else if(OP == OP_DUDT) c.f[F_DUDT][ia] = Prho2_a * acc0 + .5 * acc1;
+  else if(OP == OP_DUDT) c.f[F_DUDT][ia] = o.Prho2_a * o.acc0 + .5 * o.acc1;
   else {
     double gv = 0.0;
 #pragma unroll
-    for(int d = 0; d < D; ++d) gv += c.f[F_GACC + d][ia] * va[d];
-    c.f[F_DEDT][ia] = acc0 + gv;
+    for(int d = 0; d < D; ++d) gv += c.f[F_GACC + d][ia] * o.va[d];
+    c.f[F_DEDT][ia] = o.acc0 + gv;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_prho2(Cols c, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n) {
+    const double rho = c.f[F_RHO][i];
+    c.f[F_PRHO2][i] = c.f[F_P][i] / (rho * rho);
   }
 }
 
@@ -368,6 +501,7 @@ __global__ void __launch_bounds__(256) k_fill(double * p, int64_t n, double v) {
 template<int D, int K, int OP>
 static void launch_sweep(System & s) {
   const Search & sr = s.search;
+  if(OP != OP_DENSITY && OP != OP_VSIG) FSPH_LAUNCH(k_prho2, (unsigned)((s.n + 255) / 256), 256, s.stream, s.cols(), s.n);
   uint32_t * st = s.b_status.as<uint32_t>();
   for(int cls = 0; cls < 4; ++cls) {
     const int b = sr.class_off[cls], n = sr.class_off[cls + 1] - b;
@@ -389,6 +523,8 @@ static void sweep_dk(System & s, int op) {
       launch_sweep<D, K, OP_VSIG>(s);
       break;
     case FSPH_SWEEP_ACCELERATION: launch_sweep<D, K, OP_ACC>(s); break;
+    case 100: launch_sweep<D, K, OP_DENSITY>(s); break;   // fsph_step: density / P / cs only ...
+    case 101: launch_sweep<D, K, OP_ACCV>(s); break;      // ... and the signal speed rides on the acceleration sweep
     case FSPH_SWEEP_DUDT:
       if(s.iteration < s.par.relaxation_steps)
         FSPH_LAUNCH(k_fill, (unsigned)((s.n + 255) / 256), 256, s.stream, s.col[F_DUDT].as<double>(), s.n, 0.0);

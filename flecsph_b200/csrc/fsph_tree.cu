@@ -185,6 +185,7 @@ void sort_bodies(System & s) {
   if(moved) {
     for(int f = 0; f < NF64; ++f) {
       if(f < F_MASS && (f % 3) >= s.dim) continue;  // unused vector components
+      if(f == F_PRHO2) continue;                      // derived column
       gather8(s, s.col[f], perm);
     }
     gather8(s, s.col_id, perm);
