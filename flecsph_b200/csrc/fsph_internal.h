@@ -48,7 +48,21 @@ struct Cols {
   int32_t * nneigh;
 };
 
+// packed records for the neighbour walk: one 64-byte load per frontier node, one 32-byte load per leaf child
+struct __align__(16) NodeRec {
+  double bmin[3], bmax[3];
+  int32_t child_begin;       // first child cell
+  int32_t first_child_node;  // node index of the first node child (node children are consecutive nodes)
+  uint32_t nchild;           // number of child cells (<= 2^D)
+  uint32_t leafmask;         // bit j: child cell child_begin + j is a leaf
+};
+struct __align__(16) LeafRec {
+  double x[3], h;
+};
+
 struct Tree {
+  NodeRec * noderec;   // [nnodes]
+  LeafRec * leafrec;   // [ncells] (entries of node cells unused)
   // cells in level order (depth, then key): value >= 0 -> particle index (leaf), < 0 -> ~node index
   int32_t * cell;
   int32_t * cell_parent;  // node index of the parent (-1 for the root cell)
@@ -110,6 +124,7 @@ struct System {
   DevBuf col[NF64], col_id, col_key, col_type, col_nneigh, scratch_col;
   DevBuf b_perm, b_keys2, b_perm2, b_tmp[6];
   DevBuf b_cell, b_cell_parent, b_cell_desc, b_cell_desc2, b_child_begin, b_child_end, b_node_start, b_node_depth, b_sub;
+  DevBuf b_noderec, b_leafrec;
   DevBuf b_nmass, b_ncom[3], b_nradius, b_nlap, b_nbmin[3], b_nbmax[3];
   DevBuf b_wc_cell, b_cand_off, b_mask_off, b_cand, b_mask, b_cnt0, b_cnt1;
   DevBuf b_status, b_red, b_levels, b_ncand, b_search_scratch;

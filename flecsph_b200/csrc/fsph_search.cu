@@ -20,8 +20,8 @@
 namespace fsph {
 
 constexpr int SR_NT = 64;       // threads per CTA of the export kernel
-constexpr int SR_QCAP = 1024;   // node frontier capacity per level
-constexpr int SR_TILE = 512;    // candidates per shared-memory tile
+constexpr int SR_QCAP = 768;    // node frontier capacity per level
+constexpr int SR_TILE = 256;    // candidates per shared-memory tile
 constexpr double GEO_TOL = 2.220446049250313e-16 * 10.;  // tree_geometry.h:57
 
 template<int D>
@@ -103,14 +103,20 @@ __global__ void __launch_bounds__(32 * NW) k_search(Tree t, Cols c, Search sr, i
   __shared__ double gx[D][32 * NW];
   __shared__ double gh[32 * NW];
   __shared__ int32_t queue[2][SR_QCAP];
+  __shared__ uint32_t qres[SR_QCAP];   // per frontier node: node-children mask | candidate-children mask << 8
   __shared__ uint32_t scan_sm[NW];
   __shared__ double red_sm[NW][2 * D + 1];
   __shared__ unsigned long long base_sm[2];
+  __shared__ unsigned long long repkey_sm[NW][1 << D];
+  __shared__ int rep_sm[1 << D];
   __shared__ double cx[FILL ? D : 1][FILL ? SR_TILE : 1];
   __shared__ double ch2[FILL ? SR_TILE : 1];
 
   const int tid = threadIdx.x;
-  for(int g = g_begin + blockIdx.x; g < g_end; g += gridDim.x) {
+  // every CTA walks a contiguous run of work cells (Morton neighbours: the upper tree levels stay in L1/L2)
+  const int per_cta = (g_end - g_begin + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int g_lo = g_begin + (int)blockIdx.x * per_cta, g_hi = min(g_end, g_lo + per_cta);
+  for(int g = g_lo; g < g_hi; ++g) {
     const WorkCell wc = load_work_cell(t, sr, g);
     const int P = wc.P, gnode = wc.gnode;
     __syncthreads();
@@ -164,97 +170,153 @@ __global__ void __launch_bounds__(32 * NW) k_search(Tree t, Cols c, Search sr, i
         ghmax = fmax(ghmax, red_sm[ww][2 * D]);
       }
     }
+    // Representative particles: for each corner of G's tight box the particle of G nearest to it.  The
+    // "does any particle sphere of G touch this node box" loop tries the representative on the node's side
+    // first (pure ordering heuristic: the outcome is the exact any-of-all-particles result either way).
+    {
+      constexpr int NC = 1 << D;
+#pragma unroll
+      for(int q = 0; q < NC; ++q) {
+        unsigned long long key = ~0ull;
+        if(tid < P) {
+          double d2 = 0.0;
+#pragma unroll
+          for(int d = 0; d < D; ++d) {
+            const double df = gx[d][tid] - (((q >> d) & 1) ? tmx[d] : tmn[d]);
+            d2 += df * df;
+          }
+          key = ((unsigned long long)__double_as_longlong(d2) & ~0x7full) | (unsigned long long)tid;
+        }
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+          key = other < key ? other : key;
+        }
+        if((tid & 31) == 0) repkey_sm[tid >> 5][q] = key;
+      }
+      __syncthreads();
+      if(tid < NC) {
+        unsigned long long key = repkey_sm[0][tid];
+#pragma unroll
+        for(int ww = 1; ww < NW; ++ww) key = repkey_sm[ww][tid] < key ? repkey_sm[ww][tid] : key;
+        rep_sm[tid] = (int)(key & 0x7full);
+      }
+      __syncthreads();
+    }
+    // hmax^2 with a safety margin for the quick node reject (distance between a node box and G's tight box)
+    const double ghmax2 = ghmax * ghmax * (1.0 + 1e-9);
     int ncur = 1, cur = 0;
     uint32_t ncands = 0;
     bool overflow = false;
     while(ncur > 0) {
-      uint32_t nnext = 0;
-      for(int base = 0; base < ncur; base += NT) {
-        const int j = base + tid;
+      // ---- phase A: test every frontier node (results to shared memory), count children / candidates -------
+      uint32_t my_nodes = 0, my_cands = 0;
+      for(int j = tid; j < ncur; j += NT) {
+        const int nd = queue[cur][j];
+        const NodeRec rec = t.noderec[nd];
         uint32_t node_mask = 0, cand_mask = 0;
-        int cb = 0;
-        if(j < ncur) {
-          const int nd = queue[cur][j];
-          double mn[D], mx[D];
+        bool ok = true;
+        if(gnode >= 0) {
+          // intersects_box_box(c, G)
+          bool sep = false;
 #pragma unroll
-          for(int d = 0; d < D; ++d) { mn[d] = t.bmin[d][nd]; mx[d] = t.bmax[d][nd]; }
-          bool ok = true;
-          if(gnode >= 0) {
-            // intersects_box_box(c, G)
-            bool sep = false;
+          for(int d = 0; d < D; ++d) sep = sep || (rec.bmax[d] < gmn[d]) || (gmx[d] < rec.bmin[d]);
+          ok = !sep;
+        }
+        if(ok) {
+          // quick reject (conservative, exact outcome): the node box is farther than hmax from every position of G
+          double dd = 0.0;
 #pragma unroll
-            for(int d = 0; d < D; ++d) sep = sep || (mx[d] < gmn[d]) || (gmx[d] < mn[d]);
-            ok = !sep;
+          for(int d = 0; d < D; ++d) {
+            const double tt = fmax(0.0, fmax(rec.bmin[d] - tmx[d], tmn[d] - rec.bmax[d]));
+            dd = dd + tt * tt;
           }
-          if(ok) {
-            bool acc = false;
-            for(int k = 0; k < P && !acc; ++k) {
-              double p[D];
+          ok = dd <= ghmax2;
+        }
+        if(ok) {
+          int q = 0;
 #pragma unroll
-              for(int d = 0; d < D; ++d) p[d] = gx[d][k];
-              acc = sphere_box<D>(mn, mx, p, gh[k]);
-            }
-            ok = acc;
+          for(int d = 0; d < D; ++d) q |= (int)((rec.bmin[d] + rec.bmax[d]) > (tmn[d] + tmx[d])) << d;
+          const int kr = rep_sm[q];
+          double p[D];
+#pragma unroll
+          for(int d = 0; d < D; ++d) p[d] = gx[d][kr];
+          bool acc = sphere_box<D>(rec.bmin, rec.bmax, p, gh[kr]);
+          for(int k = 0; k < P && !acc; ++k) {
+#pragma unroll
+            for(int d = 0; d < D; ++d) p[d] = gx[d][k];
+            acc = sphere_box<D>(rec.bmin, rec.bmax, p, gh[k]);
           }
-          if(ok) {
-            cb = t.child_begin[nd];
-            const int ce = t.child_end[nd];
-            for(int cc = cb; cc < ce; ++cc) {
-              const int v = t.cell[cc];
-              if(v < 0) node_mask |= 1u << (cc - cb);
-              else {
-                bool pass = true;
-                const double he = c.f[F_H][v];
-                double xe[D];
+          ok = acc;
+        }
+        if(ok) {
+          const int cb = rec.child_begin;
+          const uint32_t leafmask = rec.leafmask;
+          node_mask = ((1u << rec.nchild) - 1u) & ~leafmask;
+          uint32_t lm = leafmask;
+          while(lm) {
+            const int b = __ffs(lm) - 1;
+            lm &= lm - 1;
+            const LeafRec lr = t.leafrec[cb + b];
+            bool pass = true;
+            if(gnode >= 0) {
+              // |x_e - X_G|^2 <= (max(h_e, lap_G) + radius_G)^2, tree_topology.h:365-370
+              const double ext = fmax(lr.h, glap) + grad;
+              double s2 = 0.0;
 #pragma unroll
-                for(int d = 0; d < D; ++d) xe[d] = c.f[F_POS + d][v];
-                if(gnode >= 0) {
-                  // |x_e - X_G|^2 <= (max(h_e, lap_G) + radius_G)^2, tree_topology.h:365-370
-                  const double ext = fmax(he, glap) + grad;
-                  double s2 = 0.0;
-#pragma unroll
-                  for(int d = 0; d < D; ++d) {
-                    const double df = xe[d] - gcom[d];
-                    s2 = d == 0 ? df * df : s2 + df * df;
-                  }
-                  pass = s2 <= ext * ext;
-                }
-                if(pass) {
-                  const double hm = fmax(he, ghmax);
-                  double dd = 0.0;
-#pragma unroll
-                  for(int d = 0; d < D; ++d) {
-                    const double tt = fmax(0.0, fmax(tmn[d] - xe[d], xe[d] - tmx[d]));
-                    dd = dd + tt * tt;
-                  }
-                  pass = dd <= hm * hm * (1.0 + 1e-9);
-                }
-                if(pass) cand_mask |= 1u << (cc - cb);
+              for(int d = 0; d < D; ++d) {
+                const double df = lr.x[d] - gcom[d];
+                s2 = d == 0 ? df * df : s2 + df * df;
               }
+              pass = s2 <= ext * ext;
             }
+            if(pass) {
+              const double hm = fmax(lr.h, ghmax);
+              double dd = 0.0;
+#pragma unroll
+              for(int d = 0; d < D; ++d) {
+                const double tt = fmax(0.0, fmax(tmn[d] - lr.x[d], lr.x[d] - tmx[d]));
+                dd = dd + tt * tt;
+              }
+              pass = dd <= hm * hm * (1.0 + 1e-9);
+            }
+            if(pass) cand_mask |= 1u << b;
           }
         }
-        uint32_t packed = (uint32_t)__popc(node_mask) | ((uint32_t)__popc(cand_mask) << 16);
-        uint32_t total;
-        uint32_t ex = block_scan_u32<NT>(packed, total, scan_sm);
-        uint32_t qpos = nnext + (ex & 0xffffu), cpos = ncands + (ex >> 16);
+        qres[j] = node_mask | (cand_mask << 8);
+        my_nodes += __popc(node_mask);
+        my_cands += __popc(cand_mask);
+      }
+      // ---- one block scan per level: output order = (thread, frontier slot, child), fixed => deterministic --
+      uint32_t total;
+      const uint32_t ex = block_scan_u32<NT>(my_nodes | (my_cands << 16), total, scan_sm);
+      uint32_t qpos = ex & 0xffffu, cpos = ncands + (ex >> 16);
+      const uint32_t nnext_raw = total & 0xffffu;
+      // ---- phase B: write the next frontier and the candidates -----------------------------------------
+      for(int j = tid; j < ncur; j += NT) {
+        const uint32_t r = qres[j];
+        if(r == 0) continue;
+        const int nd = queue[cur][j];
+        const NodeRec rec = t.noderec[nd];
+        uint32_t node_mask = r & 0xffu, cand_mask = r >> 8;
         while(node_mask) {
-          int b = __ffs(node_mask) - 1;
+          const int b = __ffs(node_mask) - 1;
           node_mask &= node_mask - 1;
-          if(qpos < SR_QCAP) queue[cur ^ 1][qpos] = ~t.cell[cb + b];
+          // node children of a node have consecutive node indices (level order)
+          if(qpos < SR_QCAP) queue[cur ^ 1][qpos] = rec.first_child_node + __popc(~rec.leafmask & ((1u << b) - 1u));
           ++qpos;
         }
         if(FILL) {
           while(cand_mask) {
-            int b = __ffs(cand_mask) - 1;
+            const int b = __ffs(cand_mask) - 1;
             cand_mask &= cand_mask - 1;
-            if(MODE == 1 || cpos < (uint32_t)scratch_cap) cout[cpos] = t.cell[cb + b];
+            if(MODE == 1 || cpos < (uint32_t)scratch_cap) cout[cpos] = t.cell[rec.child_begin + b];
             ++cpos;
           }
         }
-        nnext += total & 0xffffu;
-        ncands += total >> 16;
       }
+      ncands += total >> 16;
+      uint32_t nnext = nnext_raw;
       if(nnext > SR_QCAP) {
         if(tid == 0) atomicOr(status, (uint32_t)ERR_QUEUE_OVERFLOW);
         nnext = SR_QCAP;
@@ -378,7 +440,7 @@ static void neighbor_search_t(System & s) {
   unsigned long long * cursors = reinterpret_cast<unsigned long long *>(s.b_status.as<uint32_t>() + 8);
   // single pass when the previous search on this system gives a capacity estimate
   if(s.est_cand > 0 && s.est_n == s.n) {
-    const int grid_cap = 148 * 8, scratch_cap = 16384;
+    const int grid_cap = 148 * 12, scratch_cap = 16384;
     const unsigned long long cand_cap = s.est_cand + s.est_cand / 4 + 65536, mask_cap = s.est_mask + s.est_mask / 4 + 65536;
     s.b_cand.reserve((size_t)cand_cap * 4);
     s.b_mask.reserve((size_t)mask_cap * 4);

@@ -374,6 +374,44 @@ __global__ void __launch_bounds__(128) k_cofm(Tree t, Cols c, int nb, int ne) {
   }
 }
 
+// packed walk records (fsph_search.cu) from the SoA tables
+template<int D>
+__global__ void __launch_bounds__(256) k_pack_nodes(Tree t, int nn) {
+  int nd = blockIdx.x * blockDim.x + threadIdx.x;
+  if(nd >= nn) return;
+  NodeRec r;
+#pragma unroll
+  for(int d = 0; d < 3; ++d) {
+    r.bmin[d] = d < D ? t.bmin[d][nd] : 0.0;
+    r.bmax[d] = d < D ? t.bmax[d][nd] : 0.0;
+  }
+  const int cb = t.child_begin[nd], ce = t.child_end[nd];
+  uint32_t leafmask = 0;
+  int first = -1;
+  for(int cc = cb; cc < ce; ++cc) {
+    const int v = t.cell[cc];
+    if(v >= 0) leafmask |= 1u << (cc - cb);
+    else if(first < 0) first = ~v;
+  }
+  r.child_begin = cb;
+  r.first_child_node = first;
+  r.nchild = (uint32_t)(ce - cb);
+  r.leafmask = leafmask;
+  t.noderec[nd] = r;
+}
+template<int D>
+__global__ void __launch_bounds__(256) k_pack_leaves(Tree t, Cols c, int64_t nc) {
+  int64_t cc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(cc >= nc) return;
+  const int v = t.cell[cc];
+  if(v < 0) return;
+  LeafRec r;
+#pragma unroll
+  for(int d = 0; d < 3; ++d) r.x[d] = d < D ? c.f[F_POS + d][v] : 0.0;
+  r.h = c.f[F_H][v];
+  t.leafrec[cc] = r;
+}
+
 template<int D>
 static void build_tree_t(System & s) {
   const int64_t n = s.n;
@@ -422,6 +460,10 @@ static void build_tree_t(System & s) {
   for(int d = 0; d < 3; ++d) { t.com[d] = s.b_ncom[d].as<double>(); t.bmin[d] = s.b_nbmin[d].as<double>(); t.bmax[d] = s.b_nbmax[d].as<double>(); }
   t.ncells = (int)nc;
   t.nnodes = (int)nn;
+  s.b_noderec.reserve((size_t)std::max<int64_t>(nn, 1) * sizeof(NodeRec));
+  s.b_leafrec.reserve((size_t)nc * sizeof(LeafRec));
+  t.noderec = s.b_noderec.as<NodeRec>();
+  t.leafrec = s.b_leafrec.as<LeafRec>();
   s.b_levels.reserve(MAX_LEVELS * sizeof(int32_t));
   int32_t * lv = s.b_levels.as<int32_t>();
   FSPH_CUDA_OK(cudaMemsetAsync(lv, 0xff, MAX_LEVELS * sizeof(int32_t), s.stream));
@@ -441,6 +483,8 @@ static void build_tree_t(System & s) {
     if(e <= b) continue;
     FSPH_LAUNCH((k_cofm<D>), (e - b + 127) / 128, 128, s.stream, t, s.cols(), b, e);
   }
+  FSPH_LAUNCH((k_pack_nodes<D>), (unsigned)((nn + 255) / 256), 256, s.stream, t, (int)nn);
+  FSPH_LAUNCH((k_pack_leaves<D>), nbc, 256, s.stream, t, s.cols(), nc);
   FSPH_CUDA_OK(cudaGetLastError());
 }
 
