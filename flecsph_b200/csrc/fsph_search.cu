@@ -253,34 +253,42 @@ __global__ void __launch_bounds__(32 * NW) k_search(Tree t, Cols c, Search sr, i
           const int cb = rec.child_begin;
           const uint32_t leafmask = rec.leafmask;
           node_mask = ((1u << rec.nchild) - 1u) & ~leafmask;
-          uint32_t lm = leafmask;
-          while(lm) {
-            const int b = __ffs(lm) - 1;
-            lm &= lm - 1;
-            const LeafRec lr = t.leafrec[cb + b];
-            bool pass = true;
-            if(gnode >= 0) {
-              // |x_e - X_G|^2 <= (max(h_e, lap_G) + radius_G)^2, tree_topology.h:365-370
-              const double ext = fmax(lr.h, glap) + grad;
-              double s2 = 0.0;
+          // leaf children in two batches of four: all loads of a batch are issued before the first use
 #pragma unroll
-              for(int d = 0; d < D; ++d) {
-                const double df = lr.x[d] - gcom[d];
-                s2 = d == 0 ? df * df : s2 + df * df;
-              }
-              pass = s2 <= ext * ext;
-            }
-            if(pass) {
-              const double hm = fmax(lr.h, ghmax);
-              double dd = 0.0;
+          for(int half = 0; half < ((1 << D) + 3) / 4; ++half) {
+            const uint32_t lm4 = (leafmask >> (4 * half)) & 0xfu;
+            if(lm4 == 0) continue;
+            LeafRec lr[4];
 #pragma unroll
-              for(int d = 0; d < D; ++d) {
-                const double tt = fmax(0.0, fmax(tmn[d] - lr.x[d], lr.x[d] - tmx[d]));
-                dd = dd + tt * tt;
+            for(int jj = 0; jj < 4; ++jj)
+              if((lm4 >> jj) & 1u) lr[jj] = t.leafrec[cb + 4 * half + jj];
+#pragma unroll
+            for(int jj = 0; jj < 4; ++jj) {
+              if(!((lm4 >> jj) & 1u)) continue;
+              bool pass = true;
+              if(gnode >= 0) {
+                // |x_e - X_G|^2 <= (max(h_e, lap_G) + radius_G)^2, tree_topology.h:365-370
+                const double ext = fmax(lr[jj].h, glap) + grad;
+                double s2 = 0.0;
+#pragma unroll
+                for(int d = 0; d < D; ++d) {
+                  const double df = lr[jj].x[d] - gcom[d];
+                  s2 = d == 0 ? df * df : s2 + df * df;
+                }
+                pass = s2 <= ext * ext;
               }
-              pass = dd <= hm * hm * (1.0 + 1e-9);
+              if(pass) {
+                const double hm = fmax(lr[jj].h, ghmax);
+                double dd = 0.0;
+#pragma unroll
+                for(int d = 0; d < D; ++d) {
+                  const double tt = fmax(0.0, fmax(tmn[d] - lr[jj].x[d], lr[jj].x[d] - tmx[d]));
+                  dd = dd + tt * tt;
+                }
+                pass = dd <= hm * hm * (1.0 + 1e-9);
+              }
+              if(pass) cand_mask |= 1u << (4 * half + jj);
             }
-            if(pass) cand_mask |= 1u << b;
           }
         }
         qres[j] = node_mask | (cand_mask << 8);
@@ -306,11 +314,15 @@ __global__ void __launch_bounds__(32 * NW) k_search(Tree t, Cols c, Search sr, i
           if(qpos < SR_QCAP) queue[cur ^ 1][qpos] = rec.first_child_node + __popc(~rec.leafmask & ((1u << b) - 1u));
           ++qpos;
         }
-        if(FILL) {
-          while(cand_mask) {
-            const int b = __ffs(cand_mask) - 1;
-            cand_mask &= cand_mask - 1;
-            if(MODE == 1 || cpos < (uint32_t)scratch_cap) cout[cpos] = t.cell[rec.child_begin + b];
+        if(FILL && cand_mask) {
+          int cv[1 << D];
+#pragma unroll
+          for(int b = 0; b < (1 << D); ++b)
+            if((cand_mask >> b) & 1u) cv[b] = t.cell[rec.child_begin + b];
+#pragma unroll
+          for(int b = 0; b < (1 << D); ++b) {
+            if(!((cand_mask >> b) & 1u)) continue;
+            if(MODE == 1 || cpos < (uint32_t)scratch_cap) cout[cpos] = cv[b];
             ++cpos;
           }
         }
