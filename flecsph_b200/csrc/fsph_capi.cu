@@ -126,17 +126,19 @@ void do_step(System & s, int initial) {
   const fsph_params & P = s.par;
   if(P.enable_fmm) throw std::runtime_error("FMM gravity is not implemented on the device yet");
   auto A = [&](int op) { PhaseScope p(s, "elementwise"); apply(s, op); };
+  // the element-wise functors after the last sweep of the iteration are issued as one fused pass
+  const int recompute_op = P.thermokinetic_formulation ? FSPH_APPLY_RECOMPUTE_P_CS_THERMOKINETIC : FSPH_APPLY_RECOMPUTE_P_CS;
+  const int energy_sweep = P.thermokinetic_formulation ? FSPH_SWEEP_DEDT : FSPH_SWEEP_DUDT;
+  const int kick_energy = P.thermokinetic_formulation ? FSPH_APPLY_LEAPFROG_KICK_E : FSPH_APPLY_LEAPFROG_KICK_U;
+  int tail[8], ntail = 0;
   auto energy_passes = [&]() {
     for(int m = 1; m <= P.pressure_updates_number; ++m) {
-      if(P.thermokinetic_formulation) {
-        do_sweep(s, FSPH_SWEEP_DEDT);
-        A(FSPH_APPLY_RECOMPUTE_P_CS_THERMOKINETIC);
+      do_sweep(s, energy_sweep);
+      if(m < P.pressure_updates_number) {
+        A(recompute_op);
+        do_reset_ghosts(s);
       }
-      else {
-        do_sweep(s, FSPH_SWEEP_DUDT);
-        A(FSPH_APPLY_RECOMPUTE_P_CS);
-      }
-      if(m < P.pressure_updates_number) do_reset_ghosts(s);
+      else tail[ntail++] = recompute_op;
     }
   };
   auto timestep = [&]() {
@@ -158,11 +160,32 @@ void do_step(System & s, int initial) {
     if(P.evolve_internal_energy) energy_passes();
   }
   else {
-    if(P.evolve_internal_energy) A(P.thermokinetic_formulation ? FSPH_APPLY_LEAPFROG_KICK_E : FSPH_APPLY_LEAPFROG_KICK_U);
-    A(FSPH_APPLY_LEAPFROG_KICK_V);
-    A(FSPH_APPLY_SAVE_VELOCITYHALF);
-    A(FSPH_APPLY_LEAPFROG_DRIFT);
-    do_update_iteration(s);
+    {
+      // kick e|u, kick v, save v_half, drift: four functors, one pass
+      PhaseScope p(s, "elementwise");
+      int ops[4], k = 0;
+      if(P.evolve_internal_energy) ops[k++] = kick_energy;
+      ops[k++] = FSPH_APPLY_LEAPFROG_KICK_V;
+      ops[k++] = FSPH_APPLY_SAVE_VELOCITYHALF;
+      ops[k++] = FSPH_APPLY_LEAPFROG_DRIFT;
+      apply_fused(s, ops, k);
+    }
+    {
+      // columns the rest of this iteration overwrites before reading: acc, gacc, gpot (acceleration sweep),
+      // rho, P (density sweep), vsig, dt, the energy derivative, and u when it is recovered from e
+      for(int f = 0; f < NF64; ++f) s.dead_col[f] = false;
+      for(int d = 0; d < 3; ++d) s.dead_col[F_ACC + d] = s.dead_col[F_GACC + d] = true;
+      s.dead_col[F_GPOT] = s.dead_col[F_RHO] = s.dead_col[F_P] = s.dead_col[F_VSIG] = s.dead_col[F_CSOLD] = true;
+      if(P.adaptive_timestep) s.dead_col[F_DT] = true;
+      if(P.evolve_internal_energy) {
+        if(P.thermokinetic_formulation) s.dead_col[F_DEDT] = s.dead_col[F_U] = true;
+        else s.dead_col[F_DUDT] = true;
+      }
+      s.skip_dead_columns = true;
+      try { do_update_iteration(s); }
+      catch(...) { s.skip_dead_columns = false; throw; }
+      s.skip_dead_columns = false;
+    }
     do_sweep(s, 100);
     do_reset_ghosts(s);
     do_sweep(s, 101);
@@ -170,17 +193,27 @@ void do_step(System & s, int initial) {
     do_reset_ghosts(s);
     if(P.evolve_internal_energy) {
       energy_passes();
-      A(P.thermokinetic_formulation ? FSPH_APPLY_LEAPFROG_KICK_E : FSPH_APPLY_LEAPFROG_KICK_U);
+      tail[ntail++] = kick_energy;
     }
   }
   {
     PhaseScope p(s, "elementwise");
-    if(P.sph_variable_h) reduce(s, FSPH_GET_COMPUTE_SMOOTHINGLENGTH, nullptr, 0);
-    else if(P.sph_update_uniform_h) reduce(s, FSPH_GET_COMPUTE_AVERAGE_SMOOTHINGLENGTH, nullptr, 0);
-    apply(s, FSPH_APPLY_CHECK_NANS);
-    apply(s, FSPH_APPLY_CHECK_NEGATIVITY);
+    if(P.sph_variable_h) tail[ntail++] = 100;
+    else if(P.sph_update_uniform_h) {
+      // needs a global sum in the middle: flush what is queued, then the reference's own sequence
+      apply_fused(s, tail, ntail);
+      ntail = 0;
+      reduce(s, FSPH_GET_COMPUTE_AVERAGE_SMOOTHINGLENGTH, nullptr, 0);
+    }
+    tail[ntail++] = FSPH_APPLY_CHECK_NANS;
+    tail[ntail++] = FSPH_APPLY_CHECK_NEGATIVITY;
+    if(P.adaptive_timestep) tail[ntail++] = FSPH_APPLY_COMPUTE_DT;
+    apply_fused(s, tail, ntail);
   }
-  timestep();
+  if(P.adaptive_timestep) {
+    PhaseScope p(s, "timestep");
+    reduce(s, FSPH_GET_SET_ADAPTIVE_TIMESTEP, nullptr, 0);
+  }
   check_status(s);
   // physics::advance_time, default_physics.h:853-860
   s.iteration++;

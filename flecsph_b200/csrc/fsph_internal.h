@@ -119,6 +119,9 @@ struct System {
   int64_t iteration = 0;
   double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
   bool tree_valid = false, search_valid = false, tree_dirty = false;
+  // inside fsph_step the sort need not permute columns that are recomputed before their next read
+  bool skip_dead_columns = false;
+  bool dead_col[NF64] = {};
 
   // storage
   DevBuf col[NF64], col_id, col_key, col_type, col_nneigh, scratch_col;
@@ -187,7 +190,8 @@ void export_neighbors(System & s, std::vector<int64_t> & off, std::vector<int64_
 void sweep(System & s, int op);                 // default_physics.h:193-566
 
 // ---- fsph_apply.cu --------------------------------------------------------------------------
-void apply(System & s, int op);                 // integration.h, default_physics.h element-wise
+void apply(System & s, int op);                  // integration.h, default_physics.h element-wise
+void apply_fused(System & s, const int * ops, int nops);  // several of them in one pass (same per-particle order)
 void reduce(System & s, int op, double * out, int nout);
 double max_h(System & s);
 void check_status(System & s);                  // throws on latched device errors

@@ -186,6 +186,7 @@ void sort_bodies(System & s) {
     for(int f = 0; f < NF64; ++f) {
       if(f < F_MASS && (f % 3) >= s.dim) continue;  // unused vector components
       if(f == F_PRHO2) continue;                      // derived column
+      if(s.skip_dead_columns && s.dead_col[f]) continue;  // fsph_step: rewritten before it is next read
       gather8(s, s.col[f], perm);
     }
     gather8(s, s.col_id, perm);
