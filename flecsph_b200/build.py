@@ -60,10 +60,20 @@ def build_cuda(verbose=False, force=False):
 def build_oracle():
     """oracle/_ref from /root/reference when it is present (dev container); prebuilt files travel to the GPU box."""
     if os.path.isdir("/root/reference/include"):
-        r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref", "ref_fast"], capture_output=True, text=True)
+        r = subprocess.run(["make", "-j4", "-C", os.path.join(ROOT, "oracle"), "ref", "ref_fast", "drivers"], capture_output=True, text=True)
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("oracle/_ref build failed")
+
+
+def build_host_drivers():
+    """The unmodified reference drivers against the GPU facade (flecsph_b200/host): needs the reference checkout for
+    the driver sources and physics headers, so dev container only; the binaries travel to the GPU box."""
+    if os.path.isdir("/root/reference/app/drivers"):
+        r = subprocess.run(["make", "-j4", "-C", os.path.join(ROOT, "flecsph_b200", "host")], capture_output=True, text=True)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("host driver build failed")
 
 
 if __name__ == "__main__":

@@ -35,7 +35,9 @@ SWEEP_DENSITY, SWEEP_ACCELERATION, SWEEP_DUDT, SWEEP_DEDT, SWEEP_NEIGHBORS_ONLY 
  APPLY_CHECK_NEGATIVITY) = range(12)
 # enum fsph_reduce_op
 (GET_SET_ADAPTIVE_TIMESTEP, GET_COMPUTE_SMOOTHINGLENGTH, GET_COMPUTE_AVERAGE_SMOOTHINGLENGTH, GET_TOTAL_MASS,
- GET_TOTAL_ENERGY, GET_TOTAL_MOMENTUM) = range(6)
+ GET_TOTAL_ENERGY, GET_TOTAL_MOMENTUM, GET_TOTAL_KINETIC_ENERGY, GET_TOTAL_INTERNAL_ENERGY,
+ GET_TOTAL_GRAVITATIONAL_ENERGY, GET_TOTAL_ANG_MOM, GET_SMOOTHINGLENGTH_STATS, GET_VELOCITY_STATS,
+ GET_NEIGHBORS_STATS) = range(13)
 
 
 class Params(C.Structure):
@@ -63,8 +65,10 @@ SYMBOLS = [
     "fsph_get_time", "fsph_advance_time", "fsph_update_iteration", "fsph_reset_ghosts", "fsph_sweep", "fsph_apply",
     "fsph_reduce", "fsph_gravitation_fmm", "fsph_get_range", "fsph_get_smoothinglength", "fsph_step",
     "fsph_tree_num_nodes", "fsph_tree_get_nodes", "fsph_tree_get_leaf_depth", "fsph_neighbor_lists",
-    "fsph_phase_times",
+    "fsph_phase_times", "fsph_set_time_state", "fsph_get_time_state", "fsph_tree_root",
 ]
+# entry points only the product library has to provide (the checkers under oracle/ may omit them)
+PRODUCT_ONLY = {"fsph_set_time_state", "fsph_get_time_state", "fsph_tree_root"}
 
 PRODUCT_LIB = os.path.join(ROOT, "flecsph_b200", "libflecsph_b200.so")
 
@@ -125,8 +129,13 @@ def load(path):
         "fsph_tree_get_leaf_depth": (i32, [vp, vp]),
         "fsph_neighbor_lists": (i32, [vp, vp, vp]),
         "fsph_phase_times": (i32, [vp, vp, i32, C.POINTER(C.c_char_p)]),
+        "fsph_set_time_state": (i32, [vp, vp, i64]),
+        "fsph_get_time_state": (i32, [vp, vp, C.POINTER(i64)]),
+        "fsph_tree_root": (i32, [vp, vp, C.POINTER(dbl)]),
     }
     for name, (res, args) in sig.items():
+        if name in PRODUCT_ONLY and not hasattr(lib, name):
+            continue
         f = getattr(lib, name)
         f.restype, f.argtypes = res, args
     _LIBS[path] = lib
@@ -237,6 +246,23 @@ class BodySystem:
         dt, t, it = C.c_double(), C.c_double(), C.c_int64()
         self._ck(self.lib.fsph_get_time(self.h, C.byref(dt), C.byref(t), C.byref(it)))
         return dt.value, t.value, it.value
+
+    def set_time_state(self, st, iteration):
+        """st = [dt, dt_saved, totaltime, totaltime_next, t_h5data_output, t_screen_output, t_scalar_output]."""
+        a = np.ascontiguousarray(st, dtype=np.float64)
+        self._ck(self.lib.fsph_set_time_state(self.h, a.ctypes.data, int(iteration)))
+
+    def get_time_state(self):
+        a = np.zeros(7)
+        it = C.c_int64()
+        self._ck(self.lib.fsph_get_time_state(self.h, a.ctypes.data, C.byref(it)))
+        return a, it.value
+
+    def tree_root(self):
+        com = np.zeros(self.dim)
+        m = C.c_double()
+        self._ck(self.lib.fsph_tree_root(self.h, com.ctypes.data, C.byref(m)))
+        return com, m.value
 
     def advance_time(self):
         self._ck(self.lib.fsph_advance_time(self.h))

@@ -182,13 +182,22 @@ void apply_fused(System & s, const int * op_list, int nops) {
 void apply(System & s, int op) { apply_fused(s, &op, 1); }
 
 // ---- reductions: per-block partials in a fixed order, finished on the host (deterministic) ------------------
-enum RedKind { RED_MIN_DT = 0, RED_MAX_H, RED_SUM_H, RED_MASS, RED_ENERGY, RED_MOMENTUM };
+enum RedKind { RED_MIN_DT = 0, RED_MAX_H, RED_SUM_H, RED_MASS, RED_ENERGY, RED_MOMENTUM, RED_EKIN, RED_EINT, RED_EGRAV, RED_ANGMOM,
+               RED_H_STATS, RED_V_STATS, RED_N_STATS };
+// kinds >= RED_H_STATS reduce {min, max, sum} in slots 0, 1, 2
+__host__ __device__ inline double red_combine(int kind, int j, double a, double b) {
+  if(kind == RED_MIN_DT) return fmin(a, b);
+  if(kind == RED_MAX_H) return fmax(a, b);
+  if(kind >= RED_H_STATS) return j == 0 ? fmin(a, b) : (j == 1 ? fmax(a, b) : a + b);
+  return a + b;
+}
 
 template<int D>
 __global__ void __launch_bounds__(256) k_reduce(Cols c, int64_t n, int kind, int thermokinetic, int fmm, double * __restrict__ part) {
   double v[3] = {0, 0, 0};
   if(kind == RED_MIN_DT) v[0] = 1e24;
   if(kind == RED_MAX_H) v[0] = -DBL_MAX;
+  if(kind >= RED_H_STATS) { v[0] = DBL_MAX; v[1] = kind == RED_N_STATS ? 0.0 : DBL_MIN; }
   for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     switch(kind) {
       case RED_MIN_DT: v[0] = fmin(v[0], c.f[F_DT][i]); break;
@@ -216,6 +225,48 @@ __global__ void __launch_bounds__(256) k_reduce(Cols c, int64_t n, int kind, int
           for(int d = 0; d < D; ++d) v[d] += c.f[F_MASS][i] * c.f[F_VEL + d][i];
         }
         break;
+      case RED_EKIN:
+        if(c.type[i] == 0) {
+          double v2 = 0.0;
+#pragma unroll
+          for(int d = 0; d < D; ++d) v2 += c.f[F_VEL + d][i] * c.f[F_VEL + d][i];
+          v[0] += .5 * c.f[F_MASS][i] * v2;
+        }
+        break;
+      case RED_EINT:
+        if(c.type[i] == 0) v[0] += c.f[F_MASS][i] * c.f[F_U][i];
+        break;
+      case RED_EGRAV:
+        if(c.type[i] == 0) v[0] += c.f[F_GPOT][i] * c.f[F_MASS][i];
+        break;
+      case RED_ANGMOM:
+        if(c.type[i] == 0) {
+          const double m = c.f[F_MASS][i];
+          if(D == 2) v[0] += m * (c.f[F_POS][i] * c.f[F_VEL + 1][i] - c.f[F_POS + 1][i] * c.f[F_VEL][i]);
+          if(D == 3) {
+            const double r0 = c.f[F_POS][i], r1 = c.f[F_POS + 1][i], r2 = c.f[F_POS + (D > 2 ? 2 : 0)][i];
+            const double w0 = c.f[F_VEL][i], w1 = c.f[F_VEL + 1][i], w2 = c.f[F_VEL + (D > 2 ? 2 : 0)][i];
+            v[0] += m * (r1 * w2 - r2 * w1);
+            v[1] += m * (r2 * w0 - r0 * w2);
+            v[2] += m * (r0 * w1 - r1 * w0);
+          }
+        }
+        break;
+      case RED_H_STATS: {
+        const double h = c.f[F_H][i];
+        v[0] = fmin(v[0], h); v[1] = fmax(v[1], h); v[2] += h;
+      } break;
+      case RED_V_STATS: {
+        double v2 = 0.0;
+#pragma unroll
+        for(int d = 0; d < D; ++d) v2 += c.f[F_VEL + d][i] * c.f[F_VEL + d][i];
+        const double vn = sqrt(v2);
+        v[0] = fmin(v[0], vn); v[1] = fmax(v[1], vn); v[2] += vn;
+      } break;
+      case RED_N_STATS: {
+        const double nn = (double)c.nneigh[i];
+        v[0] = fmin(v[0], nn); v[1] = fmax(v[1], nn); v[2] += nn;
+      } break;
     }
   }
   __shared__ double sm[8][3];
@@ -225,7 +276,7 @@ __global__ void __launch_bounds__(256) k_reduce(Cols c, int64_t n, int kind, int
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) {
       double u = __shfl_xor_sync(0xffffffffu, v[j], o);
-      v[j] = kind == RED_MIN_DT ? fmin(v[j], u) : (kind == RED_MAX_H ? fmax(v[j], u) : v[j] + u);
+      v[j] = red_combine(kind, j, v[j], u);
     }
     if(lane == 0) sm[w][j] = v[j];
   }
@@ -234,7 +285,7 @@ __global__ void __launch_bounds__(256) k_reduce(Cols c, int64_t n, int kind, int
     double r = sm[0][threadIdx.x];
     for(int ww = 1; ww < 8; ++ww) {
       double u = sm[ww][threadIdx.x];
-      r = kind == RED_MIN_DT ? fmin(r, u) : (kind == RED_MAX_H ? fmax(r, u) : r + u);
+      r = red_combine(kind, (int)threadIdx.x, r, u);
     }
     part[(size_t)blockIdx.x * 3 + threadIdx.x] = r;
   }
@@ -253,7 +304,7 @@ static void run_reduce(System & s, int kind, double out[3]) {
     double r = h[j];
     for(int b = 1; b < nb; ++b) {
       double u = h[(size_t)b * 3 + j];
-      r = kind == RED_MIN_DT ? std::fmin(r, u) : (kind == RED_MAX_H ? std::fmax(r, u) : r + u);
+      r = red_combine(kind, j, r, u);
     }
     out[j] = r;
   }
@@ -313,6 +364,13 @@ void reduce(System & s, int op, double * out, int nout) {
     case FSPH_GET_TOTAL_MASS: run_reduce(s, RED_MASS, o); break;
     case FSPH_GET_TOTAL_ENERGY: run_reduce(s, RED_ENERGY, o); break;
     case FSPH_GET_TOTAL_MOMENTUM: run_reduce(s, RED_MOMENTUM, o); break;
+    case FSPH_GET_TOTAL_KINETIC_ENERGY: run_reduce(s, RED_EKIN, o); break;
+    case FSPH_GET_TOTAL_INTERNAL_ENERGY: run_reduce(s, RED_EINT, o); break;
+    case FSPH_GET_TOTAL_GRAVITATIONAL_ENERGY: run_reduce(s, RED_EGRAV, o); o[0] *= 0.5; break;
+    case FSPH_GET_TOTAL_ANG_MOM: run_reduce(s, RED_ANGMOM, o); break;
+    case FSPH_GET_SMOOTHINGLENGTH_STATS: run_reduce(s, RED_H_STATS, o); break;
+    case FSPH_GET_VELOCITY_STATS: run_reduce(s, RED_V_STATS, o); break;
+    case FSPH_GET_NEIGHBORS_STATS: run_reduce(s, RED_N_STATS, o); break;
     default: throw std::runtime_error("unknown reduce op");
   }
   for(int j = 0; j < nout && j < 3; ++j) out[j] = o[j];

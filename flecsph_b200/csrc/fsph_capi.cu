@@ -512,6 +512,22 @@ int32_t fsph_advance_time(fsph_system * s) {
   return 0;
 }
 
+int32_t fsph_set_time_state(fsph_system * s, const double * st, int64_t iteration) {
+  if(!s || !st) return 1;
+  s->dt = st[0]; s->dt_saved = st[1]; s->totaltime = st[2]; s->totaltime_next = st[3];
+  // System::t_out is ordered screen, scalar, h5data (the order set_adaptive_timestep visits them)
+  s->t_out[2] = st[4]; s->t_out[0] = st[5]; s->t_out[1] = st[6];
+  s->iteration = iteration;
+  return 0;
+}
+int32_t fsph_get_time_state(const fsph_system * s, double * st, int64_t * iteration) {
+  if(!s || !st) return 1;
+  st[0] = s->dt; st[1] = s->dt_saved; st[2] = s->totaltime; st[3] = s->totaltime_next;
+  st[4] = s->t_out[2]; st[5] = s->t_out[0]; st[6] = s->t_out[1];
+  if(iteration) *iteration = s->iteration;
+  return 0;
+}
+
 int32_t fsph_update_iteration(fsph_system * s) {
   return guarded(s, [&]() { do_update_iteration(*s); check_status(*s); });
 }
@@ -606,6 +622,17 @@ int32_t fsph_tree_get_nodes(fsph_system * s, uint64_t * key, double * mass, doub
       get(tmp.data(), s->tree.bmax[d], (size_t)nn * 8);
       for(int i = 0; i < nn; ++i) bmax[(size_t)i * D + d] = tmp[i];
     }
+  });
+}
+
+int32_t fsph_tree_root(fsph_system * s, double * com, double * mass) {
+  return guarded(s, [&]() {
+    if(!s->tree_valid) throw std::runtime_error("no tree");
+    // node 0 of the level-ordered node table is the root
+    for(int d = 0; d < s->dim; ++d)
+      FSPH_CUDA_OK(cudaMemcpyAsync(com + d, s->tree.com[d], 8, cudaMemcpyDeviceToHost, s->stream));
+    if(mass) FSPH_CUDA_OK(cudaMemcpyAsync(mass, s->tree.mass, 8, cudaMemcpyDeviceToHost, s->stream));
+    FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
   });
 }
 

@@ -1,7 +1,8 @@
-/* Single-rank MPI stand-in used ONLY to compile the unmodified reference
- * headers (/root/reference) into the test oracle oracle/_ref/.  Rank 0 of 1:
- * collectives copy send->recv, point-to-point calls abort (never reached
- * with one rank).  TEST INFRASTRUCTURE ONLY. */
+/* Single-process MPI stand-in for hosts WITHOUT an MPI installation (this image has none): lets the unmodified
+ * reference drivers and headers (/root/reference) compile -- against the GPU facade (flecsph_b200/host/bodies_system.h)
+ * for the product drivers, and against the reference's own body_system for the test oracle (oracle/_ref).  Rank 0 of 1:
+ * collectives copy send->recv, point-to-point calls abort (never reached with one rank).
+ * With a real MPI, drop this directory from the include path. */
 #ifndef FSPH_SHIM_MPI_H
 #define FSPH_SHIM_MPI_H
 #include <climits>

@@ -150,7 +150,14 @@ enum fsph_reduce_op {
   FSPH_GET_COMPUTE_AVERAGE_SMOOTHINGLENGTH,/* physics::compute_average_smoothinglength, default_physics.h:879 */
   FSPH_GET_TOTAL_MASS,                     /* analysis::compute_total_mass, analysis.h:69; out[0] */
   FSPH_GET_TOTAL_ENERGY,                   /* analysis::compute_total_energy, analysis.h:113; out[0] */
-  FSPH_GET_TOTAL_MOMENTUM                  /* analysis::compute_total_momentum, analysis.h:56; out[0..dim) */
+  FSPH_GET_TOTAL_MOMENTUM,                 /* analysis::compute_total_momentum, analysis.h:56; out[0..dim) */
+  FSPH_GET_TOTAL_KINETIC_ENERGY,           /* analysis::compute_total_kinetic_energy, analysis.h:131; out[0] */
+  FSPH_GET_TOTAL_INTERNAL_ENERGY,          /* analysis::compute_total_internal_energy, analysis.h:147; out[0] */
+  FSPH_GET_TOTAL_GRAVITATIONAL_ENERGY,     /* analysis::compute_total_gravitational_energy, analysis.h:160; out[0] */
+  FSPH_GET_TOTAL_ANG_MOM,                  /* analysis::compute_total_ang_mom, analysis.h:176; out[0] (2-D) / out[0..3) (3-D) */
+  FSPH_GET_SMOOTHINGLENGTH_STATS,          /* diagnostic::compute_smoothinglength_stats, diagnostic.h:71; out = {min, max, sum} */
+  FSPH_GET_VELOCITY_STATS,                 /* diagnostic::compute_velocity_stats, diagnostic.h:93; out = {min, max, sum} of |v| */
+  FSPH_GET_NEIGHBORS_STATS                 /* diagnostic::compute_neighbors_stats, diagnostic.h:46; out = {min, max, sum} of the counts */
 };
 
 /* --- life cycle ---------------------------------------------------------- */
@@ -181,6 +188,11 @@ int32_t fsph_download_aos(fsph_system * s, void * bodies, int64_t stride, const 
 int32_t fsph_set_time(fsph_system * s, double dt, double totaltime, int64_t iteration);
 int32_t fsph_get_time(const fsph_system * s, double * dt, double * totaltime, int64_t * iteration);
 int32_t fsph_advance_time(fsph_system * s);                       /* physics::advance_time, default_physics.h:853 */
+/* All eight time globals at once, in the order of default_physics.h:32-39: dt, dt_saved, totaltime, totaltime_next,
+ * t_h5data_output, t_screen_output, t_scalar_output (st[0..7)) and iteration.  The C++ facade mirrors the host
+ * globals into the system before a device call and back after set_adaptive_timestep. */
+int32_t fsph_set_time_state(fsph_system * s, const double * st, int64_t iteration);
+int32_t fsph_get_time_state(const fsph_system * s, double * st, int64_t * iteration);
 
 /* --- the hot path --------------------------------------------------------- */
 int32_t fsph_update_iteration(fsph_system * s);                   /* bodies_system.h:152: range, keys, sort, tree */
@@ -205,6 +217,8 @@ int32_t fsph_step(fsph_system * s, int32_t initial);
 int64_t fsph_tree_num_nodes(fsph_system * s);
 int32_t fsph_tree_get_nodes(fsph_system * s, uint64_t * key, double * mass, double * com /*[nn][dim]*/,
   double * radius, double * lap, double * bmin /*[nn][dim]*/, double * bmax /*[nn][dim]*/, int64_t * sub_entities);
+/* Root node of the tree: tree()->root_node()->coordinates() / mass() (analysis.h:396, mpisph/test/tree3d.cc:85). */
+int32_t fsph_tree_root(fsph_system * s, double * com /*[dim]*/, double * mass);
 /* Depth of every particle's leaf cell in the tree (in storage order). */
 int32_t fsph_tree_get_leaf_depth(fsph_system * s, int32_t * depth);
 /* Neighbour lists of the last sweep in CSR form, neighbour *ids* sorted

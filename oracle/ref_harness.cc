@@ -11,7 +11,7 @@
  * What is the reference's code here: everything under namespaces physics,
  * kernels, viscosity, eos, integration, fmm, analysis, flecsi::topology,
  * psort and class body_system (mpisph/bodies_system.h).  What is ours: the
- * single-rank MPI/FleCSI/Boost stand-ins in oracle/shim/, the in-memory
+ * single-rank MPI/FleCSI/Boost stand-ins in flecsph_b200/host/shim/, the in-memory
  * io:: stub below (the image has no HDF5), the column marshalling, and
  * fsph_step(), which issues the calls of app/drivers/hydro/main_driver.cc:
  * 102-277 (and newtonian/main_driver.cc:218-222) in the driver's order.

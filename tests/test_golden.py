@@ -33,13 +33,20 @@ def check_against_golden(backend, name):
     thermo = par.get("thermokinetic_formulation", 1)
     for it in range(2):
         T.step(initial=(it == 0))
-        assert np.array_equal(T.get(capi.COL_ID), g["step%d_id" % it])
+        ids, gids = T.get(capi.COL_ID), g["step%d_id" % it]
+        if it == 0:
+            # no drift yet: the storage order is the bit-exact key order
+            assert np.array_equal(ids, gids)
+        # after a drift the order is compared through the ids: on a symmetric lattice coordinates sit exactly on
+        # key-cell boundaries, where a last-bit difference of the (1e-10-tolerance) acceleration flips a key digit
+        assert np.array_equal(np.sort(ids), np.sort(gids))
+        pa, pg = np.argsort(ids), np.argsort(gids)
         for nm in STEP_FIELDS:
             if nm in ("dudt",) and thermo:
                 continue
             if nm in ("dedt", "e") and not thermo:
                 continue
-            e = rel_err(T.get(capi.COL_NAMES.index(nm)), g["step%d_%s" % (it, nm)])
+            e = rel_err(T.get(capi.COL_NAMES.index(nm))[pa], g["step%d_%s" % (it, nm)][pg])
             assert e <= 1e-10, "%s step %d: %g" % (nm, it, e)
         assert abs(T.get_time()[0] - g["step%d_time" % it][0]) <= 1e-10 * abs(g["step%d_time" % it][0])
     T.close()
