@@ -18,6 +18,8 @@ SOURCES = {
     "fsph_apply.cu": ["-fmad=false"],
     "fsph_sweeps.cu": [],
     "fsph_capi.cu": [],
+    "fsph_comm.cu": [],
+    "fsph_dist.cu": ["-fmad=false"],
 }
 
 
@@ -49,7 +51,7 @@ def build_cuda(verbose=False, force=False):
             if r.returncode:
                 raise RuntimeError("nvcc failed for " + cmd[-3])
     if jobs or not os.path.exists(OUT):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs
+        cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)

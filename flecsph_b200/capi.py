@@ -66,9 +66,14 @@ SYMBOLS = [
     "fsph_reduce", "fsph_gravitation_fmm", "fsph_get_range", "fsph_get_smoothinglength", "fsph_step",
     "fsph_tree_num_nodes", "fsph_tree_get_nodes", "fsph_tree_get_leaf_depth", "fsph_neighbor_lists",
     "fsph_phase_times", "fsph_set_time_state", "fsph_get_time_state", "fsph_tree_root",
+    "fsph_comm_unique_id", "fsph_comm_init_nccl", "fsph_local_group_create", "fsph_local_group_destroy",
+    "fsph_comm_init_local", "fsph_comm_rank", "fsph_comm_size", "fsph_nghosts", "fsph_dd_choose_splitters",
+    "fsph_dd_align_splitter",
 ]
 # entry points only the product library has to provide (the checkers under oracle/ may omit them)
-PRODUCT_ONLY = {"fsph_set_time_state", "fsph_get_time_state", "fsph_tree_root"}
+PRODUCT_ONLY = {"fsph_set_time_state", "fsph_get_time_state", "fsph_tree_root", "fsph_comm_unique_id",
+                "fsph_comm_init_nccl", "fsph_local_group_create", "fsph_local_group_destroy", "fsph_comm_init_local",
+                "fsph_comm_rank", "fsph_comm_size", "fsph_nghosts", "fsph_dd_choose_splitters", "fsph_dd_align_splitter"}
 
 PRODUCT_LIB = os.path.join(ROOT, "flecsph_b200", "libflecsph_b200.so")
 
@@ -132,6 +137,16 @@ def load(path):
         "fsph_set_time_state": (i32, [vp, vp, i64]),
         "fsph_get_time_state": (i32, [vp, vp, C.POINTER(i64)]),
         "fsph_tree_root": (i32, [vp, vp, C.POINTER(dbl)]),
+        "fsph_comm_unique_id": (i32, [vp]),
+        "fsph_comm_init_nccl": (i32, [vp, vp, i32, i32]),
+        "fsph_local_group_create": (vp, [i32]),
+        "fsph_local_group_destroy": (None, [vp]),
+        "fsph_comm_init_local": (i32, [vp, vp, i32]),
+        "fsph_comm_rank": (i32, [vp]),
+        "fsph_comm_size": (i32, [vp]),
+        "fsph_nghosts": (i64, [vp]),
+        "fsph_dd_choose_splitters": (None, [i32, i32, vp, vp, vp]),
+        "fsph_dd_align_splitter": (C.c_uint64, [i32, vp, i32, vp, i32, C.c_uint64]),
     }
     for name, (res, args) in sig.items():
         if name in PRODUCT_ONLY and not hasattr(lib, name):
@@ -194,6 +209,23 @@ class BodySystem:
     def _ck(self, rc):
         if rc != 0:
             raise FsphError(self.lib.fsph_last_error(self.h).decode())
+
+    # -- several ranks (MPI_Comm_rank / size of the reference, bodies_system.h:47-52) ---------------
+    def comm_init_nccl(self, unique_id, rank, nranks):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self.lib.fsph_comm_init_nccl(self.h, buf, rank, nranks))
+
+    def comm_init_local(self, group, rank):
+        self._ck(self.lib.fsph_comm_init_local(self.h, group, rank))
+
+    def comm_rank(self):
+        return int(self.lib.fsph_comm_rank(self.h))
+
+    def comm_size(self):
+        return int(self.lib.fsph_comm_size(self.h))
+
+    def nghosts(self):
+        return int(self.lib.fsph_nghosts(self.h))
 
     # -- storage ---------------------------------------------------------
     def resize(self, n):
@@ -328,3 +360,49 @@ class BodySystem:
         k = self.lib.fsph_phase_times(self.h, ms.ctypes.data, 64, C.byref(names))
         nm = names.value.decode().split(";") if names.value else []
         return dict(zip(nm[:k], ms[:k].tolist()))
+
+
+def nccl_unique_id():
+    """128 opaque bytes from rank 0 for fsph_comm_init_nccl (ship them to the other ranks, e.g. with torch.distributed)."""
+    lib = load(PRODUCT_LIB)
+    buf = C.create_string_buffer(128)
+    if lib.fsph_comm_unique_id(buf) != 0:
+        raise FsphError(lib.fsph_last_error(None).decode())
+    return buf.raw
+
+
+class LocalRanks:
+    """P body systems of ONE process joined by the in-process communicator, one host thread per rank (ctypes releases
+    the GIL during the calls).  Every collective call of the C ABI is issued on all ranks at once through `call`."""
+
+    def __init__(self, params, nranks, devices=None):
+        from concurrent.futures import ThreadPoolExecutor
+        self.lib = load(PRODUCT_LIB)
+        self.n = nranks
+        self.group = self.lib.fsph_local_group_create(nranks)
+        devices = devices or [0] * nranks
+        self.ranks = [BodySystem(params, backend="cuda", device=devices[r]) for r in range(nranks)]
+        for r, s in enumerate(self.ranks):
+            s.comm_init_local(self.group, r)
+        self.pool = ThreadPoolExecutor(max_workers=nranks)
+
+    def call(self, fn):
+        """fn(rank_index, system) on every rank concurrently; returns the list of results."""
+        futs = [self.pool.submit(fn, r, s) for r, s in enumerate(self.ranks)]
+        errs = [f.exception() for f in futs]
+        real = [e for e in errs if e is not None and "local group:" not in str(e)]
+        if real:
+            raise real[0]  # the rank that failed first; its peers only report the broken group
+        for e in errs:
+            if e is not None:
+                raise e
+        return [f.result() for f in futs]
+
+    def close(self):
+        for s in self.ranks:
+            s.close()
+        self.ranks = []
+        if self.group:
+            self.lib.fsph_local_group_destroy(self.group)
+            self.group = None
+        self.pool.shutdown()

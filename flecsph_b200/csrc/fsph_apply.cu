@@ -23,6 +23,7 @@ Cols System::cols() const {
   c.key = col_key.as<uint64_t>();
   c.type = col_type.as<int32_t>();
   c.nneigh = col_nneigh.as<int32_t>();
+  c.ghosts = has_ghosts ? 1 : 0;
   return c;
 }
 
@@ -154,6 +155,7 @@ template<int D>
 __global__ void __launch_bounds__(256) k_apply(Cols c, int64_t n, OpList ops, PhysParams pp, uint32_t * __restrict__ status) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= n) return;
+  if(c.ghosts && (c.type[i] & TYPE_GHOST)) return;  // remote copies are refreshed from their owner (reset_ghosts)
   for(int k = 0; k < ops.n; ++k) apply_one<D>(c, i, ops.op[k], pp, status);
 }
 
@@ -199,6 +201,7 @@ __global__ void __launch_bounds__(256) k_reduce(Cols c, int64_t n, int kind, int
   if(kind == RED_MAX_H) v[0] = -DBL_MAX;
   if(kind >= RED_H_STATS) { v[0] = DBL_MAX; v[1] = kind == RED_N_STATS ? 0.0 : DBL_MIN; }
   for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if(c.ghosts && (c.type[i] & TYPE_GHOST)) continue;
     switch(kind) {
       case RED_MIN_DT: v[0] = fmin(v[0], c.f[F_DT][i]); break;
       case RED_MAX_H: v[0] = fmax(v[0], c.f[F_H][i]); break;
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__(256) k_reduce(Cols c, int64_t n, int kind, int
   }
 }
 
-static void run_reduce(System & s, int kind, double out[3]) {
+static void run_reduce_local(System & s, int kind, double out[3]) {
   int nb = (int)std::min<int64_t>((s.n + 255) / 256, 148 * 4);
   double * part = reduce_scratch(s, (size_t)nb * 3 + 16);
   if(s.dim == 1) FSPH_LAUNCH((k_reduce<1>), nb, 256, s.stream, s.cols(), s.n, kind, s.par.thermokinetic_formulation, s.par.enable_fmm, part);
@@ -310,9 +313,26 @@ static void run_reduce(System & s, int kind, double out[3]) {
   }
 }
 
+void global_combine(System & s, int kind, double v[3]) {
+  const int P = s.comm->nranks;
+  std::vector<double> all((size_t)3 * P);
+  dist_all_gather_host(s, v, all.data(), 3 * sizeof(double));
+  for(int j = 0; j < 3; ++j) {
+    double r = all[j];
+    for(int q = 1; q < P; ++q) r = red_combine(kind, j, r, all[(size_t)3 * q + j]);
+    v[j] = r;
+  }
+}
+
+// get_all reductions end in an MPI_Allreduce in the reference (default_physics.h:769,891; analysis.h:60-200)
+static void run_reduce(System & s, int kind, double out[3]) {
+  run_reduce_local(s, kind, out);
+  if(s.comm) global_combine(s, kind, out);
+}
+
 double max_h(System & s) {
   double o[3];
-  run_reduce(s, RED_MAX_H, o);
+  run_reduce_local(s, RED_MAX_H, o);
   return o[0];
 }
 
@@ -353,7 +373,9 @@ void reduce(System & s, int op, double * out, int nout) {
     case FSPH_GET_COMPUTE_AVERAGE_SMOOTHINGLENGTH: {
       apply(s, 100);
       run_reduce(s, RED_SUM_H, o);
-      const double new_h = 1. / (double)s.n * o[0];
+      double cnt[3] = {(double)s.n_owned_or_n(), 0, 0};
+      if(s.comm) global_combine(s, RED_SUM_H, cnt);
+      const double new_h = 1. / cnt[0] * o[0];
       const double keep = s.dt;
       s.dt = new_h;
       apply(s, 101);

@@ -84,6 +84,12 @@ void do_update_iteration(System & s) {
   // body_system::update_iteration, bodies_system.h:152-229 (non-periodic)
   if(s.par.periodic_boundary_x || s.par.periodic_boundary_y || s.par.periodic_boundary_z)
     throw std::runtime_error("periodic boundaries (WALL ghosts, boundary.h) are not implemented on the device yet");
+  if(s.comm) {
+    // several ranks: range all-reduce, sample sort + all-to-all, halo of remote bodies and tree nodes (fsph_dist.cu)
+    PhaseScope p(s, "decomposition");
+    dist_update_iteration(s);
+    return;
+  }
   {
     PhaseScope p(s, "range_keys");
     compute_range(s);
@@ -103,6 +109,11 @@ void do_reset_ghosts(System & s) {
   // bodies_system.h:273 -> tree_topology::reset_ghosts (tree_topology.h:153-157): clean + build_tree with the
   // current keys.  The tree is a pure function of (keys, positions, h, mass): rebuilt only if those changed.
   if(!s.tree_valid) throw std::runtime_error("reset_ghosts before update_iteration");
+  if(s.comm) {
+    PhaseScope p(s, "halo_refresh");
+    dist_refresh_ghosts(s);
+    return;
+  }
   if(s.tree_dirty) {
     PhaseScope p(s, "tree");
     build_tree(s);
@@ -232,6 +243,7 @@ int32_t guarded(fsph_system * s, F && f) {
   catch(const std::exception & e) {
     s->err = e.what();
     s->phases.clear();
+    if(s->comm && s->err.find("local group:") == std::string::npos) s->comm->abort();
     return 1;
   }
 }
@@ -305,6 +317,11 @@ void fsph_destroy(fsph_system * s) {
   if(!s) return;
   cudaSetDevice(s->device);
   cudaStreamSynchronize(s->stream);
+  dist_release(*s);
+  delete s->comm;
+  s->comm = nullptr;
+  s->col_gd.release();
+  s->b_node_parent.release();
   DevBuf * all[] = {&s->col_id, &s->col_key, &s->col_type, &s->col_nneigh, &s->scratch_col, &s->b_perm, &s->b_keys2, &s->b_perm2,
     &s->b_cell, &s->b_cell_parent, &s->b_cell_desc, &s->b_cell_desc2, &s->b_child_begin, &s->b_child_end, &s->b_node_start,
     &s->b_node_depth, &s->b_sub, &s->b_nmass, &s->b_nradius, &s->b_nlap, &s->b_wc_cell, &s->b_cand_off, &s->b_mask_off, &s->b_cand,
@@ -339,15 +356,18 @@ int32_t fsph_resize(fsph_system * s, int64_t n) {
     FSPH_CUDA_OK(cudaMemsetAsync(s->col_nneigh.p, 0, b4, s->stream));
     if(n > 0) FSPH_LAUNCH(k_iota64, (unsigned)((n + 255) / 256), 256, s->stream, s->col_id.as<int64_t>(), n);
     s->n = n;
+    s->n_owned = n;
+    s->has_ghosts = false;
     invalidate(*s);
     FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
   });
 }
 
-int64_t fsph_nbodies(const fsph_system * s) { return s ? s->n : 0; }
+int64_t fsph_nbodies(const fsph_system * s) { return s ? s->n_owned_or_n() : 0; }
 
 int32_t fsph_set_column(fsph_system * s, int32_t col, const void * host) {
   return guarded(s, [&]() {
+    dist_drop_ghosts(*s);
     const int64_t n = s->n;
     const int D = s->dim;
     if(col >= FSPH_COL_POS && col <= FSPH_COL_GACC) {
@@ -373,6 +393,7 @@ int32_t fsph_set_column(fsph_system * s, int32_t col, const void * host) {
 
 int32_t fsph_get_column(fsph_system * s, int32_t col, void * host) {
   return guarded(s, [&]() {
+    dist_drop_ghosts(*s);
     const int64_t n = s->n;
     const int D = s->dim;
     if(col >= FSPH_COL_POS && col <= FSPH_COL_GACC) {
@@ -400,6 +421,7 @@ int32_t fsph_get_column(fsph_system * s, int32_t col, void * host) {
 
 int32_t fsph_set_component(fsph_system * s, int32_t col, int32_t comp, const void * host) {
   return guarded(s, [&]() {
+    dist_drop_ghosts(*s);
     void * dst = nullptr;
     size_t esz = 8;
     if(col >= FSPH_COL_POS && col <= FSPH_COL_GACC) {
@@ -418,6 +440,7 @@ int32_t fsph_set_component(fsph_system * s, int32_t col, int32_t comp, const voi
 
 int32_t fsph_get_component(fsph_system * s, int32_t col, int32_t comp, void * host) {
   return guarded(s, [&]() {
+    dist_drop_ghosts(*s);
     const void * src = nullptr;
     size_t esz = 8;
     if(col >= FSPH_COL_POS && col <= FSPH_COL_GACC) {
@@ -468,6 +491,7 @@ int32_t fsph_upload_aos(fsph_system * s, const void * bodies, int64_t n, int64_t
 
 int32_t fsph_download_aos(fsph_system * s, void * bodies, int64_t stride, const int64_t * offsets) {
   return guarded(s, [&]() {
+    dist_drop_ghosts(*s);
     char * base = static_cast<char *>(bodies);
     const int D = s->dim;
     const int64_t n = s->n;
@@ -557,7 +581,11 @@ int32_t fsph_get_range(fsph_system * s, double * lo, double * hi) {
 }
 double fsph_get_smoothinglength(fsph_system * s) {
   double r = 0;
-  guarded(s, [&]() { r = max_h(*s); });
+  guarded(s, [&]() {
+    double o[3] = {max_h(*s), 0, 0};
+    if(s->comm) global_combine(*s, 1 /* RED_MAX_H */, o);  // MPI_Allreduce MAX, bodies_system.h:122
+    r = o[0];
+  });
   return r;
 }
 
@@ -659,6 +687,39 @@ int32_t fsph_neighbor_lists(fsph_system * s, int64_t * offsets, int64_t * ids) {
 }
 
 uint64_t fsph_launch_count(void) { return fsph::g_launches; }
+
+// ---- several ranks -------------------------------------------------------------------------------------------
+int32_t fsph_comm_unique_id(char * out128) {
+  try { nccl_unique_id(out128); return 0; }
+  catch(const std::exception & e) { g_create_error = e.what(); return 1; }
+}
+int32_t fsph_comm_init_nccl(fsph_system * s, const char * unique_id, int32_t rank, int32_t nranks) {
+  return guarded(s, [&]() {
+    if(s->comm) throw std::runtime_error("communicator already set");
+    if(nranks < 1 || rank < 0 || rank >= nranks) throw std::runtime_error("bad rank / nranks");
+    if(nranks > 1) s->comm = make_nccl_comm(unique_id, rank, nranks);
+  });
+}
+void * fsph_local_group_create(int32_t nranks) { return nranks >= 1 ? local_group_create(nranks) : nullptr; }
+void fsph_local_group_destroy(void * g) { local_group_destroy(static_cast<LocalGroup *>(g)); }
+int32_t fsph_comm_init_local(fsph_system * s, void * group, int32_t rank) {
+  return guarded(s, [&]() {
+    if(s->comm) throw std::runtime_error("communicator already set");
+    s->comm = make_local_comm(static_cast<LocalGroup *>(group), rank);
+  });
+}
+int32_t fsph_comm_rank(const fsph_system * s) { return s && s->comm ? s->comm->rank : 0; }
+int32_t fsph_comm_size(const fsph_system * s) { return s && s->comm ? s->comm->nranks : 1; }
+int64_t fsph_nghosts(const fsph_system * s) { return s && s->has_ghosts ? s->n - s->n_owned : 0; }
+
+// host-side planning of the decomposition (no device needed; covered by the world_size-2 CPU tests)
+void fsph_dd_choose_splitters(int32_t nranks, int32_t nsamples, const uint64_t * sample_keys, const int64_t * counts, uint64_t * splitters) {
+  dd_choose_splitters(nranks, nsamples, sample_keys, counts, splitters);
+}
+uint64_t fsph_dd_align_splitter(int32_t dim, const uint64_t * below, int32_t nbelow, const uint64_t * above, int32_t nabove, uint64_t splitter) {
+  std::vector<uint64_t> b(below, below + nbelow), a(above, above + nabove);
+  return dd_align_splitter(dim, b, a, splitter);
+}
 
 int32_t fsph_phase_times(fsph_system * s, double * ms, int32_t cap, const char ** names) {
   if(!s) return 0;

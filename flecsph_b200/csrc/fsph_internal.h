@@ -9,6 +9,8 @@
 #include <stdint.h>
 #include <string>
 #include <vector>
+#include <utility>
+#include <stdexcept>
 #include "flecsph_b200.h"
 
 namespace fsph {
@@ -28,13 +30,15 @@ constexpr int MAX_LEVELS = 66;
 // error bits latched on the device (surfaced at the next call boundary)
 enum ErrBits {
   ERR_DUP_KEYS = 1, ERR_RHO_NONPOS = 2, ERR_U_NONPOS = 4, ERR_NAN = 8, ERR_NEGATIVE = 16, ERR_QUEUE_OVERFLOW = 32,
-  ERR_DT_LOOP = 64, ERR_RANGE = 128, ERR_SEARCH_CAPACITY = 256
+  ERR_DT_LOOP = 64, ERR_RANGE = 128, ERR_SEARCH_CAPACITY = 256, ERR_DD_CAPACITY = 512
 };
 
 struct DevBuf {
   void * p = nullptr;
   size_t cap = 0;
-  void reserve(size_t bytes);  // grows (contents NOT preserved)
+  void reserve(size_t bytes);  // grows with 12 % slack (contents NOT preserved)
+  void reserve_exact(size_t bytes);  // grows to exactly `bytes` (for buffers that swap roles: capacities converge)
+  void grow_keep(size_t bytes, size_t keep, cudaStream_t st);  // grows, first `keep` bytes preserved
   void release();
   template<typename T> T * as() const { return static_cast<T *>(p); }
 };
@@ -46,7 +50,10 @@ struct Cols {
   uint64_t * key;
   int32_t * type;
   int32_t * nneigh;
+  int32_t ghosts;  // != 0: bodies with (type & TYPE_GHOST) are remote copies (domain decomposition): skipped by element-wise passes and reductions
 };
+
+constexpr int32_t TYPE_GHOST = 0x100;  // flag in the type column: copy of a body owned by another rank (tree_types.h:365 "locality")
 
 // packed records for the neighbour walk: one 64-byte load per frontier node, one 32-byte load per leaf child
 struct __align__(16) NodeRec {
@@ -66,6 +73,7 @@ struct Tree {
   // cells in level order (depth, then key): value >= 0 -> particle index (leaf), < 0 -> ~node index
   int32_t * cell;
   int32_t * cell_parent;  // node index of the parent (-1 for the root cell)
+  int32_t * node_parent;  // [nnodes] parent node (-1 for the root)
   uint64_t * cell_desc;   // depth << 32 | start << 1 | is_leaf
   // nodes in level order
   int32_t * child_begin;
@@ -108,8 +116,18 @@ struct Phase {
   cudaEvent_t e0, e1;
 };
 
+struct Comm;
+struct Dist;
+
 struct System {
   fsph_params par;
+  // domain decomposition (fsph_dist.cu); comm == nullptr: one rank owns everything
+  Comm * comm = nullptr;
+  Dist * dist = nullptr;
+  int64_t n_owned = 0;     // bodies [0, n) hold n_owned owned bodies and n - n_owned ghosts once the halo is in
+  bool has_ghosts = false;
+  DevBuf col_gd;           // int32: depth of the body's leaf in the global tree (multi-rank only)
+  const uint32_t * last_perm = nullptr;  // permutation of the last sort_bodies (valid until the next sort / tree build)
   int dim = 3, device = 0;
   cudaStream_t stream = nullptr;
   std::string err;
@@ -126,6 +144,7 @@ struct System {
   // storage
   DevBuf col[NF64], col_id, col_key, col_type, col_nneigh, scratch_col;
   DevBuf b_perm, b_keys2, b_perm2, b_tmp[6];
+  DevBuf b_node_parent;
   DevBuf b_cell, b_cell_parent, b_cell_desc, b_cell_desc2, b_child_begin, b_child_end, b_node_start, b_node_depth, b_sub;
   DevBuf b_noderec, b_leafrec;
   DevBuf b_nmass, b_ncom[3], b_nradius, b_nlap, b_nbmin[3], b_nbmax[3];
@@ -149,6 +168,7 @@ struct System {
 
   Cols cols() const;
   PhysParams phys() const;
+  int64_t n_owned_or_n() const { return has_ghosts ? n_owned : n; }
 };
 
 #define FSPH_CUDA_OK(call)                                                                       \
@@ -179,7 +199,19 @@ void exclusive_scan_u64(System & s, const uint64_t * in, uint64_t * out, int64_t
 void compute_range(System & s);                 // bodies_system.h:231-268
 void compute_keys(System & s);                  // filling_curve.h:503-525
 void sort_bodies(System & s);                   // psort.h:227-322 (one rank): radix sort + column gather
+void live_columns(System & s, std::vector<std::pair<DevBuf *, int>> & out);  // columns that carry state, element size
+void gather_bodies(System & s, const uint32_t * perm, int64_t n_new);  // every live column: out[i] = in[perm[i]], i < n_new
 void build_tree(System & s);                    // tree_topology.h:878-997 + default_physics.h:59-119
+// Multi-rank variants: the local tree is the global canonical tree restricted to the bodies present here.
+struct TreeEdges {
+  bool has_before = false, has_after = false;   // last key of the previous rank / first key of the next rank
+  uint64_t key_before = 0, key_after = 0;
+  const int32_t * gd_in = nullptr;              // per body: leaf depth in the global tree (given for the merged tree)
+  int32_t * gd_out = nullptr;                   // per body: leaf depth computed here (owned tree)
+  bool finish = true;                           // pack the walk records and collect the work cells
+};
+void build_tree_edges(System & s, const TreeEdges & e);
+void finish_tree(System & s);                   // walk records + work cells (after node-table overrides)
 void find_work_cells(System & s);               // tree_topology.h:221-235
 
 // ---- fsph_search.cu -------------------------------------------------------------------------
@@ -193,9 +225,37 @@ void sweep(System & s, int op);                 // default_physics.h:193-566
 void apply(System & s, int op);                  // integration.h, default_physics.h element-wise
 void apply_fused(System & s, const int * ops, int nops);  // several of them in one pass (same per-particle order)
 void reduce(System & s, int op, double * out, int nout);
-double max_h(System & s);
+double max_h(System & s);                        // over the bodies of this rank
+void global_combine(System & s, int kind, double v[3]);  // combine a reduction across ranks (rank order: deterministic)
 void check_status(System & s);                  // throws on latched device errors
 
 double * reduce_scratch(System & s, size_t n);
+
+// ---- fsph_comm.cu / fsph_dist.cu --------------------------------------------------------------
+// Collectives on device buffers, stream-ordered.  Two backends: NCCL (one process per GPU, libnccl.so.2 resolved at
+// run time) and an in-process group of host threads (several systems in one process; used by the 1-GPU tests).
+struct Comm {
+  int rank = 0, nranks = 1;
+  virtual ~Comm() {}
+  virtual void abort() {}  // this rank failed: wake peers blocked in a collective (MPI_Abort of mpisph/utils.h:34-38)
+  virtual void all_gather(const void * send, void * recv, size_t bytes, cudaStream_t st) = 0;
+  // block for rank q: send + soff[q] (scount[q] bytes); the block from rank q lands at recv + roff[q] (rcount[q] bytes)
+  virtual void all_to_all_v(const void * send, const size_t * soff, const size_t * scount, void * recv, const size_t * roff,
+    const size_t * rcount, cudaStream_t st) = 0;
+};
+Comm * make_nccl_comm(const char * unique_id, int rank, int nranks);
+void nccl_unique_id(char * out128);
+struct LocalGroup;
+LocalGroup * local_group_create(int nranks);
+void local_group_destroy(LocalGroup * g);
+Comm * make_local_comm(LocalGroup * g, int rank);
+
+void dd_choose_splitters(int nranks, int nsamples, const uint64_t * keys, const int64_t * counts, uint64_t * out);
+uint64_t dd_align_splitter(int D, std::vector<uint64_t> & below, std::vector<uint64_t> & above, uint64_t s);
+void dist_all_gather_host(System & s, const void * in, void * out, size_t bytes);  // small host values, staged through the device
+void dist_update_iteration(System & s);          // bodies_system.h:152-229 with size > 1 (psort + tree exchange)
+void dist_refresh_ghosts(System & s);            // bodies_system.h:273 reset_ghosts with size > 1
+void dist_drop_ghosts(System & s);
+void dist_release(System & s);
 
 }  // namespace fsph

@@ -15,6 +15,7 @@
 // deterministically by a prefix sum; it is a few per cent of the pair-test cost.
 #include <stdexcept>
 #include <algorithm>
+#include <cstdlib>
 #include "fsph_internal.h"
 
 namespace fsph {
@@ -451,7 +452,14 @@ static void neighbor_search_t(System & s) {
   sr.ncand = s.b_ncand.as<int32_t>();
   unsigned long long * cursors = reinterpret_cast<unsigned long long *>(s.b_status.as<uint32_t>() + 8);
   // single pass when the previous search on this system gives a capacity estimate
-  if(s.est_cand > 0 && s.est_n == s.n) {
+  // (with ghosts the body count drifts a little from step to step: the estimate is scaled by the ratio)
+  const bool est_ok = s.est_cand > 0 && s.est_n > 0 && (s.est_n == s.n || (s.comm && std::llabs(s.est_n - s.n) < s.est_n / 4));
+  if(est_ok) {
+    if(s.est_n != s.n) {
+      const double r = (double)s.n / (double)s.est_n;
+      if(r > 1.0) { s.est_cand = (unsigned long long)(s.est_cand * r); s.est_mask = (unsigned long long)(s.est_mask * r); }
+      s.est_n = s.n;
+    }
     const int grid_cap = 148 * 12, scratch_cap = 16384;
     const unsigned long long cand_cap = s.est_cand + s.est_cand / 4 + 65536, mask_cap = s.est_mask + s.est_mask / 4 + 65536;
     s.b_cand.reserve((size_t)cand_cap * 4);
@@ -524,21 +532,39 @@ __global__ void __launch_bounds__(SR_NT) k_export(Tree t, Cols c, Search sr, con
     }
   }
 }
-__global__ void __launch_bounds__(256) k_i32_to_u64(const int32_t * __restrict__ in, uint64_t * __restrict__ out, int64_t n) {
+__global__ void __launch_bounds__(256) k_i32_to_u64(const int32_t * __restrict__ in, uint64_t * __restrict__ out, int64_t n,
+  const int32_t * __restrict__ type, int ghosts) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(i < n) out[i] = (uint64_t)in[i];
+  if(i < n) out[i] = (ghosts && (type[i] & TYPE_GHOST)) ? 0ull : (uint64_t)in[i];
 }
 
 void export_neighbors(System & s, std::vector<int64_t> & off, std::vector<int64_t> * ids) {
   const int64_t n = s.n;
   s.b_cnt1.reserve((size_t)(n + 1) * 8);
   uint64_t * o = s.b_cnt1.as<uint64_t>();
-  FSPH_LAUNCH(k_i32_to_u64, (unsigned)((n + 255) / 256), 256, s.stream, s.col_nneigh.as<int32_t>(), o, n);
+  FSPH_LAUNCH(k_i32_to_u64, (unsigned)((n + 255) / 256), 256, s.stream, s.col_nneigh.as<int32_t>(), o, n, s.col_type.as<int32_t>(),
+    s.has_ghosts ? 1 : 0);
   exclusive_scan_u64(s, o, o, n, nullptr);
   off.resize(n + 1);
   FSPH_CUDA_OK(cudaMemcpyAsync(off.data(), o, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
   FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
-  if(!ids) return;
+  // rows of remote copies are dropped: the caller sees the owned bodies in storage order
+  std::vector<int32_t> type;
+  auto drop_ghost_rows = [&]() {
+    if(!s.has_ghosts) return;
+    if(type.empty()) {
+      type.resize(n);
+      FSPH_CUDA_OK(cudaMemcpyAsync(type.data(), s.col_type.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s.stream));
+      FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
+    }
+    std::vector<int64_t> o2;
+    o2.reserve(s.n_owned + 1);
+    for(int64_t i = 0; i < n; ++i)
+      if(!(type[i] & TYPE_GHOST)) o2.push_back(off[i]);
+    o2.push_back(off[n]);
+    off.swap(o2);
+  };
+  if(!ids) { drop_ghost_rows(); return; }
   const int64_t tot = off[n];
   ids->resize(tot);
   DevBuf tmp;
@@ -548,6 +574,7 @@ void export_neighbors(System & s, std::vector<int64_t> & off, std::vector<int64_
   FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
   tmp.release();
   for(int64_t i = 0; i < n; ++i) std::sort(ids->begin() + off[i], ids->begin() + off[i + 1]);
+  drop_ghost_rows();  // ghost rows are empty, so the id array is unchanged
 }
 
 }  // namespace fsph

@@ -24,6 +24,33 @@ void DevBuf::reserve(size_t bytes) {
   }
   cap = want;
 }
+void DevBuf::reserve_exact(size_t bytes) {
+  if(bytes <= cap) return;
+  if(p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if(e != cudaSuccess) {
+    p = nullptr;
+    throw std::runtime_error(std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+  }
+  cap = bytes;
+}
+void DevBuf::grow_keep(size_t bytes, size_t keep, cudaStream_t st) {
+  if(bytes <= cap) return;
+  void * old = p;
+  p = nullptr;
+  cap = 0;
+  try { reserve(bytes + bytes / 4); }
+  catch(...) { p = old; throw; }
+  if(old) {
+    if(keep) {
+      cudaMemcpyAsync(p, old, keep, cudaMemcpyDeviceToDevice, st);
+      cudaStreamSynchronize(st);
+    }
+    cudaFree(old);
+  }
+}
 void DevBuf::release() {
   if(p) cudaFree(p);
   p = nullptr;

@@ -151,12 +151,45 @@ __global__ void __launch_bounds__(256) k_is_identity(const uint32_t * __restrict
   if(i < n && perm[i] != (uint32_t)i) *flag = 1;
 }
 
-static void gather8(System & s, DevBuf & colbuf, const uint32_t * perm) {
-  s.scratch_col.reserve((size_t)s.n * 8);
-  unsigned nb = (unsigned)((s.n + 255) / 256);
-  FSPH_LAUNCH((k_gather<uint64_t>), nb, 256, s.stream, colbuf.as<uint64_t>(), s.scratch_col.as<uint64_t>(), perm, s.n);
+static void gather8(System & s, DevBuf & colbuf, const uint32_t * perm, int64_t n_new) {
+  s.scratch_col.reserve_exact(std::max(colbuf.cap, (size_t)n_new * 8));
+  unsigned nb = (unsigned)((n_new + 255) / 256);
+  if(n_new > 0) FSPH_LAUNCH((k_gather<uint64_t>), nb, 256, s.stream, colbuf.as<uint64_t>(), s.scratch_col.as<uint64_t>(), perm, n_new);
   std::swap(colbuf.p, s.scratch_col.p);
   std::swap(colbuf.cap, s.scratch_col.cap);
+}
+static void gather4(System & s, DevBuf & colbuf, const uint32_t * perm, int64_t n_new) {
+  s.b_tmp[0].reserve_exact(std::max(colbuf.cap, (size_t)n_new * 4));
+  unsigned nb = (unsigned)((n_new + 255) / 256);
+  if(n_new > 0) FSPH_LAUNCH((k_gather<uint32_t>), nb, 256, s.stream, colbuf.as<uint32_t>(), s.b_tmp[0].as<uint32_t>(), perm, n_new);
+  std::swap(colbuf.p, s.b_tmp[0].p);
+  std::swap(colbuf.cap, s.b_tmp[0].cap);
+}
+
+// The columns that carry state across a sort / an exchange, with their element size.
+void live_columns(System & s, std::vector<std::pair<DevBuf *, int>> & out) {
+  out.clear();
+  for(int f = 0; f < NF64; ++f) {
+    if(f < F_MASS && (f % 3) >= s.dim) continue;  // unused vector components
+    if(f == F_PRHO2) continue;                      // derived column
+    if(s.skip_dead_columns && s.dead_col[f]) continue;  // fsph_step: rewritten before it is next read
+    out.emplace_back(&s.col[f], 8);
+  }
+  out.emplace_back(&s.col_id, 8);
+  out.emplace_back(&s.col_key, 8);
+  out.emplace_back(&s.col_type, 4);
+  if(s.comm) out.emplace_back(&s.col_gd, 4);
+}
+
+// out[i] = in[perm[i]] for every live column; perm must not live in scratch_col / b_tmp[0]
+void gather_bodies(System & s, const uint32_t * perm, int64_t n_new) {
+  std::vector<std::pair<DevBuf *, int>> cols;
+  live_columns(s, cols);
+  for(auto & c : cols) {
+    if(c.second == 8) gather8(s, *c.first, perm, n_new);
+    else gather4(s, *c.first, perm, n_new);
+  }
+  FSPH_CUDA_OK(cudaGetLastError());
 }
 
 void sort_bodies(System & s) {
@@ -172,8 +205,9 @@ void sort_bodies(System & s) {
   uint32_t * v1 = s.b_perm2.as<uint32_t>();
   FSPH_CUDA_OK(cudaMemcpyAsync(k0, s.col_key.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, s.stream));
   radix_sort_pairs(s, k0, v0, k1, v1, n);
-  // the sorted permutation must not live in scratch_col (gather8 overwrites it)
+  // the sorted permutation must not live in scratch_col (the gathers overwrite it)
   const uint32_t * perm = v0;
+  s.last_perm = perm;
   // skip the gathers when the bodies are already in key order
   uint32_t * flag = s.b_status.as<uint32_t>() + 1;
   FSPH_CUDA_OK(cudaMemsetAsync(flag, 0, 4, s.stream));
@@ -182,20 +216,7 @@ void sort_bodies(System & s) {
   uint32_t moved = 0;
   FSPH_CUDA_OK(cudaMemcpyAsync(&moved, flag, 4, cudaMemcpyDeviceToHost, s.stream));
   FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
-  if(moved) {
-    for(int f = 0; f < NF64; ++f) {
-      if(f < F_MASS && (f % 3) >= s.dim) continue;  // unused vector components
-      if(f == F_PRHO2) continue;                      // derived column
-      if(s.skip_dead_columns && s.dead_col[f]) continue;  // fsph_step: rewritten before it is next read
-      gather8(s, s.col[f], perm);
-    }
-    gather8(s, s.col_id, perm);
-    gather8(s, s.col_key, perm);
-    s.b_tmp[0].reserve((size_t)n * 4);
-    FSPH_LAUNCH((k_gather<uint32_t>), nb, 256, s.stream, s.col_type.as<uint32_t>(), s.b_tmp[0].as<uint32_t>(), perm, n);
-    std::swap(s.col_type.p, s.b_tmp[0].p);
-    std::swap(s.col_type.cap, s.b_tmp[0].cap);
-  }
+  if(moved) gather_bodies(s, perm, n);
   FSPH_CUDA_OK(cudaGetLastError());
 }
 
@@ -217,27 +238,55 @@ __global__ void __launch_bounds__(256) k_lcp(const uint64_t * __restrict__ key, 
       d = B - 1 - p / D;
     }
   }
-  else if(n == 1) d = 0;  // the root node always exists (tree_topology.h:893)
   lcp[i] = (int8_t)d;
 }
 
-__global__ void __launch_bounds__(256) k_cell_count(const int8_t * __restrict__ lcp, int64_t n, uint32_t * __restrict__ cnt) {
+// Leaf depth of every body in the global tree: one below the deepest node it shares with a key neighbour (the root
+// always exists, tree_topology.h:893).  On several ranks the neighbours of the first / last body live on the adjacent
+// ranks (kb / ka), and for a tree that also holds ghosts the depth is given (computed by each body's owner).
+template<int D>
+__global__ void __launch_bounds__(256) k_leaf_depth(const int8_t * __restrict__ lcp, int64_t n, const uint64_t * __restrict__ key, int has_b,
+  uint64_t kb, int has_a, uint64_t ka, int32_t * __restrict__ gd) {
+  constexpr int B = KeyBits<D>::B;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= n) return;
-  int dp = i > 0 ? lcp[i - 1] : -1, dc = lcp[i];
-  cnt[i] = (uint32_t)((dc > dp ? dc - dp : 0) + 1);
+  int dp = i > 0 ? lcp[i - 1] : -1, dc = i + 1 < n ? lcp[i] : -1;
+  if(i == 0 && has_b) {
+    uint64_t x = key[0] ^ kb;
+    dp = x ? B - 1 - (63 - __clzll((long long)x)) / D : B - 1;
+  }
+  if(i == n - 1 && has_a) {
+    uint64_t x = key[i] ^ ka;
+    dc = x ? B - 1 - (63 - __clzll((long long)x)) / D : B - 1;
+  }
+  int d = (dp > dc ? dp : dc) + 1;
+  gd[i] = d < 1 ? 1 : d;
 }
 
-__global__ void __launch_bounds__(256) k_cell_emit(const int8_t * __restrict__ lcp, int64_t n, const uint32_t * __restrict__ off,
-  uint64_t * __restrict__ desc) {
+// body i opens the nodes of depths (lcp[i-1], gd[i] - 1] and one leaf at depth gd[i]
+__global__ void __launch_bounds__(256) k_cell_count(const int8_t * __restrict__ lcp, const int32_t * __restrict__ gd, int64_t n,
+  uint32_t * __restrict__ cnt, uint32_t * status) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= n) return;
-  int dp = i > 0 ? lcp[i - 1] : -1, dc = lcp[i];
+  const int dp = i > 0 ? lcp[i - 1] : -1, dc = i + 1 < n ? lcp[i] : -1, g = gd[i];
+  if(g - 1 < dp || g - 1 < dc || g > 63) {
+    atomicOr(status, (uint32_t)ERR_DD_CAPACITY);  // inconsistent global leaf depth (cannot happen for a sub-set of one tree)
+    cnt[i] = 1;
+    return;
+  }
+  cnt[i] = (uint32_t)(g - dp);
+}
+
+__global__ void __launch_bounds__(256) k_cell_emit(const int8_t * __restrict__ lcp, const int32_t * __restrict__ gd, int64_t n,
+  const uint32_t * __restrict__ off, uint64_t * __restrict__ desc) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const int dp = i > 0 ? lcp[i - 1] : -1, g = gd[i];
+  if(g - 1 < dp) return;
   uint32_t o = off[i];
   uint64_t lowbits = (uint64_t)i << 1;
-  for(int k = dp + 1; k <= dc; ++k) desc[o++] = ((uint64_t)k << 32) | lowbits;
-  int ld = (dp > dc ? dp : dc) + 1;
-  desc[o] = ((uint64_t)ld << 32) | lowbits | 1ull;
+  for(int k = dp + 1; k <= g - 1; ++k) desc[o++] = ((uint64_t)k << 32) | lowbits;
+  desc[o] = ((uint64_t)g << 32) | lowbits | 1ull;
 }
 
 template<int D>
@@ -278,6 +327,7 @@ __global__ void __launch_bounds__(256) k_cell_link(const uint64_t * __restrict__
     t.cell[c] = ~nr;
     t.node_start[nr] = start;
     t.node_depth[nr] = depth;
+    t.node_parent[nr] = parent;
   }
   else t.cell[c] = start;
   if(head) t.child_begin[parent] = (int)c;
@@ -414,7 +464,7 @@ __global__ void __launch_bounds__(256) k_pack_leaves(Tree t, Cols c, int64_t nc)
 }
 
 template<int D>
-static void build_tree_t(System & s) {
+static void build_tree_t(System & s, const TreeEdges & te) {
   const int64_t n = s.n;
   unsigned nbp = (unsigned)((n + 255) / 256);
   uint32_t * status = s.b_status.as<uint32_t>();
@@ -423,13 +473,25 @@ static void build_tree_t(System & s) {
   int8_t * lcp = s.b_tmp[0].as<int8_t>();
   uint32_t * cnt = s.b_cnt0.as<uint32_t>();
   FSPH_LAUNCH((k_lcp<D>), nbp, 256, s.stream, s.col_key.as<uint64_t>(), n, lcp, status);
-  FSPH_LAUNCH(k_cell_count, nbp, 256, s.stream, lcp, n, cnt);
+  const int32_t * gd = te.gd_in;
+  if(!gd) {
+    int32_t * g = te.gd_out;
+    if(!g) {
+      s.b_tmp[1].reserve((size_t)n * 4);
+      g = s.b_tmp[1].as<int32_t>();
+    }
+    FSPH_LAUNCH((k_leaf_depth<D>), nbp, 256, s.stream, lcp, n, s.col_key.as<uint64_t>(), te.has_before ? 1 : 0, te.key_before,
+      te.has_after ? 1 : 0, te.key_after, g);
+    gd = g;
+  }
+  FSPH_LAUNCH(k_cell_count, nbp, 256, s.stream, lcp, gd, n, cnt, status);
   exclusive_scan_u32(s, cnt, cnt, n, nullptr);
   uint32_t h2[2];
   FSPH_CUDA_OK(cudaMemcpyAsync(&h2[0], cnt + n, 4, cudaMemcpyDeviceToHost, s.stream));
   FSPH_CUDA_OK(cudaMemcpyAsync(&h2[1], status, 4, cudaMemcpyDeviceToHost, s.stream));
   FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
   if(h2[1] & ERR_DUP_KEYS) throw std::runtime_error("two bodies have the same key (the reference's build_tree breaks on this too)");
+  if(h2[1] & ERR_DD_CAPACITY) throw std::runtime_error("inconsistent global leaf depths in the merged tree");
   const int64_t nc = h2[0];
   const int64_t nn = nc - n;
   if(nc >= (int64_t(1) << 31)) throw std::runtime_error("tree has more than 2^31 cells");
@@ -437,7 +499,7 @@ static void build_tree_t(System & s) {
   s.b_cell_desc2.reserve((size_t)nc * 8);
   uint64_t * desc0 = s.b_cell_desc2.as<uint64_t>();
   uint64_t * desc = s.b_cell_desc.as<uint64_t>();
-  FSPH_LAUNCH(k_cell_emit, nbp, 256, s.stream, lcp, n, cnt, desc0);
+  FSPH_LAUNCH(k_cell_emit, nbp, 256, s.stream, lcp, gd, n, cnt, desc0);
   radix_pass(s, desc0, nullptr, desc, nullptr, nc, 32);  // stable counting sort by depth -> level order
   // flags + scan (node rank in the low word, number of first-children in the high word)
   uint64_t * flags = desc0;  // reuse
@@ -449,12 +511,14 @@ static void build_tree_t(System & s) {
   // allocate the tables
   s.b_cell.reserve((size_t)nc * 4);
   s.b_cell_parent.reserve((size_t)nc * 4);
+  s.b_node_parent.reserve((size_t)std::max<int64_t>(nn, 1) * 4);
   size_t nn4 = (size_t)std::max<int64_t>(nn, 1) * 4, nn8 = (size_t)std::max<int64_t>(nn, 1) * 8;
   s.b_child_begin.reserve(nn4); s.b_child_end.reserve(nn4); s.b_node_start.reserve(nn4); s.b_node_depth.reserve(nn4); s.b_sub.reserve(nn4);
   s.b_nmass.reserve(nn8); s.b_nradius.reserve(nn8); s.b_nlap.reserve(nn8);
   for(int d = 0; d < 3; ++d) { s.b_ncom[d].reserve(nn8); s.b_nbmin[d].reserve(nn8); s.b_nbmax[d].reserve(nn8); }
   Tree & t = s.tree;
   t.cell = s.b_cell.as<int32_t>(); t.cell_parent = s.b_cell_parent.as<int32_t>(); t.cell_desc = desc;
+  t.node_parent = s.b_node_parent.as<int32_t>();
   t.child_begin = s.b_child_begin.as<int32_t>(); t.child_end = s.b_child_end.as<int32_t>();
   t.node_start = s.b_node_start.as<int32_t>(); t.node_depth = s.b_node_depth.as<int32_t>(); t.sub = s.b_sub.as<int32_t>();
   t.mass = s.b_nmass.as<double>(); t.radius = s.b_nradius.as<double>(); t.lap = s.b_nlap.as<double>();
@@ -484,25 +548,45 @@ static void build_tree_t(System & s) {
     if(e <= b) continue;
     FSPH_LAUNCH((k_cofm<D>), (e - b + 127) / 128, 128, s.stream, t, s.cols(), b, e);
   }
-  FSPH_LAUNCH((k_pack_nodes<D>), (unsigned)((nn + 255) / 256), 256, s.stream, t, (int)nn);
-  FSPH_LAUNCH((k_pack_leaves<D>), nbc, 256, s.stream, t, s.cols(), nc);
   FSPH_CUDA_OK(cudaGetLastError());
 }
 
-void build_tree(System & s) {
-  if(s.dim == 1) build_tree_t<1>(s);
-  else if(s.dim == 2) build_tree_t<2>(s);
-  else build_tree_t<3>(s);
+template<int D>
+static void pack_tree_t(System & s) {
+  Tree & t = s.tree;
+  FSPH_LAUNCH((k_pack_nodes<D>), (unsigned)((t.nnodes + 255) / 256), 256, s.stream, t, t.nnodes);
+  FSPH_LAUNCH((k_pack_leaves<D>), (unsigned)((t.ncells + 255) / 256), 256, s.stream, t, s.cols(), (int64_t)t.ncells);
+  FSPH_CUDA_OK(cudaGetLastError());
+}
+
+void finish_tree(System & s) {
+  if(s.dim == 1) pack_tree_t<1>(s);
+  else if(s.dim == 2) pack_tree_t<2>(s);
+  else pack_tree_t<3>(s);
+  find_work_cells(s);
+}
+
+void build_tree_edges(System & s, const TreeEdges & e) {
+  s.last_perm = nullptr;  // the tree build reuses the sort's scratch
+  if(s.dim == 1) build_tree_t<1>(s, e);
+  else if(s.dim == 2) build_tree_t<2>(s, e);
+  else build_tree_t<3>(s, e);
   s.tree_valid = true;
   s.tree_dirty = false;
   s.search_valid = false;
-  find_work_cells(s);
+  if(e.finish) finish_tree(s);
+}
+
+void build_tree(System & s) {
+  TreeEdges e;
+  build_tree_edges(s, e);
 }
 
 // ---- work cells ---------------------------------------------------------------------------------------
 // traversal_sph, tree_topology.h:221-235: maximal nodes with sub_entities <= 128, plus lone leaves hanging
 // under bigger nodes.  Work cells are disjoint particle ranges; listing them by first particle gives Morton order.
-__global__ void __launch_bounds__(256) k_wc_mark(Tree t, int64_t nc, uint32_t * __restrict__ wc_at) {
+__global__ void __launch_bounds__(256) k_wc_mark(Tree t, int64_t nc, uint32_t * __restrict__ wc_at, const int32_t * __restrict__ type,
+  int ghosts) {
   int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(c >= nc) return;
   int v = t.cell[c];
@@ -511,6 +595,8 @@ __global__ void __launch_bounds__(256) k_wc_mark(Tree t, int64_t nc, uint32_t * 
   bool parent_big = p < 0 || t.sub[p] > SUB_ENTITIES;
   if(small && parent_big) {
     int start = v >= 0 ? v : t.node_start[~v];
+    // cells of remote copies are only sources: the rank that owns them runs their sweeps (tree_topology.h:229, !is_shared)
+    if(ghosts && (type[start] & TYPE_GHOST)) return;
     wc_at[start] = (uint32_t)c + 1u;
   }
 }
@@ -539,7 +625,7 @@ void find_work_cells(System & s) {
   uint32_t * wc_at = s.b_cnt0.as<uint32_t>();
   uint32_t * ex = s.b_tmp[0].as<uint32_t>();
   FSPH_CUDA_OK(cudaMemsetAsync(wc_at, 0, (size_t)n * 4, s.stream));
-  FSPH_LAUNCH(k_wc_mark, (unsigned)((nc + 255) / 256), 256, s.stream, s.tree, nc, wc_at);
+  FSPH_LAUNCH(k_wc_mark, (unsigned)((nc + 255) / 256), 256, s.stream, s.tree, nc, wc_at, s.col_type.as<int32_t>(), s.has_ghosts ? 1 : 0);
   unsigned nbp = (unsigned)((n + 255) / 256);
   FSPH_LAUNCH(k_flag_nonzero, nbp, 256, s.stream, wc_at, ex, n);
   exclusive_scan_u32(s, ex, ex, n, nullptr);

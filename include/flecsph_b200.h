@@ -230,6 +230,38 @@ int32_t fsph_neighbor_lists(fsph_system * s, int64_t * offsets, int64_t * ids);
  * names is a ';'-separated list, returns the number of phases. */
 int32_t fsph_phase_times(fsph_system * s, double * ms, int32_t cap, const char ** names);
 
+/* --- several ranks: Morton-key domain decomposition ------------------------
+ * The reference distributes a body_system over MPI ranks (MPI_Init in
+ * app/drivers/hydro/main.cc:38; MPI_Comm_rank/size in bodies_system.h:47-52):
+ * psort.h:227-322 (sample sort + MPI_Alltoallv), tree_topology.h:1549-1744
+ * (share_nodes_) and :1276-1542 (remote branch requests).  Here a system joins
+ * a communicator once, after fsph_create; from then on fsph_update_iteration,
+ * fsph_reset_ghosts, fsph_reduce and fsph_step are collective calls (every rank
+ * must issue them in the same order) and each rank holds the bodies of one
+ * contiguous range of the global key order.  fsph_nbodies / fsph_get_column see
+ * the owned bodies only.  Results equal those of one rank.
+ *   nccl : one process per GPU; rank 0 calls fsph_comm_unique_id and ships the
+ *          128 bytes to the other ranks (any side channel), every rank then calls
+ *          fsph_comm_init_nccl.  libnccl.so.2 is resolved at run time.
+ *   local: several systems of one process, one host thread each, on one or more
+ *          GPUs (used by the single-GPU test-suite). */
+int32_t fsph_comm_unique_id(char * out128);
+int32_t fsph_comm_init_nccl(fsph_system * s, const char * unique_id, int32_t rank, int32_t nranks);
+void * fsph_local_group_create(int32_t nranks);
+void fsph_local_group_destroy(void * group);
+int32_t fsph_comm_init_local(fsph_system * s, void * group, int32_t rank);
+int32_t fsph_comm_rank(const fsph_system * s);
+int32_t fsph_comm_size(const fsph_system * s);
+int64_t fsph_nghosts(const fsph_system * s);  /* remote copies currently held (after update_iteration) */
+/* Host-side planning used by fsph_update_iteration on several ranks (pure functions, no device):
+ * weighted splitters from `nsamples` regular key samples per rank (psort.h:258-301), and the move of a splitter
+ * down to the first key of the <= 128-body work cell (tree_topology.h:221-235) that straddles it, given the keys
+ * held by all ranks just below / at-or-above it. */
+void fsph_dd_choose_splitters(int32_t nranks, int32_t nsamples, const uint64_t * sample_keys, const int64_t * counts,
+  uint64_t * splitters /*[nranks-1]*/);
+uint64_t fsph_dd_align_splitter(int32_t dim, const uint64_t * below, int32_t nbelow, const uint64_t * above, int32_t nabove,
+  uint64_t splitter);
+
 /* Number of device kernels this library has launched in the calling process (0 for the CPU checkers). */
 uint64_t fsph_launch_count(void);
 

@@ -1,0 +1,164 @@
+"""Domain decomposition: P ranks must reproduce the single-rank result -- keys and
+neighbour sets bit-exact, fp64 physics within 1e-10 -- on the same initial data, whatever the initial distribution of
+the bodies over the ranks.  The ranks are P systems of one process joined by the in-process communicator (one host
+thread each, all on cuda:0), so the whole decomposition path runs in the 1-GPU test-suite; the NCCL transport behind
+the same interface is exercised by tests/dist_nccl_check.py under torchrun on >= 2 GPUs."""
+import numpy as np
+import pytest
+from flecsph_b200 import capi
+from common import make_system, case, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ["pos", "vel", "velhalf", "rho", "P", "u", "e", "cs", "acc", "dedt", "dudt", "h", "vsig", "dt"]
+
+
+def split_fields(fields, nranks, mode, seed=3):
+    n = len(fields["mass"])
+    if mode == "random":
+        owner = np.random.default_rng(seed).integers(0, nranks, n)
+    elif mode == "chunks":
+        owner = (np.arange(n) * nranks) // n
+    else:  # everything but a handful on rank 0
+        owner = np.zeros(n, np.int64)
+        owner[: 40 * (nranks - 1)] = 1 + np.arange(40 * (nranks - 1)) % (nranks - 1)
+    return [{k: np.ascontiguousarray(v[owner == r]) for k, v in fields.items()} for r in range(nranks)]
+
+
+def make_ranks(fields, par, dim, nranks, mode):
+    p = capi.default_params(dim, **par)
+    L = capi.LocalRanks(p, nranks)
+    parts = split_fields(fields, nranks, mode)
+
+    def load(r, s):
+        s.load_bodies(parts[r])
+        s.set_time(p.initial_dt, 0.0, 0)
+    L.call(load)
+    return L
+
+
+def gathered(L, names):
+    """Columns of all ranks concatenated and ordered by body id."""
+    snaps = L.call(lambda r, s: s.snapshot(names + ["id"]))
+    ids = np.concatenate([sn["id"] for sn in snaps])
+    order = np.argsort(ids, kind="stable")
+    return {nm: np.concatenate([sn[nm] for sn in snaps])[order] for nm in names + ["id"]}
+
+
+def by_id(S, names):
+    sn = S.snapshot(names + ["id"])
+    order = np.argsort(sn["id"], kind="stable")
+    return {nm: sn[nm][order] for nm in names + ["id"]}
+
+
+def neighbor_sets(systems_or_one):
+    """dict id -> sorted neighbour ids."""
+    out = {}
+    for s_ in systems_or_one:
+        off, ids = s_.neighbor_lists()
+        own = s_.get(capi.COL_ID)
+        assert len(off) == len(own) + 1
+        for i, pid in enumerate(own):
+            out[int(pid)] = ids[off[i]:off[i + 1]]
+    return out
+
+
+CASES = [
+    ("sedov", dict(nx=24), 2, "random"),
+    ("sedov", dict(nx=24), 3, "chunks"),
+    ("sedov", dict(nx=30), 4, "random"),
+    ("noh", dict(nx=22), 2, "skewed"),
+    ("random", dict(n=6000, dim=3, h_jitter=0.2, seed=5), 3, "random"),
+    ("random", dict(n=4000, dim=2, h_jitter=0.2, seed=6), 2, "random"),
+    ("sod", dict(nx=400), 2, "chunks"),
+]
+
+
+@pytest.mark.parametrize("name,kw,nranks,mode", CASES, ids=["%s-%d-%s" % (c[0], c[2], c[3]) for c in CASES])
+def test_decomposition_matches_single_rank(name, kw, nranks, mode):
+    f, par, dim = case(name, **kw)
+    S = make_system("cuda", f, par, dim)
+    L = make_ranks(f, par, dim, nranks, mode)
+    try:
+        S.update_iteration()
+        L.call(lambda r, s: s.update_iteration())
+        # every body is owned exactly once, ranks hold increasing key ranges, keys equal the single-rank keys
+        a, b = by_id(S, ["key"]), gathered(L, ["key"])
+        assert np.array_equal(a["id"], b["id"]), "bodies lost or duplicated"
+        assert np.array_equal(a["key"], b["key"]), "keys differ"
+        keys = L.call(lambda r, s: s.get(capi.COL_KEY))
+        for r in range(nranks):
+            assert len(keys[r]) > 0 and np.all(keys[r][1:] > keys[r][:-1])
+            if r:
+                assert keys[r - 1][-1] < keys[r][0]
+        lo0, hi0 = S.get_range()
+        for lo, hi in L.call(lambda r, s: s.get_range()):
+            assert np.array_equal(lo, lo0) and np.array_equal(hi, hi0)
+        # neighbour sets (the update_iteration above was undone by the column reads: redo it, then search)
+        S.update_iteration()
+        S.apply_in_smoothinglength(capi.SWEEP_NEIGHBORS_ONLY)
+
+        def search(r, s):
+            s.update_iteration()
+            s.apply_in_smoothinglength(capi.SWEEP_NEIGHBORS_ONLY)
+            return s.nghosts()
+        ghosts = L.call(search)
+        assert sum(ghosts) > 0
+        ref = neighbor_sets([S])
+        got = neighbor_sets(L.ranks)
+        assert ref.keys() == got.keys()
+        bad = [k for k in ref if not np.array_equal(ref[k], got[k])]
+        assert not bad, "neighbour sets differ for %d bodies (e.g. id %d)" % (len(bad), bad[0])
+    finally:
+        L.close()
+        S.close()
+
+
+STEP_CASES = [
+    ("sedov", dict(nx=24), 2, "random", 3),
+    ("sedov", dict(nx=30), 4, "chunks", 3),
+    ("noh", dict(nx=22), 3, "random", 3),
+    ("collapse", dict(nx=16), 2, "random", 3),
+    ("sod", dict(nx=400), 2, "chunks", 5),
+    ("random", dict(n=4000, dim=2, h_jitter=0.1, seed=8), 2, "random", 2),
+]
+
+
+@pytest.mark.parametrize("name,kw,nranks,mode,nsteps", STEP_CASES, ids=["%s-%d" % (c[0], c[2]) for c in STEP_CASES])
+def test_steps_match_single_rank(name, kw, nranks, mode, nsteps):
+    f, par, dim = case(name, **kw)
+    S = make_system("cuda", f, par, dim)
+    L = make_ranks(f, par, dim, nranks, mode)
+    try:
+        for it in range(nsteps):
+            S.step(initial=(it == 0))
+            L.call(lambda r, s: s.step(initial=(it == 0)))
+            assert all(t == S.get_time() for t in L.call(lambda r, s: s.get_time())), "dt / time differ"
+        a, b = by_id(S, FIELDS), gathered(L, FIELDS)
+        assert np.array_equal(a["id"], b["id"])
+        for nm in FIELDS:
+            e = rel_err(b[nm], a[nm])
+            assert e <= 1e-10, "%s: max rel err %g" % (nm, e)
+        for op in (capi.GET_TOTAL_MASS, capi.GET_TOTAL_ENERGY, capi.GET_TOTAL_MOMENTUM):
+            want = S.get_all(op)
+            for got in L.call(lambda r, s: s.get_all(op)):
+                assert np.allclose(got, want, rtol=1e-12, atol=1e-14 * max(1.0, np.abs(want).max()))
+    finally:
+        L.close()
+        S.close()
+
+
+def test_conservation_100_steps_two_ranks():
+    """SURVEY.md 8 / north star: conserved energy within 1e-6 over 100 steps, also when decomposed."""
+    f, par, dim = case("sedov", nx=20)
+    L = make_ranks(f, par, dim, 2, "random")
+    try:
+        e0 = None
+        for it in range(100):
+            L.call(lambda r, s: s.step(initial=(it == 0)))
+            if it == 0:
+                e0 = L.call(lambda r, s: s.get_all(capi.GET_TOTAL_ENERGY)[0])[0]
+        e1 = L.call(lambda r, s: s.get_all(capi.GET_TOTAL_ENERGY)[0])[0]
+        assert abs(e1 - e0) <= 1e-6 * abs(e0)
+    finally:
+        L.close()
