@@ -179,6 +179,9 @@ def main():
     import torch
     import torch.distributed as dist
     from flecsph_b200 import capi
+    if os.environ.get("FSPH_BENCH_TRACE"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["FSPH_BENCH_TRACE"]), repeat=True, file=sys.stderr)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU path in the product)")
     torch.cuda.set_device(local_rank)
@@ -190,11 +193,33 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    f, par, nx = sedov_fields(a.particles)
-    n = len(f["mass"])
-    config.update({"particles_per_gpu": n, "lattice_nx": nx,
-                   "parallelism": "single GPU" if world == 1 else "%d independent replicas (weak); Morton domain decomposition + halo not implemented yet" % world})
-    s = make_cuda_system(f, par, local_rank)
+    if world == 1:
+        f, par, nx = sedov_fields(a.particles)
+        n = n_total = len(f["mass"])
+        s = make_cuda_system(f, par, local_rank)
+        config.update({"particles_per_gpu": n, "lattice_nx": nx, "parallelism": "single GPU"})
+    else:
+        # weak scaling: ONE Sedov sphere of world x 64 M bodies, Morton domain decomposition over the GPUs of the box
+        # (sample-sort all-to-all, locally-essential-tree halo, ghost refresh: NCCL over NVLink; fsph_dist.cu).
+        # Every rank generates a slab of lattice layers; the first update_iteration re-partitions by key.
+        from flecsph_b200 import initial_data as idata
+
+        def allsum(x):
+            t = torch.tensor([int(x)], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t)
+            return int(t[0])
+        nx = idata.nx_for_particles(a.particles * world)
+        f, par = idata.sedov_3d(nx=nx, slab=(rank, world), allsum=allsum)
+        n_total = allsum(len(f["mass"]))
+        n = n_total // world
+        s = make_cuda_system(f, par, local_rank)
+        uid = [capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        s.comm_init_nccl(uid[0], rank, world)
+        config.update({"particles_total": n_total, "particles_per_gpu": n, "lattice_nx": nx,
+                       "parallelism": "Morton-key domain decomposition over %d GPUs (one rank per GPU): sample-sort all-to-all, "
+                                      "locally-essential-tree halo, ghost refresh before every sweep, NCCL" % world})
+    del f
     s.step(initial=True)
     for _ in range(warmup):
         s.step()
@@ -215,24 +240,36 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     launches = s.launch_count() - l0
     clocks = sampler.stop()
-    nn_mean = float(s.get(capi.COL_NNEIGH).astype(np.float64).mean())
+    nghosts = s.nghosts()
+    nn_sum = float(s.get(capi.COL_NNEIGH).astype(np.float64).sum())
     t_dev = total_ms / 1e3
     tt = torch.tensor([t_dev, t_wall], dtype=torch.float64, device="cuda")
+    ts = torch.tensor([nn_sum, float(nghosts)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ts)
+        for k in list(phase_acc):
+            tp = torch.tensor([phase_acc[k]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            phase_acc[k] = float(tp[0])
+        config["ghosts_per_gpu_mean"] = float(ts[1]) / world
     t_dev, t_wall = float(tt[0]), float(tt[1])
-    value = n * world * a.steps / t_dev
+    nn_mean = float(ts[0]) / n_total
+    value = n_total * a.steps / t_dev
 
     # ---- e2e: host buffers, H2D of the state + D2H of the results inside the timed region ------------------
     e2e = None
     if not a.no_e2e:
         up, down = e2e_columns(capi)
         bufs = {}
+        cap = n if world == 1 else int(1.25 * n) + 4096   # the owned count of a rank drifts with the re-partitioning
         for col, nc in down:
             dt_ = torch.int64 if col == capi.COL_ID else torch.float64
-            bufs[col] = [torch.empty(n, dtype=dt_).pin_memory() for _ in range(nc)]
+            bufs[col] = [torch.empty(cap, dtype=dt_).pin_memory() for _ in range(nc)]
 
         def download():
+            if s.nbodies() > cap:
+                raise SystemExit("e2e staging buffers too small for this rank's share")
             for col, nc in down:
                 for c in range(nc):
                     s.get_component(col, c, bufs[col][c].data_ptr())
@@ -242,8 +279,8 @@ def main():
                 for c in range(nc):
                     s.set_component(col, c, bufs[col][c].data_ptr())
         download()
-        h2d = sum(nc for _, nc in up) * 8 * n
-        d2h = sum(nc for _, nc in down) * 8 * n
+        h2d = sum(nc for _, nc in up) * 8 * n_total
+        d2h = sum(nc for _, nc in down) * 8 * n_total
         barrier()
         t0 = time.perf_counter()
         for _ in range(a.steps):
@@ -255,10 +292,15 @@ def main():
         tte = torch.tensor([te], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tte, op=dist.ReduceOp.MAX)
-        e2e = {"value": n * world * a.steps / float(tte[0]), "unit": "particle-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        e2e = {"value": n_total * a.steps / float(tte[0]), "unit": "particle-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": 1e3 * float(tte[0]) / a.steps}
         del bufs
 
+    # tear down on every rank in the same order (ncclCommDestroy of the library's communicator, then torch's)
+    s.close()
+    if world > 1:
+        barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return 0
     peak, how = measured_peaks()
@@ -287,9 +329,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "roofline_step": roofline_step, "fp64": fp64, "cpu_baseline": cpu,
             "phases_ms": phases, "mean_neighbors": nn_mean, "wall_ms_per_step": 1e3 * t_wall / a.steps}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
     return 0
 
 

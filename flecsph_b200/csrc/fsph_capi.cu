@@ -35,23 +35,6 @@ int scalar_field(int col) {
   }
 }
 
-struct PhaseScope {
-  System & s;
-  PhaseScope(System & sys, const char * name) : s(sys) {
-    if(!s.timing) return;
-    Phase p;
-    p.name = name;
-    cudaEventCreate(&p.e0);
-    cudaEventCreate(&p.e1);
-    cudaEventRecord(p.e0, s.stream);
-    s.phases.push_back(p);
-  }
-  ~PhaseScope() {
-    if(!s.timing) return;
-    cudaEventRecord(s.phases.back().e1, s.stream);
-  }
-};
-
 void finish_phases(System & s) {
   if(!s.timing) return;
   cudaStreamSynchronize(s.stream);

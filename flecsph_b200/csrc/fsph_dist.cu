@@ -32,6 +32,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include "fsph_internal.h"
 
@@ -62,6 +63,7 @@ struct LevelTable {
 
 struct Dist {
   std::vector<uint64_t> split;  // [P + 1] first key of every rank's range (split[0] = 0, split[P] = ~0)
+  std::vector<uint64_t> split_raw;  // the same before the alignment to work cells (kept from step to step)
   std::vector<size_t> send_cnt, send_off, recv_cnt, recv_off;  // halo plan, in bodies
   int64_t nsend = 0, nghost = 0;
   DevBuf send_idx, ghost_pos, sendbuf, recvbuf, small, small2, bitmap, bitmap_all, nmask, emask, flags, ex, inv;
@@ -212,6 +214,18 @@ __global__ void __launch_bounds__(256) k_unpack8(const uint64_t * __restrict__ i
   uint64_t * __restrict__ out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(i < n) out[pos[i]] = in[i];
+}
+struct FieldPtrs {
+  uint64_t * p[16];
+};
+// refresh traffic of one peer: out[field][body] = col[field][idx[body]]  (blockIdx.y = field)
+__global__ void __launch_bounds__(256) k_pack_fields(FieldPtrs f, const uint32_t * __restrict__ idx, int64_t n, uint64_t * __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n) out[(size_t)blockIdx.y * n + i] = f.p[blockIdx.y][idx[i]];
+}
+__global__ void __launch_bounds__(256) k_unpack_fields(FieldPtrs f, const uint32_t * __restrict__ pos, int64_t n, const uint64_t * __restrict__ in) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n) f.p[blockIdx.y][pos[i]] = in[(size_t)blockIdx.y * n + i];
 }
 __global__ void __launch_bounds__(256) k_mark_ghost(int32_t * __restrict__ type, int64_t b, int64_t e) {
   int64_t i = b + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -500,11 +514,12 @@ static void exchange_bodies(System & s, const std::vector<size_t> & soff, const 
   std::vector<std::pair<DevBuf *, int>> cols;
   live_columns(s, cols);
   std::vector<size_t> so(P), sc(P), ro(P), rc(P);
-  const size_t room = n_new + n_new / 4 + 4096;  // head-room for the halo that is appended later
+  // head-room for the halo that is appended later; buffers only ever grow (cudaMalloc / cudaFree cost ~1 ms each)
+  const size_t room = n_new + n_new / 3 + 4096;
   for(auto & c : cols) {
     const size_t e = (size_t)c.second;
     DevBuf & scratch = e == 8 ? s.scratch_col : s.b_tmp[0];
-    scratch.reserve_exact(std::max(room * e, c.first->cap));
+    if(scratch.cap < std::max(n_new * e, c.first->cap)) scratch.reserve_exact(std::max(room * e, c.first->cap));
     for(int q = 0; q < P; ++q) { so[q] = soff[q] * e; sc[q] = scnt[q] * e; ro[q] = roff[q] * e; rc[q] = rcnt[q] * e; }
     s.comm->all_to_all_v(c.first->p, so.data(), sc.data(), scratch.p, ro.data(), rc.data(), s.stream);
     std::swap(c.first->p, scratch.p);
@@ -527,8 +542,12 @@ static void dist_update_iteration_t(System & s) {
   if(P > DD_MAX_RANKS) throw std::runtime_error("more than 32 ranks are not supported");
   Dist & d = dist_of(s);
   constexpr int B = 63 / D;
-  dist_drop_ghosts(s);
-  if(s.n <= 0) throw std::runtime_error("a rank without bodies cannot take part in the decomposition");
+  std::unique_ptr<PhaseScope> ph;
+  ph.reset(new PhaseScope(s, "dd:range_keys_sort"));
+  // the remote copies of the previous iteration are still interleaved with the owned bodies: they take no part in the
+  // range, get the largest key and fall off the end of the next sort (no separate compaction pass)
+  const int64_t n_keep = s.n_owned_or_n();
+  if(n_keep <= 0) throw std::runtime_error("a rank without bodies cannot take part in the decomposition");
   s.col_gd.grow_keep((size_t)s.n * 4, 0, s.stream);
 
   // 1. global range (bodies_system.h:231-268): min / max are exact, every rank gets the single-rank result
@@ -552,12 +571,21 @@ static void dist_update_iteration_t(System & s) {
     }
   }
   compute_keys(s);
-  sort_bodies(s);
+  sort_bodies(s, n_keep);
+  s.has_ghosts = false;
+  s.n_owned = s.n;
+  s.tree_valid = false;
+  s.search_valid = false;
 
-  // 2. splitters from regular samples, aligned to work cells (psort.h:258-301)
-  d.split.assign(P + 1, 0);
-  d.split[P] = ~0ull;
-  {
+  ph.reset(new PhaseScope(s, "dd:splitters"));
+  // 2. splitters (psort.h:258-301).  The raw splitters of the previous iteration are kept while they balance the ranks
+  //    to within 3 %: bodies move little per step, so in steady state (almost) nothing changes rank.  They are
+  //    re-aligned to the work cells of the current bodies every time.
+  bool moved_any = false;
+  std::vector<size_t> soff(P), scnt(P), rcnt(P);
+  auto sample_splitters = [&]() {
+    d.split_raw.assign(P + 1, 0);
+    d.split_raw[P] = ~0ull;
     d.small.reserve((size_t)(DD_SAMPLES + 1) * 8 + 256);
     d.small2.reserve((size_t)(DD_SAMPLES + 1) * 8 * P + 256);
     uint64_t * smp = d.small.as<uint64_t>();
@@ -574,61 +602,79 @@ static void dist_update_iteration_t(System & s) {
       std::copy(all.begin() + (size_t)q * (DD_SAMPLES + 1), all.begin() + (size_t)q * (DD_SAMPLES + 1) + DD_SAMPLES, keys.begin() + (size_t)q * DD_SAMPLES);
       counts[q] = (int64_t)all[(size_t)q * (DD_SAMPLES + 1) + DD_SAMPLES];
     }
-    dd_choose_splitters(P, DD_SAMPLES, keys.data(), counts.data(), d.split.data() + 1);
-  }
-  if(P > 1) {
-    const int ns = P - 1;
-    const size_t wbytes = (size_t)ns * 2 * DD_WIN * 8;
-    d.small.reserve(wbytes + (size_t)ns * 8 + 256);
-    d.small2.reserve(wbytes * P + 256);
-    uint64_t * dsplit = reinterpret_cast<uint64_t *>(d.small.as<char>() + wbytes);
-    FSPH_CUDA_OK(cudaMemcpyAsync(dsplit, d.split.data() + 1, (size_t)ns * 8, cudaMemcpyHostToDevice, s.stream));
-    FSPH_LAUNCH(k_split_windows, ns, 2 * DD_WIN, s.stream, s.col_key.as<uint64_t>(), s.n, dsplit, d.small.as<uint64_t>());
-    cm.all_gather(d.small.p, d.small2.p, wbytes, s.stream);
-    std::vector<uint64_t> all((size_t)ns * 2 * DD_WIN * P);
-    FSPH_CUDA_OK(cudaMemcpyAsync(all.data(), d.small2.p, all.size() * 8, cudaMemcpyDeviceToHost, s.stream));
-    FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
-    std::vector<uint64_t> below, above;
-    for(int k = 0; k < ns; ++k) {
-      below.clear();
-      above.clear();
-      for(int q = 0; q < P; ++q) {
-        const uint64_t * w = all.data() + ((size_t)q * ns + k) * 2 * DD_WIN;
-        for(int t = 0; t < DD_WIN; ++t) {
-          if(w[t] != 0ull) below.push_back(w[t]);
-          if(w[DD_WIN + t] != ~0ull) above.push_back(w[DD_WIN + t]);
-        }
-      }
-      d.split[k + 1] = dd_align_splitter(D, below, above, d.split[k + 1]);
-    }
-    for(int k = 1; k < P; ++k) d.split[k] = std::max(d.split[k], d.split[k - 1]);
-  }
-
-  // 3. cut the local order at the splitters, exchange counts, then the bodies (psort.h:303-308)
-  {
+    dd_choose_splitters(P, DD_SAMPLES, keys.data(), counts.data(), d.split_raw.data() + 1);
+  };
+  // align the raw splitters to work cells, cut the local order, all-gather the counts; returns "balanced"
+  auto plan = [&]() -> bool {
+    d.split = d.split_raw;
     std::vector<int64_t> cut(P + 1, 0);
     cut[P] = s.n;
     if(P > 1) {
-      d.small.reserve((size_t)P * 16 + 256);
-      uint64_t * dsplit = d.small.as<uint64_t>();
-      int64_t * dcut = reinterpret_cast<int64_t *>(dsplit + P);
-      FSPH_CUDA_OK(cudaMemcpyAsync(dsplit, d.split.data() + 1, (size_t)(P - 1) * 8, cudaMemcpyHostToDevice, s.stream));
-      FSPH_LAUNCH(k_cuts, 1, 32, s.stream, s.col_key.as<uint64_t>(), s.n, dsplit, P - 1, dcut);
-      FSPH_CUDA_OK(cudaMemcpyAsync(cut.data() + 1, dcut, (size_t)(P - 1) * 8, cudaMemcpyDeviceToHost, s.stream));
+      const int ns = P - 1;
+      const size_t wbytes = (size_t)ns * 2 * DD_WIN * 8;
+      d.small.reserve(wbytes + (size_t)ns * 16 + 256);
+      d.small2.reserve(wbytes * P + 256);
+      uint64_t * dsplit = reinterpret_cast<uint64_t *>(d.small.as<char>() + wbytes);
+      int64_t * dcut = reinterpret_cast<int64_t *>(dsplit + ns);
+      FSPH_CUDA_OK(cudaMemcpyAsync(dsplit, d.split.data() + 1, (size_t)ns * 8, cudaMemcpyHostToDevice, s.stream));
+      FSPH_LAUNCH(k_split_windows, ns, 2 * DD_WIN, s.stream, s.col_key.as<uint64_t>(), s.n, dsplit, d.small.as<uint64_t>());
+      cm.all_gather(d.small.p, d.small2.p, wbytes, s.stream);
+      std::vector<uint64_t> all((size_t)ns * 2 * DD_WIN * P);
+      FSPH_CUDA_OK(cudaMemcpyAsync(all.data(), d.small2.p, all.size() * 8, cudaMemcpyDeviceToHost, s.stream));
+      FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
+      std::vector<uint64_t> below, above;
+      for(int k = 0; k < ns; ++k) {
+        below.clear();
+        above.clear();
+        for(int q = 0; q < P; ++q) {
+          const uint64_t * w = all.data() + ((size_t)q * ns + k) * 2 * DD_WIN;
+          for(int t = 0; t < DD_WIN; ++t) {
+            if(w[t] != 0ull) below.push_back(w[t]);
+            if(w[DD_WIN + t] != ~0ull) above.push_back(w[DD_WIN + t]);
+          }
+        }
+        d.split[k + 1] = dd_align_splitter(D, below, above, d.split[k + 1]);
+      }
+      for(int k = 1; k < P; ++k) d.split[k] = std::max(d.split[k], d.split[k - 1]);
+      // cut the local order at the splitters (psort.h:303-308)
+      FSPH_CUDA_OK(cudaMemcpyAsync(dsplit, d.split.data() + 1, (size_t)ns * 8, cudaMemcpyHostToDevice, s.stream));
+      FSPH_LAUNCH(k_cuts, 1, 32, s.stream, s.col_key.as<uint64_t>(), s.n, dsplit, ns, dcut);
+      FSPH_CUDA_OK(cudaMemcpyAsync(cut.data() + 1, dcut, (size_t)ns * 8, cudaMemcpyDeviceToHost, s.stream));
       FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
     }
     std::vector<int64_t> mine(P), all((size_t)P * P);
-    std::vector<size_t> soff(P), scnt(P), rcnt(P);
     for(int q = 0; q < P; ++q) { soff[q] = (size_t)cut[q]; scnt[q] = (size_t)(cut[q + 1] - cut[q]); mine[q] = (int64_t)scnt[q]; }
     dist_all_gather_host(s, mine.data(), all.data(), (size_t)P * 8);
+    moved_any = false;
+    int64_t total = 0, worst = 0;
+    for(int r = 0; r < P; ++r) {
+      int64_t got = 0;
+      for(int q = 0; q < P; ++q) {
+        got += all[(size_t)q * P + r];
+        if(q != r && all[(size_t)q * P + r] != 0) moved_any = true;
+      }
+      total += got;
+      worst = std::max(worst, got);
+    }
     for(int q = 0; q < P; ++q) rcnt[q] = (size_t)all[(size_t)q * P + R];
-    exchange_bodies(s, soff, scnt, rcnt);
+    return (double)worst <= 1.03 * (double)total / P + 256.0;
+  };
+  const bool had_splitters = (int)d.split_raw.size() == P + 1;
+  if(!had_splitters) sample_splitters();
+  if(!plan() && had_splitters) {
+    sample_splitters();
+    plan();
   }
+
+  ph.reset(new PhaseScope(s, "dd:exchange"));
+  // 3. the bodies change rank (psort.h:303-308); in steady state often none does: nothing to move, nothing to merge
+  if(moved_any) exchange_bodies(s, soff, scnt, rcnt);
   if(s.n <= 0) throw std::runtime_error("too few bodies for this many ranks (a rank received none)");
   s.n_owned = s.n;
-  s.b_keys2.reserve((size_t)s.n * 8);
-  sort_bodies(s);  // merge of the received runs
+  ph.reset(new PhaseScope(s, "dd:sort_owned"));
+  if(moved_any) sort_bodies(s);  // merge of the received runs
 
+  ph.reset(new PhaseScope(s, "dd:tree_owned"));
   // 4. owned tree with the edge keys of the neighbouring ranks (exchange_boundaries_, tree_topology.h:1976)
   const uint64_t klo = d.split[R], khi_incl = R + 1 < P ? d.split[R + 1] - 1ull : ~0ull;
   TreeEdges te;
@@ -660,6 +706,7 @@ static void dist_update_iteration_t(System & s) {
   cm.all_gather(d.path.p, d.path_all.p, path_bytes, s.stream);
   apply_records<D>(s, d.path_all.as<NodeBoxRec>(), (int64_t)(1 + DD_MAX_PATH) * P, P);
 
+  ph.reset(new PhaseScope(s, "dd:let_walk"));
   // 5. occupancy bitmaps + largest h of every rank
   DDGeom & g = d.geom;
   g.B = B; g.D = D; g.P = P; g.rank = R;
@@ -738,6 +785,7 @@ static void dist_update_iteration_t(System & s) {
     }
   }
 
+  ph.reset(new PhaseScope(s, "dd:halo_exchange"));
   // 7. halo exchange: counts, then every live column straight into the tail of the column, then the node records
   {
     std::vector<int64_t> mine((size_t)2 * P), all((size_t)2 * P * P);
@@ -774,6 +822,7 @@ static void dist_update_iteration_t(System & s) {
     if(d.nghost) FSPH_LAUNCH(k_mark_ghost, blocks(d.nghost), 256, s.stream, s.col_type.as<int32_t>(), s.n_owned, n_total);
     ensure_capacity(s, n_total);
 
+    ph.reset(new PhaseScope(s, "dd:merge_sort"));
     // 8. merge owned + ghosts, remember where every ghost went and where the bodies we serve to peers went
     s.n = n_total;
     s.has_ghosts = d.nghost > 0;
@@ -783,6 +832,7 @@ static void dist_update_iteration_t(System & s) {
     FSPH_LAUNCH(k_maps, blocks(n_total), 256, s.stream, s.last_perm, n_total, s.n_owned, d.inv.as<uint32_t>(), d.ghost_pos.as<uint32_t>());
     if(nsend) FSPH_LAUNCH(k_remap, blocks(nsend), 256, s.stream, d.send_idx.as<uint32_t>(), (int64_t)nsend, d.inv.as<uint32_t>());
 
+    ph.reset(new PhaseScope(s, "dd:tree_merged"));
     // 9. merged tree with the owners' leaf depths; global boxes for every node that holds remote bodies
     TreeEdges tm;
     tm.gd_in = s.col_gd.as<int32_t>();
@@ -793,6 +843,7 @@ static void dist_update_iteration_t(System & s) {
     FSPH_LAUNCH((k_fix_straddling<D>), blocks(s.tree.nnodes), 256, s.stream, s.tree, s.col_key.as<uint64_t>(), s.tree.nnodes, klo, khi_incl);
     finish_tree(s);
   }
+  ph.reset();
   FSPH_CUDA_OK(cudaGetLastError());
 }
 
@@ -816,12 +867,14 @@ void dist_refresh_ghosts(System & s) {
   d.sendbuf.reserve(std::max<size_t>(nsend * nf, 1) * 8);
   d.recvbuf.reserve(std::max<size_t>(ng * nf, 1) * 8);
   // layout: [peer][field][body of that peer's list]
+  if(nf > 16) throw std::runtime_error("too many refresh fields");
+  FieldPtrs fp;
+  for(size_t j = 0; j < nf; ++j) fp.p[j] = s.col[fields[j]].as<uint64_t>();
   for(int q = 0; q < P; ++q) {
     const size_t cnt = d.send_cnt[q];
     if(!cnt) continue;
-    for(size_t j = 0; j < nf; ++j)
-      FSPH_LAUNCH((k_pack<uint64_t>), blocks(cnt), 256, s.stream, s.col[fields[j]].as<uint64_t>(), d.send_idx.as<uint32_t>() + d.send_off[q],
-        (int64_t)cnt, d.sendbuf.as<uint64_t>() + d.send_off[q] * nf + j * cnt);
+    FSPH_LAUNCH(k_pack_fields, dim3(blocks(cnt), (unsigned)nf), 256, s.stream, fp, d.send_idx.as<uint32_t>() + d.send_off[q], (int64_t)cnt,
+      d.sendbuf.as<uint64_t>() + d.send_off[q] * nf);
   }
   std::vector<size_t> so(P), sc(P), ro(P), rc(P);
   for(int q = 0; q < P; ++q) {
@@ -832,9 +885,8 @@ void dist_refresh_ghosts(System & s) {
   for(int q = 0; q < P; ++q) {
     const size_t cnt = d.recv_cnt[q];
     if(!cnt) continue;
-    for(size_t j = 0; j < nf; ++j)
-      FSPH_LAUNCH(k_unpack8, blocks(cnt), 256, s.stream, d.recvbuf.as<uint64_t>() + d.recv_off[q] * nf + j * cnt,
-        d.ghost_pos.as<uint32_t>() + d.recv_off[q], (int64_t)cnt, s.col[fields[j]].as<uint64_t>());
+    FSPH_LAUNCH(k_unpack_fields, dim3(blocks(cnt), (unsigned)nf), 256, s.stream, fp, d.ghost_pos.as<uint32_t>() + d.recv_off[q], (int64_t)cnt,
+      d.recvbuf.as<uint64_t>() + d.recv_off[q] * nf);
   }
   FSPH_CUDA_OK(cudaGetLastError());
 }

@@ -171,6 +171,26 @@ struct System {
   int64_t n_owned_or_n() const { return has_ghosts ? n_owned : n; }
 };
 
+// CUDA-event bracket of one phase of fsph_step (no-op unless the step is being timed)
+struct PhaseScope {
+  System & s;
+  PhaseScope(System & sys, const char * name) : s(sys) {
+    if(!s.timing) return;
+    Phase p;
+    p.name = name;
+    cudaEventCreate(&p.e0);
+    cudaEventCreate(&p.e1);
+    cudaEventRecord(p.e0, s.stream);
+    s.phases.push_back(p);
+    idx = s.phases.size() - 1;
+  }
+  ~PhaseScope() {
+    if(!s.timing) return;
+    cudaEventRecord(s.phases[idx].e1, s.stream);
+  }
+  size_t idx = 0;
+};
+
 #define FSPH_CUDA_OK(call)                                                                       \
   do {                                                                                           \
     cudaError_t e_ = (call);                                                                     \
@@ -198,7 +218,8 @@ void exclusive_scan_u64(System & s, const uint64_t * in, uint64_t * out, int64_t
 // ---- fsph_tree.cu ---------------------------------------------------------------------------
 void compute_range(System & s);                 // bodies_system.h:231-268
 void compute_keys(System & s);                  // filling_curve.h:503-525
-void sort_bodies(System & s);                   // psort.h:227-322 (one rank): radix sort + column gather
+// psort.h:227-322 (one rank): radix sort + column gather; only the first n_keep bodies of the sorted order are kept
+void sort_bodies(System & s, int64_t n_keep = -1);
 void live_columns(System & s, std::vector<std::pair<DevBuf *, int>> & out);  // columns that carry state, element size
 void gather_bodies(System & s, const uint32_t * perm, int64_t n_new);  // every live column: out[i] = in[perm[i]], i < n_new
 void build_tree(System & s);                    // tree_topology.h:878-997 + default_physics.h:59-119

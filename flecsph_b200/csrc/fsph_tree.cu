@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256) k_range_partial(Cols c, int64_t n, double
 #pragma unroll
   for(int d = 0; d < D; ++d) { mn[d] = DBL_MAX; mx[d] = -DBL_MAX; }
   for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if(c.ghosts && (c.type[i] & TYPE_GHOST)) continue;
     double h = c.f[F_H][i];
 #pragma unroll
     for(int d = 0; d < D; ++d) {
@@ -110,6 +111,10 @@ __global__ void __launch_bounds__(256) k_keys(Cols c, int64_t n, Range3 r) {
   constexpr int B = KeyBits<D>::B;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= n) return;
+  if(c.ghosts && (c.type[i] & TYPE_GHOST)) {
+    c.key[i] = ~0ull;  // last in key order: the next sort drops the remote copies of the previous iteration
+    return;
+  }
   const uint64_t maxv = (uint64_t(1) << B) - 1;
   const double two_b = (double)(uint64_t(1) << B);
   uint64_t cd[D];
@@ -178,7 +183,10 @@ void live_columns(System & s, std::vector<std::pair<DevBuf *, int>> & out) {
   out.emplace_back(&s.col_id, 8);
   out.emplace_back(&s.col_key, 8);
   out.emplace_back(&s.col_type, 4);
-  if(s.comm) out.emplace_back(&s.col_gd, 4);
+  if(s.comm) {
+    out.emplace_back(&s.col_gd, 4);
+    out.emplace_back(&s.col_nneigh, 4);  // stays aligned with the owned bodies when the ghosts are dropped
+  }
 }
 
 // out[i] = in[perm[i]] for every live column; perm must not live in scratch_col / b_tmp[0]
@@ -192,8 +200,9 @@ void gather_bodies(System & s, const uint32_t * perm, int64_t n_new) {
   FSPH_CUDA_OK(cudaGetLastError());
 }
 
-void sort_bodies(System & s) {
+void sort_bodies(System & s, int64_t n_keep) {
   const int64_t n = s.n;
+  if(n_keep < 0) n_keep = n;
   s.b_keys2.reserve((size_t)n * 8);
   s.b_perm.reserve((size_t)n * 4);
   s.b_perm2.reserve((size_t)n * 4);
@@ -211,12 +220,13 @@ void sort_bodies(System & s) {
   // skip the gathers when the bodies are already in key order
   uint32_t * flag = s.b_status.as<uint32_t>() + 1;
   FSPH_CUDA_OK(cudaMemsetAsync(flag, 0, 4, s.stream));
-  unsigned nb = (unsigned)((n + 255) / 256);
-  FSPH_LAUNCH(k_is_identity, nb, 256, s.stream, perm, n, flag);
+  unsigned nb = (unsigned)((n_keep + 255) / 256);
+  if(n_keep > 0) FSPH_LAUNCH(k_is_identity, nb, 256, s.stream, perm, n_keep, flag);
   uint32_t moved = 0;
   FSPH_CUDA_OK(cudaMemcpyAsync(&moved, flag, 4, cudaMemcpyDeviceToHost, s.stream));
   FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
-  if(moved) gather_bodies(s, perm, n);
+  if(moved) gather_bodies(s, perm, n_keep);
+  s.n = n_keep;
   FSPH_CUDA_OK(cudaGetLastError());
 }
 

@@ -27,8 +27,10 @@ def _axis(lo, hi, step, offset=0.0):
     return p[p < hi]
 
 
-def lattice_3d(lattice_type, domain_type, bmin, bmax, sep):
-    """generator_lattice_3d (lattice.h:224-293). Returns [n,3] positions in generation order."""
+def lattice_3d(lattice_type, domain_type, bmin, bmax, sep, slab=None):
+    """generator_lattice_3d (lattice.h:224-293). Returns [n,3] positions in generation order.
+    slab = (k, K): only the z layers of the k-th of K contiguous groups of layers (one group per rank of a
+    multi-GPU run; the layers of all groups together are the full lattice)."""
     xmin, ymin, zmin = bmin
     xmax, ymax, zmax = bmax
     dx, dy, dz = sep, sep * math.sqrt(3.0) / 2.0, sep * math.sqrt(2.0 / 3.0)
@@ -36,7 +38,15 @@ def lattice_3d(lattice_type, domain_type, bmin, bmax, sep):
     out = []
     zs = _axis(zmin, zmax, dx if lattice_type == 0 else dz)
     zl = 0
-    for z in zs:
+    lay_lo, lay_hi = (0, len(zs)) if slab is None else ((slab[0] * len(zs)) // slab[1], ((slab[0] + 1) * len(zs)) // slab[1])
+    for iz, z in enumerate(zs):
+        if not (lay_lo <= iz < lay_hi):
+            # stacking state advances as if the layer had been generated
+            if lattice_type == 1:
+                zl = 1 - zl
+            elif lattice_type == 2:
+                zl = (zl + 1) * (1 if zl < 3 else 0)
+            continue
         if lattice_type == 0:
             ys = _axis(ymin, ymax, dx)
             xs = _axis(xmin, xmax, dx)
@@ -61,30 +71,37 @@ def lattice_3d(lattice_type, domain_type, bmin, bmax, sep):
             zl = 1 - zl
         elif lattice_type == 2:
             zl = (zl + 1) * (1 if zl < 3 else 0)
-    return np.concatenate(out, 0)
+    return np.concatenate(out, 0) if out else np.zeros((0, 3))
 
 
-def _sphere_common(nx, rho0, P0, gamma, eta, kernel_width, R=1.0, lattice_type=2):
+def _sphere_common(nx, rho0, P0, gamma, eta, kernel_width, R=1.0, lattice_type=2, slab=None, allsum=None):
+    """slab / allsum: generate only this rank's layers; allsum(int) -> the sum over all ranks (global counts)."""
     sep = 2.0 * R / (nx - 1)
-    pos = lattice_3d(lattice_type, 1, (-R,) * 3, (R,) * 3, sep)
-    n = len(pos)
+    pos = lattice_3d(lattice_type, 1, (-R,) * 3, (R,) * 3, sep, slab=slab)
+    n_local = len(pos)
+    n = allsum(n_local) if allsum else n_local
     total_mass = rho0 * (4.0 * math.pi / 3.0) * R ** 3  # constant profile normalisation (sedov/main.cc:126-133)
     m = total_mass / n
     h = eta * kernel_width * (m / rho0) ** (1.0 / 3.0)
     K0 = P0 / rho0 ** gamma
     u = K0 * rho0 ** (gamma - 1) / (gamma - 1)
+    ids = np.arange(n_local, dtype=np.int64)
+    if slab is not None:
+        ids += np.int64(slab[0]) << np.int64(40)  # unique across ranks without a prefix sum of the counts
+    n = n_local
     f = dict(pos=pos, vel=np.zeros((n, 3)), mass=np.full(n, m), h=np.full(n, h), rho=np.full(n, rho0),
-             u=np.full(n, u), id=np.arange(n, dtype=np.int64))
+             u=np.full(n, u), id=ids)
     return f, m
 
 
-def sedov_3d(nx=20, eta=1.2, blast_energy=2e-7, blast_radius=0.06, P0=1e-7, gamma=1.4):
+def sedov_3d(nx=20, eta=1.2, blast_energy=2e-7, blast_radius=0.06, P0=1e-7, gamma=1.4, slab=None, allsum=None):
     """Sedov blast wave, data/sedov_nx20.par semantics; nx scales the particle count (~0.74 nx^3)."""
-    f, m = _sphere_common(nx, 1.0, P0, gamma, eta, 2.0)
+    f, m = _sphere_common(nx, 1.0, P0, gamma, eta, 2.0, slab=slab, allsum=allsum)
     r = np.sqrt((f["pos"] ** 2).sum(1))
     blast = r < blast_radius
-    if blast.any():
-        f["u"] = f["u"] + np.where(blast, blast_energy / (m * blast.sum()), 0.0)
+    nblast = allsum(int(blast.sum())) if allsum else int(blast.sum())
+    if nblast:
+        f["u"] = f["u"] + np.where(blast, blast_energy / (m * nblast), 0.0)
     f["P"] = f["rho"] * f["u"] * (gamma - 1)
     f["dt"] = np.full(len(r), 1e-4)
     par = dict(sph_kernel="wendland c4", sph_eta=eta, poly_gamma=gamma, initial_dt=1e-4, sph_variable_h=1,

@@ -162,3 +162,19 @@ def test_conservation_100_steps_two_ranks():
         assert abs(e1 - e0) <= 1e-6 * abs(e0)
     finally:
         L.close()
+
+
+def test_nccl_ranks():
+    """The same decomposition over the NCCL transport, one process per GPU (needs >= 2 GPUs on the box)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("one GPU: the NCCL transport needs one GPU per rank (the in-process transport covers the logic)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(ng, 4)), "--master-addr", "127.0.0.1",
+           "--master-port", "29531", os.path.join(root, "tests", "dist_nccl_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "NCCL DECOMPOSITION OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
