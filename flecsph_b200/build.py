@@ -19,6 +19,7 @@ SOURCES = {
     "fsph_sweeps.cu": [],
     "fsph_capi.cu": [],
     "fsph_comm.cu": [],
+    "fsph_fmm.cu": ["-fmad=false"],
     "fsph_dist.cu": ["-fmad=false"],
 }
 

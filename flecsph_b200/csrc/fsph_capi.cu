@@ -118,7 +118,13 @@ void do_sweep(System & s, int op) {
 void do_step(System & s, int initial) {
   // app/drivers/hydro/main_driver.cc:102-277 (+ newtonian/main_driver.cc:218-222)
   const fsph_params & P = s.par;
-  if(P.enable_fmm) throw std::runtime_error("FMM gravity is not implemented on the device yet");
+  auto gravity = [&]() {
+    // newtonian/main_driver.cc:218-222: right after compute_acceleration (which zeroed g_acc / g_pot)
+    if(P.enable_fmm) {
+      PhaseScope p(s, "fmm");
+      gravitation_fmm(s);
+    }
+  };
   auto A = [&](int op) { PhaseScope p(s, "elementwise"); apply(s, op); };
   // the element-wise functors after the last sweep of the iteration are issued as one fused pass
   const int recompute_op = P.thermokinetic_formulation ? FSPH_APPLY_RECOMPUTE_P_CS_THERMOKINETIC : FSPH_APPLY_RECOMPUTE_P_CS;
@@ -150,6 +156,7 @@ void do_step(System & s, int initial) {
     A(FSPH_APPLY_SAVE_VELOCITYHALF);
     do_reset_ghosts(s);
     do_sweep(s, 101);
+    gravity();
     timestep();
     if(P.evolve_internal_energy) energy_passes();
   }
@@ -183,6 +190,7 @@ void do_step(System & s, int initial) {
     do_sweep(s, 100);
     do_reset_ghosts(s);
     do_sweep(s, 101);
+    gravity();
     A(FSPH_APPLY_LEAPFROG_KICK_V);
     do_reset_ghosts(s);
     if(P.evolve_internal_energy) {
@@ -304,6 +312,7 @@ void fsph_destroy(fsph_system * s) {
   delete s->comm;
   s->comm = nullptr;
   s->col_gd.release();
+  s->b_fmm_nodes.release(); s->b_fmm_out.release(); s->b_fmm_stack.release();
   s->b_node_parent.release();
   DevBuf * all[] = {&s->col_id, &s->col_key, &s->col_type, &s->col_nneigh, &s->scratch_col, &s->b_perm, &s->b_keys2, &s->b_perm2,
     &s->b_cell, &s->b_cell_parent, &s->b_cell_desc, &s->b_cell_desc2, &s->b_child_begin, &s->b_child_end, &s->b_node_start,
@@ -555,7 +564,7 @@ int32_t fsph_reduce(fsph_system * s, int32_t op, double * out, int32_t nout) {
   return guarded(s, [&]() { reduce(*s, op, out, nout); });
 }
 int32_t fsph_gravitation_fmm(fsph_system * s) {
-  return guarded(s, [&]() { throw std::runtime_error("FMM gravity is not implemented on the device yet"); });
+  return guarded(s, [&]() { gravitation_fmm(*s); check_status(*s); });
 }
 int32_t fsph_get_range(fsph_system * s, double * lo, double * hi) {
   if(!s) return 1;

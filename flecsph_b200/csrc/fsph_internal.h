@@ -145,6 +145,8 @@ struct System {
   DevBuf col[NF64], col_id, col_key, col_type, col_nneigh, scratch_col;
   DevBuf b_perm, b_keys2, b_perm2, b_tmp[6];
   DevBuf b_node_parent;
+  DevBuf b_fmm_nodes, b_fmm_out, b_fmm_stack;   // FMM: node accumulators, output strip and stack of pending cell pairs
+  unsigned long long fmm_pairs = 0;             // cell pairs the last gravitation_fmm processed
   DevBuf b_cell, b_cell_parent, b_cell_desc, b_cell_desc2, b_child_begin, b_child_end, b_node_start, b_node_depth, b_sub;
   DevBuf b_noderec, b_leafrec;
   DevBuf b_nmass, b_ncom[3], b_nradius, b_nlap, b_nbmin[3], b_nbmax[3];
@@ -241,6 +243,9 @@ void export_neighbors(System & s, std::vector<int64_t> & off, std::vector<int64_
 
 // ---- fsph_sweeps.cu -------------------------------------------------------------------------
 void sweep(System & s, int op);                 // default_physics.h:193-566
+
+// ---- fsph_fmm.cu ----------------------------------------------------------------------------
+void gravitation_fmm(System & s);               // bodies_system.h:282 -> tree_topology.h:448-795 + fmm.h
 
 // ---- fsph_apply.cu --------------------------------------------------------------------------
 void apply(System & s, int op);                  // integration.h, default_physics.h element-wise
