@@ -20,6 +20,7 @@ SOURCES = {
     "fsph_capi.cu": [],
     "fsph_comm.cu": [],
     "fsph_fmm.cu": ["-fmad=false"],
+    "fsph_boundary.cu": ["-fmad=false"],
     "fsph_dist.cu": ["-fmad=false"],
 }
 

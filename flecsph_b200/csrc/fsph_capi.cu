@@ -65,8 +65,10 @@ void invalidate(System & s) {
 
 void do_update_iteration(System & s) {
   // body_system::update_iteration, bodies_system.h:152-229 (non-periodic)
-  if(s.par.periodic_boundary_x || s.par.periodic_boundary_y || s.par.periodic_boundary_z)
-    throw std::runtime_error("periodic boundaries (WALL ghosts, boundary.h) are not implemented on the device yet");
+  if(s.par.periodic_boundary_x || s.par.periodic_boundary_y || s.par.periodic_boundary_z) {
+    PhaseScope p(s, "boundary");
+    periodic_walls(s);
+  }
   if(s.comm) {
     // several ranks: range all-reduce, sample sort + all-to-all, halo of remote bodies and tree nodes (fsph_dist.cu)
     PhaseScope p(s, "decomposition");

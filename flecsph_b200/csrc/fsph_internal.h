@@ -244,6 +244,9 @@ void export_neighbors(System & s, std::vector<int64_t> & off, std::vector<int64_
 // ---- fsph_sweeps.cu -------------------------------------------------------------------------
 void sweep(System & s, int op);                 // default_physics.h:193-566
 
+// ---- fsph_boundary.cu -----------------------------------------------------------------------
+void periodic_walls(System & s);                // boundary.h:45-248 as used by bodies_system.h:160-169
+
 // ---- fsph_fmm.cu ----------------------------------------------------------------------------
 void gravitation_fmm(System & s);               // bodies_system.h:282 -> tree_topology.h:448-795 + fmm.h
 

@@ -175,6 +175,29 @@ def random_box(n, dim=3, seed=0, h_jitter=0.0, eta=1.2, vel_amp=0.1):
     return f, par
 
 
+def periodic_box(n, dim=3, seed=0, h_jitter=0.0, eta=1.2, vel_amp=0.1, box=(1.0, 1.0, 1.0), periodic=(1, 1, 1), stray=0.0):
+    """Random bodies in a box centred on the origin with periodic faces (the WALL-copy path, boundary.h:45-248);
+    `stray` > 0 puts a few bodies just outside the box so that the wrap-around (boundary.h:141-158) is exercised."""
+    rng = np.random.default_rng(seed)
+    ext = np.array(box[:dim])
+    pos = (rng.random((n, dim)) - 0.5) * ext
+    if stray > 0:
+        k = max(n // 50, 1)
+        pos[:k] += np.sign(pos[:k]) * (0.5 * ext - np.abs(pos[:k])) + np.sign(pos[:k]) * stray * rng.random((k, dim))
+    vol = float(np.prod(ext))
+    m = np.full(n, vol / n)
+    h0 = eta * 2.0 * (vol / n) ** (1.0 / dim)
+    h = h0 * (1.0 + h_jitter * (2.0 * rng.random(n) - 1.0))
+    vel = vel_amp * (2.0 * rng.random((n, dim)) - 1.0)
+    f = dict(pos=pos, vel=vel, mass=m, h=h, rho=np.ones(n), u=1.0 + 0.1 * rng.random(n), P=np.full(n, 0.4),
+             id=np.arange(n, dtype=np.int64), dt=np.full(n, 1e-3))
+    par = dict(sph_kernel="wendland c4", sph_eta=eta, poly_gamma=1.4, initial_dt=1e-3, sph_variable_h=1,
+               adaptive_timestep=1, timestep_cfl_factor=0.25, box_length=box[0], box_width=box[1], box_height=box[2],
+               periodic_boundary_x=periodic[0], periodic_boundary_y=periodic[1] if dim > 1 else 0,
+               periodic_boundary_z=periodic[2] if dim > 2 else 0)
+    return f, par
+
+
 def nx_for_particles(target, lo=8, hi=2000):
     """Smallest lattice_nx whose FCC unit sphere holds >= target particles (count ~ (4pi/3)/(s^3/sqrt2))."""
     est = lambda nx: (4.0 * math.pi / 3.0) / ((2.0 / (nx - 1)) ** 3 / math.sqrt(2.0))

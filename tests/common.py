@@ -43,6 +43,12 @@ def case(name, **kw):
         f, par = idata.random_box(kw.get("n", 2000), dim=dim, seed=kw.get("seed", 1), h_jitter=kw.get("h_jitter", 0.0))
         par = dict(par, **kw.get("par", {}))
         return f, par, dim
+    if name == "periodic":
+        dim = kw.get("dim", 3)
+        f, par = idata.periodic_box(kw.get("n", 3000), dim=dim, seed=kw.get("seed", 1), h_jitter=kw.get("h_jitter", 0.0),
+                                    box=kw.get("box", (1.0, 1.0, 1.0)), periodic=kw.get("periodic", (1, 1, 1)), stray=kw.get("stray", 0.0))
+        par = dict(par, **kw.get("par", {}))
+        return f, par, dim
     raise ValueError(name)
 
 
