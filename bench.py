@@ -248,10 +248,11 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(ts)
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {k: v / a.steps for k, v in phase_acc.items()})
+        config["phases_ms_per_rank"] = [{k: round(v, 2) for k, v in d.items() if not k.startswith("dd:")} for d in per_rank]
         for k in list(phase_acc):
-            tp = torch.tensor([phase_acc[k]], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-            phase_acc[k] = float(tp[0])
+            phase_acc[k] = max(d.get(k, 0.0) for d in per_rank) * a.steps
         config["ghosts_per_gpu_mean"] = float(ts[1]) / world
     t_dev, t_wall = float(tt[0]), float(tt[1])
     nn_mean = float(ts[0]) / n_total

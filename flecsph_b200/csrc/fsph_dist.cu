@@ -239,6 +239,20 @@ __global__ void __launch_bounds__(256) k_maps(const uint32_t * __restrict__ perm
   inv[o] = (uint32_t)i;
   if((int64_t)o >= n_owned) ghost_pos[o - n_owned] = (uint32_t)i;
 }
+// merged order [ghosts of lower ranks | owned | ghosts of higher ranks] from storage order [owned | ghosts by sender rank]
+__global__ void __launch_bounds__(256) k_merge_perm(uint32_t * __restrict__ perm, int64_t n, int64_t n_glow, int64_t n_owned) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  perm[i] = (uint32_t)(i < n_glow ? n_owned + i : (i < n_glow + n_owned ? i - n_glow : i));
+}
+__global__ void __launch_bounds__(256) k_ghost_pos(uint32_t * __restrict__ pos, int64_t ng, int64_t n_glow, int64_t n_owned) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(j < ng) pos[j] = (uint32_t)(j < n_glow ? j : n_owned + j);
+}
+__global__ void __launch_bounds__(256) k_shift_idx(uint32_t * __restrict__ idx, int64_t n, uint32_t by) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n) idx[i] += by;
+}
 __global__ void __launch_bounds__(256) k_remap(uint32_t * __restrict__ idx, int64_t n, const uint32_t * __restrict__ inv) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(i < n) idx[i] = inv[idx[i]];
@@ -824,13 +838,20 @@ static void dist_update_iteration_t(System & s) {
 
     ph.reset(new PhaseScope(s, "dd:merge_sort"));
     // 8. merge owned + ghosts, remember where every ghost went and where the bodies we serve to peers went
+    //    Ranks own increasing key ranges and every sender lists its bodies in key order, so the merged key order is
+    //    simply [ghosts of lower ranks | owned | ghosts of higher ranks]: a known permutation, no sort.
     s.n = n_total;
     s.has_ghosts = d.nghost > 0;
-    sort_bodies(s);
-    d.inv.reserve((size_t)n_total * 4);
+    int64_t n_glow = 0;
+    for(int q = 0; q < R; ++q) n_glow += (int64_t)d.recv_cnt[q];
     d.ghost_pos.reserve(std::max<size_t>(ng, 1) * 4);
-    FSPH_LAUNCH(k_maps, blocks(n_total), 256, s.stream, s.last_perm, n_total, s.n_owned, d.inv.as<uint32_t>(), d.ghost_pos.as<uint32_t>());
-    if(nsend) FSPH_LAUNCH(k_remap, blocks(nsend), 256, s.stream, d.send_idx.as<uint32_t>(), (int64_t)nsend, d.inv.as<uint32_t>());
+    if(ng) FSPH_LAUNCH(k_ghost_pos, blocks((int64_t)ng), 256, s.stream, d.ghost_pos.as<uint32_t>(), (int64_t)ng, n_glow, s.n_owned);
+    if(n_glow > 0) {
+      s.b_perm.reserve((size_t)n_total * 4);
+      FSPH_LAUNCH(k_merge_perm, blocks(n_total), 256, s.stream, s.b_perm.as<uint32_t>(), n_total, n_glow, s.n_owned);
+      gather_bodies(s, s.b_perm.as<uint32_t>(), n_total);
+      if(nsend) FSPH_LAUNCH(k_shift_idx, blocks(nsend), 256, s.stream, d.send_idx.as<uint32_t>(), (int64_t)nsend, (uint32_t)n_glow);
+    }
 
     ph.reset(new PhaseScope(s, "dd:tree_merged"));
     // 9. merged tree with the owners' leaf depths; global boxes for every node that holds remote bodies
