@@ -266,7 +266,14 @@ def main():
         cap = n if world == 1 else int(1.25 * n) + 4096   # the owned count of a rank drifts with the re-partitioning
         for col, nc in down:
             dt_ = torch.int64 if col == capi.COL_ID else torch.float64
-            bufs[col] = [torch.empty(cap, dtype=dt_).pin_memory() for _ in range(nc)]
+            bufs[col] = []
+            for _ in range(nc):
+                t = torch.empty(cap, dtype=dt_)
+                try:
+                    t = t.pin_memory()
+                except RuntimeError:      # the box refused to pin more host memory: staged copies, still host buffers
+                    config["e2e_host_buffers"] = "pageable (pinning failed)"
+                bufs[col].append(t)
 
         def download():
             if s.nbodies() > cap:

@@ -143,6 +143,17 @@ public:
     sys_ = fsph_create(&p, dev ? std::atoi(dev) : rank);
     if(!sys_)
       fsph_host::fail("fsph_create failed:", fsph_last_error(nullptr));
+    // Several MPI ranks (one per GPU): the ranks' systems join one NCCL communicator -- MPI only carries the 128-byte
+    // id, the particle traffic of update_iteration / reset_ghosts goes over NCCL inside the library (fsph_dist.cu).
+    int size = 1;
+    MPI_Comm_size(MPI_COMM_WORLD, &size);
+    if(size > 1) {
+      char id[128] = {0};
+      if(rank == 0 && fsph_comm_unique_id(id) != 0)
+        fsph_host::fail("fsph_comm_unique_id failed:", fsph_last_error(nullptr));
+      MPI_Bcast(id, 128, MPI_CHAR, 0, MPI_COMM_WORLD);
+      ck(fsph_comm_init_nccl(sys_, id, rank, size));
+    }
     tree_.bs = this;
   }
 
