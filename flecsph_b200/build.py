@@ -6,10 +6,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "flecsph_b200", "csrc")
-OUT = os.path.join(ROOT, "flecsph_b200", "libflecsph_b200.so")
+OUT = os.environ.get("FSPH_BUILD_OUT") or os.path.join(ROOT, "flecsph_b200", "libflecsph_b200.so")
+OBJ_SUFFIX = os.environ.get("FSPH_OBJ_SUFFIX", "")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+COMMON = os.environ.get("FSPH_NVCC_DEFS", "").split() + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 # translation units whose fp64 arithmetic must not be contracted into FMAs (bit-exact keys / tree / predicates)
 SOURCES = {
     "fsph_sort.cu": [],
@@ -37,7 +38,7 @@ def build_cuda(verbose=False, force=False):
     objs, jobs = [], []
     for src, extra in SOURCES.items():
         s = os.path.join(CSRC, src)
-        o = os.path.join(CSRC, src.replace(".cu", ".o"))
+        o = os.path.join(CSRC, src.replace(".cu", OBJ_SUFFIX + ".o"))
         objs.append(o)
         if force or _newer([s] + hdrs, o):
             cmd = [NVCC] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]

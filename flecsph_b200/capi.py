@@ -75,7 +75,8 @@ PRODUCT_ONLY = {"fsph_set_time_state", "fsph_get_time_state", "fsph_tree_root", 
                 "fsph_comm_init_nccl", "fsph_local_group_create", "fsph_local_group_destroy", "fsph_comm_init_local",
                 "fsph_comm_rank", "fsph_comm_size", "fsph_nghosts", "fsph_dd_choose_splitters", "fsph_dd_align_splitter"}
 
-PRODUCT_LIB = os.path.join(ROOT, "flecsph_b200", "libflecsph_b200.so")
+# FSPH_PRODUCT_LIB: another build of the same library (kernel-variant A/B runs of scripts/ab_bench.sh)
+PRODUCT_LIB = os.environ.get("FSPH_PRODUCT_LIB") or os.path.join(ROOT, "flecsph_b200", "libflecsph_b200.so")
 
 
 def library_path(which, dim=3):

@@ -23,7 +23,8 @@ Cols System::cols() const {
   c.key = col_key.as<uint64_t>();
   c.type = col_type.as<int32_t>();
   c.nneigh = col_nneigh.as<int32_t>();
-  c.ghosts = has_ghosts ? 1 : 0;
+  c.own_lo = has_ghosts ? own_begin : 0;
+  c.own_hi = has_ghosts ? own_begin + n_owned : n;
   return c;
 }
 
@@ -153,16 +154,17 @@ __device__ __forceinline__ void apply_one(const Cols & c, const int64_t i, const
 // Several element-wise functors of the driver loop in one pass over HBM (same per-particle order of operations).
 template<int D>
 __global__ void __launch_bounds__(256) k_apply(Cols c, int64_t n, OpList ops, PhysParams pp, uint32_t * __restrict__ status) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(i >= n) return;
-  if(c.ghosts && (c.type[i] & TYPE_GHOST)) return;  // remote copies are refreshed from their owner (reset_ghosts)
+  // n = number of owned bodies, starting at c.own_lo (remote copies are refreshed from their owner: reset_ghosts)
+  const int64_t i = c.own_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= c.own_lo + n) return;
   for(int k = 0; k < ops.n; ++k) apply_one<D>(c, i, ops.op[k], pp, status);
 }
 
 void apply_fused(System & s, const int * op_list, int nops) {
   if(s.n <= 0 || nops <= 0) return;
   if(nops > 8) throw std::runtime_error("apply_fused: too many ops");
-  unsigned nb = (unsigned)((s.n + 255) / 256);
+  const int64_t n_own = s.n_owned_or_n();
+  unsigned nb = (unsigned)((n_own + 255) / 256);
   uint32_t * st = s.b_status.as<uint32_t>();
   // Measured on B200 (64 M particles): one kernel looping over a run-time op list is slower than one launch per
   // functor (the dependent load -> compute -> store chains of consecutive ops serialise on HBM latency), so the
@@ -172,9 +174,9 @@ void apply_fused(System & s, const int * op_list, int nops) {
     ops.n = 1;
     for(int j = 0; j < 8; ++j) ops.op[j] = -1;
     ops.op[0] = op_list[k];
-    if(s.dim == 1) FSPH_LAUNCH((k_apply<1>), nb, 256, s.stream, s.cols(), s.n, ops, s.phys(), st);
-    else if(s.dim == 2) FSPH_LAUNCH((k_apply<2>), nb, 256, s.stream, s.cols(), s.n, ops, s.phys(), st);
-    else FSPH_LAUNCH((k_apply<3>), nb, 256, s.stream, s.cols(), s.n, ops, s.phys(), st);
+    if(s.dim == 1) FSPH_LAUNCH((k_apply<1>), nb, 256, s.stream, s.cols(), n_own, ops, s.phys(), st);
+    else if(s.dim == 2) FSPH_LAUNCH((k_apply<2>), nb, 256, s.stream, s.cols(), n_own, ops, s.phys(), st);
+    else FSPH_LAUNCH((k_apply<3>), nb, 256, s.stream, s.cols(), n_own, ops, s.phys(), st);
   }
   FSPH_CUDA_OK(cudaGetLastError());
   for(int k = 0; k < nops; ++k)
@@ -200,8 +202,7 @@ __global__ void __launch_bounds__(256) k_reduce(Cols c, int64_t n, int kind, int
   if(kind == RED_MIN_DT) v[0] = 1e24;
   if(kind == RED_MAX_H) v[0] = -DBL_MAX;
   if(kind >= RED_H_STATS) { v[0] = DBL_MAX; v[1] = kind == RED_N_STATS ? 0.0 : DBL_MIN; }
-  for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    if(c.ghosts && (c.type[i] & TYPE_GHOST)) continue;
+  for(int64_t i = c.own_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < c.own_hi; i += (int64_t)gridDim.x * blockDim.x) {
     switch(kind) {
       case RED_MIN_DT: v[0] = fmin(v[0], c.f[F_DT][i]); break;
       case RED_MAX_H: v[0] = fmax(v[0], c.f[F_H][i]); break;

@@ -844,6 +844,7 @@ static void dist_update_iteration_t(System & s) {
     s.has_ghosts = d.nghost > 0;
     int64_t n_glow = 0;
     for(int q = 0; q < R; ++q) n_glow += (int64_t)d.recv_cnt[q];
+    s.own_begin = n_glow;
     d.ghost_pos.reserve(std::max<size_t>(ng, 1) * 4);
     if(ng) FSPH_LAUNCH(k_ghost_pos, blocks((int64_t)ng), 256, s.stream, d.ghost_pos.as<uint32_t>(), (int64_t)ng, n_glow, s.n_owned);
     if(n_glow > 0) {

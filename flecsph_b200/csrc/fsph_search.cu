@@ -95,8 +95,12 @@ __device__ __forceinline__ WorkCell load_work_cell(const Tree & t, const Search 
 // MODE 2: single pass: persistent CTAs, candidates go to a per-CTA scratch strip during the walk, then the
 //         CTA reserves its exact share of the candidate / mask arrays with one atomicAdd each (capacity is
 //         estimated from the previous step; on overflow the host falls back to MODE 0 + 1)
+// resident-thread target per SM for the register allocator (threads = FSPH_SR_THREADS_PER_SM / CTA size CTAs)
+#ifndef FSPH_SR_THREADS_PER_SM
+#define FSPH_SR_THREADS_PER_SM 448
+#endif
 template<int D, int NW, int MODE>
-__global__ void __launch_bounds__(32 * NW) k_search(Tree t, Cols c, Search sr, int g_begin, int g_end, int32_t * __restrict__ scratch,
+__global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k_search(Tree t, Cols c, Search sr, int g_begin, int g_end, int32_t * __restrict__ scratch,
   int scratch_cap, unsigned long long * __restrict__ cursors, unsigned long long cand_cap, unsigned long long mask_cap,
   uint32_t * __restrict__ status) {
   constexpr int NT = 32 * NW;

@@ -18,7 +18,10 @@
 
 namespace fsph {
 
-constexpr int SW_TILE = 256;
+#ifndef FSPH_SW_TILE
+#define FSPH_SW_TILE 256
+#endif
+constexpr int SW_TILE = FSPH_SW_TILE;
 constexpr int SW_LCAP = 32;   // neighbour-list entries decoded per round and thread
 constexpr double TINY = 1e10 * DBL_MIN;  // kernels.h:64, viscosity.h:36
 constexpr double PI = 3.14159265358979323846;

@@ -31,8 +31,7 @@ __global__ void __launch_bounds__(256) k_range_partial(Cols c, int64_t n, double
   double mn[D], mx[D];
 #pragma unroll
   for(int d = 0; d < D; ++d) { mn[d] = DBL_MAX; mx[d] = -DBL_MAX; }
-  for(int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    if(c.ghosts && (c.type[i] & TYPE_GHOST)) continue;
+  for(int64_t i = c.own_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < c.own_hi; i += (int64_t)gridDim.x * blockDim.x) {
     double h = c.f[F_H][i];
 #pragma unroll
     for(int d = 0; d < D; ++d) {
@@ -111,7 +110,7 @@ __global__ void __launch_bounds__(256) k_keys(Cols c, int64_t n, Range3 r) {
   constexpr int B = KeyBits<D>::B;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= n) return;
-  if(c.ghosts && (c.type[i] & TYPE_GHOST)) {
+  if(i < c.own_lo || i >= c.own_hi) {
     c.key[i] = ~0ull;  // last in key order: the next sort drops the remote copies of the previous iteration
     return;
   }
