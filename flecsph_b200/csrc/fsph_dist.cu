@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(256) k_fix_straddling(Tree t, const uint64_t *
   uint64_t a, b;
   node_key_range<D>(node_key<D>(t, key, nd), a, b);
   const bool owned = a >= klo && b <= khi_incl, remote = b < klo || a > khi_incl;
-  if(!owned && !remote && t.sub[nd] <= SUB_ENTITIES) t.sub[nd] = SUB_ENTITIES + 1;
+  if(!owned && !remote) t.sub[nd] = 1 << 30;  // neither a work cell nor a super cell of the two-level walk
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------

@@ -25,6 +25,10 @@ enum F64 {
 };
 
 constexpr int SUB_ENTITIES = 128;  // tree_topology.h:2121
+#ifndef FSPH_SUPER_ENTITIES
+#define FSPH_SUPER_ENTITIES 1024
+#endif
+constexpr int SUPER_ENTITIES = FSPH_SUPER_ENTITIES;  // bodies per super cell of the two-level neighbour walk
 constexpr int MAX_LEVELS = 66;
 
 // error bits latched on the device (surfaced at the next call boundary)
@@ -104,6 +108,13 @@ struct Search {
   // work cells are grouped by size class (ceil(P/32) = 1..4 warps) so that every warp of a CTA owns live
   // particles; within a class they stay in Morton order.  class c occupies [class_off[c], class_off[c+1]).
   int32_t class_off[5];
+  // two-level walk (fsph_search.cu): super cells = maximal sub-trees of <= SUPER_ENTITIES bodies; each owns the list
+  // of tree nodes with leaf children that any of its work cells can accept (superset by a conservative box test)
+  int32_t * wc_super;    // [nwc] super cell of each work cell
+  int32_t * super_cell;  // [nsuper] index into Tree::cell
+  uint64_t * sl_off;     // [nsuper+1] offsets into sl_nodes
+  int32_t * sl_nodes;    // node indices
+  int32_t nsuper;
 };
 
 struct PhysParams {
@@ -154,6 +165,7 @@ struct System {
   DevBuf b_cell, b_cell_parent, b_cell_desc, b_cell_desc2, b_child_begin, b_child_end, b_node_start, b_node_depth, b_sub;
   DevBuf b_noderec, b_leafrec;
   DevBuf b_nmass, b_ncom[3], b_nradius, b_nlap, b_nbmin[3], b_nbmax[3];
+  DevBuf b_wc_super, b_super_cell, b_sl_off, b_sl_nodes;
   DevBuf b_wc_cell, b_cand_off, b_mask_off, b_cand, b_mask, b_cnt0, b_cnt1;
   DevBuf b_status, b_red, b_levels, b_ncand, b_search_scratch;
   unsigned long long est_cand = 0, est_mask = 0;  // sizes of the previous neighbour structure (capacity estimate)
@@ -240,6 +252,9 @@ struct TreeEdges {
 void build_tree_edges(System & s, const TreeEdges & e);
 void finish_tree(System & s);                   // walk records + work cells (after node-table overrides)
 void find_work_cells(System & s);               // tree_topology.h:221-235
+// cells that are maximal sub-trees of <= `limit` bodies (or lone leaves under bigger nodes), marked at their first body:
+// at[first body] = cell index + 1.  skip_ghosts: cells whose first body is a remote copy are left out.
+void mark_maximal_cells(System & s, int limit, bool skip_ghosts, uint32_t * at);
 
 // ---- fsph_search.cu -------------------------------------------------------------------------
 void neighbor_search(System & s);               // tree_topology.h:212-442

@@ -20,7 +20,18 @@
 
 namespace fsph {
 
+// 1: work cells scan a flat node list collected once per super cell (k_super_walk) instead of walking from the root.
+// Measured on B200 (64 M Sedov): the walk part of the search is 58 + 11 ms against 53 ms for the per-cell walk (four
+// times as many node tests outweigh the saved levels), so the default stays 0; kept because results are identical.
+#ifndef FSPH_SEARCH_TWO_LEVEL
+#define FSPH_SEARCH_TWO_LEVEL 0
+#endif
 constexpr int SR_NT = 64;       // threads per CTA of the export kernel
+#ifndef FSPH_SR_SPREAD
+#define FSPH_SR_SPREAD 64
+#endif
+constexpr uint32_t SR_SPREAD = FSPH_SR_SPREAD;
+constexpr int SW_QCAP = 4096;   // node frontier capacity per level of the super-cell walk
 constexpr int SR_QCAP = 768;    // node frontier capacity per level
 constexpr int SR_TILE = 256;    // candidates per shared-memory tile
 constexpr double GEO_TOL = 2.220446049250313e-16 * 10.;  // tree_geometry.h:57
@@ -138,7 +149,9 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
       grad = t.radius[gnode];
     }
     int32_t * cout = MODE == 1 ? sr.cand + sr.cand_off[g] : (MODE == 2 ? scratch + (size_t)blockIdx.x * scratch_cap : nullptr);
+#if !FSPH_SEARCH_TWO_LEVEL
     if(tid == 0) queue[0][0] = 0;  // the root node
+#endif
     // Tight box of G's positions and max h: an extra, conservative candidate cull (it only drops leaves that
     // cannot satisfy the pair predicate for any particle of G, so the neighbour sets are unchanged).
     double tmn[D], tmx[D], ghmax = 0.0;
@@ -210,6 +223,127 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
     }
     // hmax^2 with a safety margin for the quick node reject (distance between a node box and G's tight box)
     const double ghmax2 = ghmax * ghmax * (1.0 + 1e-9);
+#if FSPH_SEARCH_TWO_LEVEL
+    uint32_t ncands = 0;
+    bool overflow = false;
+    // two-level walk: the nodes that can hold candidates of G were collected once for G's super cell (k_super_walk);
+    // a node's ancestors need no test of their own (boxes are nested and both predicates are monotone in the box),
+    // so scanning that flat list with the exact tests gives exactly the leaves the reference's top-down walk reaches
+    const int sidx = sr.wc_super[g];
+    const uint64_t sl_lo = sr.sl_off[sidx];
+    const int sl_n = (int)(sr.sl_off[sidx + 1] - sl_lo);
+    for(int lbase = 0; lbase < sl_n; lbase += SR_QCAP) {
+      const int ncur = min(SR_QCAP, sl_n - lbase);
+      // ---- phase A: test every frontier node (results to shared memory), count children / candidates -------
+      uint32_t my_cands = 0;
+      for(int j = tid; j < ncur; j += NT) {
+        const int nd = sr.sl_nodes[sl_lo + lbase + j];
+        const NodeRec rec = t.noderec[nd];
+        uint32_t cand_mask = 0;
+        queue[0][j] = rec.child_begin;
+        bool ok = true;
+        if(gnode >= 0) {
+          // intersects_box_box(c, G)
+          bool sep = false;
+#pragma unroll
+          for(int d = 0; d < D; ++d) sep = sep || (rec.bmax[d] < gmn[d]) || (gmx[d] < rec.bmin[d]);
+          ok = !sep;
+        }
+        if(ok) {
+          // quick reject (conservative, exact outcome): the node box is farther than hmax from every position of G
+          double dd = 0.0;
+#pragma unroll
+          for(int d = 0; d < D; ++d) {
+            const double tt = fmax(0.0, fmax(rec.bmin[d] - tmx[d], tmn[d] - rec.bmax[d]));
+            dd = dd + tt * tt;
+          }
+          ok = dd <= ghmax2;
+        }
+        if(ok) {
+          int q = 0;
+#pragma unroll
+          for(int d = 0; d < D; ++d) q |= (int)((rec.bmin[d] + rec.bmax[d]) > (tmn[d] + tmx[d])) << d;
+          const int kr = rep_sm[q];
+          double p[D];
+#pragma unroll
+          for(int d = 0; d < D; ++d) p[d] = gx[d][kr];
+          bool acc = sphere_box<D>(rec.bmin, rec.bmax, p, gh[kr]);
+          for(int k = 0; k < P && !acc; ++k) {
+#pragma unroll
+            for(int d = 0; d < D; ++d) p[d] = gx[d][k];
+            acc = sphere_box<D>(rec.bmin, rec.bmax, p, gh[k]);
+          }
+          ok = acc;
+        }
+        if(ok) {
+          const int cb = rec.child_begin;
+          const uint32_t leafmask = rec.leafmask;
+          // leaf children in two batches of four: all loads of a batch are issued before the first use
+#pragma unroll
+          for(int half = 0; half < ((1 << D) + 3) / 4; ++half) {
+            const uint32_t lm4 = (leafmask >> (4 * half)) & 0xfu;
+            if(lm4 == 0) continue;
+            LeafRec lr[4];
+#pragma unroll
+            for(int jj = 0; jj < 4; ++jj)
+              if((lm4 >> jj) & 1u) lr[jj] = t.leafrec[cb + 4 * half + jj];
+#pragma unroll
+            for(int jj = 0; jj < 4; ++jj) {
+              if(!((lm4 >> jj) & 1u)) continue;
+              bool pass = true;
+              if(gnode >= 0) {
+                // |x_e - X_G|^2 <= (max(h_e, lap_G) + radius_G)^2, tree_topology.h:365-370
+                const double ext = fmax(lr[jj].h, glap) + grad;
+                double s2 = 0.0;
+#pragma unroll
+                for(int d = 0; d < D; ++d) {
+                  const double df = lr[jj].x[d] - gcom[d];
+                  s2 = d == 0 ? df * df : s2 + df * df;
+                }
+                pass = s2 <= ext * ext;
+              }
+              if(pass) {
+                const double hm = fmax(lr[jj].h, ghmax);
+                double dd = 0.0;
+#pragma unroll
+                for(int d = 0; d < D; ++d) {
+                  const double tt = fmax(0.0, fmax(tmn[d] - lr[jj].x[d], lr[jj].x[d] - tmx[d]));
+                  dd = dd + tt * tt;
+                }
+                pass = dd <= hm * hm * (1.0 + 1e-9);
+              }
+              if(pass) cand_mask |= 1u << (4 * half + jj);
+            }
+          }
+        }
+        qres[j] = cand_mask;
+        my_cands += __popc(cand_mask);
+      }
+      // ---- one block scan per level: output order = (thread, frontier slot, child), fixed => deterministic --
+      uint32_t total;
+      const uint32_t ex = block_scan_u32<NT>(my_cands, total, scan_sm);
+      uint32_t cpos = ncands + ex;
+      // ---- phase B: write the next frontier and the candidates -----------------------------------------
+      for(int j = tid; j < ncur; j += NT) {
+        const uint32_t cand_mask = qres[j];
+        if(FILL && cand_mask) {
+          const int child_begin = queue[0][j];
+          int cv[1 << D];
+#pragma unroll
+          for(int b = 0; b < (1 << D); ++b)
+            if((cand_mask >> b) & 1u) cv[b] = t.cell[child_begin + b];
+#pragma unroll
+          for(int b = 0; b < (1 << D); ++b) {
+            if(!((cand_mask >> b) & 1u)) continue;
+            if(MODE == 1 || cpos < (uint32_t)scratch_cap) cout[cpos] = cv[b];
+            ++cpos;
+          }
+        }
+      }
+      ncands += total;
+      __syncthreads();
+    }
+#else
     int ncur = 1, cur = 0;
     uint32_t ncands = 0;
     bool overflow = false;
@@ -342,6 +476,7 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
       ncur = (int)nnext;
       cur ^= 1;
     }
+#endif
     const int Ppad = (P + 31) & ~31;
     const uint64_t nwords = (uint64_t)((ncands + 31) / 32) * Ppad;
     if(MODE == 0) {
@@ -372,7 +507,18 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
         sr.cand_off[g] = co;
         sr.mask_off[g] = mo;
       }
-      for(uint32_t i = tid; i < ncands; i += NT) sr.cand[co + i] = cout[i];
+      // The candidates leave the walk in runs of key-neighbours.  They are stored interleaved (walk position i goes
+      // to row i % SR_SPREAD of a SR_SPREAD-row transpose): every tile of the sweeps then holds an even sample of the
+      // whole neighbourhood, so all particles of the cell find about the same number of neighbours in it and the
+      // lanes of the pair loops stay busy together (measured: -12 % on the pair sweeps).
+      {
+        const uint32_t q0 = ncands / SR_SPREAD, rem = ncands % SR_SPREAD;
+        for(uint32_t i = tid; i < ncands; i += NT) {
+          const uint32_t r = i % SR_SPREAD, k = i / SR_SPREAD;
+          sr.cand[co + r * q0 + min(r, rem) + k] = cout[i];
+        }
+      }
+      __syncthreads();
     }
     else {
       co = sr.cand_off[g];
@@ -386,11 +532,14 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
     for(int d = 0; d < D; ++d) a0[d] = active ? gx[d][tid] : 0.0;
     if(active) { h0 = gh[tid]; h0 = h0 * h0; }
     int cnt0 = 0;
+#ifdef FSPH_SR_NOPAIR
+    if(C > 0) continue;  // timing experiment: walk only
+#endif
     for(int tb = 0; tb < C; tb += SR_TILE) {
       const int tc = min(SR_TILE, C - tb);
       __syncthreads();
       for(int i = tid; i < tc; i += NT) {
-        const int p = MODE == 2 ? cout[tb + i] : sr.cand[co + tb + i];
+        const int p = sr.cand[co + tb + i];
 #pragma unroll
         for(int d = 0; d < D; ++d) cx[d][i] = c.f[F_POS + d][p];
         const double hh = c.f[F_H][p];
@@ -421,6 +570,181 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
     }
     if(active) c.nneigh[wc.start + tid] = cnt0;
   }
+}
+
+
+// ---- level 1 of the two-level walk: one node list per super cell -------------------------------------------
+// A super cell S (maximal sub-tree of <= SUPER_ENTITIES bodies) walks the tree once with a test that every node any
+// work cell G inside S can accept must pass: G accepts C only if some body sphere of G touches C's box
+// (intersects_sphere_box, tree_topology.h:348), hence the distance between C's box and the tight box of S's positions
+// is at most the largest h in S.  The nodes that pass and have leaf children are S's list (in walk order: fixed).
+// MODE 0 counts, MODE 1 fills (offsets from a prefix sum).
+template<int D, int MODE>
+__global__ void __launch_bounds__(64) k_super_walk(Tree t, Cols c, Search sr, uint32_t * __restrict__ status) {
+  constexpr int NT = 64;
+  __shared__ int32_t queue[2][SW_QCAP];
+  __shared__ uint8_t qres[SW_QCAP];
+  __shared__ uint32_t scan_sm[NT / 32];
+  __shared__ double red_sm[NT / 32][2 * D + 1];
+  const int tid = threadIdx.x, sidx = blockIdx.x;
+  int start, P;
+  {
+    const int v = t.cell[sr.super_cell[sidx]];
+    if(v >= 0) { start = v; P = 1; }
+    else { start = t.node_start[~v]; P = t.sub[~v]; }
+  }
+  double tmn[D], tmx[D], hmax = 0.0;
+#pragma unroll
+  for(int d = 0; d < D; ++d) { tmn[d] = 1.79769313486231570e308; tmx[d] = -1.79769313486231570e308; }
+  for(int k = tid; k < P; k += NT) {
+#pragma unroll
+    for(int d = 0; d < D; ++d) {
+      const double x = c.f[F_POS + d][start + k];
+      tmn[d] = fmin(tmn[d], x);
+      tmx[d] = fmax(tmx[d], x);
+    }
+    hmax = fmax(hmax, c.f[F_H][start + k]);
+  }
+#pragma unroll
+  for(int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for(int d = 0; d < D; ++d) {
+      tmn[d] = fmin(tmn[d], __shfl_xor_sync(0xffffffffu, tmn[d], o));
+      tmx[d] = fmax(tmx[d], __shfl_xor_sync(0xffffffffu, tmx[d], o));
+    }
+    hmax = fmax(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
+  }
+  if((tid & 31) == 0) {
+#pragma unroll
+    for(int d = 0; d < D; ++d) { red_sm[tid >> 5][d] = tmn[d]; red_sm[tid >> 5][D + d] = tmx[d]; }
+    red_sm[tid >> 5][2 * D] = hmax;
+  }
+  if(tid == 0) queue[0][0] = 0;  // the root node
+  __syncthreads();
+#pragma unroll
+  for(int ww = 0; ww < NT / 32; ++ww) {
+#pragma unroll
+    for(int d = 0; d < D; ++d) {
+      tmn[d] = fmin(tmn[d], red_sm[ww][d]);
+      tmx[d] = fmax(tmx[d], red_sm[ww][D + d]);
+    }
+    hmax = fmax(hmax, red_sm[ww][2 * D]);
+  }
+  const double hmax2 = hmax * hmax * (1.0 + 1e-9);
+  int32_t * out = MODE == 1 ? sr.sl_nodes + sr.sl_off[sidx] : nullptr;
+  int ncur = 1, cur = 0;
+  uint32_t nlist = 0;
+  while(ncur > 0) {
+    uint32_t my_nodes = 0, my_list = 0;
+    for(int j = tid; j < ncur; j += NT) {
+      const NodeRec rec = t.noderec[queue[cur][j]];
+      double dd = 0.0;
+#pragma unroll
+      for(int d = 0; d < D; ++d) {
+        const double tt = fmax(0.0, fmax(rec.bmin[d] - tmx[d], tmn[d] - rec.bmax[d]));
+        dd = dd + tt * tt;
+      }
+      uint32_t r = 0;
+      if(dd <= hmax2) {
+        const uint32_t node_mask = ((1u << rec.nchild) - 1u) & ~rec.leafmask;
+        r = (uint32_t)__popc(node_mask) | (rec.leafmask ? 0x80u : 0u);
+      }
+      qres[j] = (uint8_t)r;
+      my_nodes += r & 0x7fu;
+      my_list += r >> 7;
+    }
+    uint32_t total;
+    const uint32_t ex = block_scan_u32<NT>(my_nodes | (my_list << 16), total, scan_sm);
+    uint32_t qpos = ex & 0xffffu, lpos = nlist + (ex >> 16);
+    const uint32_t nnext_raw = total & 0xffffu;
+    for(int j = tid; j < ncur; j += NT) {
+      const uint32_t r = qres[j];
+      if(r == 0) continue;
+      const int nd = queue[cur][j];
+      if(r & 0x7fu) {
+        const NodeRec rec = t.noderec[nd];
+        uint32_t node_mask = ((1u << rec.nchild) - 1u) & ~rec.leafmask;
+        while(node_mask) {
+          const int b = __ffs(node_mask) - 1;
+          node_mask &= node_mask - 1;
+          if(qpos < SW_QCAP) queue[cur ^ 1][qpos] = rec.first_child_node + __popc(~rec.leafmask & ((1u << b) - 1u));
+          ++qpos;
+        }
+      }
+      if(r & 0x80u) {
+        if(MODE == 1) out[lpos] = nd;
+        ++lpos;
+      }
+    }
+    nlist += total >> 16;
+    uint32_t nnext = nnext_raw;
+    if(nnext > SW_QCAP) {
+      if(tid == 0) atomicOr(status, (uint32_t)ERR_QUEUE_OVERFLOW);
+      nnext = SW_QCAP;
+    }
+    __syncthreads();
+    ncur = (int)nnext;
+    cur ^= 1;
+  }
+  if(MODE == 0 && tid == 0) sr.sl_off[sidx] = nlist;
+}
+
+__global__ void __launch_bounds__(256) k_super_compact(const uint32_t * __restrict__ at, const uint32_t * __restrict__ ex, int64_t n,
+  int32_t * __restrict__ super_cell) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n && at[i]) super_cell[ex[i]] = (int32_t)(at[i] - 1u);
+}
+__global__ void __launch_bounds__(256) k_flag_set(const uint32_t * __restrict__ in, uint32_t * __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n) out[i] = in[i] != 0;
+}
+// super cell of a work cell = the one whose body range holds the work cell's first body
+__global__ void __launch_bounds__(256) k_wc_super(Tree t, Search sr, const uint32_t * __restrict__ at, const uint32_t * __restrict__ ex) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if(g >= sr.nwc) return;
+  const int v = t.cell[sr.wc_cell[g]];
+  const int start = v >= 0 ? v : t.node_start[~v];
+  sr.wc_super[g] = (int32_t)(ex[start] + (at[start] ? 1u : 0u)) - 1;
+}
+
+template<int D>
+static void build_super_lists(System & s) {
+  Search & sr = s.search;
+  const int64_t n = s.n;
+  uint32_t * status = s.b_status.as<uint32_t>();
+  s.b_cnt0.reserve((size_t)(n + 1) * 4);
+  s.b_tmp[0].reserve((size_t)(n + 1) * 4);
+  uint32_t * at = s.b_cnt0.as<uint32_t>();
+  uint32_t * ex = s.b_tmp[0].as<uint32_t>();
+  mark_maximal_cells(s, SUPER_ENTITIES, false, at);
+  unsigned nbp = (unsigned)((n + 255) / 256);
+  FSPH_LAUNCH(k_flag_set, nbp, 256, s.stream, at, ex, n);
+  exclusive_scan_u32(s, ex, ex, n, nullptr);
+  uint32_t nsuper = 0;
+  FSPH_CUDA_OK(cudaMemcpyAsync(&nsuper, ex + n, 4, cudaMemcpyDeviceToHost, s.stream));
+  FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
+  if(nsuper == 0) throw std::runtime_error("no super cells");
+  s.b_super_cell.reserve((size_t)nsuper * 4);
+  s.b_sl_off.reserve((size_t)(nsuper + 1) * 8);
+  s.b_wc_super.reserve((size_t)std::max(sr.nwc, 1) * 4);
+  sr.super_cell = s.b_super_cell.as<int32_t>();
+  sr.sl_off = s.b_sl_off.as<uint64_t>();
+  sr.wc_super = s.b_wc_super.as<int32_t>();
+  sr.nsuper = (int)nsuper;
+  FSPH_LAUNCH(k_super_compact, nbp, 256, s.stream, at, ex, n, sr.super_cell);
+  FSPH_LAUNCH(k_wc_super, (unsigned)((sr.nwc + 255) / 256), 256, s.stream, s.tree, sr, at, ex);
+  FSPH_LAUNCH((k_super_walk<D, 0>), nsuper, 64, s.stream, s.tree, s.cols(), sr, status);
+  exclusive_scan_u64(s, sr.sl_off, sr.sl_off, nsuper, nullptr);
+  uint64_t tot = 0;
+  uint32_t st = 0;
+  FSPH_CUDA_OK(cudaMemcpyAsync(&tot, sr.sl_off + nsuper, 8, cudaMemcpyDeviceToHost, s.stream));
+  FSPH_CUDA_OK(cudaMemcpyAsync(&st, status, 4, cudaMemcpyDeviceToHost, s.stream));
+  FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
+  if(st & ERR_QUEUE_OVERFLOW) throw std::runtime_error("neighbour search: node frontier of a super cell exceeds the shared-memory queue");
+  s.b_sl_nodes.reserve((size_t)std::max<uint64_t>(tot, 1) * 4);
+  sr.sl_nodes = s.b_sl_nodes.as<int32_t>();
+  FSPH_LAUNCH((k_super_walk<D, 1>), nsuper, 64, s.stream, s.tree, s.cols(), sr, status);
+  FSPH_CUDA_OK(cudaGetLastError());
 }
 
 template<int D, int MODE>
@@ -455,6 +779,12 @@ static void neighbor_search_t(System & s) {
   sr.mask_off = s.b_mask_off.as<uint64_t>();
   sr.ncand = s.b_ncand.as<int32_t>();
   unsigned long long * cursors = reinterpret_cast<unsigned long long *>(s.b_status.as<uint32_t>() + 8);
+#if FSPH_SEARCH_TWO_LEVEL
+  {
+    PhaseScope ph(s, "search:super_lists");
+    build_super_lists<D>(s);
+  }
+#endif
   // single pass when the previous search on this system gives a capacity estimate
   // (with ghosts the body count drifts a little from step to step: the estimate is scaled by the ratio)
   const bool est_ok = s.est_cand > 0 && s.est_n > 0 && (s.est_n == s.n || (s.comm && std::llabs(s.est_n - s.n) < s.est_n / 4));

@@ -18,10 +18,21 @@
 
 namespace fsph {
 
-#ifndef FSPH_SW_TILE
-#define FSPH_SW_TILE 256
+// candidates staged per shared-memory tile: a smaller tile lets more CTAs share an SM (the tile is most of a CTA's
+// shared memory) at the price of more tile rounds; measured on B200 (64 M Sedov): density 256, the wide pair sweeps 128
+#ifndef FSPH_SW_TILE_DENS
+#define FSPH_SW_TILE_DENS 256
 #endif
-constexpr int SW_TILE = FSPH_SW_TILE;
+#ifndef FSPH_SW_TILE_PAIR
+#define FSPH_SW_TILE_PAIR 128
+#endif
+// particles per thread of the pair sweeps.  2 (k_sweep2: key neighbours share a thread and read common neighbours
+// once) halves the shared-memory wavefronts per pair but was 1.5x SLOWER on B200 (64 M Sedov: acceleration 103 vs 64 ms):
+// half as many warps per SM leave the fp64 dependency chains exposed.  Kept for the record; the default is 1.
+#ifndef FSPH_SWEEP_PPT
+#define FSPH_SWEEP_PPT 1
+#endif
+template<int OP> struct SwTile { static constexpr int N = (OP == 0 /* OP_DENSITY */ || OP == 5 /* OP_VSIG */) ? FSPH_SW_TILE_DENS : FSPH_SW_TILE_PAIR; };
 constexpr int SW_LCAP = 32;   // neighbour-list entries decoded per round and thread
 constexpr double TINY = 1e10 * DBL_MIN;  // kernels.h:64, viscosity.h:36
 constexpr double PI = 3.14159265358979323846;
@@ -253,7 +264,7 @@ template<int D> struct Own {
 // one neighbour pair (a, candidate ci of the current tile); `valid` = false makes it a no-op (padding slot of
 // the two-pairs-per-iteration loop)
 template<int D, int K, int OP>
-__device__ __forceinline__ void pair_body(Own<D> & o, const double (*tile)[SW_TILE], const int32_t * tidx, const PhysParams & pp,
+__device__ __forceinline__ void pair_body(Own<D> & o, const double (*tile)[SwTile<OP>::N], const int32_t * tidx, const PhysParams & pp,
   const int ci, const bool valid) {
   double rab[D];
 #pragma unroll
@@ -346,37 +357,15 @@ __device__ __forceinline__ void pair_body(Own<D> & o, const double (*tile)[SW_TI
   }
 }
 
-template<int D, int K, int OP, int NW>
-__global__ void __launch_bounds__(32 * NW) k_sweep(Tree t, Cols c, Search sr, PhysParams pp, int g_begin, uint32_t * __restrict__ status) {
-  using TC = TileCols<D, OP>;
-  constexpr int NF = TC::NF;
-  constexpr int NT = 32 * NW;
-  constexpr bool NEED_IDX = OP == OP_VSIG || OP == OP_ACCV;
-  __shared__ double tile[NF][SW_TILE];
-  __shared__ int32_t tidx[NEED_IDX ? SW_TILE : 1];
-  __shared__ uint32_t mtile[SW_TILE / 32][NT];   // this tile's mask words, [word][particle]
-  __shared__ uint8_t nlist[SW_LCAP][NT];         // decoded neighbour lists of one round, [entry][particle]
-
-  const int g = g_begin + blockIdx.x, tid = threadIdx.x;
-  int start, P;
-  {
-    int v = t.cell[sr.wc_cell[g]];
-    if(v >= 0) { start = v; P = 1; }
-    else { start = t.node_start[~v]; P = t.sub[~v]; }
-  }
-  const int Ppad = (P + 31) & ~31;
-  const uint64_t co = sr.cand_off[g], mo = sr.mask_off[g];
-  const int C = sr.ncand[g];
-  const bool active = tid < P;
-
-  Own<D> o;
-  o.ia = start + tid;
+// state of the particle `ia` of a sweep (the columns op OP needs), accumulators cleared
+template<int D, int OP>
+__device__ __forceinline__ void load_own(Own<D> & o, const Cols & c, const int ia, const bool active) {
+  o.ia = ia;
   o.ha = o.rho_a = o.cs_a = o.Prho2_a = 0.0;
   o.acc0 = o.acc1 = o.vsig = 0.0;
 #pragma unroll
   for(int d = 0; d < D; ++d) { o.xa[d] = 0; o.va[d] = 0; o.vha[d] = 0; o.accv[d] = 0; }
   if(active) {
-    const int ia = o.ia;
 #pragma unroll
     for(int d = 0; d < D; ++d) o.xa[d] = c.f[F_POS + d][ia];
     o.ha = c.f[F_H][ia];
@@ -393,13 +382,83 @@ __global__ void __launch_bounds__(32 * NW) k_sweep(Tree t, Cols c, Search sr, Ph
       for(int d = 0; d < D; ++d) o.vha[d] = c.f[F_VELH + d][ia];
     }
   }
+}
 
-  for(int tb = 0; tb < C; tb += SW_TILE) {
-    const int tc = min(SW_TILE, C - tb);
+// the per-particle tail of each functor: writes the results of the sweep
+template<int D, int OP>
+__device__ __forceinline__ void store_own(const Own<D> & o, const Cols & c, const PhysParams & pp, uint32_t * __restrict__ status) {
+  const int ia = o.ia;
+  if(OP == OP_DENSITY) {
+    const double rho = o.acc0;
+    if(!(rho > 0)) atomicOr(status, (uint32_t)ERR_RHO_NONPOS);
+    c.f[F_RHO][ia] = rho;
+    double u;
+    if(pp.evolve_u && pp.thermokinetic) {
+      // recover_internal_energy (no external potential)
+      double v2 = 0.0;
+#pragma unroll
+      for(int d = 0; d < D; ++d) { const double v = c.f[F_VEL + d][ia]; v2 += v * v; }
+      u = c.f[F_E][ia] - .5 * v2 - 0.0;
+      if(!(u > 0)) atomicOr(status, (uint32_t)ERR_U_NONPOS);
+      c.f[F_U][ia] = u;
+    }
+    else u = c.f[F_U][ia];
+    c.f[F_P][ia] = (pp.gamma - 1.) * rho * u;
+    c.f[F_CSOLD][ia] = c.f[F_CS][ia];
+    c.f[F_CS][ia] = sqrt(pp.gamma * (pp.gamma - 1.) * u);
+  }
+  else if(OP == OP_VSIG) c.f[F_VSIG][ia] = o.vsig;
+  else if(OP == OP_ACC || OP == OP_ACCV) {
+#pragma unroll
+    for(int d = 0; d < D; ++d) {
+      c.f[F_ACC + d][ia] = o.accv[d];  // + external_force::acceleration == 0 (external_force_type "none")
+      c.f[F_GACC + d][ia] = 0.0;
+    }
+    c.f[F_GPOT][ia] = 0.0;
+    if(OP == OP_ACCV) c.f[F_VSIG][ia] = o.vsig;
+  }
+  else if(OP == OP_DUDT) c.f[F_DUDT][ia] = o.Prho2_a * o.acc0 + .5 * o.acc1;
+  else {
+    double gv = 0.0;
+#pragma unroll
+    for(int d = 0; d < D; ++d) gv += c.f[F_GACC + d][ia] * o.va[d];
+    c.f[F_DEDT][ia] = o.acc0 + gv;
+  }
+}
+
+template<int D, int K, int OP, int NW>
+__global__ void __launch_bounds__(32 * NW) k_sweep(Tree t, Cols c, Search sr, PhysParams pp, int g_begin, uint32_t * __restrict__ status) {
+  using TC = TileCols<D, OP>;
+  constexpr int NF = TC::NF;
+  constexpr int NT = 32 * NW;
+  constexpr int TILE = SwTile<OP>::N;
+  constexpr bool NEED_IDX = OP == OP_VSIG || OP == OP_ACCV;
+  __shared__ double tile[NF][TILE];
+  __shared__ int32_t tidx[NEED_IDX ? TILE : 1];
+  __shared__ uint32_t mtile[TILE / 32][NT];   // this tile's mask words, [word][particle]
+  __shared__ uint8_t nlist[SW_LCAP][NT];         // decoded neighbour lists of one round, [entry][particle]
+
+  const int g = g_begin + blockIdx.x, tid = threadIdx.x;
+  int start, P;
+  {
+    int v = t.cell[sr.wc_cell[g]];
+    if(v >= 0) { start = v; P = 1; }
+    else { start = t.node_start[~v]; P = t.sub[~v]; }
+  }
+  const int Ppad = (P + 31) & ~31;
+  const uint64_t co = sr.cand_off[g], mo = sr.mask_off[g];
+  const int C = sr.ncand[g];
+  const bool active = tid < P;
+
+  Own<D> o;
+  load_own<D, OP>(o, c, start + tid, active);
+
+  for(int tb = 0; tb < C; tb += TILE) {
+    const int tc = min(TILE, C - tb);
     __syncthreads();
     {
-      // all candidate indices of this thread first, then the column gathers: (SW_TILE / NT) x NF loads in flight
-      constexpr int LPT = (SW_TILE + NT - 1) / NT;
+      // all candidate indices of this thread first, then the column gathers: (TILE / NT) x NF loads in flight
+      constexpr int LPT = (TILE + NT - 1) / NT;
       int pidx[LPT];
 #pragma unroll
       for(int u = 0; u < LPT; ++u) {
@@ -448,44 +507,101 @@ __global__ void __launch_bounds__(32 * NW) k_sweep(Tree t, Cols c, Search sr, Ph
       if(jmax < SW_LCAP) break;
     }
   }
-  if(!active) return;
-  const int ia = o.ia;
-  if(OP == OP_DENSITY) {
-    const double rho = o.acc0;
-    if(!(rho > 0)) atomicOr(status, (uint32_t)ERR_RHO_NONPOS);
-    c.f[F_RHO][ia] = rho;
-    double u;
-    if(pp.evolve_u && pp.thermokinetic) {
-      // recover_internal_energy (no external potential)
-      double v2 = 0.0;
+  if(active) store_own<D, OP>(o, c, pp, status);
+}
+
+// Two particles per thread.  The pair loop is bound by shared-memory wavefronts (ncu: l1tex data pipe 77 % of peak,
+// fp64 pipe 55 %): every pair gathers its neighbour's 5-15 doubles from the tile at a lane-private address.  Key
+// neighbours (2t, 2t+1) share ~80 % of their neighbours, so a thread that owns both reads each common neighbour
+// once and evaluates it for both (a neighbour of only one of them costs a predicated-off evaluation).
+template<int D, int K, int OP, int NW>
+__global__ void __launch_bounds__(32 * NW) k_sweep2(Tree t, Cols c, Search sr, PhysParams pp, int g_begin, uint32_t * __restrict__ status) {
+  using TC = TileCols<D, OP>;
+  constexpr int NF = TC::NF;
+  constexpr int NT = 32 * NW;
+  constexpr int TILE = SwTile<OP>::N;
+  constexpr bool NEED_IDX = OP == OP_VSIG || OP == OP_ACCV;
+  __shared__ double tile[NF][TILE];
+  __shared__ int32_t tidx[NEED_IDX ? TILE : 1];
+  __shared__ uint32_t mtile[TILE / 32][2 * NT];  // this tile's mask words, [word][particle]
+  __shared__ uint16_t nlist[SW_LCAP][NT];        // decoded union lists of one round: candidate | owner bits << 8
+
+  const int g = g_begin + blockIdx.x, tid = threadIdx.x;
+  int start, P;
+  {
+    int v = t.cell[sr.wc_cell[g]];
+    if(v >= 0) { start = v; P = 1; }
+    else { start = t.node_start[~v]; P = t.sub[~v]; }
+  }
+  const int Ppad = (P + 31) & ~31;
+  const uint64_t co = sr.cand_off[g], mo = sr.mask_off[g];
+  const int C = sr.ncand[g];
+  const bool act0 = 2 * tid < P, act1 = 2 * tid + 1 < P;
+
+  Own<D> o0, o1;
+  load_own<D, OP>(o0, c, start + 2 * tid, act0);
+  load_own<D, OP>(o1, c, start + 2 * tid + 1, act1);
+
+  for(int tb = 0; tb < C; tb += TILE) {
+    const int tc = min(TILE, C - tb);
+    __syncthreads();
+    {
+      constexpr int LPT = (TILE + NT - 1) / NT;
+      int pidx[LPT];
 #pragma unroll
-      for(int d = 0; d < D; ++d) { const double v = c.f[F_VEL + d][ia]; v2 += v * v; }
-      u = c.f[F_E][ia] - .5 * v2 - 0.0;
-      if(!(u > 0)) atomicOr(status, (uint32_t)ERR_U_NONPOS);
-      c.f[F_U][ia] = u;
+      for(int u = 0; u < LPT; ++u) {
+        const int i = tid + u * NT;
+        pidx[u] = i < tc ? sr.cand[co + tb + i] : -1;
+      }
+#pragma unroll
+      for(int u = 0; u < LPT; ++u) {
+        const int i = tid + u * NT;
+        if(pidx[u] >= 0) {
+          if(NEED_IDX) tidx[i] = pidx[u];
+#pragma unroll
+          for(int j = 0; j < NF; ++j) tile[j][i] = c.f[TC::col(j)][pidx[u]];
+        }
+      }
     }
-    else u = c.f[F_U][ia];
-    c.f[F_P][ia] = (pp.gamma - 1.) * rho * u;
-    c.f[F_CSOLD][ia] = c.f[F_CS][ia];
-    c.f[F_CS][ia] = sqrt(pp.gamma * (pp.gamma - 1.) * u);
-  }
-  else if(OP == OP_VSIG) c.f[F_VSIG][ia] = o.vsig;
-  else if(OP == OP_ACC || OP == OP_ACCV) {
-#pragma unroll
-    for(int d = 0; d < D; ++d) {
-      c.f[F_ACC + d][ia] = o.accv[d];  // + external_force::acceleration == 0 (external_force_type "none")
-      c.f[F_GACC + d][ia] = 0.0;
+    {
+      const int nwt = (tc + 31) >> 5;
+      const uint32_t * mrow = sr.mask + mo + (uint64_t)(tb >> 5) * Ppad;
+      for(int i = tid; i < nwt * Ppad; i += NT) mtile[i / Ppad][i % Ppad] = mrow[i];
     }
-    c.f[F_GPOT][ia] = 0.0;
-    if(OP == OP_ACCV) c.f[F_VSIG][ia] = o.vsig;
+    __syncthreads();
+    const int nw = act0 ? (tc + 31) >> 5 : 0;
+    int w = 0;
+    uint32_t m0 = nw > 0 ? mtile[0][2 * tid] : 0u;
+    uint32_t m1 = (nw > 0 && act1) ? mtile[0][2 * tid + 1] : 0u;
+    for(;;) {
+      int cnt = 0;
+      while(cnt < SW_LCAP) {
+        while((m0 | m1) == 0 && w + 1 < nw) {
+          ++w;
+          m0 = mtile[w][2 * tid];
+          m1 = act1 ? mtile[w][2 * tid + 1] : 0u;
+        }
+        const uint32_t mu = m0 | m1;
+        if(mu == 0) break;
+        const int b = __ffs(mu) - 1;
+        nlist[cnt++][tid] = (uint16_t)((w * 32 + b) | (((m0 >> b) & 1u) << 8) | (((m1 >> b) & 1u) << 9));
+        const uint32_t clr = ~(1u << b);
+        m0 &= clr;
+        m1 &= clr;
+      }
+      const int jmax = __reduce_max_sync(0xffffffffu, cnt);
+      if(jmax == 0) break;
+      for(int j = 0; j < jmax; ++j) {
+        const int e = j < cnt ? nlist[j][tid] : 0;
+        const int ci = e & 0xff;
+        pair_body<D, K, OP>(o0, tile, tidx, pp, ci, (e >> 8) & 1);
+        pair_body<D, K, OP>(o1, tile, tidx, pp, ci, (e >> 9) & 1);
+      }
+      if(jmax < SW_LCAP) break;
+    }
   }
-  else if(OP == OP_DUDT) c.f[F_DUDT][ia] = o.Prho2_a * o.acc0 + .5 * o.acc1;
-  else {
-    double gv = 0.0;
-#pragma unroll
-    for(int d = 0; d < D; ++d) gv += c.f[F_GACC + d][ia] * o.va[d];
-    c.f[F_DEDT][ia] = o.acc0 + gv;
-  }
+  if(act0) store_own<D, OP>(o0, c, pp, status);
+  if(act1) store_own<D, OP>(o1, c, pp, status);
 }
 
 __global__ void __launch_bounds__(256) k_prho2(Cols c, int64_t n) {
@@ -509,12 +625,21 @@ static void launch_sweep(System & s) {
   for(int cls = 0; cls < 4; ++cls) {
     const int b = sr.class_off[cls], n = sr.class_off[cls + 1] - b;
     if(n <= 0) continue;
+#if FSPH_SWEEP_PPT == 2
+    // two particles per thread: classes of <= 32 / 64 particles fit one warp, <= 96 / 128 two warps
+    switch(cls) {
+      case 0: FSPH_LAUNCH((k_sweep<D, K, OP, 1>), n, 32, s.stream, s.tree, s.cols(), sr, s.phys(), b, st); break;
+      case 1: FSPH_LAUNCH((k_sweep2<D, K, OP, 1>), n, 32, s.stream, s.tree, s.cols(), sr, s.phys(), b, st); break;
+      default: FSPH_LAUNCH((k_sweep2<D, K, OP, 2>), n, 64, s.stream, s.tree, s.cols(), sr, s.phys(), b, st); break;
+    }
+#else
     switch(cls) {
       case 0: FSPH_LAUNCH((k_sweep<D, K, OP, 1>), n, 32, s.stream, s.tree, s.cols(), sr, s.phys(), b, st); break;
       case 1: FSPH_LAUNCH((k_sweep<D, K, OP, 2>), n, 64, s.stream, s.tree, s.cols(), sr, s.phys(), b, st); break;
       case 2: FSPH_LAUNCH((k_sweep<D, K, OP, 3>), n, 96, s.stream, s.tree, s.cols(), sr, s.phys(), b, st); break;
       default: FSPH_LAUNCH((k_sweep<D, K, OP, 4>), n, 128, s.stream, s.tree, s.cols(), sr, s.phys(), b, st); break;
     }
+#endif
   }
 }
 

@@ -595,13 +595,13 @@ void build_tree(System & s) {
 // traversal_sph, tree_topology.h:221-235: maximal nodes with sub_entities <= 128, plus lone leaves hanging
 // under bigger nodes.  Work cells are disjoint particle ranges; listing them by first particle gives Morton order.
 __global__ void __launch_bounds__(256) k_wc_mark(Tree t, int64_t nc, uint32_t * __restrict__ wc_at, const int32_t * __restrict__ type,
-  int ghosts) {
+  int ghosts, int limit) {
   int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(c >= nc) return;
   int v = t.cell[c];
   int p = t.cell_parent[c];
-  bool small = v >= 0 || t.sub[~v] <= SUB_ENTITIES;
-  bool parent_big = p < 0 || t.sub[p] > SUB_ENTITIES;
+  bool small = v >= 0 || t.sub[~v] <= limit;
+  bool parent_big = p < 0 || t.sub[p] > limit;
   if(small && parent_big) {
     int start = v >= 0 ? v : t.node_start[~v];
     // cells of remote copies are only sources: the rank that owns them runs their sweeps (tree_topology.h:229, !is_shared)
@@ -627,14 +627,20 @@ __global__ void __launch_bounds__(256) k_wc_compact(const uint32_t * __restrict_
   }
 }
 
+void mark_maximal_cells(System & s, int limit, bool skip_ghosts, uint32_t * at) {
+  const int64_t nc = s.tree.ncells;
+  FSPH_CUDA_OK(cudaMemsetAsync(at, 0, (size_t)s.n * 4, s.stream));
+  FSPH_LAUNCH(k_wc_mark, (unsigned)((nc + 255) / 256), 256, s.stream, s.tree, nc, at, s.col_type.as<int32_t>(),
+    (skip_ghosts && s.has_ghosts) ? 1 : 0, limit);
+}
+
 void find_work_cells(System & s) {
   const int64_t n = s.n, nc = s.tree.ncells;
   s.b_cnt0.reserve((size_t)(n + 1) * 4);
   s.b_tmp[0].reserve((size_t)(n + 1) * 4);
   uint32_t * wc_at = s.b_cnt0.as<uint32_t>();
   uint32_t * ex = s.b_tmp[0].as<uint32_t>();
-  FSPH_CUDA_OK(cudaMemsetAsync(wc_at, 0, (size_t)n * 4, s.stream));
-  FSPH_LAUNCH(k_wc_mark, (unsigned)((nc + 255) / 256), 256, s.stream, s.tree, nc, wc_at, s.col_type.as<int32_t>(), s.has_ghosts ? 1 : 0);
+  mark_maximal_cells(s, SUB_ENTITIES, true, wc_at);
   unsigned nbp = (unsigned)((n + 255) / 256);
   FSPH_LAUNCH(k_flag_nonzero, nbp, 256, s.stream, wc_at, ex, n);
   exclusive_scan_u32(s, ex, ex, n, nullptr);
