@@ -281,7 +281,7 @@ fsph_system * fsph_create(const fsph_params * p, int32_t device) {
   }
   if(p->eos_type != FSPH_EOS_IDEAL) { g_create_error = "only the ideal-gas EOS is implemented on the device"; return nullptr; }
   if(p->sph_viscosity != FSPH_VISC_CONSTANT) { g_create_error = "only constant artificial viscosity is implemented on the device"; return nullptr; }
-  if(p->sph_kernel < 0 || p->sph_kernel > FSPH_KERNEL_WENDLAND_C6) { g_create_error = "sph_kernel not implemented on the device"; return nullptr; }
+  if(p->sph_kernel < 0 || p->sph_kernel > FSPH_KERNEL_SINC) { g_create_error = "unknown sph_kernel"; return nullptr; }
   fsph_system * s = nullptr;
   try {
     FSPH_CUDA_OK(cudaSetDevice(device));

@@ -224,6 +224,85 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_WENDLAND_C6> {
   }
 };
 
+// gaussian / super gaussian (kernels.h:168-203, 582-612): support 3 r / h < 3, h is the full support radius
+template<int D> struct SphKernel<D, FSPH_KERNEL_GAUSSIAN> {
+  static __device__ __forceinline__ double sigma() {
+    return D == 1 ? 1.69260614115414981387661988500545775 : (D == 2 ? 2.86514256233641438778811727710055596 : 4.85098600188835377710867224691152783);
+  }
+  static __device__ __forceinline__ double W(double r, double h) {
+    const double ih = rcp_nr(h);
+    const double q = 3. * r * ih;
+    return q <= 3. ? sigma() * ipowD<D>(ih) * exp(-q * q) : 0.0;
+  }
+  static __device__ __forceinline__ double Fi(double r, double ih, double ir) {
+    const double q = 3. * r * ih;
+    const double sg = 3. * sigma() * ipowD<D>(ih) * ih;
+    return q < 3. ? sg * (-2. * q * exp(-q * q)) * ir : 0.0;
+  }
+  static __device__ __forceinline__ double F(double r, double h) {
+    double ih, ir;
+    inv_h_r(h, r, ih, ir);
+    return Fi(r, ih, ir);
+  }
+};
+template<int D> struct SphKernel<D, FSPH_KERNEL_SUPER_GAUSSIAN> {
+  static __device__ __forceinline__ double sigma() {
+    return D == 1 ? 1.69225265632490690298438831093977954 : (D == 2 ? 2.86196342089351035329931251213987773 : 4.83280745997963041039733264826054666);
+  }
+  static __device__ __forceinline__ double W(double r, double h) {
+    const double ih = rcp_nr(h);
+    const double q = 3. * r * ih, q2 = q * q;
+    return q < 3. ? sigma() * ipowD<D>(ih) * exp(-q2) * (D / 2.0 + 1 - q2) : 0.0;
+  }
+  static __device__ __forceinline__ double Fi(double r, double ih, double ir) {
+    const double q = 3. * r * ih;
+    const double sg = 3. * sigma() * ipowD<D>(ih) * ih;
+    const double dW = exp(-q * q) * (2. * q * q * q - (D + 4.) * q);
+    return q < 3. ? sg * dW * ir : 0.0;
+  }
+  static __device__ __forceinline__ double F(double r, double h) {
+    double ih, ir;
+    inv_h_r(h, r, ih, ir);
+    return Fi(r, ih, ir);
+  }
+};
+// sinc kernel (kernels.h:626-699): index n and its normalisation (set_sinc_kernel_normalization, :67-77) are run-time
+// parameters; they live in constant memory, refreshed by sweep() before the launches
+__constant__ double c_sinc[2];  // {n, sigma(n, D)}
+template<int D> struct SphKernel<D, FSPH_KERNEL_SINC> {
+  static __device__ __forceinline__ double W(double r, double h) {
+    const double ih = rcp_nr(h);
+    double q = fabs(r * ih);
+    if(!(q < 1.)) return 0.0;
+    q *= PI;
+    double sinc = 1.0;
+    if(q > 1e-6) sinc = sin(q) / q;
+    else if(q > 1e-24) { const double q2 = q * q; sinc += q2 * (.05 * q2 - 1.) / 6.; }
+    return c_sinc[1] * ipowD<D>(ih) * pow(sinc, c_sinc[0]);
+  }
+  static __device__ __forceinline__ double Fi(double r, double ih, double ir) {
+    double q = fabs(r * ih);
+    if(!(q < 1.)) return 0.0;
+    const double n = c_sinc[0], sg = c_sinc[1] * ipowD<D>(ih) * ih;
+    q *= PI;
+    double dW = 0.0;
+    if(q > 1e-6) {
+      const double sinc = sin(q) / q, cosx = cos(q) / q;
+      dW = -n * pow(sinc, n - 1) * PI * (sinc / q - cosx);
+    }
+    else if(q > 1e-24) {
+      const double q2 = q * q;
+      dW = -n * q / 3. * PI * (1 - .5 * q2 * (.2 - (n - 1) / 18));
+    }
+    return sg * dW * ir;
+  }
+  static __device__ __forceinline__ double F(double r, double h) {
+    double ih, ir;
+    inv_h_r(h, r, ih, ir);
+    return Fi(r, ih, ir);
+  }
+};
+
 // ---- candidate tile columns per sweep ---------------------------------------------------------------------
 template<int D, int OP> struct TileCols {
   // ACCV = acceleration + signal speed: ACC's columns + velocity + previous soundspeed
@@ -671,7 +750,21 @@ static void sweep_d(System & s, int op) {
     case FSPH_KERNEL_WENDLAND_C2: sweep_dk<D, FSPH_KERNEL_WENDLAND_C2>(s, op); break;
     case FSPH_KERNEL_WENDLAND_C4: sweep_dk<D, FSPH_KERNEL_WENDLAND_C4>(s, op); break;
     case FSPH_KERNEL_WENDLAND_C6: sweep_dk<D, FSPH_KERNEL_WENDLAND_C6>(s, op); break;
-    default: throw std::runtime_error("sph_kernel not implemented on the device (gaussian / super gaussian / sinc)");
+    case FSPH_KERNEL_GAUSSIAN: sweep_dk<D, FSPH_KERNEL_GAUSSIAN>(s, op); break;
+    case FSPH_KERNEL_SUPER_GAUSSIAN: sweep_dk<D, FSPH_KERNEL_SUPER_GAUSSIAN>(s, op); break;
+    case FSPH_KERNEL_SINC: {
+      // set_sinc_kernel_normalization, kernels.h:67-77
+      const double si = s.par.sph_sinc_index, sq = sqrt(si), s2 = si * si;
+      const double b0[3] = {-1.5404568e-2, 5.2245027e-2, 2.7012593e-2}, b1[3] = {3.6632876e-1, 1.3090245e-1, 2.0410827e-2};
+      const double b2[3] = {-4.6519576e-4, 1.9358485e-2, 3.7451957e-3}, b3[3] = {7.3658324e-2, -6.1642906e-3, 4.7013839e-2};
+      double h2[2] = {si, 0.0};
+      if(D == 1) h2[1] = 2. * (b0[0] + b1[0] * sq + b2[0] * si + b3[0] / sq);
+      else if(D == 2) h2[1] = 4. * (b0[1] + b1[1] * si + b2[1] / si + b3[1] / s2);
+      else h2[1] = 8. * (b0[2] + b1[2] * sq + b2[2] * si + b3[2] * sq * si);
+      FSPH_CUDA_OK(cudaMemcpyToSymbolAsync(c_sinc, h2, sizeof(h2), 0, cudaMemcpyHostToDevice, s.stream));
+      sweep_dk<D, FSPH_KERNEL_SINC>(s, op);
+    } break;
+    default: throw std::runtime_error("unknown sph_kernel");
   }
 }
 

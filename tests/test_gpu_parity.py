@@ -39,7 +39,12 @@ SWEEP_CASES = [("sedov", dict(nx=12)), ("random", dict(n=3000, seed=3, h_jitter=
                ("random", dict(n=2500, seed=6, par=dict(sph_kernel="cubic spline"))),
                ("random", dict(n=2500, seed=7, par=dict(sph_kernel="quintic spline"))),
                ("random", dict(n=2500, seed=8, par=dict(sph_kernel="wendland c2"))),
-               ("random", dict(n=2500, seed=8, par=dict(sph_kernel="wendland c6")))]
+               ("random", dict(n=2500, seed=8, par=dict(sph_kernel="wendland c6"))),
+               ("random", dict(n=2500, seed=9, par=dict(sph_kernel="gaussian"))),
+               ("random", dict(n=2500, seed=10, par=dict(sph_kernel="super gaussian"))),
+               ("random", dict(n=2500, seed=11, par=dict(sph_kernel="sinc", sph_sinc_index=5.0))),
+               ("random", dict(n=1500, dim=2, seed=12, par=dict(sph_kernel="sinc"))),
+               ("random", dict(n=1500, dim=2, seed=13, par=dict(sph_kernel="gaussian")))]
 
 
 @pytest.mark.parametrize("name,kw", SWEEP_CASES)
