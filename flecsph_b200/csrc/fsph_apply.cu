@@ -33,6 +33,7 @@ PhysParams System::phys() const {
   p.kernel = par.sph_kernel;
   p.thermokinetic = par.thermokinetic_formulation;
   p.evolve_u = par.evolve_internal_energy;
+  p.eos = par.eos_type;
   p.eta = par.sph_eta;
   p.gamma = par.poly_gamma;
   p.alpha = par.sph_viscosity_alpha;
@@ -80,8 +81,7 @@ __device__ __forceinline__ void apply_one(const Cols & c, const int64_t i, const
       break;
     case FSPH_APPLY_RECOMPUTE_P_CS: {
       const double u = c.f[F_U][i] + 0.5 * dt * c.f[F_DUDT][i];
-      c.f[F_P][i] = (pp.gamma - 1.) * c.f[F_RHO][i] * u;
-      c.f[F_CS][i] = sqrt(pp.gamma * (pp.gamma - 1.) * u);
+      eos_p_cs(pp, c.f[F_RHO][i], u, c.f[F_ADIA][i], c.f[F_P][i], c.f[F_CS][i]);
     } break;
     case FSPH_APPLY_RECOMPUTE_P_CS_THERMOKINETIC: {
       double v2 = 0.0, va = 0.0;
@@ -94,8 +94,7 @@ __device__ __forceinline__ void apply_one(const Cols & c, const int64_t i, const
       if(!(eint > 0)) atomicOr(status, (uint32_t)ERR_U_NONPOS);
       c.f[F_U][i] = eint;
       const double u = eint + 0.5 * dt * (c.f[F_DEDT][i] - va);
-      c.f[F_P][i] = (pp.gamma - 1.) * c.f[F_RHO][i] * u;
-      c.f[F_CS][i] = sqrt(pp.gamma * (pp.gamma - 1.) * u);
+      eos_p_cs(pp, c.f[F_RHO][i], u, c.f[F_ADIA][i], c.f[F_P][i], c.f[F_CS][i]);
     } break;
     case FSPH_APPLY_COMPUTE_DT: {
       const double tiny = 1e-24, mc = 0.6;

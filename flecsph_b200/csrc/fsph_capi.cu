@@ -279,7 +279,10 @@ fsph_system * fsph_create(const fsph_params * p, int32_t device) {
     g_create_error = "no CUDA device: libflecsph_b200 has no CPU path";
     return nullptr;
   }
-  if(p->eos_type != FSPH_EOS_IDEAL) { g_create_error = "only the ideal-gas EOS is implemented on the device"; return nullptr; }
+  if(p->eos_type != FSPH_EOS_IDEAL && p->eos_type != FSPH_EOS_POLYTROPIC) {
+    g_create_error = "eos_type not implemented on the device (ideal and polytropic are)";
+    return nullptr;
+  }
   if(p->sph_viscosity != FSPH_VISC_CONSTANT) { g_create_error = "only constant artificial viscosity is implemented on the device"; return nullptr; }
   if(p->sph_kernel < 0 || p->sph_kernel > FSPH_KERNEL_SINC) { g_create_error = "unknown sph_kernel"; return nullptr; }
   fsph_system * s = nullptr;

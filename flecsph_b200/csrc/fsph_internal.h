@@ -118,12 +118,25 @@ struct Search {
 };
 
 struct PhysParams {
-  int kernel, thermokinetic, evolve_u;
+  int kernel, thermokinetic, evolve_u, eos;
   double eta, gamma, alpha, beta, epsilon, cfl, kernel_width;
   double dt;
   int64_t iteration;
   int relaxation_steps;
 };
+
+// eos::compute_pressure + compute_soundspeed (include/physics/eos/eos.h): ideal gas :166-183 from the specific internal
+// energy, polytropic :100-118 from the particle's adiabatic invariant K = P / rho^gamma (eos::init, :68-83)
+__host__ __device__ inline void eos_p_cs(const PhysParams & pp, double rho, double u, double K, double & P, double & cs) {
+  if(pp.eos == FSPH_EOS_POLYTROPIC) {
+    P = K * pow(rho, pp.gamma);
+    cs = sqrt(K * pp.gamma * pow(rho, pp.gamma - 1.));
+  }
+  else {
+    P = (pp.gamma - 1.) * rho * u;
+    cs = sqrt(pp.gamma * (pp.gamma - 1.) * u);
+  }
+}
 
 struct Phase {
   std::string name;

@@ -482,9 +482,11 @@ __device__ __forceinline__ void store_own(const Own<D> & o, const Cols & c, cons
       c.f[F_U][ia] = u;
     }
     else u = c.f[F_U][ia];
-    c.f[F_P][ia] = (pp.gamma - 1.) * rho * u;
+    double Pn, csn;
+    eos_p_cs(pp, rho, u, pp.eos == FSPH_EOS_POLYTROPIC ? c.f[F_ADIA][ia] : 0.0, Pn, csn);
+    c.f[F_P][ia] = Pn;
     c.f[F_CSOLD][ia] = c.f[F_CS][ia];
-    c.f[F_CS][ia] = sqrt(pp.gamma * (pp.gamma - 1.) * u);
+    c.f[F_CS][ia] = csn;
   }
   else if(OP == OP_VSIG) c.f[F_VSIG][ia] = o.vsig;
   else if(OP == OP_ACC || OP == OP_ACCV) {

@@ -44,7 +44,8 @@ SWEEP_CASES = [("sedov", dict(nx=12)), ("random", dict(n=3000, seed=3, h_jitter=
                ("random", dict(n=2500, seed=10, par=dict(sph_kernel="super gaussian"))),
                ("random", dict(n=2500, seed=11, par=dict(sph_kernel="sinc", sph_sinc_index=5.0))),
                ("random", dict(n=1500, dim=2, seed=12, par=dict(sph_kernel="sinc"))),
-               ("random", dict(n=1500, dim=2, seed=13, par=dict(sph_kernel="gaussian")))]
+               ("random", dict(n=1500, dim=2, seed=13, par=dict(sph_kernel="gaussian"))),
+               ("random", dict(n=2500, seed=14, par=dict(eos_type=1, poly_gamma=1.6)))]
 
 
 @pytest.mark.parametrize("name,kw", SWEEP_CASES)
@@ -69,7 +70,8 @@ def test_individual_sweeps_match(name, kw):
 
 
 STEP_CASES = [("sedov", dict(nx=12)), ("noh", dict(nx=12)), ("sod", dict(nx=100)), ("collapse", dict(nx=10)),
-              ("random", dict(n=1200, dim=2, seed=7))]
+              ("random", dict(n=1200, dim=2, seed=7)),
+              ("random", dict(n=2000, seed=15, par=dict(eos_type=1, thermokinetic_formulation=0, sph_kernel="quintic spline")))]
 
 
 @pytest.mark.parametrize("name,kw", STEP_CASES)
