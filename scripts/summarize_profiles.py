@@ -43,7 +43,9 @@ METRICS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", 
            "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
            "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
            "smsp__inst_executed.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
-           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+           "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+           "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__sass_inst_executed_op_shared_ld.sum"]
 
 
 def full(name):
