@@ -60,14 +60,17 @@ def have(*paths):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,dim,iters", [("sedov", 3, 6), ("sod", 1, 8)])
+@pytest.mark.parametrize("name,dim,iters", [("sedov", 3, 6), ("sod", 1, 8), ("collapse", 3, 4)])
 def test_unmodified_driver_on_gpu_matches_reference_build(tmp_path, name, dim, iters):
-    exe_g = os.path.join(B200, "hydro_%dd_b200" % dim)
-    exe_r = os.path.join(REF, "hydro_%dd_ref" % dim)
+    drv = "newtonian" if name == "collapse" else "hydro"   # newtonian_3d: hydro + FMM gravity (newtonian/main_driver.cc)
+    exe_g = os.path.join(B200, "%s_%dd_b200" % (drv, dim))
+    exe_r = os.path.join(REF, "%s_%dd_ref" % (drv, dim))
     if not have(exe_g, exe_r):
         pytest.skip("driver binaries not built (need the reference checkout: make -C flecsph_b200/host; make -C oracle drivers)")
     if name == "sedov":
         f, par = idata.sedov_3d(nx=14)
+    elif name == "collapse":
+        f, par = idata.collapse_3d(nx=11)
     else:
         f, par = idata.sodtube_1d(nx=100)
     g = run_driver(exe_g, str(tmp_path / "gpu"), f, par, dim, iters)
