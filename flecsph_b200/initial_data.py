@@ -198,6 +198,51 @@ def periodic_box(n, dim=3, seed=0, h_jitter=0.0, eta=1.2, vel_amp=0.1, box=(1.0,
     return f, par
 
 
+def kh_3d(nx=20, eta=1.5, gamma=1.4, density_ratio=2.0, flow_velocity=1.0, P0=2.5, A=0.025, lam=1.0 / 6.0, L=1.0):
+    """Kelvin-Helmholtz shear layer in a fully periodic unit box, data/KH_3d.par semantics (app/id_generators/KH/main.cc):
+    a dense middle slab |y| < L/4 moving at +v/2 between two slabs of half the density moving at -v/2, equal-mass
+    particles (so the outer slabs are coarser by cbrt(density_ratio)), eta = 1.5, velocity perturbation a la Price
+    (2008) at the interfaces (main.cc:352-356).  Simplification: rectangular lattices that tile the periodic box exactly
+    (the reference builds HCP lattices and stretches the outer blocks to fit, main.cc:296-326)."""
+    s = L / nx
+    def block(n_x, n_y, n_z, y_lo, y_hi):
+        xs = -0.5 * L + (np.arange(n_x) + 0.5) * (L / n_x)
+        ys = y_lo + (np.arange(n_y) + 0.5) * ((y_hi - y_lo) / n_y)
+        zs = -0.5 * L + (np.arange(n_z) + 0.5) * (L / n_z)
+        Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
+        vol = (L / n_x) * ((y_hi - y_lo) / n_y) * (L / n_z)
+        return np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1), vol
+    n_mid_y = max(nx // 2, 1)
+    n_out = max(int(round(nx / density_ratio ** (1.0 / 3.0))), 1)
+    n_out_y = max(int(round(n_out / 4.0)), 1)
+    pm, vol_m = block(nx, n_mid_y, nx, -0.25 * L, 0.25 * L)
+    pt, vol_t = block(n_out, n_out_y, n_out, 0.25 * L, 0.5 * L)
+    pb, _ = block(n_out, n_out_y, n_out, -0.5 * L, -0.25 * L)
+    rho_m = density_ratio
+    m = rho_m * vol_m                     # equal masses
+    rho_t = m / vol_t
+    pos = np.concatenate([pm, pt, pb])
+    n, nm = len(pos), len(pm)
+    mid = np.arange(n) < nm
+    rho = np.where(mid, rho_m, rho_t)
+    vel = np.zeros((n, 3))
+    vel[:, 0] = np.where(mid, 0.5 * flow_velocity, -0.5 * flow_velocity)
+    x, y = pos[:, 0], pos[:, 1]
+    up = (y < 0.25 * L) & (y > 0.25 * L - 0.025)
+    dn = (y > -0.25 * L) & (y < -0.25 * L + 0.025)
+    vel[:, 1] = np.where(up, A * np.sin(-2 * np.pi * (x + 0.5) / lam), 0.0) + np.where(dn, A * np.sin(2 * np.pi * (x + 0.5) / lam), 0.0)
+    u = P0 / (gamma - 1.0) / rho
+    h = eta * 2.0 * (m / rho) ** (1.0 / 3.0)
+    cs = math.sqrt(gamma * P0 / rho_t)
+    dt0 = 0.25 * s / max(cs, flow_velocity)
+    f = dict(pos=pos, vel=vel, mass=np.full(n, m), h=h, rho=rho, u=u, P=np.full(n, P0), id=np.arange(n, dtype=np.int64),
+             dt=np.full(n, dt0))
+    par = dict(sph_kernel="wendland c4", sph_eta=eta, poly_gamma=gamma, initial_dt=dt0, sph_variable_h=1, adaptive_timestep=1,
+               timestep_cfl_factor=0.25, box_length=L, box_width=L, box_height=L, periodic_boundary_x=1, periodic_boundary_y=1,
+               periodic_boundary_z=1)
+    return f, par
+
+
 def nx_for_particles(target, lo=8, hi=2000):
     """Smallest lattice_nx whose FCC unit sphere holds >= target particles (count ~ (4pi/3)/(s^3/sqrt2))."""
     est = lambda nx: (4.0 * math.pi / 3.0) / ((2.0 / (nx - 1)) ** 3 / math.sqrt(2.0))

@@ -43,6 +43,9 @@ def case(name, **kw):
         f, par = idata.random_box(kw.get("n", 2000), dim=dim, seed=kw.get("seed", 1), h_jitter=kw.get("h_jitter", 0.0))
         par = dict(par, **kw.get("par", {}))
         return f, par, dim
+    if name == "kh":
+        f, par = idata.kh_3d(nx=kw.get("nx", 20))
+        return f, par, 3
     if name == "periodic":
         dim = kw.get("dim", 3)
         f, par = idata.periodic_box(kw.get("n", 3000), dim=dim, seed=kw.get("seed", 1), h_jitter=kw.get("h_jitter", 0.0),

@@ -46,3 +46,18 @@ def test_periodic_steps_match_reference(label, kw):
     for op in (capi.GET_TOTAL_MASS, capi.GET_TOTAL_ENERGY, capi.GET_TOTAL_MOMENTUM):
         assert np.allclose(G.get_all(op), R.get_all(op), rtol=1e-11, atol=1e-14)
     G.close(); R.close()
+
+
+def test_kelvin_helmholtz_steps_match_reference():
+    """BASELINE.json config 4 at test size: KH shear layer, eta = 1.5, fully periodic (WALL copies on every face, edge and
+    corner), three driver iterations."""
+    if not have_ref(3):
+        pytest.skip("oracle/_ref was not built / shipped")
+    f, par, dim = case("kh", nx=20)
+    G, R = make_system("cuda", f, par, dim), make_system("ref", f, par, dim)
+    for it in range(3):
+        G.step(initial=(it == 0)); R.step(initial=(it == 0))
+    assert G.nbodies() == R.nbodies() and G.nbodies() > 3 * len(f["mass"])
+    assert np.array_equal(G.get(capi.COL_ID), R.get(capi.COL_ID))
+    assert_fields_close(G, R, ["pos", "vel", "rho", "P", "u", "acc", "dedt", "h", "vsig", "dt"], 1e-10)
+    G.close(); R.close()
