@@ -316,17 +316,7 @@ void fsph_destroy(fsph_system * s) {
   dist_release(*s);
   delete s->comm;
   s->comm = nullptr;
-  s->col_gd.release();
-  s->b_fmm_nodes.release(); s->b_fmm_out.release(); s->b_fmm_stack.release();
-  s->b_node_parent.release();
-  DevBuf * all[] = {&s->col_id, &s->col_key, &s->col_type, &s->col_nneigh, &s->scratch_col, &s->b_perm, &s->b_keys2, &s->b_perm2,
-    &s->b_cell, &s->b_cell_parent, &s->b_cell_desc, &s->b_cell_desc2, &s->b_child_begin, &s->b_child_end, &s->b_node_start,
-    &s->b_node_depth, &s->b_sub, &s->b_nmass, &s->b_nradius, &s->b_nlap, &s->b_wc_cell, &s->b_cand_off, &s->b_mask_off, &s->b_cand,
-    &s->b_mask, &s->b_cnt0, &s->b_cnt1, &s->b_status, &s->b_red, &s->b_levels, &s->b_ncand, &s->b_search_scratch, &s->b_noderec, &s->b_leafrec};
-  for(DevBuf * b : all) b->release();
-  for(int f = 0; f < NF64; ++f) s->col[f].release();
-  for(int i = 0; i < 6; ++i) s->b_tmp[i].release();
-  for(int d = 0; d < 3; ++d) { s->b_ncom[d].release(); s->b_nbmin[d].release(); s->b_nbmax[d].release(); }
+  release_buffers(*s);
   if(s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }

@@ -71,6 +71,7 @@ struct Dist {
   std::vector<double> hmax;
   std::vector<double> rlo, rhi;
   DDGeom geom;
+  System * fmm_sys = nullptr;  // the gathered global body set + tree of gravitation_fmm on several ranks
 };
 
 void dist_release(System & s) {
@@ -79,6 +80,10 @@ void dist_release(System & s) {
   DevBuf * all[] = {&d.send_idx, &d.ghost_pos, &d.sendbuf, &d.recvbuf, &d.small, &d.small2, &d.bitmap, &d.bitmap_all, &d.nmask, &d.emask,
     &d.flags, &d.ex, &d.inv, &d.recs_send, &d.recs_recv, &d.path, &d.path_all, &d.counters};
   for(DevBuf * b : all) b->release();
+  if(d.fmm_sys) {
+    release_buffers(*d.fmm_sys);
+    delete d.fmm_sys;
+  }
   delete s.dist;
   s.dist = nullptr;
 }
@@ -873,6 +878,68 @@ void dist_update_iteration(System & s) {
   if(s.dim == 1) dist_update_iteration_t<1>(s);
   else if(s.dim == 2) dist_update_iteration_t<2>(s);
   else dist_update_iteration_t<3>(s);
+}
+
+// ---- FMM gravity on several ranks ------------------------------------------------------------------------------
+// Replaces the remote-branch traffic of traversal_fmm (tree_topology.h:583-612, 1384-1463: REQUEST_SUBTREE).  Gravity
+// needs of a body only (x, m) and of a node only (mass, centre, radius): every rank all-gathers the owned bodies' keys,
+// positions, masses and h (40 B per body over NVLink), builds the GLOBAL tree -- the ranks' ranges concatenate in key
+// order, so no sort -- and runs the dual walk restricted to the sink cells that hold its own bodies ("iam_owner" of the
+// reference).  Sink nodes that straddle ranks are evaluated by each rank that shares them (same sources, same result).
+// The tree and hence the interaction set are those of a single rank: parity with one rank by construction.
+__global__ void __launch_bounds__(256) k_add_range(double * __restrict__ dst, const double * __restrict__ src, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n) dst[i] += src[i];
+}
+
+void dist_gravitation_fmm(System & s) {
+  if(s.dim != 3) throw std::runtime_error("fmm needs 3 dimensions (bodies_system.h:283)");
+  if(!s.tree_valid) throw std::runtime_error("gravitation_fmm before update_iteration");
+  Dist & d = dist_of(s);
+  Comm & cm = *s.comm;
+  const int P = cm.nranks, R = cm.rank;
+  const int64_t n_own = s.n_owned_or_n(), own_begin = s.has_ghosts ? s.own_begin : 0;
+  std::vector<int64_t> cnt(P);
+  dist_all_gather_host(s, &n_own, cnt.data(), 8);
+  std::vector<int64_t> goff(P + 1, 0);
+  for(int q = 0; q < P; ++q) goff[q + 1] = goff[q] + cnt[q];
+  const int64_t N = goff[P];
+  if(N >= (int64_t(1) << 31)) throw std::runtime_error("more than 2^31 bodies in the gathered gravity tree");
+  if(!d.fmm_sys) {
+    d.fmm_sys = new System;
+    d.fmm_sys->b_status.reserve(128);
+    FSPH_CUDA_OK(cudaMemsetAsync(d.fmm_sys->b_status.p, 0, 128, s.stream));
+  }
+  System & g = *d.fmm_sys;
+  g.par = s.par;
+  g.dim = s.dim;
+  g.device = s.device;
+  g.stream = s.stream;
+  g.n = g.n_owned = N;
+  const int fields[] = {F_POS, F_POS + 1, F_POS + 2, F_MASS, F_H};
+  std::vector<size_t> so(P), sc(P), ro(P), rc(P);
+  for(int q = 0; q < P; ++q) { so[q] = 0; sc[q] = (size_t)n_own * 8; ro[q] = (size_t)goff[q] * 8; rc[q] = (size_t)cnt[q] * 8; }
+  for(int f : fields) {
+    g.col[f].reserve((size_t)N * 8);
+    cm.all_to_all_v(s.col[f].as<char>() + (size_t)own_begin * 8, so.data(), sc.data(), g.col[f].p, ro.data(), rc.data(), s.stream);
+  }
+  g.col_key.reserve((size_t)N * 8);
+  cm.all_to_all_v(s.col_key.as<char>() + (size_t)own_begin * 8, so.data(), sc.data(), g.col_key.p, ro.data(), rc.data(), s.stream);
+  g.col_type.reserve((size_t)N * 4);
+  FSPH_CUDA_OK(cudaMemsetAsync(g.col_type.p, 0, (size_t)N * 4, s.stream));
+  const int acc[] = {F_GACC, F_GACC + 1, F_GACC + 2, F_GPOT};
+  for(int f : acc) {
+    g.col[f].reserve((size_t)N * 8);
+    FSPH_CUDA_OK(cudaMemsetAsync(g.col[f].p, 0, (size_t)N * 8, s.stream));
+  }
+  TreeEdges te;
+  te.finish = false;
+  build_tree_edges(g, te);
+  gravitation_fmm_range(g, goff[R], goff[R + 1]);
+  for(int f : acc)
+    FSPH_LAUNCH(k_add_range, blocks(n_own), 256, s.stream, s.col[f].as<double>() + own_begin, g.col[f].as<double>() + goff[R], n_own);
+  s.fmm_pairs = g.fmm_pairs;
+  FSPH_CUDA_OK(cudaGetLastError());
 }
 
 // reset_ghosts: the owners re-send the columns the sweeps read from neighbours and that change between sweeps

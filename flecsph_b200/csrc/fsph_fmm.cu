@@ -41,14 +41,25 @@ __device__ __forceinline__ double dist3(const double * a, const double * b) {
   return sqrt(s);
 }
 
+// does cell cc hold a body of the index range [lo, hi)?  (the sinks of a rank: "iam_owner", tree_topology.h:518-524,602)
+__device__ __forceinline__ bool cell_in_range(const Tree & t, int cc, int64_t lo, int64_t hi) {
+  const int v = t.cell[cc];
+  const int64_t b = v >= 0 ? v : t.node_start[~v];
+  const int64_t e = v >= 0 ? b + 1 : b + t.sub[~v];
+  return b < hi && e > lo;
+}
+
+// PRUNE: only sink cells with bodies in [own_lo, own_hi) are followed (several ranks share one global tree)
+template<bool PRUNE>
 __global__ void __launch_bounds__(256) k_fmm_pairs(Tree t, Cols c, FmmNodes fn, const uint64_t * __restrict__ in, int64_t nin,
   uint64_t * __restrict__ out, unsigned long long * __restrict__ nout, unsigned long long out_cap, double theta, double gc,
-  uint32_t * __restrict__ status) {
+  uint32_t * __restrict__ status, int64_t own_lo, int64_t own_hi) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int nemit = 0;       // number of pairs this thread appends
   int mode = 0;        // 1: same node, 2: split sink, 3: split source
   int cb1 = 0, ce1 = 0, cb2 = 0, ce2 = 0;
   uint32_t c1 = 0, c2 = 0;
+  uint32_t keep = 0xffu;  // PRUNE: children of the sink that hold bodies of this rank
   if(i < nin) {
     const uint64_t pr = in[i];
     c1 = (uint32_t)(pr >> 32);
@@ -73,7 +84,11 @@ __global__ void __launch_bounds__(256) k_fmm_pairs(Tree t, Cols c, FmmNodes fn, 
       cb1 = t.child_begin[nd];
       ce1 = t.child_end[nd];
       mode = 1;
-      nemit = (ce1 - cb1) * (ce1 - cb1);
+      if(PRUNE) {
+        keep = 0;
+        for(int a = cb1; a < ce1; ++a) keep |= (cell_in_range(t, a, own_lo, own_hi) ? 1u : 0u) << (a - cb1);
+      }
+      nemit = (PRUNE ? __popc(keep) : (ce1 - cb1)) * (ce1 - cb1);
     }
     else {
       double X1[3], X2[3], r1 = 0.0, r2 = 0.0, m2;
@@ -122,7 +137,11 @@ __global__ void __launch_bounds__(256) k_fmm_pairs(Tree t, Cols c, FmmNodes fn, 
         cb1 = t.child_begin[~v1];
         ce1 = t.child_end[~v1];
         mode = 2;
-        nemit = ce1 - cb1;
+        if(PRUNE) {
+          keep = 0;
+          for(int a = cb1; a < ce1; ++a) keep |= (cell_in_range(t, a, own_lo, own_hi) ? 1u : 0u) << (a - cb1);
+        }
+        nemit = PRUNE ? __popc(keep) : ce1 - cb1;
       }
       else {
         cb2 = t.child_begin[~v2];
@@ -152,11 +171,16 @@ __global__ void __launch_bounds__(256) k_fmm_pairs(Tree t, Cols c, FmmNodes fn, 
   }
   if(mode == 1) {
     // (k1,k1), then (k1,k2) and (k2,k1) for k2 > k1: every ordered pair of children
-    for(int a = cb1; a < ce1; ++a)
+    for(int a = cb1; a < ce1; ++a) {
+      if(PRUNE && !((keep >> (a - cb1)) & 1u)) continue;
       for(int b = cb1; b < ce1; ++b) out[o++] = ((uint64_t)(uint32_t)a << 32) | (uint32_t)b;
+    }
   }
   else if(mode == 2) {
-    for(int a = cb1; a < ce1; ++a) out[o++] = ((uint64_t)(uint32_t)a << 32) | c2;
+    for(int a = cb1; a < ce1; ++a) {
+      if(PRUNE && !((keep >> (a - cb1)) & 1u)) continue;
+      out[o++] = ((uint64_t)(uint32_t)a << 32) | c2;
+    }
   }
   else {
     for(int b = cb2; b < ce2; ++b) out[o++] = ((uint64_t)c1 << 32) | (uint32_t)b;
@@ -171,9 +195,9 @@ __global__ void __launch_bounds__(256) k_leaf_parent(Tree t, int64_t nc, int32_t
 }
 
 // fmm::fmm_c2p / interaction_c2p (fmm.h:95-120) for every ancestor that received an interaction
-__global__ void __launch_bounds__(256) k_fmm_c2p(Tree t, Cols c, FmmNodes fn, const int32_t * __restrict__ leaf_parent, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(i >= n) return;
+__global__ void __launch_bounds__(256) k_fmm_c2p(Tree t, Cols c, FmmNodes fn, const int32_t * __restrict__ leaf_parent, int64_t lo, int64_t hi) {
+  const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= hi) return;
   double x[3], g[3] = {0.0, 0.0, 0.0}, pot = 0.0;
 #pragma unroll
   for(int d = 0; d < 3; ++d) x[d] = c.f[F_POS + d][i];
@@ -194,10 +218,15 @@ __global__ void __launch_bounds__(256) k_fmm_c2p(Tree t, Cols c, FmmNodes fn, co
 }
 
 void gravitation_fmm(System & s) {
+  if(s.comm) dist_gravitation_fmm(s);
+  else gravitation_fmm_range(s, 0, s.n);
+}
+
+void gravitation_fmm_range(System & s, int64_t own_lo, int64_t own_hi) {
   if(s.dim != 3) throw std::runtime_error("fmm needs 3 dimensions (bodies_system.h:283)");
-  if(s.comm) throw std::runtime_error("FMM gravity on several ranks is not implemented yet");
   if(!s.tree_valid) throw std::runtime_error("gravitation_fmm before update_iteration");
   const int64_t n = s.n;
+  const bool prune = own_lo > 0 || own_hi < n;
   const Tree & t = s.tree;
   const int nn = std::max(t.nnodes, 1);
   // node accumulators: pc, fc[3], affected
@@ -221,8 +250,12 @@ void gravitation_fmm(System & s) {
     const int64_t take = std::min<int64_t>(top, FMM_CHUNK);
     const uint64_t * in = s.b_fmm_stack.as<uint64_t>() + (top - take);
     FSPH_CUDA_OK(cudaMemsetAsync(cnt, 0, 8, s.stream));
-    FSPH_LAUNCH(k_fmm_pairs, (unsigned)((take + 255) / 256), 256, s.stream, t, s.cols(), fn, in, take, s.b_fmm_out.as<uint64_t>(), cnt,
-      (unsigned long long)out_cap, s.par.fmm_macangle, s.par.gravitational_constant, status);
+    if(prune)
+      FSPH_LAUNCH((k_fmm_pairs<true>), (unsigned)((take + 255) / 256), 256, s.stream, t, s.cols(), fn, in, take, s.b_fmm_out.as<uint64_t>(), cnt,
+        (unsigned long long)out_cap, s.par.fmm_macangle, s.par.gravitational_constant, status, own_lo, own_hi);
+    else
+      FSPH_LAUNCH((k_fmm_pairs<false>), (unsigned)((take + 255) / 256), 256, s.stream, t, s.cols(), fn, in, take, s.b_fmm_out.as<uint64_t>(), cnt,
+        (unsigned long long)out_cap, s.par.fmm_macangle, s.par.gravitational_constant, status, own_lo, own_hi);
     unsigned long long nout = 0;
     uint32_t st = 0;
     FSPH_CUDA_OK(cudaMemcpyAsync(&nout, cnt, 8, cudaMemcpyDeviceToHost, s.stream));
@@ -243,7 +276,7 @@ void gravitation_fmm(System & s) {
   s.b_tmp[0].reserve((size_t)n * 4);
   int32_t * leaf_parent = s.b_tmp[0].as<int32_t>();
   FSPH_LAUNCH(k_leaf_parent, (unsigned)((t.ncells + 255) / 256), 256, s.stream, t, (int64_t)t.ncells, leaf_parent);
-  FSPH_LAUNCH(k_fmm_c2p, (unsigned)((n + 255) / 256), 256, s.stream, t, s.cols(), fn, leaf_parent, n);
+  FSPH_LAUNCH(k_fmm_c2p, (unsigned)((own_hi - own_lo + 255) / 256), 256, s.stream, t, s.cols(), fn, leaf_parent, own_lo, own_hi);
   FSPH_CUDA_OK(cudaGetLastError());
 }
 

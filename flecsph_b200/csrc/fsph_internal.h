@@ -281,6 +281,9 @@ void periodic_walls(System & s);                // boundary.h:45-248 as used by 
 
 // ---- fsph_fmm.cu ----------------------------------------------------------------------------
 void gravitation_fmm(System & s);               // bodies_system.h:282 -> tree_topology.h:448-795 + fmm.h
+// the same walk restricted to sink cells that hold bodies of the index range [own_lo, own_hi) (a rank's share)
+void gravitation_fmm_range(System & s, int64_t own_lo, int64_t own_hi);
+void release_buffers(System & s);               // every device buffer of a system
 
 // ---- fsph_apply.cu --------------------------------------------------------------------------
 void apply(System & s, int op);                  // integration.h, default_physics.h element-wise
@@ -317,6 +320,7 @@ void dist_all_gather_host(System & s, const void * in, void * out, size_t bytes)
 void dist_update_iteration(System & s);          // bodies_system.h:152-229 with size > 1 (psort + tree exchange)
 void dist_refresh_ghosts(System & s);            // bodies_system.h:273 reset_ghosts with size > 1
 void dist_drop_ghosts(System & s);
+void dist_gravitation_fmm(System & s);           // gravitation_fmm with size > 1
 void dist_release(System & s);
 
 }  // namespace fsph

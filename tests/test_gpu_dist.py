@@ -148,6 +148,32 @@ def test_steps_match_single_rank(name, kw, nranks, mode, nsteps):
         S.close()
 
 
+@pytest.mark.parametrize("nranks,mode", [(2, "random"), (3, "chunks"), (4, "random")])
+def test_fmm_gravity_matches_single_rank(nranks, mode):
+    """newtonian_3d configuration (collapse: hydro + FMM gravity) decomposed: every rank gathers the global body set,
+    builds the global tree and walks the sink cells of its own bodies -- the interaction set of one rank."""
+    f, par, dim = case("collapse", nx=16, fmm=1)
+    S = make_system("cuda", f, par, dim)
+    L = make_ranks(f, par, dim, nranks, mode)
+    names = ["pos", "vel", "rho", "P", "u", "acc", "gacc", "gpot", "dudt", "h"]
+    try:
+        for it in range(3):
+            S.step(initial=(it == 0))
+            L.call(lambda r, s: s.step(initial=(it == 0)))
+        a, b = by_id(S, names), gathered(L, names)
+        assert np.array_equal(a["id"], b["id"])
+        assert np.abs(a["gacc"]).max() > 0
+        for nm in names:
+            e = rel_err(b[nm], a[nm])
+            assert e <= 1e-10, "%s: max rel err %g" % (nm, e)
+        want = S.get_all(capi.GET_TOTAL_ENERGY)
+        for got in L.call(lambda r, s: s.get_all(capi.GET_TOTAL_ENERGY)):
+            assert np.allclose(got, want, rtol=1e-11)
+    finally:
+        L.close()
+        S.close()
+
+
 def test_conservation_100_steps_two_ranks():
     """SURVEY.md 8 / north star: conserved energy within 1e-6 over 100 steps, also when decomposed."""
     f, par, dim = case("sedov", nx=20)
