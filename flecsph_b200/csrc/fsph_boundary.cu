@@ -140,7 +140,10 @@ static void resize_keep(System & s, int64_t n_new, int64_t n_keep) {
 
 template<int D>
 static void periodic_walls_t(System & s) {
-  if(s.comm) throw std::runtime_error("periodic boundaries on several ranks are not implemented yet");
+  // several ranks: every rank copies its own bodies (the copies are owned bodies that the partition step then
+  // distributes like any other); halo from the global largest h, ids from the global count of real bodies plus the
+  // copy counts of the lower ranks (boundary.h:124-126, 218-243)
+  if(s.has_ghosts) dist_drop_ghosts(s);
   const unsigned nb0 = (unsigned)((s.n + 255) / 256);
   // 1. pboundary_clean
   {
@@ -173,7 +176,11 @@ static void periodic_walls_t(System & s) {
     b.hi[d] = 0.5 * ext[d];
     b.periodic[d] = d < D ? per[d] : 0;
   }
-  b.halo = 2.5 * max_h(s);
+  {
+    double hm[3] = {max_h(s), 0, 0};
+    if(s.comm) global_combine(s, 1 /* RED_MAX_H */, hm);
+    b.halo = 2.5 * hm[0];
+  }
   FSPH_LAUNCH((k_teleport<D>), nb, 256, s.stream, s.cols(), n, b);
   // 4. count, scan, emit
   s.b_cnt0.reserve((size_t)(n + 1) * 4);
@@ -184,6 +191,16 @@ static void periodic_walls_t(System & s) {
   FSPH_CUDA_OK(cudaMemcpyAsync(&nwall, cnt + n, 4, cudaMemcpyDeviceToHost, s.stream));
   FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
   if(n + (int64_t)nwall >= (int64_t(1) << 31)) throw std::runtime_error("bodies + WALL copies exceed 2^31");
+  int64_t id_base = n;
+  if(s.comm) {
+    const int P = s.comm->nranks, R = s.comm->rank;
+    int64_t mine[2] = {n, (int64_t)nwall};
+    std::vector<int64_t> all((size_t)2 * P);
+    dist_all_gather_host(s, mine, all.data(), sizeof(mine));
+    id_base = 0;
+    for(int q = 0; q < P; ++q) id_base += all[(size_t)2 * q];
+    for(int q = 0; q < R; ++q) id_base += all[(size_t)2 * q + 1];
+  }
   if(nwall) {
     resize_keep(s, n + nwall, n);
     std::vector<std::pair<DevBuf *, int>> cols;
@@ -194,7 +211,7 @@ static void periodic_walls_t(System & s) {
       if(c.second == 8) cc.p8[cc.n8++] = c.first->as<uint64_t>();
       else cc.p4[cc.n4++] = c.first->as<uint32_t>();
     }
-    FSPH_LAUNCH((k_wall_emit<D>), (unsigned)((n + 127) / 128), 128, s.stream, s.cols(), n, b, cnt, cc, n);
+    FSPH_LAUNCH((k_wall_emit<D>), (unsigned)((n + 127) / 128), 128, s.stream, s.cols(), n, b, cnt, cc, id_base);
     s.n = n + nwall;
   }
   s.n_owned = s.n;

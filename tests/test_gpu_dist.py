@@ -174,6 +174,37 @@ def test_fmm_gravity_matches_single_rank(nranks, mode):
         S.close()
 
 
+@pytest.mark.parametrize("nranks,mode,kw", [(2, "random", dict(n=3000, dim=3, seed=21, h_jitter=0.1, stray=0.01)),
+                                            (3, "chunks", dict(n=3000, dim=3, seed=22, periodic=(1, 0, 1), box=(1.0, 0.8, 1.2))),
+                                            (2, "random", dict(n=2500, dim=2, seed=23, h_jitter=0.1))])
+def test_periodic_matches_single_rank(nranks, mode, kw):
+    """Periodic WALL copies with several ranks: every rank copies its own bodies, the partition distributes the copies;
+    the real bodies must evolve exactly as on one rank (the copies' ids differ: they are numbered per rank)."""
+    f, par, dim = case("periodic", **kw)
+    S = make_system("cuda", f, par, dim)
+    L = make_ranks(f, par, dim, nranks, mode)
+    names = ["pos", "vel", "rho", "P", "u", "acc", "dedt", "h", "vsig", "dt", "type"]
+    try:
+        for it in range(3):
+            S.step(initial=(it == 0))
+            L.call(lambda r, s: s.step(initial=(it == 0)))
+        assert sum(L.call(lambda r, s: s.nbodies())) == S.nbodies()
+        a, b = by_id(S, names), gathered(L, names)
+        ra, rb = a["type"] == 0, b["type"] == 0
+        assert np.array_equal(a["id"][ra], b["id"][rb]) and ra.sum() == len(f["mass"])
+        for nm in names[:-1]:
+            e = rel_err(b[nm][rb], a[nm][ra])
+            assert e <= 1e-10, "%s: max rel err %g" % (nm, e)
+        # the copies carry the same states too (matched by position: ids are per-rank)
+        oa = np.lexsort(np.round(a["pos"][~ra], 8).T)
+        ob = np.lexsort(np.round(b["pos"][~rb], 8).T)
+        assert np.allclose(a["pos"][~ra][oa], b["pos"][~rb][ob], rtol=0, atol=1e-11)
+        assert rel_err(b["rho"][~rb][ob], a["rho"][~ra][oa]) <= 1e-10
+    finally:
+        L.close()
+        S.close()
+
+
 def test_conservation_100_steps_two_ranks():
     """SURVEY.md 8 / north star: conserved energy within 1e-6 over 100 steps, also when decomposed."""
     f, par, dim = case("sedov", nx=20)
