@@ -32,7 +32,10 @@ constexpr int SR_NT = 64;       // threads per CTA of the export kernel
 #endif
 constexpr uint32_t SR_SPREAD = FSPH_SR_SPREAD;
 constexpr int SW_QCAP = 4096;   // node frontier capacity per level of the super-cell walk
-constexpr int SR_QCAP = 768;    // node frontier capacity per level
+#ifndef FSPH_SR_QCAP
+#define FSPH_SR_QCAP 2048
+#endif
+constexpr int SR_QCAP = FSPH_SR_QCAP;   // node frontier capacity per level (wide kernels: quintic at eta 1.2 reaches ~1000)
 constexpr int SR_TILE = 256;    // candidates per shared-memory tile
 constexpr double GEO_TOL = 2.220446049250313e-16 * 10.;  // tree_geometry.h:57
 
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
   __shared__ double gx[D][32 * NW];
   __shared__ double gh[32 * NW];
   __shared__ int32_t queue[2][SR_QCAP];
-  __shared__ uint32_t qres[SR_QCAP];   // per frontier node: node-children mask | candidate-children mask << 8
+  __shared__ uint16_t qres[SR_QCAP];   // per frontier node: node-children mask | candidate-children mask << 8
   __shared__ uint32_t scan_sm[NW];
   __shared__ double red_sm[NW][2 * D + 1];
   __shared__ unsigned long long base_sm[2];
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
             }
           }
         }
-        qres[j] = cand_mask;
+        qres[j] = (uint16_t)cand_mask;
         my_cands += __popc(cand_mask);
       }
       // ---- one block scan per level: output order = (thread, frontier slot, child), fixed => deterministic --
@@ -430,7 +433,7 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
             }
           }
         }
-        qres[j] = node_mask | (cand_mask << 8);
+        qres[j] = (uint16_t)(node_mask | (cand_mask << 8));
         my_nodes += __popc(node_mask);
         my_cands += __popc(cand_mask);
       }
@@ -532,9 +535,6 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
     for(int d = 0; d < D; ++d) a0[d] = active ? gx[d][tid] : 0.0;
     if(active) { h0 = gh[tid]; h0 = h0 * h0; }
     int cnt0 = 0;
-#ifdef FSPH_SR_NOPAIR
-    if(C > 0) continue;  // timing experiment: walk only
-#endif
     for(int tb = 0; tb < C; tb += SR_TILE) {
       const int tc = min(SR_TILE, C - tb);
       __syncthreads();

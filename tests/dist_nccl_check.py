@@ -13,14 +13,16 @@ import torch.distributed as dist
 from flecsph_b200 import capi
 from common import make_system, case, rel_err
 
-FIELDS = ["pos", "vel", "rho", "P", "u", "e", "cs", "acc", "dedt", "h", "vsig", "dt"]
+FIELDS = ["pos", "vel", "rho", "P", "u", "e", "cs", "acc", "dedt", "dudt", "gacc", "gpot", "h", "vsig", "dt"]
 
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    f, par, dim = case("sedov", nx=int(os.environ.get("FSPH_NX", "40")))
+    # FSPH_CASE=collapse: newtonian configuration (hydro + FMM gravity over the gathered global tree)
+    which = os.environ.get("FSPH_CASE", "sedov")
+    f, par, dim = case(which, nx=int(os.environ.get("FSPH_NX", "40")), fmm=1)
     n = len(f["mass"])
     owner = np.random.default_rng(11).integers(0, world, n)
     mine = {k: np.ascontiguousarray(v[owner == rank]) for k, v in f.items()}

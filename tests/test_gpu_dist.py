@@ -233,5 +233,6 @@ def test_nccl_ranks():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(ng, 4)), "--master-addr", "127.0.0.1",
            "--master-port", "29531", os.path.join(root, "tests", "dist_nccl_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "NCCL DECOMPOSITION OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    for which in ("sedov", "collapse"):
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, FSPH_CASE=which, FSPH_NX="32"))
+        assert r.returncode == 0 and "NCCL DECOMPOSITION OK" in r.stdout, which + "\n" + r.stdout[-3000:] + r.stderr[-3000:]
