@@ -20,9 +20,12 @@
 
 namespace fsph {
 
-// 1: work cells scan a flat node list collected once per super cell (k_super_walk) instead of walking from the root.
-// Measured on B200 (64 M Sedov): the walk part of the search is 58 + 11 ms against 53 ms for the per-cell walk (four
-// times as many node tests outweigh the saved levels), so the default stays 0; kept because results are identical.
+// 0: every work cell walks the tree from the root.
+// 1: work cells scan a flat node list collected once per super cell (k_super_walk).  Measured on B200 (64 M Sedov): the
+//    walk part of the search is 58 + 11 ms against 53 ms for mode 0 (four times as many node tests outweigh the saved
+//    levels).
+// 2: work cells walk from a frontier seeded by their super cell's list (the top levels of the walk are done once per
+//    super cell).  All three give identical neighbour sets (tests).
 #ifndef FSPH_SEARCH_TWO_LEVEL
 #define FSPH_SEARCH_TWO_LEVEL 0
 #endif
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
       grad = t.radius[gnode];
     }
     int32_t * cout = MODE == 1 ? sr.cand + sr.cand_off[g] : (MODE == 2 ? scratch + (size_t)blockIdx.x * scratch_cap : nullptr);
-#if !FSPH_SEARCH_TWO_LEVEL
+#if FSPH_SEARCH_TWO_LEVEL == 0
     if(tid == 0) queue[0][0] = 0;  // the root node
 #endif
     // Tight box of G's positions and max h: an extra, conservative candidate cull (it only drops leaves that
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
     }
     // hmax^2 with a safety margin for the quick node reject (distance between a node box and G's tight box)
     const double ghmax2 = ghmax * ghmax * (1.0 + 1e-9);
-#if FSPH_SEARCH_TWO_LEVEL
+#if FSPH_SEARCH_TWO_LEVEL == 1
     uint32_t ncands = 0;
     bool overflow = false;
     // two-level walk: the nodes that can hold candidates of G were collected once for G's super cell (k_super_walk);
@@ -350,11 +353,29 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
     int ncur = 1, cur = 0;
     uint32_t ncands = 0;
     bool overflow = false;
+#if FSPH_SEARCH_TWO_LEVEL == 2
+    // The walk starts from the frontier collected once for G's super cell (k_super_walk, SEED): the nodes of about
+    // super-cell size around it, plus bigger nodes that have leaf children (flagged: their node children are in the
+    // list themselves).  A node's ancestors need no test of their own (boxes are nested, both predicates are monotone
+    // in the box), so the leaves reached are exactly those of the walk from the root -- without its top levels.
+    {
+      const int sidx = sr.wc_super[g];
+      const uint64_t sl_lo = sr.sl_off[sidx];
+      ncur = (int)(sr.sl_off[sidx + 1] - sl_lo);
+      if(ncur > SR_QCAP) {
+        if(tid == 0) atomicOr(status, (uint32_t)ERR_QUEUE_OVERFLOW);
+        ncur = SR_QCAP;
+      }
+      for(int j = tid; j < ncur; j += NT) queue[0][j] = sr.sl_nodes[sl_lo + j];
+      __syncthreads();
+    }
+#endif
     while(ncur > 0) {
       // ---- phase A: test every frontier node (results to shared memory), count children / candidates -------
       uint32_t my_nodes = 0, my_cands = 0;
       for(int j = tid; j < ncur; j += NT) {
-        const int nd = queue[cur][j];
+        const int nd_raw = queue[cur][j];
+        const int nd = nd_raw & 0x3fffffff;
         const NodeRec rec = t.noderec[nd];
         uint32_t node_mask = 0, cand_mask = 0;
         bool ok = true;
@@ -394,7 +415,7 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
         if(ok) {
           const int cb = rec.child_begin;
           const uint32_t leafmask = rec.leafmask;
-          node_mask = ((1u << rec.nchild) - 1u) & ~leafmask;
+          node_mask = (nd_raw & 0x40000000) ? 0u : (((1u << rec.nchild) - 1u) & ~leafmask);
           // leaf children in two batches of four: all loads of a batch are issued before the first use
 #pragma unroll
           for(int half = 0; half < ((1 << D) + 3) / 4; ++half) {
@@ -446,7 +467,7 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
       for(int j = tid; j < ncur; j += NT) {
         const uint32_t r = qres[j];
         if(r == 0) continue;
-        const int nd = queue[cur][j];
+        const int nd = queue[cur][j] & 0x3fffffff;
         const NodeRec rec = t.noderec[nd];
         uint32_t node_mask = r & 0xffu, cand_mask = r >> 8;
         while(node_mask) {
@@ -647,11 +668,18 @@ __global__ void __launch_bounds__(64) k_super_walk(Tree t, Cols c, Search sr, ui
       uint32_t r = 0;
       if(dd <= hmax2) {
         const uint32_t node_mask = ((1u << rec.nchild) - 1u) & ~rec.leafmask;
+#if FSPH_SEARCH_TWO_LEVEL == 2
+        // seed lists: nodes of at most super-cell size end the descent and are listed whole; bigger nodes are
+        // descended and listed (flagged "leaf children only") when they have leaf children
+        if(t.sub[queue[cur][j]] <= SUPER_ENTITIES) r = 0x80u;
+        else r = (uint32_t)__popc(node_mask) | (rec.leafmask ? 0xc0u : 0u);
+#else
         r = (uint32_t)__popc(node_mask) | (rec.leafmask ? 0x80u : 0u);
+#endif
       }
       qres[j] = (uint8_t)r;
-      my_nodes += r & 0x7fu;
-      my_list += r >> 7;
+      my_nodes += r & 0x3fu;
+      my_list += (r >> 7) & 1u;
     }
     uint32_t total;
     const uint32_t ex = block_scan_u32<NT>(my_nodes | (my_list << 16), total, scan_sm);
@@ -661,7 +689,7 @@ __global__ void __launch_bounds__(64) k_super_walk(Tree t, Cols c, Search sr, ui
       const uint32_t r = qres[j];
       if(r == 0) continue;
       const int nd = queue[cur][j];
-      if(r & 0x7fu) {
+      if(r & 0x3fu) {
         const NodeRec rec = t.noderec[nd];
         uint32_t node_mask = ((1u << rec.nchild) - 1u) & ~rec.leafmask;
         while(node_mask) {
@@ -672,7 +700,7 @@ __global__ void __launch_bounds__(64) k_super_walk(Tree t, Cols c, Search sr, ui
         }
       }
       if(r & 0x80u) {
-        if(MODE == 1) out[lpos] = nd;
+        if(MODE == 1) out[lpos] = (r & 0x40u) ? (nd | 0x40000000) : nd;
         ++lpos;
       }
     }
