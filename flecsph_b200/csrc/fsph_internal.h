@@ -26,7 +26,7 @@ enum F64 {
 
 constexpr int SUB_ENTITIES = 128;  // tree_topology.h:2121
 #ifndef FSPH_SUPER_ENTITIES
-#define FSPH_SUPER_ENTITIES 1024
+#define FSPH_SUPER_ENTITIES 4096
 #endif
 constexpr int SUPER_ENTITIES = FSPH_SUPER_ENTITIES;  // bodies per super cell of the two-level neighbour walk
 constexpr int MAX_LEVELS = 66;

@@ -25,9 +25,10 @@ namespace fsph {
 //    walk part of the search is 58 + 11 ms against 53 ms for mode 0 (four times as many node tests outweigh the saved
 //    levels).
 // 2: work cells walk from a frontier seeded by their super cell's list (the top levels of the walk are done once per
-//    super cell).  All three give identical neighbour sets (tests).
+//    super cell of <= 4096 bodies): search 86.3 ms against 92.1 ms for mode 0 (lists 2.4 ms).  Default.
+// All three give identical neighbour sets (the GPU test-suite passes with each).
 #ifndef FSPH_SEARCH_TWO_LEVEL
-#define FSPH_SEARCH_TWO_LEVEL 0
+#define FSPH_SEARCH_TWO_LEVEL 2
 #endif
 constexpr int SR_NT = 64;       // threads per CTA of the export kernel
 #ifndef FSPH_SR_SPREAD
