@@ -31,6 +31,12 @@ namespace fsph {
 #define FSPH_SEARCH_TWO_LEVEL 2
 #endif
 constexpr int SR_NT = 64;       // threads per CTA of the export kernel
+// 1: decide the pair predicate in fp32 (cell-centred coordinates, rigorous error margin, exact fp64 evaluation when the
+// fp32 result is inside the margin).  Same neighbour sets (tests), but SLOWER on B200 (search 97.8 vs 86.5 ms at 64 M):
+// the pair tests are issue-bound, not fp64-bound, and the filter adds instructions and shared memory.  Default 0.
+#ifndef FSPH_SR_FP32_FILTER
+#define FSPH_SR_FP32_FILTER 0
+#endif
 #ifndef FSPH_SR_SPREAD
 #define FSPH_SR_SPREAD 64
 #endif
@@ -134,6 +140,11 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
   __shared__ int rep_sm[1 << D];
   __shared__ double cx[FILL ? D : 1][FILL ? SR_TILE : 1];
   __shared__ double ch2[FILL ? SR_TILE : 1];
+#if FSPH_SR_FP32_FILTER
+  __shared__ float cxf[FILL ? D : 1][FILL ? SR_TILE : 1];
+  __shared__ float ch2f[FILL ? SR_TILE : 1];
+  __shared__ uint32_t rmax_sm[2];
+#endif
 
   const int tid = threadIdx.x;
   // every CTA walks a contiguous run of work cells (Morton neighbours: the upper tree levels stay in L1/L2)
@@ -550,25 +561,64 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
       mo = sr.mask_off[g];
     }
     // ---- pair tests ------------------------------------------------------------------------------------
+    // The predicate is decided in fp32 on coordinates relative to the cell centre whenever the fp32 result is farther
+    // from the threshold than a rigorous error bound (|s32 - s| <= 100 eps R^2 for points within R of the centre per
+    // axis; 2^-17 R^2 is used), and evaluated exactly in fp64 otherwise: same outcome as the all-fp64 test at a
+    // fraction of the fp64-pipe work (the fp64 pipe is the scarce one: it also runs every sweep).
     const int C = (int)ncands;
     const bool active = tid < P;
     double a0[D], h0 = 0.0;
 #pragma unroll
     for(int d = 0; d < D; ++d) a0[d] = active ? gx[d][tid] : 0.0;
     if(active) { h0 = gh[tid]; h0 = h0 * h0; }
+#if FSPH_SR_FP32_FILTER
+    double ctr[D];
+    float a0f[D], extf = 0.f;
+#pragma unroll
+    for(int d = 0; d < D; ++d) {
+      ctr[d] = 0.5 * (tmn[d] + tmx[d]);
+      a0f[d] = (float)(a0[d] - ctr[d]);
+      extf = fmaxf(extf, (float)(tmx[d] - tmn[d]));   // >= twice the largest |x_k - ctr| component
+    }
+    const float h0f = (float)h0;
+    if(tid == 0) { rmax_sm[0] = 0u; rmax_sm[1] = 0u; }
+#endif
     int cnt0 = 0;
     for(int tb = 0; tb < C; tb += SR_TILE) {
       const int tc = min(SR_TILE, C - tb);
       __syncthreads();
+#if FSPH_SR_FP32_FILTER
+      const int par = (tb / SR_TILE) & 1;
+      if(tid == 0) rmax_sm[par ^ 1] = 0u;
+      float lm = 0.f;
+#endif
       for(int i = tid; i < tc; i += NT) {
         const int p = sr.cand[co + tb + i];
 #pragma unroll
-        for(int d = 0; d < D; ++d) cx[d][i] = c.f[F_POS + d][p];
+        for(int d = 0; d < D; ++d) {
+          const double x = c.f[F_POS + d][p];
+          cx[d][i] = x;
+#if FSPH_SR_FP32_FILTER
+          const float wf = (float)(x - ctr[d]);
+          cxf[d][i] = wf;
+          lm = fmaxf(lm, fabsf(wf));
+#endif
+        }
         const double hh = c.f[F_H][p];
         ch2[i] = hh * hh;
+#if FSPH_SR_FP32_FILTER
+        ch2f[i] = (float)(hh * hh);
+#endif
       }
+#if FSPH_SR_FP32_FILTER
+      atomicMax(&rmax_sm[par], __float_as_uint(lm));
+#endif
       __syncthreads();
       if(!active) continue;
+#if FSPH_SR_FP32_FILTER
+      const float Rm = fmaxf(__uint_as_float(rmax_sm[par]), extf);
+      const float marg = Rm * Rm * (1.0f / 131072.0f);
+#endif
       const int nw = (tc + 31) >> 5;
       for(int w = 0; w < nw; ++w) {
         const int nb = min(32, tc - w * 32);
@@ -577,6 +627,19 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
 #pragma unroll 8
         for(int b = 0; b < nb; ++b) {
           const int ci = w * 32 + b;
+#if FSPH_SR_FP32_FILTER
+          const float f0 = a0f[0] - cxf[0][ci];
+          float sf = f0 * f0;
+#pragma unroll
+          for(int d = 1; d < D; ++d) {
+            const float fd = a0f[d] - cxf[d][ci];
+            sf = sf + fd * fd;
+          }
+          const float thr = fmaxf(h0f, ch2f[ci]);
+          const float mt = marg + thr * 2.4e-7f;
+          bool in = sf <= thr - mt;
+          if(!in && !(sf > thr + mt)) {
+#endif
           const double e0 = cx[0][ci];
           double s0 = (a0[0] - e0) * (a0[0] - e0);
 #pragma unroll
@@ -584,7 +647,13 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
             const double ed = cx[d][ci];
             s0 = s0 + (a0[d] - ed) * (a0[d] - ed);
           }
+#if FSPH_SR_FP32_FILTER
+            in = s0 <= fmax(h0, ch2[ci]);
+          }
+          m0 |= (uint32_t)in << b;
+#else
           m0 |= (uint32_t)(s0 <= fmax(h0, ch2[ci])) << b;
+#endif
         }
         sr.mask[mo + (uint64_t)((tb >> 5) + w) * Ppad + tid] = m0;
         cnt0 += __popc(m0);
