@@ -673,7 +673,7 @@ int32_t fsph_neighbor_lists(fsph_system * s, int64_t * offsets, int64_t * ids) {
   });
 }
 
-uint64_t fsph_launch_count(void) { return fsph::g_launches; }
+uint64_t fsph_launch_count(void) { return fsph::g_launches.load(); }
 
 // ---- several ranks -------------------------------------------------------------------------------------------
 int32_t fsph_comm_unique_id(char * out128) {

@@ -66,10 +66,9 @@ struct Dist {
   std::vector<uint64_t> split_raw;  // the same before the alignment to work cells (kept from step to step)
   std::vector<size_t> send_cnt, send_off, recv_cnt, recv_off;  // halo plan, in bodies
   int64_t nsend = 0, nghost = 0;
-  DevBuf send_idx, ghost_pos, sendbuf, recvbuf, small, small2, bitmap, bitmap_all, nmask, emask, flags, ex, inv;
+  DevBuf send_idx, ghost_pos, sendbuf, recvbuf, small, small2, bitmap, bitmap_all, nmask, emask, flags, ex;
   DevBuf recs_send, recs_recv, path, path_all, counters;
-  std::vector<double> hmax;
-  std::vector<double> rlo, rhi;
+  std::vector<double> rlo, rhi;  // box of every rank's bodies before the exchange (range all-gather)
   DDGeom geom;
   System * fmm_sys = nullptr;  // the gathered global body set + tree of gravitation_fmm on several ranks
 };
@@ -78,7 +77,7 @@ void dist_release(System & s) {
   if(!s.dist) return;
   Dist & d = *s.dist;
   DevBuf * all[] = {&d.send_idx, &d.ghost_pos, &d.sendbuf, &d.recvbuf, &d.small, &d.small2, &d.bitmap, &d.bitmap_all, &d.nmask, &d.emask,
-    &d.flags, &d.ex, &d.inv, &d.recs_send, &d.recs_recv, &d.path, &d.path_all, &d.counters};
+    &d.flags, &d.ex, &d.recs_send, &d.recs_recv, &d.path, &d.path_all, &d.counters};
   for(DevBuf * b : all) b->release();
   if(d.fmm_sys) {
     release_buffers(*d.fmm_sys);
@@ -215,11 +214,6 @@ __global__ void __launch_bounds__(256) k_pack(const T * __restrict__ in, const u
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(i < n) out[i] = in[idx[i]];
 }
-__global__ void __launch_bounds__(256) k_unpack8(const uint64_t * __restrict__ in, const uint32_t * __restrict__ pos, int64_t n,
-  uint64_t * __restrict__ out) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(i < n) out[pos[i]] = in[i];
-}
 struct FieldPtrs {
   uint64_t * p[16];
 };
@@ -236,14 +230,6 @@ __global__ void __launch_bounds__(256) k_mark_ghost(int32_t * __restrict__ type,
   int64_t i = b + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(i < e) type[i] |= TYPE_GHOST;
 }
-__global__ void __launch_bounds__(256) k_maps(const uint32_t * __restrict__ perm, int64_t n, int64_t n_owned, uint32_t * __restrict__ inv,
-  uint32_t * __restrict__ ghost_pos) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(i >= n) return;
-  const uint32_t o = perm[i];
-  inv[o] = (uint32_t)i;
-  if((int64_t)o >= n_owned) ghost_pos[o - n_owned] = (uint32_t)i;
-}
 // merged order [ghosts of lower ranks | owned | ghosts of higher ranks] from storage order [owned | ghosts by sender rank]
 __global__ void __launch_bounds__(256) k_merge_perm(uint32_t * __restrict__ perm, int64_t n, int64_t n_glow, int64_t n_owned) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -257,10 +243,6 @@ __global__ void __launch_bounds__(256) k_ghost_pos(uint32_t * __restrict__ pos, 
 __global__ void __launch_bounds__(256) k_shift_idx(uint32_t * __restrict__ idx, int64_t n, uint32_t by) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(i < n) idx[i] += by;
-}
-__global__ void __launch_bounds__(256) k_remap(uint32_t * __restrict__ idx, int64_t n, const uint32_t * __restrict__ inv) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(i < n) idx[i] = inv[idx[i]];
 }
 __global__ void __launch_bounds__(256) k_count_bits(const uint32_t * __restrict__ mask, int64_t n, int P, unsigned long long * __restrict__ cnt) {
   __shared__ unsigned int sm[DD_MAX_RANKS];

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <atomic>
 #include <vector>
 #include <utility>
 #include <stdexcept>
@@ -231,7 +232,7 @@ struct PhaseScope {
   } while(0)
 
 // every kernel launch of the library goes through this macro (bench.py reports the count as gpu_launches)
-extern unsigned long long g_launches;
+extern std::atomic<unsigned long long> g_launches;
 #define FSPH_LAUNCH(kernel, grid, block, stream, ...)            \
   do {                                                           \
     ++fsph::g_launches;                                          \

@@ -9,7 +9,7 @@
 
 namespace fsph {
 
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
 void DevBuf::reserve(size_t bytes) {
   if(bytes <= cap) return;
