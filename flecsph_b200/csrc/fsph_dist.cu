@@ -67,7 +67,7 @@ struct Dist {
   std::vector<size_t> send_cnt, send_off, recv_cnt, recv_off;  // halo plan, in bodies
   int64_t nsend = 0, nghost = 0;
   DevBuf send_idx, ghost_pos, sendbuf, recvbuf, small, small2, bitmap, bitmap_all, nmask, emask, flags, ex;
-  DevBuf recs_send, recs_recv, path, path_all, counters;
+  DevBuf recs_send, recs_recv, path, path_all, counters, sel_idx, sel_mask;
   std::vector<double> rlo, rhi;  // box of every rank's bodies before the exchange (range all-gather)
   DDGeom geom;
   System * fmm_sys = nullptr;  // the gathered global body set + tree of gravitation_fmm on several ranks
@@ -77,7 +77,7 @@ void dist_release(System & s) {
   if(!s.dist) return;
   Dist & d = *s.dist;
   DevBuf * all[] = {&d.send_idx, &d.ghost_pos, &d.sendbuf, &d.recvbuf, &d.small, &d.small2, &d.bitmap, &d.bitmap_all, &d.nmask, &d.emask,
-    &d.flags, &d.ex, &d.recs_send, &d.recs_recv, &d.path, &d.path_all, &d.counters};
+    &d.flags, &d.ex, &d.recs_send, &d.recs_recv, &d.path, &d.path_all, &d.counters, &d.sel_idx, &d.sel_mask};
   for(DevBuf * b : all) b->release();
   if(d.fmm_sys) {
     release_buffers(*d.fmm_sys);
@@ -217,6 +217,34 @@ __global__ void __launch_bounds__(256) k_pack(const T * __restrict__ in, const u
 struct FieldPtrs {
   uint64_t * p[16];
 };
+struct ColPtrs8 { uint64_t * p[NF64 + 4]; };
+struct ColPtrs4 { uint32_t * p[4]; };
+// halo traffic of one peer, all live columns at once: out[col][body] = col[idx[body]]   (blockIdx.y = column)
+template<typename T, typename PT>
+__global__ void __launch_bounds__(256) k_pack_cols(PT f, const uint32_t * __restrict__ idx, int64_t n, T * __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n) out[(size_t)blockIdx.y * n + i] = reinterpret_cast<const T *>(f.p[blockIdx.y])[idx[i]];
+}
+template<typename T, typename PT>
+__global__ void __launch_bounds__(256) k_unpack_cols(PT f, int64_t dst, int64_t n, const T * __restrict__ in) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n) reinterpret_cast<T *>(f.p[blockIdx.y])[dst + i] = in[(size_t)blockIdx.y * n + i];
+}
+__global__ void __launch_bounds__(256) k_nonzero_flag(const uint32_t * __restrict__ mask, int64_t n, uint32_t * __restrict__ f) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n) f[i] = mask[i] != 0u;
+}
+// selected[k] = (index, mask) of the k-th element with a non-zero destination mask
+__global__ void __launch_bounds__(256) k_select(const uint32_t * __restrict__ mask, const uint32_t * __restrict__ f, const uint32_t * __restrict__ ex,
+  int64_t n, uint32_t * __restrict__ sel_idx, uint32_t * __restrict__ sel_mask) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n && f[i]) { sel_idx[ex[i]] = (uint32_t)i; sel_mask[ex[i]] = mask[i]; }
+}
+__global__ void __launch_bounds__(256) k_compact_sel(const uint32_t * __restrict__ f, const uint32_t * __restrict__ ex, int64_t n,
+  const uint32_t * __restrict__ sel_idx, uint32_t * __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n && f[i]) out[ex[i]] = sel_idx[i];
+}
 // refresh traffic of one peer: out[field][body] = col[field][idx[body]]  (blockIdx.y = field)
 __global__ void __launch_bounds__(256) k_pack_fields(FieldPtrs f, const uint32_t * __restrict__ idx, int64_t n, uint64_t * __restrict__ out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -410,11 +438,12 @@ __global__ void k_set_count(NodeBoxRec * out, const unsigned long long * cnt) {
   out[0].key = *cnt < (unsigned long long)DD_MAX_PATH ? *cnt : (unsigned long long)DD_MAX_PATH;
 }
 
+// records of the selected nodes sel_idx[k] (k < n) whose flag is set
 template<int D>
-__global__ void __launch_bounds__(256) k_emit_records(Tree t, const uint64_t * __restrict__ key, int nn, const uint32_t * __restrict__ f,
-  const uint32_t * __restrict__ ex, NodeBoxRec * __restrict__ out) {
-  const int nd = blockIdx.x * blockDim.x + threadIdx.x;
-  if(nd < nn && f[nd]) out[ex[nd]] = make_rec<D>(t, key, nd);
+__global__ void __launch_bounds__(256) k_emit_records(Tree t, const uint64_t * __restrict__ key, int64_t n, const uint32_t * __restrict__ sel_idx,
+  const uint32_t * __restrict__ f, const uint32_t * __restrict__ ex, NodeBoxRec * __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(k < n && f[k]) out[ex[k]] = make_rec<D>(t, key, (int)sel_idx[k]);
 }
 
 __device__ __forceinline__ void atomic_min_f64(double * p, double v) {
@@ -766,23 +795,37 @@ static void dist_update_iteration_t(System & s) {
   d.send_idx.reserve(std::max<size_t>(nsend, 1) * 4);
   d.recs_send.reserve(std::max<size_t>(nrs, 1) * sizeof(NodeBoxRec));
   {
+    // the bodies / nodes with any destination are few: select them once, then split the short lists per destination
     const int64_t m = std::max<int64_t>(n, nn);
     d.flags.reserve((size_t)(m + 1) * 4);
     d.ex.reserve((size_t)(m + 1) * 4);
     uint32_t * f = d.flags.as<uint32_t>();
     uint32_t * ex = d.ex.as<uint32_t>();
+    auto select = [&](const uint32_t * mask, int64_t cnt, DevBuf & bidx, DevBuf & bmask) -> int64_t {
+      FSPH_LAUNCH(k_nonzero_flag, blocks(cnt), 256, s.stream, mask, cnt, f);
+      exclusive_scan_u32(s, f, ex, cnt, nullptr);
+      uint32_t nsel = 0;
+      FSPH_CUDA_OK(cudaMemcpyAsync(&nsel, ex + cnt, 4, cudaMemcpyDeviceToHost, s.stream));
+      FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
+      bidx.reserve(std::max<size_t>(nsel, 1) * 4);
+      bmask.reserve(std::max<size_t>(nsel, 1) * 4);
+      if(nsel) FSPH_LAUNCH(k_select, blocks(cnt), 256, s.stream, mask, f, ex, cnt, bidx.as<uint32_t>(), bmask.as<uint32_t>());
+      return (int64_t)nsel;
+    };
+    const int64_t nsel_b = select(emask, n, d.sel_idx, d.sel_mask);
     for(int q = 0; q < P; ++q) {
-      if(d.send_cnt[q]) {
-        FSPH_LAUNCH(k_bit_flag, blocks(n), 256, s.stream, emask, n, q, f);
-        exclusive_scan_u32(s, f, ex, n, nullptr);
-        FSPH_LAUNCH(k_compact_idx, blocks(n), 256, s.stream, f, ex, n, d.send_idx.as<uint32_t>() + d.send_off[q]);
-      }
-      if(rs_cnt[q]) {
-        FSPH_LAUNCH(k_bit_flag, blocks(nn), 256, s.stream, nmask, (int64_t)nn, q, f);
-        exclusive_scan_u32(s, f, ex, nn, nullptr);
-        FSPH_LAUNCH((k_emit_records<D>), blocks(nn), 256, s.stream, s.tree, s.col_key.as<uint64_t>(), nn, f, ex,
-          d.recs_send.as<NodeBoxRec>() + rs_off[q]);
-      }
+      if(!d.send_cnt[q]) continue;
+      FSPH_LAUNCH(k_bit_flag, blocks(nsel_b), 256, s.stream, d.sel_mask.as<uint32_t>(), nsel_b, q, f);
+      exclusive_scan_u32(s, f, ex, nsel_b, nullptr);
+      FSPH_LAUNCH(k_compact_sel, blocks(nsel_b), 256, s.stream, f, ex, nsel_b, d.sel_idx.as<uint32_t>(), d.send_idx.as<uint32_t>() + d.send_off[q]);
+    }
+    const int64_t nsel_n = select(nmask, nn, d.sel_idx, d.sel_mask);
+    for(int q = 0; q < P; ++q) {
+      if(!rs_cnt[q]) continue;
+      FSPH_LAUNCH(k_bit_flag, blocks(nsel_n), 256, s.stream, d.sel_mask.as<uint32_t>(), nsel_n, q, f);
+      exclusive_scan_u32(s, f, ex, nsel_n, nullptr);
+      FSPH_LAUNCH((k_emit_records<D>), blocks(nsel_n), 256, s.stream, s.tree, s.col_key.as<uint64_t>(), nsel_n, d.sel_idx.as<uint32_t>(), f, ex,
+        d.recs_send.as<NodeBoxRec>() + rs_off[q]);
     }
   }
 
@@ -800,19 +843,40 @@ static void dist_update_iteration_t(System & s) {
     d.nghost = (int64_t)ng;
     const int64_t n_total = s.n_owned + d.nghost;
     if(n_total >= (int64_t(1) << 31)) throw std::runtime_error("owned + ghost bodies exceed 2^31 on this rank");
+    // all live columns of the bodies a peer needs travel in ONE all-to-all-v: [peer][column][body]
     std::vector<std::pair<DevBuf *, int>> cols;
     live_columns(s, cols);
     std::vector<size_t> so(P), sc(P), ro(P), rc(P);
-    d.sendbuf.reserve(std::max<size_t>(nsend, 1) * 8);
+    ColPtrs8 p8;
+    ColPtrs4 p4;
+    int n8 = 0, n4 = 0;
     for(auto & c : cols) {
-      const size_t e = (size_t)c.second;
-      c.first->grow_keep((size_t)n_total * e, (size_t)s.n_owned * e, s.stream);
-      if(nsend) {
-        if(e == 8) FSPH_LAUNCH((k_pack<uint64_t>), blocks(nsend), 256, s.stream, c.first->as<uint64_t>(), d.send_idx.as<uint32_t>(), (int64_t)nsend, d.sendbuf.as<uint64_t>());
-        else FSPH_LAUNCH((k_pack<uint32_t>), blocks(nsend), 256, s.stream, c.first->as<uint32_t>(), d.send_idx.as<uint32_t>(), (int64_t)nsend, d.sendbuf.as<uint32_t>());
-      }
-      for(int q = 0; q < P; ++q) { so[q] = d.send_off[q] * e; sc[q] = d.send_cnt[q] * e; ro[q] = d.recv_off[q] * e; rc[q] = d.recv_cnt[q] * e; }
-      cm.all_to_all_v(d.sendbuf.p, so.data(), sc.data(), c.first->as<char>() + (size_t)s.n_owned * e, ro.data(), rc.data(), s.stream);
+      c.first->grow_keep((size_t)n_total * c.second, (size_t)s.n_owned * c.second, s.stream);
+      if(c.second == 8) p8.p[n8++] = c.first->as<uint64_t>();
+      else p4.p[n4++] = c.first->as<uint32_t>();
+    }
+    const size_t row = ((size_t)8 * n8 + (size_t)4 * n4 + 7) & ~(size_t)7;   // bytes per body (blocks stay 8-byte aligned)
+    d.sendbuf.reserve(std::max<size_t>(nsend, 1) * row);
+    d.recvbuf.reserve(std::max<size_t>(ng, 1) * row);
+    for(int q = 0; q < P; ++q) {
+      const size_t cnt = d.send_cnt[q];
+      so[q] = d.send_off[q] * row; sc[q] = cnt * row; ro[q] = d.recv_off[q] * row; rc[q] = d.recv_cnt[q] * row;
+      if(!cnt) continue;
+      char * base = d.sendbuf.as<char>() + so[q];
+      const uint32_t * idx = d.send_idx.as<uint32_t>() + d.send_off[q];
+      FSPH_LAUNCH((k_pack_cols<uint64_t, ColPtrs8>), dim3(blocks(cnt), (unsigned)n8), 256, s.stream, p8, idx, (int64_t)cnt, reinterpret_cast<uint64_t *>(base));
+      FSPH_LAUNCH((k_pack_cols<uint32_t, ColPtrs4>), dim3(blocks(cnt), (unsigned)n4), 256, s.stream, p4, idx, (int64_t)cnt,
+        reinterpret_cast<uint32_t *>(base + cnt * 8 * n8));
+    }
+    cm.all_to_all_v(d.sendbuf.p, so.data(), sc.data(), d.recvbuf.p, ro.data(), rc.data(), s.stream);
+    for(int q = 0; q < P; ++q) {
+      const size_t cnt = d.recv_cnt[q];
+      if(!cnt) continue;
+      const char * base = d.recvbuf.as<char>() + ro[q];
+      const int64_t dst = s.n_owned + (int64_t)d.recv_off[q];
+      FSPH_LAUNCH((k_unpack_cols<uint64_t, ColPtrs8>), dim3(blocks(cnt), (unsigned)n8), 256, s.stream, p8, dst, (int64_t)cnt, reinterpret_cast<const uint64_t *>(base));
+      FSPH_LAUNCH((k_unpack_cols<uint32_t, ColPtrs4>), dim3(blocks(cnt), (unsigned)n4), 256, s.stream, p4, dst, (int64_t)cnt,
+        reinterpret_cast<const uint32_t *>(base + cnt * 8 * n8));
     }
     d.recs_recv.reserve(std::max<size_t>(nrr, 1) * sizeof(NodeBoxRec));
     for(int q = 0; q < P; ++q) {
