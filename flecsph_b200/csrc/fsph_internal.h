@@ -182,6 +182,8 @@ struct System {
   DevBuf b_wc_super, b_super_cell, b_sl_off, b_sl_nodes;
   DevBuf b_wc_cell, b_cand_off, b_mask_off, b_cand, b_mask, b_cnt0, b_cnt1;
   DevBuf b_status, b_red, b_levels, b_ncand, b_search_scratch;
+  bool search_global_queue = false;   // the neighbour walk of this system needs the global-memory frontier (fall-back)
+  DevBuf b_search_gq;
   unsigned long long est_cand = 0, est_mask = 0;  // sizes of the previous neighbour structure (capacity estimate)
   int64_t est_n = 0;
   void * h_pinned = nullptr;  // small pinned staging (4 KB)

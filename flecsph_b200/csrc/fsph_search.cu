@@ -37,6 +37,7 @@ constexpr int SR_NT = 64;       // threads per CTA of the export kernel
 #ifndef FSPH_SR_FP32_FILTER
 #define FSPH_SR_FP32_FILTER 0
 #endif
+constexpr int SR_QCAP_GLOBAL = 8190;    // frontier capacity per level of the global-memory fall-back (x 8 children fits 16 bits)
 #ifndef FSPH_SR_SPREAD
 #define FSPH_SR_SPREAD 64
 #endif
@@ -123,16 +124,24 @@ __device__ __forceinline__ WorkCell load_work_cell(const Tree & t, const Search 
 #ifndef FSPH_SR_THREADS_PER_SM
 #define FSPH_SR_THREADS_PER_SM 448
 #endif
-template<int D, int NW, int MODE>
+// GQ: the node frontier lives in a per-CTA strip of global memory (SR_QCAP_GLOBAL entries per level) instead of shared
+// memory: the fall-back for cells whose frontier outgrows SR_QCAP (very wide kernels / strongly varying h).
+template<int D, int NW, int MODE, bool GQ = false>
 __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k_search(Tree t, Cols c, Search sr, int g_begin, int g_end, int32_t * __restrict__ scratch,
   int scratch_cap, unsigned long long * __restrict__ cursors, unsigned long long cand_cap, unsigned long long mask_cap,
-  uint32_t * __restrict__ status) {
+  uint32_t * __restrict__ status, int32_t * __restrict__ gqueue = nullptr) {
   constexpr int NT = 32 * NW;
   constexpr bool FILL = MODE != 0;
   __shared__ double gx[D][32 * NW];
   __shared__ double gh[32 * NW];
-  __shared__ int32_t queue[2][SR_QCAP];
-  __shared__ uint16_t qres[SR_QCAP];   // per frontier node: node-children mask | candidate-children mask << 8
+  constexpr int QC = GQ ? SR_QCAP_GLOBAL : SR_QCAP;
+  __shared__ int32_t queue_sm[GQ ? 1 : 2][GQ ? 1 : SR_QCAP];
+  __shared__ uint16_t qres_sm[GQ ? 1 : SR_QCAP];   // per frontier node: node-children mask | candidate-children mask << 8
+  // accessors that keep the shared-memory address space visible to the compiler in the common (non-GQ) case
+  int32_t * const gqb = GQ ? gqueue + (size_t)blockIdx.x * 3 * QC : nullptr;
+  uint16_t * const gqr = GQ ? reinterpret_cast<uint16_t *>(gqueue + (size_t)blockIdx.x * 3 * QC + 2 * QC) : nullptr;
+#define SRQ(c, j) (*(GQ ? &gqb[(size_t)(c) * QC + (j)] : &queue_sm[GQ ? 0 : (c)][GQ ? 0 : (j)]))
+#define SRR(j) (*(GQ ? &gqr[(j)] : &qres_sm[GQ ? 0 : (j)]))
   __shared__ uint32_t scan_sm[NW];
   __shared__ double red_sm[NW][2 * D + 1];
   __shared__ unsigned long long base_sm[2];
@@ -168,7 +177,7 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
     }
     int32_t * cout = MODE == 1 ? sr.cand + sr.cand_off[g] : (MODE == 2 ? scratch + (size_t)blockIdx.x * scratch_cap : nullptr);
 #if FSPH_SEARCH_TWO_LEVEL == 0
-    if(tid == 0) queue[0][0] = 0;  // the root node
+    if(tid == 0) SRQ(0, 0) = 0;  // the root node
 #endif
     // Tight box of G's positions and max h: an extra, conservative candidate cull (it only drops leaves that
     // cannot satisfy the pair predicate for any particle of G, so the neighbour sets are unchanged).
@@ -258,7 +267,7 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
         const int nd = sr.sl_nodes[sl_lo + lbase + j];
         const NodeRec rec = t.noderec[nd];
         uint32_t cand_mask = 0;
-        queue[0][j] = rec.child_begin;
+        SRQ(0, j) = rec.child_begin;
         bool ok = true;
         if(gnode >= 0) {
           // intersects_box_box(c, G)
@@ -334,7 +343,7 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
             }
           }
         }
-        qres[j] = (uint16_t)cand_mask;
+        SRR(j) = (uint16_t)cand_mask;
         my_cands += __popc(cand_mask);
       }
       // ---- one block scan per level: output order = (thread, frontier slot, child), fixed => deterministic --
@@ -343,9 +352,9 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
       uint32_t cpos = ncands + ex;
       // ---- phase B: write the next frontier and the candidates -----------------------------------------
       for(int j = tid; j < ncur; j += NT) {
-        const uint32_t cand_mask = qres[j];
+        const uint32_t cand_mask = SRR(j);
         if(FILL && cand_mask) {
-          const int child_begin = queue[0][j];
+          const int child_begin = SRQ(0, j);
           int cv[1 << D];
 #pragma unroll
           for(int b = 0; b < (1 << D); ++b)
@@ -374,11 +383,11 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
       const int sidx = sr.wc_super[g];
       const uint64_t sl_lo = sr.sl_off[sidx];
       ncur = (int)(sr.sl_off[sidx + 1] - sl_lo);
-      if(ncur > SR_QCAP) {
+      if(ncur > QC) {
         if(tid == 0) atomicOr(status, (uint32_t)ERR_QUEUE_OVERFLOW);
-        ncur = SR_QCAP;
+        ncur = QC;
       }
-      for(int j = tid; j < ncur; j += NT) queue[0][j] = sr.sl_nodes[sl_lo + j];
+      for(int j = tid; j < ncur; j += NT) SRQ(0, j) = sr.sl_nodes[sl_lo + j];
       __syncthreads();
     }
 #endif
@@ -386,7 +395,7 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
       // ---- phase A: test every frontier node (results to shared memory), count children / candidates -------
       uint32_t my_nodes = 0, my_cands = 0;
       for(int j = tid; j < ncur; j += NT) {
-        const int nd_raw = queue[cur][j];
+        const int nd_raw = SRQ(cur, j);
         const int nd = nd_raw & 0x3fffffff;
         const NodeRec rec = t.noderec[nd];
         uint32_t node_mask = 0, cand_mask = 0;
@@ -466,7 +475,7 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
             }
           }
         }
-        qres[j] = (uint16_t)(node_mask | (cand_mask << 8));
+        SRR(j) = (uint16_t)(node_mask | (cand_mask << 8));
         my_nodes += __popc(node_mask);
         my_cands += __popc(cand_mask);
       }
@@ -477,16 +486,16 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
       const uint32_t nnext_raw = total & 0xffffu;
       // ---- phase B: write the next frontier and the candidates -----------------------------------------
       for(int j = tid; j < ncur; j += NT) {
-        const uint32_t r = qres[j];
+        const uint32_t r = SRR(j);
         if(r == 0) continue;
-        const int nd = queue[cur][j] & 0x3fffffff;
+        const int nd = SRQ(cur, j) & 0x3fffffff;
         const NodeRec rec = t.noderec[nd];
         uint32_t node_mask = r & 0xffu, cand_mask = r >> 8;
         while(node_mask) {
           const int b = __ffs(node_mask) - 1;
           node_mask &= node_mask - 1;
           // node children of a node have consecutive node indices (level order)
-          if(qpos < SR_QCAP) queue[cur ^ 1][qpos] = rec.first_child_node + __popc(~rec.leafmask & ((1u << b) - 1u));
+          if(qpos < QC) SRQ(cur ^ 1, qpos) = rec.first_child_node + __popc(~rec.leafmask & ((1u << b) - 1u));
           ++qpos;
         }
         if(FILL && cand_mask) {
@@ -504,9 +513,9 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
       }
       ncands += total >> 16;
       uint32_t nnext = nnext_raw;
-      if(nnext > SR_QCAP) {
+      if(nnext > QC) {
         if(tid == 0) atomicOr(status, (uint32_t)ERR_QUEUE_OVERFLOW);
-        nnext = SR_QCAP;
+        nnext = QC;
       }
       __syncthreads();
       ncur = (int)nnext;
@@ -662,6 +671,8 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
     if(active) c.nneigh[wc.start + tid] = cnt0;
   }
 }
+#undef SRQ
+#undef SRR
 
 
 // ---- level 1 of the two-level walk: one node list per super cell -------------------------------------------
@@ -847,9 +858,29 @@ static void build_super_lists(System & s) {
 
 template<int D, int MODE>
 static void launch_search(System & s, int32_t * scratch, int scratch_cap, int grid_cap, unsigned long long * cursors,
-  unsigned long long cand_cap, unsigned long long mask_cap) {
+  unsigned long long cand_cap, unsigned long long mask_cap, bool global_queue = false) {
   Search & sr = s.search;
   uint32_t * status = s.b_status.as<uint32_t>();
+  if(global_queue) {
+    // fall-back (MODE 0 / 1 only): persistent CTAs, each with its own frontier strip in global memory
+    const int gq_grid = 148 * 6;
+    s.b_search_gq.reserve((size_t)gq_grid * 3 * SR_QCAP_GLOBAL * 4);
+    int32_t * gq = s.b_search_gq.as<int32_t>();
+    for(int cls = 0; cls < 4; ++cls) {
+      const int b = sr.class_off[cls], e = sr.class_off[cls + 1];
+      if(e <= b) continue;
+      const int grid = std::min(e - b, gq_grid);
+      constexpr int M = MODE == 2 ? 1 : MODE;
+      switch(cls) {
+        case 0: FSPH_LAUNCH((k_search<D, 1, M, true>), grid, 32, s.stream, s.tree, s.cols(), sr, b, e, scratch, scratch_cap, cursors, cand_cap, mask_cap, status, gq); break;
+        case 1: FSPH_LAUNCH((k_search<D, 2, M, true>), grid, 64, s.stream, s.tree, s.cols(), sr, b, e, scratch, scratch_cap, cursors, cand_cap, mask_cap, status, gq); break;
+        case 2: FSPH_LAUNCH((k_search<D, 3, M, true>), grid, 96, s.stream, s.tree, s.cols(), sr, b, e, scratch, scratch_cap, cursors, cand_cap, mask_cap, status, gq); break;
+        default: FSPH_LAUNCH((k_search<D, 4, M, true>), grid, 128, s.stream, s.tree, s.cols(), sr, b, e, scratch, scratch_cap, cursors, cand_cap, mask_cap, status, gq); break;
+      }
+    }
+    FSPH_CUDA_OK(cudaGetLastError());
+    return;
+  }
   for(int cls = 0; cls < 4; ++cls) {
     const int b = sr.class_off[cls], e = sr.class_off[cls + 1];
     if(e <= b) continue;
@@ -885,7 +916,8 @@ static void neighbor_search_t(System & s) {
 #endif
   // single pass when the previous search on this system gives a capacity estimate
   // (with ghosts the body count drifts a little from step to step: the estimate is scaled by the ratio)
-  const bool est_ok = s.est_cand > 0 && s.est_n > 0 && (s.est_n == s.n || (s.comm && std::llabs(s.est_n - s.n) < s.est_n / 4));
+  if(getenv("FSPH_SEARCH_FORCE_GLOBAL_QUEUE")) s.search_global_queue = true;   // test hook
+  const bool est_ok = !s.search_global_queue && s.est_cand > 0 && s.est_n > 0 && (s.est_n == s.n || (s.comm && std::llabs(s.est_n - s.n) < s.est_n / 4));
   if(est_ok) {
     if(s.est_n != s.n) {
       const double r = (double)s.n / (double)s.est_n;
@@ -906,35 +938,51 @@ static void neighbor_search_t(System & s) {
     FSPH_CUDA_OK(cudaMemcpyAsync(tot, cursors, 16, cudaMemcpyDeviceToHost, s.stream));
     FSPH_CUDA_OK(cudaMemcpyAsync(&st, status, 4, cudaMemcpyDeviceToHost, s.stream));
     FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
-    if(st & ERR_QUEUE_OVERFLOW) throw std::runtime_error("neighbour search: node frontier exceeds the shared-memory queue");
-    if(!(st & ERR_SEARCH_CAPACITY)) {
+    if(!(st & (ERR_SEARCH_CAPACITY | ERR_QUEUE_OVERFLOW))) {
       s.est_cand = tot[0];
       s.est_mask = tot[1];
       return;
     }
-    // capacity estimate too small: clear the flag and fall through to the exact two-pass path
-    uint32_t cleared = st & ~(uint32_t)ERR_SEARCH_CAPACITY;
+    // capacity estimate too small / frontier too large for shared memory: clear the flags, take the exact two-pass path
+    if(st & ERR_QUEUE_OVERFLOW) s.search_global_queue = true;
+    uint32_t cleared = st & ~(uint32_t)(ERR_SEARCH_CAPACITY | ERR_QUEUE_OVERFLOW);
     FSPH_CUDA_OK(cudaMemcpyAsync(status, &cleared, 4, cudaMemcpyHostToDevice, s.stream));
     FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
   }
-  launch_search<D, 0>(s, nullptr, 0, 0, nullptr, 0, 0);
-  exclusive_scan_u64(s, sr.cand_off, sr.cand_off, nwc, nullptr);
-  exclusive_scan_u64(s, sr.mask_off, sr.mask_off, nwc, nullptr);
-  uint64_t tot[2];
-  uint32_t st = 0;
-  FSPH_CUDA_OK(cudaMemcpyAsync(&tot[0], sr.cand_off + nwc, 8, cudaMemcpyDeviceToHost, s.stream));
-  FSPH_CUDA_OK(cudaMemcpyAsync(&tot[1], sr.mask_off + nwc, 8, cudaMemcpyDeviceToHost, s.stream));
-  FSPH_CUDA_OK(cudaMemcpyAsync(&st, status, 4, cudaMemcpyDeviceToHost, s.stream));
-  FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
-  if(st & ERR_QUEUE_OVERFLOW) throw std::runtime_error("neighbour search: node frontier exceeds the shared-memory queue");
-  s.b_cand.reserve((size_t)std::max<uint64_t>(tot[0], 1) * 4);
-  s.b_mask.reserve((size_t)std::max<uint64_t>(tot[1], 1) * 4);
-  sr.cand = s.b_cand.as<int32_t>();
-  sr.mask = s.b_mask.as<uint32_t>();
-  launch_search<D, 1>(s, nullptr, 0, 0, nullptr, 0, 0);
-  s.est_cand = tot[0];
-  s.est_mask = tot[1];
-  s.est_n = s.n;
+  // exact two-pass path (count, prefix sum, fill); with the frontier in global memory when shared memory is too small
+  auto clear_flag = [&](uint32_t st, uint32_t bit) {
+    const uint32_t cleared = st & ~bit;
+    FSPH_CUDA_OK(cudaMemcpyAsync(status, &cleared, 4, cudaMemcpyHostToDevice, s.stream));
+    FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
+  };
+  auto two_pass = [&](bool gq) -> bool {
+    launch_search<D, 0>(s, nullptr, 0, 0, nullptr, 0, 0, gq);
+    exclusive_scan_u64(s, sr.cand_off, sr.cand_off, nwc, nullptr);
+    exclusive_scan_u64(s, sr.mask_off, sr.mask_off, nwc, nullptr);
+    uint64_t tot[2];
+    uint32_t st = 0;
+    FSPH_CUDA_OK(cudaMemcpyAsync(&tot[0], sr.cand_off + nwc, 8, cudaMemcpyDeviceToHost, s.stream));
+    FSPH_CUDA_OK(cudaMemcpyAsync(&tot[1], sr.mask_off + nwc, 8, cudaMemcpyDeviceToHost, s.stream));
+    FSPH_CUDA_OK(cudaMemcpyAsync(&st, status, 4, cudaMemcpyDeviceToHost, s.stream));
+    FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
+    if(st & ERR_QUEUE_OVERFLOW) {
+      clear_flag(st, ERR_QUEUE_OVERFLOW);
+      return false;
+    }
+    s.b_cand.reserve((size_t)std::max<uint64_t>(tot[0], 1) * 4);
+    s.b_mask.reserve((size_t)std::max<uint64_t>(tot[1], 1) * 4);
+    sr.cand = s.b_cand.as<int32_t>();
+    sr.mask = s.b_mask.as<uint32_t>();
+    launch_search<D, 1>(s, nullptr, 0, 0, nullptr, 0, 0, gq);
+    s.est_cand = tot[0];
+    s.est_mask = tot[1];
+    s.est_n = s.n;
+    return true;
+  };
+  if(!s.search_global_queue && two_pass(false)) return;
+  s.search_global_queue = true;   // stays on for this system: its cells need the big frontier
+  s.est_cand = 0;                  // the single-pass kernel has no global-queue variant
+  if(!two_pass(true)) throw std::runtime_error("neighbour search: node frontier exceeds even the global-memory queue");
 }
 
 void neighbor_search(System & s) {

@@ -149,3 +149,21 @@ def test_error_paths():
     G2 = make_system("cuda", f2, par, dim)
     with pytest.raises(capi.FsphError):
         G2.update_iteration()                            # duplicate keys
+
+
+def test_global_memory_frontier_fallback(monkeypatch):
+    """The neighbour walk keeps its node frontier in shared memory; cells whose frontier outgrows it are redone with a
+    per-CTA strip of global memory.  Forced here: neighbour sets and three driver iterations must not change."""
+    monkeypatch.setenv("FSPH_SEARCH_FORCE_GLOBAL_QUEUE", "1")
+    for name, kw in (("random", dict(n=3000, seed=3, h_jitter=0.2)), ("collapse", dict(nx=12))):
+        f, par, dim = case(name, **kw)
+        G, R = make_system("cuda", f, par, dim), make_system(oracle_backend(dim), f, par, dim)
+        G.update_iteration(); R.update_iteration()
+        G.apply_in_smoothinglength(capi.SWEEP_NEIGHBORS_ONLY); R.apply_in_smoothinglength(capi.SWEEP_NEIGHBORS_ONLY)
+        assert_neighbors_equal(G, R)
+        G.close(); R.close()
+    f, par, dim = case("sedov", nx=14)
+    G, R = make_system("cuda", f, par, dim), make_system(oracle_backend(dim), f, par, dim)
+    for it in range(3):
+        G.step(initial=(it == 0)); R.step(initial=(it == 0))
+    assert_fields_close(G, R, ["pos", "vel", "rho", "P", "u", "acc", "dedt", "h", "vsig", "dt"], 1e-10)
