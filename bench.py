@@ -316,7 +316,14 @@ def main():
     dom = max((k for k in phases if k in ("search", "density", "acceleration", "dedt", "dudt", "sort", "tree")), key=lambda k: phases[k])
     dom_ms = phases[dom]
     ach = n * PHASE_BYTES[dom] / (dom_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    # DRAM traffic of the dominant phase from the committed ncu capture of this exact workload (profiles/), else null
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r1_search_traffic_64M.json")
+    if dom == "search" and world == 1 and nx == 444 and os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj["traffic"], "profiles/r1_search_traffic_64M.json (%s)" % tj["how"]
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": how, "algorithmic_bytes_per_particle": PHASE_BYTES[dom], "ms_per_launch": dom_ms,
                 "note": "the pair sweeps and the neighbour search are FP64-pipe bound (SURVEY.md 8d); see fp64 and roofline_step"}
     step_ach = n * ALGO_BYTES_PER_UPDATE / (t_dev / a.steps) / 1e9

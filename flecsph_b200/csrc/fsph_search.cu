@@ -38,6 +38,9 @@ constexpr int SR_NT = 64;       // threads per CTA of the export kernel
 #define FSPH_SR_FP32_FILTER 0
 #endif
 constexpr int SR_QCAP_GLOBAL = 8190;    // frontier capacity per level of the global-memory fall-back (x 8 children fits 16 bits)
+#ifndef FSPH_SR_CHUNK
+#define FSPH_SR_CHUNK 2
+#endif
 #ifndef FSPH_SR_SPREAD
 #define FSPH_SR_SPREAD 64
 #endif
@@ -156,10 +159,14 @@ __global__ void __launch_bounds__(32 * NW, FSPH_SR_THREADS_PER_SM / (32 * NW)) k
 #endif
 
   const int tid = threadIdx.x;
-  // every CTA walks a contiguous run of work cells (Morton neighbours: the upper tree levels stay in L1/L2)
-  const int per_cta = (g_end - g_begin + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int g_lo = g_begin + (int)blockIdx.x * per_cta, g_hi = min(g_end, g_lo + per_cta);
-  for(int g = g_lo; g < g_hi; ++g) {
+  // Work cells are dealt to the CTAs in chunks of FSPH_SR_CHUNK consecutive cells, round-robin: the CTAs that run at
+  // the same time then work on neighbouring regions and share tree nodes / candidates in L2 (a contiguous run per CTA
+  // spreads the resident CTAs over the whole volume: 64 GB of DRAM reads per search at 64 M bodies), while the cells
+  // of a chunk still follow each other on one SM (L1).
+  const int ncell = g_end - g_begin;
+  const int nchunk = (ncell + FSPH_SR_CHUNK - 1) / FSPH_SR_CHUNK;
+  for(int ck = blockIdx.x; ck < nchunk; ck += gridDim.x)
+  for(int g = g_begin + ck * FSPH_SR_CHUNK, g_e = min(g_end, g + FSPH_SR_CHUNK); g < g_e; ++g) {
     const WorkCell wc = load_work_cell(t, sr, g);
     const int P = wc.P, gnode = wc.gnode;
     __syncthreads();
