@@ -325,7 +325,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "traffic_source": traffic_src,
                 "peak_source": how, "algorithmic_bytes_per_particle": PHASE_BYTES[dom], "ms_per_launch": dom_ms,
-                "note": "the pair sweeps and the neighbour search are FP64-pipe bound (SURVEY.md 8d); see fp64 and roofline_step"}
+                "note": "not HBM-bound: the neighbour walk is latency-bound, the pair sweeps run with the shared-memory pipe at 73-77 % and the fp64 pipe at 47-55 % of peak (profiles/r1_ncu_*.md); see fp64 and roofline_step"}
     step_ach = n * ALGO_BYTES_PER_UPDATE / (t_dev / a.steps) / 1e9
     roofline_step = {"bound": "hbm", "achieved": step_ach, "peak": peak, "unit": "GB/s", "frac": step_ach / peak,
                      "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE}
