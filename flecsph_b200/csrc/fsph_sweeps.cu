@@ -29,6 +29,11 @@ namespace fsph {
 // particles per thread of the pair sweeps.  2 (k_sweep2: key neighbours share a thread and read common neighbours
 // once) halves the shared-memory wavefronts per pair but was 1.5x SLOWER on B200 (64 M Sedov: acceleration 103 vs 64 ms):
 // half as many warps per SM leave the fp64 dependency chains exposed.  Kept for the record; the default is 1.
+// 1: every thread keeps the mask words of the current tile in registers (loaded straight from global memory) instead of
+// staging them in shared memory
+#ifndef FSPH_SW_MASK_REGS
+#define FSPH_SW_MASK_REGS 1
+#endif
 #ifndef FSPH_SWEEP_PPT
 #define FSPH_SWEEP_PPT 1
 #endif
@@ -516,7 +521,9 @@ __global__ void __launch_bounds__(32 * NW) k_sweep(Tree t, Cols c, Search sr, Ph
   constexpr bool NEED_IDX = OP == OP_VSIG || OP == OP_ACCV;
   __shared__ double tile[NF][TILE];
   __shared__ int32_t tidx[NEED_IDX ? TILE : 1];
+#if !FSPH_SW_MASK_REGS
   __shared__ uint32_t mtile[TILE / 32][NT];   // this tile's mask words, [word][particle]
+#endif
   __shared__ uint8_t nlist[SW_LCAP][NT];         // decoded neighbour lists of one round, [entry][particle]
 
   const int g = g_begin + blockIdx.x, tid = threadIdx.x;
@@ -556,6 +563,38 @@ __global__ void __launch_bounds__(32 * NW) k_sweep(Tree t, Cols c, Search sr, Ph
         }
       }
     }
+#if FSPH_SW_MASK_REGS
+    // this thread's mask words of the tile straight into registers (coalesced: the mask is laid out [word][particle]);
+    // the loads are in flight together with the tile gathers above
+    uint32_t mw[TILE / 32];
+    {
+      const int nwt = (tc + 31) >> 5;
+      const uint32_t * mrow = sr.mask + mo + (uint64_t)(tb >> 5) * Ppad + tid;
+#pragma unroll
+      for(int w = 0; w < TILE / 32; ++w) mw[w] = (active && w < nwt) ? mrow[(size_t)w * Ppad] : 0u;
+    }
+    __syncthreads();
+    for(;;) {
+      int cnt = 0;
+#pragma unroll
+      for(int w = 0; w < TILE / 32; ++w) {
+        while(mw[w] != 0u && cnt < SW_LCAP) {
+          nlist[cnt++][tid] = (uint8_t)(w * 32 + __ffs(mw[w]) - 1);
+          mw[w] &= mw[w] - 1;
+        }
+      }
+      const int jmax = __reduce_max_sync(0xffffffffu, cnt);
+      if(jmax == 0) break;
+      for(int j = 0; j < jmax; j += 2) {
+        const bool v0 = j < cnt, v1 = j + 1 < cnt;
+        const int ci0 = v0 ? nlist[j][tid] : 0;
+        const int ci1 = v1 ? nlist[j + 1][tid] : ci0;
+        pair_body<D, K, OP>(o, tile, tidx, pp, ci0, v0);
+        pair_body<D, K, OP>(o, tile, tidx, pp, ci1, v1);
+      }
+      if(jmax < SW_LCAP) break;
+    }
+#else
     {
       const int nwt = (tc + 31) >> 5;
       const uint32_t * mrow = sr.mask + mo + (uint64_t)(tb >> 5) * Ppad;
@@ -587,6 +626,7 @@ __global__ void __launch_bounds__(32 * NW) k_sweep(Tree t, Cols c, Search sr, Ph
       }
       if(jmax < SW_LCAP) break;
     }
+#endif
   }
   if(active) store_own<D, OP>(o, c, pp, status);
 }
