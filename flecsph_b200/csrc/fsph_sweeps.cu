@@ -38,7 +38,9 @@ namespace fsph {
 #define FSPH_SWEEP_PPT 1
 #endif
 template<int OP> struct SwTile { static constexpr int N = (OP == 0 /* OP_DENSITY */ || OP == 5 /* OP_VSIG */) ? FSPH_SW_TILE_DENS : FSPH_SW_TILE_PAIR; };
-constexpr int SW_LCAP = 32;   // neighbour-list entries decoded per round and thread
+// neighbour-list entries decoded per round and thread (measured at 64 M: 16 is best for the energy sweeps, 32 for the rest)
+template<int OP> struct SwLcap { static constexpr int N = (OP == 2 /* OP_DUDT */ || OP == 3 /* OP_DEDT */) ? 16 : 32; };
+constexpr int SW_LCAP = 32;   // k_sweep2 (experimental)
 constexpr double TINY = 1e10 * DBL_MIN;  // kernels.h:64, viscosity.h:36
 constexpr double PI = 3.14159265358979323846;
 
@@ -518,13 +520,14 @@ __global__ void __launch_bounds__(32 * NW) k_sweep(Tree t, Cols c, Search sr, Ph
   constexpr int NF = TC::NF;
   constexpr int NT = 32 * NW;
   constexpr int TILE = SwTile<OP>::N;
+  constexpr int LCAP = SwLcap<OP>::N;
   constexpr bool NEED_IDX = OP == OP_VSIG || OP == OP_ACCV;
   __shared__ double tile[NF][TILE];
   __shared__ int32_t tidx[NEED_IDX ? TILE : 1];
 #if !FSPH_SW_MASK_REGS
   __shared__ uint32_t mtile[TILE / 32][NT];   // this tile's mask words, [word][particle]
 #endif
-  __shared__ uint8_t nlist[SW_LCAP][NT];         // decoded neighbour lists of one round, [entry][particle]
+  __shared__ uint8_t nlist[LCAP][NT];         // decoded neighbour lists of one round, [entry][particle]
 
   const int g = g_begin + blockIdx.x, tid = threadIdx.x;
   int start, P;
@@ -578,7 +581,7 @@ __global__ void __launch_bounds__(32 * NW) k_sweep(Tree t, Cols c, Search sr, Ph
       int cnt = 0;
 #pragma unroll
       for(int w = 0; w < TILE / 32; ++w) {
-        while(mw[w] != 0u && cnt < SW_LCAP) {
+        while(mw[w] != 0u && cnt < LCAP) {
           nlist[cnt++][tid] = (uint8_t)(w * 32 + __ffs(mw[w]) - 1);
           mw[w] &= mw[w] - 1;
         }
@@ -592,7 +595,7 @@ __global__ void __launch_bounds__(32 * NW) k_sweep(Tree t, Cols c, Search sr, Ph
         pair_body<D, K, OP>(o, tile, tidx, pp, ci0, v0);
         pair_body<D, K, OP>(o, tile, tidx, pp, ci1, v1);
       }
-      if(jmax < SW_LCAP) break;
+      if(jmax < LCAP) break;
     }
 #else
     {
@@ -601,7 +604,7 @@ __global__ void __launch_bounds__(32 * NW) k_sweep(Tree t, Cols c, Search sr, Ph
       for(int i = tid; i < nwt * Ppad; i += NT) mtile[i / Ppad][i % Ppad] = mrow[i];
     }
     __syncthreads();
-    // Decode this thread's mask bits into a short list of tile-local candidate indices (<= SW_LCAP per round),
+    // Decode this thread's mask bits into a short list of tile-local candidate indices (<= LCAP per round),
     // then run a uniform, branch-free pair loop over the lists: two pairs per iteration (independent fp64
     // dependency chains), trip count = the warp's longest list.
     const int nw = active ? (tc + 31) >> 5 : 0;
@@ -609,7 +612,7 @@ __global__ void __launch_bounds__(32 * NW) k_sweep(Tree t, Cols c, Search sr, Ph
     uint32_t m = nw > 0 ? mtile[0][tid] : 0u;
     for(;;) {
       int cnt = 0;
-      while(cnt < SW_LCAP) {
+      while(cnt < LCAP) {
         while(m == 0 && w + 1 < nw) m = mtile[++w][tid];
         if(m == 0) break;
         nlist[cnt++][tid] = (uint8_t)(w * 32 + __ffs(m) - 1);
@@ -624,7 +627,7 @@ __global__ void __launch_bounds__(32 * NW) k_sweep(Tree t, Cols c, Search sr, Ph
         pair_body<D, K, OP>(o, tile, tidx, pp, ci0, v0);
         pair_body<D, K, OP>(o, tile, tidx, pp, ci1, v1);
       }
-      if(jmax < SW_LCAP) break;
+      if(jmax < LCAP) break;
     }
 #endif
   }
