@@ -179,7 +179,11 @@ void apply_fused(System & s, const int * op_list, int nops) {
   }
   FSPH_CUDA_OK(cudaGetLastError());
   for(int k = 0; k < nops; ++k)
-    if(op_list[k] == FSPH_APPLY_LEAPFROG_DRIFT || op_list[k] == 100 || op_list[k] == 101) s.tree_dirty = true;
+    if(op_list[k] == FSPH_APPLY_LEAPFROG_DRIFT || op_list[k] == 100 || op_list[k] == 101) {
+      // positions / smoothing lengths moved: the tree and the cached neighbour structure are stale
+      s.tree_dirty = true;
+      s.search_valid = false;
+    }
 }
 
 void apply(System & s, int op) { apply_fused(s, &op, 1); }
@@ -295,11 +299,19 @@ __global__ void __launch_bounds__(256) k_reduce(Cols c, int64_t n, int kind, int
 }
 
 static void run_reduce_local(System & s, int kind, double out[3]) {
+  if(s.n <= 0) {
+    // empty system: the identity of each reduction (no launch with an empty grid)
+    out[0] = kind == RED_MIN_DT ? 1e24 : (kind == RED_MAX_H ? -DBL_MAX : (kind >= RED_H_STATS ? DBL_MAX : 0.0));
+    out[1] = kind >= RED_H_STATS ? (kind == RED_N_STATS ? 0.0 : DBL_MIN) : 0.0;
+    out[2] = 0.0;
+    return;
+  }
   int nb = (int)std::min<int64_t>((s.n + 255) / 256, 148 * 4);
   double * part = reduce_scratch(s, (size_t)nb * 3 + 16);
   if(s.dim == 1) FSPH_LAUNCH((k_reduce<1>), nb, 256, s.stream, s.cols(), s.n, kind, s.par.thermokinetic_formulation, s.par.enable_fmm, part);
   else if(s.dim == 2) FSPH_LAUNCH((k_reduce<2>), nb, 256, s.stream, s.cols(), s.n, kind, s.par.thermokinetic_formulation, s.par.enable_fmm, part);
   else FSPH_LAUNCH((k_reduce<3>), nb, 256, s.stream, s.cols(), s.n, kind, s.par.thermokinetic_formulation, s.par.enable_fmm, part);
+  FSPH_CUDA_OK(cudaGetLastError());
   std::vector<double> h((size_t)nb * 3);
   FSPH_CUDA_OK(cudaMemcpyAsync(h.data(), part, h.size() * 8, cudaMemcpyDeviceToHost, s.stream));
   FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
@@ -368,11 +380,12 @@ void reduce(System & s, int op, double * out, int nout) {
       return;
     case FSPH_GET_COMPUTE_SMOOTHINGLENGTH:
       apply(s, 100);
-      s.tree_dirty = true;
       return;
     case FSPH_GET_COMPUTE_AVERAGE_SMOOTHINGLENGTH: {
       apply(s, 100);
       run_reduce(s, RED_SUM_H, o);
+      // nparticles = body_system::getNBodies(): with periodic boundaries the reference's count includes the WALL copies
+      // (bodies_system.h:166-168 re-counts after pboundary_generate), and so does the sum above
       double cnt[3] = {(double)s.n_owned_or_n(), 0, 0};
       if(s.comm) global_combine(s, RED_SUM_H, cnt);
       const double new_h = 1. / cnt[0] * o[0];
@@ -380,7 +393,6 @@ void reduce(System & s, int op, double * out, int nout) {
       s.dt = new_h;
       apply(s, 101);
       s.dt = keep;
-      s.tree_dirty = true;
       return;
     }
     case FSPH_GET_TOTAL_MASS: run_reduce(s, RED_MASS, o); break;
@@ -413,6 +425,9 @@ void check_status(System & s) {
   if(st & ERR_NEGATIVE) m += " negative density / pressure / internal energy (check_negativity);";
   if(st & ERR_QUEUE_OVERFLOW) m += " neighbour-search frontier overflow;";
   if(st & ERR_DT_LOOP) m += " eint-based dt estimator loop did not converge (default_physics.h:661);";
+  if(st & ERR_RANGE) m += " a body lies outside the key range;";
+  if(st & ERR_SEARCH_CAPACITY) m += " neighbour structure exceeded its reserved capacity;";
+  if(st & ERR_DD_CAPACITY) m += " domain-decomposition buffer capacity / inconsistent global leaf depths;";
   throw std::runtime_error(m);
 }
 

@@ -106,6 +106,12 @@ void do_reset_ghosts(System & s) {
 }
 
 void do_sweep(System & s, int op) {
+  if(s.tree_valid && s.tree_dirty && !s.comm) {
+    // positions / h / masses changed through the ABI since the tree was built (outside the driver's order of calls):
+    // rebuild it with the current keys, as reset_ghosts would, before searching on it
+    PhaseScope p(s, "tree");
+    build_tree(s);
+  }
   if(!s.search_valid) {
     PhaseScope p(s, "search");
     if(!s.tree_valid) throw std::runtime_error("sweep before update_iteration");
@@ -365,11 +371,11 @@ int32_t fsph_set_column(fsph_system * s, int32_t col, const void * host) {
         FSPH_CUDA_OK(cudaMemcpyAsync(s->col[VEC_FIELD[col] + d].p, tmp.data(), (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
         FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
       }
-      if(col == FSPH_COL_POS) s->tree_dirty = true;
+      if(col == FSPH_COL_POS) { s->tree_dirty = true; s->search_valid = false; }
     }
     else if(scalar_field(col) >= 0) {
       FSPH_CUDA_OK(cudaMemcpyAsync(s->col[scalar_field(col)].p, host, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
-      if(col == FSPH_COL_H || col == FSPH_COL_MASS) s->tree_dirty = true;
+      if(col == FSPH_COL_H || col == FSPH_COL_MASS) { s->tree_dirty = true; s->search_valid = false; }
     }
     else if(col == FSPH_COL_ID) FSPH_CUDA_OK(cudaMemcpyAsync(s->col_id.p, host, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
     else if(col == FSPH_COL_TYPE) FSPH_CUDA_OK(cudaMemcpyAsync(s->col_type.p, host, (size_t)n * 4, cudaMemcpyHostToDevice, s->stream));
@@ -421,7 +427,7 @@ int32_t fsph_set_component(fsph_system * s, int32_t col, int32_t comp, const voi
     else throw std::runtime_error("column not writable");
     FSPH_CUDA_OK(cudaMemcpyAsync(dst, host, (size_t)s->n * esz, cudaMemcpyHostToDevice, s->stream));
     FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
-    if(col == FSPH_COL_POS || col == FSPH_COL_H || col == FSPH_COL_MASS) s->tree_dirty = true;
+    if(col == FSPH_COL_POS || col == FSPH_COL_H || col == FSPH_COL_MASS) { s->tree_dirty = true; s->search_valid = false; }
   });
 }
 

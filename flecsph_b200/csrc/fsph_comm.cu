@@ -33,6 +33,7 @@ struct NcclApi {
   int (*GetUniqueId)(ncclUniqueId_ *) = nullptr;
   int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId_, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*CommAbort)(ncclComm_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -55,6 +56,7 @@ NcclApi & nccl() {
     FSPH_SYM(GetUniqueId, "ncclGetUniqueId");
     FSPH_SYM(CommInitRank, "ncclCommInitRank");
     FSPH_SYM(CommDestroy, "ncclCommDestroy");
+    FSPH_SYM(CommAbort, "ncclCommAbort");
     FSPH_SYM(GroupStart, "ncclGroupStart");
     FSPH_SYM(GroupEnd, "ncclGroupEnd");
     FSPH_SYM(Send, "ncclSend");
@@ -79,6 +81,14 @@ struct NcclComm : Comm {
   ncclComm_t comm = nullptr;
   ~NcclComm() override {
     if(comm) nccl().CommDestroy(comm);
+  }
+  // This rank failed (device guard, capacity, allocation): tear the communicator down so that the peers' pending
+  // collectives return an error instead of blocking for ever -- the reference's MPI_Abort (mpisph/utils.h:34-38).
+  void abort() override {
+    if(comm && nccl().CommAbort) {
+      nccl().CommAbort(comm);
+      comm = nullptr;
+    }
   }
   void all_gather(const void * send, void * recv, size_t bytes, cudaStream_t st) override {
     nccl_ok(nccl().AllGather(send, recv, bytes, ncclChar_, comm, st), "ncclAllGather");

@@ -246,7 +246,7 @@ extern std::atomic<unsigned long long> g_launches;
 void radix_pass(System & s, const uint64_t * kin, const uint32_t * vin, uint64_t * kout, uint32_t * vout, int64_t n, int shift);
 // Full 64-bit sort of (key, index) pairs; result in kout/vout (may swap internally): returns pointers to the sorted arrays.
 void radix_sort_pairs(System & s, uint64_t *& k0, uint32_t *& v0, uint64_t *& k1, uint32_t *& v1, int64_t n);
-void exclusive_scan_u32(System & s, const uint32_t * in, uint32_t * out, int64_t n, uint32_t * total_dev);  // out[n] not written
+void exclusive_scan_u32(System & s, const uint32_t * in, uint32_t * out, int64_t n, uint32_t * total_dev);  // out[n] = total (callers rely on it)
 void exclusive_scan_u64(System & s, const uint64_t * in, uint64_t * out, int64_t n, uint64_t * total_dev);
 
 // ---- fsph_tree.cu ---------------------------------------------------------------------------
