@@ -23,6 +23,7 @@ SOURCES = {
     "fsph_fmm.cu": ["-fmad=false"],
     "fsph_boundary.cu": ["-fmad=false"],
     "fsph_dist.cu": ["-fmad=false"],
+    "fsph_diag.cu": [],
 }
 
 

@@ -68,12 +68,13 @@ SYMBOLS = [
     "fsph_phase_times", "fsph_set_time_state", "fsph_get_time_state", "fsph_tree_root",
     "fsph_comm_unique_id", "fsph_comm_init_nccl", "fsph_local_group_create", "fsph_local_group_destroy",
     "fsph_comm_init_local", "fsph_comm_rank", "fsph_comm_size", "fsph_nghosts", "fsph_dd_choose_splitters",
-    "fsph_dd_align_splitter",
+    "fsph_dd_align_splitter", "fsph_measure_fp64_tflops", "fsph_measure_copy_gbs",
 ]
 # entry points only the product library has to provide (the checkers under oracle/ may omit them)
 PRODUCT_ONLY = {"fsph_set_time_state", "fsph_get_time_state", "fsph_tree_root", "fsph_comm_unique_id",
                 "fsph_comm_init_nccl", "fsph_local_group_create", "fsph_local_group_destroy", "fsph_comm_init_local",
-                "fsph_comm_rank", "fsph_comm_size", "fsph_nghosts", "fsph_dd_choose_splitters", "fsph_dd_align_splitter"}
+                "fsph_comm_rank", "fsph_comm_size", "fsph_nghosts", "fsph_dd_choose_splitters", "fsph_dd_align_splitter",
+                "fsph_measure_fp64_tflops", "fsph_measure_copy_gbs"}
 
 # FSPH_PRODUCT_LIB: another build of the same library (kernel-variant A/B runs of scripts/ab_bench.sh)
 PRODUCT_LIB = os.environ.get("FSPH_PRODUCT_LIB") or os.path.join(ROOT, "flecsph_b200", "libflecsph_b200.so")
@@ -148,6 +149,8 @@ def load(path):
         "fsph_nghosts": (i64, [vp]),
         "fsph_dd_choose_splitters": (None, [i32, i32, vp, vp, vp]),
         "fsph_dd_align_splitter": (C.c_uint64, [i32, vp, i32, vp, i32, C.c_uint64]),
+        "fsph_measure_fp64_tflops": (dbl, [i32, i32]),
+        "fsph_measure_copy_gbs": (dbl, [i32, i64, i32]),
     }
     for name, (res, args) in sig.items():
         if name in PRODUCT_ONLY and not hasattr(lib, name):

@@ -178,6 +178,12 @@ void apply_fused(System & s, const int * op_list, int nops) {
     else FSPH_LAUNCH((k_apply<3>), nb, 256, s.stream, s.cols(), n_own, ops, s.phys(), st);
   }
   FSPH_CUDA_OK(cudaGetLastError());
+  for(int k = 0; k < nops; ++k) {
+    // the cached pair viscosities depend on v_1/2, rho and c_s (fsph_sweeps.cu)
+    if(op_list[k] == FSPH_APPLY_SAVE_VELOCITYHALF || op_list[k] == FSPH_APPLY_RECOMPUTE_P_CS ||
+       op_list[k] == FSPH_APPLY_RECOMPUTE_P_CS_THERMOKINETIC)
+      s.pair_pi_valid = false;
+  }
   for(int k = 0; k < nops; ++k)
     if(op_list[k] == FSPH_APPLY_LEAPFROG_DRIFT || op_list[k] == 100 || op_list[k] == 101) {
       // positions / smoothing lengths moved: the tree and the cached neighbour structure are stale

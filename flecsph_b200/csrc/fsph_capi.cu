@@ -361,6 +361,7 @@ int64_t fsph_nbodies(const fsph_system * s) { return s ? s->n_owned_or_n() : 0; 
 int32_t fsph_set_column(fsph_system * s, int32_t col, const void * host) {
   return guarded(s, [&]() {
     dist_drop_ghosts(*s);
+    s->pair_pi_valid = false;
     const int64_t n = s->n;
     const int D = s->dim;
     if(col >= FSPH_COL_POS && col <= FSPH_COL_GACC) {
@@ -415,6 +416,7 @@ int32_t fsph_get_column(fsph_system * s, int32_t col, void * host) {
 int32_t fsph_set_component(fsph_system * s, int32_t col, int32_t comp, const void * host) {
   return guarded(s, [&]() {
     dist_drop_ghosts(*s);
+    s->pair_pi_valid = false;
     void * dst = nullptr;
     size_t esz = 8;
     if(col >= FSPH_COL_POS && col <= FSPH_COL_GACC) {

@@ -29,7 +29,7 @@ constexpr int SUB_ENTITIES = 128;  // tree_topology.h:2121
 #ifndef FSPH_SUPER_ENTITIES
 #define FSPH_SUPER_ENTITIES 4096
 #endif
-constexpr int SUPER_ENTITIES = FSPH_SUPER_ENTITIES;  // bodies per super cell of the two-level neighbour walk
+constexpr int SUPER_ENTITIES = FSPH_SUPER_ENTITIES;  // bodies per super cell of the neighbour search
 constexpr int MAX_LEVELS = 66;
 
 // error bits latched on the device (surfaced at the next call boundary)
@@ -98,24 +98,40 @@ struct Tree {
   int32_t ncells, nnodes;
 };
 
+// neighbour structure of one step (fsph_search.cu): blocks of <= BLK_BODIES consecutive bodies (<= BLK_CELLS whole work
+// cells of one super cell), per block a union candidate list, per (block, tile of NL_TILE candidates, warp) a
+// neighbour list stored as rows of 32 x uint16
+constexpr int BLK_BODIES = 256;   // bodies per block = threads per CTA of the search and the sweeps
+constexpr int BLK_CELLS = 16;     // work cells per block (bits of a candidate's cell mask)
+constexpr int NL_TILE = 512;      // candidates per list tile (tile-local positions fit 16 bits)
+struct __align__(16) TileDir {
+  uint64_t row0;       // first row of the tile in the list arena
+  uint16_t cmax[8];    // per warp: longest list of its lanes in this tile (the warp owns 1 + cmax rows, warps in order)
+  uint64_t pad;
+};
 struct Search {
   int32_t * wc_cell;     // work cells in Morton order: index into Tree::cell
-  int32_t * ncand;       // [nwc] number of candidates of each work cell
-  uint64_t * cand_off;   // [nwc+1] offsets into cand
-  uint64_t * mask_off;   // [nwc+1] offsets into mask (32-bit words)
-  int32_t * cand;        // candidate particle indices
-  uint32_t * mask;       // per work cell: [ceil(C/32)][Ppad] words, bit b of word (w,k): candidate 32w+b is a neighbour of particle k
   int32_t nwc;
-  // work cells are grouped by size class (ceil(P/32) = 1..4 warps) so that every warp of a CTA owns live
-  // particles; within a class they stay in Morton order.  class c occupies [class_off[c], class_off[c+1]).
-  int32_t class_off[5];
-  // two-level walk (fsph_search.cu): super cells = maximal sub-trees of <= SUPER_ENTITIES bodies; each owns the list
-  // of tree nodes with leaf children that any of its work cells can accept (superset by a conservative box test)
+  // super cells = maximal sub-trees of <= SUPER_ENTITIES bodies; each owns the list of tree nodes with leaf children
+  // that any of its work cells can accept (superset by a conservative box test)
   int32_t * wc_super;    // [nwc] super cell of each work cell
   int32_t * super_cell;  // [nsuper] index into Tree::cell
   uint64_t * sl_off;     // [nsuper+1] offsets into sl_nodes
   int32_t * sl_nodes;    // node indices
   int32_t nsuper;
+  // blocks
+  int32_t nblk;
+  int32_t * blk_wc;        // [nblk+1] first work cell of each block
+  uint64_t * blk_cand_off; // [nblk] first candidate of the block in cand
+  uint64_t * blk_dir_off;  // [nblk] first tile of the block in dir
+  int32_t * blk_ncand;     // [nblk] candidates of the block
+  int32_t * blk_body;      // [nblk] first body
+  int32_t * blk_nbody;     // [nblk] bodies (thread k of the block's CTA <-> body blk_body + k)
+  int32_t * cand;          // candidate particle indices, block after block, in walk order
+  TileDir * dir;           // one entry per (block, tile)
+  uint16_t * nl;           // list arena: rows of 32 uint16; per (tile, warp): row 0 = the lanes' counts, row 1 + j = the
+                           // tile-local position of each lane's j-th neighbour
+  uint64_t nrows;          // rows in use
 };
 
 struct PhysParams {
@@ -180,12 +196,19 @@ struct System {
   DevBuf b_noderec, b_leafrec;
   DevBuf b_nmass, b_ncom[3], b_nradius, b_nlap, b_nbmin[3], b_nbmax[3];
   DevBuf b_wc_super, b_super_cell, b_sl_off, b_sl_nodes;
-  DevBuf b_wc_cell, b_cand_off, b_mask_off, b_cand, b_mask, b_cnt0, b_cnt1;
-  DevBuf b_status, b_red, b_levels, b_ncand, b_search_scratch;
-  bool search_global_queue = false;   // the neighbour walk of this system needs the global-memory frontier (fall-back)
-  DevBuf b_search_gq;
-  unsigned long long est_cand = 0, est_mask = 0;  // sizes of the previous neighbour structure (capacity estimate)
+  DevBuf b_wc_cell, b_cand, b_cnt0, b_cnt1;
+  DevBuf b_status, b_red, b_levels, b_search_scratch;
+  DevBuf b_blk_wc, b_blk_meta, b_dir, b_nl;
+  DevBuf b_pair_a, b_pair_pi;         // per-pair caches of the sweeps, parallel to the list arena (fsph_sweeps.cu)
+  unsigned long long est_cand = 0, est_dir = 0, est_rows = 0;  // sizes of the previous neighbour structure (capacity estimate)
   int64_t est_n = 0;
+  int search_scratch_cap = 8192;      // candidates per CTA strip of the block search (grows on demand)
+  bool search_tiny_done = false;      // test hook FSPH_SEARCH_TINY_CAP used up
+  uint64_t search_epoch = 0;          // bumped by every neighbour search (validity of the pair caches)
+  // pair caches (fsph_sweeps.cu): decided per neighbour structure; A is valid for the structure it was stored with,
+  // Pi additionally only while rho, c_s and v_1/2 are unchanged
+  uint64_t pair_cache_epoch = ~0ull, pair_a_epoch = 0;
+  bool pair_cache_on = false, pair_pi_valid = false;
   void * h_pinned = nullptr;  // small pinned staging (4 KB)
   Tree tree;
   Search search;
@@ -239,6 +262,14 @@ extern std::atomic<unsigned long long> g_launches;
   do {                                                           \
     ++fsph::g_launches;                                          \
     kernel<<<grid, block, 0, stream>>>(__VA_ARGS__);             \
+  } while(0)
+
+// launch with dynamic shared memory (the opt-in above 48 KB is per device: set before every launch, it is cheap)
+#define FSPH_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...)                                            \
+  do {                                                                                                      \
+    FSPH_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)));   \
+    ++fsph::g_launches;                                                                                     \
+    kernel<<<grid, block, smem, stream>>>(__VA_ARGS__);                                                     \
   } while(0)
 
 // ---- fsph_sort.cu ---------------------------------------------------------------------------

@@ -6,47 +6,38 @@
 //                                                  eos ideal eos/eos.h:166-183, compute_signalspeed :236-265)
 //   compute_acceleration :348-408, compute_dudt :421-487, compute_dedt :502-566
 // with the SPH kernels of include/physics/kernels.h (cubic :106-153, quintic :217-268, Wendland C2 :282-365,
-// C4 :375-463, C6 :480-566) and the constant artificial viscosity of include/physics/viscosity.h:81-137.
+// C4 :375-463, C6 :480-566, gaussian :168-203, super gaussian :582-612, sinc :626-699) and the constant artificial
+// viscosity of include/physics/viscosity.h:81-137.
 //
-// One CTA per work cell (thread k <-> particle k of the cell).  The cell's candidate particles are staged
-// in shared memory in tiles of 256 as SoA columns (coalesced gathers: candidates are runs of consecutive
-// Morton indices); each thread then walks the set bits of its own mask words and reads its neighbours'
-// fields from shared memory.  FP64-pipe bound; FMA contraction is allowed here (1e-10 bar).
+// One CTA of 256 threads per block of the neighbour structure (thread k <-> body k of the block; a block is a run of
+// whole work cells, fsph_search.cu).  The block's union candidate list is staged in shared memory in tiles of 512 as
+// SoA columns (coalesced gathers: candidates are runs of consecutive Morton indices); each warp then reads its
+// neighbour-list rows of the tile (32 x uint16, coalesced) and every lane evaluates its own neighbours from shared
+// memory, two pairs per iteration.  FP64-pipe bound; FMA contraction is allowed here (1e-10 bar).
+//
+// Pair caches.  x, h and m are frozen between the sweeps of an iteration, and so is everything the artificial viscosity
+// reads between the acceleration and the energy sweep (rho, c_s, v_1/2).  When device memory allows, the density
+// sweep therefore also stores A_ab = m_b [x_b != x_a] F(r_ab, h_ab) for every pair (grad W = r_ab F), the
+// acceleration sweep reads A and stores Pi_ab, and the energy sweep reads both: its pair costs ~20 fp64 instructions
+// instead of ~90, and the acceleration sweep skips the kernel gradient.  The caches are parallel to the list arena
+// (one double per list slot) and are used only while the neighbour structure and the fields they were computed from
+// are unchanged (System::pair_a_epoch / pair_pi_valid); without them every sweep recomputes (CM = 0).
 #include <stdexcept>
 #include <cfloat>
+#include <cstdlib>
 #include "fsph_internal.h"
 
 namespace fsph {
 
-// candidates staged per shared-memory tile: a smaller tile lets more CTAs share an SM (the tile is most of a CTA's
-// shared memory) at the price of more tile rounds; measured on B200 (64 M Sedov): density 256, the wide pair sweeps 128
-#ifndef FSPH_SW_TILE_DENS
-#define FSPH_SW_TILE_DENS 256
-#endif
-#ifndef FSPH_SW_TILE_PAIR
-#define FSPH_SW_TILE_PAIR 128
-#endif
-// particles per thread of the pair sweeps.  2 (k_sweep2: key neighbours share a thread and read common neighbours
-// once) halves the shared-memory wavefronts per pair but was 1.5x SLOWER on B200 (64 M Sedov: acceleration 103 vs 64 ms):
-// half as many warps per SM leave the fp64 dependency chains exposed.  Kept for the record; the default is 1.
-// 1: every thread keeps the mask words of the current tile in registers (loaded straight from global memory) instead of
-// staging them in shared memory
-#ifndef FSPH_SW_MASK_REGS
-#define FSPH_SW_MASK_REGS 1
-#endif
-#ifndef FSPH_SWEEP_PPT
-#define FSPH_SWEEP_PPT 1
-#endif
-template<int OP> struct SwTile { static constexpr int N = (OP == 0 /* OP_DENSITY */ || OP == 5 /* OP_VSIG */) ? FSPH_SW_TILE_DENS : FSPH_SW_TILE_PAIR; };
-// neighbour-list entries decoded per round and thread (measured at 64 M: 16 is best for the energy sweeps, 32 for the rest)
-template<int OP> struct SwLcap { static constexpr int N = (OP == 2 /* OP_DUDT */ || OP == 3 /* OP_DEDT */) ? 16 : 32; };
-constexpr int SW_LCAP = 32;   // k_sweep2 (experimental)
 constexpr double TINY = 1e10 * DBL_MIN;  // kernels.h:64, viscosity.h:36
 constexpr double PI = 3.14159265358979323846;
 
 enum SweepOp { OP_DENSITY = 0, OP_ACC = 1, OP_DUDT = 2, OP_DEDT = 3, OP_VSIG = 5, OP_ACCV = 6 };
+// cache mode of a sweep.  density: 1 = write A.  acceleration: 1 = read A, write Pi.  energy: 1 = read A and Pi,
+// 2 = read A only (Pi is stale, e.g. second pressure pass).  0 = no cache.
+enum CacheMode { CM_NONE = 0, CM_FULL = 1, CM_A_ONLY = 2 };
 
-// ---- SPH kernels: value W(r,h) and the scalar F with grad W = r_ab * F ------------------------------------
+// ---- SPH kernels: value Wi(r, 1/h) and the scalar Fi(r, 1/h, 1/r) with grad W = r_ab * Fi --------------------
 
 template<int D> __device__ __forceinline__ double ipowD(double ih) { return D == 1 ? ih : (D == 2 ? ih * ih : ih * ih * ih); }
 // Reciprocal and reciprocal square root from the MUFU seeds (~20 bits) plus two Newton steps (error ~1e-16
@@ -69,37 +60,16 @@ __device__ __forceinline__ double rsqrt_nr(double x) {
   e = fma(-hx * y, y, 0.5);
   return fma(y, e, y);
 }
-// 1/h and 1/(r + TINY) from a single fp64 reciprocal
-__device__ __forceinline__ void inv_h_r(double h, double r, double & ih, double & ir) {
-  const double rt = r + TINY;
-  const double inv = rcp_nr(h * rt);
-  ih = inv * rt;
-  ir = inv * h;
-}
-
 template<int D, int K> struct SphKernel;
 
 template<int D> struct SphKernel<D, FSPH_KERNEL_CUBIC_SPLINE> {
   static __device__ __forceinline__ double sigma() { return D == 1 ? 4. / 3. : (D == 2 ? 40. / (7. * PI) : 8. / PI); }
-  static __device__ __forceinline__ double W(double r, double h) {
-    const double ih = rcp_nr(h);
+  static __device__ __forceinline__ double Wi(double r, double ih) {
     const double q = 2. * r * ih;
     double res = 0.;
     if(q < 2.0) {
       res = q < 1.0 ? 1.0 - 1.5 * q * q + .75 * q * q * q : 0.25 * (2 - q) * (2 - q) * (2 - q);
       res *= sigma() * ipowD<D>(ih);
-    }
-    return res;
-  }
-  static __device__ __forceinline__ double F(double r, double h) {
-    double ih, ir;
-    inv_h_r(h, r, ih, ir);
-    const double q = 2. * r * ih;
-    double res = 0.;
-    if(q < 2.0) {
-      const double sg = 2. * sigma() * ipowD<D>(ih) * ih;
-      const double dW = q < 1.0 ? -3.0 * q + 9. / 4. * q * q : -.75 * (2 - q) * (2 - q);
-      res = sg * dW * ir;
     }
     return res;
   }
@@ -118,8 +88,7 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_QUINTIC_SPLINE> {
   static __device__ __forceinline__ double sigma() { return D == 1 ? 1. / 40. : (D == 2 ? 63. / (478. * PI) : 81. / (359. * PI)); }
   static __device__ __forceinline__ double p5(double x) { double x2 = x * x; return x2 * x2 * x; }
   static __device__ __forceinline__ double p4(double x) { double x2 = x * x; return x2 * x2; }
-  static __device__ __forceinline__ double W(double r, double h) {
-    const double ih = rcp_nr(h);
+  static __device__ __forceinline__ double Wi(double r, double ih) {
     const double q = 3. * r * ih;
     double res = 0.;
     if(q < 3.) {
@@ -127,20 +96,6 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_QUINTIC_SPLINE> {
       if(q < 2.) res += -6 * p5(2 - q);
       if(q < 1.) res += 15 * p5(1 - q);
       res *= sigma() * ipowD<D>(ih);
-    }
-    return res;
-  }
-  static __device__ __forceinline__ double F(double r, double h) {
-    double ih, ir;
-    inv_h_r(h, r, ih, ir);
-    const double q = 3. * r * ih;
-    double res = 0.;
-    if(q < 3.) {
-      const double sg = 3. * sigma() * ipowD<D>(ih) * ih;
-      double dW = -5. * p4(3 - q);
-      if(q < 2.) dW += 30. * p4(2 - q);
-      if(q < 1.) dW += -75. * p4(1 - q);
-      res = sg * dW * ir;
     }
     return res;
   }
@@ -159,19 +114,10 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_QUINTIC_SPLINE> {
 };
 template<int D> struct SphKernel<D, FSPH_KERNEL_WENDLAND_C2> {
   static __device__ __forceinline__ double sigma() { return D == 1 ? 1.25 : (D == 2 ? 7. / PI : 21. / (2. * PI)); }
-  static __device__ __forceinline__ double W(double r, double h) {
-    const double ih = rcp_nr(h);
+  static __device__ __forceinline__ double Wi(double r, double ih) {
     const double q = r * ih, o = 1 - q, o2 = o * o;
     const double res = D == 1 ? sigma() * ih * o2 * o * (3 * q + 1) : sigma() * ipowD<D>(ih) * o2 * o2 * (4 * q + 1);
     return q < 1.0 ? res : 0.0;
-  }
-  static __device__ __forceinline__ double F(double r, double h) {
-    double ih, ir;
-    inv_h_r(h, r, ih, ir);
-    const double q = r * ih, o = 1 - q, o2 = o * o;
-    const double sg = D == 1 ? sigma() * ih * ih : 2. * sigma() * ipowD<D>(ih) * ih;
-    const double dW = D == 1 ? -12. * q * o2 : -10. * q * o2 * o;
-    return q < 1.0 ? sg * dW * ir : 0.0;
   }
   static __device__ __forceinline__ double Fi(double r, double ih, double ir) {
     const double q = r * ih, o = 1 - q, o2 = o * o;
@@ -182,21 +128,12 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_WENDLAND_C2> {
 };
 template<int D> struct SphKernel<D, FSPH_KERNEL_WENDLAND_C4> {
   static __device__ __forceinline__ double sigma() { return D == 1 ? 1.5 : (D == 2 ? 9. / PI : 495. / (32. * PI)); }
-  static __device__ __forceinline__ double W(double r, double h) {
-    const double ih = rcp_nr(h);
+  static __device__ __forceinline__ double Wi(double r, double ih) {
     const double q = r * ih, o = 1 - q, o2 = o * o;
     double res;
     if(D == 1) res = sigma() * ih * (o2 * o) * o2 * (1 + q * (5 + q * 8));
     else res = sigma() * ipowD<D>(ih) * (o2 * o2 * o2) * (1 + q * (6 + q * (35. / 3.)));
     return q < 1.0 ? res : 0.0;
-  }
-  static __device__ __forceinline__ double F(double r, double h) {
-    double ih, ir;
-    inv_h_r(h, r, ih, ir);
-    const double q = r * ih, o = 1 - q, o2 = o * o;
-    const double sg = 14. * sigma() * ipowD<D>(ih) * ih;
-    const double dW = D == 1 ? -q * o2 * o2 * (1 + 4. * q) : -4. / 3. * q * (o2 * o) * o2 * (1 + 5. * q);
-    return q < 1.0 ? sg * dW * ir : 0.0;
   }
   static __device__ __forceinline__ double Fi(double r, double ih, double ir) {
     const double q = r * ih, o = 1 - q, o2 = o * o;
@@ -207,21 +144,12 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_WENDLAND_C4> {
 };
 template<int D> struct SphKernel<D, FSPH_KERNEL_WENDLAND_C6> {
   static __device__ __forceinline__ double sigma() { return D == 1 ? 55. / 32. : (D == 2 ? 78. / (7. * PI) : 1365. / (64. * PI)); }
-  static __device__ __forceinline__ double W(double r, double h) {
-    const double ih = rcp_nr(h);
+  static __device__ __forceinline__ double Wi(double r, double ih) {
     const double q = r * ih, o = 1 - q, o2 = o * o, o4 = o2 * o2;
     double res;
     if(D == 1) res = sigma() * ih * (o2 * o) * o4 * (1 + q * (7 + q * (19 + q * 21)));
     else res = sigma() * ipowD<D>(ih) * o4 * o4 * (1 + q * (8 + q * (25 + q * 32)));
     return q < 1.0 ? res : 0.0;
-  }
-  static __device__ __forceinline__ double F(double r, double h) {
-    double ih, ir;
-    inv_h_r(h, r, ih, ir);
-    const double q = r * ih, o = 1 - q, o2 = o * o, o3 = o2 * o, o4 = o2 * o2;
-    const double sg = sigma() * ipowD<D>(ih) * ih;
-    const double dW = D == 1 ? -6. * q * o3 * o3 * (3 + q * (18 + q * 35)) : -22. * q * o4 * o3 * (1 + q * (7 + q * 16));
-    return q < 1.0 ? sg * dW * ir : 0.0;
   }
   static __device__ __forceinline__ double Fi(double r, double ih, double ir) {
     const double q = r * ih, o = 1 - q, o2 = o * o, o3 = o2 * o, o4 = o2 * o2;
@@ -236,8 +164,7 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_GAUSSIAN> {
   static __device__ __forceinline__ double sigma() {
     return D == 1 ? 1.69260614115414981387661988500545775 : (D == 2 ? 2.86514256233641438778811727710055596 : 4.85098600188835377710867224691152783);
   }
-  static __device__ __forceinline__ double W(double r, double h) {
-    const double ih = rcp_nr(h);
+  static __device__ __forceinline__ double Wi(double r, double ih) {
     const double q = 3. * r * ih;
     return q <= 3. ? sigma() * ipowD<D>(ih) * exp(-q * q) : 0.0;
   }
@@ -246,18 +173,12 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_GAUSSIAN> {
     const double sg = 3. * sigma() * ipowD<D>(ih) * ih;
     return q < 3. ? sg * (-2. * q * exp(-q * q)) * ir : 0.0;
   }
-  static __device__ __forceinline__ double F(double r, double h) {
-    double ih, ir;
-    inv_h_r(h, r, ih, ir);
-    return Fi(r, ih, ir);
-  }
 };
 template<int D> struct SphKernel<D, FSPH_KERNEL_SUPER_GAUSSIAN> {
   static __device__ __forceinline__ double sigma() {
     return D == 1 ? 1.69225265632490690298438831093977954 : (D == 2 ? 2.86196342089351035329931251213987773 : 4.83280745997963041039733264826054666);
   }
-  static __device__ __forceinline__ double W(double r, double h) {
-    const double ih = rcp_nr(h);
+  static __device__ __forceinline__ double Wi(double r, double ih) {
     const double q = 3. * r * ih, q2 = q * q;
     return q < 3. ? sigma() * ipowD<D>(ih) * exp(-q2) * (D / 2.0 + 1 - q2) : 0.0;
   }
@@ -267,18 +188,12 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_SUPER_GAUSSIAN> {
     const double dW = exp(-q * q) * (2. * q * q * q - (D + 4.) * q);
     return q < 3. ? sg * dW * ir : 0.0;
   }
-  static __device__ __forceinline__ double F(double r, double h) {
-    double ih, ir;
-    inv_h_r(h, r, ih, ir);
-    return Fi(r, ih, ir);
-  }
 };
 // sinc kernel (kernels.h:626-699): index n and its normalisation (set_sinc_kernel_normalization, :67-77) are run-time
 // parameters; they live in constant memory, refreshed by sweep() before the launches
 __constant__ double c_sinc[2];  // {n, sigma(n, D)}
 template<int D> struct SphKernel<D, FSPH_KERNEL_SINC> {
-  static __device__ __forceinline__ double W(double r, double h) {
-    const double ih = rcp_nr(h);
+  static __device__ __forceinline__ double Wi(double r, double ih) {
     double q = fabs(r * ih);
     if(!(q < 1.)) return 0.0;
     q *= PI;
@@ -303,41 +218,47 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_SINC> {
     }
     return sg * dW * ir;
   }
-  static __device__ __forceinline__ double F(double r, double h) {
-    double ih, ir;
-    inv_h_r(h, r, ih, ir);
-    return Fi(r, ih, ir);
-  }
 };
+
 
 // ---- candidate tile columns per sweep ---------------------------------------------------------------------
-template<int D, int OP> struct TileCols {
-  // ACCV = acceleration + signal speed: ACC's columns + velocity + previous soundspeed
-  static constexpr int NF = OP == OP_DENSITY ? D + 2 : (OP == OP_VSIG ? 2 * D + 2 : (OP == OP_ACC ? 2 * D + 5 : (OP == OP_ACCV ? 3 * D + 6 : 3 * D + 5)));
+// which neighbour fields a sweep gathers into shared memory; positions come first, the rest in a fixed order
+template<int D, int OP, int CM> struct TileCols {
+  static constexpr bool ACCX = OP == OP_ACC || OP == OP_ACCV;
+  static constexpr bool ENER = OP == OP_DUDT || OP == OP_DEDT;
+  static constexpr bool VISC = (ACCX) || (ENER && CM != CM_FULL);        // the sweep evaluates Pi itself
+  static constexpr bool GRAD = (ACCX || ENER) && CM == CM_NONE;          // the sweep evaluates the kernel gradient itself
+  static constexpr bool hasH = OP == OP_DENSITY || VISC || GRAD;
+  static constexpr bool hasM = OP == OP_DENSITY || GRAD;
+  static constexpr bool hasRHO = VISC;
+  static constexpr bool hasPR = ACCX || OP == OP_DEDT;
+  static constexpr bool hasCS = VISC || OP == OP_VSIG;
+  static constexpr bool hasVH = VISC;
+  static constexpr bool hasV = ENER || OP == OP_VSIG;
+  static constexpr bool hasCSO = OP == OP_VSIG || OP == OP_ACCV;
+  static constexpr bool hasIDX = OP == OP_VSIG || OP == OP_ACCV;
+  static constexpr int iH = D;
+  static constexpr int iM = iH + (hasH ? 1 : 0);
+  static constexpr int iRHO = iM + (hasM ? 1 : 0);
+  static constexpr int iPR = iRHO + (hasRHO ? 1 : 0);
+  static constexpr int iCS = iPR + (hasPR ? 1 : 0);
+  static constexpr int iVH = iCS + (hasCS ? 1 : 0);
+  static constexpr int iV = iVH + (hasVH ? D : 0);
+  static constexpr int iCSO = iV + (hasV ? D : 0);
+  static constexpr int NF = iCSO + (hasCSO ? 1 : 0);
   static __device__ __forceinline__ int col(int j) {
     if(j < D) return F_POS + j;
-    if(OP == OP_DENSITY) return j == D ? F_H : F_MASS;
-    if(OP == OP_VSIG) return j < 2 * D ? F_VEL + (j - D) : (j == 2 * D ? F_CS : F_CSOLD);
-    const int r = j - D;
-    if(r == 0) return F_H;
-    if(r == 1) return F_MASS;
-    if(r == 2) return F_RHO;
-    if(r == 3) return F_PRHO2;   // P / rho^2, refreshed by k_prho2 right before the sweep
-    if(r == 4) return F_CS;
-    if(r < 5 + D) return F_VELH + (r - 5);
-    if(r < 5 + 2 * D) return F_VEL + (r - 5 - D);
+    if(hasH && j == iH) return F_H;
+    if(hasM && j == iM) return F_MASS;
+    if(hasRHO && j == iRHO) return F_RHO;
+    if(hasPR && j == iPR) return F_PRHO2;   // P / rho^2, refreshed by k_prho2 right before the sweep
+    if(hasCS && j == iCS) return F_CS;
+    if(hasVH && j >= iVH && j < iVH + D) return F_VELH + (j - iVH);
+    if(hasV && j >= iV && j < iV + D) return F_VEL + (j - iV);
     return F_CSOLD;
   }
+  static constexpr size_t smem_bytes() { return (size_t)NF * NL_TILE * 8 + (hasIDX ? NL_TILE * 4 : 0); }
 };
-
-template<int D>
-__device__ __forceinline__ double norm_vec(const double * v) {
-  if(D == 1) return fabs(v[0]);
-  double s = 0.0;
-#pragma unroll
-  for(int d = 0; d < D; ++d) s += v[d] * v[d];
-  return sqrt(s);
-}
 
 // state of the particle a thread owns + its accumulators
 template<int D> struct Own {
@@ -347,74 +268,91 @@ template<int D> struct Own {
   int ia;
 };
 
-// one neighbour pair (a, candidate ci of the current tile); `valid` = false makes it a no-op (padding slot of
-// the two-pairs-per-iteration loop)
-template<int D, int K, int OP>
-__device__ __forceinline__ void pair_body(Own<D> & o, const double (*tile)[SwTile<OP>::N], const int32_t * tidx, const PhysParams & pp,
-  const int ci, const bool valid) {
+// Pi_ab of the constant artificial viscosity (viscosity.h:81-137): mu = h dot / (r^2 + eps h^2 + TINY);
+// Pi = (-alpha c + beta mu) mu / rho -- one division for both
+__device__ __forceinline__ double visc_pi(const PhysParams & pp, double dotvr, double dist2, double hab, double rho_ab, double c_ab) {
+  double Pi = 0.0;
+  if(dotvr < 0.0) {
+    const double den = dist2 + pp.epsilon * hab * hab + TINY;
+    const double inv = rcp_nr(den * rho_ab);
+    const double mu = hab * dotvr * (inv * rho_ab);
+    Pi = (-pp.alpha * c_ab + pp.beta * mu) * mu * (inv * den);
+  }
+  return Pi;
+}
+
+// one neighbour pair (a, candidate ci of the current tile); `valid` = false makes it a no-op (padding slot of the
+// two-pairs-per-iteration loop).  cA / cP: the pair's cache slots (read or written according to CM).
+template<int D, int K, int OP, int CM>
+__device__ __forceinline__ void pair_body(Own<D> & o, const double (*tile)[NL_TILE], const int32_t * tidx, const PhysParams & pp,
+  const int ci, const bool valid, double & cA, double & cP) {
+  using TC = TileCols<D, OP, CM>;
   double rab[D];
+  double dist2 = 0.0;
 #pragma unroll
-  for(int d = 0; d < D; ++d) rab[d] = o.xa[d] - tile[d][ci];
+  for(int d = 0; d < D; ++d) {
+    rab[d] = o.xa[d] - tile[d][ci];
+    dist2 += rab[d] * rab[d];
+  }
   if(OP == OP_DENSITY) {
-    double d2 = 0.0;
-#pragma unroll
-    for(int d = 0; d < D; ++d) d2 += rab[d] * rab[d];
-    const double r = D == 1 ? fabs(rab[0]) : d2 * rsqrt_nr(fmax(d2, 1e-280));
-    const double hab = .5 * (o.ha + tile[D][ci]);
-    const double t = tile[D + 1][ci] * SphKernel<D, K>::W(r, hab);
+    // r, 1/r and 1/h_ab: one reciprocal square root + one reciprocal (dist2 clamped away from 0: W(0) is finite and the
+    // gradient factor of the particle itself / coincident particles is dropped through m_b [x_b != x_a] = 0)
+    const double ir = rsqrt_nr(fmax(dist2, 1e-280));
+    const double r = D == 1 ? fabs(rab[0]) : dist2 * ir;
+    const double hab = .5 * (o.ha + tile[TC::iH][ci]);
+    const double ih = rcp_nr(hab);
+    const double mb = tile[TC::iM][ci];
+    const double t = mb * SphKernel<D, K>::Wi(r, ih);
     o.acc0 += valid ? t : 0.0;
+    if(CM == CM_FULL) cA = (dist2 == 0.0 || !valid) ? 0.0 : mb * SphKernel<D, K>::Fi(r, ih, ir);
   }
   else if(OP == OP_VSIG) {
     // compute_signalspeed: b contributes its new soundspeed iff it was processed before a, i.e. iff its
     // (descending-key processing order) index is larger
-    const double csb = tidx[ci] > o.ia ? tile[2 * D][ci] : tile[2 * D + 1][ci];
+    const double csb = tidx[ci] > o.ia ? tile[TC::iCS][ci] : tile[TC::iCSO][ci];
     const double cab = fmax(o.cs_a, csb);
-    const double dist = norm_vec<D>(rab);
+    const double dist = D == 1 ? fabs(rab[0]) : sqrt(dist2);
     double vr = 0.0;
 #pragma unroll
-    for(int d = 0; d < D; ++d) vr += (o.va[d] - tile[D + d][ci]) * rab[d];
+    for(int d = 0; d < D; ++d) vr += (o.va[d] - tile[TC::iV + d][ci]) * rab[d];
     vr = vr / dist;                            // 0/0 = NaN for the particle itself
     const double mn = (0.0 < vr) ? 0.0 : vr;  // std::min(vr, 0.0), NaN-preserving
     const double val = cab - mn;
     if(valid && o.vsig < val) o.vsig = val;   // std::max(vsig, val): NaN (self) dropped
   }
   else {
-    const double hab = .5 * (o.ha + tile[D][ci]);
-    double dotvr = 0.0, dist2 = 0.0;
+    // ---- A = m_b [x_b != x_a] F(r, h_ab) and Pi_ab: computed here or taken from the caches ---------------------
+    double A, Pi, ir = 0.0;
+    if(TC::GRAD) {
+      const double hab = .5 * (o.ha + tile[TC::iH][ci]);
+      ir = rsqrt_nr(fmax(dist2, 1e-280));
+      const double r = D == 1 ? fabs(rab[0]) : dist2 * ir;
+      const double mb = (dist2 == 0.0 || !valid) ? 0.0 : tile[TC::iM][ci];   // m_b * (pos_b != pos_a)
+      A = mb * SphKernel<D, K>::Fi(r, rcp_nr(hab), ir);
+    }
+    else A = valid ? cA : 0.0;
+    if(TC::VISC) {
+      const double hab = .5 * (o.ha + tile[TC::iH][ci]);
+      double dotvr = 0.0;
 #pragma unroll
-    for(int d = 0; d < D; ++d) {
-      dotvr += (o.vha[d] - tile[D + 5 + d][ci]) * rab[d];
-      dist2 += rab[d] * rab[d];
+      for(int d = 0; d < D; ++d) dotvr += (o.vha[d] - tile[TC::iVH + d][ci]) * rab[d];
+      Pi = visc_pi(pp, dotvr, dist2, hab, .5 * (o.rho_a + tile[TC::iRHO][ci]), .5 * (o.cs_a + tile[TC::iCS][ci]));
+      if(TC::ACCX && CM == CM_FULL) cP = Pi;
     }
-    const double mb = (dist2 == 0.0 || !valid) ? 0.0 : tile[D + 1][ci];   // m_b * (pos_b != pos_a)
-    const double rho_ab = .5 * (o.rho_a + tile[D + 2][ci]);
-    double Pi = 0.0;
-    if(dotvr < 0.0) {
-      // mu = h dot / (r^2 + eps h^2 + TINY);  Pi = (-alpha c + beta mu) mu / rho  -- one division for both
-      const double den = dist2 + pp.epsilon * hab * hab + TINY;
-      const double inv = rcp_nr(den * rho_ab);
-      const double mu = hab * dotvr * (inv * rho_ab);
-      const double c_ab = .5 * (o.cs_a + tile[D + 4][ci]);
-      Pi = (-pp.alpha * c_ab + pp.beta * mu) * mu * (inv * den);
-    }
-    // r, 1/r and 1/h_ab: one reciprocal square root + one reciprocal (dist2 clamped away from 0: the particle
-    // itself / coincident particles carry m_b = 0 and the kernel gradient is 0 at r = 0 anyway)
-    const double ir = rsqrt_nr(fmax(dist2, 1e-280));
-    const double r = dist2 * ir;
-    const double ih = rcp_nr(hab);
-    const double Fk = SphKernel<D, K>::Fi(r, ih, ir);
-    const double Prho2_b = tile[D + 3][ci];
-    if(OP == OP_ACC || OP == OP_ACCV) {
-      const double coef = -mb * (o.Prho2_a + Prho2_b + Pi) * Fk;
+    else Pi = cP;
+    if(TC::ACCX) {
+      const double coef = -(o.Prho2_a + tile[TC::iPR][ci] + Pi) * A;
 #pragma unroll
       for(int d = 0; d < D; ++d) o.accv[d] += coef * rab[d];
       if(OP == OP_ACCV) {
-        // compute_signalspeed fused into the acceleration sweep (fsph_step only): all new soundspeeds exist by now
-        const double csb = tidx[ci] > o.ia ? tile[D + 4][ci] : tile[3 * D + 5][ci];
+        // compute_signalspeed fused into the acceleration sweep (fsph_step only: v == v_1/2 there, and all new
+        // soundspeeds exist by now)
+        if(!TC::GRAD) ir = rsqrt_nr(fmax(dist2, 1e-280));
+        const double csb = tidx[ci] > o.ia ? tile[TC::iCS][ci] : tile[TC::iCSO][ci];
         const double cab = fmax(o.cs_a, csb);
         double vr = 0.0;
 #pragma unroll
-        for(int d = 0; d < D; ++d) vr += (o.va[d] - tile[2 * D + 5 + d][ci]) * rab[d];
+        for(int d = 0; d < D; ++d) vr += (o.vha[d] - tile[TC::iVH + d][ci]) * rab[d];
         vr = vr * ir;                              // dist2 == 0 (self) is excluded below instead of via NaN
         const double mn = (0.0 < vr) ? 0.0 : vr;
         const double val = cab - mn;
@@ -424,21 +362,21 @@ __device__ __forceinline__ void pair_body(Own<D> & o, const double (*tile)[SwTil
     else if(OP == OP_DUDT) {
       double vdw = 0.0;
 #pragma unroll
-      for(int d = 0; d < D; ++d) vdw += (o.va[d] - tile[2 * D + 5 + d][ci]) * rab[d];
-      vdw *= Fk;
-      o.acc0 += mb * vdw;
-      o.acc1 += mb * vdw * Pi;
+      for(int d = 0; d < D; ++d) vdw += (o.va[d] - tile[TC::iV + d][ci]) * rab[d];
+      vdw *= A;
+      o.acc0 += vdw;
+      o.acc1 += vdw * Pi;
     }
     else {  // OP_DEDT
       double vadw = 0.0, vbdw = 0.0;
 #pragma unroll
       for(int d = 0; d < D; ++d) {
         vadw += o.va[d] * rab[d];
-        vbdw += tile[2 * D + 5 + d][ci] * rab[d];
+        vbdw += tile[TC::iV + d][ci] * rab[d];
       }
-      vadw *= Fk;
-      vbdw *= Fk;
-      o.acc0 -= mb * (o.Prho2_a * vbdw + vadw * Prho2_b + .5 * Pi * (vbdw + vadw));
+      vadw *= A;
+      vbdw *= A;
+      o.acc0 -= o.Prho2_a * vbdw + vadw * tile[TC::iPR][ci] + .5 * Pi * (vbdw + vadw);
     }
   }
 }
@@ -455,7 +393,7 @@ __device__ __forceinline__ void load_own(Own<D> & o, const Cols & c, const int i
 #pragma unroll
     for(int d = 0; d < D; ++d) o.xa[d] = c.f[F_POS + d][ia];
     o.ha = c.f[F_H][ia];
-    if(OP == OP_VSIG || OP == OP_DUDT || OP == OP_DEDT || OP == OP_ACCV) {
+    if(OP == OP_VSIG || OP == OP_DUDT || OP == OP_DEDT) {
 #pragma unroll
       for(int d = 0; d < D; ++d) o.va[d] = c.f[F_VEL + d][ia];
     }
@@ -514,42 +452,50 @@ __device__ __forceinline__ void store_own(const Own<D> & o, const Cols & c, cons
   }
 }
 
-template<int D, int K, int OP, int NW>
-__global__ void __launch_bounds__(32 * NW) k_sweep(Tree t, Cols c, Search sr, PhysParams pp, int g_begin, uint32_t * __restrict__ status) {
-  using TC = TileCols<D, OP>;
-  constexpr int NF = TC::NF;
-  constexpr int NT = 32 * NW;
-  constexpr int TILE = SwTile<OP>::N;
-  constexpr int LCAP = SwLcap<OP>::N;
-  constexpr bool NEED_IDX = OP == OP_VSIG || OP == OP_ACCV;
-  __shared__ double tile[NF][TILE];
-  __shared__ int32_t tidx[NEED_IDX ? TILE : 1];
-#if !FSPH_SW_MASK_REGS
-  __shared__ uint32_t mtile[TILE / 32][NT];   // this tile's mask words, [word][particle]
-#endif
-  __shared__ uint8_t nlist[LCAP][NT];         // decoded neighbour lists of one round, [entry][particle]
+template<int OP> struct SweepOcc { static constexpr int MINB = (OP == OP_DENSITY || OP == OP_VSIG) ? 4 : 3; };
 
-  const int g = g_begin + blockIdx.x, tid = threadIdx.x;
-  int start, P;
-  {
-    int v = t.cell[sr.wc_cell[g]];
-    if(v >= 0) { start = v; P = 1; }
-    else { start = t.node_start[~v]; P = t.sub[~v]; }
-  }
-  const int Ppad = (P + 31) & ~31;
-  const uint64_t co = sr.cand_off[g], mo = sr.mask_off[g];
-  const int C = sr.ncand[g];
-  const bool active = tid < P;
+template<int D, int K, int OP, int CM>
+__global__ void __launch_bounds__(BLK_BODIES, SweepOcc<OP>::MINB) k_sweep(Cols c, Search sr, PhysParams pp, uint32_t * __restrict__ status,
+  double * __restrict__ pair_a, double * __restrict__ pair_pi) {
+  using TC = TileCols<D, OP, CM>;
+  constexpr int NF = TC::NF;
+  constexpr int NT = BLK_BODIES;
+  constexpr bool A_RD = (OP != OP_DENSITY && OP != OP_VSIG) && CM != CM_NONE;
+  constexpr bool A_WR = OP == OP_DENSITY && CM == CM_FULL;
+  constexpr bool P_RD = (OP == OP_DUDT || OP == OP_DEDT) && CM == CM_FULL;
+  constexpr bool P_WR = (OP == OP_ACC || OP == OP_ACCV) && CM == CM_FULL;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double (* const tile)[NL_TILE] = reinterpret_cast<double (*)[NL_TILE]>(smem_raw);
+  int32_t * const tidx = reinterpret_cast<int32_t *>(smem_raw + (size_t)NF * NL_TILE * 8);
+
+  const int blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int body0 = sr.blk_body[blk], PB = sr.blk_nbody[blk], C = sr.blk_ncand[blk];
+  const uint64_t co = sr.blk_cand_off[blk], dir0 = sr.blk_dir_off[blk];
+  const bool active = tid < PB;
+  const int nwarp_act = (PB + 31) >> 5;
 
   Own<D> o;
-  load_own<D, OP>(o, c, start + tid, active);
+  load_own<D, OP>(o, c, body0 + tid, active);
 
-  for(int tb = 0; tb < C; tb += TILE) {
-    const int tc = min(TILE, C - tb);
+  const int ntile = (C + NL_TILE - 1) / NL_TILE;
+  for(int ti = 0; ti < ntile; ++ti) {
+    const int tb = ti * NL_TILE;
+    const int tc = min(NL_TILE, C - tb);
+    // this warp's rows of the tile
+    const TileDir td = sr.dir[dir0 + ti];
+    uint64_t rb = td.row0;
+    int cmax = 0;
+#pragma unroll
+    for(int w = 0; w < NT / 32; ++w) {
+      if(w < warp) rb += 1 + td.cmax[w];
+      if(w == warp && warp < nwarp_act) cmax = td.cmax[w];
+    }
+    const uint16_t * rows = sr.nl + rb * 32 + lane;
+    const int cnt = warp < nwarp_act ? rows[0] : 0;
     __syncthreads();
     {
-      // all candidate indices of this thread first, then the column gathers: (TILE / NT) x NF loads in flight
-      constexpr int LPT = (TILE + NT - 1) / NT;
+      // all candidate indices of this thread first, then the column gathers: 2 x NF loads in flight
+      constexpr int LPT = NL_TILE / NT;
       int pidx[LPT];
 #pragma unroll
       for(int u = 0; u < LPT; ++u) {
@@ -560,172 +506,32 @@ __global__ void __launch_bounds__(32 * NW) k_sweep(Tree t, Cols c, Search sr, Ph
       for(int u = 0; u < LPT; ++u) {
         const int i = tid + u * NT;
         if(pidx[u] >= 0) {
-          if(NEED_IDX) tidx[i] = pidx[u];
+          if(TC::hasIDX) tidx[i] = pidx[u];
 #pragma unroll
           for(int j = 0; j < NF; ++j) tile[j][i] = c.f[TC::col(j)][pidx[u]];
         }
       }
     }
-#if FSPH_SW_MASK_REGS
-    // this thread's mask words of the tile straight into registers (coalesced: the mask is laid out [word][particle]);
-    // the loads are in flight together with the tile gathers above
-    uint32_t mw[TILE / 32];
-    {
-      const int nwt = (tc + 31) >> 5;
-      const uint32_t * mrow = sr.mask + mo + (uint64_t)(tb >> 5) * Ppad + tid;
-#pragma unroll
-      for(int w = 0; w < TILE / 32; ++w) mw[w] = (active && w < nwt) ? mrow[(size_t)w * Ppad] : 0u;
-    }
     __syncthreads();
-    for(;;) {
-      int cnt = 0;
-#pragma unroll
-      for(int w = 0; w < TILE / 32; ++w) {
-        while(mw[w] != 0u && cnt < LCAP) {
-          nlist[cnt++][tid] = (uint8_t)(w * 32 + __ffs(mw[w]) - 1);
-          mw[w] &= mw[w] - 1;
-        }
-      }
-      const int jmax = __reduce_max_sync(0xffffffffu, cnt);
-      if(jmax == 0) break;
-      for(int j = 0; j < jmax; j += 2) {
-        const bool v0 = j < cnt, v1 = j + 1 < cnt;
-        const int ci0 = v0 ? nlist[j][tid] : 0;
-        const int ci1 = v1 ? nlist[j + 1][tid] : ci0;
-        pair_body<D, K, OP>(o, tile, tidx, pp, ci0, v0);
-        pair_body<D, K, OP>(o, tile, tidx, pp, ci1, v1);
-      }
-      if(jmax < LCAP) break;
+    // uniform pair loop over the lanes' lists, two pairs per iteration (independent fp64 dependency chains); the
+    // entries of the next iteration are loaded before this one is evaluated
+    int e0 = cmax > 0 ? rows[32] : 0, e1 = cmax > 1 ? rows[64] : 0;
+    for(int j = 0; j < cmax; j += 2) {
+      const bool v0 = j < cnt, v1 = j + 1 < cnt;
+      const int ci0 = v0 ? e0 : 0, ci1 = v1 ? e1 : 0;
+      const size_t slot0 = (size_t)(rb + 1 + j) * 32 + lane, slot1 = slot0 + 32;
+      double a0 = 0.0, a1 = 0.0, p0 = 0.0, p1 = 0.0;
+      if(A_RD) { a0 = v0 ? pair_a[slot0] : 0.0; a1 = v1 ? pair_a[slot1] : 0.0; }
+      if(P_RD) { p0 = v0 ? pair_pi[slot0] : 0.0; p1 = v1 ? pair_pi[slot1] : 0.0; }
+      if(j + 2 < cmax) e0 = rows[(3 + j) * 32];
+      if(j + 3 < cmax) e1 = rows[(4 + j) * 32];
+      pair_body<D, K, OP, CM>(o, tile, tidx, pp, ci0, v0, a0, p0);
+      pair_body<D, K, OP, CM>(o, tile, tidx, pp, ci1, v1, a1, p1);
+      if(A_WR) { if(v0) pair_a[slot0] = a0; if(v1) pair_a[slot1] = a1; }
+      if(P_WR) { if(v0) pair_pi[slot0] = p0; if(v1) pair_pi[slot1] = p1; }
     }
-#else
-    {
-      const int nwt = (tc + 31) >> 5;
-      const uint32_t * mrow = sr.mask + mo + (uint64_t)(tb >> 5) * Ppad;
-      for(int i = tid; i < nwt * Ppad; i += NT) mtile[i / Ppad][i % Ppad] = mrow[i];
-    }
-    __syncthreads();
-    // Decode this thread's mask bits into a short list of tile-local candidate indices (<= LCAP per round),
-    // then run a uniform, branch-free pair loop over the lists: two pairs per iteration (independent fp64
-    // dependency chains), trip count = the warp's longest list.
-    const int nw = active ? (tc + 31) >> 5 : 0;
-    int w = 0;
-    uint32_t m = nw > 0 ? mtile[0][tid] : 0u;
-    for(;;) {
-      int cnt = 0;
-      while(cnt < LCAP) {
-        while(m == 0 && w + 1 < nw) m = mtile[++w][tid];
-        if(m == 0) break;
-        nlist[cnt++][tid] = (uint8_t)(w * 32 + __ffs(m) - 1);
-        m &= m - 1;
-      }
-      const int jmax = __reduce_max_sync(0xffffffffu, cnt);
-      if(jmax == 0) break;
-      for(int j = 0; j < jmax; j += 2) {
-        const bool v0 = j < cnt, v1 = j + 1 < cnt;
-        const int ci0 = v0 ? nlist[j][tid] : 0;
-        const int ci1 = v1 ? nlist[j + 1][tid] : ci0;
-        pair_body<D, K, OP>(o, tile, tidx, pp, ci0, v0);
-        pair_body<D, K, OP>(o, tile, tidx, pp, ci1, v1);
-      }
-      if(jmax < LCAP) break;
-    }
-#endif
   }
   if(active) store_own<D, OP>(o, c, pp, status);
-}
-
-// Two particles per thread.  The pair loop is bound by shared-memory wavefronts (ncu: l1tex data pipe 77 % of peak,
-// fp64 pipe 55 %): every pair gathers its neighbour's 5-15 doubles from the tile at a lane-private address.  Key
-// neighbours (2t, 2t+1) share ~80 % of their neighbours, so a thread that owns both reads each common neighbour
-// once and evaluates it for both (a neighbour of only one of them costs a predicated-off evaluation).
-template<int D, int K, int OP, int NW>
-__global__ void __launch_bounds__(32 * NW) k_sweep2(Tree t, Cols c, Search sr, PhysParams pp, int g_begin, uint32_t * __restrict__ status) {
-  using TC = TileCols<D, OP>;
-  constexpr int NF = TC::NF;
-  constexpr int NT = 32 * NW;
-  constexpr int TILE = SwTile<OP>::N;
-  constexpr bool NEED_IDX = OP == OP_VSIG || OP == OP_ACCV;
-  __shared__ double tile[NF][TILE];
-  __shared__ int32_t tidx[NEED_IDX ? TILE : 1];
-  __shared__ uint32_t mtile[TILE / 32][2 * NT];  // this tile's mask words, [word][particle]
-  __shared__ uint16_t nlist[SW_LCAP][NT];        // decoded union lists of one round: candidate | owner bits << 8
-
-  const int g = g_begin + blockIdx.x, tid = threadIdx.x;
-  int start, P;
-  {
-    int v = t.cell[sr.wc_cell[g]];
-    if(v >= 0) { start = v; P = 1; }
-    else { start = t.node_start[~v]; P = t.sub[~v]; }
-  }
-  const int Ppad = (P + 31) & ~31;
-  const uint64_t co = sr.cand_off[g], mo = sr.mask_off[g];
-  const int C = sr.ncand[g];
-  const bool act0 = 2 * tid < P, act1 = 2 * tid + 1 < P;
-
-  Own<D> o0, o1;
-  load_own<D, OP>(o0, c, start + 2 * tid, act0);
-  load_own<D, OP>(o1, c, start + 2 * tid + 1, act1);
-
-  for(int tb = 0; tb < C; tb += TILE) {
-    const int tc = min(TILE, C - tb);
-    __syncthreads();
-    {
-      constexpr int LPT = (TILE + NT - 1) / NT;
-      int pidx[LPT];
-#pragma unroll
-      for(int u = 0; u < LPT; ++u) {
-        const int i = tid + u * NT;
-        pidx[u] = i < tc ? sr.cand[co + tb + i] : -1;
-      }
-#pragma unroll
-      for(int u = 0; u < LPT; ++u) {
-        const int i = tid + u * NT;
-        if(pidx[u] >= 0) {
-          if(NEED_IDX) tidx[i] = pidx[u];
-#pragma unroll
-          for(int j = 0; j < NF; ++j) tile[j][i] = c.f[TC::col(j)][pidx[u]];
-        }
-      }
-    }
-    {
-      const int nwt = (tc + 31) >> 5;
-      const uint32_t * mrow = sr.mask + mo + (uint64_t)(tb >> 5) * Ppad;
-      for(int i = tid; i < nwt * Ppad; i += NT) mtile[i / Ppad][i % Ppad] = mrow[i];
-    }
-    __syncthreads();
-    const int nw = act0 ? (tc + 31) >> 5 : 0;
-    int w = 0;
-    uint32_t m0 = nw > 0 ? mtile[0][2 * tid] : 0u;
-    uint32_t m1 = (nw > 0 && act1) ? mtile[0][2 * tid + 1] : 0u;
-    for(;;) {
-      int cnt = 0;
-      while(cnt < SW_LCAP) {
-        while((m0 | m1) == 0 && w + 1 < nw) {
-          ++w;
-          m0 = mtile[w][2 * tid];
-          m1 = act1 ? mtile[w][2 * tid + 1] : 0u;
-        }
-        const uint32_t mu = m0 | m1;
-        if(mu == 0) break;
-        const int b = __ffs(mu) - 1;
-        nlist[cnt++][tid] = (uint16_t)((w * 32 + b) | (((m0 >> b) & 1u) << 8) | (((m1 >> b) & 1u) << 9));
-        const uint32_t clr = ~(1u << b);
-        m0 &= clr;
-        m1 &= clr;
-      }
-      const int jmax = __reduce_max_sync(0xffffffffu, cnt);
-      if(jmax == 0) break;
-      for(int j = 0; j < jmax; ++j) {
-        const int e = j < cnt ? nlist[j][tid] : 0;
-        const int ci = e & 0xff;
-        pair_body<D, K, OP>(o0, tile, tidx, pp, ci, (e >> 8) & 1);
-        pair_body<D, K, OP>(o1, tile, tidx, pp, ci, (e >> 9) & 1);
-      }
-      if(jmax < SW_LCAP) break;
-    }
-  }
-  if(act0) store_own<D, OP>(o0, c, pp, status);
-  if(act1) store_own<D, OP>(o1, c, pp, status);
 }
 
 __global__ void __launch_bounds__(256) k_prho2(Cols c, int64_t n) {
@@ -741,48 +547,86 @@ __global__ void __launch_bounds__(256) k_fill(double * p, int64_t n, double v) {
   if(i < n) p[i] = v;
 }
 
-template<int D, int K, int OP>
+template<int D, int K, int OP, int CM>
 static void launch_sweep(System & s) {
   const Search & sr = s.search;
   if(OP != OP_DENSITY && OP != OP_VSIG) FSPH_LAUNCH(k_prho2, (unsigned)((s.n + 255) / 256), 256, s.stream, s.cols(), s.n);
   uint32_t * st = s.b_status.as<uint32_t>();
-  for(int cls = 0; cls < 4; ++cls) {
-    const int b = sr.class_off[cls], n = sr.class_off[cls + 1] - b;
-    if(n <= 0) continue;
-#if FSPH_SWEEP_PPT == 2
-    // two particles per thread: classes of <= 32 / 64 particles fit one warp, <= 96 / 128 two warps
-    switch(cls) {
-      case 0: FSPH_LAUNCH((k_sweep<D, K, OP, 1>), n, 32, s.stream, s.tree, s.cols(), sr, s.phys(), b, st); break;
-      case 1: FSPH_LAUNCH((k_sweep2<D, K, OP, 1>), n, 32, s.stream, s.tree, s.cols(), sr, s.phys(), b, st); break;
-      default: FSPH_LAUNCH((k_sweep2<D, K, OP, 2>), n, 64, s.stream, s.tree, s.cols(), sr, s.phys(), b, st); break;
+  FSPH_LAUNCH_SMEM((k_sweep<D, K, OP, CM>), sr.nblk, BLK_BODIES, (TileCols<D, OP, CM>::smem_bytes()), s.stream, s.cols(), sr, s.phys(), st,
+    s.b_pair_a.as<double>(), s.b_pair_pi.as<double>());
+}
+
+// Pair caches: decide once per neighbour structure whether they fit (two doubles per list slot next to everything else
+// the step needs); FSPH_PAIR_CACHE=0/1 overrides (tests run both ways).
+static bool pair_cache_ready(System & s) {
+  if(s.pair_cache_epoch == s.search_epoch) return s.pair_cache_on;
+  s.pair_cache_epoch = s.search_epoch;
+  s.pair_a_epoch = 0;
+  s.pair_pi_valid = false;
+  int want = -1;
+  if(const char * e = getenv("FSPH_PAIR_CACHE")) want = atoi(e);
+  const size_t need = (size_t)(s.search.nrows + 2) * 32 * 8;
+  bool on = want != 0;
+  if(on && (s.b_pair_a.cap < need || s.b_pair_pi.cap < need)) {
+    size_t fr = 0, tot = 0;
+    FSPH_CUDA_OK(cudaMemGetInfo(&fr, &tot));
+    const size_t have = s.b_pair_a.cap + s.b_pair_pi.cap;
+    // keep 12 % of the device (and at least 2 GB) free for the buffers that still grow during a run
+    const size_t reserve = std::max<size_t>(tot / 8, (size_t)2 << 30);
+    if(want < 0 && fr + have < 2 * (need + need / 8) + reserve) on = false;
+    if(on) {
+      try {
+        s.b_pair_a.reserve(need);
+        s.b_pair_pi.reserve(need);
+      }
+      catch(const std::exception &) {
+        cudaGetLastError();
+        s.b_pair_a.release();
+        s.b_pair_pi.release();
+        on = false;
+      }
     }
-#else
-    switch(cls) {
-      case 0: FSPH_LAUNCH((k_sweep<D, K, OP, 1>), n, 32, s.stream, s.tree, s.cols(), sr, s.phys(), b, st); break;
-      case 1: FSPH_LAUNCH((k_sweep<D, K, OP, 2>), n, 64, s.stream, s.tree, s.cols(), sr, s.phys(), b, st); break;
-      case 2: FSPH_LAUNCH((k_sweep<D, K, OP, 3>), n, 96, s.stream, s.tree, s.cols(), sr, s.phys(), b, st); break;
-      default: FSPH_LAUNCH((k_sweep<D, K, OP, 4>), n, 128, s.stream, s.tree, s.cols(), sr, s.phys(), b, st); break;
-    }
-#endif
   }
+  if(!on) { s.b_pair_a.release(); s.b_pair_pi.release(); }
+  s.pair_cache_on = on;
+  return on;
 }
 
 template<int D, int K>
 static void sweep_dk(System & s, int op) {
+  const bool cache = pair_cache_ready(s);
+  const bool a_ok = cache && s.pair_a_epoch == s.search_epoch;   // A of this neighbour structure is stored
   switch(op) {
     case FSPH_SWEEP_DENSITY_PRESSURE_SOUNDSPEED:
-      launch_sweep<D, K, OP_DENSITY>(s);
-      launch_sweep<D, K, OP_VSIG>(s);
+    case 100:   // fsph_step: density / P / cs only (the signal speed rides on the acceleration sweep)
+      s.pair_pi_valid = false;   // rho, cs change
+      if(cache && !a_ok) {
+        launch_sweep<D, K, OP_DENSITY, CM_FULL>(s);
+        s.pair_a_epoch = s.search_epoch;
+      }
+      else launch_sweep<D, K, OP_DENSITY, CM_NONE>(s);
+      if(op != 100) launch_sweep<D, K, OP_VSIG, CM_NONE>(s);
       break;
-    case FSPH_SWEEP_ACCELERATION: launch_sweep<D, K, OP_ACC>(s); break;
-    case 100: launch_sweep<D, K, OP_DENSITY>(s); break;   // fsph_step: density / P / cs only ...
-    case 101: launch_sweep<D, K, OP_ACCV>(s); break;      // ... and the signal speed rides on the acceleration sweep
+    case FSPH_SWEEP_ACCELERATION:
+      if(a_ok) { launch_sweep<D, K, OP_ACC, CM_FULL>(s); s.pair_pi_valid = true; }
+      else launch_sweep<D, K, OP_ACC, CM_NONE>(s);
+      break;
+    case 101:
+      if(a_ok) { launch_sweep<D, K, OP_ACCV, CM_FULL>(s); s.pair_pi_valid = true; }
+      else launch_sweep<D, K, OP_ACCV, CM_NONE>(s);
+      break;
     case FSPH_SWEEP_DUDT:
       if(s.iteration < s.par.relaxation_steps)
         FSPH_LAUNCH(k_fill, (unsigned)((s.n + 255) / 256), 256, s.stream, s.col[F_DUDT].as<double>(), s.n, 0.0);
-      else launch_sweep<D, K, OP_DUDT>(s);
+      else if(a_ok && s.pair_pi_valid) launch_sweep<D, K, OP_DUDT, CM_FULL>(s);
+      else if(a_ok) launch_sweep<D, K, OP_DUDT, CM_A_ONLY>(s);
+      else launch_sweep<D, K, OP_DUDT, CM_NONE>(s);
       break;
-    case FSPH_SWEEP_DEDT: launch_sweep<D, K, OP_DEDT>(s); break;
+    case FSPH_SWEEP_DEDT:
+      if(a_ok && s.pair_pi_valid) launch_sweep<D, K, OP_DEDT, CM_FULL>(s);
+      else if(a_ok) launch_sweep<D, K, OP_DEDT, CM_A_ONLY>(s);
+      else launch_sweep<D, K, OP_DEDT, CM_NONE>(s);
+      break;
     default: throw std::runtime_error("unknown sweep op");
   }
 }

@@ -614,17 +614,9 @@ __global__ void __launch_bounds__(256) k_flag_nonzero(const uint32_t * __restric
   if(i < n) out[i] = in[i] != 0;
 }
 __global__ void __launch_bounds__(256) k_wc_compact(const uint32_t * __restrict__ wc_at, const uint32_t * __restrict__ ex, int64_t n,
-  Tree t, uint64_t * __restrict__ keys, uint32_t * __restrict__ vals, uint32_t * __restrict__ class_count) {
+  int32_t * __restrict__ wc_cell) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(i < n && wc_at[i]) {
-    const uint32_t c = wc_at[i] - 1u;
-    const int v = t.cell[c];
-    const int P = v >= 0 ? 1 : t.sub[~v];
-    const uint32_t cls = (uint32_t)((P + 31) / 32 - 1);
-    keys[ex[i]] = ((uint64_t)cls << 32) | ex[i];
-    vals[ex[i]] = c;
-    atomicAdd(&class_count[cls], 1u);
-  }
+  if(i < n && wc_at[i]) wc_cell[ex[i]] = (int32_t)(wc_at[i] - 1u);
 }
 
 void mark_maximal_cells(System & s, int limit, bool skip_ghosts, uint32_t * at) {
@@ -635,7 +627,7 @@ void mark_maximal_cells(System & s, int limit, bool skip_ghosts, uint32_t * at) 
 }
 
 void find_work_cells(System & s) {
-  const int64_t n = s.n, nc = s.tree.ncells;
+  const int64_t n = s.n;
   s.b_cnt0.reserve((size_t)(n + 1) * 4);
   s.b_tmp[0].reserve((size_t)(n + 1) * 4);
   uint32_t * wc_at = s.b_cnt0.as<uint32_t>();
@@ -647,24 +639,10 @@ void find_work_cells(System & s) {
   uint32_t nwc = 0;
   FSPH_CUDA_OK(cudaMemcpyAsync(&nwc, ex + n, 4, cudaMemcpyDeviceToHost, s.stream));
   FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
-  const size_t m = std::max<uint32_t>(nwc, 1);
-  s.b_wc_cell.reserve(m * 4);
-  s.b_cnt1.reserve(m * 8 * 2 + m * 4 + 64);
-  uint64_t * keys = s.b_cnt1.as<uint64_t>();
-  uint64_t * keys2 = keys + m;
-  uint32_t * vals = reinterpret_cast<uint32_t *>(keys2 + m);
-  uint32_t * ccount = s.b_status.as<uint32_t>() + 4;
-  FSPH_CUDA_OK(cudaMemsetAsync(ccount, 0, 16, s.stream));
-  FSPH_LAUNCH(k_wc_compact, nbp, 256, s.stream, wc_at, ex, n, s.tree, keys, vals, ccount);
+  s.b_wc_cell.reserve((size_t)std::max<uint32_t>(nwc, 1) * 4);
   s.search.wc_cell = s.b_wc_cell.as<int32_t>();
   s.search.nwc = (int)nwc;
-  // stable counting sort by size class (Morton order kept inside a class)
-  radix_pass(s, keys, vals, keys2, reinterpret_cast<uint32_t *>(s.search.wc_cell), nwc, 32);
-  uint32_t hc[4];
-  FSPH_CUDA_OK(cudaMemcpyAsync(hc, ccount, 16, cudaMemcpyDeviceToHost, s.stream));
-  FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
-  s.search.class_off[0] = 0;
-  for(int c = 0; c < 4; ++c) s.search.class_off[c + 1] = s.search.class_off[c] + (int)hc[c];
+  FSPH_LAUNCH(k_wc_compact, nbp, 256, s.stream, wc_at, ex, n, s.search.wc_cell);
   FSPH_CUDA_OK(cudaGetLastError());
 }
 

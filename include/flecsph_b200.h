@@ -226,6 +226,12 @@ int32_t fsph_tree_get_leaf_depth(fsph_system * s, int32_t * depth);
  * offsets has n+1 entries; call with ids == NULL to get only offsets. */
 int32_t fsph_neighbor_lists(fsph_system * s, int64_t * offsets, int64_t * ids);
 
+/* Device micro-benchmarks (roofline denominators measured on the GPU the run uses; SURVEY.md 8d asks for the fp64
+ * one because MEASURED_PEAKS.json has none): sustained DFMA rate in TFLOP/s and 128-bit copy bandwidth in GB/s
+ * (read + write bytes).  < 0 on failure.  No reference counterpart (the reference has no GPU path). */
+double fsph_measure_fp64_tflops(int32_t device, int32_t reps);
+double fsph_measure_copy_gbs(int32_t device, int64_t bytes, int32_t reps);
+
 /* Per-phase device times of the last fsph_step in milliseconds (CUDA events);
  * names is a ';'-separated list, returns the number of phases. */
 int32_t fsph_phase_times(fsph_system * s, double * ms, int32_t cap, const char ** names);

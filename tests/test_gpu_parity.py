@@ -151,10 +151,11 @@ def test_error_paths():
         G2.update_iteration()                            # duplicate keys
 
 
-def test_global_memory_frontier_fallback(monkeypatch):
-    """The neighbour walk keeps its node frontier in shared memory; cells whose frontier outgrows it are redone with a
-    per-CTA strip of global memory.  Forced here: neighbour sets and three driver iterations must not change."""
-    monkeypatch.setenv("FSPH_SEARCH_FORCE_GLOBAL_QUEUE", "1")
+def test_search_capacity_retry(monkeypatch):
+    """The neighbour structure is bump-allocated against a capacity estimate; when it does not fit, the cursors keep
+    counting and the search is repeated with the exact sizes.  Forced here with a tiny first capacity: neighbour sets
+    and three driver iterations must not change."""
+    monkeypatch.setenv("FSPH_SEARCH_TINY_CAP", "1")
     for name, kw in (("random", dict(n=3000, seed=3, h_jitter=0.2)), ("collapse", dict(nx=12))):
         f, par, dim = case(name, **kw)
         G, R = make_system("cuda", f, par, dim), make_system(oracle_backend(dim), f, par, dim)
@@ -167,3 +168,20 @@ def test_global_memory_frontier_fallback(monkeypatch):
     for it in range(3):
         G.step(initial=(it == 0)); R.step(initial=(it == 0))
     assert_fields_close(G, R, ["pos", "vel", "rho", "P", "u", "acc", "dedt", "h", "vsig", "dt"], 1e-10)
+
+
+@pytest.mark.parametrize("cache", ["0", "1"])
+@pytest.mark.parametrize("name,kw", [("sedov", dict(nx=14)), ("collapse", dict(nx=10)),
+                                     ("random", dict(n=2000, seed=21, h_jitter=0.2, par=dict(pressure_updates_number=2)))])
+def test_pair_cache_modes(monkeypatch, cache, name, kw):
+    """The sweeps with and without the per-pair caches (kernel-gradient factor stored by the density sweep, viscosity
+    by the acceleration sweep): both ways within 1e-10 of the reference, through three driver iterations (the
+    two-pressure-pass case re-evaluates the viscosity in the second energy pass)."""
+    monkeypatch.setenv("FSPH_PAIR_CACHE", cache)
+    f, par, dim = case(name, **kw)
+    G, R = make_system("cuda", f, par, dim), make_system(oracle_backend(dim), f, par, dim)
+    names = ["pos", "vel", "rho", "P", "u", "cs", "acc", "h", "vsig", "dt"] + \
+            (["dedt", "e"] if par.get("thermokinetic_formulation", 1) else ["dudt"])
+    for it in range(3):
+        G.step(initial=(it == 0)); R.step(initial=(it == 0))
+        assert_fields_close(G, R, names, 1e-10 if it < 2 else 1e-9)
