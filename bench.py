@@ -33,7 +33,8 @@ ALGO_BYTES_PER_UPDATE = 1386.0   # hydro thermokinetic path, fp64 
 PHASE_BYTES = {"density": 120.0, "acceleration": 112.0, "dedt": 120.0, "dudt": 120.0, "search": 52.0, "sort": 416.0,
                "tree": 90.0, "range_keys": 64.0, "elementwise": 404.0, "timestep": 88.0}
 PAIR_FLOPS = {"density": 43.0, "acceleration": 77.0, "dedt": 90.0, "dudt": 82.0}   # SURVEY.md 8d, per accepted pair
-FP64_PEAK_TFLOPS = 37.2   # nominal B200 vector fp64 (148 SM x 64 DFMA/clk x 2 x 1.965 GHz); not in MEASURED_PEAKS.json
+FP64_NOMINAL_TFLOPS = 37.2   # nominal B200 vector fp64 (148 SM x 64 DFMA/clk x 2 x 1.965 GHz); the measured DFMA rate of
+                             # the GPU the run uses (fsph_measure_fp64_tflops) is the denominator of the fp64 fractions
 
 
 def measured_peaks():
@@ -103,6 +104,38 @@ def make_cuda_system(f, par, device):
     return s
 
 
+def make_sphere_system(kind, nx, device, slab=None, allsum=None, **par_over):
+    """A Sedov / Noh / collapse FCC sphere generated on the device (fsph_generate_lattice + fsph_id_fill: the same bodies
+    as flecsph_b200/initial_data.py, bit for bit).  Returns (system, n_local)."""
+    from flecsph_b200 import capi, initial_data as idata
+    par = {"sedov": idata.sedov_3d, "noh": idata.noh_3d, "collapse": idata.collapse_3d}[kind](nx=4)[1]
+    par.update(par_over)
+    p = capi.default_params(3, **par)
+    s = capi.BodySystem(p, backend="cuda", device=device)
+    n_local, _ = idata.sphere_on_device(s, kind, nx, slab=slab, allsum=allsum)
+    s.set_time(p.initial_dt, 0.0, 0)
+    return s, n_local
+
+
+def time_steps(s, steps, warmup, barrier=None):
+    """initial iteration + warm-up + `steps` timed iterations; returns (device ms per step, phases of the timed steps)."""
+    s.step(initial=True)
+    for _ in range(warmup):
+        s.step()
+    if barrier:
+        barrier()
+    tot, acc = 0.0, {}
+    for _ in range(steps):
+        s.step()
+        ph = s.phase_times()
+        tot += ph.get("total", 0.0)
+        for k, v in ph.items():
+            acc[k] = acc.get(k, 0.0) + v
+    if barrier:
+        barrier()
+    return tot / steps, {k: round(v / steps, 2) for k, v in acc.items() if k != "total" and not k.startswith("dd:")}
+
+
 # state a non-initial step reads / results it produces (column, components)
 def e2e_columns(capi):
     up = [(capi.COL_POS, 3), (capi.COL_VEL, 3), (capi.COL_ACC, 3), (capi.COL_GACC, 3), (capi.COL_MASS, 1), (capi.COL_H, 1),
@@ -113,13 +146,9 @@ def e2e_columns(capi):
     return up, down
 
 
-def run_cpu_reference(nx, steps, warmup):
-    """The reference's own step loop (unmodified headers, -Ofast build of oracle/_ref) on one host core."""
+def _cpu_worker(nx, steps, warmup, barrier, q):
+    """One replica of the reference's own step loop (unmodified headers, -Ofast build of oracle/_ref) on one host core."""
     from flecsph_b200 import capi, initial_data as idata
-    path = capi.library_path("ref_fast")
-    kind = "reference"
-    if not os.path.exists(path):
-        return None
     f, par = idata.sedov_3d(nx=nx)
     p = capi.default_params(3, **par)
     s = capi.BodySystem(p, backend="ref_fast")
@@ -129,15 +158,93 @@ def run_cpu_reference(nx, steps, warmup):
     s.step(initial=True)
     for _ in range(warmup):
         s.step()
+    barrier.wait()
     t0 = time.perf_counter()
     for _ in range(steps):
         s.step()
     t = time.perf_counter() - t0
     s.close()
-    return {"value": n * steps / t, "unit": "particle-updates/s", "cores": 1, "kind": kind,
-            "sample": "Sedov 3-D FCC sphere lattice_nx=%d (%d particles), %d non-initial steps after the initial one + %d warm-up, "
-                      "1 rank (the reference hot path is single-threaded per MPI rank; no MPI in this image), -Ofast" % (nx, n, steps, warmup),
-            "ms_per_step": 1e3 * t / steps, "n": n}
+    q.put((n, t))
+
+
+def run_cpu_reference(nx, steps, warmup, nproc=None):
+    """The reference hot path is single-threaded per MPI rank and there is no MPI in this image, so "all the host
+    cores" means one independent replica of the same Sedov sample per core, started together (ranks without
+    communication: an upper bound for what an MPI run of the reference could reach on this host)."""
+    import multiprocessing as mp
+    from flecsph_b200 import capi
+    if not os.path.exists(capi.library_path("ref_fast")):
+        return None
+    nproc = nproc or max(1, min(os.cpu_count() or 1, 32))
+    ctx = mp.get_context("spawn")
+    barrier, q = ctx.Barrier(nproc), ctx.Queue()
+    procs = [ctx.Process(target=_cpu_worker, args=(nx, steps, warmup, barrier, q)) for _ in range(nproc)]
+    for pr in procs:
+        pr.start()
+    res = [q.get() for _ in procs]
+    for pr in procs:
+        pr.join()
+    n, t = res[0][0], max(r[1] for r in res)
+    return {"value": nproc * n * steps / t, "unit": "particle-updates/s", "cores": nproc, "kind": "reference",
+            "sample": "Sedov 3-D FCC sphere lattice_nx=%d (%d particles) per replica, %d independent replicas (one per host core; the "
+                      "reference hot path is single-threaded per MPI rank and there is no MPI in this image), %d non-initial steps "
+                      "after the initial one + %d warm-up, -Ofast; %.3g updates/s per core" % (nx, n, nproc, steps, warmup, n * steps / t),
+            "ms_per_step": 1e3 * t / steps, "n": n, "per_core": n * steps / t}
+
+
+def reference_nx(steps, warmup, budget_s=270.0, rate_per_core=6.0e4):
+    """Largest lattice_nx (<= 112, i.e. ~1.0 M bodies per replica) whose --steps/--warmup run fits the time budget."""
+    from flecsph_b200 import initial_data as idata
+    nmax = budget_s * rate_per_core / (steps + warmup + 1.5)
+    nx = 112
+    while nx > 40 and 0.74 * nx ** 3 > nmax:
+        nx -= 2
+    return nx
+
+
+def parity_record(capi, dist, torch, rank, world, local_rank, nx=143):
+    """Decomposed-vs-one-rank check over NCCL on a Sedov sphere of ~2.1 M bodies, outside the timed region: every rank
+    loads a random share, two driver iterations run decomposed, and every rank compares the bodies it ends up owning
+    with its own single-GPU run of the same input (matched by id).  Returns {bodies, max_rel, nneigh_mismatch}."""
+    from flecsph_b200 import initial_data as idata
+    f, par = idata.sedov_3d(nx=nx)
+    n = len(f["mass"])
+    owner = np.random.default_rng(11).integers(0, world, n)
+    mine = {k: np.ascontiguousarray(v[owner == rank]) for k, v in f.items()}
+    p = capi.default_params(3, **par)
+    s = capi.BodySystem(p, backend="cuda", device=local_rank)
+    s.load_bodies(mine)
+    s.set_time(p.initial_dt, 0.0, 0)
+    uid = [capi.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    s.comm_init_nccl(uid[0], rank, world)
+    one = capi.BodySystem(p, backend="cuda", device=local_rank)
+    one.load_bodies(f)
+    one.set_time(p.initial_dt, 0.0, 0)
+    for it in range(2):
+        s.step(initial=(it == 0))
+        one.step(initial=(it == 0))
+    names = ["pos", "vel", "rho", "P", "u", "cs", "acc", "dedt", "h", "vsig", "dt"]
+    ids, rid = s.get(capi.COL_ID), one.get(capi.COL_ID)
+    order = np.argsort(rid)
+    at = order[np.searchsorted(rid[order], ids)]
+    worst = 0.0
+    for nm in names:
+        col = capi.COL_NAMES.index(nm)
+        ref = one.get(col)
+        got = s.get(col)
+        scale = np.abs(ref).max()
+        worst = max(worst, float(np.abs(got - ref[at]).max() / max(scale, 1e-300)))
+    mism = int((s.get(capi.COL_NNEIGH) != one.get(capi.COL_NNEIGH)[at]).sum())
+    tt = torch.tensor([worst, float(mism), float(len(ids))], dtype=torch.float64, device="cuda")
+    mx = tt.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    dist.all_reduce(tt)
+    s.close()
+    one.close()
+    return {"bodies": n, "owned_sum": int(tt[2]), "max_rel": float(mx[0]), "nneigh_mismatch": int(tt[1]), "ranks": world,
+            "what": "Sedov nx=%d, random initial distribution, 2 driver iterations over NCCL vs the same input on one GPU; "
+                    "max over %s of max|a-b|/max|b|, and the number of bodies whose neighbour count differs" % (nx, ",".join(names))}
 
 
 def main():
@@ -147,9 +254,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--particles", type=float, default=64e6, help="target particle count per GPU")
-    ap.add_argument("--cpu-nx", type=int, default=64, help="lattice_nx of the bounded CPU sample")
+    ap.add_argument("--cpu-nx", type=int, default=0, help="lattice_nx of the CPU sample (0: chosen from the time budget)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE.json configurations / scaling sub-records")
+    ap.add_argument("--host-ids", action="store_true", help="generate the initial data on the host (numpy) instead of on the device")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -162,11 +271,14 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        r = run_cpu_reference(a.cpu_nx, a.steps, a.warmup)
+        nx = a.cpu_nx or reference_nx(a.steps, a.warmup)
+        r = run_cpu_reference(nx, a.steps, a.warmup)
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libflecsph_ref_3d_fast.so was not built/shipped"}))
             return 0
-        config["particles"] = r["n"]
+        config["particles"] = r["n"] * r["cores"]
+        config["particles_per_replica"] = r["n"]
+        config["lattice_nx"] = nx
         line = {"impl": "reference", "metric": "particle-updates/sec per SPH step (Sedov 3D)", "value": r["value"],
                 "unit": "particle-updates/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -178,7 +290,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from flecsph_b200 import capi
+    from flecsph_b200 import capi, initial_data as idata
     if os.environ.get("FSPH_BENCH_TRACE"):
         import faulthandler
         faulthandler.dump_traceback_later(int(os.environ["FSPH_BENCH_TRACE"]), repeat=True, file=sys.stderr)
@@ -193,33 +305,47 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    if world == 1:
-        f, par, nx = sedov_fields(a.particles)
-        n = n_total = len(f["mass"])
+    def allsum(x):
+        if world == 1:
+            return int(x)
+        t = torch.tensor([int(x)], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        return int(t[0])
+
+    def join(s):
+        if world > 1:
+            uid = [capi.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            s.comm_init_nccl(uid[0], rank, world)
+
+    # measured denominators of this GPU: DFMA rate and copy bandwidth
+    lib = capi.load(capi.PRODUCT_LIB)
+    fp64_peak = float(lib.fsph_measure_fp64_tflops(local_rank, 3))
+    copy_gbs = float(lib.fsph_measure_copy_gbs(local_rank, 2 << 30, 3))
+
+    t_setup0 = time.perf_counter()
+    nx = idata.nx_for_particles(a.particles * world)
+    slab = (rank, world) if world > 1 else None
+    if a.host_ids:
+        f, par = idata.sedov_3d(nx=nx, slab=slab, allsum=allsum if world > 1 else None)
         s = make_cuda_system(f, par, local_rank)
+        n_local = len(f["mass"])
+        del f
+    else:
+        s, n_local = make_sphere_system("sedov", nx, local_rank, slab=slab, allsum=allsum if world > 1 else None)
+    n_total = allsum(n_local)
+    n = n_total // world
+    join(s)
+    if world == 1:
         config.update({"particles_per_gpu": n, "lattice_nx": nx, "parallelism": "single GPU"})
     else:
         # weak scaling: ONE Sedov sphere of world x 64 M bodies, Morton domain decomposition over the GPUs of the box
         # (sample-sort all-to-all, locally-essential-tree halo, ghost refresh: NCCL over NVLink; fsph_dist.cu).
         # Every rank generates a slab of lattice layers; the first update_iteration re-partitions by key.
-        from flecsph_b200 import initial_data as idata
-
-        def allsum(x):
-            t = torch.tensor([int(x)], dtype=torch.int64, device="cuda")
-            dist.all_reduce(t)
-            return int(t[0])
-        nx = idata.nx_for_particles(a.particles * world)
-        f, par = idata.sedov_3d(nx=nx, slab=(rank, world), allsum=allsum)
-        n_total = allsum(len(f["mass"]))
-        n = n_total // world
-        s = make_cuda_system(f, par, local_rank)
-        uid = [capi.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        s.comm_init_nccl(uid[0], rank, world)
         config.update({"particles_total": n_total, "particles_per_gpu": n, "lattice_nx": nx,
                        "parallelism": "Morton-key domain decomposition over %d GPUs (one rank per GPU): sample-sort all-to-all, "
                                       "locally-essential-tree halo, ghost refresh before every sweep, NCCL" % world})
-    del f
+    config["initial_data"] = "host numpy" if a.host_ids else "device (fsph_generate_lattice + fsph_id_fill), %.1f s" % (time.perf_counter() - t_setup0)
     s.step(initial=True)
     for _ in range(warmup):
         s.step()
@@ -251,6 +377,7 @@ def main():
         per_rank = [None] * world
         dist.all_gather_object(per_rank, {k: v / a.steps for k, v in phase_acc.items()})
         config["phases_ms_per_rank"] = [{k: round(v, 2) for k, v in d.items() if not k.startswith("dd:")} for d in per_rank]
+        config["dd_phases_ms_per_rank"] = [{k: round(v, 2) for k, v in d.items() if k.startswith("dd:")} for d in per_rank]
         for k in list(phase_acc):
             phase_acc[k] = max(d.get(k, 0.0) for d in per_rank) * a.steps
         config["ghosts_per_gpu_mean"] = float(ts[1]) / world
@@ -303,9 +430,42 @@ def main():
         e2e = {"value": n_total * a.steps / float(tte[0]), "unit": "particle-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": 1e3 * float(tte[0]) / a.steps}
         del bufs
-
-    # tear down on every rank in the same order (ncclCommDestroy of the library's communicator, then torch's)
     s.close()
+
+    # ---- sub-records outside the timed region: the other BASELINE.json configurations, strong scaling, N-rank parity ----
+    configs = {}
+    if not a.no_configs:
+        def sub(kind, target, label, **par_over):
+            nxs = idata.nx_for_particles(target)
+            ss, nl = make_sphere_system(kind, nxs, local_rank, slab=slab, allsum=allsum if world > 1 else None, **par_over)
+            ntot = allsum(nl)
+            join(ss)
+            ms, ph = time_steps(ss, 3, 2, barrier)
+            tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ss.close()
+            configs[label] = {"bodies": ntot, "lattice_nx": nxs, "ms_per_step": float(tm[0]), "updates_per_s": ntot / (float(tm[0]) * 1e-3),
+                              "phases_ms_rank0": ph, "n_gpus": world}
+        if world == 1:
+            # BASELINE.json configs[3] and [4] at full size on one GPU (KH: periodic box, eta 1.5; collapse: quintic, FMM)
+            f, par = idata.kh_3d(nx=310)
+            ss = make_cuda_system(f, par, local_rank)
+            nb = len(f["mass"])
+            del f
+            ms, ph = time_steps(ss, 3, 2)
+            configs["kelvin_helmholtz_3d"] = {"bodies": nb, "bodies_with_periodic_copies": ss.nbodies(), "ms_per_step": ms,
+                                              "updates_per_s": nb / (ms * 1e-3), "phases_ms_rank0": ph, "n_gpus": 1}
+            ss.close()
+            sub("collapse", 32e6, "collapse_newtonian_3d")
+            sub("sedov", 16e6, "sedov_3d_16M")
+        else:
+            sub("sedov", 64e6, "sedov_3d_64M_strong_scaling")     # the metric as BASELINE.json quotes it: 64 M bodies in total
+            sub("noh", 128e6, "noh_3d_128M")
+            sub("collapse", 32e6, "collapse_newtonian_3d")
+            configs["parity"] = parity_record(capi, dist, torch, rank, world, local_rank)
+
+    # tear down on every rank in the same order (ncclCommDestroy of the library's communicators, then torch's)
     if world > 1:
         barrier()
         dist.destroy_process_group()
@@ -318,32 +478,37 @@ def main():
     ach = n * PHASE_BYTES[dom] / (dom_ms * 1e-3) / 1e9
     # DRAM traffic of the dominant phase from the committed ncu capture of this exact workload (profiles/), else null
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r1_search_traffic_64M.json")
-    if dom == "search" and world == 1 and nx == 444 and os.path.exists(tp):
+    tp = os.path.join(ROOT, "profiles", "r2_traffic_64M.json")
+    if world == 1 and nx == 444 and os.path.exists(tp):
         tj = json.load(open(tp))
-        traffic, traffic_src = tj["traffic"], "profiles/r1_search_traffic_64M.json (%s)" % tj["how"]
+        if dom in tj.get("phases", {}):
+            traffic, traffic_src = tj["phases"][dom], "profiles/r2_traffic_64M.json (%s)" % tj["how"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                "traffic_source": traffic_src,
-                "peak_source": how, "algorithmic_bytes_per_particle": PHASE_BYTES[dom], "ms_per_launch": dom_ms,
-                "note": "not HBM-bound: the neighbour walk is latency-bound, the pair sweeps run with the shared-memory pipe at 73-77 % and the fp64 pipe at 47-55 % of peak (profiles/r1_ncu_*.md); see fp64 and roofline_step"}
+                "traffic_source": traffic_src, "peak_source": how, "copy_gbs_this_gpu": copy_gbs,
+                "algorithmic_bytes_per_particle": PHASE_BYTES[dom], "ms_per_launch": dom_ms,
+                "note": "the dominant phase is fp64-issue / latency bound, not HBM bound (profiles/r2_ncu_*.md): see fp64 (fractions of the "
+                        "measured DFMA rate) and roofline_step"}
     step_ach = n * ALGO_BYTES_PER_UPDATE / (t_dev / a.steps) / 1e9
     roofline_step = {"bound": "hbm", "achieved": step_ach, "peak": peak, "unit": "GB/s", "frac": step_ach / peak,
                      "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE}
-    fp64 = {}
+    fp64 = {"peak_tflops_measured": fp64_peak, "peak_tflops_nominal": FP64_NOMINAL_TFLOPS,
+            "how": "fsph_measure_fp64_tflops: 8 independent DFMA chains per thread, 8 CTAs of 256 threads per SM, best of 3"}
     for k in ("density", "acceleration", "dedt", "dudt"):
         if k in phases and phases[k] > 0:
             tf = n * nn_mean * PAIR_FLOPS[k] / (phases[k] * 1e-3) / 1e12
-            fp64[k] = {"tflops": tf, "frac_of_nominal_37.2": tf / FP64_PEAK_TFLOPS}
+            fp64[k] = {"tflops": tf, "frac_of_measured": tf / fp64_peak if fp64_peak > 0 else None, "frac_of_nominal_37.2": tf / FP64_NOMINAL_TFLOPS}
     cpu = None
-    if not a.no_cpu:
-        r = run_cpu_reference(a.cpu_nx, 2, 0)
+    if not a.no_cpu and world == 1:
+        r = run_cpu_reference(a.cpu_nx or 90, 2, 0)
         if r is not None:
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {"metric": "particle-updates/sec per SPH step (Sedov 3D)", "value": value, "unit": "particle-updates/s", "n_gpus": world,
             "steps": a.steps, "warmup": warmup, "ms_per_step": 1e3 * t_dev / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "roofline_step": roofline_step, "fp64": fp64, "cpu_baseline": cpu,
-            "phases_ms": phases, "mean_neighbors": nn_mean, "wall_ms_per_step": 1e3 * t_wall / a.steps}
+            "phases_ms": phases, "mean_neighbors": nn_mean, "wall_ms_per_step": 1e3 * t_wall / a.steps, "configs": configs}
+    if "parity" in configs:
+        line["parity"] = configs.pop("parity")
     print(json.dumps(line), flush=True)
     return 0
 

@@ -24,6 +24,7 @@ SOURCES = {
     "fsph_boundary.cu": ["-fmad=false"],
     "fsph_dist.cu": ["-fmad=false"],
     "fsph_diag.cu": [],
+    "fsph_idgen.cu": ["-fmad=false"],
 }
 
 

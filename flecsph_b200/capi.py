@@ -69,12 +69,14 @@ SYMBOLS = [
     "fsph_comm_unique_id", "fsph_comm_init_nccl", "fsph_local_group_create", "fsph_local_group_destroy",
     "fsph_comm_init_local", "fsph_comm_rank", "fsph_comm_size", "fsph_nghosts", "fsph_dd_choose_splitters",
     "fsph_dd_align_splitter", "fsph_measure_fp64_tflops", "fsph_measure_copy_gbs",
+    "fsph_generate_lattice", "fsph_count_within", "fsph_id_fill",
 ]
 # entry points only the product library has to provide (the checkers under oracle/ may omit them)
 PRODUCT_ONLY = {"fsph_set_time_state", "fsph_get_time_state", "fsph_tree_root", "fsph_comm_unique_id",
                 "fsph_comm_init_nccl", "fsph_local_group_create", "fsph_local_group_destroy", "fsph_comm_init_local",
                 "fsph_comm_rank", "fsph_comm_size", "fsph_nghosts", "fsph_dd_choose_splitters", "fsph_dd_align_splitter",
-                "fsph_measure_fp64_tflops", "fsph_measure_copy_gbs"}
+                "fsph_measure_fp64_tflops", "fsph_measure_copy_gbs", "fsph_generate_lattice", "fsph_count_within",
+                "fsph_id_fill"}
 
 # FSPH_PRODUCT_LIB: another build of the same library (kernel-variant A/B runs of scripts/ab_bench.sh)
 PRODUCT_LIB = os.environ.get("FSPH_PRODUCT_LIB") or os.path.join(ROOT, "flecsph_b200", "libflecsph_b200.so")
@@ -151,6 +153,9 @@ def load(path):
         "fsph_dd_align_splitter": (C.c_uint64, [i32, vp, i32, vp, i32, C.c_uint64]),
         "fsph_measure_fp64_tflops": (dbl, [i32, i32]),
         "fsph_measure_copy_gbs": (dbl, [i32, i64, i32]),
+        "fsph_generate_lattice": (i32, [vp, i32, i32, vp, vp, dbl, i32, i32, i64, C.POINTER(i64)]),
+        "fsph_count_within": (i32, [vp, vp, dbl, C.POINTER(i64)]),
+        "fsph_id_fill": (i32, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         if name in PRODUCT_ONLY and not hasattr(lib, name):
@@ -269,6 +274,24 @@ class BodySystem:
         self.resize(n)
         for name, arr in fields.items():
             self.set(COL_NAMES.index(name), arr)
+
+    # -- initial data on the device (lattice.h generators + the sphere set-ups of app/id_generators) ------------
+    def generate_lattice(self, lattice_type, domain_type, bmin, bmax, sep, slab=(0, 1), id_offset=0):
+        lo, hi = np.ascontiguousarray(bmin, np.float64), np.ascontiguousarray(bmax, np.float64)
+        n = C.c_int64()
+        self._ck(self.lib.fsph_generate_lattice(self.h, lattice_type, domain_type, lo.ctypes.data, hi.ctypes.data, float(sep),
+                                                 int(slab[0]), int(slab[1]), int(id_offset), C.byref(n)))
+        return n.value
+
+    def count_within(self, center, radius):
+        c = np.ascontiguousarray(center, np.float64)
+        n = C.c_int64()
+        self._ck(self.lib.fsph_count_within(self.h, c.ctypes.data, float(radius), C.byref(n)))
+        return n.value
+
+    def id_fill(self, mass, h, rho, u, u_blast_add=0.0, blast_radius=0.0, gamma=1.4, dt=0.0, radial_velocity=0.0):
+        f = np.array([mass, h, rho, u, u_blast_add, blast_radius, gamma, dt, radial_velocity], np.float64)
+        self._ck(self.lib.fsph_id_fill(self.h, f.ctypes.data))
 
     def snapshot(self, names=None):
         names = names or [c for c in COL_NAMES if c != "nneigh"]

@@ -101,13 +101,17 @@ __device__ __forceinline__ uint32_t block_scan_u32(uint32_t v, uint32_t & total,
   return base + x - v;
 }
 
+// max / min of finite doubles: one compare + select (fmax / fmin also order NaNs, which costs several more instructions)
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+
 // squared distance between two axis-aligned boxes (0 when they overlap)
 template<int D>
 __device__ __forceinline__ double box_gap2(const double * amn, const double * amx, const double * bmn, const double * bmx) {
   double dd = 0.0;
 #pragma unroll
   for(int d = 0; d < D; ++d) {
-    const double tt = fmax(0.0, fmax(amn[d] - bmx[d], bmn[d] - amx[d]));
+    const double tt = dmax(0.0, dmax(amn[d] - bmx[d], bmn[d] - amx[d]));
     dd = dd + tt * tt;
   }
   return dd;
@@ -338,6 +342,13 @@ static void build_super_lists(System & s) {
   FSPH_CUDA_OK(cudaGetLastError());
 }
 
+// tile ti of a block with n candidates in nt tiles (dealt round-robin): its first candidate and its size
+__host__ __device__ __forceinline__ uint32_t tile_start(uint32_t n, uint32_t nt, uint32_t ti) {
+  const uint32_t q = n / nt, r = n % nt;
+  return ti * q + (ti < r ? ti : r);
+}
+__host__ __device__ __forceinline__ int tile_count(uint32_t n, uint32_t nt, uint32_t ti) { return (int)(n / nt + (ti < n % nt ? 1u : 0u)); }
+
 // ---- the block kernel ---------------------------------------------------------------------------------------------
 // per work cell of a block, in shared memory
 template<int D> struct CellInfo {
@@ -354,6 +365,121 @@ struct SearchCursors {
   unsigned long long cand, dir, rows;
 };
 
+// one candidate of the current tile in shared memory
+struct __align__(16) CandRec {
+  double x[3], h2;
+};
+// dynamic shared memory of k_block_search: walk queue (node, cell mask, first child cell, leaf mask) OR candidate tile,
+// cell masks, per-warp candidate lists and per-warp list staging
+constexpr int SR_HALF = NL_TILE / 2;          // candidates compacted and tested per pass
+constexpr int SR_QCAPL = SR_HALF + 16;        // entries of a quarter-warp's candidate list (padded to a multiple of 16)
+constexpr int SM_CM = (NL_TILE + 1) * 32;     // + the sentinel record
+constexpr int SM_WL = SM_CM + NL_TILE * 2;
+constexpr int SM_LBUF = SM_WL + SR_NW * 4 * SR_QCAPL * 2;
+constexpr int SM_TOTAL = SM_LBUF + SR_NW * (SR_LROWS + 1) * 64;
+// walk: node, cell mask, first child cell, leaf mask per queue entry, then the leaf items of 256 entries
+constexpr int SM_QITEM = SR_CHUNK * 13;
+constexpr int SM_QTOTAL = SM_QITEM + BLK_BODIES * 8 * 6;
+constexpr int block_search_smem() { return SM_TOTAL > SM_QTOTAL ? SM_TOTAL : SM_QTOTAL; }
+
+// Tight box, reach and cells of the 8 bodies of a quarter warp, in fp32 relative to the centre of the block's tight box
+// (bounds rounded outwards).  `reach` = largest h of the quarter plus the absolute error bound of the fp32 distances.
+struct QuarterBox {
+  float mn[3], mx[3], reach;
+  uint32_t cells;
+};
+
+// s0 <= h0 || s0 <= h2c [&& cellbit != 0] -> m |= bit.  Written in PTX: the compiler otherwise rewrites the two compares
+// into one against fmax() and pays for its NaN handling (~10 instructions per test).
+template<bool MULTI>
+__device__ __forceinline__ void pair_test_bit(uint32_t & m, const uint32_t bit, const double s0, const double h0, const double h2c,
+  const uint32_t cellbit) {
+  if(MULTI)
+    asm("{\n\t.reg .pred p;\n\tsetp.le.f64 p, %1, %2;\n\tsetp.le.or.f64 p, %1, %3, p;\n\tsetp.ne.and.b32 p, %5, 0, p;\n\t@p or.b32 %0, %0, %4;\n\t}"
+        : "+r"(m) : "d"(s0), "d"(h0), "d"(h2c), "r"(bit), "r"(cellbit));
+  else
+    asm("{\n\t.reg .pred p;\n\tsetp.le.f64 p, %1, %2;\n\tsetp.le.or.f64 p, %1, %3, p;\n\t@p or.b32 %0, %0, %4;\n\t}"
+        : "+r"(m) : "d"(s0), "d"(h0), "d"(h2c), "r"(bit));
+}
+
+// The pair tests of one warp on the candidates compacted for it: within_distance2(x_k, x_e, max(h_k, h_e))
+// (tree_geometry.h:265-275); max(h_k,h_e)^2 == max(h_k^2,h_e^2) exactly (rounding is monotonic), tested as
+// s <= h_k^2 || s <= h_e^2.  Every lane walks the list of its quarter warp (all four padded to nmax with the sentinel
+// record, which no body accepts) and appends the tile positions of its neighbours to its own list: row 1 + j of the
+// warp's staging area in shared memory (rows beyond SR_LROWS are counted, not stored), or, DIRECT, straight to the
+// warp's rows in global memory (slow path for lists longer than the staging area).  cnt: the lane's running count.
+template<int D, bool DIRECT, bool MULTI>
+__device__ __forceinline__ void warp_pair_tests(const CandRec * __restrict__ c4, const uint16_t * __restrict__ cm, const uint16_t * __restrict__ wlq,
+  const int nmax, const double * a0, const double h0, const uint32_t my_bit, const bool active, const int lane, uint16_t (* lrows)[32],
+  uint16_t * __restrict__ dst, int & cnt) {
+  for(int jb = 0; jb < nmax; jb += 16) {
+    uint32_t m = 0;
+#pragma unroll
+    for(int b = 0; b < 16; ++b) {
+      const int ci = wlq[jb + b];
+      const double2 xy = *reinterpret_cast<const double2 *>(&c4[ci].x[0]);
+      const double2 zh = *reinterpret_cast<const double2 *>(&c4[ci].x[2]);
+      double s0 = (a0[0] - xy.x) * (a0[0] - xy.x);
+      if(D > 1) s0 = s0 + (a0[1] - xy.y) * (a0[1] - xy.y);
+      if(D > 2) s0 = s0 + (a0[2] - zh.x) * (a0[2] - zh.x);
+      pair_test_bit<MULTI>(m, 1u << b, s0, h0, zh.y, MULTI ? (cm[ci] & my_bit) : 0u);
+    }
+    if(!active) m = 0;
+    while(m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      const uint16_t pos = wlq[jb + b];
+      if(DIRECT) dst[(1 + cnt) * 32 + lane] = pos;
+      else if(cnt < SR_LROWS) lrows[1 + cnt][lane] = pos;
+      ++cnt;
+    }
+  }
+}
+
+// The candidates [hf * SR_HALF, ...) of the staged tile that a quarter warp has to test: those of its cells that lie
+// within max(h_e, hmax_quarter) of the tight box of its 8 bodies.  The cull only has to be conservative (it drops
+// candidates no body of the quarter can pair with), so it runs in fp32 on coordinates relative to the block centre:
+// every rounding error is bounded by `feps` (a few ulps of the block extent, folded into the reach of both sides), the
+// box bounds are rounded outwards.  One candidate per lane and round, four ballots; lists in tile order, padded with
+// the sentinel record to the common length nmax (a multiple of 16), which is returned.
+template<int D>
+__device__ __forceinline__ int compact_quarters(const CandRec * __restrict__ c4, const uint16_t * __restrict__ cm, const QuarterBox * __restrict__ qb,
+  uint16_t (* wlw)[SR_QCAPL], const int hf, const int tc, const int lane, const double * bctr, const float feps) {
+  int n[4] = {0, 0, 0, 0};
+  const int i1 = min(tc, (hf + 1) * SR_HALF);
+  for(int i0 = hf * SR_HALF; i0 < i1; i0 += 32) {
+    const int i = i0 + lane;
+    const bool valid = i < i1;
+    const CandRec cr = c4[valid ? i : NL_TILE];
+    const uint32_t cmi = valid ? cm[i] : 0u;
+    float xf[D];
+#pragma unroll
+    for(int d = 0; d < D; ++d) xf[d] = (float)(cr.x[d] - bctr[d]);
+    const float hf32 = __fsqrt_ru(__double2float_ru(cr.h2)) + feps;   // >= h_e + error bound
+#pragma unroll
+    for(int q = 0; q < 4; ++q) {
+      bool pass = (cmi & qb[q].cells) != 0u;
+      float dd = 0.f;
+#pragma unroll
+      for(int d = 0; d < D; ++d) {
+        const float tt = fmaxf(0.f, fmaxf(qb[q].mn[d] - xf[d], xf[d] - qb[q].mx[d]));
+        dd = fmaf(tt, tt, dd);
+      }
+      const float rch = fmaxf(qb[q].reach, hf32);
+      pass = pass && dd <= rch * rch * 1.0001f;
+      const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+      if(pass) wlw[q][n[q] + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
+      n[q] += __popc(bal);
+    }
+  }
+  const int nmax = (max(max(n[0], n[1]), max(n[2], n[3])) + 15) & ~15;
+#pragma unroll
+  for(int q = 0; q < 4; ++q)
+    for(int j = n[q] + lane; j < nmax; j += 32) wlw[q][j] = (uint16_t)NL_TILE;
+  __syncwarp();
+  return nmax;
+}
+
 template<int D>
 __global__ void __launch_bounds__(SR_NT, 3) k_block_search(Tree t, Cols c, Search sr, int64_t * __restrict__ scratch, int scratch_cap,
   SearchCursors * __restrict__ cur, unsigned long long cand_cap, unsigned long long dir_cap, unsigned long long rows_cap,
@@ -366,19 +492,21 @@ __global__ void __launch_bounds__(SR_NT, 3) k_block_search(Tree t, Cols c, Searc
   __shared__ uint8_t slot_of[NT];
   __shared__ uint32_t scan_sm[SR_NW];
   __shared__ uint32_t wcnt[SR_CHUNK / NT][SR_NW];
-  __shared__ unsigned long long base_sm[2];
-  __shared__ int cmax_sm[SR_NW];
-  __shared__ uint32_t wm[SR_NW][NL_TILE / 32];
+  __shared__ unsigned long long base_sm[2][2];
+  __shared__ int cmax_sm[2][SR_NW];
+  __shared__ QuarterBox qbox[SR_NW][4];
   // the node queue of the walk and the candidate tile + list staging of the pair tests are never live together
-  constexpr int QBYTES = SR_CHUNK * 8;
-  constexpr int TBYTES = (D + 1) * NL_TILE * 8 + NL_TILE * 2;
-  extern __shared__ __align__(16) unsigned char ubuf[];   // max(QBYTES, TBYTES + LBYTES) bytes: block_search_smem<D>()
+  extern __shared__ __align__(16) unsigned char ubuf[];   // block_search_smem() bytes
   int32_t * const q_node = reinterpret_cast<int32_t *>(ubuf);
   uint32_t * const q_mask = reinterpret_cast<uint32_t *>(ubuf + SR_CHUNK * 4);
-  double (* const cx)[NL_TILE] = reinterpret_cast<double (*)[NL_TILE]>(ubuf);
-  double * const ch2 = reinterpret_cast<double *>(ubuf + D * NL_TILE * 8);
-  uint16_t * const cm = reinterpret_cast<uint16_t *>(ubuf + (D + 1) * NL_TILE * 8);
-  uint16_t (* const lbuf)[SR_LROWS + 1][32] = reinterpret_cast<uint16_t (*)[SR_LROWS + 1][32]>(ubuf + TBYTES);
+  int32_t * const q_cb = reinterpret_cast<int32_t *>(ubuf + SR_CHUNK * 8);
+  uint8_t * const q_leaf = reinterpret_cast<uint8_t *>(ubuf + SR_CHUNK * 12);
+  CandRec * const c4 = reinterpret_cast<CandRec *>(ubuf);                                    // [NL_TILE] x, y, z, h^2
+  uint16_t * const cm = reinterpret_cast<uint16_t *>(ubuf + SM_CM);                          // [NL_TILE] cell masks
+  uint16_t (* const wl)[4][SR_QCAPL] = reinterpret_cast<uint16_t (*)[4][SR_QCAPL]>(ubuf + SM_WL);   // per quarter warp: its candidates
+  int32_t * const it_cell = reinterpret_cast<int32_t *>(ubuf + SM_QITEM);                   // leaf items of the walk: leaf cell,
+  uint16_t * const it_ent = reinterpret_cast<uint16_t *>(ubuf + SM_QITEM + BLK_BODIES * 8 * 4);   // ... queue entry
+  uint16_t (* const lbuf)[SR_LROWS + 1][32] = reinterpret_cast<uint16_t (*)[SR_LROWS + 1][32]>(ubuf + SM_LBUF);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int64_t * const strip = scratch + (size_t)blockIdx.x * scratch_cap;
@@ -490,6 +618,46 @@ __global__ void __launch_bounds__(SR_NT, 3) k_block_search(Tree t, Cols c, Searc
       bh2 = bh * bh * (1.0 + 1e-9);
     }
     const int my_slot = active ? slot_of[tid] : 0;
+    // tight box, largest h and cells of every quarter warp (8 consecutive bodies): its candidates are culled with them,
+    // in fp32 relative to the centre of the block's tight box.  feps bounds the error of one fp32 coordinate difference
+    // (conversion of both operands + the subtraction): coordinates are within `ext` = block extent + reach of the centre.
+    double bctr[D];
+    float feps;
+    {
+      double ext = 0.0;
+#pragma unroll
+      for(int d = 0; d < D; ++d) {
+        bctr[d] = 0.5 * (bmn[d] + bmx[d]);
+        ext = dmax(ext, bmx[d] - bmn[d]);
+      }
+      ext = ext + 2.0 * sqrt(bh2);
+      feps = __double2float_ru(ext * 4.0e-7);   // > 3 * 2^-24 * ext * sqrt(3), with room to spare
+      double qmn[D], qmx[D], qh = active ? ha : 0.0;
+      uint32_t qc = active ? (1u << my_slot) : 0u;
+#pragma unroll
+      for(int d = 0; d < D; ++d) { qmn[d] = active ? a0[d] : 1.79769313486231570e308; qmx[d] = active ? a0[d] : -1.79769313486231570e308; }
+#pragma unroll
+      for(int o = 4; o > 0; o >>= 1) {
+#pragma unroll
+        for(int d = 0; d < D; ++d) {
+          qmn[d] = dmin(qmn[d], __shfl_xor_sync(0xffffffffu, qmn[d], o));
+          qmx[d] = dmax(qmx[d], __shfl_xor_sync(0xffffffffu, qmx[d], o));
+        }
+        qh = dmax(qh, __shfl_xor_sync(0xffffffffu, qh, o));
+        qc |= __shfl_xor_sync(0xffffffffu, qc, o);
+      }
+      if((lane & 7) == 0) {
+        QuarterBox & qb = qbox[warp][lane >> 3];
+#pragma unroll
+        for(int d = 0; d < 3; ++d) {
+          // an empty quarter (no active body) keeps cells == 0 and is never matched; its bounds only have to be finite
+          qb.mn[d] = (d < D && qc) ? __double2float_rd(qmn[d] - bctr[d]) : 0.f;
+          qb.mx[d] = (d < D && qc) ? __double2float_ru(qmx[d] - bctr[d]) : 0.f;
+        }
+        qb.reach = __double2float_ru(qh) + feps;
+        qb.cells = qc;
+      }
+    }
     // ---- walk: filter the super cell's node list, exact cell tests, leaves -----------------------------------
     const int sidx = sr.wc_super[g0];
     const uint64_t sl_lo = sr.sl_off[sidx];
@@ -541,8 +709,11 @@ __global__ void __launch_bounds__(SR_NT, 3) k_block_search(Tree t, Cols c, Searc
           const uint32_t bal = __ballot_sync(0xffffffffu, ok);
           if(ok) {
             const uint32_t p = my_off[r] + __popc(bal & ((1u << lane) - 1u));
+            const NodeRec & rec = t.noderec[ndr[r]];
             q_node[p] = ndr[r];
             q_mask[p] = 0u;
+            q_cb[p] = rec.child_begin;
+            q_leaf[p] = (uint8_t)rec.leafmask;
           }
         }
       }
@@ -583,75 +754,61 @@ __global__ void __launch_bounds__(SR_NT, 3) k_block_search(Tree t, Cols c, Searc
         if(ok) atomicOr(&q_mask[e], 1u << ci);
       }
       __syncthreads();
-      // (c) leaf children of the accepted nodes -> candidates (leaf cell index, mask of the cells that take it)
+      // (c) leaf children of the accepted nodes -> candidates (leaf cell index, mask of the cells that take it), in
+      //     queue order.  256 queue entries at a time list their leaf children (scan), then one leaf per thread.
       for(int eb = 0; eb < nq; eb += NT) {
         const int e = eb + tid;
-        uint32_t lm[NCH];
-        int cb = 0;
-        uint32_t cnt = 0;
+        const uint32_t lmask = (e < nq && q_mask[e]) ? (uint32_t)q_leaf[e] : 0u;
+        uint32_t nitem;
+        uint32_t off = block_scan_u32<NT>(__popc(lmask), nitem, scan_sm);
+        for(uint32_t rest = lmask; rest; rest &= rest - 1) {
+          it_cell[off] = q_cb[e] + (__ffs(rest) - 1);
+          it_ent[off] = (uint16_t)e;
+          ++off;
+        }
+        __syncthreads();
+        for(uint32_t ib = 0; ib < nitem; ib += NT) {
+          const uint32_t it = ib + tid;
+          uint32_t m = 0;
+          int cidx = 0;
+          if(it < nitem) {
+            cidx = it_cell[it];
+            const LeafRec lr = t.leafrec[cidx];
+            for(uint32_t rest = q_mask[it_ent[it]]; rest; rest &= rest - 1) {
+              const int ci = __ffs(rest) - 1;
+              const CellInfo<D> & G = cell[ci];
+              bool pass = true;
+              if(G.has_node) {
+                // |x_e - X_G|^2 <= (max(h_e, lap_G) + radius_G)^2, tree_topology.h:365-370
+                const double ext = dmax(lr.h, G.glap) + G.grad;
+                double s2 = 0.0;
 #pragma unroll
-        for(int j = 0; j < NCH; ++j) lm[j] = 0;
-        const uint32_t nmask = e < nq ? q_mask[e] : 0u;
-        if(nmask) {
-          const NodeRec & rec = t.noderec[q_node[e]];
-          cb = rec.child_begin;
-          const uint32_t leafmask = rec.leafmask;
-          // leaf children in batches of four: all loads of a batch are issued before the first use
-#pragma unroll
-          for(int half = 0; half < (NCH + 3) / 4; ++half) {
-            const uint32_t lm4 = (leafmask >> (4 * half)) & 0xfu;
-            if(lm4 == 0) continue;
-            LeafRec lr[4];
-#pragma unroll
-            for(int jj = 0; jj < 4; ++jj)
-              if((lm4 >> jj) & 1u) lr[jj] = t.leafrec[cb + 4 * half + jj];
-#pragma unroll
-            for(int jj = 0; jj < 4; ++jj) {
-              if(4 * half + jj >= NCH || !((lm4 >> jj) & 1u)) continue;
-              uint32_t m = 0;
-              for(uint32_t rest = nmask; rest; rest &= rest - 1) {
-                const int ci = __ffs(rest) - 1;
-                const CellInfo<D> & G = cell[ci];
-                bool pass = true;
-                if(G.has_node) {
-                  // |x_e - X_G|^2 <= (max(h_e, lap_G) + radius_G)^2, tree_topology.h:365-370
-                  const double ext = fmax(lr[jj].h, G.glap) + G.grad;
-                  double s2 = 0.0;
-#pragma unroll
-                  for(int d = 0; d < D; ++d) {
-                    const double df = lr[jj].x[d] - G.gcom[d];
-                    s2 = d == 0 ? df * df : s2 + df * df;
-                  }
-                  pass = s2 <= ext * ext;
+                for(int d = 0; d < D; ++d) {
+                  const double df = lr.x[d] - G.gcom[d];
+                  s2 = d == 0 ? df * df : s2 + df * df;
                 }
-                if(pass) {
-                  // conservative cull: no body of G is within max(h_e, hmax_G) of the leaf
-                  const double hm = fmax(lr[jj].h, G.hmax);
-                  double dd = 0.0;
-#pragma unroll
-                  for(int d = 0; d < D; ++d) {
-                    const double tt = fmax(0.0, fmax(G.tmn[d] - lr[jj].x[d], lr[jj].x[d] - G.tmx[d]));
-                    dd = dd + tt * tt;
-                  }
-                  pass = dd <= hm * hm * (1.0 + 1e-9);
-                }
-                if(pass) m |= 1u << ci;
+                pass = s2 <= ext * ext;
               }
-              lm[4 * half + jj] = m;
-              cnt += m != 0u;
+              if(pass) {
+                // conservative cull: no body of G is within max(h_e, hmax_G) of the leaf
+                const double hm = dmax(lr.h, G.hmax);
+                double dd = 0.0;
+#pragma unroll
+                for(int d = 0; d < D; ++d) {
+                  const double tt = dmax(0.0, dmax(G.tmn[d] - lr.x[d], lr.x[d] - G.tmx[d]));
+                  dd = dd + tt * tt;
+                }
+                pass = dd <= hm * hm * (1.0 + 1e-9);
+              }
+              if(pass) m |= 1u << ci;
             }
           }
+          uint32_t total;
+          const uint32_t pos = ncands + block_scan_u32<NT>(m != 0u ? 1u : 0u, total, scan_sm);
+          if(m && pos < (uint32_t)scratch_cap) strip[pos] = ((int64_t)m << 32) | (uint32_t)cidx;
+          ncands += total;
         }
-        uint32_t total;
-        uint32_t pos = ncands + block_scan_u32<NT>(cnt, total, scan_sm);
-#pragma unroll
-        for(int j = 0; j < NCH; ++j) {
-          if(lm[j]) {
-            if(pos < (uint32_t)scratch_cap) strip[pos] = ((int64_t)lm[j] << 32) | (uint32_t)(cb + j);
-            ++pos;
-          }
-        }
-        ncands += total;
+        __syncthreads();   // the item list is rewritten by the next 256 entries
       }
       __syncthreads();
     }
@@ -659,12 +816,12 @@ __global__ void __launch_bounds__(SR_NT, 3) k_block_search(Tree t, Cols c, Searc
     const int ntile = (int)((ncands + NL_TILE - 1) / NL_TILE);
     bool overflow = ncands > (uint32_t)scratch_cap;
     if(tid == 0) {
-      base_sm[0] = atomicAdd(&cur->cand, (unsigned long long)ncands);
-      base_sm[1] = atomicAdd(&cur->dir, (unsigned long long)ntile);
+      base_sm[0][0] = atomicAdd(&cur->cand, (unsigned long long)ncands);
+      base_sm[0][1] = atomicAdd(&cur->dir, (unsigned long long)ntile);
       if(overflow) atomicOr(status, (uint32_t)ERR_QUEUE_OVERFLOW);
     }
     __syncthreads();
-    const unsigned long long co = base_sm[0], dir0 = base_sm[1];
+    const unsigned long long co = base_sm[0][0], dir0 = base_sm[0][1];
     if(co + ncands > cand_cap || dir0 + ntile > dir_cap) overflow = true;
     if(!overflow) {
       if(tid == 0) {
@@ -674,143 +831,152 @@ __global__ void __launch_bounds__(SR_NT, 3) k_block_search(Tree t, Cols c, Searc
         sr.blk_body[blk] = body0;
         sr.blk_nbody[blk] = PB;
       }
-      for(uint32_t i = tid; i < ncands; i += NT) sr.cand[co + i] = t.cell[(uint32_t)strip[i]];
+      // Candidates leave the walk in runs of key-neighbours.  They are dealt to the tiles round-robin (walk position i
+      // goes to tile i % ntile, slot i / ntile): every tile then holds an even sample of the whole neighbourhood, so all
+      // bodies of the block find about the same number of neighbours in it and the lanes of the pair loops stay busy
+      // together; tile ti starts at co + tile_start(ti) and holds tile_count(ti) candidates.
+      for(uint32_t i = tid; i < ncands; i += NT) {
+        const uint32_t ti = i % (uint32_t)ntile, p = i / (uint32_t)ntile;
+        sr.cand[co + tile_start(ncands, ntile, ti) + p] = t.cell[(uint32_t)strip[i]];
+      }
     }
     // ---- pair tests, tile by tile -----------------------------------------------------------------------------
+    // Two block barriers per tile: S1 (tile staged, row base of the previous tile known) -> the warps copy their
+    // staged lists of the previous tile out, then test this tile -> S2 (tests done: the tile buffers are free) ->
+    // thread 0 reserves the rows of this tile while everybody stages the next one.
     const double h0 = ha * ha;
     const int nwarp_act = (PB + 31) >> 5;
+    const bool no_strip = ncands > (uint32_t)scratch_cap;
     // cells of this warp's bodies
     uint32_t warp_cells = active ? (1u << my_slot) : 0u;
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) warp_cells |= __shfl_xor_sync(0xffffffffu, warp_cells, o);
     const bool multi = (warp_cells & (warp_cells - 1u)) != 0u;
-    int nn = 0;
-    for(int ti = 0; ti < ntile; ++ti) {
-      const int tb = ti * NL_TILE;
-      const int tc = overflow && ncands > (uint32_t)scratch_cap ? 0 : min(NL_TILE, (int)ncands - tb);
-      __syncthreads();
+    const uint32_t my_bit = 1u << my_slot;
+    if(tid == 0) {
+      // the sentinel record that pads the candidate lists: accepted by nobody
+      CandRec r;
+      r.x[0] = r.x[1] = r.x[2] = 1e300;
+      r.h2 = -1.0;
+      c4[NL_TILE] = r;
+    }
+    auto stage = [&](const int ti) {
+      const int tc = no_strip ? 0 : tile_count(ncands, ntile, ti);
       for(int i = tid; i < NL_TILE; i += NT) {
         if(i < tc) {
-          const int64_t sv = strip[tb + i];
+          const int64_t sv = strip[(size_t)i * ntile + ti];
           const LeafRec lr = t.leafrec[(uint32_t)sv];
-#pragma unroll
-          for(int d = 0; d < D; ++d) cx[d][i] = lr.x[d];
-          ch2[i] = lr.h * lr.h;
+          CandRec r;
+          r.x[0] = lr.x[0]; r.x[1] = lr.x[1]; r.x[2] = lr.x[2];
+          r.h2 = lr.h * lr.h;
+          c4[i] = r;
           cm[i] = (uint16_t)(sv >> 32);
         }
         else cm[i] = 0;
       }
-      __syncthreads();
-      // candidate words of this warp: bit b of word w <=> candidate 32 w + b belongs to a cell of the warp
+    };
+    // the warp's rows of tile ti -> global memory (and the tile's directory entry)
+    auto copy_out = [&](const int ti, const int cnt, const int cmax) {
+      const int par = ti & 1;
+      const unsigned long long row0 = base_sm[par][0];
+      if(row0 + base_sm[par][1] > rows_cap) overflow = true;
+      if(overflow) return;
+      if(tid == 0) {
+        TileDir td;
+        td.row0 = row0;
 #pragma unroll
-      for(int w = 0; w < NL_TILE / 32; ++w) {
-        const uint32_t bal = __ballot_sync(0xffffffffu, (cm[w * 32 + lane] & warp_cells) != 0u);
-        if(lane == 0) wm[warp][w] = bal;
+        for(int w = 0; w < SR_NW; ++w) td.cmax[w] = (uint16_t)(cmax_sm[par][w] < 0 ? 0 : cmax_sm[par][w]);
+        td.pad = 0;
+        sr.dir[dir0 + ti] = td;
       }
-      __syncwarp();
-      // within_distance2(x_k, x_e, max(h_k, h_e)): max(h_k,h_e)^2 == max(h_k^2,h_e^2) exactly (rounding is monotonic)
-      int cnt = 0;
-      bool spilled = false;
-      const int nwords = (tc + 31) >> 5;
       if(warp < nwarp_act) {
-        for(int w = 0; w < nwords; ++w) {
-          uint32_t u = wm[warp][w];
-          uint32_t m0 = 0;
-          while(u) {
-            const int b = __ffs(u) - 1;
-            u &= u - 1;
-            const int ci = w * 32 + b;
-            const double e0 = cx[0][ci];
-            double s0 = (a0[0] - e0) * (a0[0] - e0);
-#pragma unroll
-            for(int d = 1; d < D; ++d) {
-              const double ed = cx[d][ci];
-              s0 = s0 + (a0[d] - ed) * (a0[d] - ed);
-            }
-            bool in = s0 <= fmax(h0, ch2[ci]);
-            if(multi) in = in && ((cm[ci] >> my_slot) & 1u);
-            m0 |= (uint32_t)in << b;
-          }
-          if(!active) m0 = 0;
-          // append the set bits to this lane's list (row 1 + j of the warp's staging area)
-          while(m0) {
-            const int b = __ffs(m0) - 1;
-            m0 &= m0 - 1;
-            if(cnt < SR_LROWS) lbuf[warp][1 + cnt][lane] = (uint16_t)(w * 32 + b);
-            ++cnt;
-          }
+        unsigned long long rb = row0;
+        for(int w = 0; w < warp; ++w) rb += 1 + cmax_sm[par][w];
+        uint16_t * dst = sr.nl + rb * 32;
+        // rows past a lane's own count are zeroed (the sweeps read whole rows)
+        for(int j = 0; j <= cmax; ++j) dst[j * 32 + lane] = j <= cnt ? lbuf[warp][j][lane] : (uint16_t)0;
+      }
+    };
+    int nn = 0, cnt_prev = 0, cmax_prev = 0;
+    bool copied_prev = true;
+    if(ntile > 0) stage(0);
+    for(int ti = 0; ti < ntile; ++ti) {
+      const int par = ti & 1;
+      __syncthreads();   // S1
+      if(!copied_prev) copy_out(ti - 1, cnt_prev, cmax_prev);
+      const int tc = no_strip ? 0 : tile_count(ncands, ntile, ti);
+      int cnt = 0;
+      if(warp < nwarp_act) {
+        for(int hf = 0; hf * SR_HALF < tc; ++hf) {
+          const int nmax = compact_quarters<D>(c4, cm, qbox[warp], wl[warp], hf, tc, lane, bctr, feps);
+          if(multi) warp_pair_tests<D, false, true>(c4, cm, wl[warp][lane >> 3], nmax, a0, h0, my_bit, active, lane, lbuf[warp], nullptr, cnt);
+          else warp_pair_tests<D, false, false>(c4, cm, wl[warp][lane >> 3], nmax, a0, h0, my_bit, active, lane, lbuf[warp], nullptr, cnt);
+          __syncwarp();
         }
         lbuf[warp][0][lane] = (uint16_t)cnt;
       }
       nn += cnt;
       const int cmax = __reduce_max_sync(0xffffffffu, cnt);
-      spilled = cmax > SR_LROWS;
-      if(lane == 0) cmax_sm[warp] = warp < nwarp_act ? cmax : -1;
-      __syncthreads();
-      // rows of this tile: 1 + cmax per live warp
+      if(lane == 0) cmax_sm[par][warp] = warp < nwarp_act ? cmax : -1;
+      __syncthreads();   // S2
+      bool any_spill = false;
+#pragma unroll
+      for(int w = 0; w < SR_NW; ++w) any_spill = any_spill || cmax_sm[par][w] > SR_LROWS;
       if(tid == 0) {
         unsigned long long rows = 0;
-        for(int w = 0; w < nwarp_act; ++w) rows += 1 + cmax_sm[w];
-        base_sm[0] = atomicAdd(&cur->rows, rows);
-        base_sm[1] = rows;
+        for(int w = 0; w < nwarp_act; ++w) rows += 1 + cmax_sm[par][w];
+        base_sm[par][0] = atomicAdd(&cur->rows, rows);
+        base_sm[par][1] = rows;
       }
-      __syncthreads();
-      const unsigned long long row0 = base_sm[0];
-      if(row0 + base_sm[1] > rows_cap) overflow = true;
-      if(!overflow) {
-        if(tid == 0) {
-          TileDir td;
-          td.row0 = row0;
-#pragma unroll
-          for(int w = 0; w < SR_NW; ++w) td.cmax[w] = (uint16_t)(cmax_sm[w] < 0 ? 0 : cmax_sm[w]);
-          td.pad = 0;
-          sr.dir[dir0 + ti] = td;
-        }
-        if(warp < nwarp_act) {
-          unsigned long long rb = row0;
-          for(int w = 0; w < warp; ++w) rb += 1 + cmax_sm[w];
-          uint16_t * dst = sr.nl + rb * 32;
-          if(!spilled) {
-            // rows past a lane's own count are zeroed (the sweeps read whole rows)
-            for(int j = 0; j <= cmax; ++j) dst[j * 32 + lane] = j <= cnt ? lbuf[warp][j][lane] : (uint16_t)0;
-          }
-          else {
-            // a lane has more neighbours in this tile than the staging area holds: redo the warp's tests and write
-            // the rows straight to global memory (slow path, rare)
+      if(any_spill) {
+        // a lane has more neighbours in this tile than the staging area holds (rare): finish the tile now, while its
+        // candidates are still in shared memory; warps with long lists redo their tests and write straight to their rows
+        __syncthreads();
+        const bool spilled = cmax > SR_LROWS;
+        if(!spilled) copy_out(ti, cnt, cmax);
+        else {
+          const unsigned long long row0 = base_sm[par][0];
+          if(row0 + base_sm[par][1] > rows_cap) overflow = true;
+          if(!overflow) {
+            unsigned long long rb = row0;
+            for(int w = 0; w < warp; ++w) rb += 1 + cmax_sm[par][w];
+            uint16_t * dst = sr.nl + rb * 32;
             dst[lane] = (uint16_t)cnt;
             for(int j = cnt + 1; j <= cmax; ++j) dst[j * 32 + lane] = (uint16_t)0;
             int k = 0;
-            for(int w = 0; w < nwords; ++w) {
-              uint32_t u = wm[warp][w];
-              while(u) {
-                const int b = __ffs(u) - 1;
-                u &= u - 1;
-                const int ci = w * 32 + b;
-                const double e0 = cx[0][ci];
-                double s0 = (a0[0] - e0) * (a0[0] - e0);
-#pragma unroll
-                for(int d = 1; d < D; ++d) {
-                  const double ed = cx[d][ci];
-                  s0 = s0 + (a0[d] - ed) * (a0[d] - ed);
-                }
-                bool in = active && s0 <= fmax(h0, ch2[ci]);
-                if(multi) in = in && ((cm[ci] >> my_slot) & 1u);
-                if(in) { dst[(1 + k) * 32 + lane] = (uint16_t)ci; ++k; }
-              }
+            for(int hf = 0; hf * SR_HALF < tc; ++hf) {
+              const int nmax = compact_quarters<D>(c4, cm, qbox[warp], wl[warp], hf, tc, lane, bctr, feps);
+              warp_pair_tests<D, true, true>(c4, cm, wl[warp][lane >> 3], nmax, a0, h0, my_bit, active, lane, nullptr, dst, k);
+              __syncwarp();
             }
           }
         }
+        // the directory entry is written by thread 0 inside copy_out; if thread 0's own warp took the slow path, here
+        if(tid == 0 && spilled && !overflow) {
+          TileDir td;
+          td.row0 = base_sm[par][0];
+#pragma unroll
+          for(int w = 0; w < SR_NW; ++w) td.cmax[w] = (uint16_t)(cmax_sm[par][w] < 0 ? 0 : cmax_sm[par][w]);
+          td.pad = 0;
+          sr.dir[dir0 + ti] = td;
+        }
+        copied_prev = true;
+        __syncthreads();
       }
+      else {
+        copied_prev = false;
+        cnt_prev = cnt;
+        cmax_prev = cmax;
+      }
+      if(ti + 1 < ntile) stage(ti + 1);
+    }
+    if(!copied_prev) {
+      __syncthreads();
+      copy_out(ntile - 1, cnt_prev, cmax_prev);
     }
     if(active && !overflow) c.nneigh[body0 + tid] = nn;
     if(overflow && tid == 0) atomicOr(status, (uint32_t)ERR_SEARCH_CAPACITY);
   }
-}
-
-template<int D>
-constexpr int block_search_smem() {
-  constexpr int q = SR_CHUNK * 8, tb = (D + 1) * NL_TILE * 8 + NL_TILE * 2, lb = SR_NW * (SR_LROWS + 1) * 64;
-  return q > tb + lb ? q : tb + lb;
 }
 
 template<int D>
@@ -860,7 +1026,7 @@ static void neighbor_search_t(System & s) {
     sr.dir = s.b_dir.as<TileDir>();
     sr.nl = s.b_nl.as<uint16_t>();
     FSPH_CUDA_OK(cudaMemsetAsync(cursors, 0, sizeof(SearchCursors), s.stream));
-    FSPH_LAUNCH_SMEM((k_block_search<D>), grid, SR_NT, block_search_smem<D>(), s.stream, s.tree, s.cols(), sr,
+    FSPH_LAUNCH_SMEM((k_block_search<D>), grid, SR_NT, block_search_smem(), s.stream, s.tree, s.cols(), sr,
       s.b_search_scratch.as<int64_t>(), scratch_cap, cursors, cand_cap, dir_cap, rows_cap, status);
     SearchCursors tot;
     uint32_t st = 0;
@@ -919,7 +1085,8 @@ __global__ void __launch_bounds__(SR_NT) k_export(Cols c, Search sr, const uint6
       if(w < warp && w < nwarp_act) rb += 1 + td.cmax[w];
     const uint16_t * rows = sr.nl + rb * 32;
     const int cnt = rows[lane];
-    for(int j = 0; j < cnt; ++j) ids[o++] = c.id[sr.cand[co + (uint64_t)ti * NL_TILE + rows[(1 + j) * 32 + lane]]];
+    const uint64_t tb = co + tile_start((uint32_t)sr.blk_ncand[blk], (uint32_t)ntile, (uint32_t)ti);
+    for(int j = 0; j < cnt; ++j) ids[o++] = c.id[sr.cand[tb + rows[(1 + j) * 32 + lane]]];
   }
 }
 __global__ void __launch_bounds__(256) k_i32_to_u64(const int32_t * __restrict__ in, uint64_t * __restrict__ out, int64_t n,

@@ -479,8 +479,10 @@ __global__ void __launch_bounds__(BLK_BODIES, SweepOcc<OP>::MINB) k_sweep(Cols c
 
   const int ntile = (C + NL_TILE - 1) / NL_TILE;
   for(int ti = 0; ti < ntile; ++ti) {
-    const int tb = ti * NL_TILE;
-    const int tc = min(NL_TILE, C - tb);
+    // candidates are dealt to the tiles round-robin (fsph_search.cu): tile ti starts at tb and holds tc of them
+    const int tq = C / ntile, tr = C % ntile;
+    const int tb = ti * tq + min(ti, tr);
+    const int tc = tq + (ti < tr ? 1 : 0);
     // this warp's rows of the tile
     const TileDir td = sr.dir[dir0 + ti];
     uint64_t rb = td.row0;

@@ -27,50 +27,61 @@ def _axis(lo, hi, step, offset=0.0):
     return p[p < hi]
 
 
+def in_domain_3d(X, Y, Z, bmin, bmax, domain_type):
+    """in_domain_3d (lattice.h:107-133), operation by operation."""
+    dx = B_TOL * (bmax[0] - bmin[0])
+    xmin, xmax = bmin[0] - dx, bmax[0] - dx
+    ymin, ymax = bmin[1] - dx, bmax[1] - dx
+    zmin, zmax = bmin[2] - dx, bmax[2] - dx
+    m = (X > xmin) & (X < xmax) & (Y > ymin) & (Y < ymax) & (Z > zmin) & (Z < zmax)
+    if domain_type == 1:
+        r = 0.5 * min(min(xmax - xmin, ymax - ymin), zmax - zmin)
+        x0, y0, z0 = 0.5 * (xmin + xmax), 0.5 * (ymin + ymax), 0.5 * (zmin + zmax)
+        m &= ((X - x0) * (X - x0) + (Y - y0) * (Y - y0)) + (Z - z0) * (Z - z0) < r * r
+    return m
+
+
+def lattice_axes(lattice_type, bmin, bmax, sep):
+    """The coordinate values the loops of generator_lattice_3d (lattice.h:224-293) visit, as tables: every loop
+    variable is accumulated sequentially from its own start (`p += d`), so there is one z table, one y table per
+    stacking state zl and one x table per (zl, row parity yo).  Returns (zs, zl_of_layer, ys[zl], xs[zl][yo])."""
+    xmin, ymin, zmin = bmin
+    xmax, ymax, zmax = bmax
+    dx, dy, dz = sep, sep * math.sqrt(3.0) / 2.0, sep * math.sqrt(2.0 / 3.0)
+    if lattice_type == 0:
+        zs = _axis(zmin, zmax, dx)
+        return zs, np.zeros(len(zs), np.int32), [_axis(ymin, ymax, dx)], [[_axis(xmin, xmax, dx)] * 2]
+    zs = _axis(zmin, zmax, dz)
+    nstate = 2 if lattice_type == 1 else 4
+    zl_of = np.zeros(len(zs), np.int32)
+    zl = 0
+    for iz in range(len(zs)):
+        zl_of[iz] = zl
+        zl = 1 - zl if lattice_type == 1 else (zl + 1) * (1 if zl < 3 else 0)
+    ys = [_axis(ymin - z * dy / 3, ymax, dy) for z in range(nstate)]
+    xs = [[_axis(xmin + (yo - z) * dx / 2.0, xmax, dx) for yo in (0, 1)] for z in range(nstate)]
+    return zs, zl_of, ys, xs
+
+
 def lattice_3d(lattice_type, domain_type, bmin, bmax, sep, slab=None):
     """generator_lattice_3d (lattice.h:224-293). Returns [n,3] positions in generation order.
     slab = (k, K): only the z layers of the k-th of K contiguous groups of layers (one group per rank of a
     multi-GPU run; the layers of all groups together are the full lattice)."""
-    xmin, ymin, zmin = bmin
-    xmax, ymax, zmax = bmax
-    dx, dy, dz = sep, sep * math.sqrt(3.0) / 2.0, sep * math.sqrt(2.0 / 3.0)
-    tol = B_TOL * (xmax - xmin)
+    zs, zl_of, ys_t, xs_t = lattice_axes(lattice_type, bmin, bmax, sep)
     out = []
-    zs = _axis(zmin, zmax, dx if lattice_type == 0 else dz)
-    zl = 0
     lay_lo, lay_hi = (0, len(zs)) if slab is None else ((slab[0] * len(zs)) // slab[1], ((slab[0] + 1) * len(zs)) // slab[1])
-    for iz, z in enumerate(zs):
-        if not (lay_lo <= iz < lay_hi):
-            # stacking state advances as if the layer had been generated
-            if lattice_type == 1:
-                zl = 1 - zl
-            elif lattice_type == 2:
-                zl = (zl + 1) * (1 if zl < 3 else 0)
-            continue
-        if lattice_type == 0:
-            ys = _axis(ymin, ymax, dx)
-            xs = _axis(xmin, xmax, dx)
-            X, Y = np.meshgrid(xs, ys)
-        else:
-            ys = _axis(ymin - zl * dy / 3, ymax, dy)
-            yo = (np.arange(len(ys)) % 2).astype(np.float64)
-            x0 = _axis(xmin, xmax + 2 * dx, dx)  # row template, shifted per row below
-            # rows start at xmin + (yo - zl)*dx/2 and run while x < xmax
-            X = x0[None, :] + ((yo - zl) * dx / 2.0)[:, None]
-            Y = np.broadcast_to(ys[:, None], X.shape)
+    for iz in range(lay_lo, lay_hi):
+        z, zl = zs[iz], int(zl_of[iz])
+        ys = ys_t[zl]
+        x0, x1 = xs_t[zl][0], xs_t[zl][1]
+        L = max(len(x0), len(x1))
+        pad = lambda a: np.concatenate([a, np.full(L - len(a), np.inf)])
+        rows = np.stack([pad(x0), pad(x1)])
+        X = rows[np.arange(len(ys)) % 2]
+        Y = np.broadcast_to(ys[:, None], X.shape)
         Z = np.full(X.shape, z)
-        m = (X > xmin - tol) & (X < xmax - tol) & (Y > ymin - tol) & (Y < ymax - tol) & (z > zmin - tol) & (z < zmax - tol)
-        if lattice_type != 0:
-            m &= X < xmax
-        if domain_type == 1:
-            r = 0.5 * min(xmax - xmin, ymax - ymin, zmax - zmin)
-            x0c, y0c, z0c = 0.5 * (xmin + xmax) - tol, 0.5 * (ymin + ymax) - tol, 0.5 * (zmin + zmax) - tol
-            m &= (X - x0c) ** 2 + (Y - y0c) ** 2 + (z - z0c) ** 2 < r * r
+        m = np.isfinite(X) & in_domain_3d(X, Y, Z, bmin, bmax, domain_type)
         out.append(np.stack([X[m], Y[m], Z[m]], 1))
-        if lattice_type == 1:
-            zl = 1 - zl
-        elif lattice_type == 2:
-            zl = (zl + 1) * (1 if zl < 3 else 0)
     return np.concatenate(out, 0) if out else np.zeros((0, 3))
 
 
@@ -241,6 +252,35 @@ def kh_3d(nx=20, eta=1.5, gamma=1.4, density_ratio=2.0, flow_velocity=1.0, P0=2.
                timestep_cfl_factor=0.25, box_length=L, box_width=L, box_height=L, periodic_boundary_x=1, periodic_boundary_y=1,
                periodic_boundary_z=1)
     return f, par
+
+
+def sphere_on_device(system, kind, nx, slab=None, allsum=None, eta=1.2, R=1.0, **kw):
+    """The FCC-sphere set-ups (sedov_3d / noh_3d / collapse_3d above) built directly in the columns of a device system
+    (fsph_generate_lattice / fsph_count_within / fsph_id_fill): the same bodies bit for bit, without the host arrays.
+    Returns (n_local, par)."""
+    spec = {"sedov": dict(P0=1e-7, gamma=1.4, kw_=2.0, dt=1e-4, v=0.0, blast=(2e-7, 0.06)),
+            "noh": dict(P0=1e-6, gamma=1.6666667, kw_=2.0, dt=2e-3, v=-0.1, blast=None),
+            "collapse": dict(P0=1e-10, gamma=1.4, kw_=3.0, dt=5e-4, v=0.0, blast=None)}[kind]
+    spec.update(kw)
+    rho0, P0, gamma = 1.0, spec["P0"], spec["gamma"]
+    sep = 2.0 * R / (nx - 1)
+    slab = slab or (0, 1)
+    n_local = system.generate_lattice(2, 1, (-R,) * 3, (R,) * 3, sep, slab=slab, id_offset=(slab[0] << 40) if slab[1] > 1 else 0)
+    n = allsum(n_local) if allsum else n_local
+    total_mass = rho0 * (4.0 * math.pi / 3.0) * R ** 3
+    m = total_mass / n
+    h = eta * spec["kw_"] * (m / rho0) ** (1.0 / 3.0)
+    K0 = P0 / rho0 ** gamma
+    u = K0 * rho0 ** (gamma - 1) / (gamma - 1)
+    add, rb = 0.0, 0.0
+    if spec["blast"]:
+        e_blast, rb = spec["blast"]
+        nb = system.count_within((0.0, 0.0, 0.0), rb)
+        nb = allsum(nb) if allsum else nb
+        add = e_blast / (m * nb) if nb else 0.0
+    system.id_fill(m, h, rho0, u, add, rb, gamma, spec["dt"], spec["v"])
+    par = {"sedov": sedov_3d, "noh": noh_3d, "collapse": collapse_3d}[kind](nx=4)[1]
+    return n_local, par
 
 
 def nx_for_particles(target, lo=8, hi=2000):

@@ -109,7 +109,9 @@ def test_conservation_100_steps():
     assert np.abs(p1).max() <= 1e-6 * m1 * max(vmax, 1e-300)
     er = R.get_all(capi.GET_TOTAL_ENERGY, 1)[0]
     assert abs(e1 - er) <= 1e-6 * abs(er)
-    assert rel_err(G.get(capi.COL_RHO), R.get(capi.COL_RHO)) < 1e-6
+    # body by body (after 100 drifts the storage order of bodies on key-cell boundaries may differ)
+    ga, ra = np.argsort(G.get(capi.COL_ID)), np.argsort(R.get(capi.COL_ID))
+    assert rel_err(G.get(capi.COL_RHO)[ga], R.get(capi.COL_RHO)[ra]) < 1e-6
 
 
 def test_large_properties():
