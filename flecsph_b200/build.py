@@ -17,7 +17,10 @@ SOURCES = {
     "fsph_tree.cu": ["-fmad=false"],
     "fsph_search.cu": ["-fmad=false"],
     "fsph_apply.cu": ["-fmad=false"],
-    "fsph_sweeps.cu": [],
+    # the pair sweeps: one translation unit per dimension (hundreds of kernel instantiations each; built in parallel)
+    "fsph_sweeps.cu@1": ["-DFSPH_SWEEPS_DIM=1"],
+    "fsph_sweeps.cu@2": ["-DFSPH_SWEEPS_DIM=2"],
+    "fsph_sweeps.cu@3": ["-DFSPH_SWEEPS_DIM=3"],
     "fsph_capi.cu": [],
     "fsph_comm.cu": [],
     "fsph_fmm.cu": ["-fmad=false"],
@@ -38,9 +41,10 @@ def _newer(src_list, out):
 def build_cuda(verbose=False, force=False):
     hdrs = [os.path.join(CSRC, "fsph_internal.h"), os.path.join(ROOT, "include", "flecsph_b200.h"), os.path.abspath(__file__)]
     objs, jobs = [], []
-    for src, extra in SOURCES.items():
+    for key, extra in SOURCES.items():
+        src, _, tag = key.partition("@")
         s = os.path.join(CSRC, src)
-        o = os.path.join(CSRC, src.replace(".cu", OBJ_SUFFIX + ".o"))
+        o = os.path.join(CSRC, src.replace(".cu", (("_" + tag) if tag else "") + OBJ_SUFFIX + ".o"))
         objs.append(o)
         if force or _newer([s] + hdrs, o):
             cmd = [NVCC] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
@@ -49,7 +53,7 @@ def build_cuda(verbose=False, force=False):
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
         return cmd, r
-    with ThreadPoolExecutor(max_workers=6) as ex:
+    with ThreadPoolExecutor(max_workers=8) as ex:
         for cmd, r in ex.map(run, jobs):
             if verbose or r.returncode:
                 sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)

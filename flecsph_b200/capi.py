@@ -15,24 +15,26 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # enum fsph_kernel / fsph_eos / fsph_viscosity
 KERNELS = {"cubic spline": 0, "quintic spline": 1, "wendland c2": 2, "wendland c4": 3,
            "wendland c6": 4, "gaussian": 5, "super gaussian": 6, "sinc": 7}
-EOS_IDEAL, EOS_POLYTROPIC = 0, 1
+EOS_IDEAL, EOS_POLYTROPIC, EOS_WD, EOS_PPT, EOS_NONE = range(5)
 VISC_CONSTANT, VISC_CULLEN = 0, 1
 
 # enum fsph_column
 (COL_POS, COL_VEL, COL_VELHALF, COL_ACC, COL_GACC, COL_MASS, COL_H, COL_RHO, COL_P, COL_U, COL_E,
  COL_CS, COL_DUDT, COL_DEDT, COL_DT, COL_ALPHA, COL_VSIG, COL_GPOT, COL_ADIABATIC, COL_ID, COL_KEY,
- COL_TYPE, COL_NNEIGH) = range(23)
+ COL_TYPE, COL_NNEIGH, COL_YE, COL_DIVV, COL_DDIVVDT, COL_TRIGGER, COL_XI, COL_TRACESS, COL_GRADV) = range(30)
 VECTOR_COLS = (COL_POS, COL_VEL, COL_VELHALF, COL_ACC, COL_GACC)
 COL_DTYPE = {COL_ID: np.int64, COL_KEY: np.uint64, COL_TYPE: np.int32, COL_NNEIGH: np.int32}
 COL_NAMES = ["pos", "vel", "velhalf", "acc", "gacc", "mass", "h", "rho", "P", "u", "e", "cs", "dudt",
-             "dedt", "dt", "alpha", "vsig", "gpot", "adiabatic", "id", "key", "type", "nneigh"]
+             "dedt", "dt", "alpha", "vsig", "gpot", "adiabatic", "id", "key", "type", "nneigh", "ye", "divv", "ddivvdt",
+             "trigger", "xi", "tracess", "gradv"]
 
 # enum fsph_sweep_op
-SWEEP_DENSITY, SWEEP_ACCELERATION, SWEEP_DUDT, SWEEP_DEDT, SWEEP_NEIGHBORS_ONLY = range(5)
+(SWEEP_DENSITY, SWEEP_ACCELERATION, SWEEP_DUDT, SWEEP_DEDT, SWEEP_NEIGHBORS_ONLY, SWEEP_COMPUTE_ALPHA,
+ SWEEP_SHORT_RANGE_REPULSION) = range(7)
 # enum fsph_apply_op
 (APPLY_EOS_INIT, APPLY_SET_TOTAL_ENERGY, APPLY_SAVE_VELOCITYHALF, APPLY_KICK_V, APPLY_KICK_U, APPLY_KICK_E,
  APPLY_DRIFT, APPLY_RECOMPUTE_P_CS, APPLY_RECOMPUTE_P_CS_TK, APPLY_COMPUTE_DT, APPLY_CHECK_NANS,
- APPLY_CHECK_NEGATIVITY) = range(12)
+ APPLY_CHECK_NEGATIVITY, APPLY_INITIALIZE_ALPHA, APPLY_ADD_DRAG_ACCELERATION, APPLY_ADD_DRAG_DEDT, APPLY_ADD_DRAG_DUDT) = range(16)
 # enum fsph_reduce_op
 (GET_SET_ADAPTIVE_TIMESTEP, GET_COMPUTE_SMOOTHINGLENGTH, GET_COMPUTE_AVERAGE_SMOOTHINGLENGTH, GET_TOTAL_MASS,
  GET_TOTAL_ENERGY, GET_TOTAL_MOMENTUM, GET_TOTAL_KINETIC_ENERGY, GET_TOTAL_INTERNAL_ENERGY,
@@ -55,6 +57,9 @@ class Params(C.Structure):
         ("relaxation_steps", C.c_int32), ("pressure_updates_number", C.c_int32),
         ("periodic_boundary_x", C.c_int32), ("periodic_boundary_y", C.c_int32), ("periodic_boundary_z", C.c_int32),
         ("reserved_", C.c_int32),
+        ("sph_viscosity_alpha_max", C.c_double), ("sph_viscosity_l", C.c_double), ("sph_viscosity_delta", C.c_double),
+        ("poly_gamma2", C.c_double), ("ppt_density_thr", C.c_double), ("relaxation_beta", C.c_double),
+        ("relaxation_gamma", C.c_double), ("relaxation_repulsion_radius", C.c_double), ("relaxation_repulsion_gamma", C.c_double),
     ]
 
 
@@ -179,6 +184,9 @@ def default_params(dim=3, lib=None, **kw):
         p.timestep_cfl_factor, p.initial_dt, p.gravitational_constant = 0.25, 0.001, 1.0
         p.box_length, p.box_width, p.box_height = 3.0, 1.0, 1.0
         p.evolve_internal_energy = p.thermokinetic_formulation = p.pressure_updates_number = 1
+        p.sph_viscosity_alpha_max, p.sph_viscosity_l, p.sph_viscosity_delta = 1.0, 0.05, 1.0
+        p.poly_gamma2, p.ppt_density_thr = 2.5, 5e14
+        p.relaxation_beta, p.relaxation_gamma, p.relaxation_repulsion_radius, p.relaxation_repulsion_gamma = 1e-6, 0.0, 0.25, 0.0
     for k, v in kw.items():
         if k == "sph_kernel" and isinstance(v, str):
             v = KERNELS[v.lower()]

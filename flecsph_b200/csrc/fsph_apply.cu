@@ -44,6 +44,16 @@ PhysParams System::phys() const {
   p.dt = dt;
   p.iteration = iteration;
   p.relaxation_steps = par.relaxation_steps;
+  p.visc = par.sph_viscosity;
+  p.alpha_max = par.sph_viscosity_alpha_max;
+  p.visc_l = par.sph_viscosity_l;
+  p.visc_delta = par.sph_viscosity_delta;
+  p.gamma2 = par.poly_gamma2;
+  p.rho_thr = par.ppt_density_thr;
+  p.relax_beta = par.relaxation_beta;
+  p.relax_gamma = par.relaxation_gamma;
+  p.repulsion_radius = par.relaxation_repulsion_radius;
+  p.repulsion_gamma = par.relaxation_repulsion_gamma;
   return p;
 }
 
@@ -52,69 +62,120 @@ struct OpList {
   int op[8];
 };
 
+// Columns an element-wise functor reads / writes (bit f = F64 column f; vector columns stand for their D components).
+struct OpAccess { uint64_t rd, wr; };
+constexpr uint64_t fbit(int f) { return uint64_t(1) << f; }
+constexpr uint64_t vbit(int f) { return fbit(f) | fbit(f + 1) | fbit(f + 2); }
+static OpAccess op_access(int op, const PhysParams & pp) {
+  const uint64_t eos_in = fbit(F_RHO) | fbit(F_ADIA) | (pp.eos == FSPH_EOS_WD ? fbit(F_YE) : 0) | fbit(F_P) | fbit(F_CS);
+  switch(op) {
+    case FSPH_APPLY_EOS_INIT: return {fbit(F_RHO) | fbit(F_P) | (pp.eos == FSPH_EOS_WD ? fbit(F_YE) : 0), fbit(F_ADIA) | fbit(F_U)};
+    case FSPH_APPLY_SET_TOTAL_ENERGY: return {vbit(F_VEL) | fbit(F_U), fbit(F_E)};
+    case FSPH_APPLY_SAVE_VELOCITYHALF: return {vbit(F_VEL), vbit(F_VELH)};
+    case FSPH_APPLY_LEAPFROG_KICK_V: return {vbit(F_VEL) | vbit(F_ACC) | vbit(F_GACC), vbit(F_VEL)};
+    case FSPH_APPLY_LEAPFROG_KICK_U: return {fbit(F_U) | fbit(F_DUDT), fbit(F_U)};
+    case FSPH_APPLY_LEAPFROG_KICK_E: return {fbit(F_E) | fbit(F_DEDT), fbit(F_E)};
+    case FSPH_APPLY_LEAPFROG_DRIFT: return {vbit(F_POS) | vbit(F_VEL), vbit(F_POS)};
+    case FSPH_APPLY_RECOMPUTE_P_CS: return {fbit(F_U) | fbit(F_DUDT) | eos_in, fbit(F_P) | fbit(F_CS)};
+    case FSPH_APPLY_RECOMPUTE_P_CS_THERMOKINETIC:
+      return {vbit(F_VEL) | vbit(F_ACC) | fbit(F_E) | fbit(F_DEDT) | eos_in, fbit(F_U) | fbit(F_P) | fbit(F_CS)};
+    case FSPH_APPLY_COMPUTE_DT: return {fbit(F_H) | vbit(F_VEL) | vbit(F_ACC) | vbit(F_GACC) | fbit(F_VSIG) | fbit(F_U), fbit(F_DT)};
+    case FSPH_APPLY_CHECK_NANS:
+      return {vbit(F_POS) | vbit(F_VEL) | vbit(F_VELH) | vbit(F_ACC) | vbit(F_GACC) | fbit(F_MASS) | fbit(F_GPOT) | fbit(F_RHO) | fbit(F_P) |
+                fbit(F_E) | fbit(F_DEDT) | fbit(F_DUDT) | fbit(F_ADIA) | fbit(F_VSIG) | fbit(F_U), 0};
+    case FSPH_APPLY_CHECK_NEGATIVITY: return {fbit(F_RHO) | fbit(F_P) | fbit(F_U), 0};
+    case FSPH_APPLY_INITIALIZE_ALPHA: return {0, fbit(F_ALPHA)};
+    case FSPH_APPLY_ADD_DRAG_ACCELERATION: return {vbit(F_VEL) | vbit(F_ACC), vbit(F_ACC)};
+    case FSPH_APPLY_ADD_DRAG_DEDT: return {vbit(F_VEL) | fbit(F_DEDT), fbit(F_DEDT)};
+    case FSPH_APPLY_ADD_DRAG_DUDT: return {vbit(F_VEL) | fbit(F_DUDT), fbit(F_DUDT)};
+    case 100: return {fbit(F_MASS) | fbit(F_RHO), fbit(F_H)};
+    case 101: return {0, fbit(F_H)};
+  }
+  throw std::runtime_error("unknown apply op");
+}
+
+// One functor on the body's columns held in registers (v[f] = column f of this body): the statements of the reference's
+// functors, operation by operation (this file is compiled without FMA contraction).
 template<int D>
-__device__ __forceinline__ void apply_one(const Cols & c, const int64_t i, const int op, const PhysParams & pp, uint32_t * __restrict__ status) {
+__device__ __forceinline__ void apply_one(double * v, const int op, const PhysParams & pp, uint32_t * __restrict__ status) {
   const double dt = pp.dt;
   switch(op) {
-    case FSPH_APPLY_EOS_INIT:
-      c.f[F_ADIA][i] = c.f[F_P][i] / pow(c.f[F_RHO][i], pp.gamma);
-      break;
+    case FSPH_APPLY_EOS_INIT: {
+      // eos::init: adiabatic invariant (ideal / polytropic eos.h:68-83; piecewise polytrope :337-351: K1 of the first
+      // segment), internal energy of the cold white dwarf (:292-302)
+      const double rho = v[F_RHO], P = v[F_P];
+      if(pp.eos == FSPH_EOS_PPT) {
+        double K1;
+        if(rho < pp.rho_thr) K1 = P / pow(rho, pp.gamma);
+        else {
+          const double K2 = P / pow(rho, pp.gamma2);
+          K1 = K2 * pow(pp.rho_thr, pp.gamma2 - pp.gamma);
+        }
+        v[F_ADIA] = K1;
+      }
+      else if(pp.eos == FSPH_EOS_WD) {
+        const double A_wd = 6.00233181e22, B_wd_nm = 9.73932099e5;
+        const double x = cbrt(rho * v[F_YE] / B_wd_nm), x2 = x * x, x3 = x * x * x;
+        v[F_U] = A_wd / rho * (8. * x3 * (sqrt(x2 + 1.) - 1.) - (x * (2. * x2 - 3.) * sqrt(x2 + 1.) + 3. * asinh(x)));
+      }
+      else if(pp.eos != FSPH_EOS_NONE) v[F_ADIA] = P / pow(rho, pp.gamma);
+    } break;
     case FSPH_APPLY_SET_TOTAL_ENERGY: {
       double v2 = 0.0;
 #pragma unroll
-      for(int d = 0; d < D; ++d) v2 = v2 + c.f[F_VEL + d][i] * c.f[F_VEL + d][i];
-      c.f[F_E][i] = .5 * v2 + c.f[F_U][i] + 0.0;
+      for(int d = 0; d < D; ++d) v2 = v2 + v[F_VEL + d] * v[F_VEL + d];
+      v[F_E] = .5 * v2 + v[F_U] + 0.0;
     } break;
     case FSPH_APPLY_SAVE_VELOCITYHALF:
 #pragma unroll
-      for(int d = 0; d < D; ++d) c.f[F_VELH + d][i] = c.f[F_VEL + d][i];
+      for(int d = 0; d < D; ++d) v[F_VELH + d] = v[F_VEL + d];
       break;
     case FSPH_APPLY_LEAPFROG_KICK_V:
 #pragma unroll
-      for(int d = 0; d < D; ++d) c.f[F_VEL + d][i] = c.f[F_VEL + d][i] + (0.5 * dt) * (c.f[F_ACC + d][i] + c.f[F_GACC + d][i]);
+      for(int d = 0; d < D; ++d) v[F_VEL + d] = v[F_VEL + d] + (0.5 * dt) * (v[F_ACC + d] + v[F_GACC + d]);
       break;
-    case FSPH_APPLY_LEAPFROG_KICK_U: c.f[F_U][i] = c.f[F_U][i] + 0.5 * dt * c.f[F_DUDT][i]; break;
-    case FSPH_APPLY_LEAPFROG_KICK_E: c.f[F_E][i] = c.f[F_E][i] + 0.5 * dt * c.f[F_DEDT][i]; break;
+    case FSPH_APPLY_LEAPFROG_KICK_U: v[F_U] = v[F_U] + 0.5 * dt * v[F_DUDT]; break;
+    case FSPH_APPLY_LEAPFROG_KICK_E: v[F_E] = v[F_E] + 0.5 * dt * v[F_DEDT]; break;
     case FSPH_APPLY_LEAPFROG_DRIFT:
 #pragma unroll
-      for(int d = 0; d < D; ++d) c.f[F_POS + d][i] = c.f[F_POS + d][i] + dt * c.f[F_VEL + d][i];
+      for(int d = 0; d < D; ++d) v[F_POS + d] = v[F_POS + d] + dt * v[F_VEL + d];
       break;
     case FSPH_APPLY_RECOMPUTE_P_CS: {
-      const double u = c.f[F_U][i] + 0.5 * dt * c.f[F_DUDT][i];
-      eos_p_cs(pp, c.f[F_RHO][i], u, c.f[F_ADIA][i], c.f[F_P][i], c.f[F_CS][i]);
+      const double u = v[F_U] + 0.5 * dt * v[F_DUDT];
+      eos_p_cs(pp, v[F_RHO], u, v[F_ADIA], v[F_YE], v[F_P], v[F_CS]);
     } break;
     case FSPH_APPLY_RECOMPUTE_P_CS_THERMOKINETIC: {
       double v2 = 0.0, va = 0.0;
 #pragma unroll
       for(int d = 0; d < D; ++d) {
-        v2 = v2 + c.f[F_VEL + d][i] * c.f[F_VEL + d][i];
-        va = va + c.f[F_VEL + d][i] * c.f[F_ACC + d][i];
+        v2 = v2 + v[F_VEL + d] * v[F_VEL + d];
+        va = va + v[F_VEL + d] * v[F_ACC + d];
       }
-      const double eint = c.f[F_E][i] - .5 * v2 - 0.0;
+      const double eint = v[F_E] - .5 * v2 - 0.0;
       if(!(eint > 0)) atomicOr(status, (uint32_t)ERR_U_NONPOS);
-      c.f[F_U][i] = eint;
-      const double u = eint + 0.5 * dt * (c.f[F_DEDT][i] - va);
-      eos_p_cs(pp, c.f[F_RHO][i], u, c.f[F_ADIA][i], c.f[F_P][i], c.f[F_CS][i]);
+      v[F_U] = eint;
+      const double u = eint + 0.5 * dt * (v[F_DEDT] - va);
+      eos_p_cs(pp, v[F_RHO], u, v[F_ADIA], v[F_YE], v[F_P], v[F_CS]);
     } break;
     case FSPH_APPLY_COMPUTE_DT: {
       const double tiny = 1e-24, mc = 0.6;
-      const double dx = c.f[F_H][i] / (pp.eta * pp.kernel_width);
+      const double dx = v[F_H] / (pp.eta * pp.kernel_width);
       double v2 = 0.0, a2 = 0.0, vg = 0.0;
 #pragma unroll
       for(int d = 0; d < D; ++d) {
-        const double v = c.f[F_VEL + d][i], a = c.f[F_ACC + d][i] + c.f[F_GACC + d][i];
-        v2 = v2 + v * v;
+        const double w = v[F_VEL + d], a = v[F_ACC + d] + v[F_GACC + d];
+        v2 = v2 + w * w;
         a2 = a2 + a * a;
-        vg = vg + v * c.f[F_GACC + d][i];
+        vg = vg + w * v[F_GACC + d];
       }
-      const double vn = D == 1 ? fabs(c.f[F_VEL][i]) : sqrt(v2);
-      const double acc = D == 1 ? fabs(c.f[F_ACC][i] + c.f[F_GACC][i]) : sqrt(a2);
+      const double vn = D == 1 ? fabs(v[F_VEL]) : sqrt(v2);
+      const double acc = D == 1 ? fabs(v[F_ACC] + v[F_GACC]) : sqrt(a2);
       const double dt_v = dx / (vn + tiny);
       const double dt_a = sqrt(dx / (acc + tiny));
-      const double dt_c = dx / (tiny + c.f[F_VSIG][i] * (1 + mc * pp.alpha));
+      const double dt_c = dx / (tiny + v[F_VSIG] * (1 + mc * pp.alpha));
       double dtmin = pp.cfl * fmin(fmin(dt_v, dt_a), dt_c);
       if(pp.evolve_u && pp.thermokinetic) {
-        const double eint = c.f[F_U][i];
+        const double eint = v[F_U];
         if(!(eint > 0)) atomicOr(status, (uint32_t)ERR_U_NONPOS);
         int it;
         for(it = 0; it < 20; ++it) {
@@ -124,59 +185,97 @@ __device__ __forceinline__ void apply_one(const Cols & c, const int64_t i, const
         }
         if(it >= 20) atomicOr(status, (uint32_t)ERR_DT_LOOP);
       }
-      c.f[F_DT][i] = dtmin;
+      v[F_DT] = dtmin;
     } break;
     case FSPH_APPLY_CHECK_NANS: {
       bool bad = false;
 #pragma unroll
       for(int d = 0; d < D; ++d) {
-        bad = bad || isnan(c.f[F_POS + d][i]) || isnan(c.f[F_VEL + d][i]) || isnan(c.f[F_VELH + d][i]) ||
-              isnan(c.f[F_ACC + d][i]) || isnan(c.f[F_GACC + d][i]);
+        bad = bad || isnan(v[F_POS + d]) || isnan(v[F_VEL + d]) || isnan(v[F_VELH + d]) || isnan(v[F_ACC + d]) || isnan(v[F_GACC + d]);
       }
-      bad = bad || isnan(c.f[F_MASS][i]) || isnan(c.f[F_GPOT][i]) || isnan(c.f[F_RHO][i]) || isnan(c.f[F_P][i]) ||
-            isnan(c.f[F_E][i]) || isnan(c.f[F_DEDT][i]) || isnan(c.f[F_DUDT][i]) || isnan(c.f[F_ADIA][i]) || isnan(c.f[F_VSIG][i]);
-      if(pp.evolve_u) bad = bad || isnan(c.f[F_U][i]);
+      bad = bad || isnan(v[F_MASS]) || isnan(v[F_GPOT]) || isnan(v[F_RHO]) || isnan(v[F_P]) || isnan(v[F_E]) || isnan(v[F_DEDT]) ||
+            isnan(v[F_DUDT]) || isnan(v[F_ADIA]) || isnan(v[F_VSIG]);
+      if(pp.evolve_u) bad = bad || isnan(v[F_U]);
       if(bad) atomicOr(status, (uint32_t)ERR_NAN);
     } break;
     case FSPH_APPLY_CHECK_NEGATIVITY:
-      if(c.f[F_RHO][i] < 0 || c.f[F_P][i] < 0 || (pp.evolve_u && c.f[F_U][i] < 0)) atomicOr(status, (uint32_t)ERR_NEGATIVE);
+      if(v[F_RHO] < 0 || v[F_P] < 0 || (pp.evolve_u && v[F_U] < 0)) atomicOr(status, (uint32_t)ERR_NEGATIVE);
       break;
-    case 100: {  // compute_smoothinglength
-      const double q = c.f[F_MASS][i] / c.f[F_RHO][i];
-      const double r = D == 1 ? q : (D == 2 ? sqrt(q) : cbrt(q));
-      c.f[F_H][i] = r * pp.eta * pp.kernel_width;
+    case FSPH_APPLY_INITIALIZE_ALPHA:   // viscosity.h:172-180
+      v[F_ALPHA] = pp.visc == FSPH_VISC_CONSTANT ? pp.alpha : 0.0;
+      break;
+    case FSPH_APPLY_ADD_DRAG_ACCELERATION:
+    case FSPH_APPLY_ADD_DRAG_DEDT:
+    case FSPH_APPLY_ADD_DRAG_DUDT: {
+      // external_force::acceleration_drag (eforce.h:441-451): a = 0 - (beta + gamma v^2) v
+      double v2 = v[F_VEL] * v[F_VEL];
+#pragma unroll
+      for(int d = 1; d < D; ++d) v2 = v2 + v[F_VEL + d] * v[F_VEL + d];
+      const double k = pp.relax_beta + pp.relax_gamma * v2;
+      double va = 0.0;
+#pragma unroll
+      for(int d = 0; d < D; ++d) {
+        const double w = v[F_VEL + d], a = 0.0 - k * w;
+        if(op == FSPH_APPLY_ADD_DRAG_ACCELERATION) v[F_ACC + d] = v[F_ACC + d] + a;
+        va = va + w * a;
+      }
+      if(op == FSPH_APPLY_ADD_DRAG_DEDT) v[F_DEDT] = v[F_DEDT] + va;
+      if(op == FSPH_APPLY_ADD_DRAG_DUDT) v[F_DUDT] = v[F_DUDT] + va;
     } break;
-    case 101: c.f[F_H][i] = pp.dt; break;  // uniform h (value carried in pp.dt)
+    case 100: {  // compute_smoothinglength
+      const double q = v[F_MASS] / v[F_RHO];
+      const double r = D == 1 ? q : (D == 2 ? sqrt(q) : cbrt(q));
+      v[F_H] = r * pp.eta * pp.kernel_width;
+    } break;
+    case 101: v[F_H] = pp.dt; break;  // uniform h (value carried in pp.dt)
   }
 }
 
-// Several element-wise functors of the driver loop in one pass over HBM (same per-particle order of operations).
+// Several element-wise functors of the driver loop in ONE pass over HBM: every column any of them reads is loaded once
+// up front (all loads in flight together), the functors run in order on the registers, every column any of them wrote is
+// stored once.  `need` / `dirty`: the column sets (bit f = F64 column f), from op_access on the host.
 template<int D>
-__global__ void __launch_bounds__(256) k_apply(Cols c, int64_t n, OpList ops, PhysParams pp, uint32_t * __restrict__ status) {
+__global__ void __launch_bounds__(128) k_apply(Cols c, int64_t n, OpList ops, PhysParams pp, uint64_t need, uint64_t dirty,
+  uint32_t * __restrict__ status) {
   // n = number of owned bodies, starting at c.own_lo (remote copies are refreshed from their owner: reset_ghosts)
   const int64_t i = c.own_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= c.own_lo + n) return;
-  for(int k = 0; k < ops.n; ++k) apply_one<D>(c, i, ops.op[k], pp, status);
+  double v[NF64];
+#pragma unroll
+  for(int f = 0; f < NF64; ++f) {
+    v[f] = 0.0;
+    if(f < F_MASS && (f % 3) >= D) continue;   // unused vector components
+    if((need >> f) & 1ull) v[f] = c.f[f][i];
+  }
+  for(int k = 0; k < ops.n; ++k) apply_one<D>(v, ops.op[k], pp, status);
+#pragma unroll
+  for(int f = 0; f < NF64; ++f) {
+    if(f < F_MASS && (f % 3) >= D) continue;
+    if((dirty >> f) & 1ull) c.f[f][i] = v[f];
+  }
 }
 
 void apply_fused(System & s, const int * op_list, int nops) {
   if(s.n <= 0 || nops <= 0) return;
   if(nops > 8) throw std::runtime_error("apply_fused: too many ops");
   const int64_t n_own = s.n_owned_or_n();
-  unsigned nb = (unsigned)((n_own + 255) / 256);
+  unsigned nb = (unsigned)((n_own + 127) / 128);
   uint32_t * st = s.b_status.as<uint32_t>();
-  // Measured on B200 (64 M particles): one kernel looping over a run-time op list is slower than one launch per
-  // functor (the dependent load -> compute -> store chains of consecutive ops serialise on HBM latency), so the
-  // list is issued as separate streaming passes; a compile-time fused pass is future work.
+  const PhysParams pp = s.phys();
+  OpList ops;
+  ops.n = nops;
+  uint64_t need = 0, dirty = 0;
+  for(int j = 0; j < 8; ++j) ops.op[j] = j < nops ? op_list[j] : -1;
   for(int k = 0; k < nops; ++k) {
-    OpList ops;
-    ops.n = 1;
-    for(int j = 0; j < 8; ++j) ops.op[j] = -1;
-    ops.op[0] = op_list[k];
-    if(s.dim == 1) FSPH_LAUNCH((k_apply<1>), nb, 256, s.stream, s.cols(), n_own, ops, s.phys(), st);
-    else if(s.dim == 2) FSPH_LAUNCH((k_apply<2>), nb, 256, s.stream, s.cols(), n_own, ops, s.phys(), st);
-    else FSPH_LAUNCH((k_apply<3>), nb, 256, s.stream, s.cols(), n_own, ops, s.phys(), st);
+    const OpAccess a = op_access(op_list[k], pp);
+    need |= a.rd | a.wr;   // a functor may write a column only for some bodies (e.g. eos::init): keep the others' values
+    dirty |= a.wr;
   }
+  for(int f = 0; f < NF64; ++f)
+    if(!s.col_used[f]) { need &= ~fbit(f); dirty &= ~fbit(f); }
+  if(s.dim == 1) FSPH_LAUNCH((k_apply<1>), nb, 128, s.stream, s.cols(), n_own, ops, pp, need, dirty, st);
+  else if(s.dim == 2) FSPH_LAUNCH((k_apply<2>), nb, 128, s.stream, s.cols(), n_own, ops, pp, need, dirty, st);
+  else FSPH_LAUNCH((k_apply<3>), nb, 128, s.stream, s.cols(), n_own, ops, pp, need, dirty, st);
   FSPH_CUDA_OK(cudaGetLastError());
   for(int k = 0; k < nops; ++k) {
     // the cached pair viscosities depend on v_1/2, rho and c_s (fsph_sweeps.cu)

@@ -133,7 +133,8 @@ static void resize_keep(System & s, int64_t n_new, int64_t n_keep) {
   std::vector<std::pair<DevBuf *, int>> cols;
   live_columns(s, cols);
   for(auto & c : cols) c.first->grow_keep((size_t)n_new * c.second, (size_t)n_keep * c.second, s.stream);
-  for(int f = 0; f < NF64; ++f) s.col[f].grow_keep((size_t)n_new * 8, 0, s.stream);  // the others only need the room
+  for(int f = 0; f < NF64; ++f)
+    if(s.col_used[f]) s.col[f].grow_keep((size_t)n_new * 8, 0, s.stream);  // the others only need the room
   s.col_nneigh.grow_keep((size_t)n_new * 4, 0, s.stream);
   s.scratch_col.reserve((size_t)n_new * 8);
 }

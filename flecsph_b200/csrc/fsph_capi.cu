@@ -15,7 +15,7 @@ namespace {
 
 const int VEC_FIELD[5] = {F_POS, F_VEL, F_VELH, F_ACC, F_GACC};
 
-int scalar_field(int col) {
+int scalar_field_any(int col) {
   switch(col) {
     case FSPH_COL_MASS: return F_MASS;
     case FSPH_COL_H: return F_H;
@@ -31,8 +31,21 @@ int scalar_field(int col) {
     case FSPH_COL_VSIG: return F_VSIG;
     case FSPH_COL_GPOT: return F_GPOT;
     case FSPH_COL_ADIABATIC: return F_ADIA;
+    case FSPH_COL_YE: return F_YE;
+    case FSPH_COL_DIVV: return F_DIVV;
+    case FSPH_COL_DDIVVDT: return F_DDIVVDT;
+    case FSPH_COL_TRIGGER: return F_TRIGGER;
+    case FSPH_COL_XI: return F_XI;
+    case FSPH_COL_TRACESS: return F_TRACESS;
+    case FSPH_COL_GRADV: return F_GRADV;
     default: return -1;
   }
+}
+
+// F64 index of a scalar column of this system; -1 for non-scalar columns and for optional columns it did not allocate
+int scalar_field(const System & s, int col) {
+  const int f = scalar_field_any(col);
+  return f >= 0 && s.col_used[f] ? f : -1;
 }
 
 void finish_phases(System & s) {
@@ -118,7 +131,8 @@ void do_sweep(System & s, int op) {
     neighbor_search(s);
   }
   const char * nm = (op == FSPH_SWEEP_DENSITY_PRESSURE_SOUNDSPEED || op == 100) ? "density" : (op == FSPH_SWEEP_ACCELERATION || op == 101) ? "acceleration"
-                  : op == FSPH_SWEEP_DUDT ? "dudt" : op == FSPH_SWEEP_DEDT ? "dedt" : "neighbors";
+                  : op == FSPH_SWEEP_DUDT ? "dudt" : op == FSPH_SWEEP_DEDT ? "dedt" : op == FSPH_SWEEP_COMPUTE_ALPHA ? "viscosity_alpha"
+                  : op == FSPH_SWEEP_SHORT_RANGE_REPULSION ? "repulsion" : "neighbors";
   PhaseScope p(s, nm);
   sweep(s, op);
 }
@@ -139,9 +153,24 @@ void do_step(System & s, int initial) {
   const int energy_sweep = P.thermokinetic_formulation ? FSPH_SWEEP_DEDT : FSPH_SWEEP_DUDT;
   const int kick_energy = P.thermokinetic_formulation ? FSPH_APPLY_LEAPFROG_KICK_E : FSPH_APPLY_LEAPFROG_KICK_U;
   int tail[8], ntail = 0;
+  const bool relaxing = s.iteration < P.relaxation_steps;
+  const bool cullen = P.sph_viscosity != FSPH_VISC_CONSTANT;
+  // compute_acceleration and what the drivers hang on it (hydro/main_driver.cc:123-133,197-206): the adaptive viscosity
+  // sweep before it, the relaxation terms after it
+  auto acceleration = [&]() {
+    if(cullen) do_sweep(s, FSPH_SWEEP_COMPUTE_ALPHA);
+    do_reset_ghosts(s);
+    do_sweep(s, 101);
+    if(relaxing) {
+      A(FSPH_APPLY_ADD_DRAG_ACCELERATION);
+      do_sweep(s, FSPH_SWEEP_SHORT_RANGE_REPULSION);
+    }
+  };
   auto energy_passes = [&]() {
     for(int m = 1; m <= P.pressure_updates_number; ++m) {
       do_sweep(s, energy_sweep);
+      // relaxation phase (hydro/main_driver.cc:152,165,221,235): energy dissipated by the drag
+      if(relaxing) A(P.thermokinetic_formulation ? FSPH_APPLY_ADD_DRAG_DEDT : FSPH_APPLY_ADD_DRAG_DUDT);
       if(m < P.pressure_updates_number) {
         A(recompute_op);
         do_reset_ghosts(s);
@@ -160,10 +189,10 @@ void do_step(System & s, int initial) {
     do_update_iteration(s);
     A(FSPH_APPLY_EOS_INIT);
     if(P.thermokinetic_formulation) A(FSPH_APPLY_SET_TOTAL_ENERGY);
+    if(cullen) A(FSPH_APPLY_INITIALIZE_ALPHA);
     do_sweep(s, 100);
     A(FSPH_APPLY_SAVE_VELOCITYHALF);
-    do_reset_ghosts(s);
-    do_sweep(s, 101);
+    acceleration();
     gravity();
     timestep();
     if(P.evolve_internal_energy) energy_passes();
@@ -196,8 +225,7 @@ void do_step(System & s, int initial) {
       s.skip_dead_columns = false;
     }
     do_sweep(s, 100);
-    do_reset_ghosts(s);
-    do_sweep(s, 101);
+    acceleration();
     gravity();
     A(FSPH_APPLY_LEAPFROG_KICK_V);
     do_reset_ghosts(s);
@@ -285,11 +313,8 @@ fsph_system * fsph_create(const fsph_params * p, int32_t device) {
     g_create_error = "no CUDA device: libflecsph_b200 has no CPU path";
     return nullptr;
   }
-  if(p->eos_type != FSPH_EOS_IDEAL && p->eos_type != FSPH_EOS_POLYTROPIC) {
-    g_create_error = "eos_type not implemented on the device (ideal and polytropic are)";
-    return nullptr;
-  }
-  if(p->sph_viscosity != FSPH_VISC_CONSTANT) { g_create_error = "only constant artificial viscosity is implemented on the device"; return nullptr; }
+  if(p->eos_type < 0 || p->eos_type > FSPH_EOS_NONE) { g_create_error = "unknown eos_type"; return nullptr; }
+  if(p->sph_viscosity != FSPH_VISC_CONSTANT && p->sph_viscosity != FSPH_VISC_CULLEN) { g_create_error = "unknown sph_viscosity"; return nullptr; }
   if(p->sph_kernel < 0 || p->sph_kernel > FSPH_KERNEL_SINC) { g_create_error = "unknown sph_kernel"; return nullptr; }
   fsph_system * s = nullptr;
   try {
@@ -299,6 +324,10 @@ fsph_system * fsph_create(const fsph_params * p, int32_t device) {
     s->dim = p->dim;
     s->device = device;
     s->dt = p->initial_dt;
+    // optional columns
+    for(int f = 0; f < F_FIRST_OPTIONAL; ++f) s->col_used[f] = true;
+    s->col_used[F_YE] = p->eos_type == FSPH_EOS_WD;
+    for(int f = F_DIVV; f <= F_GRADV; ++f) s->col_used[f] = p->sph_viscosity == FSPH_VISC_CULLEN;
     // kernels::select, kernels.h:753-764
     s->kernel_width = (p->sph_kernel == FSPH_KERNEL_QUINTIC_SPLINE || p->sph_kernel == FSPH_KERNEL_GAUSSIAN ||
                        p->sph_kernel == FSPH_KERNEL_SUPER_GAUSSIAN) ? 3.0 : 2.0;
@@ -339,6 +368,7 @@ int32_t fsph_resize(fsph_system * s, int64_t n) {
     if(n < 0 || n >= (int64_t(1) << 31)) throw std::runtime_error("bad body count");
     const size_t b8 = (size_t)std::max<int64_t>(n, 1) * 8, b4 = (size_t)std::max<int64_t>(n, 1) * 4;
     for(int f = 0; f < NF64; ++f) {
+      if(!s->col_used[f]) continue;
       s->col[f].reserve(b8);
       FSPH_CUDA_OK(cudaMemsetAsync(s->col[f].p, 0, b8, s->stream));
     }
@@ -374,8 +404,8 @@ int32_t fsph_set_column(fsph_system * s, int32_t col, const void * host) {
       }
       if(col == FSPH_COL_POS) { s->tree_dirty = true; s->search_valid = false; }
     }
-    else if(scalar_field(col) >= 0) {
-      FSPH_CUDA_OK(cudaMemcpyAsync(s->col[scalar_field(col)].p, host, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+    else if(scalar_field(*s, col) >= 0) {
+      FSPH_CUDA_OK(cudaMemcpyAsync(s->col[scalar_field(*s, col)].p, host, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
       if(col == FSPH_COL_H || col == FSPH_COL_MASS) { s->tree_dirty = true; s->search_valid = false; }
     }
     else if(col == FSPH_COL_ID) FSPH_CUDA_OK(cudaMemcpyAsync(s->col_id.p, host, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
@@ -402,7 +432,7 @@ int32_t fsph_get_column(fsph_system * s, int32_t col, void * host) {
     }
     const void * src = nullptr;
     size_t bytes = (size_t)n * 8;
-    if(scalar_field(col) >= 0) src = s->col[scalar_field(col)].p;
+    if(scalar_field(*s, col) >= 0) src = s->col[scalar_field(*s, col)].p;
     else if(col == FSPH_COL_ID) src = s->col_id.p;
     else if(col == FSPH_COL_KEY) src = s->col_key.p;
     else if(col == FSPH_COL_TYPE) { src = s->col_type.p; bytes = (size_t)n * 4; }
@@ -423,7 +453,7 @@ int32_t fsph_set_component(fsph_system * s, int32_t col, int32_t comp, const voi
       if(comp < 0 || comp >= s->dim) throw std::runtime_error("bad component");
       dst = s->col[VEC_FIELD[col] + comp].p;
     }
-    else if(scalar_field(col) >= 0) dst = s->col[scalar_field(col)].p;
+    else if(scalar_field(*s, col) >= 0) dst = s->col[scalar_field(*s, col)].p;
     else if(col == FSPH_COL_ID) dst = s->col_id.p;
     else if(col == FSPH_COL_TYPE) { dst = s->col_type.p; esz = 4; }
     else throw std::runtime_error("column not writable");
@@ -442,7 +472,7 @@ int32_t fsph_get_component(fsph_system * s, int32_t col, int32_t comp, void * ho
       if(comp < 0 || comp >= s->dim) throw std::runtime_error("bad component");
       src = s->col[VEC_FIELD[col] + comp].p;
     }
-    else if(scalar_field(col) >= 0) src = s->col[scalar_field(col)].p;
+    else if(scalar_field(*s, col) >= 0) src = s->col[scalar_field(*s, col)].p;
     else if(col == FSPH_COL_ID) src = s->col_id.p;
     else if(col == FSPH_COL_KEY) src = s->col_key.p;
     else if(col == FSPH_COL_TYPE) { src = s->col_type.p; esz = 4; }
@@ -476,7 +506,7 @@ int32_t fsph_upload_aos(fsph_system * s, const void * bodies, int64_t n, int64_t
     for(int col = 0; col < FSPH_COL_COUNT_; ++col) {
       if(offsets[col] < 0) continue;
       if(col <= FSPH_COL_GACC) for(int d = 0; d < D; ++d) up(s->col[VEC_FIELD[col] + d].p, offsets[col] + 8 * d, 8);
-      else if(scalar_field(col) >= 0) up(s->col[scalar_field(col)].p, offsets[col], 8);
+      else if(scalar_field(*s, col) >= 0) up(s->col[scalar_field(*s, col)].p, offsets[col], 8);
       else if(col == FSPH_COL_ID) up(s->col_id.p, offsets[col], 8);
       else if(col == FSPH_COL_TYPE) up(s->col_type.p, offsets[col], 4);
     }
@@ -500,7 +530,7 @@ int32_t fsph_download_aos(fsph_system * s, void * bodies, int64_t stride, const 
     for(int col = 0; col < FSPH_COL_COUNT_; ++col) {
       if(offsets[col] < 0) continue;
       if(col <= FSPH_COL_GACC) for(int d = 0; d < D; ++d) down(s->col[VEC_FIELD[col] + d].p, offsets[col] + 8 * d, 8);
-      else if(scalar_field(col) >= 0) down(s->col[scalar_field(col)].p, offsets[col], 8);
+      else if(scalar_field(*s, col) >= 0) down(s->col[scalar_field(*s, col)].p, offsets[col], 8);
       else if(col == FSPH_COL_ID) down(s->col_id.p, offsets[col], 8);
       else if(col == FSPH_COL_KEY) down(s->col_key.p, offsets[col], 8);
       else if(col == FSPH_COL_TYPE) down(s->col_type.p, offsets[col], 4);
@@ -558,7 +588,7 @@ int32_t fsph_sweep(fsph_system * s, int32_t op) {
 }
 int32_t fsph_apply(fsph_system * s, int32_t op) {
   return guarded(s, [&]() {
-    if(op < 0 || op > FSPH_APPLY_CHECK_NEGATIVITY) throw std::runtime_error("unknown apply op");
+    if(op < 0 || op > FSPH_APPLY_ADD_DRAG_DUDT) throw std::runtime_error("unknown apply op");
     apply(*s, op);
     check_status(*s);
   });

@@ -560,7 +560,8 @@ static void exchange_bodies(System & s, const std::vector<size_t> & soff, const 
 
 static void ensure_capacity(System & s, int64_t n_total) {
   // columns that are not carried (dead inside fsph_step, derived, neighbour counts) only need the room
-  for(int f = 0; f < NF64; ++f) s.col[f].grow_keep((size_t)n_total * 8, 0, s.stream);
+  for(int f = 0; f < NF64; ++f)
+    if(s.col_used[f]) s.col[f].grow_keep((size_t)n_total * 8, 0, s.stream);
   s.col_nneigh.grow_keep((size_t)n_total * 4, 0, s.stream);
   s.scratch_col.reserve((size_t)n_total * 8);
 }
@@ -996,6 +997,7 @@ void dist_refresh_ghosts(System & s) {
   if(!s.tree_valid) throw std::runtime_error("reset_ghosts before update_iteration");
   const int P = s.comm->nranks;
   std::vector<int> fields = {F_RHO, F_P, F_CS, F_CSOLD};
+  if(s.par.sph_viscosity == FSPH_VISC_CULLEN) { fields.push_back(F_ALPHA); fields.push_back(F_DIVV); }   // read from neighbours
   for(int k = 0; k < s.dim; ++k) { fields.push_back(F_VEL + k); fields.push_back(F_VELH + k); }
   const size_t nf = fields.size();
   const size_t nsend = (size_t)d.nsend, ng = (size_t)d.nghost;

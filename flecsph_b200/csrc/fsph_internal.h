@@ -22,8 +22,13 @@ enum F64 {
   F_MASS = 15, F_H, F_RHO, F_P, F_U, F_E, F_CS, F_DUDT, F_DEDT, F_DT, F_ALPHA, F_VSIG, F_GPOT, F_ADIA,
   F_CSOLD,  // soundspeed before the current density sweep (signal-speed order dependence)
   F_PRHO2,  // P / rho^2, derived right before each pair sweep that needs it (not permuted by the sort)
+  // optional columns (allocated only for the physics that uses them, System::col_used):
+  F_YE,                                  // electron fraction: white-dwarf EOS (eos/eos.h:225-315)
+  F_DIVV, F_DDIVVDT,                     // Cullen-Dehnen viscosity state (default_physics.h:273-300)
+  F_TRIGGER, F_XI, F_TRACESS, F_GRADV,   // ... and the diagnostics viscosity::compute_alpha stores (viscosity.h:193-363)
   NF64
 };
+constexpr int F_FIRST_OPTIONAL = F_YE;
 
 constexpr int SUB_ENTITIES = 128;  // tree_topology.h:2121
 #ifndef FSPH_SUPER_ENTITIES
@@ -135,24 +140,48 @@ struct Search {
 };
 
 struct PhysParams {
-  int kernel, thermokinetic, evolve_u, eos;
+  int kernel, thermokinetic, evolve_u, eos, visc;
   double eta, gamma, alpha, beta, epsilon, cfl, kernel_width;
   double dt;
   int64_t iteration;
   int relaxation_steps;
+  double alpha_max, visc_l, visc_delta;                      // Cullen-Dehnen viscosity
+  double gamma2, rho_thr;                                    // piecewise polytrope
+  double relax_beta, relax_gamma, repulsion_radius, repulsion_gamma;   // relaxation phase
 };
 
 // eos::compute_pressure + compute_soundspeed (include/physics/eos/eos.h): ideal gas :166-183 from the specific internal
-// energy, polytropic :100-118 from the particle's adiabatic invariant K = P / rho^gamma (eos::init, :68-83)
-__host__ __device__ inline void eos_p_cs(const PhysParams & pp, double rho, double u, double K, double & P, double & cs) {
+// energy, polytropic :100-118 from the particle's adiabatic invariant K = P / rho^gamma (eos::init, :68-83), piecewise
+// polytrope :365-394 (K = K1 of the first segment), cold white dwarf :254-275 from the electron fraction
+__host__ __device__ inline void eos_p_cs(const PhysParams & pp, double rho, double u, double K, double ye, double & P, double & cs) {
   if(pp.eos == FSPH_EOS_POLYTROPIC) {
     P = K * pow(rho, pp.gamma);
     cs = sqrt(K * pp.gamma * pow(rho, pp.gamma - 1.));
   }
-  else {
+  else if(pp.eos == FSPH_EOS_PPT) {
+    if(rho < pp.rho_thr) {
+      P = K * pow(rho, pp.gamma);
+      cs = sqrt(K * pp.gamma * pow(rho, pp.gamma - 1.));
+    }
+    else {
+      const double K2 = K * pow(pp.rho_thr, pp.gamma - pp.gamma2);
+      P = K2 * pow(rho, pp.gamma2);
+      cs = sqrt(K2 * pp.gamma2 * pow(rho, pp.gamma2 - 1.));
+    }
+  }
+  else if(pp.eos == FSPH_EOS_WD) {
+    const double A_wd = 6.00233181e22, B_wd_nm = 9.73932099e5, C_LIGHT_CGS = 2.99792458e10;
+    const double x = cbrt(rho * ye / B_wd_nm), x2 = x * x;
+    P = A_wd * (x * (2. * x2 - 3.) * sqrt(x2 + 1.) + 3. * asinh(x));
+    const double numer = (1. + x2) * (6. * x2 - 3.) + 3. + x2 * (2. * x2 - 3.);
+    const double denom = (1. + x2) * (6. * x2 + 1.) - 1. + x2 * (2. * x2 + 1.);
+    cs = sqrt(numer / (3. * denom)) * C_LIGHT_CGS;
+  }
+  else if(pp.eos == FSPH_EOS_IDEAL) {
     P = (pp.gamma - 1.) * rho * u;
     cs = sqrt(pp.gamma * (pp.gamma - 1.) * u);
   }
+  // FSPH_EOS_NONE: pressure and sound speed are left as they are (eos.h:425-432)
 }
 
 struct Phase {
@@ -185,6 +214,7 @@ struct System {
   // inside fsph_step the sort need not permute columns that are recomputed before their next read
   bool skip_dead_columns = false;
   bool dead_col[NF64] = {};
+  bool col_used[NF64] = {};   // optional columns this system allocates (fsph_create)
 
   // storage
   DevBuf col[NF64], col_id, col_key, col_type, col_nneigh, scratch_col;
@@ -198,7 +228,7 @@ struct System {
   DevBuf b_wc_super, b_super_cell, b_sl_off, b_sl_nodes;
   DevBuf b_wc_cell, b_cand, b_cnt0, b_cnt1;
   DevBuf b_status, b_red, b_levels, b_search_scratch;
-  DevBuf b_blk_wc, b_blk_meta, b_dir, b_nl;
+  DevBuf b_blk_wc, b_blk_meta, b_dir, b_nl, b_super_queue;
   DevBuf b_pair_a, b_pair_pi;         // per-pair caches of the sweeps, parallel to the list arena (fsph_sweeps.cu)
   unsigned long long est_cand = 0, est_dir = 0, est_rows = 0;  // sizes of the previous neighbour structure (capacity estimate)
   int64_t est_n = 0;

@@ -41,7 +41,8 @@
 
 namespace fsph {
 
-constexpr int SW_QCAP = 4096;   // node frontier capacity per level of the super-cell walk
+constexpr int SW_QCAP = 16384;  // node frontier capacity per level of the super-cell walk (per-CTA strip of global memory)
+constexpr int SW_NT = 256;      // threads per CTA of the super-cell walk
 constexpr int SR_NT = BLK_BODIES;
 constexpr int SR_NW = SR_NT / 32;
 constexpr int SR_CHUNK = 2048;  // super-list entries filtered per round (8 per thread)
@@ -123,108 +124,120 @@ __device__ __forceinline__ double box_gap2(const double * amn, const double * am
 // distance between C's box and the tight box of S's positions is at most the largest h in S.  The nodes that pass
 // and have leaf children are S's list (in walk order: fixed).  MODE 0 counts, MODE 1 fills (offsets: prefix sum).
 template<int D, int MODE>
-__global__ void __launch_bounds__(64) k_super_walk(Tree t, Cols c, Search sr, uint32_t * __restrict__ status) {
-  constexpr int NT = 64;
-  __shared__ int32_t queue[2][SW_QCAP];
-  __shared__ uint8_t qres[SW_QCAP];
+__global__ void __launch_bounds__(SW_NT) k_super_walk(Tree t, Cols c, Search sr, const int32_t * __restrict__ super_first_wc, int32_t * __restrict__ gqueue,
+  uint32_t * __restrict__ status) {
+  constexpr int NT = SW_NT;
   __shared__ uint32_t scan_sm[NT / 32];
   __shared__ double red_sm[NT / 32][2 * D + 1];
-  const int tid = threadIdx.x, sidx = blockIdx.x;
-  int start, P;
-  {
-    const int v = t.cell[sr.super_cell[sidx]];
-    if(v >= 0) { start = v; P = 1; }
-    else { start = t.node_start[~v]; P = t.sub[~v]; }
-  }
-  double tmn[D], tmx[D], hmax = 0.0;
-#pragma unroll
-  for(int d = 0; d < D; ++d) { tmn[d] = 1.79769313486231570e308; tmx[d] = -1.79769313486231570e308; }
-  for(int k = tid; k < P; k += NT) {
-#pragma unroll
-    for(int d = 0; d < D; ++d) {
-      const double x = c.f[F_POS + d][start + k];
-      tmn[d] = fmin(tmn[d], x);
-      tmx[d] = fmax(tmx[d], x);
+  // the node frontier lives in a per-CTA strip of global memory (two levels of SW_QCAP nodes + one result byte per node):
+  // its size depends on the data (bodies per leaf-parent node, kernel width), and the walk is a small part of the search
+  int32_t * const queue0 = gqueue + (size_t)blockIdx.x * (2 * SW_QCAP + SW_QCAP / 4);
+  uint8_t * const qres = reinterpret_cast<uint8_t *>(queue0 + 2 * SW_QCAP);
+  const int tid = threadIdx.x;
+  for(int sidx = blockIdx.x; sidx < sr.nsuper; sidx += gridDim.x) {
+    __syncthreads();
+    if(super_first_wc[sidx] < 0) {
+      // no work cell of this rank inside (remote copies only): no list
+      if(MODE == 0 && tid == 0) sr.sl_off[sidx] = 0;
+      continue;
     }
-    hmax = fmax(hmax, c.f[F_H][start + k]);
-  }
-#pragma unroll
-  for(int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-    for(int d = 0; d < D; ++d) {
-      tmn[d] = fmin(tmn[d], __shfl_xor_sync(0xffffffffu, tmn[d], o));
-      tmx[d] = fmax(tmx[d], __shfl_xor_sync(0xffffffffu, tmx[d], o));
+    int start, P;
+    {
+      const int v = t.cell[sr.super_cell[sidx]];
+      if(v >= 0) { start = v; P = 1; }
+      else { start = t.node_start[~v]; P = t.sub[~v]; }
     }
-    hmax = fmax(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
-  }
-  if((tid & 31) == 0) {
+    double tmn[D], tmx[D], hmax = 0.0;
 #pragma unroll
-    for(int d = 0; d < D; ++d) { red_sm[tid >> 5][d] = tmn[d]; red_sm[tid >> 5][D + d] = tmx[d]; }
-    red_sm[tid >> 5][2 * D] = hmax;
-  }
-  if(tid == 0) queue[0][0] = 0;  // the root node
-  __syncthreads();
+    for(int d = 0; d < D; ++d) { tmn[d] = 1.79769313486231570e308; tmx[d] = -1.79769313486231570e308; }
+    for(int k = tid; k < P; k += NT) {
 #pragma unroll
-  for(int ww = 0; ww < NT / 32; ++ww) {
-#pragma unroll
-    for(int d = 0; d < D; ++d) {
-      tmn[d] = fmin(tmn[d], red_sm[ww][d]);
-      tmx[d] = fmax(tmx[d], red_sm[ww][D + d]);
-    }
-    hmax = fmax(hmax, red_sm[ww][2 * D]);
-  }
-  const double hmax2 = hmax * hmax * (1.0 + 1e-9);
-  int32_t * out = MODE == 1 ? sr.sl_nodes + sr.sl_off[sidx] : nullptr;
-  int ncur = 1, cur = 0;
-  uint32_t nlist = 0;
-  while(ncur > 0) {
-    uint32_t my_nodes = 0, my_list = 0;
-    for(int j = tid; j < ncur; j += NT) {
-      const NodeRec rec = t.noderec[queue[cur][j]];
-      uint32_t r = 0;
-      if(box_gap2<D>(rec.bmin, rec.bmax, tmn, tmx) <= hmax2) {
-        const uint32_t node_mask = ((1u << rec.nchild) - 1u) & ~rec.leafmask;
-        r = (uint32_t)__popc(node_mask) | (rec.leafmask ? 0x80u : 0u);
+      for(int d = 0; d < D; ++d) {
+        const double x = c.f[F_POS + d][start + k];
+        tmn[d] = fmin(tmn[d], x);
+        tmx[d] = fmax(tmx[d], x);
       }
-      qres[j] = (uint8_t)r;
-      my_nodes += r & 0x3fu;
-      my_list += (r >> 7) & 1u;
+      hmax = fmax(hmax, c.f[F_H][start + k]);
     }
-    uint32_t total;
-    const uint32_t ex = block_scan_u32<NT>(my_nodes | (my_list << 16), total, scan_sm);
-    uint32_t qpos = ex & 0xffffu, lpos = nlist + (ex >> 16);
-    const uint32_t nnext_raw = total & 0xffffu;
-    for(int j = tid; j < ncur; j += NT) {
-      const uint32_t r = qres[j];
-      if(r == 0) continue;
-      const int nd = queue[cur][j];
-      if(r & 0x3fu) {
-        const NodeRec rec = t.noderec[nd];
-        uint32_t node_mask = ((1u << rec.nchild) - 1u) & ~rec.leafmask;
-        while(node_mask) {
-          const int b = __ffs(node_mask) - 1;
-          node_mask &= node_mask - 1;
-          // node children of a node have consecutive node indices (level order)
-          if(qpos < SW_QCAP) queue[cur ^ 1][qpos] = rec.first_child_node + __popc(~rec.leafmask & ((1u << b) - 1u));
-          ++qpos;
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for(int d = 0; d < D; ++d) {
+        tmn[d] = fmin(tmn[d], __shfl_xor_sync(0xffffffffu, tmn[d], o));
+        tmx[d] = fmax(tmx[d], __shfl_xor_sync(0xffffffffu, tmx[d], o));
+      }
+      hmax = fmax(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
+    }
+    if((tid & 31) == 0) {
+#pragma unroll
+      for(int d = 0; d < D; ++d) { red_sm[tid >> 5][d] = tmn[d]; red_sm[tid >> 5][D + d] = tmx[d]; }
+      red_sm[tid >> 5][2 * D] = hmax;
+    }
+    if(tid == 0) queue0[0] = 0;  // the root node
+    __syncthreads();
+#pragma unroll
+    for(int ww = 0; ww < NT / 32; ++ww) {
+#pragma unroll
+      for(int d = 0; d < D; ++d) {
+        tmn[d] = fmin(tmn[d], red_sm[ww][d]);
+        tmx[d] = fmax(tmx[d], red_sm[ww][D + d]);
+      }
+      hmax = fmax(hmax, red_sm[ww][2 * D]);
+    }
+    const double hmax2 = hmax * hmax * (1.0 + 1e-9);
+    int32_t * out = MODE == 1 ? sr.sl_nodes + sr.sl_off[sidx] : nullptr;
+    int ncur = 1, cur = 0;
+    uint32_t nlist = 0;
+    while(ncur > 0) {
+      const int32_t * qc = queue0 + cur * SW_QCAP;
+      int32_t * qn = queue0 + (cur ^ 1) * SW_QCAP;
+      uint32_t my_nodes = 0, my_list = 0;
+      for(int j = tid; j < ncur; j += NT) {
+        const NodeRec rec = t.noderec[qc[j]];
+        uint32_t r = 0;
+        if(box_gap2<D>(rec.bmin, rec.bmax, tmn, tmx) <= hmax2) {
+          const uint32_t node_mask = ((1u << rec.nchild) - 1u) & ~rec.leafmask;
+          r = (uint32_t)__popc(node_mask) | (rec.leafmask ? 0x80u : 0u);
+        }
+        qres[j] = (uint8_t)r;
+        my_nodes += r & 0x3fu;
+        my_list += (r >> 7) & 1u;
+      }
+      uint32_t nnext_raw, nlist_add;
+      uint32_t qpos = block_scan_u32<NT>(my_nodes, nnext_raw, scan_sm);
+      uint32_t lpos = nlist + block_scan_u32<NT>(my_list, nlist_add, scan_sm);
+      for(int j = tid; j < ncur; j += NT) {
+        const uint32_t r = qres[j];
+        if(r == 0) continue;
+        const int nd = qc[j];
+        if(r & 0x3fu) {
+          const NodeRec rec = t.noderec[nd];
+          uint32_t node_mask = ((1u << rec.nchild) - 1u) & ~rec.leafmask;
+          while(node_mask) {
+            const int b = __ffs(node_mask) - 1;
+            node_mask &= node_mask - 1;
+            // node children of a node have consecutive node indices (level order)
+            if(qpos < SW_QCAP) qn[qpos] = rec.first_child_node + __popc(~rec.leafmask & ((1u << b) - 1u));
+            ++qpos;
+          }
+        }
+        if(r & 0x80u) {
+          if(MODE == 1) out[lpos] = nd;
+          ++lpos;
         }
       }
-      if(r & 0x80u) {
-        if(MODE == 1) out[lpos] = nd;
-        ++lpos;
+      nlist += nlist_add;
+      uint32_t nnext = nnext_raw;
+      if(nnext > SW_QCAP) {
+        if(tid == 0) atomicOr(status, (uint32_t)ERR_QUEUE_OVERFLOW);
+        nnext = SW_QCAP;
       }
+      __syncthreads();
+      ncur = (int)nnext;
+      cur ^= 1;
     }
-    nlist += total >> 16;
-    uint32_t nnext = nnext_raw;
-    if(nnext > SW_QCAP) {
-      if(tid == 0) atomicOr(status, (uint32_t)ERR_QUEUE_OVERFLOW);
-      nnext = SW_QCAP;
-    }
-    __syncthreads();
-    ncur = (int)nnext;
-    cur ^= 1;
+    if(MODE == 0 && tid == 0) sr.sl_off[sidx] = nlist;
   }
-  if(MODE == 0 && tid == 0) sr.sl_off[sidx] = nlist;
 }
 
 __global__ void __launch_bounds__(256) k_super_compact(const uint32_t * __restrict__ at, const uint32_t * __restrict__ ex, int64_t n,
@@ -322,7 +335,10 @@ static void build_super_lists(System & s) {
   FSPH_LAUNCH((k_block_pack<0>), (nsuper + 127) / 128, 128, s.stream, s.tree, sr, first_wc, bcnt, nullptr);
   exclusive_scan_u32(s, bcnt, bcnt, nsuper, nullptr);
   // node lists
-  FSPH_LAUNCH((k_super_walk<D, 0>), nsuper, 64, s.stream, s.tree, s.cols(), sr, status);
+  const int sw_grid = (int)std::min<uint32_t>(nsuper, 148 * 6);
+  s.b_super_queue.reserve((size_t)sw_grid * (2 * SW_QCAP + SW_QCAP / 4) * 4);
+  int32_t * gq = s.b_super_queue.as<int32_t>();
+  FSPH_LAUNCH((k_super_walk<D, 0>), sw_grid, SW_NT, s.stream, s.tree, s.cols(), sr, first_wc, gq, status);
   exclusive_scan_u64(s, sr.sl_off, sr.sl_off, nsuper, nullptr);
   uint64_t tot = 0;
   uint32_t st = 0, nblk = 0;
@@ -330,7 +346,7 @@ static void build_super_lists(System & s) {
   FSPH_CUDA_OK(cudaMemcpyAsync(&st, status, 4, cudaMemcpyDeviceToHost, s.stream));
   FSPH_CUDA_OK(cudaMemcpyAsync(&nblk, bcnt + nsuper, 4, cudaMemcpyDeviceToHost, s.stream));
   FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
-  if(st & ERR_QUEUE_OVERFLOW) throw std::runtime_error("neighbour search: node frontier of a super cell exceeds the shared-memory queue");
+  if(st & ERR_QUEUE_OVERFLOW) throw std::runtime_error("neighbour search: the node frontier of a super cell exceeds 16384 nodes per level");
   if(nblk == 0) throw std::runtime_error("no blocks");
   s.b_sl_nodes.reserve((size_t)std::max<uint64_t>(tot, 1) * 4);
   sr.sl_nodes = s.b_sl_nodes.as<int32_t>();
@@ -338,7 +354,7 @@ static void build_super_lists(System & s) {
   sr.blk_wc = s.b_blk_wc.as<int32_t>();
   sr.nblk = (int)nblk;
   FSPH_LAUNCH((k_block_pack<1>), (nsuper + 127) / 128, 128, s.stream, s.tree, sr, first_wc, nullptr, bcnt);
-  FSPH_LAUNCH((k_super_walk<D, 1>), nsuper, 64, s.stream, s.tree, s.cols(), sr, status);
+  FSPH_LAUNCH((k_super_walk<D, 1>), sw_grid, SW_NT, s.stream, s.tree, s.cols(), sr, first_wc, gq, status);
   FSPH_CUDA_OK(cudaGetLastError());
 }
 

@@ -32,7 +32,9 @@ namespace fsph {
 constexpr double TINY = 1e10 * DBL_MIN;  // kernels.h:64, viscosity.h:36
 constexpr double PI = 3.14159265358979323846;
 
-enum SweepOp { OP_DENSITY = 0, OP_ACC = 1, OP_DUDT = 2, OP_DEDT = 3, OP_VSIG = 5, OP_ACCV = 6 };
+enum SweepOp { OP_DENSITY = 0, OP_ACC = 1, OP_DUDT = 2, OP_DEDT = 3, OP_VSIG = 5, OP_ACCV = 6, OP_ALPHA = 7, OP_REPULSION = 8 };
+// VISC (template flag): 0 = constant artificial viscosity, 1 = Cullen-Dehnen (per-body alpha; the density sweep also
+// accumulates the velocity divergence)
 // cache mode of a sweep.  density: 1 = write A.  acceleration: 1 = read A, write Pi.  energy: 1 = read A and Pi,
 // 2 = read A only (Pi is stale, e.g. second pressure pass).  0 = no cache.
 enum CacheMode { CM_NONE = 0, CM_FULL = 1, CM_A_ONLY = 2 };
@@ -191,7 +193,7 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_SUPER_GAUSSIAN> {
 };
 // sinc kernel (kernels.h:626-699): index n and its normalisation (set_sinc_kernel_normalization, :67-77) are run-time
 // parameters; they live in constant memory, refreshed by sweep() before the launches
-__constant__ double c_sinc[2];  // {n, sigma(n, D)}
+static __constant__ double c_sinc[2];  // {n, sigma(n, D)}
 template<int D> struct SphKernel<D, FSPH_KERNEL_SINC> {
   static __device__ __forceinline__ double Wi(double r, double ih) {
     double q = fabs(r * ih);
@@ -223,20 +225,22 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_SINC> {
 
 // ---- candidate tile columns per sweep ---------------------------------------------------------------------
 // which neighbour fields a sweep gathers into shared memory; positions come first, the rest in a fixed order
-template<int D, int OP, int CM> struct TileCols {
+template<int D, int OP, int CM, int VISC> struct TileCols {
   static constexpr bool ACCX = OP == OP_ACC || OP == OP_ACCV;
   static constexpr bool ENER = OP == OP_DUDT || OP == OP_DEDT;
-  static constexpr bool VISC = (ACCX) || (ENER && CM != CM_FULL);        // the sweep evaluates Pi itself
-  static constexpr bool GRAD = (ACCX || ENER) && CM == CM_NONE;          // the sweep evaluates the kernel gradient itself
-  static constexpr bool hasH = OP == OP_DENSITY || VISC || GRAD;
-  static constexpr bool hasM = OP == OP_DENSITY || GRAD;
-  static constexpr bool hasRHO = VISC;
+  static constexpr bool PIV = (ACCX) || (ENER && CM != CM_FULL);         // the sweep evaluates Pi itself
+  static constexpr bool GRAD = ((ACCX || ENER) && CM == CM_NONE) || OP == OP_ALPHA;   // ... the kernel gradient itself
+  static constexpr bool hasH = OP == OP_DENSITY || PIV || GRAD || OP == OP_REPULSION;
+  static constexpr bool hasM = OP == OP_DENSITY || GRAD || OP == OP_REPULSION;
+  static constexpr bool hasRHO = PIV;
   static constexpr bool hasPR = ACCX || OP == OP_DEDT;
-  static constexpr bool hasCS = VISC || OP == OP_VSIG;
-  static constexpr bool hasVH = VISC;
-  static constexpr bool hasV = ENER || OP == OP_VSIG;
+  static constexpr bool hasCS = PIV || OP == OP_VSIG || OP == OP_ALPHA;
+  static constexpr bool hasVH = PIV;
+  static constexpr bool hasV = ENER || OP == OP_VSIG || OP == OP_ALPHA;
   static constexpr bool hasCSO = OP == OP_VSIG || OP == OP_ACCV;
-  static constexpr bool hasIDX = OP == OP_VSIG || OP == OP_ACCV;
+  static constexpr bool hasAL = PIV && VISC == 1;                        // alpha_b of the Cullen-Dehnen viscosity
+  static constexpr bool hasDV = OP == OP_ALPHA;                          // div v of the neighbour
+  static constexpr bool hasIDX = OP == OP_VSIG || OP == OP_ACCV || OP == OP_REPULSION;
   static constexpr int iH = D;
   static constexpr int iM = iH + (hasH ? 1 : 0);
   static constexpr int iRHO = iM + (hasM ? 1 : 0);
@@ -245,7 +249,9 @@ template<int D, int OP, int CM> struct TileCols {
   static constexpr int iVH = iCS + (hasCS ? 1 : 0);
   static constexpr int iV = iVH + (hasVH ? D : 0);
   static constexpr int iCSO = iV + (hasV ? D : 0);
-  static constexpr int NF = iCSO + (hasCSO ? 1 : 0);
+  static constexpr int iAL = iCSO + (hasCSO ? 1 : 0);
+  static constexpr int iDV = iAL + (hasAL ? 1 : 0);
+  static constexpr int NF = iDV + (hasDV ? 1 : 0);
   static __device__ __forceinline__ int col(int j) {
     if(j < D) return F_POS + j;
     if(hasH && j == iH) return F_H;
@@ -255,7 +261,9 @@ template<int D, int OP, int CM> struct TileCols {
     if(hasCS && j == iCS) return F_CS;
     if(hasVH && j >= iVH && j < iVH + D) return F_VELH + (j - iVH);
     if(hasV && j >= iV && j < iV + D) return F_VEL + (j - iV);
-    return F_CSOLD;
+    if(hasCSO && j == iCSO) return F_CSOLD;
+    if(hasAL && j == iAL) return F_ALPHA;
+    return F_DIVV;
   }
   static constexpr size_t smem_bytes() { return (size_t)NF * NL_TILE * 8 + (hasIDX ? NL_TILE * 4 : 0); }
 };
@@ -263,30 +271,35 @@ template<int D, int OP, int CM> struct TileCols {
 // state of the particle a thread owns + its accumulators
 template<int D> struct Own {
   double xa[D], va[D], vha[D];
-  double ha, rho_a, cs_a, Prho2_a;
+  double ha, rho_a, cs_a, Prho2_a, alpha_a;
   double acc0, acc1, accv[D], vsig;
+  double gv[D * D];   // compute_alpha only: velocity-gradient sums
   int ia;
 };
 
 // Pi_ab of the constant artificial viscosity (viscosity.h:81-137): mu = h dot / (r^2 + eps h^2 + TINY);
 // Pi = (-alpha c + beta mu) mu / rho -- one division for both
-__device__ __forceinline__ double visc_pi(const PhysParams & pp, double dotvr, double dist2, double hab, double rho_ab, double c_ab) {
+// Cullen-Dehnen (viscosity.h:150-157): Pi = -alpha_ab (c - 2 mu) mu / rho with the bodies' own alphas
+template<int VISC>
+__device__ __forceinline__ double visc_pi(const PhysParams & pp, double dotvr, double dist2, double hab, double rho_ab, double c_ab,
+  double alpha_ab) {
   double Pi = 0.0;
   if(dotvr < 0.0) {
     const double den = dist2 + pp.epsilon * hab * hab + TINY;
     const double inv = rcp_nr(den * rho_ab);
     const double mu = hab * dotvr * (inv * rho_ab);
-    Pi = (-pp.alpha * c_ab + pp.beta * mu) * mu * (inv * den);
+    if(VISC == 1) Pi = -alpha_ab * (c_ab - 2.0 * mu) * mu * (inv * den);
+    else Pi = (-pp.alpha * c_ab + pp.beta * mu) * mu * (inv * den);
   }
   return Pi;
 }
 
 // one neighbour pair (a, candidate ci of the current tile); `valid` = false makes it a no-op (padding slot of the
 // two-pairs-per-iteration loop).  cA / cP: the pair's cache slots (read or written according to CM).
-template<int D, int K, int OP, int CM>
+template<int D, int K, int OP, int CM, int VISC>
 __device__ __forceinline__ void pair_body(Own<D> & o, const double (*tile)[NL_TILE], const int32_t * tidx, const PhysParams & pp,
   const int ci, const bool valid, double & cA, double & cP) {
-  using TC = TileCols<D, OP, CM>;
+  using TC = TileCols<D, OP, CM, VISC>;
   double rab[D];
   double dist2 = 0.0;
 #pragma unroll
@@ -304,7 +317,54 @@ __device__ __forceinline__ void pair_body(Own<D> & o, const double (*tile)[NL_TI
     const double mb = tile[TC::iM][ci];
     const double t = mb * SphKernel<D, K>::Wi(r, ih);
     o.acc0 += valid ? t : 0.0;
-    if(CM == CM_FULL) cA = (dist2 == 0.0 || !valid) ? 0.0 : mb * SphKernel<D, K>::Fi(r, ih, ir);
+    if(CM == CM_FULL || VISC == 1) {
+      const double A = (dist2 == 0.0 || !valid) ? 0.0 : mb * SphKernel<D, K>::Fi(r, ih, ir);
+      if(CM == CM_FULL) cA = A;
+      if(VISC == 1) {
+        // compute_divv (default_physics.h:273-300): sum_b m_b grad W_ab, contracted with v_a at the end
+#pragma unroll
+        for(int d = 0; d < D; ++d) o.accv[d] += A * rab[d];
+      }
+    }
+  }
+  else if(OP == OP_ALPHA) {
+    // viscosity::compute_alpha (viscosity.h:310-363) with compute_xi (:193-262): signal velocity, R_a and the
+    // velocity-gradient matrix
+    const double hab = .5 * (o.ha + tile[TC::iH][ci]);
+    const double ir = rsqrt_nr(fmax(dist2, 1e-280));
+    const double r = D == 1 ? fabs(rab[0]) : dist2 * ir;
+    const double ih = rcp_nr(hab);
+    const double mb = valid ? tile[TC::iM][ci] : 0.0;
+    const double Wab = SphKernel<D, K>::Wi(r, ih);
+    const double Fab = dist2 == 0.0 ? 0.0 : SphKernel<D, K>::Fi(r, ih, ir);
+    const double dvb = tile[TC::iDV][ci];
+    const double sg = dvb > 0.0 ? 1.0 : (dvb < 0.0 ? -1.0 : dvb);   // signnum_c
+    o.acc0 += sg * mb * Wab;
+    double vab[D], vr = 0.0;
+#pragma unroll
+    for(int d = 0; d < D; ++d) {
+      vab[d] = o.va[d] - tile[TC::iV + d][ci];
+      vr += vab[d] * rab[d];
+    }
+#pragma unroll
+    for(int i = 0; i < D; ++i)
+#pragma unroll
+      for(int j = 0; j < D; ++j) o.gv[D * i + j] += mb * (-vab[i]) * (rab[j] * Fab);
+    const double cab = fmax(o.cs_a, tile[TC::iCS][ci]);
+    vr = vr * ir;
+    const double mn = (0.0 < vr) ? 0.0 : vr;
+    const double val = cab - mn;
+    if(valid && dist2 != 0.0 && o.vsig < val) o.vsig = val;   // the body itself contributes NaN in the reference: dropped
+  }
+  else if(OP == OP_REPULSION) {
+    // add_short_range_repulsion (default_physics.h:718-754): the body itself is skipped by id
+    const double hab = .5 * (o.ha + tile[TC::iH][ci]);
+    const double r = D == 1 ? fabs(rab[0]) : sqrt(dist2);
+    if(valid && tidx[ci] != o.ia && !(r > hab * pp.repulsion_radius)) {
+      const double f = tile[TC::iM][ci] / (r * r * r);
+#pragma unroll
+      for(int d = 0; d < D; ++d) o.accv[d] += f * rab[d];
+    }
   }
   else if(OP == OP_VSIG) {
     // compute_signalspeed: b contributes its new soundspeed iff it was processed before a, i.e. iff its
@@ -331,12 +391,13 @@ __device__ __forceinline__ void pair_body(Own<D> & o, const double (*tile)[NL_TI
       A = mb * SphKernel<D, K>::Fi(r, rcp_nr(hab), ir);
     }
     else A = valid ? cA : 0.0;
-    if(TC::VISC) {
+    if(TC::PIV) {
       const double hab = .5 * (o.ha + tile[TC::iH][ci]);
       double dotvr = 0.0;
 #pragma unroll
       for(int d = 0; d < D; ++d) dotvr += (o.vha[d] - tile[TC::iVH + d][ci]) * rab[d];
-      Pi = visc_pi(pp, dotvr, dist2, hab, .5 * (o.rho_a + tile[TC::iRHO][ci]), .5 * (o.cs_a + tile[TC::iCS][ci]));
+      const double alpha_ab = VISC == 1 ? .5 * (o.alpha_a + tile[TC::hasAL ? TC::iAL : 0][ci]) : 0.0;
+      Pi = visc_pi<VISC>(pp, dotvr, dist2, hab, .5 * (o.rho_a + tile[TC::iRHO][ci]), .5 * (o.cs_a + tile[TC::iCS][ci]), alpha_ab);
       if(TC::ACCX && CM == CM_FULL) cP = Pi;
     }
     else Pi = cP;
@@ -382,22 +443,26 @@ __device__ __forceinline__ void pair_body(Own<D> & o, const double (*tile)[NL_TI
 }
 
 // state of the particle `ia` of a sweep (the columns op OP needs), accumulators cleared
-template<int D, int OP>
+template<int D, int OP, int VISC>
 __device__ __forceinline__ void load_own(Own<D> & o, const Cols & c, const int ia, const bool active) {
   o.ia = ia;
-  o.ha = o.rho_a = o.cs_a = o.Prho2_a = 0.0;
+  o.ha = o.rho_a = o.cs_a = o.Prho2_a = o.alpha_a = 0.0;
   o.acc0 = o.acc1 = o.vsig = 0.0;
 #pragma unroll
   for(int d = 0; d < D; ++d) { o.xa[d] = 0; o.va[d] = 0; o.vha[d] = 0; o.accv[d] = 0; }
+#pragma unroll
+  for(int d = 0; d < D * D; ++d) o.gv[d] = 0;
   if(active) {
 #pragma unroll
     for(int d = 0; d < D; ++d) o.xa[d] = c.f[F_POS + d][ia];
     o.ha = c.f[F_H][ia];
-    if(OP == OP_VSIG || OP == OP_DUDT || OP == OP_DEDT) {
+    if(OP == OP_VSIG || OP == OP_DUDT || OP == OP_DEDT || OP == OP_ALPHA || (OP == OP_DENSITY && VISC == 1)) {
 #pragma unroll
       for(int d = 0; d < D; ++d) o.va[d] = c.f[F_VEL + d][ia];
     }
-    if(OP == OP_VSIG) o.cs_a = c.f[F_CS][ia];
+    if(OP == OP_VSIG || OP == OP_ALPHA) o.cs_a = c.f[F_CS][ia];
+    if(OP == OP_ALPHA) o.rho_a = c.f[F_RHO][ia];
+    if(VISC == 1 && (OP == OP_ACC || OP == OP_DUDT || OP == OP_DEDT || OP == OP_ACCV)) o.alpha_a = c.f[F_ALPHA][ia];
     if(OP == OP_ACC || OP == OP_DUDT || OP == OP_DEDT || OP == OP_ACCV) {
       o.rho_a = c.f[F_RHO][ia];
       o.cs_a = c.f[F_CS][ia];
@@ -409,7 +474,7 @@ __device__ __forceinline__ void load_own(Own<D> & o, const Cols & c, const int i
 }
 
 // the per-particle tail of each functor: writes the results of the sweep
-template<int D, int OP>
+template<int D, int OP, int VISC>
 __device__ __forceinline__ void store_own(const Own<D> & o, const Cols & c, const PhysParams & pp, uint32_t * __restrict__ status) {
   const int ia = o.ia;
   if(OP == OP_DENSITY) {
@@ -427,11 +492,57 @@ __device__ __forceinline__ void store_own(const Own<D> & o, const Cols & c, cons
       c.f[F_U][ia] = u;
     }
     else u = c.f[F_U][ia];
-    double Pn, csn;
-    eos_p_cs(pp, rho, u, pp.eos == FSPH_EOS_POLYTROPIC ? c.f[F_ADIA][ia] : 0.0, Pn, csn);
+    double Pn = c.f[F_P][ia], csn = c.f[F_CS][ia];
+    eos_p_cs(pp, rho, u, (pp.eos == FSPH_EOS_POLYTROPIC || pp.eos == FSPH_EOS_PPT) ? c.f[F_ADIA][ia] : 0.0,
+      pp.eos == FSPH_EOS_WD ? c.f[F_YE][ia] : 0.0, Pn, csn);
     c.f[F_P][ia] = Pn;
     c.f[F_CSOLD][ia] = c.f[F_CS][ia];
     c.f[F_CS][ia] = csn;
+    if(VISC == 1) {
+      // compute_divv (default_physics.h:273-300): div v = (v_a . sum_b m_b grad W_ab) / rho_a and its rate of change
+      double dv = 0.0;
+#pragma unroll
+      for(int d = 0; d < D; ++d) dv += o.va[d] * o.accv[d];
+      dv = dv / rho;
+      c.f[F_DDIVVDT][ia] = (dv - c.f[F_DIVV][ia]) / pp.dt;
+      c.f[F_DIVV][ia] = dv;
+    }
+  }
+  else if(OP == OP_ALPHA) {
+    const double divV = c.f[F_DIVV][ia], h_a = o.ha, alpha_a = c.f[F_ALPHA][ia];
+    const double R_a = o.acc0 / o.rho_a;
+    double g[D * D];
+#pragma unroll
+    for(int k = 0; k < D * D; ++k) g[k] = o.gv[k] / o.rho_a;
+    c.f[F_GRADV][ia] = g[0];
+    // traceless symmetric part of the velocity gradient
+    double traceSS = 0.0;
+#pragma unroll
+    for(int i = 0; i < D; ++i)
+#pragma unroll
+      for(int j = 0; j < D; ++j) {
+        double sym = 0.5 * (g[D * i + j] + g[D * j + i]);
+        if(i == j) sym -= divV / D;
+        traceSS += sym * sym;
+      }
+    c.f[F_TRACESS][ia] = traceSS;
+    const double omr = 1.0 - R_a, q4 = omr * omr * omr * omr, t2 = 2.0 * q4 * divV, res = t2 * t2;
+    const double xi = res < 1e-16 ? 0.0 : res / (res + traceSS);
+    const double trig = fmax(-c.f[F_DDIVVDT][ia], 0.0);
+    c.f[F_XI][ia] = xi;
+    c.f[F_TRIGGER][ia] = trig;
+    const double Atrig = xi * trig, vsig = o.vsig, vh = vsig / h_a;
+    const double alpha_loc = pp.alpha_max * Atrig / (pp.visc_delta * (vh * vh) + Atrig);
+    if(alpha_a <= alpha_loc) c.f[F_ALPHA][ia] = alpha_loc;
+    else {
+      const double decayt = h_a / (2.0 * pp.visc_l * vsig);
+      const double dalphadt = (alpha_a - alpha_loc) / decayt;
+      c.f[F_ALPHA][ia] = alpha_a * exp(-dalphadt * pp.dt);
+    }
+  }
+  else if(OP == OP_REPULSION) {
+#pragma unroll
+    for(int d = 0; d < D; ++d) c.f[F_ACC + d][ia] = c.f[F_ACC + d][ia] + o.accv[d] * pp.repulsion_gamma;
   }
   else if(OP == OP_VSIG) c.f[F_VSIG][ia] = o.vsig;
   else if(OP == OP_ACC || OP == OP_ACCV) {
@@ -452,15 +563,15 @@ __device__ __forceinline__ void store_own(const Own<D> & o, const Cols & c, cons
   }
 }
 
-template<int OP> struct SweepOcc { static constexpr int MINB = (OP == OP_DENSITY || OP == OP_VSIG) ? 4 : 3; };
+template<int OP> struct SweepOcc { static constexpr int MINB = (OP == OP_DENSITY || OP == OP_VSIG || OP == OP_REPULSION) ? 4 : 3; };
 
-template<int D, int K, int OP, int CM>
+template<int D, int K, int OP, int CM, int VISC>
 __global__ void __launch_bounds__(BLK_BODIES, SweepOcc<OP>::MINB) k_sweep(Cols c, Search sr, PhysParams pp, uint32_t * __restrict__ status,
   double * __restrict__ pair_a, double * __restrict__ pair_pi) {
-  using TC = TileCols<D, OP, CM>;
+  using TC = TileCols<D, OP, CM, VISC>;
   constexpr int NF = TC::NF;
   constexpr int NT = BLK_BODIES;
-  constexpr bool A_RD = (OP != OP_DENSITY && OP != OP_VSIG) && CM != CM_NONE;
+  constexpr bool A_RD = (OP == OP_ACC || OP == OP_ACCV || OP == OP_DUDT || OP == OP_DEDT) && CM != CM_NONE;
   constexpr bool A_WR = OP == OP_DENSITY && CM == CM_FULL;
   constexpr bool P_RD = (OP == OP_DUDT || OP == OP_DEDT) && CM == CM_FULL;
   constexpr bool P_WR = (OP == OP_ACC || OP == OP_ACCV) && CM == CM_FULL;
@@ -475,7 +586,7 @@ __global__ void __launch_bounds__(BLK_BODIES, SweepOcc<OP>::MINB) k_sweep(Cols c
   const int nwarp_act = (PB + 31) >> 5;
 
   Own<D> o;
-  load_own<D, OP>(o, c, body0 + tid, active);
+  load_own<D, OP, VISC>(o, c, body0 + tid, active);
 
   const int ntile = (C + NL_TILE - 1) / NL_TILE;
   for(int ti = 0; ti < ntile; ++ti) {
@@ -527,16 +638,16 @@ __global__ void __launch_bounds__(BLK_BODIES, SweepOcc<OP>::MINB) k_sweep(Cols c
       if(P_RD) { p0 = v0 ? pair_pi[slot0] : 0.0; p1 = v1 ? pair_pi[slot1] : 0.0; }
       if(j + 2 < cmax) e0 = rows[(3 + j) * 32];
       if(j + 3 < cmax) e1 = rows[(4 + j) * 32];
-      pair_body<D, K, OP, CM>(o, tile, tidx, pp, ci0, v0, a0, p0);
-      pair_body<D, K, OP, CM>(o, tile, tidx, pp, ci1, v1, a1, p1);
+      pair_body<D, K, OP, CM, VISC>(o, tile, tidx, pp, ci0, v0, a0, p0);
+      pair_body<D, K, OP, CM, VISC>(o, tile, tidx, pp, ci1, v1, a1, p1);
       if(A_WR) { if(v0) pair_a[slot0] = a0; if(v1) pair_a[slot1] = a1; }
       if(P_WR) { if(v0) pair_pi[slot0] = p0; if(v1) pair_pi[slot1] = p1; }
     }
   }
-  if(active) store_own<D, OP>(o, c, pp, status);
+  if(active) store_own<D, OP, VISC>(o, c, pp, status);
 }
 
-__global__ void __launch_bounds__(256) k_prho2(Cols c, int64_t n) {
+static __global__ void __launch_bounds__(256) k_prho2(Cols c, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(i < n) {
     const double rho = c.f[F_RHO][i];
@@ -544,18 +655,25 @@ __global__ void __launch_bounds__(256) k_prho2(Cols c, int64_t n) {
   }
 }
 
-__global__ void __launch_bounds__(256) k_fill(double * p, int64_t n, double v) {
+static __global__ void __launch_bounds__(256) k_fill(double * p, int64_t n, double v) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(i < n) p[i] = v;
 }
 
-template<int D, int K, int OP, int CM>
+template<int D, int K, int OP, int CM, int VISC = 0>
 static void launch_sweep(System & s) {
   const Search & sr = s.search;
-  if(OP != OP_DENSITY && OP != OP_VSIG) FSPH_LAUNCH(k_prho2, (unsigned)((s.n + 255) / 256), 256, s.stream, s.cols(), s.n);
+  if(OP == OP_ACC || OP == OP_ACCV || OP == OP_DUDT || OP == OP_DEDT)
+    FSPH_LAUNCH(k_prho2, (unsigned)((s.n + 255) / 256), 256, s.stream, s.cols(), s.n);
   uint32_t * st = s.b_status.as<uint32_t>();
-  FSPH_LAUNCH_SMEM((k_sweep<D, K, OP, CM>), sr.nblk, BLK_BODIES, (TileCols<D, OP, CM>::smem_bytes()), s.stream, s.cols(), sr, s.phys(), st,
-    s.b_pair_a.as<double>(), s.b_pair_pi.as<double>());
+  FSPH_LAUNCH_SMEM((k_sweep<D, K, OP, CM, VISC>), sr.nblk, BLK_BODIES, (TileCols<D, OP, CM, VISC>::smem_bytes()), s.stream, s.cols(), sr,
+    s.phys(), st, s.b_pair_a.as<double>(), s.b_pair_pi.as<double>());
+}
+// the Cullen-Dehnen variants are instantiated for every kernel as well: the viscosity is a run-time parameter
+template<int D, int K, int OP, int CM>
+static void launch_sweep_v(System & s) {
+  if(s.par.sph_viscosity == FSPH_VISC_CULLEN) launch_sweep<D, K, OP, CM, 1>(s);
+  else launch_sweep<D, K, OP, CM, 0>(s);
 }
 
 // Pair caches: decide once per neighbour structure whether they fit (two doubles per list slot next to everything else
@@ -603,31 +721,39 @@ static void sweep_dk(System & s, int op) {
     case 100:   // fsph_step: density / P / cs only (the signal speed rides on the acceleration sweep)
       s.pair_pi_valid = false;   // rho, cs change
       if(cache && !a_ok) {
-        launch_sweep<D, K, OP_DENSITY, CM_FULL>(s);
+        launch_sweep_v<D, K, OP_DENSITY, CM_FULL>(s);
         s.pair_a_epoch = s.search_epoch;
       }
-      else launch_sweep<D, K, OP_DENSITY, CM_NONE>(s);
+      else launch_sweep_v<D, K, OP_DENSITY, CM_NONE>(s);
       if(op != 100) launch_sweep<D, K, OP_VSIG, CM_NONE>(s);
       break;
     case FSPH_SWEEP_ACCELERATION:
-      if(a_ok) { launch_sweep<D, K, OP_ACC, CM_FULL>(s); s.pair_pi_valid = true; }
-      else launch_sweep<D, K, OP_ACC, CM_NONE>(s);
+      if(a_ok) { launch_sweep_v<D, K, OP_ACC, CM_FULL>(s); s.pair_pi_valid = true; }
+      else launch_sweep_v<D, K, OP_ACC, CM_NONE>(s);
       break;
     case 101:
-      if(a_ok) { launch_sweep<D, K, OP_ACCV, CM_FULL>(s); s.pair_pi_valid = true; }
-      else launch_sweep<D, K, OP_ACCV, CM_NONE>(s);
+      if(a_ok) { launch_sweep_v<D, K, OP_ACCV, CM_FULL>(s); s.pair_pi_valid = true; }
+      else launch_sweep_v<D, K, OP_ACCV, CM_NONE>(s);
       break;
     case FSPH_SWEEP_DUDT:
       if(s.iteration < s.par.relaxation_steps)
         FSPH_LAUNCH(k_fill, (unsigned)((s.n + 255) / 256), 256, s.stream, s.col[F_DUDT].as<double>(), s.n, 0.0);
-      else if(a_ok && s.pair_pi_valid) launch_sweep<D, K, OP_DUDT, CM_FULL>(s);
-      else if(a_ok) launch_sweep<D, K, OP_DUDT, CM_A_ONLY>(s);
-      else launch_sweep<D, K, OP_DUDT, CM_NONE>(s);
+      else if(a_ok && s.pair_pi_valid) launch_sweep_v<D, K, OP_DUDT, CM_FULL>(s);
+      else if(a_ok) launch_sweep_v<D, K, OP_DUDT, CM_A_ONLY>(s);
+      else launch_sweep_v<D, K, OP_DUDT, CM_NONE>(s);
       break;
     case FSPH_SWEEP_DEDT:
-      if(a_ok && s.pair_pi_valid) launch_sweep<D, K, OP_DEDT, CM_FULL>(s);
-      else if(a_ok) launch_sweep<D, K, OP_DEDT, CM_A_ONLY>(s);
-      else launch_sweep<D, K, OP_DEDT, CM_NONE>(s);
+      if(a_ok && s.pair_pi_valid) launch_sweep_v<D, K, OP_DEDT, CM_FULL>(s);
+      else if(a_ok) launch_sweep_v<D, K, OP_DEDT, CM_A_ONLY>(s);
+      else launch_sweep_v<D, K, OP_DEDT, CM_NONE>(s);
+      break;
+    case FSPH_SWEEP_COMPUTE_ALPHA:
+      if(s.par.sph_viscosity != FSPH_VISC_CULLEN) throw std::runtime_error("compute_alpha needs sph_viscosity = cullen (its columns are not allocated otherwise)");
+      s.pair_pi_valid = false;   // alpha changes
+      launch_sweep<D, K, OP_ALPHA, CM_NONE>(s);
+      break;
+    case FSPH_SWEEP_SHORT_RANGE_REPULSION:
+      launch_sweep<D, FSPH_KERNEL_WENDLAND_C4, OP_REPULSION, CM_NONE>(s);   // no kernel function in this sweep
       break;
     default: throw std::runtime_error("unknown sweep op");
   }
@@ -659,14 +785,27 @@ static void sweep_d(System & s, int op) {
   }
 }
 
+// This file is compiled once per dimension (-DFSPH_SWEEPS_DIM=1|2|3, flecsph_b200/build.py): every (kernel, sweep, cache
+// mode, viscosity) combination is a separate kernel, and the three translation units build in parallel.
+#ifndef FSPH_SWEEPS_DIM
+#error "compile with -DFSPH_SWEEPS_DIM=1, 2 or 3"
+#endif
+#if FSPH_SWEEPS_DIM == 1
+void sweep_1d(System & s, int op) { sweep_d<1>(s, op); }
+#elif FSPH_SWEEPS_DIM == 2
+void sweep_2d(System & s, int op) { sweep_d<2>(s, op); }
+#else
+void sweep_1d(System & s, int op);
+void sweep_2d(System & s, int op);
 void sweep(System & s, int op) {
   if(!s.tree_valid) throw std::runtime_error("sweep before update_iteration");
   if(!s.search_valid) neighbor_search(s);
   if(op == FSPH_SWEEP_NEIGHBORS_ONLY) return;
-  if(s.dim == 1) sweep_d<1>(s, op);
-  else if(s.dim == 2) sweep_d<2>(s, op);
+  if(s.dim == 1) sweep_1d(s, op);
+  else if(s.dim == 2) sweep_2d(s, op);
   else sweep_d<3>(s, op);
   FSPH_CUDA_OK(cudaGetLastError());
 }
+#endif
 
 }  // namespace fsph

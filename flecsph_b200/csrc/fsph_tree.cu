@@ -176,6 +176,7 @@ void live_columns(System & s, std::vector<std::pair<DevBuf *, int>> & out) {
   for(int f = 0; f < NF64; ++f) {
     if(f < F_MASS && (f % 3) >= s.dim) continue;  // unused vector components
     if(f == F_PRHO2) continue;                      // derived column
+    if(!s.col_used[f]) continue;                    // optional column this physics does not allocate
     if(s.skip_dead_columns && s.dead_col[f]) continue;  // fsph_step: rewritten before it is next read
     out.emplace_back(&s.col[f], 8);
   }

@@ -137,6 +137,15 @@ public:
     p.periodic_boundary_x = periodic_boundary_x;
     p.periodic_boundary_y = periodic_boundary_y;
     p.periodic_boundary_z = periodic_boundary_z;
+    p.sph_viscosity_alpha_max = sph_viscosity_alpha_max;
+    p.sph_viscosity_l = sph_viscosity_l;
+    p.sph_viscosity_delta = sph_viscosity_delta;
+    p.poly_gamma2 = poly_gamma2;
+    p.ppt_density_thr = ppt_density_thr;
+    p.relaxation_beta = relaxation_beta;
+    p.relaxation_gamma = relaxation_gamma;
+    p.relaxation_repulsion_radius = relaxation_repulsion_radius;
+    p.relaxation_repulsion_gamma = relaxation_repulsion_gamma;
     int rank = 0;
     MPI_Comm_rank(MPI_COMM_WORLD, &rank);
     const char * dev = std::getenv("FSPH_DEVICE");
@@ -221,6 +230,8 @@ public:
       else if(f == &physics::compute_acceleration) op = FSPH_SWEEP_ACCELERATION;
       else if(f == &physics::compute_dudt) op = FSPH_SWEEP_DUDT;
       else if(f == &physics::compute_dedt) op = FSPH_SWEEP_DEDT;
+      else if(f == &viscosity::compute_alpha) op = FSPH_SWEEP_COMPUTE_ALPHA;
+      else if(f == &physics::add_short_range_repulsion) op = FSPH_SWEEP_SHORT_RANGE_REPULSION;
     }
     if(op < 0)
       fsph_host::fail("apply_in_smoothinglength: this functor has no device implementation (no CPU fallback)");
@@ -247,6 +258,10 @@ public:
       else if(f == &physics::compute_dt) op = FSPH_APPLY_COMPUTE_DT;
       else if(f == &physics::check_nans) op = FSPH_APPLY_CHECK_NANS;
       else if(f == &physics::check_negativity) op = FSPH_APPLY_CHECK_NEGATIVITY;
+      else if(f == &viscosity::initialize_alpha) op = FSPH_APPLY_INITIALIZE_ALPHA;
+      else if(f == &physics::add_drag_acceleration) op = FSPH_APPLY_ADD_DRAG_ACCELERATION;
+      else if(f == &physics::add_drag_dedt) op = FSPH_APPLY_ADD_DRAG_DEDT;
+      else if(f == &physics::add_drag_dudt) op = FSPH_APPLY_ADD_DRAG_DUDT;
     }
     if(op < 0)
       fsph_host::fail("apply_all: this functor has no device implementation (no CPU fallback)");
@@ -423,6 +438,11 @@ private:
     sca(FSPH_COL_VSIG, [](body & b) { return b.getSignalspeed(); });
     sca(FSPH_COL_GPOT, [](body & b) { return b.getGPotential(); });
     sca(FSPH_COL_ADIABATIC, [](body & b) { return b.getAdiabatic(); });
+    if(param::eos_type == param::eos_wd) sca(FSPH_COL_YE, [](body & b) { return b.getElectronfraction(); });
+    if(param::sph_viscosity == param::visc_cullen) {
+      sca(FSPH_COL_DIVV, [](body & b) { return b.getDivergenceV(); });
+      sca(FSPH_COL_DDIVVDT, [](body & b) { return b.getDdivvdt(); });
+    }
     {
       std::vector<int64_t> l((size_t)n);
       for(int64_t i = 0; i < n; ++i) l[i] = (int64_t)bodies_[i].id();
@@ -475,6 +495,14 @@ private:
     sca(FSPH_COL_VSIG, [](body & b, double x) { b.setSignalspeed(x); });
     sca(FSPH_COL_GPOT, [](body & b, double x) { b.setGPotential(x); });
     sca(FSPH_COL_ADIABATIC, [](body & b, double x) { b.setAdiabatic(x); });
+    if(param::sph_viscosity == param::visc_cullen) {
+      sca(FSPH_COL_DIVV, [](body & b, double x) { b.setDivergenceV(x); });
+      sca(FSPH_COL_DDIVVDT, [](body & b, double x) { b.setDdivvdt(x); });
+      sca(FSPH_COL_TRIGGER, [](body & b, double x) { b.setTrigger(x); });
+      sca(FSPH_COL_XI, [](body & b, double x) { b.setXi(x); });
+      sca(FSPH_COL_TRACESS, [](body & b, double x) { b.setTraceSS(x); });
+      sca(FSPH_COL_GRADV, [](body & b, double x) { b.setGradV(x); });
+    }
     {
       std::vector<int64_t> l((size_t)n);
       ck(fsph_get_component(sys_, FSPH_COL_ID, 0, l.data()));

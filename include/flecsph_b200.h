@@ -45,7 +45,7 @@ enum fsph_kernel {
   FSPH_KERNEL_SINC = 7
 };
 /* eos_type keyword, include/params.h:135-141 */
-enum fsph_eos { FSPH_EOS_IDEAL = 0, FSPH_EOS_POLYTROPIC = 1 };
+enum fsph_eos { FSPH_EOS_IDEAL = 0, FSPH_EOS_POLYTROPIC = 1, FSPH_EOS_WD = 2, FSPH_EOS_PPT = 3, FSPH_EOS_NONE = 4 };
 /* sph_viscosity keyword, include/params.h:145-148 */
 enum fsph_viscosity { FSPH_VISC_CONSTANT = 0, FSPH_VISC_CULLEN = 1 };
 
@@ -81,6 +81,15 @@ typedef struct fsph_params {
   int32_t pressure_updates_number;/* params.h:194 */
   int32_t periodic_boundary_x, periodic_boundary_y, periodic_boundary_z; /* params.h:292-300 */
   int32_t reserved_;
+  double sph_viscosity_alpha_max;   /* params.h:516  (Cullen-Dehnen viscosity) */
+  double sph_viscosity_l;           /* params.h:523 */
+  double sph_viscosity_delta;       /* params.h:529 */
+  double poly_gamma2;               /* params.h:483  (piecewise polytrope) */
+  double ppt_density_thr;           /* params.h:488 */
+  double relaxation_beta;           /* params.h:568  (drag of the relaxation phase) */
+  double relaxation_gamma;          /* params.h:572 */
+  double relaxation_repulsion_radius; /* params.h:576 */
+  double relaxation_repulsion_gamma;  /* params.h:580 */
 } fsph_params;
 
 /* Fill `p` with the reference's defaults (include/params.h) for `dim`. */
@@ -114,6 +123,13 @@ enum fsph_column {
   FSPH_COL_KEY,         /* key_              [n] u64 (read-only: written by update_iteration) */
   FSPH_COL_TYPE,        /* type_ (0 NORMAL, 1 WALL) [n] i32 */
   FSPH_COL_NNEIGH,      /* neighbour count of the last sweep [n] i32 (read-only) */
+  FSPH_COL_YE,          /* electronfraction_ (white-dwarf EOS) [n] f64 */
+  FSPH_COL_DIVV,        /* divergenceV_      (Cullen-Dehnen viscosity) */
+  FSPH_COL_DDIVVDT,     /* dDivVdt_          */
+  FSPH_COL_TRIGGER,     /* trigger_          (outputs of viscosity::compute_alpha) */
+  FSPH_COL_XI,          /* xi_               */
+  FSPH_COL_TRACESS,     /* traceSS_          */
+  FSPH_COL_GRADV,       /* gradv_ (first component of the velocity-gradient matrix) */
   FSPH_COL_COUNT_
 };
 
@@ -124,7 +140,9 @@ enum fsph_sweep_op {
   FSPH_SWEEP_ACCELERATION = 1,                /* physics::compute_acceleration, default_physics.h:348 */
   FSPH_SWEEP_DUDT = 2,                        /* physics::compute_dudt, default_physics.h:421 */
   FSPH_SWEEP_DEDT = 3,                        /* physics::compute_dedt, default_physics.h:502 */
-  FSPH_SWEEP_NEIGHBORS_ONLY = 4               /* empty functor: neighbour search only (app/drivers/tree/main_driver.cc:103) */
+  FSPH_SWEEP_NEIGHBORS_ONLY = 4,              /* empty functor: neighbour search only (app/drivers/tree/main_driver.cc:103) */
+  FSPH_SWEEP_COMPUTE_ALPHA = 5,               /* viscosity::compute_alpha, viscosity.h:310 (Cullen-Dehnen) */
+  FSPH_SWEEP_SHORT_RANGE_REPULSION = 6        /* physics::add_short_range_repulsion, default_physics.h:718 */
 };
 
 /* apply_all(f) callables (mpisph/bodies_system.h:318). */
@@ -140,7 +158,11 @@ enum fsph_apply_op {
   FSPH_APPLY_RECOMPUTE_P_CS_THERMOKINETIC, /* physics::recompute_pressure_soundspeed_thermokinetic, default_physics.h:169 */
   FSPH_APPLY_COMPUTE_DT,                   /* physics::compute_dt, default_physics.h:602 */
   FSPH_APPLY_CHECK_NANS,                   /* physics::check_nans, default_physics.h:918 */
-  FSPH_APPLY_CHECK_NEGATIVITY              /* physics::check_negativity, default_physics.h:962 */
+  FSPH_APPLY_CHECK_NEGATIVITY,             /* physics::check_negativity, default_physics.h:962 */
+  FSPH_APPLY_INITIALIZE_ALPHA,             /* viscosity::initialize_alpha, viscosity.h:172 */
+  FSPH_APPLY_ADD_DRAG_ACCELERATION,        /* physics::add_drag_acceleration, default_physics.h:702 */
+  FSPH_APPLY_ADD_DRAG_DEDT,                /* physics::add_drag_dedt, default_physics.h:573 */
+  FSPH_APPLY_ADD_DRAG_DUDT                 /* physics::add_drag_dudt, default_physics.h:587 */
 };
 
 /* get_all(f) callables (mpisph/bodies_system.h:335). */

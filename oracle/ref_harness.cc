@@ -86,6 +86,15 @@ install_params(const fsph_params & p) {
   _periodic_boundary_x = p.periodic_boundary_x;
   _periodic_boundary_y = p.periodic_boundary_y;
   _periodic_boundary_z = p.periodic_boundary_z;
+  _sph_viscosity_alpha_max = p.sph_viscosity_alpha_max;
+  _sph_viscosity_l = p.sph_viscosity_l;
+  _sph_viscosity_delta = p.sph_viscosity_delta;
+  _poly_gamma2 = p.poly_gamma2;
+  _ppt_density_thr = p.ppt_density_thr;
+  _relaxation_beta = p.relaxation_beta;
+  _relaxation_gamma = p.relaxation_gamma;
+  _relaxation_repulsion_radius = p.relaxation_repulsion_radius;
+  _relaxation_repulsion_gamma = p.relaxation_repulsion_gamma;
   // what set_derived_params does (app/drivers/hydro/main_driver.cc:52-74)
   kernels::select();
   viscosity::select();
@@ -126,6 +135,13 @@ fsph_default_params(fsph_params * p, int32_t dim) {
   p->evolve_internal_energy = 1;
   p->thermokinetic_formulation = 1;
   p->pressure_updates_number = 1;
+  p->sph_viscosity_alpha_max = 1.0;
+  p->sph_viscosity_l = 0.05;
+  p->sph_viscosity_delta = 1.0;
+  p->poly_gamma2 = 2.5;
+  p->ppt_density_thr = 5e14;
+  p->relaxation_beta = 1e-6;
+  p->relaxation_repulsion_radius = 0.25;
 }
 
 const char *
@@ -220,6 +236,9 @@ fsph_set_column(fsph_system * s, int32_t col, const void * host) {
       case FSPH_COL_VSIG: b.setSignalspeed(d[i]); break;
       case FSPH_COL_GPOT: b.setGPotential(d[i]); break;
       case FSPH_COL_ADIABATIC: b.setAdiabatic(d[i]); break;
+      case FSPH_COL_YE: b.setElectronfraction(d[i]); break;
+      case FSPH_COL_DIVV: b.setDivergenceV(d[i]); break;
+      case FSPH_COL_DDIVVDT: b.setDdivvdt(d[i]); break;
       case FSPH_COL_ID: b.set_id(static_cast<const int64_t *>(host)[i]); break;
       case FSPH_COL_TYPE: b.setType(static_cast<const int32_t *>(host)[i]); break;
       default: s->err = "column not writable"; return 1;
@@ -256,6 +275,13 @@ fsph_get_column(fsph_system * s, int32_t col, void * host) {
       case FSPH_COL_VSIG: d[i] = b.getSignalspeed(); break;
       case FSPH_COL_GPOT: d[i] = b.getGPotential(); break;
       case FSPH_COL_ADIABATIC: d[i] = b.getAdiabatic(); break;
+      case FSPH_COL_YE: d[i] = b.getElectronfraction(); break;
+      case FSPH_COL_DIVV: d[i] = b.getDivergenceV(); break;
+      case FSPH_COL_DDIVVDT: d[i] = b.getDdivvdt(); break;
+      case FSPH_COL_TRIGGER: d[i] = b.getTrigger(); break;
+      case FSPH_COL_XI: d[i] = b.getXi(); break;
+      case FSPH_COL_TRACESS: d[i] = b.getTraceSS(); break;
+      case FSPH_COL_GRADV: d[i] = b.getGradV(); break;
       case FSPH_COL_ID: static_cast<int64_t *>(host)[i] = b.id(); break;
       case FSPH_COL_KEY: static_cast<uint64_t *>(host)[i] = b.key().value(); break;
       case FSPH_COL_TYPE: static_cast<int32_t *>(host)[i] = b.type(); break;
@@ -352,6 +378,8 @@ fsph_sweep(fsph_system * s, int32_t op) {
     case FSPH_SWEEP_DUDT: sweep_recording(s, physics::compute_dudt); break;
     case FSPH_SWEEP_DEDT: sweep_recording(s, physics::compute_dedt); break;
     case FSPH_SWEEP_NEIGHBORS_ONLY: sweep_recording(s, [](body &, std::vector<body *> &) {}); break;
+    case FSPH_SWEEP_COMPUTE_ALPHA: sweep_recording(s, viscosity::compute_alpha); break;
+    case FSPH_SWEEP_SHORT_RANGE_REPULSION: sweep_recording(s, physics::add_short_range_repulsion); break;
     default: s->err = "unknown sweep op"; return 1;
   }
   return 0;
@@ -366,6 +394,8 @@ sweep_plain(fsph_system * s, int32_t op) {
     case FSPH_SWEEP_ACCELERATION: s->bs->apply_in_smoothinglength(physics::compute_acceleration); break;
     case FSPH_SWEEP_DUDT: s->bs->apply_in_smoothinglength(physics::compute_dudt); break;
     case FSPH_SWEEP_DEDT: s->bs->apply_in_smoothinglength(physics::compute_dedt); break;
+    case FSPH_SWEEP_COMPUTE_ALPHA: s->bs->apply_in_smoothinglength(viscosity::compute_alpha); break;
+    case FSPH_SWEEP_SHORT_RANGE_REPULSION: s->bs->apply_in_smoothinglength(physics::add_short_range_repulsion); break;
   }
 }
 
@@ -386,6 +416,10 @@ fsph_apply(fsph_system * s, int32_t op) {
     case FSPH_APPLY_COMPUTE_DT: bs.apply_all(physics::compute_dt); break;
     case FSPH_APPLY_CHECK_NANS: bs.apply_all(physics::check_nans); break;
     case FSPH_APPLY_CHECK_NEGATIVITY: bs.apply_all(physics::check_negativity); break;
+    case FSPH_APPLY_INITIALIZE_ALPHA: bs.apply_all(viscosity::initialize_alpha); break;
+    case FSPH_APPLY_ADD_DRAG_ACCELERATION: bs.apply_all(physics::add_drag_acceleration); break;
+    case FSPH_APPLY_ADD_DRAG_DEDT: bs.apply_all(physics::add_drag_dedt); break;
+    case FSPH_APPLY_ADD_DRAG_DUDT: bs.apply_all(physics::add_drag_dudt); break;
     default: s->err = "unknown apply op"; return 1;
   }
   return 0;
@@ -455,10 +489,14 @@ fsph_step(fsph_system * s, int32_t initial) {
     for(int m = 1; m <= pressure_updates_number; ++m) {
       if(thermokinetic_formulation) {
         sweep_plain(s, FSPH_SWEEP_DEDT);
+        if(physics::iteration < relaxation_steps)
+          bs.apply_all(physics::add_drag_dedt);
         bs.apply_all(physics::recompute_pressure_soundspeed_thermokinetic);
       }
       else {
         sweep_plain(s, FSPH_SWEEP_DUDT);
+        if(physics::iteration < relaxation_steps)
+          bs.apply_all(physics::add_drag_dudt);
         bs.apply_all(physics::recompute_pressure_soundspeed);
       }
       if(m < pressure_updates_number)
@@ -470,10 +508,18 @@ fsph_step(fsph_system * s, int32_t initial) {
     bs.apply_all(eos::init);
     if(thermokinetic_formulation)
       bs.apply_all(physics::set_total_energy);
+    if(sph_viscosity != visc_constant)
+      bs.apply_all(viscosity::initialize_alpha);
     sweep_plain(s, FSPH_SWEEP_DENSITY_PRESSURE_SOUNDSPEED);
     bs.apply_all(integration::save_velocityhalf);
+    if(sph_viscosity != visc_constant)
+      sweep_plain(s, FSPH_SWEEP_COMPUTE_ALPHA);
     bs.reset_ghosts();
     sweep_plain(s, FSPH_SWEEP_ACCELERATION);
+    if(physics::iteration < relaxation_steps) {
+      bs.apply_all(physics::add_drag_acceleration);
+      sweep_plain(s, FSPH_SWEEP_SHORT_RANGE_REPULSION);
+    }
     if(enable_fmm)
       bs.gravitation_fmm();
     if(adaptive_timestep) {
@@ -495,8 +541,14 @@ fsph_step(fsph_system * s, int32_t initial) {
     bs.apply_all(integration::leapfrog_drift);
     bs.update_iteration();
     sweep_plain(s, FSPH_SWEEP_DENSITY_PRESSURE_SOUNDSPEED);
+    if(sph_viscosity != visc_constant)
+      sweep_plain(s, FSPH_SWEEP_COMPUTE_ALPHA);
     bs.reset_ghosts();
     sweep_plain(s, FSPH_SWEEP_ACCELERATION);
+    if(physics::iteration < relaxation_steps) {
+      bs.apply_all(physics::add_drag_acceleration);
+      sweep_plain(s, FSPH_SWEEP_SHORT_RANGE_REPULSION);
+    }
     if(enable_fmm)
       bs.gravitation_fmm();
     bs.apply_all(integration::leapfrog_kick_v);
