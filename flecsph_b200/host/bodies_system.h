@@ -221,8 +221,28 @@ public:
   }
 
   template<typename EF, typename... ARGS>
-  void apply_in_smoothinglength(EF && ef, ARGS &&...) {
-    static_assert(sizeof...(ARGS) == 0, "device sweeps take no extra arguments");
+  void apply_in_smoothinglength(EF && ef, ARGS &&... args) {
+    if constexpr(sizeof...(ARGS) == 1) {
+      // The neighbour census of the search micro-benchmark (app/drivers/tree/main_driver.cc:103-114): a capturing
+      // lambda (entity &, std::vector<entity *> &, size_t & total) that adds up the list lengths and asserts that every
+      // body is in its own list.  The search runs on the device (FSPH_SWEEP_NEIGHBORS_ONLY); the functor body is not
+      // executed on the host: the total comes from the device reduction of the neighbour counts, the self-membership
+      // from its minimum (a body always satisfies the pair predicate with itself).
+      sync_device();
+      ck(fsph_sweep(sys_, FSPH_SWEEP_NEIGHBORS_ONLY));
+      double o[3] = {0, 0, 0};
+      ck(fsph_reduce(sys_, FSPH_GET_NEIGHBORS_STATS, o, 3));
+      if(!(o[0] >= 1)) fsph_host::fail("apply_in_smoothinglength: a body is missing from its own neighbour list");
+      ((args += (std::remove_reference_t<ARGS>)o[2]), ...);
+      return;
+    }
+    else {
+      apply_in_smoothinglength_known(std::forward<EF>(ef));
+    }
+  }
+
+  template<typename EF>
+  void apply_in_smoothinglength_known(EF && ef) {
     int op = -1;
     if constexpr(std::is_convertible<EF, sweep_fn>::value) {
       const sweep_fn f = ef;

@@ -78,6 +78,36 @@ def test_unmodified_driver_on_gpu_matches_reference_build(tmp_path, name, dim, i
     compare(g, r, iters)
 
 
+@pytest.mark.gpu
+def test_unmodified_tree_driver_on_gpu(tmp_path):
+    """The neighbour-search micro-benchmark (app/drivers/tree/main.cc + main_driver.cc, unmodified) on the facade:
+    update_iteration + the neighbour census on the device, iteration after iteration (the driver loops 5000 times; it is
+    stopped after a few seconds).  The average neighbour count it prints must be that of the reference search."""
+    from flecsph_b200 import capi
+    from common import make_system
+    exe = os.path.join(B200, "tree_3d_b200")
+    if not have(exe):
+        pytest.skip("tree_3d_b200 not built (need the reference checkout: make -C flecsph_b200/host)")
+    f, par = idata.sedov_3d(nx=20)
+    wd = str(tmp_path / "tree")
+    os.makedirs(wd, exist_ok=True)
+    fsphbin.write_initial_data(os.path.join(wd, "id.fsphbin"), f, 3)
+    fsphbin.write_par(os.path.join(wd, "run.par"), par, initial_data_prefix="id", output_h5data_prefix="out", final_iteration=3)
+    if not os.access(exe, os.X_OK):
+        os.chmod(exe, 0o755)
+    try:
+        out = subprocess.run([exe, "run.par"], cwd=wd, capture_output=True, text=True, timeout=20).stdout
+    except subprocess.TimeoutExpired as e:
+        out = (e.stdout or b"").decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+    avg = [int(l.split()[1]) for l in out.splitlines() if l.startswith("Average:")]
+    assert len(avg) >= 3, out[-1000:]
+    S = make_system("cuda", f, par, 3)
+    S.update_iteration()
+    S.apply_in_smoothinglength(capi.SWEEP_NEIGHBORS_ONLY)
+    nn = S.get(capi.COL_NNEIGH)
+    assert avg[0] == int(nn.sum()) // len(nn)
+
+
 def test_reference_driver_build_matches_reference_library(tmp_path):
     """CPU plumbing check of the .par / .fsphbin path: the reference driver binary against the reference headers
     behind the C ABI (oracle/_ref/libflecsph_ref_1d.so) stepping the same Sod tube."""
