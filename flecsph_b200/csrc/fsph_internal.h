@@ -219,6 +219,7 @@ struct System {
   // storage
   DevBuf col[NF64], col_id, col_key, col_type, col_nneigh, scratch_col;
   DevBuf b_perm, b_keys2, b_perm2, b_tmp[6];
+  DevBuf b_gather[7];   // spare column buffers of the fused gather (fsph_tree.cu)
   DevBuf b_node_parent;
   DevBuf b_fmm_nodes, b_fmm_out, b_fmm_stack;   // FMM: node accumulators, output strip and stack of pending cell pairs
   unsigned long long fmm_pairs = 0;             // cell pairs the last gravitation_fmm processed
@@ -306,7 +307,8 @@ extern std::atomic<unsigned long long> g_launches;
 // One stable LSD pass on an 8-bit digit at `shift`; vals may be null (keys only).
 void radix_pass(System & s, const uint64_t * kin, const uint32_t * vin, uint64_t * kout, uint32_t * vout, int64_t n, int shift);
 // Full 64-bit sort of (key, index) pairs; result in kout/vout (may swap internally): returns pointers to the sorted arrays.
-void radix_sort_pairs(System & s, uint64_t *& k0, uint32_t *& v0, uint64_t *& k1, uint32_t *& v1, int64_t n);
+// keys_src: the caller's copy of the unsorted keys (enables the four-pass + run fix-up path; null: eight passes)
+void radix_sort_pairs(System & s, uint64_t *& k0, uint32_t *& v0, uint64_t *& k1, uint32_t *& v1, int64_t n, const uint64_t * keys_src = nullptr);
 void exclusive_scan_u32(System & s, const uint32_t * in, uint32_t * out, int64_t n, uint32_t * total_dev);  // out[n] = total (callers rely on it)
 void exclusive_scan_u64(System & s, const uint64_t * in, uint64_t * out, int64_t n, uint64_t * total_dev);
 

@@ -37,6 +37,7 @@
 #include <stdexcept>
 #include <algorithm>
 #include <cstdlib>
+#include <cstdio>
 #include "fsph_internal.h"
 
 namespace fsph {
@@ -1056,6 +1057,22 @@ static void neighbor_search_t(System & s) {
       s.est_rows = tot.rows;
       s.est_n = s.n;
       sr.nrows = tot.rows;
+      if(getenv("FSPH_DEBUG_SEARCH")) {
+        // structure statistics (diagnostic): block fill, candidates per block, list-row padding
+        std::vector<int32_t> nb(nblk), nc(nblk);
+        FSPH_CUDA_OK(cudaMemcpy(nb.data(), sr.blk_nbody, (size_t)nblk * 4, cudaMemcpyDeviceToHost));
+        FSPH_CUDA_OK(cudaMemcpy(nc.data(), sr.blk_ncand, (size_t)nblk * 4, cudaMemcpyDeviceToHost));
+        double sb = 0, sc = 0, sw = 0;
+        int full = 0;
+        for(int b = 0; b < nblk; ++b) { sb += nb[b]; sc += nc[b]; sw += (nb[b] + 31) / 32; full += nb[b] > 224; }
+        std::vector<int32_t> nn(s.n);
+        FSPH_CUDA_OK(cudaMemcpy(nn.data(), s.col_nneigh.p, (size_t)s.n * 4, cudaMemcpyDeviceToHost));
+        double sn = 0;
+        for(int64_t i = 0; i < s.n; ++i) sn += nn[i];
+        fprintf(stderr, "[search] n %lld nwc %d nsuper %d nblk %d bodies/block %.1f (>224: %.0f%%) warps/block %.2f cands/block %.0f tiles %llu rows %llu "
+                        "pairs %.4g slot efficiency %.3f\n", (long long)s.n, sr.nwc, sr.nsuper, nblk, sb / nblk, 100.0 * full / nblk, sw / nblk, sc / nblk,
+          (unsigned long long)tot.dir, (unsigned long long)tot.rows, sn, sn / ((double)tot.rows * 32));
+      }
       return;
     }
     const uint32_t cleared = st & ~(uint32_t)(ERR_SEARCH_CAPACITY | ERR_QUEUE_OVERFLOW);

@@ -67,6 +67,7 @@ void release_buffers(System & s) {
   for(DevBuf * b : all) b->release();
   for(int f = 0; f < NF64; ++f) s.col[f].release();
   for(int i = 0; i < 6; ++i) s.b_tmp[i].release();
+  for(int i = 0; i < 7; ++i) s.b_gather[i].release();
   for(int d = 0; d < 3; ++d) { s.b_ncom[d].release(); s.b_nbmin[d].release(); s.b_nbmax[d].release(); }
 }
 
@@ -266,9 +267,38 @@ void radix_pass(System & s, const uint64_t * kin, const uint32_t * vin, uint64_t
   radix_pass_mode(s, kin, vin, kout, vout, n, shift, vin ? 1 : 0);
 }
 
+// Runs of equal high key halves after the passes on the four high digits: the stable passes left each run in its order
+// of the previous step; it is finished here by an insertion sort on the full key (runs are almost always single bodies:
+// 2^32 high halves for at most 2^31 bodies).  A run longer than 32 sets *flag (the caller then sorts all eight digits).
+__global__ void __launch_bounds__(256) k_fix_runs(uint64_t * __restrict__ k, uint32_t * __restrict__ v, int64_t n, uint32_t * __restrict__ flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const uint64_t hi = k[i] >> 32;
+  if(i > 0 && (k[i - 1] >> 32) == hi) return;        // not the first of its run
+  if(i + 1 >= n || (k[i + 1] >> 32) != hi) return;   // run of one
+  int L = 2;
+  while(i + L < n && (k[i + L] >> 32) == hi) {
+    if(++L > 32) { *flag = 1u; return; }
+  }
+  for(int a = 1; a < L; ++a) {
+    const uint64_t ka = k[i + a];
+    const uint32_t va = v[i + a];
+    int b = a - 1;
+    while(b >= 0 && k[i + b] > ka) {
+      k[i + b + 1] = k[i + b];
+      v[i + b + 1] = v[i + b];
+      --b;
+    }
+    k[i + b + 1] = ka;
+    v[i + b + 1] = va;
+  }
+}
+
 // Sort (key, index) pairs: on entry k0 holds the keys (v0 contents ignored: the payload starts as the
 // identity); on return k0/v0 point at the sorted keys / permutation and k1/v1 at the scratch pair.
-void radix_sort_pairs(System & s, uint64_t *& k0, uint32_t *& v0, uint64_t *& k1, uint32_t *& v1, int64_t n) {
+// The bodies arrive in the key order of the previous step, so the low key half only matters inside runs of equal high
+// halves: four stable passes on the high digits, then k_fix_runs; eight passes when a run is too long for that.
+void radix_sort_pairs(System & s, uint64_t *& k0, uint32_t *& v0, uint64_t *& k1, uint32_t *& v1, int64_t n, const uint64_t * keys_src) {
   s.b_tmp[1].reserve(8 * 256 * sizeof(uint32_t));
   uint32_t * hist = s.b_tmp[1].as<uint32_t>();
   FSPH_CUDA_OK(cudaMemsetAsync(hist, 0, 8 * 256 * sizeof(uint32_t), s.stream));
@@ -277,22 +307,37 @@ void radix_sort_pairs(System & s, uint64_t *& k0, uint32_t *& v0, uint64_t *& k1
   std::vector<uint32_t> h(8 * 256);
   FSPH_CUDA_OK(cudaMemcpyAsync(h.data(), hist, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
   FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
-  bool first = true;
-  for(int p = 0; p < 8; ++p) {
-    bool trivial = false;
+  auto trivial = [&](int p) {
     for(int d = 0; d < 256; ++d)
-      if(h[p * 256 + d] == (uint32_t)n) trivial = true;
-    if(trivial) continue;
-    radix_pass_mode(s, k0, v0, k1, v1, n, 8 * p, first ? 2 : 1);
-    first = false;
-    std::swap(k0, k1);
-    std::swap(v0, v1);
-  }
-  if(first) {
-    // all passes trivial (n <= 1): identity permutation
-    radix_pass_mode(s, k0, v0, k1, v1, n, 0, 2);
-    std::swap(k0, k1);
-    std::swap(v0, v1);
+      if(h[p * 256 + d] == (uint32_t)n) return true;
+    return false;
+  };
+  for(int attempt = 0; attempt < 2; ++attempt) {
+    const int p_lo = (attempt == 0 && keys_src) ? 4 : 0;
+    bool first = true;
+    for(int p = p_lo; p < 8; ++p) {
+      if(trivial(p)) continue;
+      radix_pass_mode(s, k0, v0, k1, v1, n, 8 * p, first ? 2 : 1);
+      first = false;
+      std::swap(k0, k1);
+      std::swap(v0, v1);
+    }
+    if(first) {
+      // all passes trivial: identity permutation
+      radix_pass_mode(s, k0, v0, k1, v1, n, 0, 2);
+      std::swap(k0, k1);
+      std::swap(v0, v1);
+    }
+    if(p_lo == 0) return;
+    uint32_t * flag = s.b_status.as<uint32_t>() + 2;
+    FSPH_CUDA_OK(cudaMemsetAsync(flag, 0, 4, s.stream));
+    FSPH_LAUNCH(k_fix_runs, (unsigned)((n + 255) / 256), 256, s.stream, k0, v0, n, flag);
+    uint32_t f = 0;
+    FSPH_CUDA_OK(cudaMemcpyAsync(&f, flag, 4, cudaMemcpyDeviceToHost, s.stream));
+    FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
+    if(!f) return;
+    // a long run of equal high halves (bodies clustered below 2^-10 of the range): start again from the caller's keys
+    FSPH_CUDA_OK(cudaMemcpyAsync(k0, keys_src, (size_t)n * 8, cudaMemcpyDeviceToDevice, s.stream));
   }
 }
 

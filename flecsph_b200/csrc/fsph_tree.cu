@@ -155,13 +155,6 @@ __global__ void __launch_bounds__(256) k_is_identity(const uint32_t * __restrict
   if(i < n && perm[i] != (uint32_t)i) *flag = 1;
 }
 
-static void gather8(System & s, DevBuf & colbuf, const uint32_t * perm, int64_t n_new) {
-  s.scratch_col.reserve_exact(std::max(colbuf.cap, (size_t)n_new * 8));
-  unsigned nb = (unsigned)((n_new + 255) / 256);
-  if(n_new > 0) FSPH_LAUNCH((k_gather<uint64_t>), nb, 256, s.stream, colbuf.as<uint64_t>(), s.scratch_col.as<uint64_t>(), perm, n_new);
-  std::swap(colbuf.p, s.scratch_col.p);
-  std::swap(colbuf.cap, s.scratch_col.cap);
-}
 static void gather4(System & s, DevBuf & colbuf, const uint32_t * perm, int64_t n_new) {
   s.b_tmp[0].reserve_exact(std::max(colbuf.cap, (size_t)n_new * 4));
   unsigned nb = (unsigned)((n_new + 255) / 256);
@@ -189,13 +182,55 @@ void live_columns(System & s, std::vector<std::pair<DevBuf *, int>> & out) {
   }
 }
 
-// out[i] = in[perm[i]] for every live column; perm must not live in scratch_col / b_tmp[0]
+// Several 8-byte columns gathered in one pass: the permutation is read once per body for all of them.
+struct GatherSet {
+  const uint64_t * in[8];
+  uint64_t * out[8];
+  int n;
+};
+__global__ void __launch_bounds__(256) k_gather_set(GatherSet g, const uint32_t * __restrict__ perm, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const uint32_t p = perm[i];
+  uint64_t v[8];
+#pragma unroll
+  for(int j = 0; j < 8; ++j)
+    if(j < g.n) v[j] = g.in[j][p];
+#pragma unroll
+  for(int j = 0; j < 8; ++j)
+    if(j < g.n) g.out[j][i] = v[j];
+}
+
+// out[i] = in[perm[i]] for every live column; perm must not live in scratch_col / b_tmp[0].  The 8-byte columns go
+// through a ring of spare buffers, eight columns per launch: column j's old storage becomes the spare of a later one.
 void gather_bodies(System & s, const uint32_t * perm, int64_t n_new) {
   std::vector<std::pair<DevBuf *, int>> cols;
   live_columns(s, cols);
+  std::vector<DevBuf *> c8;
   for(auto & c : cols) {
-    if(c.second == 8) gather8(s, *c.first, perm, n_new);
+    if(c.second == 8) c8.push_back(c.first);
     else gather4(s, *c.first, perm, n_new);
+  }
+  const unsigned nb = (unsigned)((n_new + 255) / 256);
+  size_t need = (size_t)n_new * 8;
+  for(DevBuf * c : c8) need = std::max(need, c->cap);
+  for(size_t b = 0; b < c8.size(); b += 8) {
+    const int k = (int)std::min<size_t>(8, c8.size() - b);
+    // spares for this batch: scratch_col and the gather pool
+    DevBuf * spare[8];
+    for(int j = 0; j < k; ++j) {
+      spare[j] = j == 0 ? &s.scratch_col : &s.b_gather[j - 1];
+      spare[j]->reserve_exact(need);
+    }
+    GatherSet g;
+    g.n = k;
+    for(int j = 0; j < 8; ++j) { g.in[j] = nullptr; g.out[j] = nullptr; }
+    for(int j = 0; j < k; ++j) { g.in[j] = c8[b + j]->as<uint64_t>(); g.out[j] = spare[j]->as<uint64_t>(); }
+    if(n_new > 0) FSPH_LAUNCH(k_gather_set, nb, 256, s.stream, g, perm, n_new);
+    for(int j = 0; j < k; ++j) {
+      std::swap(c8[b + j]->p, spare[j]->p);
+      std::swap(c8[b + j]->cap, spare[j]->cap);
+    }
   }
   FSPH_CUDA_OK(cudaGetLastError());
 }
@@ -213,7 +248,8 @@ void sort_bodies(System & s, int64_t n_keep) {
   uint32_t * v0 = s.b_perm.as<uint32_t>();
   uint32_t * v1 = s.b_perm2.as<uint32_t>();
   FSPH_CUDA_OK(cudaMemcpyAsync(k0, s.col_key.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, s.stream));
-  radix_sort_pairs(s, k0, v0, k1, v1, n);
+  // with remote copies in the array (their keys are all ~0: one long run) the run fix-up does not apply: eight passes
+  radix_sort_pairs(s, k0, v0, k1, v1, n, s.comm ? nullptr : s.col_key.as<uint64_t>());
   // the sorted permutation must not live in scratch_col (the gathers overwrite it)
   const uint32_t * perm = v0;
   s.last_perm = perm;
