@@ -626,30 +626,22 @@ __global__ void __launch_bounds__(BLK_BODIES, SweepOcc<OP>::MINB) k_sweep(Cols c
       }
     }
     __syncthreads();
-    // uniform pair loop over the lanes' lists, two pairs per iteration (independent fp64 dependency chains); the list
-    // entries and cache slots of the next iteration are loaded before this one is evaluated (their DRAM latency hides
-    // behind the arithmetic)
-    const double * pa = pair_a + (size_t)(rb + 1) * 32 + lane;
-    const double * pp_ = pair_pi + (size_t)(rb + 1) * 32 + lane;
+    // uniform pair loop over the lanes' lists, two pairs per iteration (independent fp64 dependency chains); the
+    // entries of the next iteration are loaded before this one is evaluated
     int e0 = cmax > 0 ? rows[32] : 0, e1 = cmax > 1 ? rows[64] : 0;
-    double na0 = 0.0, na1 = 0.0, np0 = 0.0, np1 = 0.0;
-    if(A_RD) { na0 = 0 < cnt ? pa[0] : 0.0; na1 = 1 < cnt ? pa[32] : 0.0; }
-    if(P_RD) { np0 = 0 < cnt ? pp_[0] : 0.0; np1 = 1 < cnt ? pp_[32] : 0.0; }
     for(int j = 0; j < cmax; j += 2) {
       const bool v0 = j < cnt, v1 = j + 1 < cnt;
       const int ci0 = v0 ? e0 : 0, ci1 = v1 ? e1 : 0;
-      double a0 = na0, a1 = na1, p0 = np0, p1 = np1;
+      const size_t slot0 = (size_t)(rb + 1 + j) * 32 + lane, slot1 = slot0 + 32;
+      double a0 = 0.0, a1 = 0.0, p0 = 0.0, p1 = 0.0;
+      if(A_RD) { a0 = v0 ? pair_a[slot0] : 0.0; a1 = v1 ? pair_a[slot1] : 0.0; }
+      if(P_RD) { p0 = v0 ? pair_pi[slot0] : 0.0; p1 = v1 ? pair_pi[slot1] : 0.0; }
       if(j + 2 < cmax) e0 = rows[(3 + j) * 32];
       if(j + 3 < cmax) e1 = rows[(4 + j) * 32];
-      if(A_RD) { na0 = j + 2 < cnt ? pa[(size_t)(j + 2) * 32] : 0.0; na1 = j + 3 < cnt ? pa[(size_t)(j + 3) * 32] : 0.0; }
-      if(P_RD) { np0 = j + 2 < cnt ? pp_[(size_t)(j + 2) * 32] : 0.0; np1 = j + 3 < cnt ? pp_[(size_t)(j + 3) * 32] : 0.0; }
       pair_body<D, K, OP, CM, VISC>(o, tile, tidx, pp, ci0, v0, a0, p0);
       pair_body<D, K, OP, CM, VISC>(o, tile, tidx, pp, ci1, v1, a1, p1);
-      if(A_WR || P_WR) {
-        const size_t slot0 = (size_t)(rb + 1 + j) * 32 + lane, slot1 = slot0 + 32;
-        if(A_WR) { if(v0) pair_a[slot0] = a0; if(v1) pair_a[slot1] = a1; }
-        if(P_WR) { if(v0) pair_pi[slot0] = p0; if(v1) pair_pi[slot1] = p1; }
-      }
+      if(A_WR) { if(v0) pair_a[slot0] = a0; if(v1) pair_a[slot1] = a1; }
+      if(P_WR) { if(v0) pair_pi[slot0] = p0; if(v1) pair_pi[slot1] = p1; }
     }
   }
   if(active) store_own<D, OP, VISC>(o, c, pp, status);
