@@ -88,11 +88,10 @@ PRODUCT_LIB = os.environ.get("FSPH_PRODUCT_LIB") or os.path.join(ROOT, "flecsph_
 
 
 def library_path(which, dim=3):
-    """'cuda' -> the product; 'port' / 'ref' / 'ref_fast' -> the checkers under oracle/ (tests and bench baseline only)."""
+    """'cuda' -> the product; 'ref' / 'ref_fast' -> the reference headers behind the ABI under oracle/_ref (tests and bench
+    baseline only; the numpy restatement oracle/oracle_port.py is imported directly by the tests)."""
     if which == "cuda":
         return PRODUCT_LIB
-    if which == "port":
-        return os.path.join(ROOT, "oracle", "liboracle_port.so")
     if which == "ref":
         return os.path.join(ROOT, "oracle", "_ref", "libflecsph_ref_%dd.so" % dim)
     if which == "ref_fast":

@@ -158,7 +158,12 @@ void do_step(System & s, int initial) {
   // compute_acceleration and what the drivers hang on it (hydro/main_driver.cc:123-133,197-206): the adaptive viscosity
   // sweep before it, the relaxation terms after it
   auto acceleration = [&]() {
-    if(cullen) do_sweep(s, FSPH_SWEEP_COMPUTE_ALPHA);
+    if(cullen) {
+      // compute_alpha reads the neighbours' new sound speed and velocity divergence: remote copies are refreshed first
+      // (the reference fetches them from their owner while it traverses)
+      if(s.comm) do_reset_ghosts(s);
+      do_sweep(s, FSPH_SWEEP_COMPUTE_ALPHA);
+    }
     do_reset_ghosts(s);
     do_sweep(s, 101);
     if(relaxing) {
@@ -301,6 +306,15 @@ void fsph_default_params(fsph_params * p, int32_t dim) {
   p->evolve_internal_energy = 1;
   p->thermokinetic_formulation = 1;
   p->pressure_updates_number = 1;
+  p->sph_viscosity_alpha_max = 1.0;
+  p->sph_viscosity_l = 0.05;
+  p->sph_viscosity_delta = 1.0;
+  p->poly_gamma2 = 2.5;
+  p->ppt_density_thr = 5e14;
+  p->relaxation_beta = 1e-6;
+  p->relaxation_gamma = 0.0;
+  p->relaxation_repulsion_radius = 0.25;
+  p->relaxation_repulsion_gamma = 0.0;
 }
 
 const char * fsph_backend(void) { return "cuda-sm100a"; }
@@ -624,9 +638,12 @@ int32_t fsph_step(fsph_system * s, int32_t initial) {
     cudaEventCreate(&tot.e1);
     cudaEventRecord(tot.e0, s->stream);
     try {
+      s->in_step = true;
       do_step(*s, initial);
+      s->in_step = false;
     }
     catch(...) {
+      s->in_step = false;
       cudaEventDestroy(tot.e0);
       cudaEventDestroy(tot.e1);
       for(auto & p : s->phases) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }

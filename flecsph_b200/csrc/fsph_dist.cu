@@ -844,9 +844,14 @@ static void dist_update_iteration_t(System & s) {
     d.nghost = (int64_t)ng;
     const int64_t n_total = s.n_owned + d.nghost;
     if(n_total >= (int64_t(1) << 31)) throw std::runtime_error("owned + ghost bodies exceed 2^31 on this rank");
-    // all live columns of the bodies a peer needs travel in ONE all-to-all-v: [peer][column][body]
-    std::vector<std::pair<DevBuf *, int>> cols;
-    live_columns(s, cols);
+    // the columns of the bodies a peer needs travel in ONE all-to-all-v: [peer][column][body].  Inside fsph_step only
+    // what the tree, the search and the density sweep read from a neighbour (the rest is re-sent by reset_ghosts before
+    // the sweep that reads it); outside it every live column (the caller may run any sweep next).
+    std::vector<std::pair<DevBuf *, int>> cols, all_cols;
+    live_columns(s, all_cols);
+    if(s.in_step) halo_columns(s, cols);
+    else cols = all_cols;
+    for(auto & c : all_cols) c.first->grow_keep((size_t)n_total * c.second, (size_t)s.n_owned * c.second, s.stream);
     std::vector<size_t> so(P), sc(P), ro(P), rc(P);
     ColPtrs8 p8;
     ColPtrs4 p4;

@@ -213,6 +213,7 @@ struct System {
   bool tree_valid = false, search_valid = false, tree_dirty = false;
   // inside fsph_step the sort need not permute columns that are recomputed before their next read
   bool skip_dead_columns = false;
+  bool in_step = false;   // inside fsph_step: the order of the sweeps and ghost refreshes is the driver's
   bool dead_col[NF64] = {};
   bool col_used[NF64] = {};   // optional columns this system allocates (fsph_create)
 
@@ -318,6 +319,7 @@ void compute_keys(System & s);                  // filling_curve.h:503-525
 // psort.h:227-322 (one rank): radix sort + column gather; only the first n_keep bodies of the sorted order are kept
 void sort_bodies(System & s, int64_t n_keep = -1);
 void live_columns(System & s, std::vector<std::pair<DevBuf *, int>> & out);  // columns that carry state, element size
+void halo_columns(System & s, std::vector<std::pair<DevBuf *, int>> & out);  // columns a remote copy arrives with inside fsph_step
 void gather_bodies(System & s, const uint32_t * perm, int64_t n_new);  // every live column: out[i] = in[perm[i]], i < n_new
 void build_tree(System & s);                    // tree_topology.h:878-997 + default_physics.h:59-119
 // Multi-rank variants: the local tree is the global canonical tree restricted to the bodies present here.

@@ -47,7 +47,16 @@ constexpr int SW_NT = 256;      // threads per CTA of the super-cell walk
 constexpr int SR_NT = BLK_BODIES;
 constexpr int SR_NW = SR_NT / 32;
 constexpr int SR_CHUNK = 2048;  // super-list entries filtered per round (8 per thread)
-constexpr int SR_LROWS = 48;    // list rows staged per warp and tile in shared memory (longer lists: slow path)
+#ifndef FSPH_SR_LROWS
+#define FSPH_SR_LROWS 48
+#endif
+#ifndef FSPH_SR_HALF
+#define FSPH_SR_HALF 256
+#endif
+#ifndef FSPH_SR_OCC
+#define FSPH_SR_OCC 3
+#endif
+constexpr int SR_LROWS = FSPH_SR_LROWS;   // list rows staged per warp and tile in shared memory (longer lists: slow path)
 constexpr double GEO_TOL = 2.220446049250313e-16 * 10.;  // tree_geometry.h:57
 
 template<int D>
@@ -388,7 +397,7 @@ struct __align__(16) CandRec {
 };
 // dynamic shared memory of k_block_search: walk queue (node, cell mask, first child cell, leaf mask) OR candidate tile,
 // cell masks, per-warp candidate lists and per-warp list staging
-constexpr int SR_HALF = NL_TILE / 2;          // candidates compacted and tested per pass
+constexpr int SR_HALF = FSPH_SR_HALF;         // candidates compacted and tested per pass
 constexpr int SR_QCAPL = SR_HALF + 16;        // entries of a quarter-warp's candidate list (padded to a multiple of 16)
 constexpr int SM_CM = (NL_TILE + 1) * 32;     // + the sentinel record
 constexpr int SM_WL = SM_CM + NL_TILE * 2;
@@ -396,7 +405,8 @@ constexpr int SM_LBUF = SM_WL + SR_NW * 4 * SR_QCAPL * 2;
 constexpr int SM_TOTAL = SM_LBUF + SR_NW * (SR_LROWS + 1) * 64;
 // walk: node, cell mask, first child cell, leaf mask per queue entry, then the leaf items of 256 entries
 constexpr int SM_QITEM = SR_CHUNK * 13;
-constexpr int SM_QTOTAL = SM_QITEM + BLK_BODIES * 8 * 6;
+constexpr int SM_GX = SM_QITEM + BLK_BODIES * 8 * 6;   // positions and h of the block's bodies (walk phases only)
+constexpr int SM_QTOTAL = SM_GX + 4 * BLK_BODIES * 8;
 constexpr int block_search_smem() { return SM_TOTAL > SM_QTOTAL ? SM_TOTAL : SM_QTOTAL; }
 
 // Tight box, reach and cells of the 8 bodies of a quarter warp, in fp32 relative to the centre of the block's tight box
@@ -498,13 +508,11 @@ __device__ __forceinline__ int compact_quarters(const CandRec * __restrict__ c4,
 }
 
 template<int D>
-__global__ void __launch_bounds__(SR_NT, 3) k_block_search(Tree t, Cols c, Search sr, int64_t * __restrict__ scratch, int scratch_cap,
+__global__ void __launch_bounds__(SR_NT, FSPH_SR_OCC) k_block_search(Tree t, Cols c, Search sr, int64_t * __restrict__ scratch, int scratch_cap,
   SearchCursors * __restrict__ cur, unsigned long long cand_cap, unsigned long long dir_cap, unsigned long long rows_cap,
   uint32_t * __restrict__ status) {
   constexpr int NT = SR_NT;
   constexpr int NCH = 1 << D;
-  __shared__ double gx[D][NT];
-  __shared__ double gh[NT];
   __shared__ CellInfo<D> cell[BLK_CELLS];
   __shared__ uint8_t slot_of[NT];
   __shared__ uint32_t scan_sm[SR_NW];
@@ -521,6 +529,8 @@ __global__ void __launch_bounds__(SR_NT, 3) k_block_search(Tree t, Cols c, Searc
   CandRec * const c4 = reinterpret_cast<CandRec *>(ubuf);                                    // [NL_TILE] x, y, z, h^2
   uint16_t * const cm = reinterpret_cast<uint16_t *>(ubuf + SM_CM);                          // [NL_TILE] cell masks
   uint16_t (* const wl)[4][SR_QCAPL] = reinterpret_cast<uint16_t (*)[4][SR_QCAPL]>(ubuf + SM_WL);   // per quarter warp: its candidates
+  double (* const gx)[NT] = reinterpret_cast<double (*)[NT]>(ubuf + SM_GX);                 // walk: the block's positions,
+  double * const gh = reinterpret_cast<double *>(ubuf + SM_GX + 3 * NT * 8);                //       and smoothing lengths
   int32_t * const it_cell = reinterpret_cast<int32_t *>(ubuf + SM_QITEM);                   // leaf items of the walk: leaf cell,
   uint16_t * const it_ent = reinterpret_cast<uint16_t *>(ubuf + SM_QITEM + BLK_BODIES * 8 * 4);   // ... queue entry
   uint16_t (* const lbuf)[SR_LROWS + 1][32] = reinterpret_cast<uint16_t (*)[SR_LROWS + 1][32]>(ubuf + SM_LBUF);
@@ -1015,7 +1025,7 @@ static void neighbor_search_t(System & s) {
   sr.blk_body = sr.blk_ncand + nblk;
   sr.blk_nbody = sr.blk_body + nblk;
   SearchCursors * cursors = reinterpret_cast<SearchCursors *>(s.b_status.as<uint32_t>() + 8);
-  const int grid = std::min(nblk, 148 * 3 * 2);
+  const int grid = std::min(nblk, 148 * FSPH_SR_OCC * 2);
   int scratch_cap = s.search_scratch_cap;
   // capacities: from the previous search of this system (scaled when the body count drifts, e.g. with ghosts), else a
   // first guess; a search that does not fit still counts, and is repeated once with the exact sizes

@@ -274,6 +274,12 @@ __global__ void __launch_bounds__(256) k_fix_runs(uint64_t * __restrict__ k, uin
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= n) return;
   const uint64_t hi = k[i] >> 32;
+  if(hi == 0xffffffffull) {
+    // the run of the largest high half holds the remote copies of the previous iteration (key ~0, dropped by the caller:
+    // their order is irrelevant); a real key up there (a body in the last 2^-10 of the range on every axis) needs the full sort
+    if(k[i] != ~0ull) *flag = 1u;
+    return;
+  }
   if(i > 0 && (k[i - 1] >> 32) == hi) return;        // not the first of its run
   if(i + 1 >= n || (k[i + 1] >> 32) != hi) return;   // run of one
   int L = 2;

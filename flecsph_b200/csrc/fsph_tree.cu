@@ -201,6 +201,20 @@ __global__ void __launch_bounds__(256) k_gather_set(GatherSet g, const uint32_t 
     if(j < g.n) g.out[j][i] = v[j];
 }
 
+// The columns a remote copy needs when it ARRIVES (fsph_dist.cu, halo exchange inside fsph_step): what the tree, the
+// neighbour search and the density sweep read from neighbours -- position, h, mass -- plus identity.  Everything else a
+// sweep reads from a neighbour (rho, P, c_s, v, v_1/2, alpha, div v) is re-sent by reset_ghosts before that sweep.
+void halo_columns(System & s, std::vector<std::pair<DevBuf *, int>> & out) {
+  out.clear();
+  for(int d = 0; d < s.dim; ++d) out.emplace_back(&s.col[F_POS + d], 8);
+  out.emplace_back(&s.col[F_H], 8);
+  out.emplace_back(&s.col[F_MASS], 8);
+  out.emplace_back(&s.col_id, 8);
+  out.emplace_back(&s.col_key, 8);
+  out.emplace_back(&s.col_type, 4);
+  out.emplace_back(&s.col_gd, 4);
+}
+
 // out[i] = in[perm[i]] for every live column; perm must not live in scratch_col / b_tmp[0].  The 8-byte columns go
 // through a ring of spare buffers, eight columns per launch: column j's old storage becomes the spare of a later one.
 void gather_bodies(System & s, const uint32_t * perm, int64_t n_new) {
@@ -248,8 +262,7 @@ void sort_bodies(System & s, int64_t n_keep) {
   uint32_t * v0 = s.b_perm.as<uint32_t>();
   uint32_t * v1 = s.b_perm2.as<uint32_t>();
   FSPH_CUDA_OK(cudaMemcpyAsync(k0, s.col_key.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, s.stream));
-  // with remote copies in the array (their keys are all ~0: one long run) the run fix-up does not apply: eight passes
-  radix_sort_pairs(s, k0, v0, k1, v1, n, s.comm ? nullptr : s.col_key.as<uint64_t>());
+  radix_sort_pairs(s, k0, v0, k1, v1, n, s.col_key.as<uint64_t>());
   // the sorted permutation must not live in scratch_col (the gathers overwrite it)
   const uint32_t * perm = v0;
   s.last_perm = perm;

@@ -18,7 +18,7 @@
  * The same ABI is implemented three times, which is what makes the parity
  * tests read like one another:
  *   flecsph_b200/csrc  -> libflecsph_b200.so   the product (sm_100a CUDA, no CPU path)
- *   oracle/            -> liboracle_port.so    CPU restatement (test infrastructure)
+ *   oracle/            -> oracle_port.py       numpy restatement with the same method names (test infrastructure)
  *   oracle/_ref        -> libflecsph_ref_Dd.so the unmodified reference headers behind
  *                                              this ABI (test infrastructure)
  */

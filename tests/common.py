@@ -27,7 +27,7 @@ def case(name, **kw):
     """Named seeded inputs -> (fields, par, dim)."""
     if name == "sedov":
         f, par = idata.sedov_3d(nx=kw.get("nx", 12))
-        return f, par, 3
+        return f, dict(par, **kw.get("par", {})), 3
     if name == "noh":
         f, par = idata.noh_3d(nx=kw.get("nx", 12))
         return f, par, 3

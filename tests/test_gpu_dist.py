@@ -121,6 +121,9 @@ STEP_CASES = [
     ("collapse", dict(nx=16), 2, "random", 3),
     ("sod", dict(nx=400), 2, "chunks", 5),
     ("random", dict(n=4000, dim=2, h_jitter=0.1, seed=8), 2, "random", 2),
+    # Cullen-Dehnen viscosity (remote copies need alpha and div v) and the relaxation phase on several ranks
+    ("sedov", dict(nx=22, par=dict(sph_viscosity=1, sph_viscosity_alpha_max=1.5)), 3, "random", 4),
+    ("random", dict(n=5000, seed=9, h_jitter=0.1, par=dict(relaxation_steps=2, relaxation_beta=0.3, relaxation_repulsion_gamma=1e-4)), 2, "random", 3),
 ]
 
 
