@@ -110,9 +110,7 @@ constexpr int BLK_BODIES = 256;   // bodies per block = threads per CTA of the s
 constexpr int BLK_CELLS = 16;     // work cells per block (bits of a candidate's cell mask)
 constexpr int NL_TILE = 512;      // candidates per list tile (tile-local positions fit 16 bits)
 struct __align__(16) TileDir {
-  uint64_t row0;       // first row of the tile in the list arena
-  uint16_t cmax[8];    // per warp: longest list of its lanes in this tile (the warp owns 1 + cmax rows, warps in order)
-  uint64_t pad;
+  uint32_t row[8];     // per warp: its first row of the tile in the list arena (it owns 1 + the longest list of its lanes)
 };
 struct Search {
   int32_t * wc_cell;     // work cells in Morton order: index into Tree::cell
@@ -230,11 +228,11 @@ struct System {
   DevBuf b_wc_super, b_super_cell, b_sl_off, b_sl_nodes;
   DevBuf b_wc_cell, b_cand, b_cnt0, b_cnt1;
   DevBuf b_status, b_red, b_levels, b_search_scratch;
-  DevBuf b_blk_wc, b_blk_meta, b_dir, b_nl, b_super_queue;
+  DevBuf b_blk_wc, b_blk_meta, b_dir, b_nl, b_super_queue, b_wcinfo, b_wcand;
   DevBuf b_pair_a, b_pair_pi;         // per-pair caches of the sweeps, parallel to the list arena (fsph_sweeps.cu)
   unsigned long long est_cand = 0, est_dir = 0, est_rows = 0;  // sizes of the previous neighbour structure (capacity estimate)
   int64_t est_n = 0;
-  int search_scratch_cap = 8192;      // candidates per CTA strip of the block search (grows on demand)
+  int search_scratch_cap = 8192;      // candidates per warp strip of the walk (grows on demand)
   bool search_tiny_done = false;      // test hook FSPH_SEARCH_TINY_CAP used up
   uint64_t search_epoch = 0;          // bumped by every neighbour search (validity of the pair caches)
   // pair caches (fsph_sweeps.cu): decided per neighbour structure; A is valid for the structure it was stored with,

@@ -50,9 +50,6 @@ constexpr int SR_CHUNK = 2048;  // super-list entries filtered per round (8 per 
 #ifndef FSPH_SR_LROWS
 #define FSPH_SR_LROWS 48
 #endif
-#ifndef FSPH_SR_HALF
-#define FSPH_SR_HALF 256
-#endif
 #ifndef FSPH_SR_OCC
 #define FSPH_SR_OCC 3
 #endif
@@ -375,435 +372,256 @@ __host__ __device__ __forceinline__ uint32_t tile_start(uint32_t n, uint32_t nt,
 }
 __host__ __device__ __forceinline__ int tile_count(uint32_t n, uint32_t nt, uint32_t ti) { return (int)(n / nt + (ti < n % nt ? 1u : 0u)); }
 
-// ---- the block kernel ---------------------------------------------------------------------------------------------
-// per work cell of a block, in shared memory
-template<int D> struct CellInfo {
+// ---- work-cell records -------------------------------------------------------------------------------------------
+// Everything the walk needs of a work cell G, computed once per search by k_wc_info (16 lanes per cell).
+template<int D> struct __align__(16) WcInfo {
   double gmn[D], gmx[D];   // node box (intersects_box_box)
   double gcom[D], glap, grad;
   double tmn[D], tmx[D];   // tight box of the cell's positions
   double hmax, hmax2;      // largest h of the cell, and its square with the safety margin of the quick reject
-  int32_t first, P;        // first thread / body count
+  int32_t first, P;        // first body / body count
   int32_t has_node;        // 0: lone leaf under a bigger node (no box test, no prefilter: tree_topology.h:326,364)
-  uint8_t rep[1 << D];     // per corner of the tight box: the nearest body of the cell (thread index)
+  uint8_t rep[1 << D];     // per corner of the tight box: the nearest body of the cell (offset from `first`)
 };
 
 struct SearchCursors {
   unsigned long long cand, dir, rows;
 };
 
-// one candidate of the current tile in shared memory
-struct __align__(16) CandRec {
-  double x[3], h2;
-};
-// dynamic shared memory of k_block_search: walk queue (node, cell mask, first child cell, leaf mask) OR candidate tile,
-// cell masks, per-warp candidate lists and per-warp list staging
-constexpr int SR_HALF = FSPH_SR_HALF;         // candidates compacted and tested per pass
-constexpr int SR_QCAPL = SR_HALF + 16;        // entries of a quarter-warp's candidate list (padded to a multiple of 16)
-constexpr int SM_CM = (NL_TILE + 1) * 32;     // + the sentinel record
-constexpr int SM_WL = SM_CM + NL_TILE * 2;
-constexpr int SM_LBUF = SM_WL + SR_NW * 4 * SR_QCAPL * 2;
-constexpr int SM_TOTAL = SM_LBUF + SR_NW * (SR_LROWS + 1) * 64;
-// walk: node, cell mask, first child cell, leaf mask per queue entry, then the leaf items of 256 entries
-constexpr int SM_QITEM = SR_CHUNK * 13;
-constexpr int SM_GX = SM_QITEM + BLK_BODIES * 8 * 6;   // positions and h of the block's bodies (walk phases only)
-constexpr int SM_QTOTAL = SM_GX + 4 * BLK_BODIES * 8;
-constexpr int block_search_smem() { return SM_TOTAL > SM_QTOTAL ? SM_TOTAL : SM_QTOTAL; }
-
-// Tight box, reach and cells of the 8 bodies of a quarter warp, in fp32 relative to the centre of the block's tight box
-// (bounds rounded outwards).  `reach` = largest h of the quarter plus the absolute error bound of the fp32 distances.
-struct QuarterBox {
-  float mn[3], mx[3], reach;
-  uint32_t cells;
-};
-
-// s0 <= h0 || s0 <= h2c [&& cellbit != 0] -> m |= bit.  Written in PTX: the compiler otherwise rewrites the two compares
-// into one against fmax() and pays for its NaN handling (~10 instructions per test).
-template<bool MULTI>
-__device__ __forceinline__ void pair_test_bit(uint32_t & m, const uint32_t bit, const double s0, const double h0, const double h2c,
-  const uint32_t cellbit) {
-  if(MULTI)
-    asm("{\n\t.reg .pred p;\n\tsetp.le.f64 p, %1, %2;\n\tsetp.le.or.f64 p, %1, %3, p;\n\tsetp.ne.and.b32 p, %5, 0, p;\n\t@p or.b32 %0, %0, %4;\n\t}"
-        : "+r"(m) : "d"(s0), "d"(h0), "d"(h2c), "r"(bit), "r"(cellbit));
-  else
-    asm("{\n\t.reg .pred p;\n\tsetp.le.f64 p, %1, %2;\n\tsetp.le.or.f64 p, %1, %3, p;\n\t@p or.b32 %0, %0, %4;\n\t}"
-        : "+r"(m) : "d"(s0), "d"(h0), "d"(h2c), "r"(bit));
-}
-
-// The pair tests of one warp on the candidates compacted for it: within_distance2(x_k, x_e, max(h_k, h_e))
-// (tree_geometry.h:265-275); max(h_k,h_e)^2 == max(h_k^2,h_e^2) exactly (rounding is monotonic), tested as
-// s <= h_k^2 || s <= h_e^2.  Every lane walks the list of its quarter warp (all four padded to nmax with the sentinel
-// record, which no body accepts) and appends the tile positions of its neighbours to its own list: row 1 + j of the
-// warp's staging area in shared memory (rows beyond SR_LROWS are counted, not stored), or, DIRECT, straight to the
-// warp's rows in global memory (slow path for lists longer than the staging area).  cnt: the lane's running count.
-template<int D, bool DIRECT, bool MULTI>
-__device__ __forceinline__ void warp_pair_tests(const CandRec * __restrict__ c4, const uint16_t * __restrict__ cm, const uint16_t * __restrict__ wlq,
-  const int nmax, const double * a0, const double h0, const uint32_t my_bit, const bool active, const int lane, uint16_t (* lrows)[32],
-  uint16_t * __restrict__ dst, int & cnt) {
-  for(int jb = 0; jb < nmax; jb += 16) {
-    uint32_t m = 0;
-#pragma unroll
-    for(int b = 0; b < 16; ++b) {
-      const int ci = wlq[jb + b];
-      const double2 xy = *reinterpret_cast<const double2 *>(&c4[ci].x[0]);
-      const double2 zh = *reinterpret_cast<const double2 *>(&c4[ci].x[2]);
-      double s0 = (a0[0] - xy.x) * (a0[0] - xy.x);
-      if(D > 1) s0 = s0 + (a0[1] - xy.y) * (a0[1] - xy.y);
-      if(D > 2) s0 = s0 + (a0[2] - zh.x) * (a0[2] - zh.x);
-      pair_test_bit<MULTI>(m, 1u << b, s0, h0, zh.y, MULTI ? (cm[ci] & my_bit) : 0u);
-    }
-    if(!active) m = 0;
-    while(m) {
-      const int b = __ffs(m) - 1;
-      m &= m - 1;
-      const uint16_t pos = wlq[jb + b];
-      if(DIRECT) dst[(1 + cnt) * 32 + lane] = pos;
-      else if(cnt < SR_LROWS) lrows[1 + cnt][lane] = pos;
-      ++cnt;
-    }
-  }
-}
-
-// The candidates [hf * SR_HALF, ...) of the staged tile that a quarter warp has to test: those of its cells that lie
-// within max(h_e, hmax_quarter) of the tight box of its 8 bodies.  The cull only has to be conservative (it drops
-// candidates no body of the quarter can pair with), so it runs in fp32 on coordinates relative to the block centre:
-// every rounding error is bounded by `feps` (a few ulps of the block extent, folded into the reach of both sides), the
-// box bounds are rounded outwards.  One candidate per lane and round, four ballots; lists in tile order, padded with
-// the sentinel record to the common length nmax (a multiple of 16), which is returned.
 template<int D>
-__device__ __forceinline__ int compact_quarters(const CandRec * __restrict__ c4, const uint16_t * __restrict__ cm, const QuarterBox * __restrict__ qb,
-  uint16_t (* wlw)[SR_QCAPL], const int hf, const int tc, const int lane, const double * bctr, const float feps) {
-  int n[4] = {0, 0, 0, 0};
-  const int i1 = min(tc, (hf + 1) * SR_HALF);
-  for(int i0 = hf * SR_HALF; i0 < i1; i0 += 32) {
-    const int i = i0 + lane;
-    const bool valid = i < i1;
-    const CandRec cr = c4[valid ? i : NL_TILE];
-    const uint32_t cmi = valid ? cm[i] : 0u;
-    float xf[D];
-#pragma unroll
-    for(int d = 0; d < D; ++d) xf[d] = (float)(cr.x[d] - bctr[d]);
-    const float hf32 = __fsqrt_ru(__double2float_ru(cr.h2)) + feps;   // >= h_e + error bound
-#pragma unroll
-    for(int q = 0; q < 4; ++q) {
-      bool pass = (cmi & qb[q].cells) != 0u;
-      float dd = 0.f;
-#pragma unroll
-      for(int d = 0; d < D; ++d) {
-        const float tt = fmaxf(0.f, fmaxf(qb[q].mn[d] - xf[d], xf[d] - qb[q].mx[d]));
-        dd = fmaf(tt, tt, dd);
-      }
-      const float rch = fmaxf(qb[q].reach, hf32);
-      pass = pass && dd <= rch * rch * 1.0001f;
-      const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-      if(pass) wlw[q][n[q] + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
-      n[q] += __popc(bal);
-    }
-  }
-  const int nmax = (max(max(n[0], n[1]), max(n[2], n[3])) + 15) & ~15;
-#pragma unroll
-  for(int q = 0; q < 4; ++q)
-    for(int j = n[q] + lane; j < nmax; j += 32) wlw[q][j] = (uint16_t)NL_TILE;
-  __syncwarp();
-  return nmax;
-}
-
-template<int D>
-__global__ void __launch_bounds__(SR_NT, FSPH_SR_OCC) k_block_search(Tree t, Cols c, Search sr, int64_t * __restrict__ scratch, int scratch_cap,
-  SearchCursors * __restrict__ cur, unsigned long long cand_cap, unsigned long long dir_cap, unsigned long long rows_cap,
-  uint32_t * __restrict__ status) {
-  constexpr int NT = SR_NT;
+__global__ void __launch_bounds__(256) k_wc_info(Tree t, Cols c, Search sr, WcInfo<D> * __restrict__ out) {
   constexpr int NCH = 1 << D;
-  __shared__ CellInfo<D> cell[BLK_CELLS];
-  __shared__ uint8_t slot_of[NT];
-  __shared__ uint32_t scan_sm[SR_NW];
-  __shared__ uint32_t wcnt[SR_CHUNK / NT][SR_NW];
-  __shared__ unsigned long long base_sm[2][2];
-  __shared__ int cmax_sm[2][SR_NW];
-  __shared__ QuarterBox qbox[SR_NW][4];
-  // the node queue of the walk and the candidate tile + list staging of the pair tests are never live together
-  extern __shared__ __align__(16) unsigned char ubuf[];   // block_search_smem() bytes
-  int32_t * const q_node = reinterpret_cast<int32_t *>(ubuf);
-  uint32_t * const q_mask = reinterpret_cast<uint32_t *>(ubuf + SR_CHUNK * 4);
-  int32_t * const q_cb = reinterpret_cast<int32_t *>(ubuf + SR_CHUNK * 8);
-  uint8_t * const q_leaf = reinterpret_cast<uint8_t *>(ubuf + SR_CHUNK * 12);
-  CandRec * const c4 = reinterpret_cast<CandRec *>(ubuf);                                    // [NL_TILE] x, y, z, h^2
-  uint16_t * const cm = reinterpret_cast<uint16_t *>(ubuf + SM_CM);                          // [NL_TILE] cell masks
-  uint16_t (* const wl)[4][SR_QCAPL] = reinterpret_cast<uint16_t (*)[4][SR_QCAPL]>(ubuf + SM_WL);   // per quarter warp: its candidates
-  double (* const gx)[NT] = reinterpret_cast<double (*)[NT]>(ubuf + SM_GX);                 // walk: the block's positions,
-  double * const gh = reinterpret_cast<double *>(ubuf + SM_GX + 3 * NT * 8);                //       and smoothing lengths
-  int32_t * const it_cell = reinterpret_cast<int32_t *>(ubuf + SM_QITEM);                   // leaf items of the walk: leaf cell,
-  uint16_t * const it_ent = reinterpret_cast<uint16_t *>(ubuf + SM_QITEM + BLK_BODIES * 8 * 4);   // ... queue entry
-  uint16_t (* const lbuf)[SR_LROWS + 1][32] = reinterpret_cast<uint16_t (*)[SR_LROWS + 1][32]>(ubuf + SM_LBUF);
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int64_t * const strip = scratch + (size_t)blockIdx.x * scratch_cap;
-
-  for(int blk = blockIdx.x; blk < sr.nblk; blk += gridDim.x) {
-    const int g0 = sr.blk_wc[blk], g1 = sr.blk_wc[blk + 1];
-    const int K = g1 - g0;
-    __syncthreads();   // the previous block is done with shared memory
-    // ---- the block's cells ---------------------------------------------------------------------------------
-    if(tid < K) {
-      const int v = t.cell[sr.wc_cell[g0 + tid]];
-      cell[tid].has_node = v < 0;
-      const int start = v >= 0 ? v : t.node_start[~v];
-      cell[tid].first = start;   // body index for now; made block-relative below
-      cell[tid].P = v >= 0 ? 1 : t.sub[~v];
-      if(v < 0) {
-        const int nd = ~v;
+  const int g = (int)((blockIdx.x * 256u + threadIdx.x) >> 4), l16 = threadIdx.x & 15;
+  const bool live = g < sr.nwc;
+  int v = 0, start = 0, P = 0;
+  if(live) {
+    v = t.cell[sr.wc_cell[g]];
+    start = v >= 0 ? v : t.node_start[~v];
+    P = v >= 0 ? 1 : t.sub[~v];
+  }
+  double tmn[D], tmx[D], hm = 0.0;
 #pragma unroll
-        for(int d = 0; d < D; ++d) { cell[tid].gmn[d] = t.bmin[d][nd]; cell[tid].gmx[d] = t.bmax[d][nd]; cell[tid].gcom[d] = t.com[d][nd]; }
-        cell[tid].glap = t.lap[nd];
-        cell[tid].grad = t.radius[nd];
-      }
+  for(int d = 0; d < D; ++d) { tmn[d] = 1.79769313486231570e308; tmx[d] = -1.79769313486231570e308; }
+  for(int k = l16; k < P; k += 16) {
+#pragma unroll
+    for(int d = 0; d < D; ++d) {
+      const double x = c.f[F_POS + d][start + k];
+      tmn[d] = fmin(tmn[d], x);
+      tmx[d] = fmax(tmx[d], x);
     }
-    __syncthreads();
-    const int body0 = cell[0].first;
-    const int PB = cell[K - 1].first + cell[K - 1].P - body0;
-    __syncthreads();
-    if(tid < K) cell[tid].first -= body0;
-    const bool active = tid < PB;
-    double a0[D], ha = 0.0;
+    hm = fmax(hm, c.f[F_H][start + k]);
+  }
 #pragma unroll
-    for(int d = 0; d < D; ++d) a0[d] = 0.0;
-    if(active) {
+  for(int o = 8; o > 0; o >>= 1) {
 #pragma unroll
-      for(int d = 0; d < D; ++d) { a0[d] = c.f[F_POS + d][body0 + tid]; gx[d][tid] = a0[d]; }
-      ha = c.f[F_H][body0 + tid];
-      gh[tid] = ha;
+    for(int d = 0; d < D; ++d) {
+      tmn[d] = fmin(tmn[d], __shfl_xor_sync(0xffffffffu, tmn[d], o));
+      tmx[d] = fmax(tmx[d], __shfl_xor_sync(0xffffffffu, tmx[d], o));
     }
-    __syncthreads();
-    // tight boxes, largest h and corner representatives of each cell: 16 threads per cell
-    {
-      const int ci = tid >> 4, l16 = tid & 15;
-      double tmn[D], tmx[D], hm = 0.0;
+    hm = fmax(hm, __shfl_xor_sync(0xffffffffu, hm, o));
+  }
+  // representative bodies: for each corner of the tight box the body of the cell nearest to it.  The "does any body
+  // sphere of G touch this node box" loop tries the representative on the node's side first (pure ordering heuristic:
+  // the outcome is the exact any-of-all-bodies result either way).
+  uint8_t rep[NCH];
 #pragma unroll
-      for(int d = 0; d < D; ++d) { tmn[d] = 1.79769313486231570e308; tmx[d] = -1.79769313486231570e308; }
-      const int cf = ci < K ? cell[ci].first : 0, cp = ci < K ? cell[ci].P : 0;
-      for(int k = l16; k < cp; k += 16) {
-#pragma unroll
-        for(int d = 0; d < D; ++d) {
-          const double x = gx[d][cf + k];
-          tmn[d] = fmin(tmn[d], x);
-          tmx[d] = fmax(tmx[d], x);
-        }
-        hm = fmax(hm, gh[cf + k]);
-        slot_of[cf + k] = (uint8_t)ci;
-      }
-#pragma unroll
-      for(int o = 8; o > 0; o >>= 1) {
-#pragma unroll
-        for(int d = 0; d < D; ++d) {
-          tmn[d] = fmin(tmn[d], __shfl_xor_sync(0xffffffffu, tmn[d], o));
-          tmx[d] = fmax(tmx[d], __shfl_xor_sync(0xffffffffu, tmx[d], o));
-        }
-        hm = fmax(hm, __shfl_xor_sync(0xffffffffu, hm, o));
-      }
-      // representative bodies: for each corner of the tight box the body of the cell nearest to it.  The "does any
-      // body sphere of G touch this node box" loop tries the representative on the node's side first (pure ordering
-      // heuristic: the outcome is the exact any-of-all-bodies result either way).
-#pragma unroll
-      for(int q = 0; q < NCH; ++q) {
-        unsigned long long key = ~0ull;
-        for(int k = l16; k < cp; k += 16) {
-          double d2 = 0.0;
-#pragma unroll
-          for(int d = 0; d < D; ++d) {
-            const double df = gx[d][cf + k] - (((q >> d) & 1) ? tmx[d] : tmn[d]);
-            d2 += df * df;
-          }
-          const unsigned long long kk = ((unsigned long long)__double_as_longlong(d2) & ~0xffull) | (unsigned long long)(cf + k);
-          key = kk < key ? kk : key;
-        }
-#pragma unroll
-        for(int o = 8; o > 0; o >>= 1) {
-          const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-          key = other < key ? other : key;
-        }
-        if(l16 == 0 && ci < K) cell[ci].rep[q] = (uint8_t)(key & 0xffull);
-      }
-      if(l16 == 0 && ci < K) {
-#pragma unroll
-        for(int d = 0; d < D; ++d) { cell[ci].tmn[d] = tmn[d]; cell[ci].tmx[d] = tmx[d]; }
-        cell[ci].hmax = hm;
-        cell[ci].hmax2 = hm * hm * (1.0 + 1e-9);
-      }
-    }
-    __syncthreads();
-    // the block's own tight box and largest h
-    double bmn[D], bmx[D], bh2;
-    {
-      double bh = 0.0;
-#pragma unroll
-      for(int d = 0; d < D; ++d) { bmn[d] = cell[0].tmn[d]; bmx[d] = cell[0].tmx[d]; }
-      bh = cell[0].hmax;
-      for(int k = 1; k < K; ++k) {
-#pragma unroll
-        for(int d = 0; d < D; ++d) { bmn[d] = fmin(bmn[d], cell[k].tmn[d]); bmx[d] = fmax(bmx[d], cell[k].tmx[d]); }
-        bh = fmax(bh, cell[k].hmax);
-      }
-      bh2 = bh * bh * (1.0 + 1e-9);
-    }
-    const int my_slot = active ? slot_of[tid] : 0;
-    // tight box, largest h and cells of every quarter warp (8 consecutive bodies): its candidates are culled with them,
-    // in fp32 relative to the centre of the block's tight box.  feps bounds the error of one fp32 coordinate difference
-    // (conversion of both operands + the subtraction): coordinates are within `ext` = block extent + reach of the centre.
-    double bctr[D];
-    float feps;
-    {
-      double ext = 0.0;
+  for(int q = 0; q < NCH; ++q) {
+    unsigned long long key = ~0ull;
+    for(int k = l16; k < P; k += 16) {
+      double d2 = 0.0;
 #pragma unroll
       for(int d = 0; d < D; ++d) {
-        bctr[d] = 0.5 * (bmn[d] + bmx[d]);
-        ext = dmax(ext, bmx[d] - bmn[d]);
+        const double df = c.f[F_POS + d][start + k] - (((q >> d) & 1) ? tmx[d] : tmn[d]);
+        d2 += df * df;
       }
-      ext = ext + 2.0 * sqrt(bh2);
-      feps = __double2float_ru(ext * 4.0e-7);   // > 3 * 2^-24 * ext * sqrt(3), with room to spare
-      double qmn[D], qmx[D], qh = active ? ha : 0.0;
-      uint32_t qc = active ? (1u << my_slot) : 0u;
-#pragma unroll
-      for(int d = 0; d < D; ++d) { qmn[d] = active ? a0[d] : 1.79769313486231570e308; qmx[d] = active ? a0[d] : -1.79769313486231570e308; }
-#pragma unroll
-      for(int o = 4; o > 0; o >>= 1) {
-#pragma unroll
-        for(int d = 0; d < D; ++d) {
-          qmn[d] = dmin(qmn[d], __shfl_xor_sync(0xffffffffu, qmn[d], o));
-          qmx[d] = dmax(qmx[d], __shfl_xor_sync(0xffffffffu, qmx[d], o));
-        }
-        qh = dmax(qh, __shfl_xor_sync(0xffffffffu, qh, o));
-        qc |= __shfl_xor_sync(0xffffffffu, qc, o);
-      }
-      if((lane & 7) == 0) {
-        QuarterBox & qb = qbox[warp][lane >> 3];
-#pragma unroll
-        for(int d = 0; d < 3; ++d) {
-          // an empty quarter (no active body) keeps cells == 0 and is never matched; its bounds only have to be finite
-          qb.mn[d] = (d < D && qc) ? __double2float_rd(qmn[d] - bctr[d]) : 0.f;
-          qb.mx[d] = (d < D && qc) ? __double2float_ru(qmx[d] - bctr[d]) : 0.f;
-        }
-        qb.reach = __double2float_ru(qh) + feps;
-        qb.cells = qc;
-      }
+      const unsigned long long kk = ((unsigned long long)__double_as_longlong(d2) & ~0xffull) | (unsigned long long)k;
+      key = kk < key ? kk : key;
     }
-    // ---- walk: filter the super cell's node list, exact cell tests, leaves -----------------------------------
+#pragma unroll
+    for(int o = 8; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+      key = other < key ? other : key;
+    }
+    rep[q] = (uint8_t)(key & 0xffull);
+  }
+  if(live && l16 == 0) {
+    WcInfo<D> w;
+#pragma unroll
+    for(int d = 0; d < D; ++d) {
+      w.tmn[d] = tmn[d];
+      w.tmx[d] = tmx[d];
+      w.gmn[d] = w.gmx[d] = w.gcom[d] = 0.0;
+    }
+    w.glap = w.grad = 0.0;
+    w.hmax = hm;
+    w.hmax2 = hm * hm * (1.0 + 1e-9);
+    w.first = start;
+    w.P = P;
+    w.has_node = v < 0;
+    if(v < 0) {
+      const int nd = ~v;
+#pragma unroll
+      for(int d = 0; d < D; ++d) { w.gmn[d] = t.bmin[d][nd]; w.gmx[d] = t.bmax[d][nd]; w.gcom[d] = t.com[d][nd]; }
+      w.glap = t.lap[nd];
+      w.grad = t.radius[nd];
+    }
+#pragma unroll
+    for(int q = 0; q < NCH; ++q) w.rep[q] = rep[q];
+    out[g] = w;
+  }
+}
+
+// ---- the walk: one warp per block ------------------------------------------------------------------------------
+// (a) the super cell's node list is filtered with the conservative test against the block's tight box, 32 nodes per
+//     round, survivors queued in shared memory (per warp);
+// (b) 32 queued nodes at a time, one per lane: the exact tests against every work cell of the block -> cell mask;
+// (c) the leaf children of the accepted nodes, one per lane: prefilter + conservative tight-box cull per accepting cell
+//     -> (leaf cell, mask) appended to the warp's strip in walk order.
+// The warps of a CTA take consecutive blocks (same super cell: its list is shared through L1); no block barriers.
+constexpr int WK_WARPS = 4;
+constexpr int WK_NT = WK_WARPS * 32;
+constexpr int WK_Q = 256;        // queued nodes per round of (b) + (c)
+constexpr int WK_ITEMS = 32 * 8; // leaf children of 32 queue entries
+template<int D> struct WalkSmem {
+  WcInfo<D> cell[BLK_CELLS];
+  int32_t q_node[WK_Q];
+  int32_t it_cell[WK_ITEMS];
+  uint16_t it_mask[WK_ITEMS];
+};
+
+template<int D>
+__global__ void __launch_bounds__(WK_NT, 8) k_block_walk(Tree t, Cols c, Search sr, const WcInfo<D> * __restrict__ wci, int64_t * __restrict__ scratch,
+  int scratch_cap, SearchCursors * __restrict__ cur, unsigned long long cand_cap, unsigned long long dir_cap, int64_t * __restrict__ wcand,
+  uint32_t * __restrict__ status) {
+  __shared__ WalkSmem<D> sm_all[WK_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  WalkSmem<D> & sm = sm_all[warp];
+  int64_t * const strip = scratch + (size_t)(blockIdx.x * WK_WARPS + warp) * scratch_cap;
+  for(int blk = blockIdx.x * WK_WARPS + warp; blk < sr.nblk; blk += gridDim.x * WK_WARPS) {
+    const int g0 = sr.blk_wc[blk], K = sr.blk_wc[blk + 1] - g0;
+    __syncwarp();
+    {
+      const uint4 * src = reinterpret_cast<const uint4 *>(wci + g0);
+      uint4 * dst = reinterpret_cast<uint4 *>(sm.cell);
+      const int n16 = K * (int)(sizeof(WcInfo<D>) / 16);
+      for(int i = lane; i < n16; i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
+    // the block's own tight box and largest h
+    double bmn[D], bmx[D], bh = 0.0;
+#pragma unroll
+    for(int d = 0; d < D; ++d) { bmn[d] = 1.79769313486231570e308; bmx[d] = -1.79769313486231570e308; }
+    if(lane < K) {
+#pragma unroll
+      for(int d = 0; d < D; ++d) { bmn[d] = sm.cell[lane].tmn[d]; bmx[d] = sm.cell[lane].tmx[d]; }
+      bh = sm.cell[lane].hmax;
+    }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for(int d = 0; d < D; ++d) {
+        bmn[d] = fmin(bmn[d], __shfl_xor_sync(0xffffffffu, bmn[d], o));
+        bmx[d] = fmax(bmx[d], __shfl_xor_sync(0xffffffffu, bmx[d], o));
+      }
+      bh = fmax(bh, __shfl_xor_sync(0xffffffffu, bh, o));
+    }
+    const double bh2 = bh * bh * (1.0 + 1e-9);
+    const int body0 = sm.cell[0].first;
+    const int PB = sm.cell[K - 1].first + sm.cell[K - 1].P - body0;
     const int sidx = sr.wc_super[g0];
     const uint64_t sl_lo = sr.sl_off[sidx];
     const int sl_n = (int)(sr.sl_off[sidx + 1] - sl_lo);
     uint32_t ncands = 0;
-    for(int lbase = 0; lbase < sl_n; lbase += SR_CHUNK) {
+    int nq = 0;
+    for(int lbase = 0; lbase < sl_n || nq > 0; lbase += 32) {
       // (a) conservative filter: node box within the block's largest h of the block's tight box (necessary for
-      //     intersects_sphere_box with any body of the block); compacted in list order
-      int ndr[SR_CHUNK / NT];
-      uint32_t flags = 0;
-#pragma unroll
-      for(int r = 0; r < SR_CHUNK / NT; ++r) {
-        const int e = lbase + r * NT + tid;
-        ndr[r] = e < sl_n ? sr.sl_nodes[sl_lo + e] : -1;
-      }
-#pragma unroll
-      for(int r = 0; r < SR_CHUNK / NT; ++r) {
+      //     intersects_sphere_box with any body of the block); queued in list order
+      if(lbase < sl_n) {
+        const int e = lbase + lane;
+        const int nd = e < sl_n ? sr.sl_nodes[sl_lo + e] : -1;
         bool ok = false;
-        if(ndr[r] >= 0) {
-          const NodeRec & rec = t.noderec[ndr[r]];
+        if(nd >= 0) {
+          const NodeRec & rec = t.noderec[nd];
           double nmn[D], nmx[D];
 #pragma unroll
           for(int d = 0; d < D; ++d) { nmn[d] = rec.bmin[d]; nmx[d] = rec.bmax[d]; }
           ok = box_gap2<D>(nmn, nmx, bmn, bmx) <= bh2;
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-        if(lane == 0) wcnt[r][warp] = __popc(bal);
-        flags |= (uint32_t)ok << r;
+        if(ok) sm.q_node[nq + __popc(bal & lt)] = nd;
+        nq += __popc(bal);
+        if(nq <= WK_Q - 32 && lbase + 32 < sl_n) continue;
       }
-      __syncthreads();
-      int nq = 0;
-      {
-        // offsets of the (round, warp) groups in list order; every thread adds up the 64 counters it needs
-        uint32_t my_off[SR_CHUNK / NT];
-        uint32_t run = 0;
+      __syncwarp();
+      for(int eb = 0; eb < nq; eb += 32) {
+        // (b) exact tests of one node per lane against every cell: intersects_box_box + any-body intersects_sphere_box
+        const int e = eb + lane;
+        uint32_t mask = 0, lmask = 0;
+        int cb = 0;
+        if(e < nq) {
+          const NodeRec & rec = t.noderec[sm.q_node[e]];
+          double nmn[D], nmx[D];
 #pragma unroll
-        for(int r = 0; r < SR_CHUNK / NT; ++r) {
+          for(int d = 0; d < D; ++d) { nmn[d] = rec.bmin[d]; nmx[d] = rec.bmax[d]; }
+          cb = rec.child_begin;
+          lmask = rec.leafmask;
+          for(int ci = 0; ci < K; ++ci) {
+            const WcInfo<D> & G = sm.cell[ci];
+            bool ok = true;
+            if(G.has_node) {
+              bool sep = false;
 #pragma unroll
-          for(int w = 0; w < SR_NW; ++w) {
-            if(w == warp) my_off[r] = run;
-            run += wcnt[r][w];
+              for(int d = 0; d < D; ++d) sep = sep || (nmx[d] < G.gmn[d]) || (G.gmx[d] < nmn[d]);
+              ok = !sep;
+            }
+            // quick reject (conservative, exact outcome): the node box is farther than hmax from every position of G
+            if(ok) ok = box_gap2<D>(nmn, nmx, G.tmn, G.tmx) <= G.hmax2;
+            if(ok) {
+              int q = 0;
+#pragma unroll
+              for(int d = 0; d < D; ++d) q |= (int)((nmn[d] + nmx[d]) > (G.tmn[d] + G.tmx[d])) << d;
+              const int kr = G.first + G.rep[q];
+              double p[D];
+#pragma unroll
+              for(int d = 0; d < D; ++d) p[d] = c.f[F_POS + d][kr];
+              bool acc = sphere_box<D>(nmn, nmx, p, c.f[F_H][kr]);
+              for(int k = G.first; k < G.first + G.P && !acc; ++k) {
+#pragma unroll
+                for(int d = 0; d < D; ++d) p[d] = c.f[F_POS + d][k];
+                acc = sphere_box<D>(nmn, nmx, p, c.f[F_H][k]);
+              }
+              ok = acc;
+            }
+            if(ok) mask |= 1u << ci;
           }
+          if(!mask) lmask = 0;
         }
-        nq = (int)run;
-        __syncthreads();   // wcnt is reused by the next chunk; q_node / q_mask are written below
+        // (c) the leaf children of the 32 entries, flattened over the lanes
+        uint32_t x = __popc(lmask);
 #pragma unroll
-        for(int r = 0; r < SR_CHUNK / NT; ++r) {
-          const bool ok = (flags >> r) & 1u;
-          const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-          if(ok) {
-            const uint32_t p = my_off[r] + __popc(bal & ((1u << lane) - 1u));
-            const NodeRec & rec = t.noderec[ndr[r]];
-            q_node[p] = ndr[r];
-            q_mask[p] = 0u;
-            q_cb[p] = rec.child_begin;
-            q_leaf[p] = (uint8_t)rec.leafmask;
-          }
+        for(int o = 1; o < 32; o <<= 1) {
+          const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+          if(lane >= o) x += y;
         }
-      }
-      __syncthreads();
-      // (b) exact tests of every (node, cell) pair: intersects_box_box + any-body intersects_sphere_box
-      for(int it = tid; it < nq * K; it += NT) {
-        const int e = it / K, ci = it - e * K;
-        const NodeRec & rec = t.noderec[q_node[e]];
-        double nmn[D], nmx[D];
-#pragma unroll
-        for(int d = 0; d < D; ++d) { nmn[d] = rec.bmin[d]; nmx[d] = rec.bmax[d]; }
-        const CellInfo<D> & G = cell[ci];
-        bool ok = true;
-        if(G.has_node) {
-          bool sep = false;
-#pragma unroll
-          for(int d = 0; d < D; ++d) sep = sep || (nmx[d] < G.gmn[d]) || (G.gmx[d] < nmn[d]);
-          ok = !sep;
-        }
-        // quick reject (conservative, exact outcome): the node box is farther than hmax from every position of G
-        if(ok) ok = box_gap2<D>(nmn, nmx, G.tmn, G.tmx) <= G.hmax2;
-        if(ok) {
-          int q = 0;
-#pragma unroll
-          for(int d = 0; d < D; ++d) q |= (int)((nmn[d] + nmx[d]) > (G.tmn[d] + G.tmx[d])) << d;
-          const int kr = G.rep[q];
-          double p[D];
-#pragma unroll
-          for(int d = 0; d < D; ++d) p[d] = gx[d][kr];
-          bool acc = sphere_box<D>(nmn, nmx, p, gh[kr]);
-          for(int k = G.first; k < G.first + G.P && !acc; ++k) {
-#pragma unroll
-            for(int d = 0; d < D; ++d) p[d] = gx[d][k];
-            acc = sphere_box<D>(nmn, nmx, p, gh[k]);
-          }
-          ok = acc;
-        }
-        if(ok) atomicOr(&q_mask[e], 1u << ci);
-      }
-      __syncthreads();
-      // (c) leaf children of the accepted nodes -> candidates (leaf cell index, mask of the cells that take it), in
-      //     queue order.  256 queue entries at a time list their leaf children (scan), then one leaf per thread.
-      for(int eb = 0; eb < nq; eb += NT) {
-        const int e = eb + tid;
-        const uint32_t lmask = (e < nq && q_mask[e]) ? (uint32_t)q_leaf[e] : 0u;
-        uint32_t nitem;
-        uint32_t off = block_scan_u32<NT>(__popc(lmask), nitem, scan_sm);
+        const int nitem = (int)__shfl_sync(0xffffffffu, x, 31);
+        uint32_t off = x - __popc(lmask);
         for(uint32_t rest = lmask; rest; rest &= rest - 1) {
-          it_cell[off] = q_cb[e] + (__ffs(rest) - 1);
-          it_ent[off] = (uint16_t)e;
+          sm.it_cell[off] = cb + (__ffs(rest) - 1);
+          sm.it_mask[off] = (uint16_t)mask;
           ++off;
         }
-        __syncthreads();
-        for(uint32_t ib = 0; ib < nitem; ib += NT) {
-          const uint32_t it = ib + tid;
+        __syncwarp();
+        for(int ib = 0; ib < nitem; ib += 32) {
+          const int it = ib + lane;
           uint32_t m = 0;
           int cidx = 0;
           if(it < nitem) {
-            cidx = it_cell[it];
+            cidx = sm.it_cell[it];
             const LeafRec lr = t.leafrec[cidx];
-            for(uint32_t rest = q_mask[it_ent[it]]; rest; rest &= rest - 1) {
+            for(uint32_t rest = sm.it_mask[it]; rest; rest &= rest - 1) {
               const int ci = __ffs(rest) - 1;
-              const CellInfo<D> & G = cell[ci];
+              const WcInfo<D> & G = sm.cell[ci];
               bool pass = true;
               if(G.has_node) {
                 // |x_e - X_G|^2 <= (max(h_e, lap_G) + radius_G)^2, tree_topology.h:365-370
@@ -830,179 +648,365 @@ __global__ void __launch_bounds__(SR_NT, FSPH_SR_OCC) k_block_search(Tree t, Col
               if(pass) m |= 1u << ci;
             }
           }
-          uint32_t total;
-          const uint32_t pos = ncands + block_scan_u32<NT>(m != 0u ? 1u : 0u, total, scan_sm);
+          const uint32_t bal = __ballot_sync(0xffffffffu, m != 0u);
+          const uint32_t pos = ncands + __popc(bal & lt);
           if(m && pos < (uint32_t)scratch_cap) strip[pos] = ((int64_t)m << 32) | (uint32_t)cidx;
-          ncands += total;
+          ncands += __popc(bal);
         }
-        __syncthreads();   // the item list is rewritten by the next 256 entries
+        __syncwarp();
       }
-      __syncthreads();
+      nq = 0;
     }
-    // ---- reserve the block's share of the candidate array and the tile directory --------------------------------
+    // ---- the block's share of the candidate array and of the tile directory -------------------------------------
     const int ntile = (int)((ncands + NL_TILE - 1) / NL_TILE);
-    bool overflow = ncands > (uint32_t)scratch_cap;
-    if(tid == 0) {
-      base_sm[0][0] = atomicAdd(&cur->cand, (unsigned long long)ncands);
-      base_sm[0][1] = atomicAdd(&cur->dir, (unsigned long long)ntile);
-      if(overflow) atomicOr(status, (uint32_t)ERR_QUEUE_OVERFLOW);
+    unsigned long long co = 0, dir0 = 0;
+    if(lane == 0) {
+      co = atomicAdd(&cur->cand, (unsigned long long)ncands);
+      dir0 = atomicAdd(&cur->dir, (unsigned long long)ntile);
+    }
+    co = __shfl_sync(0xffffffffu, co, 0);
+    dir0 = __shfl_sync(0xffffffffu, dir0, 0);
+    const bool strip_over = ncands > (uint32_t)scratch_cap;
+    const bool overflow = strip_over || co + ncands > cand_cap || dir0 + ntile > dir_cap;
+    if(lane == 0) {
+      if(strip_over) atomicOr(status, (uint32_t)ERR_QUEUE_OVERFLOW);
+      else if(overflow) atomicOr(status, (uint32_t)ERR_SEARCH_CAPACITY);
+      sr.blk_cand_off[blk] = co;
+      sr.blk_dir_off[blk] = dir0;
+      sr.blk_ncand[blk] = overflow ? -1 : (int32_t)ncands;
+      sr.blk_body[blk] = body0;
+      sr.blk_nbody[blk] = PB;
+    }
+    if(!overflow)
+      for(uint32_t i = lane; i < ncands; i += 32) wcand[co + i] = strip[i];
+  }
+}
+
+// ---- the pair kernel -----------------------------------------------------------------------------------------------
+// One CTA of 256 threads per block, one body per thread.  The block's candidates (walk order, from k_block_walk) are
+// dealt to tiles of <= NL_TILE round-robin and staged in shared memory -- all tiles at once, SR_GROUP tiles per group
+// for the rare bigger blocks -- as 16-byte records: fp32 coordinates relative to the centre of the block's tight box and
+// fp32 h^2.  After that the warps are independent: per tile a warp compacts per quarter warp the candidates within reach
+// (compact_quarters), tests them (warp_pair_tests), reserves its own rows with one atomicAdd and copies its staged lists
+// out; no block barrier inside the tile loop.
+//
+// The pair predicate within_distance2(x_k, x_e, max(h_k, h_e)) (tree_geometry.h:265-275) is decided in fp32 with a
+// rigorous error bound, and re-evaluated exactly in fp64 only where fp32 cannot decide:
+//   u = 2^-24, M = max |coordinate - centre| over the block's bodies and the staged candidates, Hm = their largest h.
+//   Every fp32 coordinate difference d32 is within e1 = 4.01 u M of the true difference (two conversions + one
+//   subtraction), so for any pair with sqrt(s) <= Rm = 1.001 Hm + 2 e1 the fp32 sum s32 of the three squares (mul, fma,
+//   fma: 3 roundings of positive terms) satisfies |s32 - s| <= e1 (2 sqrt(3) Rm + 3 e1) + 3.1 u Rm^2 < EB - 4.9 u Rm^2,
+//   EB = e1 (2 sqrt(3) Rm + 3 e1) + 8 u Rm^2.  With t32 = max(fl32(h_k^2), fl32(h_e^2)):
+//     s32 <= t32 - EB  =>  s <= max(h_k^2, h_e^2)   (accepted; the remaining 1.9 u Rm^2 absorb the roundings of t32,
+//     s32 >  t32 + EB  =>  s >  max(h_k^2, h_e^2)   (rejected)   t32 -+ EB and of the fp64 evaluation itself)
+//   and the band in between (relative width ~ 30 u M / Hm: one pair in ~10^5) goes to the exact fp64 test, evaluated
+//   operation by operation as the reference does.
+struct __align__(16) CandRec {
+  float x[3], h2;
+};
+constexpr int SR_GROUP = 3;                   // tiles staged together
+constexpr int SR_CAP = SR_GROUP * NL_TILE;    // candidate records in shared memory (+ the sentinel)
+constexpr int SR_WCAPL = NL_TILE + 16;        // entries of a warp's candidate list (padded to a multiple of 16)
+constexpr int SM_CM = (SR_CAP + 1) * 16;      // + the sentinel record
+constexpr int SM_WL = SM_CM + ((SR_CAP + 1) * 2 + 15) / 16 * 16;
+constexpr int SM_LBUF = SM_WL + SR_NW * SR_WCAPL * 2;
+constexpr int SM_TOTAL = SM_LBUF + SR_NW * (SR_LROWS + 1) * 64;
+constexpr int block_pairs_smem() { return SM_TOTAL; }
+
+// The pair tests of one warp on the candidates compacted for it.  Every lane walks the warp's list (padded to a multiple
+// of 16 with the sentinel record, which no body accepts) and appends the tile positions of its neighbours to its own
+// list: row 1 + j of the warp's staging area in shared memory (rows beyond SR_LROWS are counted, not stored), or,
+// DIRECT, straight to the warp's rows in global memory (slow path for lists longer than the staging area).
+// cnt: the lane's running count.  cidx: the body indices of the tile's candidates (for the exact re-evaluation).
+template<int D, bool DIRECT, bool MULTI>
+__device__ __forceinline__ void warp_pair_tests(const CandRec * __restrict__ c4, const uint16_t * __restrict__ cm, const uint16_t * __restrict__ wlw,
+  const int nmax, const float * af, const float h0f, const float EB, const double * a0, const double h0, const Cols & c,
+  const int32_t * __restrict__ cidx, const uint32_t my_bit, const bool active, const int lane, uint16_t (* lrows)[32],
+  uint16_t * __restrict__ dst, int & cnt) {
+  for(int jb = 0; jb < nmax; jb += 16) {
+    uint32_t m = 0;
+    bool amb = false;
+#pragma unroll
+    for(int b = 0; b < 16; ++b) {
+      const int ci = wlw[jb + b];
+      const float4 r = *reinterpret_cast<const float4 *>(&c4[ci]);
+      const float dx = af[0] - r.x;
+      float s = dx * dx;
+      if(D > 1) { const float dy = af[1] - r.y; s = fmaf(dy, dy, s); }
+      if(D > 2) { const float dz = af[2] - r.z; s = fmaf(dz, dz, s); }
+      const float dd = s - fmaxf(h0f, r.w);
+      bool in = dd <= EB;
+      if(MULTI) in = in && (cm[ci] & my_bit) != 0u;
+      if(in) m |= 1u << b;
+      amb = amb || fabsf(dd) <= EB;
+    }
+    if(!active) { m = 0; amb = false; }
+    if(amb) {
+      // fp32 cannot decide some pair of this round: those within the band are re-evaluated with the exact predicate,
+      // (dx^2 + dy^2) + dz^2 <= max(h_k, h_e)^2 in fp64 (max(h_k,h_e)^2 == max(h_k^2,h_e^2) exactly: rounding is monotonic)
+      for(uint32_t rest = m; rest; rest &= rest - 1) {
+        const int b = __ffs(rest) - 1;
+        const int ci = wlw[jb + b];
+        const float4 r = *reinterpret_cast<const float4 *>(&c4[ci]);
+        const float dx = af[0] - r.x;
+        float s = dx * dx;
+        if(D > 1) { const float dy = af[1] - r.y; s = fmaf(dy, dy, s); }
+        if(D > 2) { const float dz = af[2] - r.z; s = fmaf(dz, dz, s); }
+        if(s - fmaxf(h0f, r.w) < -EB) continue;   // decided: inside
+        const int e = cidx[ci];
+        double s0 = (a0[0] - c.f[F_POS][e]) * (a0[0] - c.f[F_POS][e]);
+        if(D > 1) s0 = s0 + (a0[1] - c.f[F_POS + 1][e]) * (a0[1] - c.f[F_POS + 1][e]);
+        if(D > 2) s0 = s0 + (a0[2] - c.f[F_POS + 2][e]) * (a0[2] - c.f[F_POS + 2][e]);
+        const double he = c.f[F_H][e];
+        if(!(s0 <= h0 || s0 <= he * he)) m &= ~(1u << b);
+      }
+    }
+    while(m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      const uint16_t pos = wlw[jb + b];
+      if(DIRECT) dst[(1 + cnt) * 32 + lane] = pos;
+      else if(cnt < SR_LROWS) lrows[1 + cnt][lane] = pos;
+      ++cnt;
+    }
+  }
+}
+
+// The candidates of a staged tile that a warp has to test: those of its cells that lie within max(h_e, hmax_warp) of
+// the tight box of its bodies.  The cull only has to be conservative (it drops candidates no body of the warp can pair
+// with); every rounding error of the fp32 coordinates is bounded by `feps` (added to the reach), the box bounds are
+// rounded outwards.  One candidate per lane and round; the list is in tile order, padded with the sentinel record to a
+// multiple of 16 (the padded length is returned).  c4 / cm point at the tile's first record, `sentinel` is the index of
+// the sentinel relative to it.
+template<int D>
+__device__ __forceinline__ int compact_warp(const CandRec * __restrict__ c4, const uint16_t * __restrict__ cm, const float * wmn, const float * wmx,
+  const float wreach, const uint32_t wcells, uint16_t * __restrict__ wlw, const int tc, const int lane, const int sentinel, const float feps) {
+  int n = 0;
+  for(int i0 = 0; i0 < tc; i0 += 32) {
+    const int i = i0 + lane;
+    const bool valid = i < tc;
+    const float4 cr = *reinterpret_cast<const float4 *>(&c4[valid ? i : sentinel]);
+    const uint32_t cmi = valid ? cm[i] : 0u;
+    const float xf[3] = {cr.x, cr.y, cr.z};
+    const float rch = fmaxf(wreach, __fsqrt_ru(fmaxf(cr.w, 0.f))) + feps;   // max(h_e, hmax_warp) + error bound
+    float dd = 0.f;
+#pragma unroll
+    for(int d = 0; d < D; ++d) {
+      const float tt = fmaxf(0.f, fmaxf(wmn[d] - xf[d], xf[d] - wmx[d]));
+      dd = fmaf(tt, tt, dd);
+    }
+    const bool pass = (cmi & wcells) != 0u && dd <= rch * rch * 1.0001f;
+    const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+    if(pass) wlw[n + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
+    n += __popc(bal);
+  }
+  const int nmax = (n + 15) & ~15;
+  for(int j = n + lane; j < nmax; j += 32) wlw[j] = (uint16_t)sentinel;
+  __syncwarp();
+  return nmax;
+}
+
+template<int D>
+__global__ void __launch_bounds__(SR_NT, FSPH_SR_OCC) k_block_pairs(Tree t, Cols c, Search sr, const WcInfo<D> * __restrict__ wci,
+  const int64_t * __restrict__ wcand, SearchCursors * __restrict__ cur, unsigned long long rows_cap, uint32_t * __restrict__ status) {
+  constexpr int NT = SR_NT;
+  __shared__ int32_t cfirst[BLK_CELLS];
+  __shared__ double cbox[BLK_CELLS][2 * D];
+  __shared__ float red_sm[2][SR_NW];
+  extern __shared__ __align__(16) unsigned char ubuf[];   // block_pairs_smem() bytes
+  CandRec * const c4 = reinterpret_cast<CandRec *>(ubuf);                                    // [SR_CAP + 1] x, y, z, h^2
+  uint16_t * const cm = reinterpret_cast<uint16_t *>(ubuf + SM_CM);                          // [SR_CAP + 1] cell masks
+  uint16_t (* const wl)[SR_WCAPL] = reinterpret_cast<uint16_t (*)[SR_WCAPL]>(ubuf + SM_WL);   // per warp: its candidates of the tile
+  uint16_t (* const lbuf)[SR_LROWS + 1][32] = reinterpret_cast<uint16_t (*)[SR_LROWS + 1][32]>(ubuf + SM_LBUF);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if(tid == 0) {
+    // the sentinel record that pads the candidate lists: accepted by nobody (s = inf)
+    CandRec r;
+    r.x[0] = r.x[1] = r.x[2] = 1e30f;
+    r.h2 = -1.f;
+    c4[SR_CAP] = r;
+    cm[SR_CAP] = 0;
+  }
+  for(int blk = blockIdx.x; blk < sr.nblk; blk += gridDim.x) {
+    const int ncand_s = sr.blk_ncand[blk];
+    if(ncand_s < 0) continue;   // did not fit (the search is repeated)
+    const uint32_t ncands = (uint32_t)ncand_s;
+    const int g0 = sr.blk_wc[blk], K = sr.blk_wc[blk + 1] - g0;
+    const int body0 = sr.blk_body[blk], PB = sr.blk_nbody[blk];
+    const unsigned long long co = sr.blk_cand_off[blk], dir0 = sr.blk_dir_off[blk];
+    const int64_t * const strip = wcand + co;
+    __syncthreads();   // the previous block is done with shared memory
+    if(tid < K) {
+      const WcInfo<D> & w = wci[g0 + tid];
+      cfirst[tid] = w.first - body0;
+#pragma unroll
+      for(int d = 0; d < D; ++d) { cbox[tid][d] = w.tmn[d]; cbox[tid][D + d] = w.tmx[d]; }
+    }
+    const bool active = tid < PB;
+    double a0[D], ha = 0.0;
+#pragma unroll
+    for(int d = 0; d < D; ++d) a0[d] = 0.0;
+    if(active) {
+#pragma unroll
+      for(int d = 0; d < D; ++d) a0[d] = c.f[F_POS + d][body0 + tid];
+      ha = c.f[F_H][body0 + tid];
+    }
+    const int ntile = (int)((ncands + NL_TILE - 1) / NL_TILE);
+    // Candidates leave the walk in runs of key-neighbours.  They are dealt to the tiles round-robin (walk position i
+    // goes to tile i % ntile, slot i / ntile): every tile then holds an even sample of the whole neighbourhood, so all
+    // bodies of the block find about the same number of neighbours in it and the lanes of the pair loops stay busy
+    // together; tile ti starts at co + tile_start(ti) and holds tile_count(ti) candidates.
+    for(uint32_t i = tid; i < ncands; i += NT) {
+      const uint32_t ti = i % (uint32_t)ntile, p = i / (uint32_t)ntile;
+      sr.cand[co + tile_start(ncands, ntile, ti) + p] = t.cell[(uint32_t)strip[i]];
     }
     __syncthreads();
-    const unsigned long long co = base_sm[0][0], dir0 = base_sm[0][1];
-    if(co + ncands > cand_cap || dir0 + ntile > dir_cap) overflow = true;
-    if(!overflow) {
-      if(tid == 0) {
-        sr.blk_cand_off[blk] = co;
-        sr.blk_dir_off[blk] = dir0;
-        sr.blk_ncand[blk] = (int32_t)ncands;
-        sr.blk_body[blk] = body0;
-        sr.blk_nbody[blk] = PB;
-      }
-      // Candidates leave the walk in runs of key-neighbours.  They are dealt to the tiles round-robin (walk position i
-      // goes to tile i % ntile, slot i / ntile): every tile then holds an even sample of the whole neighbourhood, so all
-      // bodies of the block find about the same number of neighbours in it and the lanes of the pair loops stay busy
-      // together; tile ti starts at co + tile_start(ti) and holds tile_count(ti) candidates.
-      for(uint32_t i = tid; i < ncands; i += NT) {
-        const uint32_t ti = i % (uint32_t)ntile, p = i / (uint32_t)ntile;
-        sr.cand[co + tile_start(ncands, ntile, ti) + p] = t.cell[(uint32_t)strip[i]];
-      }
+    // the block's tight box and the cell of each body
+    double bmn[D], bmx[D];
+#pragma unroll
+    for(int d = 0; d < D; ++d) { bmn[d] = cbox[0][d]; bmx[d] = cbox[0][D + d]; }
+    int my_slot = 0;
+    for(int k = 1; k < K; ++k) {
+#pragma unroll
+      for(int d = 0; d < D; ++d) { bmn[d] = fmin(bmn[d], cbox[k][d]); bmx[d] = fmax(bmx[d], cbox[k][D + d]); }
+      my_slot += cfirst[k] <= tid;
     }
-    // ---- pair tests, tile by tile -----------------------------------------------------------------------------
-    // Two block barriers per tile: S1 (tile staged, row base of the previous tile known) -> the warps copy their
-    // staged lists of the previous tile out, then test this tile -> S2 (tests done: the tile buffers are free) ->
-    // thread 0 reserves the rows of this tile while everybody stages the next one.
+    double bctr[D];
+#pragma unroll
+    for(int d = 0; d < D; ++d) bctr[d] = 0.5 * (bmn[d] + bmx[d]);
+    float af[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for(int d = 0; d < D; ++d) af[d] = active ? (float)(a0[d] - bctr[d]) : 0.f;
     const double h0 = ha * ha;
+    const float h0f = (float)h0;
     const int nwarp_act = (PB + 31) >> 5;
-    const bool no_strip = ncands > (uint32_t)scratch_cap;
     // cells of this warp's bodies
     uint32_t warp_cells = active ? (1u << my_slot) : 0u;
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) warp_cells |= __shfl_xor_sync(0xffffffffu, warp_cells, o);
     const bool multi = (warp_cells & (warp_cells - 1u)) != 0u;
     const uint32_t my_bit = 1u << my_slot;
-    if(tid == 0) {
-      // the sentinel record that pads the candidate lists: accepted by nobody
-      CandRec r;
-      r.x[0] = r.x[1] = r.x[2] = 1e300;
-      r.h2 = -1.0;
-      c4[NL_TILE] = r;
+    // tight box and largest h of the warp's bodies, in fp32 relative to the block centre (bounds rounded outwards)
+    float wmn[3] = {0.f, 0.f, 0.f}, wmx[3] = {0.f, 0.f, 0.f}, wreach;
+    {
+      double qmn[D], qmx[D], qh = active ? ha : 0.0;
+#pragma unroll
+      for(int d = 0; d < D; ++d) { qmn[d] = active ? a0[d] : 1.79769313486231570e308; qmx[d] = active ? a0[d] : -1.79769313486231570e308; }
+#pragma unroll
+      for(int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for(int d = 0; d < D; ++d) {
+          qmn[d] = dmin(qmn[d], __shfl_xor_sync(0xffffffffu, qmn[d], o));
+          qmx[d] = dmax(qmx[d], __shfl_xor_sync(0xffffffffu, qmx[d], o));
+        }
+        qh = dmax(qh, __shfl_xor_sync(0xffffffffu, qh, o));
+      }
+#pragma unroll
+      for(int d = 0; d < D; ++d) {
+        // a warp without bodies is never used; its bounds only have to be finite
+        wmn[d] = warp_cells ? __double2float_rd(qmn[d] - bctr[d]) : 0.f;
+        wmx[d] = warp_cells ? __double2float_ru(qmx[d] - bctr[d]) : 0.f;
+      }
+      wreach = __double2float_ru(qh);
     }
-    auto stage = [&](const int ti) {
-      const int tc = no_strip ? 0 : tile_count(ncands, ntile, ti);
-      for(int i = tid; i < NL_TILE; i += NT) {
-        if(i < tc) {
-          const int64_t sv = strip[(size_t)i * ntile + ti];
+    bool overflow = false;
+    int nn = 0;
+    for(int t0 = 0; t0 < ntile; t0 += SR_GROUP) {
+      const int t1 = min(ntile, t0 + SR_GROUP);
+      const uint32_t gbase = tile_start(ncands, ntile, t0);
+      if(t0 > 0) __syncthreads();   // the previous group's records are no longer read
+      // ---- stage the group: record j <-> candidate co + gbase + j (tile-major) -------------------------------
+      float mloc = 0.f, hloc = h0f;
+#pragma unroll
+      for(int d = 0; d < D; ++d) mloc = fmaxf(mloc, fabsf(af[d]));
+      for(int ti = t0; ti < t1; ++ti) {
+        const uint32_t tb = tile_start(ncands, ntile, ti) - gbase;
+        const int tc = tile_count(ncands, ntile, ti);
+        for(int slot = tid; slot < tc; slot += NT) {
+          const int64_t sv = strip[(size_t)slot * ntile + ti];
           const LeafRec lr = t.leafrec[(uint32_t)sv];
           CandRec r;
-          r.x[0] = lr.x[0]; r.x[1] = lr.x[1]; r.x[2] = lr.x[2];
-          r.h2 = lr.h * lr.h;
-          c4[i] = r;
-          cm[i] = (uint16_t)(sv >> 32);
-        }
-        else cm[i] = 0;
-      }
-    };
-    // the warp's rows of tile ti -> global memory (and the tile's directory entry)
-    auto copy_out = [&](const int ti, const int cnt, const int cmax) {
-      const int par = ti & 1;
-      const unsigned long long row0 = base_sm[par][0];
-      if(row0 + base_sm[par][1] > rows_cap) overflow = true;
-      if(overflow) return;
-      if(tid == 0) {
-        TileDir td;
-        td.row0 = row0;
+          r.x[0] = r.x[1] = r.x[2] = 0.f;
 #pragma unroll
-        for(int w = 0; w < SR_NW; ++w) td.cmax[w] = (uint16_t)(cmax_sm[par][w] < 0 ? 0 : cmax_sm[par][w]);
-        td.pad = 0;
-        sr.dir[dir0 + ti] = td;
+          for(int d = 0; d < D; ++d) {
+            r.x[d] = (float)(lr.x[d] - bctr[d]);
+            mloc = fmaxf(mloc, fabsf(r.x[d]));
+          }
+          r.h2 = (float)(lr.h * lr.h);
+          hloc = fmaxf(hloc, r.h2);
+          c4[tb + slot] = r;
+          cm[tb + slot] = (uint16_t)(sv >> 32);
+        }
       }
-      if(warp < nwarp_act) {
-        unsigned long long rb = row0;
-        for(int w = 0; w < warp; ++w) rb += 1 + cmax_sm[par][w];
-        uint16_t * dst = sr.nl + rb * 32;
-        // rows past a lane's own count are zeroed (the sweeps read whole rows)
-        for(int j = 0; j <= cmax; ++j) dst[j * 32 + lane] = j <= cnt ? lbuf[warp][j][lane] : (uint16_t)0;
+#pragma unroll
+      for(int o = 16; o > 0; o >>= 1) {
+        mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, o));
+        hloc = fmaxf(hloc, __shfl_xor_sync(0xffffffffu, hloc, o));
       }
-    };
-    int nn = 0, cnt_prev = 0, cmax_prev = 0;
-    bool copied_prev = true;
-    if(ntile > 0) stage(0);
-    for(int ti = 0; ti < ntile; ++ti) {
-      const int par = ti & 1;
-      __syncthreads();   // S1
-      if(!copied_prev) copy_out(ti - 1, cnt_prev, cmax_prev);
-      const int tc = no_strip ? 0 : tile_count(ncands, ntile, ti);
-      int cnt = 0;
+      if(lane == 0) { red_sm[0][warp] = mloc; red_sm[1][warp] = hloc; }
+      __syncthreads();
+#pragma unroll
+      for(int w = 0; w < SR_NW; ++w) { mloc = fmaxf(mloc, red_sm[0][w]); hloc = fmaxf(hloc, red_sm[1][w]); }
+      // error bounds of the fp32 arithmetic (header comment)
+      float EB, feps;
+      {
+        const double u = 5.9604644775390625e-8;   // 2^-24
+        const double M = (double)mloc, Hm = sqrt((double)hloc) * (1.0 + 1e-6);
+        const double e1 = 4.01 * u * M;
+        const double Rm = 1.001 * Hm + 2.0 * e1;
+        EB = __double2float_ru((e1 * (3.4641016151377553 * Rm + 3.0 * e1) + 8.0 * u * Rm * Rm) * 1.0001);
+        feps = __double2float_ru(1.1 * 1.7320508075688774 * e1 + 2e-7 * Hm);
+      }
+      // ---- the warp's tiles of this group: no block barrier from here on ----------------------------------------
       if(warp < nwarp_act) {
-        for(int hf = 0; hf * SR_HALF < tc; ++hf) {
-          const int nmax = compact_quarters<D>(c4, cm, qbox[warp], wl[warp], hf, tc, lane, bctr, feps);
-          if(multi) warp_pair_tests<D, false, true>(c4, cm, wl[warp][lane >> 3], nmax, a0, h0, my_bit, active, lane, lbuf[warp], nullptr, cnt);
-          else warp_pair_tests<D, false, false>(c4, cm, wl[warp][lane >> 3], nmax, a0, h0, my_bit, active, lane, lbuf[warp], nullptr, cnt);
+        for(int ti = t0; ti < t1; ++ti) {
+          const uint32_t tb = tile_start(ncands, ntile, ti);
+          const int tc = tile_count(ncands, ntile, ti);
+          const CandRec * const tc4 = c4 + (tb - gbase);
+          const uint16_t * const tcm = cm + (tb - gbase);
+          const int sentinel = SR_CAP - (int)(tb - gbase);
+          const int32_t * const cidx = sr.cand + co + tb;
+          int cnt = 0;
+          const int nmax = compact_warp<D>(tc4, tcm, wmn, wmx, wreach, warp_cells, wl[warp], tc, lane, sentinel, feps);
+          if(multi) warp_pair_tests<D, false, true>(tc4, tcm, wl[warp], nmax, af, h0f, EB, a0, h0, c, cidx, my_bit, active, lane, lbuf[warp], nullptr, cnt);
+          else warp_pair_tests<D, false, false>(tc4, tcm, wl[warp], nmax, af, h0f, EB, a0, h0, c, cidx, my_bit, active, lane, lbuf[warp], nullptr, cnt);
           __syncwarp();
-        }
-        lbuf[warp][0][lane] = (uint16_t)cnt;
-      }
-      nn += cnt;
-      const int cmax = __reduce_max_sync(0xffffffffu, cnt);
-      if(lane == 0) cmax_sm[par][warp] = warp < nwarp_act ? cmax : -1;
-      __syncthreads();   // S2
-      bool any_spill = false;
-#pragma unroll
-      for(int w = 0; w < SR_NW; ++w) any_spill = any_spill || cmax_sm[par][w] > SR_LROWS;
-      if(tid == 0) {
-        unsigned long long rows = 0;
-        for(int w = 0; w < nwarp_act; ++w) rows += 1 + cmax_sm[par][w];
-        base_sm[par][0] = atomicAdd(&cur->rows, rows);
-        base_sm[par][1] = rows;
-      }
-      if(any_spill) {
-        // a lane has more neighbours in this tile than the staging area holds (rare): finish the tile now, while its
-        // candidates are still in shared memory; warps with long lists redo their tests and write straight to their rows
-        __syncthreads();
-        const bool spilled = cmax > SR_LROWS;
-        if(!spilled) copy_out(ti, cnt, cmax);
-        else {
-          const unsigned long long row0 = base_sm[par][0];
-          if(row0 + base_sm[par][1] > rows_cap) overflow = true;
+          lbuf[warp][0][lane] = (uint16_t)cnt;
+          nn += cnt;
+          const int cmax = __reduce_max_sync(0xffffffffu, cnt);
+          // the warp's rows of this tile: 1 + cmax (row 0: the lanes' counts)
+          unsigned long long rb = 0;
+          if(lane == 0) rb = atomicAdd(&cur->rows, (unsigned long long)(1 + cmax));
+          rb = __shfl_sync(0xffffffffu, rb, 0);
+          if(rb + 1 + cmax > rows_cap) overflow = true;
+          __syncwarp();
           if(!overflow) {
-            unsigned long long rb = row0;
-            for(int w = 0; w < warp; ++w) rb += 1 + cmax_sm[par][w];
+            if(lane == 0) sr.dir[dir0 + ti].row[warp] = (uint32_t)rb;
             uint16_t * dst = sr.nl + rb * 32;
-            dst[lane] = (uint16_t)cnt;
-            for(int j = cnt + 1; j <= cmax; ++j) dst[j * 32 + lane] = (uint16_t)0;
-            int k = 0;
-            for(int hf = 0; hf * SR_HALF < tc; ++hf) {
-              const int nmax = compact_quarters<D>(c4, cm, qbox[warp], wl[warp], hf, tc, lane, bctr, feps);
-              warp_pair_tests<D, true, true>(c4, cm, wl[warp][lane >> 3], nmax, a0, h0, my_bit, active, lane, nullptr, dst, k);
-              __syncwarp();
+            if(cmax <= SR_LROWS) {
+              // rows past a lane's own count are zeroed (the sweeps read whole rows)
+              for(int j = 0; j <= cmax; ++j) dst[j * 32 + lane] = j <= cnt ? lbuf[warp][j][lane] : (uint16_t)0;
+            }
+            else {
+              // a lane has more neighbours in this tile than the staging area holds (rare): the tests are repeated,
+              // writing straight to the rows
+              dst[lane] = (uint16_t)cnt;
+              for(int j = cnt + 1; j <= cmax; ++j) dst[j * 32 + lane] = (uint16_t)0;
+              int k = 0;
+              warp_pair_tests<D, true, true>(tc4, tcm, wl[warp], nmax, af, h0f, EB, a0, h0, c, cidx, my_bit, active, lane, nullptr, dst, k);
             }
           }
+          __syncwarp();
         }
-        // the directory entry is written by thread 0 inside copy_out; if thread 0's own warp took the slow path, here
-        if(tid == 0 && spilled && !overflow) {
-          TileDir td;
-          td.row0 = base_sm[par][0];
-#pragma unroll
-          for(int w = 0; w < SR_NW; ++w) td.cmax[w] = (uint16_t)(cmax_sm[par][w] < 0 ? 0 : cmax_sm[par][w]);
-          td.pad = 0;
-          sr.dir[dir0 + ti] = td;
-        }
-        copied_prev = true;
-        __syncthreads();
       }
       else {
-        copied_prev = false;
-        cnt_prev = cnt;
-        cmax_prev = cmax;
+        // warps without bodies own no rows
+        for(int ti = t0 + lane; ti < t1; ti += 32) sr.dir[dir0 + ti].row[warp] = 0u;
       }
-      if(ti + 1 < ntile) stage(ti + 1);
-    }
-    if(!copied_prev) {
-      __syncthreads();
-      copy_out(ntile - 1, cnt_prev, cmax_prev);
     }
     if(active && !overflow) c.nneigh[body0 + tid] = nn;
-    if(overflow && tid == 0) atomicOr(status, (uint32_t)ERR_SEARCH_CAPACITY);
+    if(overflow && lane == 0) atomicOr(status, (uint32_t)ERR_SEARCH_CAPACITY);
   }
 }
 
@@ -1025,10 +1029,18 @@ static void neighbor_search_t(System & s) {
   sr.blk_body = sr.blk_ncand + nblk;
   sr.blk_nbody = sr.blk_body + nblk;
   SearchCursors * cursors = reinterpret_cast<SearchCursors *>(s.b_status.as<uint32_t>() + 8);
-  const int grid = std::min(nblk, 148 * FSPH_SR_OCC * 2);
+  // per work cell: boxes, largest h, corner representatives
+  s.b_wcinfo.reserve((size_t)sr.nwc * sizeof(WcInfo<D>));
+  WcInfo<D> * wci = s.b_wcinfo.as<WcInfo<D>>();
+  {
+    PhaseScope ph(s, "search:cells");
+    FSPH_LAUNCH((k_wc_info<D>), (unsigned)((sr.nwc + 15) / 16), 256, s.stream, s.tree, s.cols(), sr, wci);
+  }
+  const int walk_grid = std::min((nblk + WK_WARPS - 1) / WK_WARPS, 148 * 8);
+  const int pair_grid = std::min(nblk, 148 * FSPH_SR_OCC * 2);
   int scratch_cap = s.search_scratch_cap;
   // capacities: from the previous search of this system (scaled when the body count drifts, e.g. with ghosts), else a
-  // first guess; a search that does not fit still counts, and is repeated once with the exact sizes
+  // first guess; a search that does not fit still counts, and is repeated with the exact sizes
   unsigned long long cand_cap, dir_cap, rows_cap;
   if(s.est_cand > 0 && s.est_n > 0) {
     const double r = std::max(1.0, (double)s.n / (double)s.est_n);
@@ -1046,15 +1058,24 @@ static void neighbor_search_t(System & s) {
   }
   for(int attempt = 0;; ++attempt) {
     s.b_cand.reserve((size_t)cand_cap * 4);
+    s.b_wcand.reserve((size_t)cand_cap * 8);
     s.b_dir.reserve((size_t)dir_cap * sizeof(TileDir));
     s.b_nl.reserve((size_t)rows_cap * 64);
-    s.b_search_scratch.reserve((size_t)grid * scratch_cap * 8);
+    s.b_search_scratch.reserve((size_t)walk_grid * WK_WARPS * scratch_cap * 8);
     sr.cand = s.b_cand.as<int32_t>();
     sr.dir = s.b_dir.as<TileDir>();
     sr.nl = s.b_nl.as<uint16_t>();
     FSPH_CUDA_OK(cudaMemsetAsync(cursors, 0, sizeof(SearchCursors), s.stream));
-    FSPH_LAUNCH_SMEM((k_block_search<D>), grid, SR_NT, block_search_smem(), s.stream, s.tree, s.cols(), sr,
-      s.b_search_scratch.as<int64_t>(), scratch_cap, cursors, cand_cap, dir_cap, rows_cap, status);
+    {
+      PhaseScope ph(s, "search:walk");
+      FSPH_LAUNCH((k_block_walk<D>), walk_grid, WK_NT, s.stream, s.tree, s.cols(), sr, wci, s.b_search_scratch.as<int64_t>(), scratch_cap, cursors,
+        cand_cap, dir_cap, s.b_wcand.as<int64_t>(), status);
+    }
+    {
+      PhaseScope ph(s, "search:pairs");
+      FSPH_LAUNCH_SMEM((k_block_pairs<D>), pair_grid, SR_NT, block_pairs_smem(), s.stream, s.tree, s.cols(), sr, wci, s.b_wcand.as<int64_t>(), cursors,
+        rows_cap, status);
+    }
     SearchCursors tot;
     uint32_t st = 0;
     FSPH_CUDA_OK(cudaMemcpyAsync(&tot, cursors, sizeof(tot), cudaMemcpyDeviceToHost, s.stream));
@@ -1072,6 +1093,8 @@ static void neighbor_search_t(System & s) {
         std::vector<int32_t> nb(nblk), nc(nblk);
         FSPH_CUDA_OK(cudaMemcpy(nb.data(), sr.blk_nbody, (size_t)nblk * 4, cudaMemcpyDeviceToHost));
         FSPH_CUDA_OK(cudaMemcpy(nc.data(), sr.blk_ncand, (size_t)nblk * 4, cudaMemcpyDeviceToHost));
+        std::vector<uint64_t> so(sr.nsuper + 1);
+        FSPH_CUDA_OK(cudaMemcpy(so.data(), sr.sl_off, (size_t)(sr.nsuper + 1) * 8, cudaMemcpyDeviceToHost));
         double sb = 0, sc = 0, sw = 0;
         int full = 0;
         for(int b = 0; b < nblk; ++b) { sb += nb[b]; sc += nc[b]; sw += (nb[b] + 31) / 32; full += nb[b] > 224; }
@@ -1079,27 +1102,29 @@ static void neighbor_search_t(System & s) {
         FSPH_CUDA_OK(cudaMemcpy(nn.data(), s.col_nneigh.p, (size_t)s.n * 4, cudaMemcpyDeviceToHost));
         double sn = 0;
         for(int64_t i = 0; i < s.n; ++i) sn += nn[i];
-        fprintf(stderr, "[search] n %lld nwc %d nsuper %d nblk %d bodies/block %.1f (>224: %.0f%%) warps/block %.2f cands/block %.0f tiles %llu rows %llu "
-                        "pairs %.4g slot efficiency %.3f\n", (long long)s.n, sr.nwc, sr.nsuper, nblk, sb / nblk, 100.0 * full / nblk, sw / nblk, sc / nblk,
-          (unsigned long long)tot.dir, (unsigned long long)tot.rows, sn, sn / ((double)tot.rows * 32));
+        fprintf(stderr, "[search] n %lld nwc %d nsuper %d (list %.0f nodes) nblk %d bodies/block %.1f (>224: %.0f%%) warps/block %.2f cands/block %.0f "
+                        "tiles %llu rows %llu pairs %.4g slot efficiency %.3f\n", (long long)s.n, sr.nwc, sr.nsuper, (double)so[sr.nsuper] / sr.nsuper,
+          nblk, sb / nblk, 100.0 * full / nblk, sw / nblk, sc / nblk, (unsigned long long)tot.dir, (unsigned long long)tot.rows, sn,
+          sn / ((double)tot.rows * 32));
       }
       return;
     }
     const uint32_t cleared = st & ~(uint32_t)(ERR_SEARCH_CAPACITY | ERR_QUEUE_OVERFLOW);
     FSPH_CUDA_OK(cudaMemcpyAsync(status, &cleared, 4, cudaMemcpyHostToDevice, s.stream));
     FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
-    if(attempt >= 6) throw std::runtime_error("neighbour search: capacity retry did not converge");
+    if(attempt >= 8) throw std::runtime_error("neighbour search: capacity retry did not converge");
     if(st & ERR_QUEUE_OVERFLOW) {
-      // a block has more candidates than its scratch strip holds (very wide kernels): grow the strips
+      // a block has more candidates than a walk strip holds (very wide kernels): grow the strips
       if(scratch_cap >= (1 << 20)) throw std::runtime_error("neighbour search: a block has more than 2^20 candidates");
       scratch_cap *= 4;
       s.search_scratch_cap = scratch_cap;
       continue;
     }
-    // the cursors counted everything: exact sizes
+    // the cursors counted every candidate and tile; the rows only of the blocks whose candidates fitted
+    const bool walk_fitted = tot.cand <= cand_cap && tot.dir <= dir_cap;
     cand_cap = tot.cand + 64;
     dir_cap = tot.dir + 64;
-    rows_cap = tot.rows + 64;
+    if(walk_fitted) rows_cap = tot.rows + 64;
   }
 }
 
@@ -1121,12 +1146,7 @@ __global__ void __launch_bounds__(SR_NT) k_export(Cols c, Search sr, const uint6
   const uint64_t co = sr.blk_cand_off[blk];
   uint64_t o = off[sr.blk_body[blk] + tid];
   for(int ti = 0; ti < ntile; ++ti) {
-    const TileDir td = sr.dir[sr.blk_dir_off[blk] + ti];
-    uint64_t rb = td.row0;
-#pragma unroll
-    for(int w = 0; w < SR_NW; ++w)
-      if(w < warp && w < nwarp_act) rb += 1 + td.cmax[w];
-    const uint16_t * rows = sr.nl + rb * 32;
+    const uint16_t * rows = sr.nl + (uint64_t)sr.dir[sr.blk_dir_off[blk] + ti].row[warp] * 32;
     const int cnt = rows[lane];
     const uint64_t tb = co + tile_start((uint32_t)sr.blk_ncand[blk], (uint32_t)ntile, (uint32_t)ti);
     for(int j = 0; j < cnt; ++j) ids[o++] = c.id[sr.cand[tb + rows[(1 + j) * 32 + lane]]];

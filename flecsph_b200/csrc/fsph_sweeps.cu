@@ -595,16 +595,10 @@ __global__ void __launch_bounds__(BLK_BODIES, SweepOcc<OP>::MINB) k_sweep(Cols c
     const int tb = ti * tq + min(ti, tr);
     const int tc = tq + (ti < tr ? 1 : 0);
     // this warp's rows of the tile
-    const TileDir td = sr.dir[dir0 + ti];
-    uint64_t rb = td.row0;
-    int cmax = 0;
-#pragma unroll
-    for(int w = 0; w < NT / 32; ++w) {
-      if(w < warp) rb += 1 + td.cmax[w];
-      if(w == warp && warp < nwarp_act) cmax = td.cmax[w];
-    }
+    const uint64_t rb = warp < nwarp_act ? sr.dir[dir0 + ti].row[warp] : 0u;
     const uint16_t * rows = sr.nl + rb * 32 + lane;
     const int cnt = warp < nwarp_act ? rows[0] : 0;
+    const int cmax = __reduce_max_sync(0xffffffffu, cnt);
     __syncthreads();
     {
       // all candidate indices of this thread first, then the column gathers: 2 x NF loads in flight

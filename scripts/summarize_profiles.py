@@ -76,11 +76,11 @@ def traffic():
                  "msecond": 1.0, "ms": 1.0, "second": 1e3}.get(u, 1)
         per.setdefault(k, {})[r[mi]] = v * scale
     phases = {}
-    order = ["search", "density", "acceleration", "dedt"]     # launch order of the captured window
+    order = ["search_walk", "search", "density", "acceleration", "dedt"]     # launch order of the captured window
     for (k, m), ph in zip(per.items(), order):
         phases[ph] = m.get("dram__bytes_read.sum", 0) + m.get("dram__bytes_write.sum", 0)
         print(ph, k[:60], {a: "%.4g" % b for a, b in m.items()})
-    json.dump({"how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:k_block_search|k_sweep -s 16 -c 4 "
+    json.dump({"how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:k_block_walk|k_block_pairs|k_sweep -s 20 -c 5 "
                       "python bench.py --particles %s --steps 1 --warmup 3 --no-e2e --no-cpu --no-configs" % what,
                "unit": "bytes per launch (read + write)", "phases": phases,
                "kernels": {ph: {"kernel": k, **m} for (k, m), ph in zip(per.items(), order)}},
@@ -129,5 +129,5 @@ def full(name):
 os.makedirs(out, exist_ok=True)
 launch_list()
 traffic()
-for k in ("search", "density", "accv", "dedt"):
+for k in ("search", "walk", "density", "accv", "dedt"):
     full(k)
