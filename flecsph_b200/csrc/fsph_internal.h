@@ -109,6 +109,21 @@ struct Tree {
 constexpr int BLK_BODIES = 256;   // bodies per block = threads per CTA of the search and the sweeps
 constexpr int BLK_CELLS = 16;     // work cells per block (bits of a candidate's cell mask)
 constexpr int NL_TILE = 512;      // candidates per list tile (tile-local positions fit 16 bits)
+// A block's candidates (walk order) are cut into chunks of NL_CHUNK; every chunk is sorted by micro-cell and dealt to
+// its <= NL_CHUNK_TILES tiles round-robin (fsph_search.cu).  Tile ti of a block with C candidates covers the candidate
+// positions [tb, tb + tc) of the block:
+constexpr int NL_CHUNK_TILES = 3;
+constexpr int NL_CHUNK = NL_CHUNK_TILES * NL_TILE;
+__host__ __device__ inline int nl_ntiles(int C) { return (C / NL_CHUNK) * NL_CHUNK_TILES + ((C % NL_CHUNK) + NL_TILE - 1) / NL_TILE; }
+__host__ __device__ inline void nl_tile_range(int C, int ti, int & tb, int & tc) {
+  const int ch = ti / NL_CHUNK_TILES, tj = ti - ch * NL_CHUNK_TILES;
+  const int base = ch * NL_CHUNK;
+  const int n = C - base < NL_CHUNK ? C - base : NL_CHUNK;
+  const int nt = (n + NL_TILE - 1) / NL_TILE;
+  const int q = n / nt, r = n % nt;
+  tb = base + tj * q + (tj < r ? tj : r);
+  tc = q + (tj < r ? 1 : 0);
+}
 struct __align__(16) TileDir {
   uint32_t row[8];     // per warp: its first row of the tile in the list arena (it owns 1 + the longest list of its lanes)
 };
@@ -130,7 +145,8 @@ struct Search {
   int32_t * blk_ncand;     // [nblk] candidates of the block
   int32_t * blk_body;      // [nblk] first body
   int32_t * blk_nbody;     // [nblk] bodies (thread k of the block's CTA <-> body blk_body + k)
-  int32_t * cand;          // candidate particle indices, block after block, in walk order
+  float * blk_hmax;        // [nblk] largest h among the block's candidates (rounded up)
+  int32_t * cand;          // candidate particle indices, block after block, tile after tile
   TileDir * dir;           // one entry per (block, tile)
   uint16_t * nl;           // list arena: rows of 32 uint16; per (tile, warp): row 0 = the lanes' counts, row 1 + j = the
                            // tile-local position of each lane's j-th neighbour

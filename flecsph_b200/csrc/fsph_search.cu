@@ -46,7 +46,6 @@ constexpr int SW_QCAP = 16384;  // node frontier capacity per level of the super
 constexpr int SW_NT = 256;      // threads per CTA of the super-cell walk
 constexpr int SR_NT = BLK_BODIES;
 constexpr int SR_NW = SR_NT / 32;
-constexpr int SR_CHUNK = 2048;  // super-list entries filtered per round (8 per thread)
 #ifndef FSPH_SR_LROWS
 #define FSPH_SR_LROWS 48
 #endif
@@ -365,13 +364,6 @@ static void build_super_lists(System & s) {
   FSPH_CUDA_OK(cudaGetLastError());
 }
 
-// tile ti of a block with n candidates in nt tiles (dealt round-robin): its first candidate and its size
-__host__ __device__ __forceinline__ uint32_t tile_start(uint32_t n, uint32_t nt, uint32_t ti) {
-  const uint32_t q = n / nt, r = n % nt;
-  return ti * q + (ti < r ? ti : r);
-}
-__host__ __device__ __forceinline__ int tile_count(uint32_t n, uint32_t nt, uint32_t ti) { return (int)(n / nt + (ti < n % nt ? 1u : 0u)); }
-
 // ---- work-cell records -------------------------------------------------------------------------------------------
 // Everything the walk needs of a work cell G, computed once per search by k_wc_info (16 lanes per cell).
 template<int D> struct __align__(16) WcInfo {
@@ -475,8 +467,9 @@ __global__ void __launch_bounds__(256) k_wc_info(Tree t, Cols c, Search sr, WcIn
 // (a) the super cell's node list is filtered with the conservative test against the block's tight box, 32 nodes per
 //     round, survivors queued in shared memory (per warp);
 // (b) 32 queued nodes at a time, one per lane: the exact tests against every work cell of the block -> cell mask;
-// (c) the leaf children of the accepted nodes, one per lane: prefilter + conservative tight-box cull per accepting cell
-//     -> (leaf cell, mask) appended to the warp's strip in walk order.
+// (c) the leaf children of the accepted nodes, one per lane: per cell a conservative reach test against the cell's tight
+//     box, then (accepting cells only) the prefilter -> (leaf cell, mask of the cells it is a candidate of, flag: within
+//     reach of a cell that does not take it) appended to the warp's strip in walk order.
 // The warps of a CTA take consecutive blocks (same super cell: its list is shared through L1); no block barriers.
 constexpr int WK_WARPS = 4;
 constexpr int WK_NT = WK_WARPS * 32;
@@ -534,6 +527,7 @@ __global__ void __launch_bounds__(WK_NT, 8) k_block_walk(Tree t, Cols c, Search 
     const int sl_n = (int)(sr.sl_off[sidx + 1] - sl_lo);
     uint32_t ncands = 0;
     int nq = 0;
+    double hcand = 0.0;   // largest h among the candidates
     for(int lbase = 0; lbase < sl_n || nq > 0; lbase += 32) {
       // (a) conservative filter: node box within the block's largest h of the block's tight box (necessary for
       //     intersects_sphere_box with any body of the block); queued in list order
@@ -616,14 +610,24 @@ __global__ void __launch_bounds__(WK_NT, 8) k_block_walk(Tree t, Cols c, Search 
           const int it = ib + lane;
           uint32_t m = 0;
           int cidx = 0;
+          bool excl = false;
           if(it < nitem) {
             cidx = sm.it_cell[it];
             const LeafRec lr = t.leafrec[cidx];
-            for(uint32_t rest = sm.it_mask[it]; rest; rest &= rest - 1) {
-              const int ci = __ffs(rest) - 1;
+            const uint32_t nmask = sm.it_mask[it];
+            for(int ci = 0; ci < K; ++ci) {
               const WcInfo<D> & G = sm.cell[ci];
-              bool pass = true;
-              if(G.has_node) {
+              // reach (conservative): some body of G may lie within max(h_e, hmax_G) of the leaf
+              const double hm = dmax(lr.h, G.hmax);
+              double dd = 0.0;
+#pragma unroll
+              for(int d = 0; d < D; ++d) {
+                const double tt = dmax(0.0, dmax(G.tmn[d] - lr.x[d], lr.x[d] - G.tmx[d]));
+                dd = dd + tt * tt;
+              }
+              if(!(dd <= hm * hm * (1.0 + 1e-9))) continue;
+              bool incl = (nmask >> ci) & 1u;
+              if(incl && G.has_node) {
                 // |x_e - X_G|^2 <= (max(h_e, lap_G) + radius_G)^2, tree_topology.h:365-370
                 const double ext = dmax(lr.h, G.glap) + G.grad;
                 double s2 = 0.0;
@@ -632,21 +636,14 @@ __global__ void __launch_bounds__(WK_NT, 8) k_block_walk(Tree t, Cols c, Search 
                   const double df = lr.x[d] - G.gcom[d];
                   s2 = d == 0 ? df * df : s2 + df * df;
                 }
-                pass = s2 <= ext * ext;
+                incl = s2 <= ext * ext;
               }
-              if(pass) {
-                // conservative cull: no body of G is within max(h_e, hmax_G) of the leaf
-                const double hm = dmax(lr.h, G.hmax);
-                double dd = 0.0;
-#pragma unroll
-                for(int d = 0; d < D; ++d) {
-                  const double tt = dmax(0.0, dmax(G.tmn[d] - lr.x[d], lr.x[d] - G.tmx[d]));
-                  dd = dd + tt * tt;
-                }
-                pass = dd <= hm * hm * (1.0 + 1e-9);
-              }
-              if(pass) m |= 1u << ci;
+              // within reach of G but not one of G's candidates in the reference: the pair kernel has to consult the mask
+              if(incl) m |= 1u << ci;
+              else excl = true;
             }
+            if(m) hcand = dmax(hcand, lr.h);
+            if(m && excl) m |= 1u << 16;
           }
           const uint32_t bal = __ballot_sync(0xffffffffu, m != 0u);
           const uint32_t pos = ncands + __popc(bal & lt);
@@ -658,7 +655,9 @@ __global__ void __launch_bounds__(WK_NT, 8) k_block_walk(Tree t, Cols c, Search 
       nq = 0;
     }
     // ---- the block's share of the candidate array and of the tile directory -------------------------------------
-    const int ntile = (int)((ncands + NL_TILE - 1) / NL_TILE);
+    const int ntile = nl_ntiles((int)ncands);
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) hcand = fmax(hcand, __shfl_xor_sync(0xffffffffu, hcand, o));
     unsigned long long co = 0, dir0 = 0;
     if(lane == 0) {
       co = atomicAdd(&cur->cand, (unsigned long long)ncands);
@@ -676,7 +675,9 @@ __global__ void __launch_bounds__(WK_NT, 8) k_block_walk(Tree t, Cols c, Search 
       sr.blk_ncand[blk] = overflow ? -1 : (int32_t)ncands;
       sr.blk_body[blk] = body0;
       sr.blk_nbody[blk] = PB;
+      sr.blk_hmax[blk] = __double2float_ru(hcand);
     }
+    __syncwarp();
     if(!overflow)
       for(uint32_t i = lane; i < ncands; i += 32) wcand[co + i] = strip[i];
   }
@@ -684,126 +685,196 @@ __global__ void __launch_bounds__(WK_NT, 8) k_block_walk(Tree t, Cols c, Search 
 
 // ---- the pair kernel -----------------------------------------------------------------------------------------------
 // One CTA of 256 threads per block, one body per thread.  The block's candidates (walk order, from k_block_walk) are
-// dealt to tiles of <= NL_TILE round-robin and staged in shared memory -- all tiles at once, SR_GROUP tiles per group
-// for the rare bigger blocks -- as 16-byte records: fp32 coordinates relative to the centre of the block's tight box and
-// fp32 h^2.  After that the warps are independent: per tile a warp compacts per quarter warp the candidates within reach
-// (compact_quarters), tests them (warp_pair_tests), reserves its own rows with one atomicAdd and copies its staged lists
-// out; no block barrier inside the tile loop.
+// processed in chunks of NL_CHUNK (almost always one).  A chunk is staged in shared memory as 16-byte records -- fp32
+// coordinates relative to the centre of the block's tight box, fp32 h^2 -- SORTED by the cell of a small uniform grid
+// laid over the block's neighbourhood (cell size ~ half the largest h; rows along x are contiguous in the sorted
+// order) and dealt to the chunk's tiles round-robin by sorted position, so that every tile is an even sample of the
+// whole neighbourhood and a row of the grid is a contiguous run of slots in every tile.  After that the warps are
+// independent (no block barrier inside the tile loop): every lane walks, tile by tile, the rows of the grid that its
+// own sphere of reach touches -- about (2 h + cell)^3 candidates instead of the union over a group of bodies, without any
+// compaction pass -- appends the tile slots of its neighbours to its list in the warp's staging area, and the warp
+// reserves its rows of the tile with one atomicAdd and copies the staged lists out.
 //
 // The pair predicate within_distance2(x_k, x_e, max(h_k, h_e)) (tree_geometry.h:265-275) is decided in fp32 with a
 // rigorous error bound, and re-evaluated exactly in fp64 only where fp32 cannot decide:
-//   u = 2^-24, M = max |coordinate - centre| over the block's bodies and the staged candidates, Hm = their largest h.
-//   Every fp32 coordinate difference d32 is within e1 = 4.01 u M of the true difference (two conversions + one
-//   subtraction), so for any pair with sqrt(s) <= Rm = 1.001 Hm + 2 e1 the fp32 sum s32 of the three squares (mul, fma,
-//   fma: 3 roundings of positive terms) satisfies |s32 - s| <= e1 (2 sqrt(3) Rm + 3 e1) + 3.1 u Rm^2 < EB - 4.9 u Rm^2,
+//   u = 2^-24; M bounds |coordinate - centre| of the block's bodies and candidates (half extent of the tight box +
+//   Hm: a candidate lies within max(h_e, hmax_G) of a cell's tight box), Hm = the largest h among them.  Every fp32
+//   coordinate difference d32 is within e1 = 4.01 u M of the true difference (two conversions + one subtraction), so
+//   for any pair with sqrt(s) <= Rm = 1.001 Hm + 2 e1 the fp32 sum s32 of the three squares (mul, fma, fma: 3 roundings
+//   of positive terms) satisfies |s32 - s| <= e1 (2 sqrt(3) Rm + 3 e1) + 3.1 u Rm^2 < EB - 4.9 u Rm^2,
 //   EB = e1 (2 sqrt(3) Rm + 3 e1) + 8 u Rm^2.  With t32 = max(fl32(h_k^2), fl32(h_e^2)):
-//     s32 <= t32 - EB  =>  s <= max(h_k^2, h_e^2)   (accepted; the remaining 1.9 u Rm^2 absorb the roundings of t32,
-//     s32 >  t32 + EB  =>  s >  max(h_k^2, h_e^2)   (rejected)   t32 -+ EB and of the fp64 evaluation itself)
+//     s32 - t32 < -EB  =>  s <= max(h_k^2, h_e^2)   (accepted; the remaining 1.9 u Rm^2 absorb the roundings of t32,
+//     s32 - t32 >  EB  =>  s >  max(h_k^2, h_e^2)   (rejected)   of the difference and of the fp64 evaluation itself)
 //   and the band in between (relative width ~ 30 u M / Hm: one pair in ~10^5) goes to the exact fp64 test, evaluated
 //   operation by operation as the reference does.
+// A candidate that lies within reach of a work cell of the block without being one of that cell's candidates in the
+// reference (possible with unequal h: the reference's node tests are not conservative) carries a flag -- the sign of
+// its h^2 -- and only for those the cell mask is consulted.
 struct __align__(16) CandRec {
   float x[3], h2;
 };
-constexpr int SR_GROUP = 3;                   // tiles staged together
-constexpr int SR_CAP = SR_GROUP * NL_TILE;    // candidate records in shared memory (+ the sentinel)
-constexpr int SR_WCAPL = NL_TILE + 16;        // entries of a warp's candidate list (padded to a multiple of 16)
-constexpr int SM_CM = (SR_CAP + 1) * 16;      // + the sentinel record
-constexpr int SM_WL = SM_CM + ((SR_CAP + 1) * 2 + 15) / 16 * 16;
-constexpr int SM_LBUF = SM_WL + SR_NW * SR_WCAPL * 2;
+constexpr int SR_CAP = NL_CHUNK;              // candidate records in shared memory (+ the sentinel)
+constexpr int SR_NCELL = 2048;                // cells of the grid (at most)
+constexpr int SR_CST = SR_NCELL + 16;         // entries of a tile's cell table
+constexpr int SM_CM = (SR_CAP + 1) * 16;
+constexpr int SM_CS = SM_CM + (SR_CAP + 8) * 2;
+constexpr int SM_LBUF = SM_CS + NL_CHUNK_TILES * SR_CST * 2;
 constexpr int SM_TOTAL = SM_LBUF + SR_NW * (SR_LROWS + 1) * 64;
+// during the sort the list staging area holds the cell counters / cursors and the sorted walk positions
+constexpr int SM_CNT = SM_LBUF;
+constexpr int SM_WIDX = SM_CNT + SR_CST * 4;
+static_assert(SM_WIDX + SR_CAP * 2 <= SM_TOTAL, "sort scratch does not fit the list staging area");
 constexpr int block_pairs_smem() { return SM_TOTAL; }
 
-// The pair tests of one warp on the candidates compacted for it.  Every lane walks the warp's list (padded to a multiple
-// of 16 with the sentinel record, which no body accepts) and appends the tile positions of its neighbours to its own
-// list: row 1 + j of the warp's staging area in shared memory (rows beyond SR_LROWS are counted, not stored), or,
-// DIRECT, straight to the warp's rows in global memory (slow path for lists longer than the staging area).
-// cnt: the lane's running count.  cidx: the body indices of the tile's candidates (for the exact re-evaluation).
-template<int D, bool DIRECT, bool MULTI>
-__device__ __forceinline__ void warp_pair_tests(const CandRec * __restrict__ c4, const uint16_t * __restrict__ cm, const uint16_t * __restrict__ wlw,
-  const int nmax, const float * af, const float h0f, const float EB, const double * a0, const double h0, const Cols & c,
-  const int32_t * __restrict__ cidx, const uint32_t my_bit, const bool active, const int lane, uint16_t (* lrows)[32],
-  uint16_t * __restrict__ dst, int & cnt) {
-  for(int jb = 0; jb < nmax; jb += 16) {
-    uint32_t m = 0;
-    bool amb = false;
+// the grid of a chunk and the division by the chunk's tile count
+struct PairGrid {
+  float org[3], invc;     // origin (relative to the block centre), 1 / cell size
+  int nx, ny, nz;
+};
+
+template<int D>
+__device__ __forceinline__ int grid_cell(const PairGrid & g, const float * x) {
+  int cidx = 0;
 #pragma unroll
-    for(int b = 0; b < 16; ++b) {
-      const int ci = wlw[jb + b];
-      const float4 r = *reinterpret_cast<const float4 *>(&c4[ci]);
+  for(int d = D - 1; d >= 0; --d) {
+    const int n = d == 0 ? g.nx : (d == 1 ? g.ny : g.nz);
+    int i = (int)floorf((x[d] - g.org[d]) * g.invc);
+    i = min(max(i, 0), n - 1);
+    cidx = cidx * n + i;
+  }
+  return cidx;
+}
+
+// The pair tests of one lane on a tile of the staged chunk: the rows (iy, iz) of the grid within reach, and in each row
+// the slots of the tile that belong to the cells [cx0, cx1] (cst: first slot of each cell in this tile).  All lanes of
+// the warp run the loop together, each on its own rows: a lane that has used up its row takes the next one in the same
+// iteration (predicated), a lane whose row is empty sits the iteration out on the sentinel record.  Neighbours' slots
+// go to row 1 + j of the lane's column of the warp's staging area (rows beyond SR_LROWS are counted, not stored).
+// Optimistic: a pair is taken when the fp32 predicate does not exclude it; the return value tells whether any of the
+// lane's decisions needs the careful version below (a pair inside the error band, or a flagged candidate accepted).
+// shared-memory accesses of the hot loop through 32-bit shared-window addresses (the generic-pointer forms make the
+// compiler rebuild the window base inside the loop)
+__device__ __forceinline__ float4 lds_f4(const uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(const uint32_t a) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u16(const uint32_t a, const uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((uint16_t)v));
+}
+
+template<int D>
+__device__ __forceinline__ bool lane_pair_tests_fast(const CandRec * __restrict__ c4, const int sentinel, const uint16_t * __restrict__ cst,
+  const PairGrid & g, const int cx0, const int cx1, const int cy0, const int cy1, const int cz0, const int cz1, const float * af, const float h0f,
+  const float EB, const bool active, uint16_t * const lcol, int & cnt) {
+  const uint32_t rec0 = (uint32_t)__cvta_generic_to_shared(c4);
+  const uint32_t sent = rec0 + (uint32_t)sentinel * 16u;
+  const uint32_t hioff = (uint32_t)(cx1 + 1 - cx0) * 2u;                // from a row's first cell of the lane to one past its last
+  const uint32_t rowstep = (uint32_t)g.nx * 2u;
+  const uint32_t wrapstep = (uint32_t)((g.ny - (cy1 - cy0)) * g.nx) * 2u;   // from the last row of a z-slab to the first of the next
+  uint32_t row = (uint32_t)__cvta_generic_to_shared(cst) + (uint32_t)((cz0 * g.ny + cy0 - 1) * g.nx + cx0) * 2u;   // the row before the first
+  int yleft = 0, zleft = cz1 - cz0 + 1;       // rows left in the current z-slab, z-slabs left (including the current one)
+  const int ny_lane = cy1 - cy0 + 1;
+  uint32_t cur = 0, end = 0;
+  bool done = !active;
+  const uint32_t l0 = (uint32_t)__cvta_generic_to_shared(lcol), lmax = l0 + SR_LROWS * 64u;
+  uint32_t lp = l0;
+  float amin = 3.0e38f;
+  int fb = 0;
+  // before the first row: yleft == 0 makes the first advance open the first z-slab
+  row -= wrapstep - rowstep;
+  // a lane that has run out of rows parks on an empty row (both ends read from the table's first entry)
+  const uint32_t park = (uint32_t)__cvta_generic_to_shared(cst);
+  if(done) zleft = 0;
+  for(;;) {
+#pragma unroll
+    for(int rep = 0; rep < 4; ++rep) {
+      if(cur >= end) {
+        const bool wrap = yleft == 0;
+        row += wrap ? wrapstep : rowstep;
+        yleft = wrap ? ny_lane - 1 : yleft - 1;
+        zleft -= wrap ? 1 : 0;
+        const bool out = zleft < 0;
+        row = out ? park : row;
+        cur = lds_u16(row);
+        end = lds_u16(row + (out ? 0u : hioff));
+      }
+      const bool valid = cur < end;
+      const float4 r = lds_f4(valid ? rec0 + cur * 16u : sent);
       const float dx = af[0] - r.x;
       float s = dx * dx;
       if(D > 1) { const float dy = af[1] - r.y; s = fmaf(dy, dy, s); }
       if(D > 2) { const float dz = af[2] - r.z; s = fmaf(dz, dz, s); }
-      const float dd = s - fmaxf(h0f, r.w);
-      bool in = dd <= EB;
-      if(MULTI) in = in && (cm[ci] & my_bit) != 0u;
-      if(in) m |= 1u << b;
-      amb = amb || fabsf(dd) <= EB;
+      const float dd = s - fmaxf(h0f, fabsf(r.w));
+      amin = fminf(amin, fabsf(dd));
+      const bool in = dd <= EB;
+      if(in) fb |= __float_as_int(r.w);
+      if(in && lp < lmax) sts_u16(lp, cur);
+      lp += in ? 64u : 0u;
+      cur += valid ? 1u : 0u;
     }
-    if(!active) { m = 0; amb = false; }
-    if(amb) {
-      // fp32 cannot decide some pair of this round: those within the band are re-evaluated with the exact predicate,
-      // (dx^2 + dy^2) + dz^2 <= max(h_k, h_e)^2 in fp64 (max(h_k,h_e)^2 == max(h_k^2,h_e^2) exactly: rounding is monotonic)
-      for(uint32_t rest = m; rest; rest &= rest - 1) {
-        const int b = __ffs(rest) - 1;
-        const int ci = wlw[jb + b];
-        const float4 r = *reinterpret_cast<const float4 *>(&c4[ci]);
-        const float dx = af[0] - r.x;
-        float s = dx * dx;
-        if(D > 1) { const float dy = af[1] - r.y; s = fmaf(dy, dy, s); }
-        if(D > 2) { const float dz = af[2] - r.z; s = fmaf(dz, dz, s); }
-        if(s - fmaxf(h0f, r.w) < -EB) continue;   // decided: inside
-        const int e = cidx[ci];
-        double s0 = (a0[0] - c.f[F_POS][e]) * (a0[0] - c.f[F_POS][e]);
-        if(D > 1) s0 = s0 + (a0[1] - c.f[F_POS + 1][e]) * (a0[1] - c.f[F_POS + 1][e]);
-        if(D > 2) s0 = s0 + (a0[2] - c.f[F_POS + 2][e]) * (a0[2] - c.f[F_POS + 2][e]);
-        const double he = c.f[F_H][e];
-        if(!(s0 <= h0 || s0 <= he * he)) m &= ~(1u << b);
-      }
-    }
-    while(m) {
-      const int b = __ffs(m) - 1;
-      m &= m - 1;
-      const uint16_t pos = wlw[jb + b];
-      if(DIRECT) dst[(1 + cnt) * 32 + lane] = pos;
-      else if(cnt < SR_LROWS) lrows[1 + cnt][lane] = pos;
-      ++cnt;
-    }
+    if(__all_sync(0xffffffffu, zleft < 0)) break;
   }
+  cnt = (int)((lp - l0) >> 6);
+  return amin <= EB || fb < 0;
 }
 
-// The candidates of a staged tile that a warp has to test: those of its cells that lie within max(h_e, hmax_warp) of
-// the tight box of its bodies.  The cull only has to be conservative (it drops candidates no body of the warp can pair
-// with); every rounding error of the fp32 coordinates is bounded by `feps` (added to the reach), the box bounds are
-// rounded outwards.  One candidate per lane and round; the list is in tile order, padded with the sentinel record to a
-// multiple of 16 (the padded length is returned).  c4 / cm point at the tile's first record, `sentinel` is the index of
-// the sentinel relative to it.
-template<int D>
-__device__ __forceinline__ int compact_warp(const CandRec * __restrict__ c4, const uint16_t * __restrict__ cm, const float * wmn, const float * wmx,
-  const float wreach, const uint32_t wcells, uint16_t * __restrict__ wlw, const int tc, const int lane, const int sentinel, const float feps) {
-  int n = 0;
-  for(int i0 = 0; i0 < tc; i0 += 32) {
-    const int i = i0 + lane;
-    const bool valid = i < tc;
-    const float4 cr = *reinterpret_cast<const float4 *>(&c4[valid ? i : sentinel]);
-    const uint32_t cmi = valid ? cm[i] : 0u;
-    const float xf[3] = {cr.x, cr.y, cr.z};
-    const float rch = fmaxf(wreach, __fsqrt_ru(fmaxf(cr.w, 0.f))) + feps;   // max(h_e, hmax_warp) + error bound
-    float dd = 0.f;
-#pragma unroll
-    for(int d = 0; d < D; ++d) {
-      const float tt = fmaxf(0.f, fmaxf(wmn[d] - xf[d], xf[d] - wmx[d]));
-      dd = fmaf(tt, tt, dd);
+// The careful version: flagged candidates (within reach of a work cell that does not take them in the reference) are
+// checked against the body's cell, pairs inside the error band of the fp32 predicate are re-evaluated exactly in fp64.
+// Lanes with `active` false only keep the warp together.  DIRECT: the slots go straight to the warp's rows in global
+// memory (lists longer than the staging area).  cm: the cell masks, cidx: the body indices of the tile's candidates.
+template<int D, bool DIRECT>
+__device__ __forceinline__ void lane_pair_tests_slow(const CandRec * __restrict__ c4, const uint16_t * __restrict__ cm, const uint16_t * __restrict__ cst,
+  const PairGrid & g, const int cx0, const int cx1, const int cy0, const int cy1, const int cz0, const int cz1, const float * af, const float h0f,
+  const float EB, const double * a0, const double h0, const Cols & c, const int32_t * __restrict__ cidx, const uint32_t my_bit, const bool active,
+  const int lane, uint16_t (* lrows)[32], uint16_t * __restrict__ dst, int & cnt) {
+  int iy = cy0 - 1, iz = cz0;
+  int cur = 0, end = 0;
+  bool done = !active;
+  for(;;) {
+    if(cur >= end && !done) {
+      if(++iy > cy1) { iy = cy0; ++iz; }
+      if(iz > cz1) done = true;
+      else {
+        const int base = (iz * g.ny + iy) * g.nx;
+        cur = cst[base + cx0];
+        end = cst[base + cx1 + 1];
+      }
     }
-    const bool pass = (cmi & wcells) != 0u && dd <= rch * rch * 1.0001f;
-    const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-    if(pass) wlw[n + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
-    n += __popc(bal);
+    if(__all_sync(0xffffffffu, done)) break;
+    if(cur < end) {
+      const float4 r = *reinterpret_cast<const float4 *>(&c4[cur]);
+      const float dx = af[0] - r.x;
+      float s = dx * dx;
+      if(D > 1) { const float dy = af[1] - r.y; s = fmaf(dy, dy, s); }
+      if(D > 2) { const float dz = af[2] - r.z; s = fmaf(dz, dz, s); }
+      const float dd = s - fmaxf(h0f, fabsf(r.w));
+      if(dd <= EB) {
+        bool in = true;
+        if(r.w < 0.f) in = (cm[cur] & my_bit) != 0u;
+        if(in && dd >= -EB) {
+          // (dx^2 + dy^2) + dz^2 <= max(h_k, h_e)^2 in fp64 (max(h_k,h_e)^2 == max(h_k^2,h_e^2) exactly: rounding is monotonic)
+          const int e = cidx[cur];
+          double s0 = (a0[0] - c.f[F_POS][e]) * (a0[0] - c.f[F_POS][e]);
+          if(D > 1) s0 = s0 + (a0[1] - c.f[F_POS + 1][e]) * (a0[1] - c.f[F_POS + 1][e]);
+          if(D > 2) s0 = s0 + (a0[2] - c.f[F_POS + 2][e]) * (a0[2] - c.f[F_POS + 2][e]);
+          const double he = c.f[F_H][e];
+          in = s0 <= h0 || s0 <= he * he;
+        }
+        if(in) {
+          if(DIRECT) dst[(1 + cnt) * 32 + lane] = (uint16_t)cur;
+          else if(cnt < SR_LROWS) lrows[1 + cnt][lane] = (uint16_t)cur;
+          ++cnt;
+        }
+      }
+      ++cur;
+    }
   }
-  const int nmax = (n + 15) & ~15;
-  for(int j = n + lane; j < nmax; j += 32) wlw[j] = (uint16_t)sentinel;
-  __syncwarp();
-  return nmax;
 }
 
 template<int D>
@@ -811,27 +882,28 @@ __global__ void __launch_bounds__(SR_NT, FSPH_SR_OCC) k_block_pairs(Tree t, Cols
   const int64_t * __restrict__ wcand, SearchCursors * __restrict__ cur, unsigned long long rows_cap, uint32_t * __restrict__ status) {
   constexpr int NT = SR_NT;
   __shared__ int32_t cfirst[BLK_CELLS];
-  __shared__ double cbox[BLK_CELLS][2 * D];
-  __shared__ float red_sm[2][SR_NW];
+  __shared__ double cbox[BLK_CELLS][2 * D + 1];
+  __shared__ uint32_t scan_sm[SR_NW];
   extern __shared__ __align__(16) unsigned char ubuf[];   // block_pairs_smem() bytes
   CandRec * const c4 = reinterpret_cast<CandRec *>(ubuf);                                    // [SR_CAP + 1] x, y, z, h^2
-  uint16_t * const cm = reinterpret_cast<uint16_t *>(ubuf + SM_CM);                          // [SR_CAP + 1] cell masks
-  uint16_t (* const wl)[SR_WCAPL] = reinterpret_cast<uint16_t (*)[SR_WCAPL]>(ubuf + SM_WL);   // per warp: its candidates of the tile
+  uint16_t * const cm = reinterpret_cast<uint16_t *>(ubuf + SM_CM);                          // [SR_CAP] cell masks
+  uint16_t (* const cst)[SR_CST] = reinterpret_cast<uint16_t (*)[SR_CST]>(ubuf + SM_CS);     // per tile: [cells + 1] first slot of each cell
   uint16_t (* const lbuf)[SR_LROWS + 1][32] = reinterpret_cast<uint16_t (*)[SR_LROWS + 1][32]>(ubuf + SM_LBUF);
+  uint32_t * const cnt_sm = reinterpret_cast<uint32_t *>(ubuf + SM_CNT);                     // sort: per cell counter / cursor
+  uint16_t * const widx = reinterpret_cast<uint16_t *>(ubuf + SM_WIDX);                      // sort: walk position by sorted position
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if(tid == 0) {
-    // the sentinel record that pads the candidate lists: accepted by nobody (s = inf)
+    // the sentinel record lanes without a candidate test: accepted by nobody (s = inf)
     CandRec r;
     r.x[0] = r.x[1] = r.x[2] = 1e30f;
-    r.h2 = -1.f;
+    r.h2 = 1.f;
     c4[SR_CAP] = r;
-    cm[SR_CAP] = 0;
   }
   for(int blk = blockIdx.x; blk < sr.nblk; blk += gridDim.x) {
     const int ncand_s = sr.blk_ncand[blk];
     if(ncand_s < 0) continue;   // did not fit (the search is repeated)
-    const uint32_t ncands = (uint32_t)ncand_s;
+    const int ncands = ncand_s;
     const int g0 = sr.blk_wc[blk], K = sr.blk_wc[blk + 1] - g0;
     const int body0 = sr.blk_body[blk], PB = sr.blk_nbody[blk];
     const unsigned long long co = sr.blk_cand_off[blk], dir0 = sr.blk_dir_off[blk];
@@ -842,6 +914,7 @@ __global__ void __launch_bounds__(SR_NT, FSPH_SR_OCC) k_block_pairs(Tree t, Cols
       cfirst[tid] = w.first - body0;
 #pragma unroll
       for(int d = 0; d < D; ++d) { cbox[tid][d] = w.tmn[d]; cbox[tid][D + d] = w.tmx[d]; }
+      cbox[tid][2 * D] = w.hmax;
     }
     const bool active = tid < PB;
     double a0[D], ha = 0.0;
@@ -852,126 +925,177 @@ __global__ void __launch_bounds__(SR_NT, FSPH_SR_OCC) k_block_pairs(Tree t, Cols
       for(int d = 0; d < D; ++d) a0[d] = c.f[F_POS + d][body0 + tid];
       ha = c.f[F_H][body0 + tid];
     }
-    const int ntile = (int)((ncands + NL_TILE - 1) / NL_TILE);
-    // Candidates leave the walk in runs of key-neighbours.  They are dealt to the tiles round-robin (walk position i
-    // goes to tile i % ntile, slot i / ntile): every tile then holds an even sample of the whole neighbourhood, so all
-    // bodies of the block find about the same number of neighbours in it and the lanes of the pair loops stay busy
-    // together; tile ti starts at co + tile_start(ti) and holds tile_count(ti) candidates.
-    for(uint32_t i = tid; i < ncands; i += NT) {
-      const uint32_t ti = i % (uint32_t)ntile, p = i / (uint32_t)ntile;
-      sr.cand[co + tile_start(ncands, ntile, ti) + p] = t.cell[(uint32_t)strip[i]];
-    }
     __syncthreads();
-    // the block's tight box and the cell of each body
-    double bmn[D], bmx[D];
+    // the block's tight box and largest h, and the cell of each body
+    double bmn[D], bmx[D], bh = cbox[0][2 * D];
 #pragma unroll
     for(int d = 0; d < D; ++d) { bmn[d] = cbox[0][d]; bmx[d] = cbox[0][D + d]; }
     int my_slot = 0;
     for(int k = 1; k < K; ++k) {
 #pragma unroll
       for(int d = 0; d < D; ++d) { bmn[d] = fmin(bmn[d], cbox[k][d]); bmx[d] = fmax(bmx[d], cbox[k][D + d]); }
+      bh = fmax(bh, cbox[k][2 * D]);
       my_slot += cfirst[k] <= tid;
     }
-    double bctr[D];
+    double bctr[D], hext = 0.0;
 #pragma unroll
-    for(int d = 0; d < D; ++d) bctr[d] = 0.5 * (bmn[d] + bmx[d]);
+    for(int d = 0; d < D; ++d) {
+      bctr[d] = 0.5 * (bmn[d] + bmx[d]);
+      hext = dmax(hext, bmx[d] - bctr[d]);
+      hext = dmax(hext, bctr[d] - bmn[d]);
+    }
     float af[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for(int d = 0; d < D; ++d) af[d] = active ? (float)(a0[d] - bctr[d]) : 0.f;
     const double h0 = ha * ha;
     const float h0f = (float)h0;
     const int nwarp_act = (PB + 31) >> 5;
-    // cells of this warp's bodies
-    uint32_t warp_cells = active ? (1u << my_slot) : 0u;
-#pragma unroll
-    for(int o = 16; o > 0; o >>= 1) warp_cells |= __shfl_xor_sync(0xffffffffu, warp_cells, o);
-    const bool multi = (warp_cells & (warp_cells - 1u)) != 0u;
     const uint32_t my_bit = 1u << my_slot;
-    // tight box and largest h of the warp's bodies, in fp32 relative to the block centre (bounds rounded outwards)
-    float wmn[3] = {0.f, 0.f, 0.f}, wmx[3] = {0.f, 0.f, 0.f}, wreach;
+    // error bound of the fp32 predicate, reach and grid (header comment)
+    const double Hm = dmax(bh, (double)sr.blk_hmax[blk]) * (1.0 + 1e-6);
+    float EB, reach;
+    PairGrid g;
     {
-      double qmn[D], qmx[D], qh = active ? ha : 0.0;
+      const double u = 5.9604644775390625e-8;   // 2^-24
+      const double M = hext + 1.0001 * Hm;
+      const double e1 = 4.01 * u * M;
+      const double Rm = 1.001 * Hm + 2.0 * e1;
+      EB = __double2float_ru((e1 * (3.4641016151377553 * Rm + 3.0 * e1) + 8.0 * u * Rm * Rm) * 1.0001);
+      const double R = 1.0001 * Hm + 8.0 * e1;   // no pair farther apart than this along any axis
+      reach = __double2float_ru(R);
+      // cells of half the reach, enlarged until the grid has at most SR_NCELL cells
+      double cell = 0.5 * R;
+      double ext[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-      for(int d = 0; d < D; ++d) { qmn[d] = active ? a0[d] : 1.79769313486231570e308; qmx[d] = active ? a0[d] : -1.79769313486231570e308; }
-#pragma unroll
-      for(int o = 16; o > 0; o >>= 1) {
+      for(int d = 0; d < D; ++d) ext[d] = (bmx[d] - bmn[d]) + 2.0 * R;
+      int n[3] = {1, 1, 1};
+      for(int pass = 0; pass < 8; ++pass) {
+        double tot = 1.0;
 #pragma unroll
         for(int d = 0; d < D; ++d) {
-          qmn[d] = dmin(qmn[d], __shfl_xor_sync(0xffffffffu, qmn[d], o));
-          qmx[d] = dmax(qmx[d], __shfl_xor_sync(0xffffffffu, qmx[d], o));
+          const double q = ceil(ext[d] / cell);
+          n[d] = (int)dmin(q, 1024.0);
+          if(n[d] < 1) n[d] = 1;
+          tot *= q;
         }
-        qh = dmax(qh, __shfl_xor_sync(0xffffffffu, qh, o));
+        if(tot <= (double)SR_NCELL && n[0] * n[1] * n[2] <= SR_NCELL) break;
+        cell *= (D == 1 ? tot / SR_NCELL : (D == 2 ? sqrt(tot / SR_NCELL) : cbrt(tot / SR_NCELL))) * 1.02;
       }
+      if(n[0] * n[1] * n[2] > SR_NCELL) n[0] = n[1] = n[2] = 1;   // (never in practice) one cell: every lane tests every candidate
+      g.nx = n[0]; g.ny = n[1]; g.nz = n[2];
+      g.invc = (float)(1.0 / cell);
 #pragma unroll
-      for(int d = 0; d < D; ++d) {
-        // a warp without bodies is never used; its bounds only have to be finite
-        wmn[d] = warp_cells ? __double2float_rd(qmn[d] - bctr[d]) : 0.f;
-        wmx[d] = warp_cells ? __double2float_ru(qmx[d] - bctr[d]) : 0.f;
-      }
-      wreach = __double2float_ru(qh);
+      for(int d = 0; d < 3; ++d) g.org[d] = d < D ? __double2float_rd((bmn[d] - bctr[d]) - R) : 0.f;
+    }
+    const int ncell = g.nx * g.ny * g.nz;
+    // the lane's cell ranges (the margin of 1e-3 cells covers the roundings of both sides' cell coordinates)
+    int cl[3] = {0, 0, 0}, ch[3] = {0, 0, 0};
+#pragma unroll
+    for(int d = 0; d < D; ++d) {
+      const int n = d == 0 ? g.nx : (d == 1 ? g.ny : g.nz);
+      const float gx = (af[d] - g.org[d]) * g.invc, rc = reach * g.invc + 1e-3f;
+      cl[d] = min(max((int)floorf(gx - rc), 0), n - 1);
+      ch[d] = min(max((int)floorf(gx + rc), 0), n - 1);
     }
     bool overflow = false;
     int nn = 0;
-    for(int t0 = 0; t0 < ntile; t0 += SR_GROUP) {
-      const int t1 = min(ntile, t0 + SR_GROUP);
-      const uint32_t gbase = tile_start(ncands, ntile, t0);
-      if(t0 > 0) __syncthreads();   // the previous group's records are no longer read
-      // ---- stage the group: record j <-> candidate co + gbase + j (tile-major) -------------------------------
-      float mloc = 0.f, hloc = h0f;
+    const int nchunk = (ncands + NL_CHUNK - 1) / NL_CHUNK;
+    for(int chk = 0; chk < nchunk; ++chk) {
+      const int cbase = chk * NL_CHUNK;
+      const int nc = min(NL_CHUNK, ncands - cbase);
+      const int nt = (nc + NL_TILE - 1) / NL_TILE;
+      if(chk > 0) __syncthreads();   // the previous chunk's records and lists are no longer used
+      // ---- sort the chunk by grid cell (ties in walk order) and stage it ----------------------------------------
+      for(int i = tid; i <= ncell; i += NT) cnt_sm[i] = 0u;
+      __syncthreads();
+      for(int i = tid; i < nc; i += NT) {
+        const LeafRec lr = t.leafrec[(uint32_t)strip[cbase + i]];
+        float x[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-      for(int d = 0; d < D; ++d) mloc = fmaxf(mloc, fabsf(af[d]));
-      for(int ti = t0; ti < t1; ++ti) {
-        const uint32_t tb = tile_start(ncands, ntile, ti) - gbase;
-        const int tc = tile_count(ncands, ntile, ti);
-        for(int slot = tid; slot < tc; slot += NT) {
-          const int64_t sv = strip[(size_t)slot * ntile + ti];
-          const LeafRec lr = t.leafrec[(uint32_t)sv];
-          CandRec r;
-          r.x[0] = r.x[1] = r.x[2] = 0.f;
+        for(int d = 0; d < D; ++d) x[d] = (float)(lr.x[d] - bctr[d]);
+        atomicAdd(&cnt_sm[grid_cell<D>(g, x)], 1u);
+      }
+      __syncthreads();
+      {
+        // exclusive scan of the cell counters: 8 consecutive cells per thread
+        constexpr int PER = SR_NCELL / NT + 1;   // cells 0 .. ncell (the end marker) in runs of PER per thread
+        uint32_t v[PER], sum = 0;
 #pragma unroll
-          for(int d = 0; d < D; ++d) {
-            r.x[d] = (float)(lr.x[d] - bctr[d]);
-            mloc = fmaxf(mloc, fabsf(r.x[d]));
+        for(int k = 0; k < PER; ++k) {
+          const int i = tid * PER + k;
+          v[k] = i < ncell ? cnt_sm[i] : 0u;
+          sum += v[k];
+        }
+        uint32_t total;
+        uint32_t run = block_scan_u32<NT>(sum, total, scan_sm);
+#pragma unroll
+        for(int k = 0; k < PER; ++k) {
+          const int i = tid * PER + k;
+          if(i <= ncell) {
+            // sorted positions [run, ...) of cell i; those of tile tj are p = tj (mod nt): first slot ceil((run - tj) / nt)
+            const uint32_t pos = i < ncell ? run : (uint32_t)nc;
+            if(i < ncell) cnt_sm[i] = run;
+            for(int tj = 0; tj < nt; ++tj) cst[tj][i] = (uint16_t)((pos + (uint32_t)(nt - 1 - tj)) / (uint32_t)nt);
           }
-          r.h2 = (float)(lr.h * lr.h);
-          hloc = fmaxf(hloc, r.h2);
-          c4[tb + slot] = r;
-          cm[tb + slot] = (uint16_t)(sv >> 32);
+          run += v[k];
         }
       }
-#pragma unroll
-      for(int o = 16; o > 0; o >>= 1) {
-        mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, o));
-        hloc = fmaxf(hloc, __shfl_xor_sync(0xffffffffu, hloc, o));
-      }
-      if(lane == 0) { red_sm[0][warp] = mloc; red_sm[1][warp] = hloc; }
       __syncthreads();
+      for(int i = tid; i < nc; i += NT) {
+        const LeafRec lr = t.leafrec[(uint32_t)strip[cbase + i]];
+        float x[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-      for(int w = 0; w < SR_NW; ++w) { mloc = fmaxf(mloc, red_sm[0][w]); hloc = fmaxf(hloc, red_sm[1][w]); }
-      // error bounds of the fp32 arithmetic (header comment)
-      float EB, feps;
-      {
-        const double u = 5.9604644775390625e-8;   // 2^-24
-        const double M = (double)mloc, Hm = sqrt((double)hloc) * (1.0 + 1e-6);
-        const double e1 = 4.01 * u * M;
-        const double Rm = 1.001 * Hm + 2.0 * e1;
-        EB = __double2float_ru((e1 * (3.4641016151377553 * Rm + 3.0 * e1) + 8.0 * u * Rm * Rm) * 1.0001);
-        feps = __double2float_ru(1.1 * 1.7320508075688774 * e1 + 2e-7 * Hm);
+        for(int d = 0; d < D; ++d) x[d] = (float)(lr.x[d] - bctr[d]);
+        widx[atomicAdd(&cnt_sm[grid_cell<D>(g, x)], 1u)] = (uint16_t)i;
       }
-      // ---- the warp's tiles of this group: no block barrier from here on ----------------------------------------
+      __syncthreads();
+      // the order inside a cell is that of the atomics: put every cell in walk order (cells hold ~1 candidate)
+      for(int i = tid; i < ncell; i += NT) {
+        const int lo = i > 0 ? (int)cnt_sm[i - 1] : 0, hi = (int)cnt_sm[i];   // the cursors now stand at the cells' ends
+        for(int a = lo + 1; a < hi; ++a) {
+          const uint16_t key = widx[a];
+          int b = a - 1;
+          while(b >= lo && widx[b] > key) { widx[b + 1] = widx[b]; --b; }
+          widx[b + 1] = key;
+        }
+      }
+      __syncthreads();
+      // sorted position p -> tile p % nt, slot p / nt: record index tb(tile) + slot (the chunk's tiles back to back)
+      const int tq = nc / nt, tr = nc % nt;
+      for(int p = tid; p < nc; p += NT) {
+        const int64_t sv = strip[cbase + widx[p]];
+        const LeafRec lr = t.leafrec[(uint32_t)sv];
+        const int tj = p % nt, slot = p / nt;
+        const int j = tj * tq + min(tj, tr) + slot;
+        CandRec r;
+        r.x[0] = r.x[1] = r.x[2] = 0.f;
+#pragma unroll
+        for(int d = 0; d < D; ++d) r.x[d] = (float)(lr.x[d] - bctr[d]);
+        const float h2 = (float)(lr.h * lr.h);
+        r.h2 = ((sv >> 48) & 1) ? -h2 : h2;
+        c4[j] = r;
+        cm[j] = (uint16_t)(sv >> 32);
+        sr.cand[co + cbase + j] = t.cell[(uint32_t)sv];
+      }
+      __syncthreads();   // the sort scratch becomes the list staging area
+      // ---- the warp's tiles of this chunk: no block barrier from here on ----------------------------------------
       if(warp < nwarp_act) {
-        for(int ti = t0; ti < t1; ++ti) {
-          const uint32_t tb = tile_start(ncands, ntile, ti);
-          const int tc = tile_count(ncands, ntile, ti);
-          const CandRec * const tc4 = c4 + (tb - gbase);
-          const uint16_t * const tcm = cm + (tb - gbase);
-          const int sentinel = SR_CAP - (int)(tb - gbase);
-          const int32_t * const cidx = sr.cand + co + tb;
+        for(int tj = 0; tj < nt; ++tj) {
+          const int ti = chk * NL_CHUNK_TILES + tj;
+          const int tb = tj * tq + min(tj, tr);
+          const CandRec * const tc4 = c4 + tb;
+          const uint16_t * const tcm = cm + tb;
+          const int32_t * const cidx = sr.cand + co + cbase + tb;
+          const int sentinel = SR_CAP - tb;
           int cnt = 0;
-          const int nmax = compact_warp<D>(tc4, tcm, wmn, wmx, wreach, warp_cells, wl[warp], tc, lane, sentinel, feps);
-          if(multi) warp_pair_tests<D, false, true>(tc4, tcm, wl[warp], nmax, af, h0f, EB, a0, h0, c, cidx, my_bit, active, lane, lbuf[warp], nullptr, cnt);
-          else warp_pair_tests<D, false, false>(tc4, tcm, wl[warp], nmax, af, h0f, EB, a0, h0, c, cidx, my_bit, active, lane, lbuf[warp], nullptr, cnt);
-          __syncwarp();
+          const bool redo = lane_pair_tests_fast<D>(tc4, sentinel, cst[tj], g, cl[0], ch[0], cl[1], ch[1], cl[2], ch[2], af, h0f, EB, active,
+            &lbuf[warp][1][lane], cnt);
+          if(__any_sync(0xffffffffu, redo)) {
+            int cnt2 = 0;
+            lane_pair_tests_slow<D, false>(tc4, tcm, cst[tj], g, cl[0], ch[0], cl[1], ch[1], cl[2], ch[2], af, h0f, EB, a0, h0, c, cidx, my_bit,
+              redo, lane, lbuf[warp], nullptr, cnt2);
+            if(redo) cnt = cnt2;
+          }
           lbuf[warp][0][lane] = (uint16_t)cnt;
           nn += cnt;
           const int cmax = __reduce_max_sync(0xffffffffu, cnt);
@@ -994,7 +1118,8 @@ __global__ void __launch_bounds__(SR_NT, FSPH_SR_OCC) k_block_pairs(Tree t, Cols
               dst[lane] = (uint16_t)cnt;
               for(int j = cnt + 1; j <= cmax; ++j) dst[j * 32 + lane] = (uint16_t)0;
               int k = 0;
-              warp_pair_tests<D, true, true>(tc4, tcm, wl[warp], nmax, af, h0f, EB, a0, h0, c, cidx, my_bit, active, lane, nullptr, dst, k);
+              lane_pair_tests_slow<D, true>(tc4, tcm, cst[tj], g, cl[0], ch[0], cl[1], ch[1], cl[2], ch[2], af, h0f, EB, a0, h0, c, cidx, my_bit, active,
+                lane, nullptr, dst, k);
             }
           }
           __syncwarp();
@@ -1002,7 +1127,7 @@ __global__ void __launch_bounds__(SR_NT, FSPH_SR_OCC) k_block_pairs(Tree t, Cols
       }
       else {
         // warps without bodies own no rows
-        for(int ti = t0 + lane; ti < t1; ti += 32) sr.dir[dir0 + ti].row[warp] = 0u;
+        for(int tj = lane; tj < nt; tj += 32) sr.dir[dir0 + chk * NL_CHUNK_TILES + tj].row[warp] = 0u;
       }
     }
     if(active && !overflow) c.nneigh[body0 + tid] = nn;
@@ -1022,12 +1147,13 @@ static void neighbor_search_t(System & s) {
   const int nblk = sr.nblk;
   // sentinel of the block table
   FSPH_CUDA_OK(cudaMemcpyAsync(sr.blk_wc + nblk, &sr.nwc, 4, cudaMemcpyHostToDevice, s.stream));
-  s.b_blk_meta.reserve((size_t)nblk * 32);
+  s.b_blk_meta.reserve((size_t)nblk * 36);
   sr.blk_cand_off = s.b_blk_meta.as<uint64_t>();
   sr.blk_dir_off = sr.blk_cand_off + nblk;
   sr.blk_ncand = reinterpret_cast<int32_t *>(sr.blk_dir_off + nblk);
   sr.blk_body = sr.blk_ncand + nblk;
   sr.blk_nbody = sr.blk_body + nblk;
+  sr.blk_hmax = reinterpret_cast<float *>(sr.blk_nbody + nblk);
   SearchCursors * cursors = reinterpret_cast<SearchCursors *>(s.b_status.as<uint32_t>() + 8);
   // per work cell: boxes, largest h, corner representatives
   s.b_wcinfo.reserve((size_t)sr.nwc * sizeof(WcInfo<D>));
@@ -1141,14 +1267,15 @@ __global__ void __launch_bounds__(SR_NT) k_export(Cols c, Search sr, const uint6
   const int blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int PB = sr.blk_nbody[blk];
   if(tid >= PB) return;
-  const int nwarp_act = (PB + 31) >> 5;
-  const int ntile = (sr.blk_ncand[blk] + NL_TILE - 1) / NL_TILE;
+  const int C = sr.blk_ncand[blk], ntile = nl_ntiles(C);
   const uint64_t co = sr.blk_cand_off[blk];
   uint64_t o = off[sr.blk_body[blk] + tid];
   for(int ti = 0; ti < ntile; ++ti) {
     const uint16_t * rows = sr.nl + (uint64_t)sr.dir[sr.blk_dir_off[blk] + ti].row[warp] * 32;
     const int cnt = rows[lane];
-    const uint64_t tb = co + tile_start((uint32_t)sr.blk_ncand[blk], (uint32_t)ntile, (uint32_t)ti);
+    int tb0, tc;
+    nl_tile_range(C, ti, tb0, tc);
+    const uint64_t tb = co + (uint64_t)tb0;
     for(int j = 0; j < cnt; ++j) ids[o++] = c.id[sr.cand[tb + rows[(1 + j) * 32 + lane]]];
   }
 }

@@ -588,12 +588,11 @@ __global__ void __launch_bounds__(BLK_BODIES, SweepOcc<OP>::MINB) k_sweep(Cols c
   Own<D> o;
   load_own<D, OP, VISC>(o, c, body0 + tid, active);
 
-  const int ntile = (C + NL_TILE - 1) / NL_TILE;
+  const int ntile = nl_ntiles(C);
   for(int ti = 0; ti < ntile; ++ti) {
-    // candidates are dealt to the tiles round-robin (fsph_search.cu): tile ti starts at tb and holds tc of them
-    const int tq = C / ntile, tr = C % ntile;
-    const int tb = ti * tq + min(ti, tr);
-    const int tc = tq + (ti < tr ? 1 : 0);
+    // tile ti starts at candidate tb of the block and holds tc of them
+    int tb, tc;
+    nl_tile_range(C, ti, tb, tc);
     // this warp's rows of the tile
     const uint64_t rb = warp < nwarp_act ? sr.dir[dir0 + ti].row[warp] : 0u;
     const uint16_t * rows = sr.nl + rb * 32 + lane;
