@@ -127,6 +127,11 @@ __host__ __device__ inline void nl_tile_range(int C, int ti, int & tb, int & tc)
 struct __align__(16) TileDir {
   uint32_t row[8];     // per warp: its first row of the tile in the list arena (it owns 1 + the longest list of its lanes)
 };
+// one entry of a super cell's node list as the per-block filter reads it
+struct __align__(16) SlRec {
+  float mn[3], mx[3];
+  int32_t node, pad;
+};
 struct Search {
   int32_t * wc_cell;     // work cells in Morton order: index into Tree::cell
   int32_t nwc;
@@ -136,6 +141,7 @@ struct Search {
   int32_t * super_cell;  // [nsuper] index into Tree::cell
   uint64_t * sl_off;     // [nsuper+1] offsets into sl_nodes
   int32_t * sl_nodes;    // node indices
+  struct SlRec * sl_rec; // the same nodes with their boxes in fp32 (rounded outwards): what the per-block filter reads
   int32_t nsuper;
   // blocks
   int32_t nblk;
@@ -241,10 +247,10 @@ struct System {
   DevBuf b_cell, b_cell_parent, b_cell_desc, b_cell_desc2, b_child_begin, b_child_end, b_node_start, b_node_depth, b_sub;
   DevBuf b_noderec, b_leafrec;
   DevBuf b_nmass, b_ncom[3], b_nradius, b_nlap, b_nbmin[3], b_nbmax[3];
-  DevBuf b_wc_super, b_super_cell, b_sl_off, b_sl_nodes;
+  DevBuf b_wc_super, b_super_cell, b_sl_off, b_sl_nodes, b_sl_rec;
   DevBuf b_wc_cell, b_cand, b_cnt0, b_cnt1;
   DevBuf b_status, b_red, b_levels, b_search_scratch;
-  DevBuf b_blk_wc, b_blk_meta, b_dir, b_nl, b_super_queue, b_wcinfo, b_wcand;
+  DevBuf b_blk_wc, b_blk_meta, b_dir, b_nl, b_super_queue, b_wcinfo, b_wcrep, b_wcand;
   DevBuf b_pair_a, b_pair_pi;         // per-pair caches of the sweeps, parallel to the list arena (fsph_sweeps.cu)
   unsigned long long est_cand = 0, est_dir = 0, est_rows = 0;  // sizes of the previous neighbour structure (capacity estimate)
   int64_t est_n = 0;

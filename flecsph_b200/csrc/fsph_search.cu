@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(SW_NT) k_super_walk(Tree t, Cols c, Search sr,
     }
     const double hmax2 = hmax * hmax * (1.0 + 1e-9);
     int32_t * out = MODE == 1 ? sr.sl_nodes + sr.sl_off[sidx] : nullptr;
+    SlRec * out_rec = MODE == 1 ? sr.sl_rec + sr.sl_off[sidx] : nullptr;
     int ncur = 1, cur = 0;
     uint32_t nlist = 0;
     while(ncur > 0) {
@@ -228,7 +229,19 @@ __global__ void __launch_bounds__(SW_NT) k_super_walk(Tree t, Cols c, Search sr,
           }
         }
         if(r & 0x80u) {
-          if(MODE == 1) out[lpos] = nd;
+          if(MODE == 1) {
+            out[lpos] = nd;
+            const NodeRec rec = t.noderec[nd];
+            SlRec sl;
+#pragma unroll
+            for(int d = 0; d < 3; ++d) {
+              sl.mn[d] = d < D ? __double2float_rd(rec.bmin[d]) : 0.f;
+              sl.mx[d] = d < D ? __double2float_ru(rec.bmax[d]) : 0.f;
+            }
+            sl.node = nd;
+            sl.pad = 0;
+            out_rec[lpos] = sl;
+          }
           ++lpos;
         }
       }
@@ -356,6 +369,8 @@ static void build_super_lists(System & s) {
   if(nblk == 0) throw std::runtime_error("no blocks");
   s.b_sl_nodes.reserve((size_t)std::max<uint64_t>(tot, 1) * 4);
   sr.sl_nodes = s.b_sl_nodes.as<int32_t>();
+  s.b_sl_rec.reserve((size_t)std::max<uint64_t>(tot, 1) * sizeof(SlRec));
+  sr.sl_rec = s.b_sl_rec.as<SlRec>();
   s.b_blk_wc.reserve((size_t)(nblk + 1) * 4);
   sr.blk_wc = s.b_blk_wc.as<int32_t>();
   sr.nblk = (int)nblk;
@@ -381,7 +396,7 @@ struct SearchCursors {
 };
 
 template<int D>
-__global__ void __launch_bounds__(256) k_wc_info(Tree t, Cols c, Search sr, WcInfo<D> * __restrict__ out) {
+__global__ void __launch_bounds__(256) k_wc_info(Tree t, Cols c, Search sr, WcInfo<D> * __restrict__ out, LeafRec * __restrict__ reps) {
   constexpr int NCH = 1 << D;
   const int g = (int)((blockIdx.x * 256u + threadIdx.x) >> 4), l16 = threadIdx.x & 15;
   const bool live = g < sr.nwc;
@@ -461,6 +476,16 @@ __global__ void __launch_bounds__(256) k_wc_info(Tree t, Cols c, Search sr, WcIn
     for(int q = 0; q < NCH; ++q) w.rep[q] = rep[q];
     out[g] = w;
   }
+  // position and h of the representatives, packed (one 32-byte load in the walk)
+  if(live && l16 < NCH) {
+    const int k = start + rep[l16 < NCH ? l16 : 0];
+    LeafRec r;
+    r.x[0] = r.x[1] = r.x[2] = 0.0;
+#pragma unroll
+    for(int d = 0; d < D; ++d) r.x[d] = c.f[F_POS + d][k];
+    r.h = c.f[F_H][k];
+    reps[(size_t)g * NCH + l16] = r;
+  }
 }
 
 // ---- the walk: one warp per block ------------------------------------------------------------------------------
@@ -477,13 +502,15 @@ constexpr int WK_Q = 256;        // queued nodes per round of (b) + (c)
 constexpr int WK_ITEMS = 32 * 8; // leaf children of 32 queue entries
 template<int D> struct WalkSmem {
   WcInfo<D> cell[BLK_CELLS];
+  float fbox[BLK_CELLS][8];   // per cell: tight box relative to the block centre (rounded outwards), largest h (rounded up),
+                              // largest |coordinate| of the box
   int32_t q_node[WK_Q];
   int32_t it_cell[WK_ITEMS];
   uint16_t it_mask[WK_ITEMS];
 };
 
 template<int D>
-__global__ void __launch_bounds__(WK_NT, 8) k_block_walk(Tree t, Cols c, Search sr, const WcInfo<D> * __restrict__ wci, int64_t * __restrict__ scratch,
+__global__ void __launch_bounds__(WK_NT, 8) k_block_walk(Tree t, Cols c, Search sr, const WcInfo<D> * __restrict__ wci, const LeafRec * __restrict__ reps, int64_t * __restrict__ scratch,
   int scratch_cap, SearchCursors * __restrict__ cur, unsigned long long cand_cap, unsigned long long dir_cap, int64_t * __restrict__ wcand,
   uint32_t * __restrict__ status) {
   __shared__ WalkSmem<D> sm_all[WK_WARPS];
@@ -519,7 +546,31 @@ __global__ void __launch_bounds__(WK_NT, 8) k_block_walk(Tree t, Cols c, Search 
       }
       bh = fmax(bh, __shfl_xor_sync(0xffffffffu, bh, o));
     }
-    const double bh2 = bh * bh * (1.0 + 1e-9);
+    // the block box in fp32 (absolute coordinates, rounded outwards) for the list filter
+    float fbmn[D], fbmx[D], fbabs = 0.f;
+#pragma unroll
+    for(int d = 0; d < D; ++d) {
+      fbmn[d] = __double2float_rd(bmn[d]);
+      fbmx[d] = __double2float_ru(bmx[d]);
+      fbabs = fmaxf(fbabs, fmaxf(fabsf(fbmn[d]), fabsf(fbmx[d])));
+    }
+    const float fbh = __double2float_ru(bh);
+    double bctr[D];
+#pragma unroll
+    for(int d = 0; d < D; ++d) bctr[d] = 0.5 * (bmn[d] + bmx[d]);
+    if(lane < K) {
+#pragma unroll
+      for(int d = 0; d < D; ++d) {
+        sm.fbox[lane][d] = __double2float_rd(sm.cell[lane].tmn[d] - bctr[d]);
+        sm.fbox[lane][3 + d] = __double2float_ru(sm.cell[lane].tmx[d] - bctr[d]);
+      }
+      sm.fbox[lane][6] = __double2float_ru(sm.cell[lane].hmax);
+      float bext = 0.f;
+#pragma unroll
+      for(int d = 0; d < D; ++d) bext = fmaxf(bext, fmaxf(fabsf(sm.fbox[lane][d]), fabsf(sm.fbox[lane][3 + d])));
+      sm.fbox[lane][7] = bext;
+    }
+    __syncwarp();
     const int body0 = sm.cell[0].first;
     const int PB = sm.cell[K - 1].first + sm.cell[K - 1].P - body0;
     const int sidx = sr.wc_super[g0];
@@ -530,17 +581,25 @@ __global__ void __launch_bounds__(WK_NT, 8) k_block_walk(Tree t, Cols c, Search 
     double hcand = 0.0;   // largest h among the candidates
     for(int lbase = 0; lbase < sl_n || nq > 0; lbase += 32) {
       // (a) conservative filter: node box within the block's largest h of the block's tight box (necessary for
-      //     intersects_sphere_box with any body of the block); queued in list order
+      //     intersects_sphere_box with any body of the block), in fp32 on boxes rounded outwards; queued in list order
       if(lbase < sl_n) {
         const int e = lbase + lane;
-        const int nd = e < sl_n ? sr.sl_nodes[sl_lo + e] : -1;
+        int nd = -1;
         bool ok = false;
-        if(nd >= 0) {
-          const NodeRec & rec = t.noderec[nd];
-          double nmn[D], nmx[D];
+        if(e < sl_n) {
+          const float4 * rp = reinterpret_cast<const float4 *>(sr.sl_rec + sl_lo + e);
+          const float4 ra = rp[0], rb = rp[1];   // mn.xyz mx.x | mx.yz node pad
+          nd = __float_as_int(rb.z);
+          const float nmn[3] = {ra.x, ra.y, ra.z}, nmx[3] = {ra.w, rb.x, rb.y};
+          float g2 = 0.f, nabs = 0.f;
 #pragma unroll
-          for(int d = 0; d < D; ++d) { nmn[d] = rec.bmin[d]; nmx[d] = rec.bmax[d]; }
-          ok = box_gap2<D>(nmn, nmx, bmn, bmx) <= bh2;
+          for(int d = 0; d < D; ++d) {
+            const float tt = fmaxf(0.f, fmaxf(nmn[d] - fbmx[d], fbmn[d] - nmx[d]));
+            g2 = fmaf(tt, tt, g2);
+            nabs = fmaxf(nabs, fmaxf(fabsf(nmn[d]), fabsf(nmx[d])));
+          }
+          const float hm = fbh + 1e-6f * (fbabs + nabs);
+          ok = g2 <= hm * hm * 1.00001f;
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, ok);
         if(ok) sm.q_node[nq + __popc(bal & lt)] = nd;
@@ -560,7 +619,27 @@ __global__ void __launch_bounds__(WK_NT, 8) k_block_walk(Tree t, Cols c, Search 
           for(int d = 0; d < D; ++d) { nmn[d] = rec.bmin[d]; nmx[d] = rec.bmax[d]; }
           cb = rec.child_begin;
           lmask = rec.leafmask;
+          // the node box in fp32 relative to the block centre, rounded outwards: cells farther from it than their largest
+          // h are skipped before any fp64 work (the exact quick reject below would drop them as well)
+          float fmn[D], fmx[D], nabs = 0.f;
+#pragma unroll
+          for(int d = 0; d < D; ++d) {
+            fmn[d] = __double2float_rd(nmn[d] - bctr[d]);
+            fmx[d] = __double2float_ru(nmx[d] - bctr[d]);
+            nabs = fmaxf(nabs, fmaxf(fabsf(fmn[d]), fabsf(fmx[d])));
+          }
           for(int ci = 0; ci < K; ++ci) {
+            {
+              const float * fb = sm.fbox[ci];
+              float g2 = 0.f;
+#pragma unroll
+              for(int d = 0; d < D; ++d) {
+                const float tt = fmaxf(0.f, fmaxf(fmn[d] - fb[3 + d], fb[d] - fmx[d]));
+                g2 = fmaf(tt, tt, g2);
+              }
+              const float hm = fb[6] + 1e-6f * (fb[7] + nabs);
+              if(g2 > hm * hm * 1.00001f) continue;
+            }
             const WcInfo<D> & G = sm.cell[ci];
             bool ok = true;
             if(G.has_node) {
@@ -575,11 +654,11 @@ __global__ void __launch_bounds__(WK_NT, 8) k_block_walk(Tree t, Cols c, Search 
               int q = 0;
 #pragma unroll
               for(int d = 0; d < D; ++d) q |= (int)((nmn[d] + nmx[d]) > (G.tmn[d] + G.tmx[d])) << d;
-              const int kr = G.first + G.rep[q];
+              const LeafRec rr = reps[(size_t)(g0 + ci) * (1 << D) + q];
               double p[D];
 #pragma unroll
-              for(int d = 0; d < D; ++d) p[d] = c.f[F_POS + d][kr];
-              bool acc = sphere_box<D>(nmn, nmx, p, c.f[F_H][kr]);
+              for(int d = 0; d < D; ++d) p[d] = rr.x[d];
+              bool acc = sphere_box<D>(nmn, nmx, p, rr.h);
               for(int k = G.first; k < G.first + G.P && !acc; ++k) {
 #pragma unroll
                 for(int d = 0; d < D; ++d) p[d] = c.f[F_POS + d][k];
@@ -615,17 +694,28 @@ __global__ void __launch_bounds__(WK_NT, 8) k_block_walk(Tree t, Cols c, Search 
             cidx = sm.it_cell[it];
             const LeafRec lr = t.leafrec[cidx];
             const uint32_t nmask = sm.it_mask[it];
+            // reach test in fp32 on coordinates relative to the block centre.  It only has to be conservative: the cell's
+            // box is rounded outwards, h upwards, and `slack` covers the roundings of the leaf's coordinates and of the
+            // differences (each below 2^-23 of the larger operand)
+            float lx[D], lmax = 0.f;
+#pragma unroll
+            for(int d = 0; d < D; ++d) {
+              lx[d] = (float)(lr.x[d] - bctr[d]);
+              lmax = fmaxf(lmax, fabsf(lx[d]));
+            }
+            const float lh = __double2float_ru(lr.h);
             for(int ci = 0; ci < K; ++ci) {
-              const WcInfo<D> & G = sm.cell[ci];
+              const float * fb = sm.fbox[ci];
               // reach (conservative): some body of G may lie within max(h_e, hmax_G) of the leaf
-              const double hm = dmax(lr.h, G.hmax);
-              double dd = 0.0;
+              float dd = 0.f;
 #pragma unroll
               for(int d = 0; d < D; ++d) {
-                const double tt = dmax(0.0, dmax(G.tmn[d] - lr.x[d], lr.x[d] - G.tmx[d]));
-                dd = dd + tt * tt;
+                const float tt = fmaxf(0.f, fmaxf(fb[d] - lx[d], lx[d] - fb[3 + d]));
+                dd = fmaf(tt, tt, dd);
               }
-              if(!(dd <= hm * hm * (1.0 + 1e-9))) continue;
+              const float hm = fmaxf(lh, fb[6]) + 1e-6f * (lmax + fb[7]);
+              if(!(dd <= hm * hm * 1.00001f)) continue;
+              const WcInfo<D> & G = sm.cell[ci];
               bool incl = (nmask >> ci) & 1u;
               if(incl && G.has_node) {
                 // |x_e - X_G|^2 <= (max(h_e, lap_G) + radius_G)^2, tree_topology.h:365-370
@@ -1157,10 +1247,12 @@ static void neighbor_search_t(System & s) {
   SearchCursors * cursors = reinterpret_cast<SearchCursors *>(s.b_status.as<uint32_t>() + 8);
   // per work cell: boxes, largest h, corner representatives
   s.b_wcinfo.reserve((size_t)sr.nwc * sizeof(WcInfo<D>));
+  s.b_wcrep.reserve((size_t)sr.nwc * (1 << D) * sizeof(LeafRec));
   WcInfo<D> * wci = s.b_wcinfo.as<WcInfo<D>>();
+  LeafRec * reps = s.b_wcrep.as<LeafRec>();
   {
     PhaseScope ph(s, "search:cells");
-    FSPH_LAUNCH((k_wc_info<D>), (unsigned)((sr.nwc + 15) / 16), 256, s.stream, s.tree, s.cols(), sr, wci);
+    FSPH_LAUNCH((k_wc_info<D>), (unsigned)((sr.nwc + 15) / 16), 256, s.stream, s.tree, s.cols(), sr, wci, reps);
   }
   const int walk_grid = std::min((nblk + WK_WARPS - 1) / WK_WARPS, 148 * 8);
   const int pair_grid = std::min(nblk, 148 * FSPH_SR_OCC * 2);
@@ -1194,7 +1286,7 @@ static void neighbor_search_t(System & s) {
     FSPH_CUDA_OK(cudaMemsetAsync(cursors, 0, sizeof(SearchCursors), s.stream));
     {
       PhaseScope ph(s, "search:walk");
-      FSPH_LAUNCH((k_block_walk<D>), walk_grid, WK_NT, s.stream, s.tree, s.cols(), sr, wci, s.b_search_scratch.as<int64_t>(), scratch_cap, cursors,
+      FSPH_LAUNCH((k_block_walk<D>), walk_grid, WK_NT, s.stream, s.tree, s.cols(), sr, wci, reps, s.b_search_scratch.as<int64_t>(), scratch_cap, cursors,
         cand_cap, dir_cap, s.b_wcand.as<int64_t>(), status);
     }
     {
