@@ -234,8 +234,11 @@ __device__ __forceinline__ void apply_one(double * v, const int op, const PhysPa
 // Several element-wise functors of the driver loop in ONE pass over HBM: every column any of them reads is loaded once
 // up front (all loads in flight together), the functors run in order on the registers, every column any of them wrote is
 // stored once.  `need` / `dirty`: the column sets (bit f = F64 column f), from op_access on the host.
+#ifndef FSPH_APPLY_OCC
+#define FSPH_APPLY_OCC 4
+#endif
 template<int D>
-__global__ void __launch_bounds__(128) k_apply(Cols c, int64_t n, OpList ops, PhysParams pp, uint64_t need, uint64_t dirty,
+__global__ void __launch_bounds__(128, FSPH_APPLY_OCC) k_apply(Cols c, int64_t n, OpList ops, PhysParams pp, uint64_t need, uint64_t dirty,
   uint32_t * __restrict__ status) {
   // n = number of owned bodies, starting at c.own_lo (remote copies are refreshed from their owner: reset_ghosts)
   const int64_t i = c.own_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
