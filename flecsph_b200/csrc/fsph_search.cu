@@ -608,68 +608,90 @@ __global__ void __launch_bounds__(WK_NT, 8) k_block_walk(Tree t, Cols c, Search 
       }
       __syncwarp();
       for(int eb = 0; eb < nq; eb += 32) {
-        // (b) exact tests of one node per lane against every cell: intersects_box_box + any-body intersects_sphere_box
+        // (b) the tests of 32 queued nodes against every cell of the block: intersects_box_box + any-body
+        //     intersects_sphere_box.  First one node per lane: in fp32, relative to the block centre and with the node box
+        //     rounded outwards, the cells farther from it than their largest h are dropped (the exact quick reject below
+        //     would drop them as well); then the surviving (node, cell) pairs are dealt to the lanes for the exact tests.
         const int e = eb + lane;
-        uint32_t mask = 0, lmask = 0;
+        uint32_t pm = 0, lmask = 0;
         int cb = 0;
         if(e < nq) {
           const NodeRec & rec = t.noderec[sm.q_node[e]];
-          double nmn[D], nmx[D];
-#pragma unroll
-          for(int d = 0; d < D; ++d) { nmn[d] = rec.bmin[d]; nmx[d] = rec.bmax[d]; }
           cb = rec.child_begin;
           lmask = rec.leafmask;
-          // the node box in fp32 relative to the block centre, rounded outwards: cells farther from it than their largest
-          // h are skipped before any fp64 work (the exact quick reject below would drop them as well)
           float fmn[D], fmx[D], nabs = 0.f;
 #pragma unroll
           for(int d = 0; d < D; ++d) {
-            fmn[d] = __double2float_rd(nmn[d] - bctr[d]);
-            fmx[d] = __double2float_ru(nmx[d] - bctr[d]);
+            fmn[d] = __double2float_rd(rec.bmin[d] - bctr[d]);
+            fmx[d] = __double2float_ru(rec.bmax[d] - bctr[d]);
             nabs = fmaxf(nabs, fmaxf(fabsf(fmn[d]), fabsf(fmx[d])));
           }
           for(int ci = 0; ci < K; ++ci) {
-            {
-              const float * fb = sm.fbox[ci];
-              float g2 = 0.f;
+            const float * fb = sm.fbox[ci];
+            float g2 = 0.f;
 #pragma unroll
-              for(int d = 0; d < D; ++d) {
-                const float tt = fmaxf(0.f, fmaxf(fmn[d] - fb[3 + d], fb[d] - fmx[d]));
-                g2 = fmaf(tt, tt, g2);
-              }
-              const float hm = fb[6] + 1e-6f * (fb[7] + nabs);
-              if(g2 > hm * hm * 1.00001f) continue;
+            for(int d = 0; d < D; ++d) {
+              const float tt = fmaxf(0.f, fmaxf(fmn[d] - fb[3 + d], fb[d] - fmx[d]));
+              g2 = fmaf(tt, tt, g2);
             }
-            const WcInfo<D> & G = sm.cell[ci];
-            bool ok = true;
-            if(G.has_node) {
-              bool sep = false;
-#pragma unroll
-              for(int d = 0; d < D; ++d) sep = sep || (nmx[d] < G.gmn[d]) || (G.gmx[d] < nmn[d]);
-              ok = !sep;
-            }
-            // quick reject (conservative, exact outcome): the node box is farther than hmax from every position of G
-            if(ok) ok = box_gap2<D>(nmn, nmx, G.tmn, G.tmx) <= G.hmax2;
-            if(ok) {
-              int q = 0;
-#pragma unroll
-              for(int d = 0; d < D; ++d) q |= (int)((nmn[d] + nmx[d]) > (G.tmn[d] + G.tmx[d])) << d;
-              const LeafRec rr = reps[(size_t)(g0 + ci) * (1 << D) + q];
-              double p[D];
-#pragma unroll
-              for(int d = 0; d < D; ++d) p[d] = rr.x[d];
-              bool acc = sphere_box<D>(nmn, nmx, p, rr.h);
-              for(int k = G.first; k < G.first + G.P && !acc; ++k) {
-#pragma unroll
-                for(int d = 0; d < D; ++d) p[d] = c.f[F_POS + d][k];
-                acc = sphere_box<D>(nmn, nmx, p, c.f[F_H][k]);
-              }
-              ok = acc;
-            }
-            if(ok) mask |= 1u << ci;
+            const float hm = fb[6] + 1e-6f * (fb[7] + nabs);
+            if(g2 <= hm * hm * 1.00001f) pm |= 1u << ci;
           }
-          if(!mask) lmask = 0;
         }
+        uint16_t * const pair_sm = reinterpret_cast<uint16_t *>(sm.it_cell);   // (lane of the node) << 8 | cell
+        uint32_t * const mask_sm = reinterpret_cast<uint32_t *>(sm.it_mask);   // per node: accepting cells
+        int npair;
+        {
+          uint32_t x = __popc(pm);
+#pragma unroll
+          for(int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if(lane >= o) x += y;
+          }
+          npair = (int)__shfl_sync(0xffffffffu, x, 31);
+          uint32_t off = x - __popc(pm);
+          for(uint32_t rest = pm; rest; rest &= rest - 1) pair_sm[off++] = (uint16_t)((lane << 8) | (__ffs(rest) - 1));
+          mask_sm[lane] = 0u;
+        }
+        __syncwarp();
+        for(int pi = lane; pi < npair; pi += 32) {
+          const int slot = pair_sm[pi] >> 8, ci = pair_sm[pi] & 255;
+          const NodeRec & rec = t.noderec[sm.q_node[eb + slot]];
+          double nmn[D], nmx[D];
+#pragma unroll
+          for(int d = 0; d < D; ++d) { nmn[d] = rec.bmin[d]; nmx[d] = rec.bmax[d]; }
+          const WcInfo<D> & G = sm.cell[ci];
+          bool ok = true;
+          if(G.has_node) {
+            bool sep = false;
+#pragma unroll
+            for(int d = 0; d < D; ++d) sep = sep || (nmx[d] < G.gmn[d]) || (G.gmx[d] < nmn[d]);
+            ok = !sep;
+          }
+          // quick reject (conservative, exact outcome): the node box is farther than hmax from every position of G
+          if(ok) ok = box_gap2<D>(nmn, nmx, G.tmn, G.tmx) <= G.hmax2;
+          if(ok) {
+            int q = 0;
+#pragma unroll
+            for(int d = 0; d < D; ++d) q |= (int)((nmn[d] + nmx[d]) > (G.tmn[d] + G.tmx[d])) << d;
+            const LeafRec rr = reps[(size_t)(g0 + ci) * (1 << D) + q];
+            double p[D];
+#pragma unroll
+            for(int d = 0; d < D; ++d) p[d] = rr.x[d];
+            bool acc = sphere_box<D>(nmn, nmx, p, rr.h);
+            for(int k = G.first; k < G.first + G.P && !acc; ++k) {
+#pragma unroll
+              for(int d = 0; d < D; ++d) p[d] = c.f[F_POS + d][k];
+              acc = sphere_box<D>(nmn, nmx, p, c.f[F_H][k]);
+            }
+            ok = acc;
+          }
+          if(ok) atomicOr(&mask_sm[slot], 1u << ci);
+        }
+        __syncwarp();
+        const uint32_t mask = mask_sm[lane];
+        if(!mask) lmask = 0;
+        __syncwarp();
         // (c) the leaf children of the 32 entries, flattened over the lanes
         uint32_t x = __popc(lmask);
 #pragma unroll
