@@ -125,7 +125,8 @@ __host__ __device__ inline void nl_tile_range(int C, int ti, int & tb, int & tc)
   tc = q + (tj < r ? 1 : 0);
 }
 struct __align__(16) TileDir {
-  uint32_t row[8];     // per warp: its first row of the tile in the list arena (it owns 1 + the longest list of its lanes)
+  uint32_t row[8];     // per warp: its first row of the tile in the list arena
+  uint32_t cmax[8];    // per warp: the longest list of its lanes in this tile (the warp owns 1 + cmax rows)
 };
 // one entry of a super cell's node list as the per-block filter reads it
 struct __align__(16) SlRec {

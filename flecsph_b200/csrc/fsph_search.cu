@@ -880,6 +880,16 @@ __device__ __forceinline__ void sts_u16(const uint32_t a, const uint32_t v) {
   asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((uint16_t)v));
 }
 
+// shared -> global copy of `bytes` (a multiple of 16, both sides 16-byte aligned) by the TMA engine; returns once the
+// source may be overwritten.  The fence makes the generic-proxy writes of the staged rows visible to the async proxy.
+__device__ __forceinline__ void bulk_store_rows(void * dst, const void * src_shared, const uint32_t bytes) {
+  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(src_shared);
+  asm volatile("fence.proxy.async.shared::cta;\n\t"
+               "cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\t"
+               "cp.async.bulk.commit_group;\n\t"
+               "cp.async.bulk.wait_group.read 0;" :: "l"(dst), "r"(sa), "r"(bytes) : "memory");
+}
+
 template<int D>
 __device__ __forceinline__ bool lane_pair_tests_fast(const CandRec * __restrict__ c4, const int sentinel, const uint16_t * __restrict__ cst,
   const PairGrid & g, const int cx0, const int cx1, const int cy0, const int cy1, const int cz0, const int cz1, const float * af, const float h0f,
@@ -1218,11 +1228,14 @@ __global__ void __launch_bounds__(SR_NT, FSPH_SR_OCC) k_block_pairs(Tree t, Cols
           if(rb + 1 + cmax > rows_cap) overflow = true;
           __syncwarp();
           if(!overflow) {
-            if(lane == 0) sr.dir[dir0 + ti].row[warp] = (uint32_t)rb;
+            if(lane == 0) { sr.dir[dir0 + ti].row[warp] = (uint32_t)rb; sr.dir[dir0 + ti].cmax[warp] = (uint32_t)cmax; }
             uint16_t * dst = sr.nl + rb * 32;
             if(cmax <= SR_LROWS) {
-              // rows past a lane's own count are zeroed (the sweeps read whole rows)
-              for(int j = 0; j <= cmax; ++j) dst[j * 32 + lane] = j <= cnt ? lbuf[warp][j][lane] : (uint16_t)0;
+              // rows past a lane's own count are zeroed (the sweeps read whole rows); then the warp's 1 + cmax staged rows,
+              // contiguous in shared and in global memory, leave with one TMA bulk store
+              for(int j = cnt + 1; j <= cmax; ++j) lbuf[warp][j][lane] = (uint16_t)0;
+              __syncwarp();
+              if(lane == 0) bulk_store_rows(dst, &lbuf[warp][0][0], (uint32_t)(1 + cmax) * 64u);
             }
             else {
               // a lane has more neighbours in this tile than the staging area holds (rare): the tests are repeated,
@@ -1239,7 +1252,7 @@ __global__ void __launch_bounds__(SR_NT, FSPH_SR_OCC) k_block_pairs(Tree t, Cols
       }
       else {
         // warps without bodies own no rows
-        for(int tj = lane; tj < nt; tj += 32) sr.dir[dir0 + chk * NL_CHUNK_TILES + tj].row[warp] = 0u;
+        for(int tj = lane; tj < nt; tj += 32) { sr.dir[dir0 + chk * NL_CHUNK_TILES + tj].row[warp] = 0u; sr.dir[dir0 + chk * NL_CHUNK_TILES + tj].cmax[warp] = 0u; }
       }
     }
     if(active && !overflow) c.nneigh[body0 + tid] = nn;

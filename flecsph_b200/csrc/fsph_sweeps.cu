@@ -225,6 +225,10 @@ template<int D> struct SphKernel<D, FSPH_KERNEL_SINC> {
 
 // ---- candidate tile columns per sweep ---------------------------------------------------------------------
 // which neighbour fields a sweep gathers into shared memory; positions come first, the rest in a fixed order
+#ifndef FSPH_SW_ROWS_SMEM
+#define FSPH_SW_ROWS_SMEM 1
+#endif
+constexpr int ROW_STAGE = 48;   // list rows per (tile, warp) staged in shared memory (longer lists are read from global memory)
 template<int D, int OP, int CM, int VISC> struct TileCols {
   static constexpr bool ACCX = OP == OP_ACC || OP == OP_ACCV;
   static constexpr bool ENER = OP == OP_DUDT || OP == OP_DEDT;
@@ -265,7 +269,14 @@ template<int D, int OP, int CM, int VISC> struct TileCols {
     if(hasAL && j == iAL) return F_ALPHA;
     return F_DIVV;
   }
-  static constexpr size_t smem_bytes() { return (size_t)NF * NL_TILE * 8 + (hasIDX ? NL_TILE * 4 : 0); }
+  __host__ __device__ static constexpr size_t tile_bytes() { return (size_t)NF * NL_TILE * 8 + (hasIDX ? NL_TILE * 4 : 0); }
+  // The warps' list rows of a tile are fetched by TMA bulk copies into shared memory (ROW_STAGE rows + the count row per
+  // warp) while the tile's candidate columns are being gathered: measured to pay for the density and the energy sweeps
+  // (density 22.1 -> 21.1 ms at 64 M); the acceleration sweep, at its register limit, loses (39.7 -> 49.6 ms) and keeps
+  // reading its rows from global memory.
+  static constexpr bool ROWS_SMEM = FSPH_SW_ROWS_SMEM && !ACCX && OP != OP_ALPHA &&
+                                    tile_bytes() + (size_t)(BLK_BODIES / 32) * (ROW_STAGE + 1) * 64 + 64 <= 74 * 1024;
+  static constexpr size_t smem_bytes() { return tile_bytes() + (ROWS_SMEM ? (size_t)(BLK_BODIES / 32) * (ROW_STAGE + 1) * 64 + 64 : 0); }
 };
 
 // state of the particle a thread owns + its accumulators
@@ -588,53 +599,125 @@ __global__ void __launch_bounds__(BLK_BODIES, SweepOcc<OP>::MINB) k_sweep(Cols c
   Own<D> o;
   load_own<D, OP, VISC>(o, c, body0 + tid, active);
 
-  const int ntile = nl_ntiles(C);
-  for(int ti = 0; ti < ntile; ++ti) {
-    // tile ti starts at candidate tb of the block and holds tc of them
-    int tb, tc;
-    nl_tile_range(C, ti, tb, tc);
-    // this warp's rows of the tile
-    const uint64_t rb = warp < nwarp_act ? sr.dir[dir0 + ti].row[warp] : 0u;
-    const uint16_t * rows = sr.nl + rb * 32 + lane;
-    const int cnt = warp < nwarp_act ? rows[0] : 0;
-    const int cmax = __reduce_max_sync(0xffffffffu, cnt);
-    __syncthreads();
-    {
-      // all candidate indices of this thread first, then the column gathers: 2 x NF loads in flight
-      constexpr int LPT = NL_TILE / NT;
-      int pidx[LPT];
-#pragma unroll
-      for(int u = 0; u < LPT; ++u) {
-        const int i = tid + u * NT;
-        pidx[u] = i < tc ? sr.cand[co + tb + i] : -1;
+  if(TC::ROWS_SMEM) {
+    // ---- variant with the list rows staged in shared memory by TMA -------------------------------------------------
+    uint16_t * const lrow = reinterpret_cast<uint16_t *>(smem_raw + TC::tile_bytes()) + (size_t)warp * (ROW_STAGE + 1) * 32;
+    const uint32_t lrow_s = (uint32_t)__cvta_generic_to_shared(lrow);
+    const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(smem_raw + TC::tile_bytes() + (size_t)NT / 32 * (ROW_STAGE + 1) * 64) + warp * 8;
+    uint32_t phase = 0;
+    if(lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar_s));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    const int ntile = nl_ntiles(C);
+    for(int ti = 0; ti < ntile; ++ti) {
+      int tb, tc;
+      nl_tile_range(C, ti, tb, tc);
+      const uint64_t rb = warp < nwarp_act ? sr.dir[dir0 + ti].row[warp] : 0u;
+      const int cmax = warp < nwarp_act ? (int)sr.dir[dir0 + ti].cmax[warp] : 0;
+      const bool staged = cmax <= ROW_STAGE && warp < nwarp_act;
+      __syncthreads();   // the previous tile's columns and staged rows are no longer read
+      if(staged && lane == 0) {
+        // the warp's 1 + cmax rows are contiguous: one bulk copy, completion signalled on the warp's mbarrier
+        const uint32_t bytes = (uint32_t)(1 + cmax) * 64u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar_s), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(lrow_s), "l"(sr.nl + rb * 32), "r"(bytes), "r"(mbar_s) : "memory");
       }
+      {
+        constexpr int LPT = NL_TILE / NT;
+        int pidx[LPT];
 #pragma unroll
-      for(int u = 0; u < LPT; ++u) {
-        const int i = tid + u * NT;
-        if(pidx[u] >= 0) {
-          if(TC::hasIDX) tidx[i] = pidx[u];
+        for(int u = 0; u < LPT; ++u) {
+          const int i = tid + u * NT;
+          pidx[u] = i < tc ? sr.cand[co + tb + i] : -1;
+        }
 #pragma unroll
-          for(int j = 0; j < NF; ++j) tile[j][i] = c.f[TC::col(j)][pidx[u]];
+        for(int u = 0; u < LPT; ++u) {
+          const int i = tid + u * NT;
+          if(pidx[u] >= 0) {
+            if(TC::hasIDX) tidx[i] = pidx[u];
+#pragma unroll
+            for(int j = 0; j < NF; ++j) tile[j][i] = c.f[TC::col(j)][pidx[u]];
+          }
         }
       }
+      __syncthreads();
+      const uint16_t * list = sr.nl + rb * 32 + lane;   // lists longer than the staging area: straight from global memory
+      if(staged) {
+        uint32_t done = 0;
+        while(!done)
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(done) : "r"(mbar_s), "r"(phase) : "memory");
+        phase ^= 1u;
+        list = lrow + lane;
+      }
+      const int cnt = warp < nwarp_act ? list[0] : 0;
+      int e0 = cmax > 0 ? list[32] : 0, e1 = cmax > 1 ? list[64] : 0;
+      for(int j = 0; j < cmax; j += 2) {
+        const bool v0 = j < cnt, v1 = j + 1 < cnt;
+        const int ci0 = v0 ? e0 : 0, ci1 = v1 ? e1 : 0;
+        const size_t slot0 = (size_t)(rb + 1 + j) * 32 + lane, slot1 = slot0 + 32;
+        double a0 = 0.0, a1 = 0.0, p0 = 0.0, p1 = 0.0;
+        if(A_RD) { a0 = v0 ? pair_a[slot0] : 0.0; a1 = v1 ? pair_a[slot1] : 0.0; }
+        if(P_RD) { p0 = v0 ? pair_pi[slot0] : 0.0; p1 = v1 ? pair_pi[slot1] : 0.0; }
+        if(j + 2 < cmax) e0 = list[(3 + j) * 32];
+        if(j + 3 < cmax) e1 = list[(4 + j) * 32];
+        pair_body<D, K, OP, CM, VISC>(o, tile, tidx, pp, ci0, v0, a0, p0);
+        pair_body<D, K, OP, CM, VISC>(o, tile, tidx, pp, ci1, v1, a1, p1);
+        if(A_WR) { if(v0) pair_a[slot0] = a0; if(v1) pair_a[slot1] = a1; }
+        if(P_WR) { if(v0) pair_pi[slot0] = p0; if(v1) pair_pi[slot1] = p1; }
+      }
     }
-    __syncthreads();
-    // uniform pair loop over the lanes' lists, two pairs per iteration (independent fp64 dependency chains); the
-    // entries of the next iteration are loaded before this one is evaluated
-    int e0 = cmax > 0 ? rows[32] : 0, e1 = cmax > 1 ? rows[64] : 0;
-    for(int j = 0; j < cmax; j += 2) {
-      const bool v0 = j < cnt, v1 = j + 1 < cnt;
-      const int ci0 = v0 ? e0 : 0, ci1 = v1 ? e1 : 0;
-      const size_t slot0 = (size_t)(rb + 1 + j) * 32 + lane, slot1 = slot0 + 32;
-      double a0 = 0.0, a1 = 0.0, p0 = 0.0, p1 = 0.0;
-      if(A_RD) { a0 = v0 ? pair_a[slot0] : 0.0; a1 = v1 ? pair_a[slot1] : 0.0; }
-      if(P_RD) { p0 = v0 ? pair_pi[slot0] : 0.0; p1 = v1 ? pair_pi[slot1] : 0.0; }
-      if(j + 2 < cmax) e0 = rows[(3 + j) * 32];
-      if(j + 3 < cmax) e1 = rows[(4 + j) * 32];
-      pair_body<D, K, OP, CM, VISC>(o, tile, tidx, pp, ci0, v0, a0, p0);
-      pair_body<D, K, OP, CM, VISC>(o, tile, tidx, pp, ci1, v1, a1, p1);
-      if(A_WR) { if(v0) pair_a[slot0] = a0; if(v1) pair_a[slot1] = a1; }
-      if(P_WR) { if(v0) pair_pi[slot0] = p0; if(v1) pair_pi[slot1] = p1; }
+  }
+  else {
+    const int ntile = nl_ntiles(C);
+    for(int ti = 0; ti < ntile; ++ti) {
+      // tile ti starts at candidate tb of the block and holds tc of them
+      int tb, tc;
+      nl_tile_range(C, ti, tb, tc);
+      // this warp's rows of the tile
+      const uint64_t rb = warp < nwarp_act ? sr.dir[dir0 + ti].row[warp] : 0u;
+      const uint16_t * rows = sr.nl + rb * 32 + lane;
+      const int cnt = warp < nwarp_act ? rows[0] : 0;
+      const int cmax = __reduce_max_sync(0xffffffffu, cnt);
+      __syncthreads();
+      {
+        // all candidate indices of this thread first, then the column gathers: 2 x NF loads in flight
+        constexpr int LPT = NL_TILE / NT;
+        int pidx[LPT];
+  #pragma unroll
+        for(int u = 0; u < LPT; ++u) {
+          const int i = tid + u * NT;
+          pidx[u] = i < tc ? sr.cand[co + tb + i] : -1;
+        }
+  #pragma unroll
+        for(int u = 0; u < LPT; ++u) {
+          const int i = tid + u * NT;
+          if(pidx[u] >= 0) {
+            if(TC::hasIDX) tidx[i] = pidx[u];
+  #pragma unroll
+            for(int j = 0; j < NF; ++j) tile[j][i] = c.f[TC::col(j)][pidx[u]];
+          }
+        }
+      }
+      __syncthreads();
+      // uniform pair loop over the lanes' lists, two pairs per iteration (independent fp64 dependency chains); the
+      // entries of the next iteration are loaded before this one is evaluated
+      int e0 = cmax > 0 ? rows[32] : 0, e1 = cmax > 1 ? rows[64] : 0;
+      for(int j = 0; j < cmax; j += 2) {
+        const bool v0 = j < cnt, v1 = j + 1 < cnt;
+        const int ci0 = v0 ? e0 : 0, ci1 = v1 ? e1 : 0;
+        const size_t slot0 = (size_t)(rb + 1 + j) * 32 + lane, slot1 = slot0 + 32;
+        double a0 = 0.0, a1 = 0.0, p0 = 0.0, p1 = 0.0;
+        if(A_RD) { a0 = v0 ? pair_a[slot0] : 0.0; a1 = v1 ? pair_a[slot1] : 0.0; }
+        if(P_RD) { p0 = v0 ? pair_pi[slot0] : 0.0; p1 = v1 ? pair_pi[slot1] : 0.0; }
+        if(j + 2 < cmax) e0 = rows[(3 + j) * 32];
+        if(j + 3 < cmax) e1 = rows[(4 + j) * 32];
+        pair_body<D, K, OP, CM, VISC>(o, tile, tidx, pp, ci0, v0, a0, p0);
+        pair_body<D, K, OP, CM, VISC>(o, tile, tidx, pp, ci1, v1, a1, p1);
+        if(A_WR) { if(v0) pair_a[slot0] = a0; if(v1) pair_a[slot1] = a1; }
+        if(P_WR) { if(v0) pair_pi[slot0] = p0; if(v1) pair_pi[slot1] = p1; }
+      }
     }
   }
   if(active) store_own<D, OP, VISC>(o, c, pp, status);
