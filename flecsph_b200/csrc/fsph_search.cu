@@ -826,7 +826,10 @@ struct __align__(16) CandRec {
   float x[3], h2;
 };
 constexpr int SR_CAP = NL_CHUNK;              // candidate records in shared memory (+ the sentinel)
-constexpr int SR_NCELL = 2048;                // cells of the grid (at most)
+#ifndef FSPH_SR_NCELL
+#define FSPH_SR_NCELL 2048
+#endif
+constexpr int SR_NCELL = FSPH_SR_NCELL;        // cells of the grid (at most)
 constexpr int SR_CST = SR_NCELL + 16;         // entries of a tile's cell table
 constexpr int SM_CM = (SR_CAP + 1) * 16;
 constexpr int SM_CS = SM_CM + (SR_CAP + 8) * 2;

@@ -34,6 +34,30 @@ def test_tree_and_neighbors_bit_exact(name, kw):
     assert np.array_equal(G.get(capi.COL_NNEIGH), np.diff(R.neighbor_lists()[0]).astype(np.int32))
 
 
+@pytest.mark.parametrize("scale,jitter", [(1.8, 0.0), (2.6, 0.2)])
+def test_wide_neighbourhoods_bit_exact(scale, jitter):
+    """Smoothing lengths scaled up until a block has several chunks of candidates (> 1536) and a lane more neighbours in
+    one tile than the staging areas hold (> 48: rows written straight to global memory by the pair kernel, read from
+    global memory by the sweeps): neighbour sets bit-exact, density and acceleration sweeps 1e-10."""
+    f, par, dim = case("random", n=6000, seed=21, h_jitter=jitter)
+    f = dict(f)
+    f["h"] = f["h"] * scale
+    f["velhalf"] = f["vel"].copy()
+    f["cs"] = 0.5 + np.random.default_rng(0).random(len(f["mass"]))
+    f["e"] = f["u"] + 0.5 * (f["vel"] ** 2).sum(1)
+    G, R = make_system("cuda", f, par, dim), make_system(oracle_backend(dim), f, par, dim)
+    G.update_iteration(); R.update_iteration()
+    assert_tree_equal(G, R)
+    G.apply_in_smoothinglength(capi.SWEEP_NEIGHBORS_ONLY); R.apply_in_smoothinglength(capi.SWEEP_NEIGHBORS_ONLY)
+    assert_neighbors_equal(G, R)
+    nn = G.get(capi.COL_NNEIGH)
+    assert nn.mean() > (150 if scale < 2 else 400), nn.mean()
+    G.apply_in_smoothinglength(capi.SWEEP_DENSITY); R.apply_in_smoothinglength(capi.SWEEP_DENSITY)
+    assert_fields_close(G, R, ["rho", "P", "cs"], 1e-10)
+    G.apply_in_smoothinglength(capi.SWEEP_ACCELERATION); R.apply_in_smoothinglength(capi.SWEEP_ACCELERATION)
+    assert_fields_close(G, R, ["acc"], 1e-10)
+
+
 SWEEP_CASES = [("sedov", dict(nx=12)), ("random", dict(n=3000, seed=3, h_jitter=0.2)),
                ("random", dict(n=1500, dim=2, seed=4, h_jitter=0.1)), ("sod", dict(nx=100)),
                ("random", dict(n=2500, seed=6, par=dict(sph_kernel="cubic spline"))),
