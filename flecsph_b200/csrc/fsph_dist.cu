@@ -34,6 +34,9 @@
 #include <cstring>
 #include <memory>
 #include <stdexcept>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include "fsph_internal.h"
 
 namespace fsph {
@@ -758,12 +761,14 @@ static void dist_update_iteration_t(System & s) {
       for(int k = 0; k < 3; ++k) { g.rlo[q][k] = all[(size_t)7 * q + k]; g.rhi[q][k] = all[(size_t)7 * q + 3 + k]; }
     }
   }
+  ph.reset(new PhaseScope(s, "dd:let_bitmap"));
   d.bitmap.reserve(g.bitmap_words * 4);
   d.bitmap_all.reserve(g.bitmap_words * 4 * P);
   FSPH_CUDA_OK(cudaMemsetAsync(d.bitmap.p, 0, g.bitmap_words * 4, s.stream));
   FSPH_LAUNCH((k_occupancy<D>), blocks(s.n), 256, s.stream, s.col_key.as<uint64_t>(), s.n, g.gb, d.bitmap.as<uint32_t>());
   cm.all_gather(d.bitmap.p, d.bitmap_all.p, g.bitmap_words * 4, s.stream);
 
+  ph.reset(new PhaseScope(s, "dd:let_nodes"));
   // 6. sender-side walk: destination masks of nodes (top-down, level by level) and of bodies
   const int nn = s.tree.nnodes;
   const int64_t nc = s.tree.ncells, n = s.n;
@@ -775,9 +780,14 @@ static void dist_update_iteration_t(System & s) {
     const int b = s.level_node_begin[k], e = s.level_node_begin[k + 1];
     if(e > b) FSPH_LAUNCH((k_let_nodes<D>), blocks(e - b, 128), 128, s.stream, s.tree, b, e, g, d.bitmap_all.as<uint32_t>(), nmask);
   }
+  ph.reset(new PhaseScope(s, "dd:let_leaves"));
   FSPH_LAUNCH((k_let_leaves<D>), blocks(nc, 128), 128, s.stream, s.tree, s.cols(), nc, g, d.bitmap_all.as<uint32_t>(), nmask, emask);
+  ph.reset(new PhaseScope(s, "dd:let_select"));
   FSPH_LAUNCH(k_count_bits, (unsigned)std::min<int64_t>(blocks(n), 148 * 8), 256, s.stream, emask, n, P, ctr);
   FSPH_LAUNCH(k_count_bits, (unsigned)std::min<int64_t>(blocks(nn), 148 * 8), 256, s.stream, nmask, (int64_t)nn, P, ctr + DD_MAX_RANKS);
+  const bool dd_debug = getenv("FSPH_DEBUG_DD") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double tdbg[8] = {now(), 0, 0, 0, 0, 0, 0, 0};
   std::vector<unsigned long long> hc(2 * DD_MAX_RANKS);
   uint32_t st = 0;
   FSPH_CUDA_OK(cudaMemcpyAsync(hc.data(), ctr, hc.size() * 8, cudaMemcpyDeviceToHost, s.stream));
@@ -785,6 +795,7 @@ static void dist_update_iteration_t(System & s) {
   FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
   if(st & ERR_DD_CAPACITY) throw std::runtime_error("more boundary-path nodes than DD_MAX_PATH");
 
+  tdbg[1] = now();
   d.send_cnt.assign(P, 0); d.send_off.assign(P, 0); d.recv_cnt.assign(P, 0); d.recv_off.assign(P, 0);
   std::vector<size_t> rs_cnt(P, 0), rs_off(P, 0), rr_cnt(P, 0), rr_off(P, 0);
   size_t nsend = 0, nrs = 0;
@@ -793,8 +804,8 @@ static void dist_update_iteration_t(System & s) {
     rs_cnt[q] = (size_t)hc[DD_MAX_RANKS + q]; rs_off[q] = nrs; nrs += rs_cnt[q];
   }
   d.nsend = (int64_t)nsend;
-  d.send_idx.reserve(std::max<size_t>(nsend, 1) * 4);
-  d.recs_send.reserve(std::max<size_t>(nrs, 1) * sizeof(NodeBoxRec));
+  d.send_idx.reserve_roomy(std::max<size_t>(nsend, 1) * 4);
+  d.recs_send.reserve_roomy(std::max<size_t>(nrs, 1) * sizeof(NodeBoxRec));
   {
     // the bodies / nodes with any destination are few: select them once, then split the short lists per destination
     const int64_t m = std::max<int64_t>(n, nn);
@@ -808,19 +819,23 @@ static void dist_update_iteration_t(System & s) {
       uint32_t nsel = 0;
       FSPH_CUDA_OK(cudaMemcpyAsync(&nsel, ex + cnt, 4, cudaMemcpyDeviceToHost, s.stream));
       FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
-      bidx.reserve(std::max<size_t>(nsel, 1) * 4);
-      bmask.reserve(std::max<size_t>(nsel, 1) * 4);
+      bidx.reserve_roomy(std::max<size_t>(nsel, 1) * 4);
+      bmask.reserve_roomy(std::max<size_t>(nsel, 1) * 4);
       if(nsel) FSPH_LAUNCH(k_select, blocks(cnt), 256, s.stream, mask, f, ex, cnt, bidx.as<uint32_t>(), bmask.as<uint32_t>());
       return (int64_t)nsel;
     };
+    tdbg[2] = now();
     const int64_t nsel_b = select(emask, n, d.sel_idx, d.sel_mask);
+    tdbg[3] = now();
     for(int q = 0; q < P; ++q) {
       if(!d.send_cnt[q]) continue;
       FSPH_LAUNCH(k_bit_flag, blocks(nsel_b), 256, s.stream, d.sel_mask.as<uint32_t>(), nsel_b, q, f);
       exclusive_scan_u32(s, f, ex, nsel_b, nullptr);
       FSPH_LAUNCH(k_compact_sel, blocks(nsel_b), 256, s.stream, f, ex, nsel_b, d.sel_idx.as<uint32_t>(), d.send_idx.as<uint32_t>() + d.send_off[q]);
     }
+    tdbg[4] = now();
     const int64_t nsel_n = select(nmask, nn, d.sel_idx, d.sel_mask);
+    tdbg[5] = now();
     for(int q = 0; q < P; ++q) {
       if(!rs_cnt[q]) continue;
       FSPH_LAUNCH(k_bit_flag, blocks(nsel_n), 256, s.stream, d.sel_mask.as<uint32_t>(), nsel_n, q, f);
@@ -830,6 +845,12 @@ static void dist_update_iteration_t(System & s) {
     }
   }
 
+  if(dd_debug) {
+    FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
+    tdbg[6] = now();
+    fprintf(stderr, "[dd rank %d] n %lld nn %d nsend %zu nrecs %zu | host ms: counts+sync %.2f reserve %.2f select_b %.2f loop_b %.2f select_n %.2f loop_n+sync %.2f\n",
+      R, (long long)n, nn, nsend, nrs, tdbg[1] - tdbg[0], tdbg[2] - tdbg[1], tdbg[3] - tdbg[2], tdbg[4] - tdbg[3], tdbg[5] - tdbg[4], tdbg[6] - tdbg[5]);
+  }
   ph.reset(new PhaseScope(s, "dd:halo_exchange"));
   // 7. halo exchange: counts, then every live column straight into the tail of the column, then the node records
   {
@@ -862,8 +883,8 @@ static void dist_update_iteration_t(System & s) {
       else p4.p[n4++] = c.first->as<uint32_t>();
     }
     const size_t row = ((size_t)8 * n8 + (size_t)4 * n4 + 7) & ~(size_t)7;   // bytes per body (blocks stay 8-byte aligned)
-    d.sendbuf.reserve(std::max<size_t>(nsend, 1) * row);
-    d.recvbuf.reserve(std::max<size_t>(ng, 1) * row);
+    d.sendbuf.reserve_roomy(std::max<size_t>(nsend, 1) * row);
+    d.recvbuf.reserve_roomy(std::max<size_t>(ng, 1) * row);
     for(int q = 0; q < P; ++q) {
       const size_t cnt = d.send_cnt[q];
       so[q] = d.send_off[q] * row; sc[q] = cnt * row; ro[q] = d.recv_off[q] * row; rc[q] = d.recv_cnt[q] * row;
@@ -884,7 +905,7 @@ static void dist_update_iteration_t(System & s) {
       FSPH_LAUNCH((k_unpack_cols<uint32_t, ColPtrs4>), dim3(blocks(cnt), (unsigned)n4), 256, s.stream, p4, dst, (int64_t)cnt,
         reinterpret_cast<const uint32_t *>(base + cnt * 8 * n8));
     }
-    d.recs_recv.reserve(std::max<size_t>(nrr, 1) * sizeof(NodeBoxRec));
+    d.recs_recv.reserve_roomy(std::max<size_t>(nrr, 1) * sizeof(NodeBoxRec));
     for(int q = 0; q < P; ++q) {
       so[q] = rs_off[q] * sizeof(NodeBoxRec); sc[q] = rs_cnt[q] * sizeof(NodeBoxRec);
       ro[q] = rr_off[q] * sizeof(NodeBoxRec); rc[q] = rr_cnt[q] * sizeof(NodeBoxRec);
@@ -902,7 +923,7 @@ static void dist_update_iteration_t(System & s) {
     int64_t n_glow = 0;
     for(int q = 0; q < R; ++q) n_glow += (int64_t)d.recv_cnt[q];
     s.own_begin = n_glow;
-    d.ghost_pos.reserve(std::max<size_t>(ng, 1) * 4);
+    d.ghost_pos.reserve_roomy(std::max<size_t>(ng, 1) * 4);
     if(ng) FSPH_LAUNCH(k_ghost_pos, blocks((int64_t)ng), 256, s.stream, d.ghost_pos.as<uint32_t>(), (int64_t)ng, n_glow, s.n_owned);
     if(n_glow > 0) {
       s.b_perm.reserve((size_t)n_total * 4);
@@ -1006,8 +1027,8 @@ void dist_refresh_ghosts(System & s) {
   for(int k = 0; k < s.dim; ++k) { fields.push_back(F_VEL + k); fields.push_back(F_VELH + k); }
   const size_t nf = fields.size();
   const size_t nsend = (size_t)d.nsend, ng = (size_t)d.nghost;
-  d.sendbuf.reserve(std::max<size_t>(nsend * nf, 1) * 8);
-  d.recvbuf.reserve(std::max<size_t>(ng * nf, 1) * 8);
+  d.sendbuf.reserve_roomy(std::max<size_t>(nsend * nf, 1) * 8);
+  d.recvbuf.reserve_roomy(std::max<size_t>(ng * nf, 1) * 8);
   // layout: [peer][field][body of that peer's list]
   if(nf > 16) throw std::runtime_error("too many refresh fields");
   FieldPtrs fp;

@@ -47,6 +47,8 @@ struct DevBuf {
   void * p = nullptr;
   size_t cap = 0;
   void reserve(size_t bytes);  // grows with 12 % slack (contents NOT preserved)
+  void reserve_roomy(size_t bytes) { if(bytes > cap) reserve(bytes + bytes / 2); }  // halo-sized buffers: their sizes move by several
+                                                                                    // per cent from step to step, and cudaFree + cudaMalloc cost ~40 ms
   void reserve_exact(size_t bytes);  // grows to exactly `bytes` (for buffers that swap roles: capacities converge)
   void grow_keep(size_t bytes, size_t keep, cudaStream_t st);  // grows, first `keep` bytes preserved
   void release();
