@@ -498,7 +498,13 @@ __global__ void __launch_bounds__(256) k_wc_info(Tree t, Cols c, Search sr, WcIn
 // The warps of a CTA take consecutive blocks (same super cell: its list is shared through L1); no block barriers.
 constexpr int WK_WARPS = 4;
 constexpr int WK_NT = WK_WARPS * 32;
-constexpr int WK_Q = 256;        // queued nodes per round of (b) + (c)
+#ifndef FSPH_WK_Q
+#define FSPH_WK_Q 256
+#endif
+#ifndef FSPH_WK_OCC
+#define FSPH_WK_OCC 8
+#endif
+constexpr int WK_Q = FSPH_WK_Q;  // queued nodes per round of (b) + (c)
 constexpr int WK_ITEMS = 32 * 8; // leaf children of 32 queue entries
 template<int D> struct WalkSmem {
   WcInfo<D> cell[BLK_CELLS];
@@ -510,7 +516,7 @@ template<int D> struct WalkSmem {
 };
 
 template<int D>
-__global__ void __launch_bounds__(WK_NT, 8) k_block_walk(Tree t, Cols c, Search sr, const WcInfo<D> * __restrict__ wci, const LeafRec * __restrict__ reps, int64_t * __restrict__ scratch,
+__global__ void __launch_bounds__(WK_NT, FSPH_WK_OCC) k_block_walk(Tree t, Cols c, Search sr, const WcInfo<D> * __restrict__ wci, const LeafRec * __restrict__ reps, int64_t * __restrict__ scratch,
   int scratch_cap, SearchCursors * __restrict__ cur, unsigned long long cand_cap, unsigned long long dir_cap, int64_t * __restrict__ wcand,
   uint32_t * __restrict__ status) {
   __shared__ WalkSmem<D> sm_all[WK_WARPS];
@@ -1292,7 +1298,7 @@ static void neighbor_search_t(System & s) {
     PhaseScope ph(s, "search:cells");
     FSPH_LAUNCH((k_wc_info<D>), (unsigned)((sr.nwc + 15) / 16), 256, s.stream, s.tree, s.cols(), sr, wci, reps);
   }
-  const int walk_grid = std::min((nblk + WK_WARPS - 1) / WK_WARPS, 148 * 8);
+  const int walk_grid = std::min((nblk + WK_WARPS - 1) / WK_WARPS, 148 * FSPH_WK_OCC);
   const int pair_grid = std::min(nblk, 148 * FSPH_SR_OCC * 2);
   int scratch_cap = s.search_scratch_cap;
   // capacities: from the previous search of this system (scaled when the body count drifts, e.g. with ghosts), else a
