@@ -63,12 +63,16 @@ class Params(C.Structure):
     ]
 
 
+class StreamOut(C.Structure):   # fsph_stream_out
+    _fields_ = [("col", C.c_int32), ("comp", C.c_int32), ("host", C.c_void_p)]
+
+
 # every symbol include/flecsph_b200.h declares
 SYMBOLS = [
     "fsph_default_params", "fsph_create", "fsph_destroy", "fsph_last_error", "fsph_backend", "fsph_resize",
     "fsph_nbodies", "fsph_set_column", "fsph_get_column", "fsph_set_component", "fsph_get_component", "fsph_launch_count", "fsph_upload_aos", "fsph_download_aos", "fsph_set_time",
     "fsph_get_time", "fsph_advance_time", "fsph_update_iteration", "fsph_reset_ghosts", "fsph_sweep", "fsph_apply",
-    "fsph_reduce", "fsph_gravitation_fmm", "fsph_get_range", "fsph_get_smoothinglength", "fsph_step",
+    "fsph_reduce", "fsph_gravitation_fmm", "fsph_get_range", "fsph_get_smoothinglength", "fsph_step", "fsph_step_streamed",
     "fsph_tree_num_nodes", "fsph_tree_get_nodes", "fsph_tree_get_leaf_depth", "fsph_neighbor_lists",
     "fsph_phase_times", "fsph_set_time_state", "fsph_get_time_state", "fsph_tree_root",
     "fsph_comm_unique_id", "fsph_comm_init_nccl", "fsph_local_group_create", "fsph_local_group_destroy",
@@ -77,7 +81,7 @@ SYMBOLS = [
     "fsph_generate_lattice", "fsph_count_within", "fsph_id_fill",
 ]
 # entry points only the product library has to provide (the checkers under oracle/ may omit them)
-PRODUCT_ONLY = {"fsph_set_time_state", "fsph_get_time_state", "fsph_tree_root", "fsph_comm_unique_id",
+PRODUCT_ONLY = {"fsph_step_streamed", "fsph_set_time_state", "fsph_get_time_state", "fsph_tree_root", "fsph_comm_unique_id",
                 "fsph_comm_init_nccl", "fsph_local_group_create", "fsph_local_group_destroy", "fsph_comm_init_local",
                 "fsph_comm_rank", "fsph_comm_size", "fsph_nghosts", "fsph_dd_choose_splitters", "fsph_dd_align_splitter",
                 "fsph_measure_fp64_tflops", "fsph_measure_copy_gbs", "fsph_generate_lattice", "fsph_count_within",
@@ -137,6 +141,7 @@ def load(path):
         "fsph_get_range": (i32, [vp, vp, vp]),
         "fsph_get_smoothinglength": (dbl, [vp]),
         "fsph_step": (i32, [vp, i32]),
+        "fsph_step_streamed": (i32, [vp, i32, vp, i32]),
         "fsph_tree_num_nodes": (i64, [vp]),
         "fsph_tree_get_nodes": (i32, [vp] + [vp] * 8),
         "fsph_tree_get_leaf_depth": (i32, [vp, vp]),
@@ -364,6 +369,13 @@ class BodySystem:
 
     def step(self, initial=False):
         self._ck(self.lib.fsph_step(self.h, 1 if initial else 0))
+
+    def step_streamed(self, outputs, initial=False):
+        """fsph_step_streamed: `outputs` = [(column, component, address of a pinned host buffer)]."""
+        arr = (StreamOut * len(outputs))()
+        for k, (col, comp, ptr) in enumerate(outputs):
+            arr[k].col, arr[k].comp, arr[k].host = col, comp, ptr
+        self._ck(self.lib.fsph_step_streamed(self.h, 1 if initial else 0, C.cast(arr, C.c_void_p), len(outputs)))
 
     # -- introspection ------------------------------------------------------
     def tree_nodes(self):

@@ -54,6 +54,7 @@ PhysParams System::phys() const {
   p.relax_gamma = par.relaxation_gamma;
   p.repulsion_radius = par.relaxation_repulsion_radius;
   p.repulsion_gamma = par.relaxation_repulsion_gamma;
+  p.fuse_kick_v = fuse_kick_v ? 1 : 0;
   return p;
 }
 

@@ -137,6 +137,44 @@ void do_sweep(System & s, int op) {
   sweep(s, op);
 }
 
+// device address and element size of one component of a C-ABI column
+static const void * column_source(System & s, int col, int comp, size_t & esz) {
+  esz = 8;
+  if(col >= FSPH_COL_POS && col <= FSPH_COL_GACC) {
+    if(comp < 0 || comp >= s.dim) throw std::runtime_error("bad component");
+    return s.col[VEC_FIELD[col] + comp].p;
+  }
+  if(scalar_field(s, col) >= 0) return s.col[scalar_field(s, col)].p;
+  if(col == FSPH_COL_ID) return s.col_id.p;
+  if(col == FSPH_COL_KEY) return s.col_key.p;
+  if(col == FSPH_COL_TYPE) { esz = 4; return s.col_type.p; }
+  if(col == FSPH_COL_NNEIGH) { esz = 4; return s.col_nneigh.p; }
+  throw std::runtime_error("bad column");
+}
+
+// fsph_step_streamed: the listed columns (all the remaining ones when `cols` is null) are final from here on; their
+// owned range goes to the host on the side stream, ordered after everything queued on the main stream so far
+static void stream_flush(System & s, const int * cols, int ncols) {
+  if(s.stream_out.empty()) return;
+  bool any = false;
+  for(auto & e : s.stream_out) {
+    if(e.done) continue;
+    bool take = cols == nullptr;
+    for(int k = 0; k < ncols && !take; ++k) take = e.col == cols[k];
+    if(!take) continue;
+    if(!any) {
+      FSPH_CUDA_OK(cudaEventRecord(s.side_event, s.stream));
+      FSPH_CUDA_OK(cudaStreamWaitEvent(s.side_stream, s.side_event, 0));
+      any = true;
+    }
+    size_t esz;
+    const char * src = static_cast<const char *>(column_source(s, e.col, e.comp, esz));
+    const int64_t first = s.has_ghosts ? s.own_begin : 0, cnt = s.n_owned_or_n();
+    FSPH_CUDA_OK(cudaMemcpyAsync(e.host, src + (size_t)first * esz, (size_t)cnt * esz, cudaMemcpyDeviceToHost, s.side_stream));
+    e.done = true;
+  }
+}
+
 void do_step(System & s, int initial) {
   // app/drivers/hydro/main_driver.cc:102-277 (+ newtonian/main_driver.cc:218-222)
   const fsph_params & P = s.par;
@@ -190,8 +228,12 @@ void do_step(System & s, int initial) {
       reduce(s, FSPH_GET_SET_ADAPTIVE_TIMESTEP, nullptr, 0);
     }
   };
+  static const int cols_after_update[] = {FSPH_COL_ID, FSPH_COL_MASS, FSPH_COL_POS};
+  static const int cols_after_acceleration[] = {FSPH_COL_ACC, FSPH_COL_GACC};
+  static const int cols_after_kick[] = {FSPH_COL_VEL};
   if(initial) {
     do_update_iteration(s);
+    stream_flush(s, cols_after_update, 3);
     A(FSPH_APPLY_EOS_INIT);
     if(P.thermokinetic_formulation) A(FSPH_APPLY_SET_TOTAL_ENERGY);
     if(cullen) A(FSPH_APPLY_INITIALIZE_ALPHA);
@@ -199,6 +241,8 @@ void do_step(System & s, int initial) {
     A(FSPH_APPLY_SAVE_VELOCITYHALF);
     acceleration();
     gravity();
+    stream_flush(s, cols_after_acceleration, 2);
+    stream_flush(s, cols_after_kick, 1);   // the first iteration does not kick
     timestep();
     if(P.evolve_internal_energy) energy_passes();
   }
@@ -229,10 +273,19 @@ void do_step(System & s, int initial) {
       catch(...) { s.skip_dead_columns = false; throw; }
       s.skip_dead_columns = false;
     }
+    stream_flush(s, cols_after_update, 3);
     do_sweep(s, 100);
-    acceleration();
+    // without gravity and relaxation terms nothing touches the acceleration between the sweep and the second kick: the
+    // sweep applies it to each body it finishes (one element-wise pass less)
+    const bool fuse_kick = !P.enable_fmm && !relaxing;
+    s.fuse_kick_v = fuse_kick;
+    try { acceleration(); }
+    catch(...) { s.fuse_kick_v = false; throw; }
+    s.fuse_kick_v = false;
     gravity();
-    A(FSPH_APPLY_LEAPFROG_KICK_V);
+    stream_flush(s, cols_after_acceleration, 2);
+    if(!fuse_kick) A(FSPH_APPLY_LEAPFROG_KICK_V);
+    stream_flush(s, cols_after_kick, 1);
     do_reset_ghosts(s);
     if(P.evolve_internal_energy) {
       energy_passes();
@@ -366,6 +419,8 @@ void fsph_destroy(fsph_system * s) {
   delete s->comm;
   s->comm = nullptr;
   release_buffers(*s);
+  if(s->side_event) cudaEventDestroy(s->side_event);
+  if(s->side_stream) cudaStreamDestroy(s->side_stream);
   if(s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -628,7 +683,36 @@ double fsph_get_smoothinglength(fsph_system * s) {
   return r;
 }
 
+static int32_t step_impl(fsph_system * s, int32_t initial);
+
 int32_t fsph_step(fsph_system * s, int32_t initial) {
+  if(s) s->stream_out.clear();
+  return step_impl(s, initial);
+}
+
+int32_t fsph_step_streamed(fsph_system * s, int32_t initial, const fsph_stream_out * out, int32_t nout) {
+  if(!s) return 1;
+  int32_t rc = guarded(s, [&]() {
+    if(nout < 0 || (nout > 0 && !out)) throw std::runtime_error("fsph_step_streamed: bad output list");
+    if(!s->side_stream) {
+      FSPH_CUDA_OK(cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking));
+      FSPH_CUDA_OK(cudaEventCreateWithFlags(&s->side_event, cudaEventDisableTiming));
+    }
+    s->stream_out.clear();
+    for(int k = 0; k < nout; ++k) s->stream_out.push_back({out[k].col, out[k].comp, out[k].host, false});
+  });
+  if(rc) return rc;
+  rc = step_impl(s, initial);
+  const int32_t rc2 = guarded(s, [&]() {
+    if(rc == 0) stream_flush(*s, nullptr, 0);
+    const cudaError_t e = cudaStreamSynchronize(s->side_stream);
+    s->stream_out.clear();
+    FSPH_CUDA_OK(e);
+  });
+  return rc ? rc : rc2;
+}
+
+static int32_t step_impl(fsph_system * s, int32_t initial) {
   return guarded(s, [&]() {
     s->timing = true;
     s->phases.clear();

@@ -171,6 +171,7 @@ struct PhysParams {
   double alpha_max, visc_l, visc_delta;                      // Cullen-Dehnen viscosity
   double gamma2, rho_thr;                                    // piecewise polytrope
   double relax_beta, relax_gamma, repulsion_radius, repulsion_gamma;   // relaxation phase
+  int fuse_kick_v;   // the acceleration sweep of fsph_step also applies the second velocity kick (integration.h:71-79)
 };
 
 // eos::compute_pressure + compute_soundspeed (include/physics/eos/eos.h): ideal gas :166-183 from the specific internal
@@ -237,6 +238,7 @@ struct System {
   // inside fsph_step the sort need not permute columns that are recomputed before their next read
   bool skip_dead_columns = false;
   bool in_step = false;   // inside fsph_step: the order of the sweeps and ghost refreshes is the driver's
+  bool fuse_kick_v = false;   // ... and the acceleration sweep applies leapfrog_kick_v to the bodies it finishes
   bool dead_col[NF64] = {};
   bool col_used[NF64] = {};   // optional columns this system allocates (fsph_create)
 
@@ -271,6 +273,12 @@ struct System {
   int nlevels = 0;
   double kernel_width = 2.0;
   uint32_t host_err = 0;
+
+  // fsph_step_streamed: results copied out on a side stream as soon as they are final
+  struct StreamOut { int col, comp; void * host; bool done; };
+  std::vector<StreamOut> stream_out;
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t side_event = nullptr;
 
   // phase timing of the last fsph_step
   std::vector<Phase> phases;

@@ -563,7 +563,16 @@ __device__ __forceinline__ void store_own(const Own<D> & o, const Cols & c, cons
       c.f[F_GACC + d][ia] = 0.0;
     }
     c.f[F_GPOT][ia] = 0.0;
-    if(OP == OP_ACCV) c.f[F_VSIG][ia] = o.vsig;
+    if(OP == OP_ACCV) {
+      c.f[F_VSIG][ia] = o.vsig;
+      if(pp.fuse_kick_v) {
+        // leapfrog_kick_v (integration.h:71-79) right here: v += dt/2 (a + g) with g = 0, operation by operation as the
+        // element-wise pass does it (no sweep of this step reads v of another body before the ghost refresh that follows)
+#pragma unroll
+        for(int d = 0; d < D; ++d)
+          c.f[F_VEL + d][ia] = __dadd_rn(c.f[F_VEL + d][ia], __dmul_rn(0.5 * pp.dt, __dadd_rn(o.accv[d], 0.0)));
+      }
+    }
   }
   else if(OP == OP_DUDT) c.f[F_DUDT][ia] = o.Prho2_a * o.acc0 + .5 * o.acc1;
   else {

@@ -233,6 +233,21 @@ double fsph_get_smoothinglength(fsph_system * s);                 /* getSmoothin
  * `initial` != 0 runs the first-iteration branch (hydro/main_driver.cc:102-173). */
 int32_t fsph_step(fsph_system * s, int32_t initial);
 
+/* fsph_step with its results streamed to the host while the step is still running
+ * (the host-resident body array of the reference, bodies_system.h:352-358, wants
+ * every field back after an iteration): component `comp` of column `col` of the
+ * bodies this rank owns goes to the pinned host buffer `host` on a side stream as
+ * soon as the iteration has written it for the last time -- ids, masses and
+ * positions right after update_iteration, accelerations after the acceleration
+ * sweep (and gravity), velocities after the second kick, the rest at the end.
+ * Returns when every copy has arrived.  Same results as fsph_step followed by
+ * fsph_get_component for each entry. */
+typedef struct fsph_stream_out {
+  int32_t col, comp;
+  void * host;
+} fsph_stream_out;
+int32_t fsph_step_streamed(fsph_system * s, int32_t initial, const fsph_stream_out * out, int32_t nout);
+
 /* --- introspection used by the parity tests ------------------------------- */
 /* Octree node table, sorted by key: tree_topology::cofm_ (tree_topology.h:2103)
  * with node fields of cofm_u (tree_types.h:51-141). */

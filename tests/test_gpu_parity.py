@@ -211,3 +211,22 @@ def test_pair_cache_modes(monkeypatch, cache, name, kw):
     for it in range(3):
         G.step(initial=(it == 0)); R.step(initial=(it == 0))
         assert_fields_close(G, R, names, 1e-10 if it < 2 else 1e-9)
+
+
+def test_step_streamed_equals_step_then_download():
+    """fsph_step_streamed: columns copied out while the step is still running == fsph_step + fsph_get_component."""
+    import torch
+    f, par, dim = case("sedov", nx=16)
+    A, B = make_system("cuda", f, par, dim), make_system("cuda", f, par, dim)
+    n = A.nbodies()
+    cols = [(capi.COL_POS, 3), (capi.COL_VEL, 3), (capi.COL_ACC, 3), (capi.COL_GACC, 3), (capi.COL_MASS, 1), (capi.COL_H, 1), (capi.COL_E, 1),
+            (capi.COL_DEDT, 1), (capi.COL_RHO, 1), (capi.COL_P, 1), (capi.COL_U, 1), (capi.COL_VSIG, 1), (capi.COL_DT, 1), (capi.COL_ID, 1)]
+    bufs = {(col, c): torch.empty(n, dtype=torch.int64 if col == capi.COL_ID else torch.float64).pin_memory() for col, nc in cols for c in range(nc)}
+    plan = [(col, c, t.data_ptr()) for (col, c), t in bufs.items()]
+    for it in range(3):
+        A.step(initial=(it == 0))
+        B.step_streamed(plan, initial=(it == 0))
+        for (col, c), t in bufs.items():
+            ref = np.empty(n, np.int64 if col == capi.COL_ID else np.float64)
+            A.get_component(col, c, ref.ctypes.data)
+            assert np.array_equal(t.numpy(), ref), (it, capi.COL_NAMES[col], c)
