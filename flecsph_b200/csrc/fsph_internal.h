@@ -142,7 +142,8 @@ struct Search {
   // that any of its work cells can accept (superset by a conservative box test)
   int32_t * wc_super;    // [nwc] super cell of each work cell
   int32_t * super_cell;  // [nsuper] index into Tree::cell
-  uint64_t * sl_off;     // [nsuper+1] offsets into sl_nodes
+  uint64_t * sl_off;     // [nsuper] offset of each super cell's list in sl_nodes / sl_rec
+  int32_t * sl_len;      // [nsuper] its length
   int32_t * sl_nodes;    // node indices
   struct SlRec * sl_rec; // the same nodes with their boxes in fp32 (rounded outwards): what the per-block filter reads
   int32_t nsuper;
@@ -252,7 +253,8 @@ struct System {
   DevBuf b_cell, b_cell_parent, b_cell_desc, b_cell_desc2, b_child_begin, b_child_end, b_node_start, b_node_depth, b_sub;
   DevBuf b_noderec, b_leafrec;
   DevBuf b_nmass, b_ncom[3], b_nradius, b_nlap, b_nbmin[3], b_nbmax[3];
-  DevBuf b_wc_super, b_super_cell, b_sl_off, b_sl_nodes, b_sl_rec;
+  DevBuf b_wc_super, b_super_cell, b_sl_off, b_sl_len, b_sl_nodes, b_sl_rec, b_sl_stage;
+  uint64_t est_sl = 0;   // entries of the previous step's node lists (capacity of the single-pass list build)
   DevBuf b_wc_cell, b_cand, b_cnt0, b_cnt1;
   DevBuf b_status, b_red, b_levels, b_search_scratch;
   DevBuf b_blk_wc, b_blk_meta, b_dir, b_nl, b_super_queue, b_wcinfo, b_wcrep, b_wcand;

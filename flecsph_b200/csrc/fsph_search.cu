@@ -129,9 +129,16 @@ __device__ __forceinline__ double box_gap2(const double * amn, const double * am
 // G accepts C only if some body sphere of G touches C's box (intersects_sphere_box, tree_topology.h:348), hence the
 // distance between C's box and the tight box of S's positions is at most the largest h in S.  The nodes that pass
 // and have leaf children are S's list (in walk order: fixed).  MODE 0 counts, MODE 1 fills (offsets: prefix sum).
+// MODE 2 does it in one pass when the previous search left an estimate of the total: the list is staged in a per-CTA strip
+// of global memory, the super cell reserves its share of the arrays with one atomicAdd when its walk is done and copies
+// the strip over (lists land in completion order; sl_off / sl_len say where).  A list longer than the strip or a total
+// beyond the capacity raises ERR_SEARCH_CAPACITY and the host falls back to the two passes.
+constexpr int SW_STAGE = 16384;   // entries of a CTA's staging strip
 template<int D, int MODE>
 __global__ void __launch_bounds__(SW_NT) k_super_walk(Tree t, Cols c, Search sr, const int32_t * __restrict__ super_first_wc, int32_t * __restrict__ gqueue,
-  uint32_t * __restrict__ status) {
+  uint32_t * __restrict__ status, int32_t * __restrict__ gstage, unsigned long long * __restrict__ sl_total, unsigned long long sl_cap) {
+  __shared__ unsigned long long base_sm;
+  int32_t * const stage = MODE == 2 ? gstage + (size_t)blockIdx.x * SW_STAGE : nullptr;
   constexpr int NT = SW_NT;
   __shared__ uint32_t scan_sm[NT / 32];
   __shared__ double red_sm[NT / 32][2 * D + 1];
@@ -145,6 +152,7 @@ __global__ void __launch_bounds__(SW_NT) k_super_walk(Tree t, Cols c, Search sr,
     if(super_first_wc[sidx] < 0) {
       // no work cell of this rank inside (remote copies only): no list
       if(MODE == 0 && tid == 0) sr.sl_off[sidx] = 0;
+      if(MODE == 2 && tid == 0) { sr.sl_off[sidx] = 0; sr.sl_len[sidx] = 0; }
       continue;
     }
     int start, P;
@@ -242,6 +250,7 @@ __global__ void __launch_bounds__(SW_NT) k_super_walk(Tree t, Cols c, Search sr,
             sl.pad = 0;
             out_rec[lpos] = sl;
           }
+          if(MODE == 2 && lpos < (uint32_t)SW_STAGE) stage[lpos] = nd;
           ++lpos;
         }
       }
@@ -256,7 +265,38 @@ __global__ void __launch_bounds__(SW_NT) k_super_walk(Tree t, Cols c, Search sr,
       cur ^= 1;
     }
     if(MODE == 0 && tid == 0) sr.sl_off[sidx] = nlist;
+    if(MODE == 2) {
+      if(tid == 0) base_sm = atomicAdd(sl_total, (unsigned long long)nlist);
+      __syncthreads();
+      const unsigned long long base = base_sm;
+      const bool fits = nlist <= (uint32_t)SW_STAGE && base + nlist <= sl_cap;
+      if(tid == 0) {
+        sr.sl_off[sidx] = base;
+        sr.sl_len[sidx] = fits ? (int32_t)nlist : 0;
+        if(!fits) atomicOr(status, (uint32_t)ERR_SEARCH_CAPACITY);
+      }
+      if(fits)
+        for(uint32_t i = tid; i < nlist; i += NT) {
+          const int nd = stage[i];
+          const NodeRec rec = t.noderec[nd];
+          SlRec sl;
+#pragma unroll
+          for(int d = 0; d < 3; ++d) {
+            sl.mn[d] = d < D ? __double2float_rd(rec.bmin[d]) : 0.f;
+            sl.mx[d] = d < D ? __double2float_ru(rec.bmax[d]) : 0.f;
+          }
+          sl.node = nd;
+          sl.pad = 0;
+          sr.sl_nodes[base + i] = nd;
+          sr.sl_rec[base + i] = sl;
+        }
+    }
   }
+}
+
+__global__ void __launch_bounds__(256) k_sl_len(const uint64_t * __restrict__ off, int32_t * __restrict__ len, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n) len[i] = (int32_t)(off[i + 1] - off[i]);
 }
 
 __global__ void __launch_bounds__(256) k_super_compact(const uint32_t * __restrict__ at, const uint32_t * __restrict__ ex, int64_t n,
@@ -353,29 +393,60 @@ static void build_super_lists(System & s) {
   // blocks
   FSPH_LAUNCH((k_block_pack<0>), (nsuper + 127) / 128, 128, s.stream, s.tree, sr, first_wc, bcnt, nullptr);
   exclusive_scan_u32(s, bcnt, bcnt, nsuper, nullptr);
-  // node lists
-  const int sw_grid = (int)std::min<uint32_t>(nsuper, 148 * 6);
-  s.b_super_queue.reserve((size_t)sw_grid * (2 * SW_QCAP + SW_QCAP / 4) * 4);
-  int32_t * gq = s.b_super_queue.as<int32_t>();
-  FSPH_LAUNCH((k_super_walk<D, 0>), sw_grid, SW_NT, s.stream, s.tree, s.cols(), sr, first_wc, gq, status);
-  exclusive_scan_u64(s, sr.sl_off, sr.sl_off, nsuper, nullptr);
-  uint64_t tot = 0;
   uint32_t st = 0, nblk = 0;
-  FSPH_CUDA_OK(cudaMemcpyAsync(&tot, sr.sl_off + nsuper, 8, cudaMemcpyDeviceToHost, s.stream));
-  FSPH_CUDA_OK(cudaMemcpyAsync(&st, status, 4, cudaMemcpyDeviceToHost, s.stream));
   FSPH_CUDA_OK(cudaMemcpyAsync(&nblk, bcnt + nsuper, 4, cudaMemcpyDeviceToHost, s.stream));
   FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
-  if(st & ERR_QUEUE_OVERFLOW) throw std::runtime_error("neighbour search: the node frontier of a super cell exceeds 16384 nodes per level");
   if(nblk == 0) throw std::runtime_error("no blocks");
-  s.b_sl_nodes.reserve((size_t)std::max<uint64_t>(tot, 1) * 4);
-  sr.sl_nodes = s.b_sl_nodes.as<int32_t>();
-  s.b_sl_rec.reserve((size_t)std::max<uint64_t>(tot, 1) * sizeof(SlRec));
-  sr.sl_rec = s.b_sl_rec.as<SlRec>();
   s.b_blk_wc.reserve((size_t)(nblk + 1) * 4);
   sr.blk_wc = s.b_blk_wc.as<int32_t>();
   sr.nblk = (int)nblk;
   FSPH_LAUNCH((k_block_pack<1>), (nsuper + 127) / 128, 128, s.stream, s.tree, sr, first_wc, nullptr, bcnt);
-  FSPH_LAUNCH((k_super_walk<D, 1>), sw_grid, SW_NT, s.stream, s.tree, s.cols(), sr, first_wc, gq, status);
+  // node lists
+  const int sw_grid = (int)std::min<uint32_t>(nsuper, 148 * 6);
+  s.b_super_queue.reserve((size_t)sw_grid * (2 * SW_QCAP + SW_QCAP / 4) * 4);
+  s.b_sl_len.reserve((size_t)nsuper * 4);
+  sr.sl_len = s.b_sl_len.as<int32_t>();
+  int32_t * gq = s.b_super_queue.as<int32_t>();
+  unsigned long long * sl_total = reinterpret_cast<unsigned long long *>(status + 24);
+  if(s.est_sl > 0 && s.est_n > 0 && !getenv("FSPH_SL_TWO_PASS")) {
+    // one pass, capacity from the previous search
+    const double r = std::max(1.0, (double)s.n / (double)s.est_n);
+    const unsigned long long cap = (unsigned long long)(s.est_sl * r * 1.25) + 65536;
+    s.b_sl_nodes.reserve((size_t)cap * 4);
+    s.b_sl_rec.reserve((size_t)cap * sizeof(SlRec));
+    s.b_sl_stage.reserve((size_t)sw_grid * SW_STAGE * 4);
+    sr.sl_nodes = s.b_sl_nodes.as<int32_t>();
+    sr.sl_rec = s.b_sl_rec.as<SlRec>();
+    FSPH_CUDA_OK(cudaMemsetAsync(sl_total, 0, 8, s.stream));
+    FSPH_LAUNCH((k_super_walk<D, 2>), sw_grid, SW_NT, s.stream, s.tree, s.cols(), sr, first_wc, gq, status, s.b_sl_stage.as<int32_t>(), sl_total, cap);
+    unsigned long long tot = 0;
+    FSPH_CUDA_OK(cudaMemcpyAsync(&tot, sl_total, 8, cudaMemcpyDeviceToHost, s.stream));
+    FSPH_CUDA_OK(cudaMemcpyAsync(&st, status, 4, cudaMemcpyDeviceToHost, s.stream));
+    FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
+    if(st & ERR_QUEUE_OVERFLOW) throw std::runtime_error("neighbour search: the node frontier of a super cell exceeds 16384 nodes per level");
+    if(!(st & ERR_SEARCH_CAPACITY)) {
+      s.est_sl = tot;
+      FSPH_CUDA_OK(cudaGetLastError());
+      return;
+    }
+    const uint32_t cleared = st & ~(uint32_t)ERR_SEARCH_CAPACITY;
+    FSPH_CUDA_OK(cudaMemcpyAsync(status, &cleared, 4, cudaMemcpyHostToDevice, s.stream));
+  }
+  // two passes: count, offsets, fill
+  FSPH_LAUNCH((k_super_walk<D, 0>), sw_grid, SW_NT, s.stream, s.tree, s.cols(), sr, first_wc, gq, status, nullptr, nullptr, 0ull);
+  exclusive_scan_u64(s, sr.sl_off, sr.sl_off, nsuper, nullptr);
+  uint64_t tot = 0;
+  FSPH_CUDA_OK(cudaMemcpyAsync(&tot, sr.sl_off + nsuper, 8, cudaMemcpyDeviceToHost, s.stream));
+  FSPH_CUDA_OK(cudaMemcpyAsync(&st, status, 4, cudaMemcpyDeviceToHost, s.stream));
+  FSPH_CUDA_OK(cudaStreamSynchronize(s.stream));
+  if(st & ERR_QUEUE_OVERFLOW) throw std::runtime_error("neighbour search: the node frontier of a super cell exceeds 16384 nodes per level");
+  s.b_sl_nodes.reserve((size_t)std::max<uint64_t>(tot, 1) * 4);
+  sr.sl_nodes = s.b_sl_nodes.as<int32_t>();
+  s.b_sl_rec.reserve((size_t)std::max<uint64_t>(tot, 1) * sizeof(SlRec));
+  sr.sl_rec = s.b_sl_rec.as<SlRec>();
+  FSPH_LAUNCH(k_sl_len, (nsuper + 255) / 256, 256, s.stream, sr.sl_off, sr.sl_len, (int)nsuper);
+  FSPH_LAUNCH((k_super_walk<D, 1>), sw_grid, SW_NT, s.stream, s.tree, s.cols(), sr, first_wc, gq, status, nullptr, nullptr, 0ull);
+  s.est_sl = tot;
   FSPH_CUDA_OK(cudaGetLastError());
 }
 
@@ -581,7 +652,7 @@ __global__ void __launch_bounds__(WK_NT, FSPH_WK_OCC) k_block_walk(Tree t, Cols 
     const int PB = sm.cell[K - 1].first + sm.cell[K - 1].P - body0;
     const int sidx = sr.wc_super[g0];
     const uint64_t sl_lo = sr.sl_off[sidx];
-    const int sl_n = (int)(sr.sl_off[sidx + 1] - sl_lo);
+    const int sl_n = sr.sl_len[sidx];
     uint32_t ncands = 0;
     int nq = 0;
     double hcand = 0.0;   // largest h among the candidates
@@ -844,7 +915,8 @@ constexpr int SM_TOTAL = SM_LBUF + SR_NW * (SR_LROWS + 1) * 64;
 // during the sort the list staging area holds the cell counters / cursors and the sorted walk positions
 constexpr int SM_CNT = SM_LBUF;
 constexpr int SM_WIDX = SM_CNT + SR_CST * 4;
-static_assert(SM_WIDX + SR_CAP * 2 <= SM_TOTAL, "sort scratch does not fit the list staging area");
+constexpr int SM_CCELL = SM_WIDX + SR_CAP * 2;
+static_assert(SM_CCELL + SR_CAP * 2 <= SM_TOTAL, "sort scratch does not fit the list staging area");
 constexpr int block_pairs_smem() { return SM_TOTAL; }
 
 // the grid of a chunk and the division by the chunk's tile count
@@ -1022,6 +1094,7 @@ __global__ void __launch_bounds__(SR_NT, FSPH_SR_OCC) k_block_pairs(Tree t, Cols
   uint16_t (* const lbuf)[SR_LROWS + 1][32] = reinterpret_cast<uint16_t (*)[SR_LROWS + 1][32]>(ubuf + SM_LBUF);
   uint32_t * const cnt_sm = reinterpret_cast<uint32_t *>(ubuf + SM_CNT);                     // sort: per cell counter / cursor
   uint16_t * const widx = reinterpret_cast<uint16_t *>(ubuf + SM_WIDX);                      // sort: walk position by sorted position
+  uint16_t * const ccell = reinterpret_cast<uint16_t *>(ubuf + SM_CCELL);                    // sort: grid cell by walk position
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if(tid == 0) {
@@ -1144,7 +1217,9 @@ __global__ void __launch_bounds__(SR_NT, FSPH_SR_OCC) k_block_pairs(Tree t, Cols
         float x[3] = {0.f, 0.f, 0.f};
 #pragma unroll
         for(int d = 0; d < D; ++d) x[d] = (float)(lr.x[d] - bctr[d]);
-        atomicAdd(&cnt_sm[grid_cell<D>(g, x)], 1u);
+        const int gc = grid_cell<D>(g, x);
+        ccell[i] = (uint16_t)gc;
+        atomicAdd(&cnt_sm[gc], 1u);
       }
       __syncthreads();
       {
@@ -1172,13 +1247,7 @@ __global__ void __launch_bounds__(SR_NT, FSPH_SR_OCC) k_block_pairs(Tree t, Cols
         }
       }
       __syncthreads();
-      for(int i = tid; i < nc; i += NT) {
-        const LeafRec lr = t.leafrec[(uint32_t)strip[cbase + i]];
-        float x[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for(int d = 0; d < D; ++d) x[d] = (float)(lr.x[d] - bctr[d]);
-        widx[atomicAdd(&cnt_sm[grid_cell<D>(g, x)], 1u)] = (uint16_t)i;
-      }
+      for(int i = tid; i < nc; i += NT) widx[atomicAdd(&cnt_sm[ccell[i]], 1u)] = (uint16_t)i;
       __syncthreads();
       // the order inside a cell is that of the atomics: put every cell in walk order (cells hold ~1 candidate)
       for(int i = tid; i < ncell; i += NT) {
@@ -1355,8 +1424,10 @@ static void neighbor_search_t(System & s) {
         std::vector<int32_t> nb(nblk), nc(nblk);
         FSPH_CUDA_OK(cudaMemcpy(nb.data(), sr.blk_nbody, (size_t)nblk * 4, cudaMemcpyDeviceToHost));
         FSPH_CUDA_OK(cudaMemcpy(nc.data(), sr.blk_ncand, (size_t)nblk * 4, cudaMemcpyDeviceToHost));
-        std::vector<uint64_t> so(sr.nsuper + 1);
-        FSPH_CUDA_OK(cudaMemcpy(so.data(), sr.sl_off, (size_t)(sr.nsuper + 1) * 8, cudaMemcpyDeviceToHost));
+        std::vector<int32_t> sl(sr.nsuper);
+        FSPH_CUDA_OK(cudaMemcpy(sl.data(), sr.sl_len, (size_t)sr.nsuper * 4, cudaMemcpyDeviceToHost));
+        double sl_sum = 0;
+        for(int i = 0; i < sr.nsuper; ++i) sl_sum += sl[i];
         double sb = 0, sc = 0, sw = 0;
         int full = 0;
         for(int b = 0; b < nblk; ++b) { sb += nb[b]; sc += nc[b]; sw += (nb[b] + 31) / 32; full += nb[b] > 224; }
@@ -1365,7 +1436,7 @@ static void neighbor_search_t(System & s) {
         double sn = 0;
         for(int64_t i = 0; i < s.n; ++i) sn += nn[i];
         fprintf(stderr, "[search] n %lld nwc %d nsuper %d (list %.0f nodes) nblk %d bodies/block %.1f (>224: %.0f%%) warps/block %.2f cands/block %.0f "
-                        "tiles %llu rows %llu pairs %.4g slot efficiency %.3f\n", (long long)s.n, sr.nwc, sr.nsuper, (double)so[sr.nsuper] / sr.nsuper,
+                        "tiles %llu rows %llu pairs %.4g slot efficiency %.3f\n", (long long)s.n, sr.nwc, sr.nsuper, sl_sum / sr.nsuper,
           nblk, sb / nblk, 100.0 * full / nblk, sw / nblk, sc / nblk, (unsigned long long)tot.dir, (unsigned long long)tot.rows, sn,
           sn / ((double)tot.rows * 32));
       }

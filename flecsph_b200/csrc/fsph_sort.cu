@@ -62,7 +62,7 @@ void release_buffers(System & s) {
     &s.b_node_parent, &s.b_fmm_nodes, &s.b_fmm_out, &s.b_fmm_stack, &s.b_cell, &s.b_cell_parent, &s.b_cell_desc, &s.b_cell_desc2,
     &s.b_child_begin, &s.b_child_end, &s.b_node_start, &s.b_node_depth, &s.b_sub, &s.b_noderec, &s.b_leafrec, &s.b_nmass, &s.b_nradius,
     &s.b_nlap, &s.b_wc_super, &s.b_super_cell, &s.b_sl_off, &s.b_sl_nodes, &s.b_wc_cell, &s.b_cand,
-    &s.b_cnt0, &s.b_cnt1, &s.b_status, &s.b_red, &s.b_levels, &s.b_search_scratch, &s.b_blk_wc, &s.b_blk_meta, &s.b_dir, &s.b_nl, &s.b_super_queue, &s.b_wcinfo, &s.b_wcrep, &s.b_wcand, &s.b_sl_rec,
+    &s.b_cnt0, &s.b_cnt1, &s.b_status, &s.b_red, &s.b_levels, &s.b_search_scratch, &s.b_blk_wc, &s.b_blk_meta, &s.b_dir, &s.b_nl, &s.b_super_queue, &s.b_wcinfo, &s.b_wcrep, &s.b_wcand, &s.b_sl_rec, &s.b_sl_len, &s.b_sl_stage,
     &s.b_pair_a, &s.b_pair_pi};
   for(DevBuf * b : all) b->release();
   for(int f = 0; f < NF64; ++f) s.col[f].release();
