@@ -32,7 +32,12 @@ ALGO_BYTES_PER_UPDATE = 1386.0   # hydro thermokinetic path, fp64 
 # per-phase algorithmic bytes per particle; the neighbour search is the traversal part of the
 # density sweep in the reference (x,h 32 B read + tree summaries ~16 B read + neighbour count 4 B written)
 PHASE_BYTES = {"density": 120.0, "acceleration": 112.0, "dedt": 120.0, "dudt": 120.0, "search": 52.0, "sort": 416.0,
-               "tree": 90.0, "range_keys": 64.0, "elementwise": 404.0, "timestep": 88.0}
+               "tree": 90.0, "range_keys": 64.0, "elementwise": 404.0, "timestep": 88.0,
+               # the search's 52 B split over its two big kernels: the walk reads the tree summaries (16 B per
+               # particle), the pair kernel reads x, h of every body (32 B) and writes its neighbour count (4 B)
+               "search:walk": 16.0, "search:pairs": 36.0}
+KERNEL_OF = {"search:pairs": "k_block_pairs", "search:walk": "k_block_walk", "density": "k_sweep<density>", "acceleration": "k_sweep<acceleration + signal speed>",
+             "dedt": "k_sweep<de/dt>", "dudt": "k_sweep<du/dt>"}
 PAIR_FLOPS = {"density": 43.0, "acceleration": 77.0, "dedt": 90.0, "dudt": 82.0}   # SURVEY.md 8d, per accepted pair
 FP64_NOMINAL_TFLOPS = 37.2   # nominal B200 vector fp64 (148 SM x 64 DFMA/clk x 2 x 1.965 GHz); the measured DFMA rate of
                              # the GPU the run uses (fsph_measure_fp64_tflops) is the denominator of the fp64 fractions
@@ -286,7 +291,8 @@ def main():
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        sys.stdout.write("\n")   # the reference's own logging may have left an unterminated line
+        print(json.dumps(line), flush=True)
         return 0
 
     import torch
@@ -479,7 +485,8 @@ def main():
         return 0
     peak, how = measured_peaks()
     phases = {k: v / a.steps for k, v in phase_acc.items() if k != "total"}
-    dom = max((k for k in phases if k in ("search", "density", "acceleration", "dedt", "dudt", "sort", "tree")), key=lambda k: phases[k])
+    # the dominant KERNEL: each of these phases is one launch per step, timed with its own pair of CUDA events
+    dom = max((k for k in phases if k in ("search:pairs", "search:walk", "density", "acceleration", "dedt", "dudt")), key=lambda k: phases[k])
     dom_ms = phases[dom]
     ach = n * PHASE_BYTES[dom] / (dom_ms * 1e-3) / 1e9
     # DRAM traffic of the dominant phase from the committed ncu capture of this exact workload (profiles/), else null
@@ -489,7 +496,7 @@ def main():
         tj = json.load(open(tp))
         if dom in tj.get("phases", {}):
             traffic, traffic_src = tj["phases"][dom], "profiles/r2_traffic_64M.json (%s)" % tj["how"]
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+    roofline = {"bound": "hbm", "kernel": KERNEL_OF.get(dom, dom), "phase": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": how, "copy_gbs_this_gpu": copy_gbs,
                 "algorithmic_bytes_per_particle": PHASE_BYTES[dom], "ms_per_launch": dom_ms,
                 "note": "the dominant phase is fp64-issue / latency bound, not HBM bound (profiles/r2_ncu_*.md): see fp64 (fractions of the "
@@ -515,6 +522,7 @@ def main():
             "phases_ms": phases, "mean_neighbors": nn_mean, "wall_ms_per_step": 1e3 * t_wall / a.steps, "configs": configs}
     if "parity" in configs:
         line["parity"] = configs.pop("parity")
+    sys.stdout.write("\n")   # the reference's own logging (cpu_baseline leg) may have left an unterminated line
     print(json.dumps(line), flush=True)
     return 0
 

@@ -76,7 +76,7 @@ def traffic():
                  "msecond": 1.0, "ms": 1.0, "second": 1e3}.get(u, 1)
         per.setdefault(k, {})[r[mi]] = v * scale
     phases = {}
-    order = ["search_walk", "search", "density", "acceleration", "dedt"]     # launch order of the captured window
+    order = ["search:walk", "search:pairs", "density", "acceleration", "dedt"]     # launch order of the captured window
     for (k, m), ph in zip(per.items(), order):
         phases[ph] = m.get("dram__bytes_read.sum", 0) + m.get("dram__bytes_write.sum", 0)
         print(ph, k[:60], {a: "%.4g" % b for a, b in m.items()})
