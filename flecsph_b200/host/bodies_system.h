@@ -21,7 +21,10 @@
 #include "params.h"
 #include "utils.h"
 
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
@@ -202,6 +205,13 @@ public:
   }
 
   void update_iteration() {
+    if(getenv("FSPH_FACADE_TRACE")) {
+      // wall time from one update_iteration to the next = one driver iteration on the facade
+      static double last = -1.0;
+      const double now = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+      if(last >= 0.0) fprintf(stderr, "[facade] iteration wall %.1f ms (%lld bodies)\n", 1e3 * (now - last), (long long)fsph_nbodies(sys_));
+      last = now;
+    }
     sync_device();
     ck(fsph_update_iteration(sys_));
     localnbodies_ = fsph_nbodies(sys_);
