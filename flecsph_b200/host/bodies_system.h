@@ -22,6 +22,9 @@
 #include "utils.h"
 
 #include <chrono>
+#include <thread>
+#include <vector>
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -78,6 +81,27 @@ struct root_node_view {
   }
 };
 } // namespace fsph_host
+
+namespace fsph_host {
+// index loop over the AoS mirror on up to 16 host threads (the conversions between the 368-byte records and the device
+// columns are memory-bound: ~35 passes over the bodies per synchronisation)
+template<typename F>
+inline void parallel_for(int64_t n, F f) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  const unsigned nt = std::min<unsigned>(hw ? hw : 1u, 16u);
+  if(n < 200000 || nt <= 1) {
+    f((int64_t)0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  const int64_t chunk = (n + nt - 1) / nt;
+  for(unsigned t = 0; t < nt; ++t) {
+    const int64_t a = (int64_t)t * chunk, b = std::min<int64_t>(n, a + chunk);
+    if(a < b) th.emplace_back([=]() { f(a, b); });
+  }
+  for(auto & x : th) x.join();
+}
+}   // namespace fsph_host
 
 template<typename T, size_t D>
 class body_system
@@ -441,12 +465,12 @@ private:
     std::vector<double> v((size_t)n);
     auto vec = [&](int col, auto getter) {
       for(size_t d = 0; d < D; ++d) {
-        for(int64_t i = 0; i < n; ++i) v[i] = getter(bodies_[i])[d];
+        fsph_host::parallel_for(n, [&](int64_t a, int64_t b) { for(int64_t i = a; i < b; ++i) v[i] = getter(bodies_[i])[d]; });
         ck(fsph_set_component(sys_, col, (int)d, v.data()));
       }
     };
     auto sca = [&](int col, auto getter) {
-      for(int64_t i = 0; i < n; ++i) v[i] = getter(bodies_[i]);
+      fsph_host::parallel_for(n, [&](int64_t a, int64_t b) { for(int64_t i = a; i < b; ++i) v[i] = getter(bodies_[i]); });
       ck(fsph_set_component(sys_, col, 0, v.data()));
     };
     vec(FSPH_COL_POS, [](body & b) { return b.coordinates(); });
@@ -475,10 +499,10 @@ private:
     }
     {
       std::vector<int64_t> l((size_t)n);
-      for(int64_t i = 0; i < n; ++i) l[i] = (int64_t)bodies_[i].id();
+      fsph_host::parallel_for(n, [&](int64_t a, int64_t b) { for(int64_t i = a; i < b; ++i) l[i] = (int64_t)bodies_[i].id(); });
       ck(fsph_set_component(sys_, FSPH_COL_ID, 0, l.data()));
       std::vector<int32_t> w((size_t)n);
-      for(int64_t i = 0; i < n; ++i) w[i] = (int32_t)bodies_[i].getType();
+      fsph_host::parallel_for(n, [&](int64_t a, int64_t b) { for(int64_t i = a; i < b; ++i) w[i] = (int32_t)bodies_[i].getType(); });
       ck(fsph_set_component(sys_, FSPH_COL_TYPE, 0, w.data()));
     }
     host_newer_ = false;
@@ -498,13 +522,13 @@ private:
       std::vector<point_t> p((size_t)n);
       for(size_t d = 0; d < D; ++d) {
         ck(fsph_get_component(sys_, col, (int)d, v.data()));
-        for(int64_t i = 0; i < n; ++i) p[i][d] = v[i];
+        fsph_host::parallel_for(n, [&](int64_t a, int64_t b) { for(int64_t i = a; i < b; ++i) p[i][d] = v[i]; });
       }
-      for(int64_t i = 0; i < n; ++i) setter(bodies_[i], p[i]);
+      fsph_host::parallel_for(n, [&](int64_t a, int64_t b) { for(int64_t i = a; i < b; ++i) setter(bodies_[i], p[i]); });
     };
     auto sca = [&](int col, auto setter) {
       ck(fsph_get_component(sys_, col, 0, v.data()));
-      for(int64_t i = 0; i < n; ++i) setter(bodies_[i], v[i]);
+      fsph_host::parallel_for(n, [&](int64_t a, int64_t b) { for(int64_t i = a; i < b; ++i) setter(bodies_[i], v[i]); });
     };
     vec(FSPH_COL_POS, [](body & b, const point_t & p) { b.set_coordinates(p); });
     vec(FSPH_COL_VEL, [](body & b, const point_t & p) { b.setVelocity(p); });
