@@ -903,6 +903,9 @@ struct __align__(16) CandRec {
   float x[3], h2;
 };
 constexpr int SR_CAP = NL_CHUNK;              // candidate records in shared memory (+ the sentinel)
+#ifndef FSPH_SR_UNROLL
+#define FSPH_SR_UNROLL 8
+#endif
 #ifndef FSPH_SR_NCELL
 #define FSPH_SR_NCELL 2048
 #endif
@@ -996,7 +999,7 @@ __device__ __forceinline__ bool lane_pair_tests_fast(const CandRec * __restrict_
   if(done) zleft = 0;
   for(;;) {
 #pragma unroll
-    for(int rep = 0; rep < 4; ++rep) {
+    for(int rep = 0; rep < FSPH_SR_UNROLL; ++rep) {
       if(cur >= end) {
         const bool wrap = yleft == 0;
         row += wrap ? wrapstep : rowstep;

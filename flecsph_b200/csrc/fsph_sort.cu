@@ -195,8 +195,11 @@ __global__ void __launch_bounds__(RS_NT) k_radix_count(const uint64_t * __restri
 }
 
 // VMODE: 0 keys only, 1 values from vin, 2 values = source index
+#ifndef FSPH_RS_OCC
+#define FSPH_RS_OCC 2
+#endif
 template<int VMODE>
-__global__ void __launch_bounds__(RS_NT) k_radix_scatter(const uint64_t * __restrict__ kin, const uint32_t * __restrict__ vin,
+__global__ void __launch_bounds__(RS_NT, FSPH_RS_OCC) k_radix_scatter(const uint64_t * __restrict__ kin, const uint32_t * __restrict__ vin,
   uint64_t * __restrict__ kout, uint32_t * __restrict__ vout, int64_t n, int shift, const uint32_t * __restrict__ tile_off,
   int ntiles) {
   __shared__ uint32_t wcnt[RS_WARPS][256];
