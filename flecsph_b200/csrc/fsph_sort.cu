@@ -195,6 +195,12 @@ __global__ void __launch_bounds__(RS_NT) k_radix_count(const uint64_t * __restri
 }
 
 // VMODE: 0 keys only, 1 values from vin, 2 values = source index
+// Ranking: per warp, 16 rounds of 32 consecutive items; __match_any_sync groups the lanes of a round by digit, the
+// group's leader advances the warp's digit counter, so an item's rank follows the input order (stable).  The tile is
+// then put in digit order in shared memory and leaves in runs: items of one digit are consecutive in the tile and in
+// global memory, so the stores of a warp cover a few whole sectors instead of one sector per item (29 sectors per
+// store request before, on the pass whose digit changes fastest along the nearly sorted input).
+constexpr int RS_SMEM = RS_TILE * 8 + RS_TILE * 4 + RS_WARPS * 256 * 4 + 256 * 4 + 256 * 4 + 64;
 #ifndef FSPH_RS_OCC
 #define FSPH_RS_OCC 2
 #endif
@@ -202,11 +208,18 @@ template<int VMODE>
 __global__ void __launch_bounds__(RS_NT, FSPH_RS_OCC) k_radix_scatter(const uint64_t * __restrict__ kin, const uint32_t * __restrict__ vin,
   uint64_t * __restrict__ kout, uint32_t * __restrict__ vout, int64_t n, int shift, const uint32_t * __restrict__ tile_off,
   int ntiles) {
-  __shared__ uint32_t wcnt[RS_WARPS][256];
+  extern __shared__ __align__(16) unsigned char rs_raw[];
+  uint64_t * const skey = reinterpret_cast<uint64_t *>(rs_raw);                                  // [RS_TILE] tile in digit order
+  uint32_t * const sval = reinterpret_cast<uint32_t *>(rs_raw + RS_TILE * 8);                    // [RS_TILE]
+  uint32_t (* const wcnt)[256] = reinterpret_cast<uint32_t (*)[256]>(rs_raw + RS_TILE * 12);     // [RS_WARPS][256]
+  uint32_t * const lstart = reinterpret_cast<uint32_t *>(rs_raw + RS_TILE * 12 + RS_WARPS * 1024);   // [256] first tile slot of a digit
+  uint32_t * const gdelta = lstart + 256;                                                        // [256] global position - tile slot
+  uint32_t * const scan_sm = gdelta + 256;                                                       // [RS_WARPS]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for(int i = threadIdx.x; i < RS_WARPS * 256; i += RS_NT) (&wcnt[0][0])[i] = 0;
   __syncthreads();
-  const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * (32 * RS_IPT);
+  const int64_t tbase = (int64_t)blockIdx.x * RS_TILE;
+  const int64_t wbase = tbase + (int64_t)w * (32 * RS_IPT);
   uint64_t key[RS_IPT];
   uint32_t rank[RS_IPT];
 #pragma unroll
@@ -228,26 +241,50 @@ __global__ void __launch_bounds__(RS_NT, FSPH_RS_OCC) k_radix_scatter(const uint
   }
   __syncthreads();
   {
-    int d = threadIdx.x;  // RS_NT == 256 digits
-    uint32_t run = tile_off[(size_t)d * ntiles + blockIdx.x];
+    // thread d: the warps' counts of digit d -> exclusive prefix over the warps; the digits' tile totals -> exclusive scan
+    const int d = threadIdx.x;  // RS_NT == 256 digits
+    uint32_t run = 0;
 #pragma unroll
     for(int ww = 0; ww < RS_WARPS; ++ww) {
-      uint32_t c = wcnt[ww][d];
+      const uint32_t c = wcnt[ww][d];
       wcnt[ww][d] = run;
       run += c;
     }
+    uint32_t x = run;
+#pragma unroll
+    for(int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if(lane >= o) x += y;
+    }
+    if(lane == 31) scan_sm[w] = x;
+    __syncthreads();
+    uint32_t base = 0;
+#pragma unroll
+    for(int ww = 0; ww < RS_WARPS; ++ww)
+      if(ww < w) base += scan_sm[ww];
+    const uint32_t first = base + x - run;
+    lstart[d] = first;
+    gdelta[d] = tile_off[(size_t)d * ntiles + blockIdx.x] - first;
   }
   __syncthreads();
 #pragma unroll
   for(int r = 0; r < RS_IPT; ++r) {
-    int64_t i = wbase + r * 32 + lane;
+    const int64_t i = wbase + r * 32 + lane;
     if(i < n) {
-      uint32_t d = (uint32_t)((key[r] >> shift) & 255);
-      uint32_t dst = wcnt[w][d] + rank[r];
-      kout[dst] = key[r];
-      if(VMODE == 1) vout[dst] = vin[i];
-      if(VMODE == 2) vout[dst] = (uint32_t)i;
+      const uint32_t d = (uint32_t)((key[r] >> shift) & 255);
+      const uint32_t slot = lstart[d] + wcnt[w][d] + rank[r];
+      skey[slot] = key[r];
+      if(VMODE == 1) sval[slot] = vin[i];
+      if(VMODE == 2) sval[slot] = (uint32_t)i;
     }
+  }
+  __syncthreads();
+  const int tile_n = (int)(n - tbase < (int64_t)RS_TILE ? n - tbase : (int64_t)RS_TILE);
+  for(int j = threadIdx.x; j < tile_n; j += RS_NT) {
+    const uint64_t k = skey[j];
+    const uint32_t dst = gdelta[(uint32_t)((k >> shift) & 255)] + (uint32_t)j;
+    kout[dst] = k;
+    if(VMODE != 0) vout[dst] = sval[j];
   }
 }
 
@@ -260,9 +297,9 @@ static void radix_pass_mode(System & s, const uint64_t * kin, const uint32_t * v
   uint32_t * th = s.b_tmp[2].as<uint32_t>();
   FSPH_LAUNCH(k_radix_count, ntiles, RS_NT, s.stream, kin, n, shift, th, ntiles);
   exclusive_scan_u32(s, th, th, (int64_t)256 * ntiles, nullptr);
-  if(vmode == 0) FSPH_LAUNCH((k_radix_scatter<0>), ntiles, RS_NT, s.stream, kin, vin, kout, vout, n, shift, th, ntiles);
-  else if(vmode == 1) FSPH_LAUNCH((k_radix_scatter<1>), ntiles, RS_NT, s.stream, kin, vin, kout, vout, n, shift, th, ntiles);
-  else FSPH_LAUNCH((k_radix_scatter<2>), ntiles, RS_NT, s.stream, kin, vin, kout, vout, n, shift, th, ntiles);
+  if(vmode == 0) FSPH_LAUNCH_SMEM((k_radix_scatter<0>), ntiles, RS_NT, RS_SMEM, s.stream, kin, vin, kout, vout, n, shift, th, ntiles);
+  else if(vmode == 1) FSPH_LAUNCH_SMEM((k_radix_scatter<1>), ntiles, RS_NT, RS_SMEM, s.stream, kin, vin, kout, vout, n, shift, th, ntiles);
+  else FSPH_LAUNCH_SMEM((k_radix_scatter<2>), ntiles, RS_NT, RS_SMEM, s.stream, kin, vin, kout, vout, n, shift, th, ntiles);
   FSPH_CUDA_OK(cudaGetLastError());
 }
 
