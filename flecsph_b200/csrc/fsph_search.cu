@@ -502,25 +502,36 @@ __global__ void __launch_bounds__(256) k_wc_info(Tree t, Cols c, Search sr, WcIn
   // sphere of G touch this node box" loop tries the representative on the node's side first (pure ordering heuristic:
   // the outcome is the exact any-of-all-bodies result either way).
   uint8_t rep[NCH];
+  {
+    // one pass over the cell's bodies, all corners at once
+    unsigned long long key[NCH];
 #pragma unroll
-  for(int q = 0; q < NCH; ++q) {
-    unsigned long long key = ~0ull;
+    for(int q = 0; q < NCH; ++q) key[q] = ~0ull;
     for(int k = l16; k < P; k += 16) {
-      double d2 = 0.0;
+      double x[D];
 #pragma unroll
-      for(int d = 0; d < D; ++d) {
-        const double df = c.f[F_POS + d][start + k] - (((q >> d) & 1) ? tmx[d] : tmn[d]);
-        d2 += df * df;
+      for(int d = 0; d < D; ++d) x[d] = c.f[F_POS + d][start + k];
+#pragma unroll
+      for(int q = 0; q < NCH; ++q) {
+        double d2 = 0.0;
+#pragma unroll
+        for(int d = 0; d < D; ++d) {
+          const double df = x[d] - (((q >> d) & 1) ? tmx[d] : tmn[d]);
+          d2 += df * df;
+        }
+        const unsigned long long kk = ((unsigned long long)__double_as_longlong(d2) & ~0xffull) | (unsigned long long)k;
+        key[q] = kk < key[q] ? kk : key[q];
       }
-      const unsigned long long kk = ((unsigned long long)__double_as_longlong(d2) & ~0xffull) | (unsigned long long)k;
-      key = kk < key ? kk : key;
     }
 #pragma unroll
-    for(int o = 8; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-      key = other < key ? other : key;
+    for(int q = 0; q < NCH; ++q) {
+#pragma unroll
+      for(int o = 8; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key[q], o);
+        key[q] = other < key[q] ? other : key[q];
+      }
+      rep[q] = (uint8_t)(key[q] & 0xffull);
     }
-    rep[q] = (uint8_t)(key & 0xffull);
   }
   if(live && l16 == 0) {
     WcInfo<D> w;
