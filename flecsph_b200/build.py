@@ -39,7 +39,7 @@ def _newer(src_list, out):
 
 
 def build_cuda(verbose=False, force=False):
-    hdrs = [os.path.join(CSRC, "fsph_internal.h"), os.path.join(ROOT, "include", "flecsph_b200.h"), os.path.abspath(__file__)]
+    hdrs = [os.path.join(CSRC, "fsph_internal.h"), os.path.join(CSRC, "fsph_eforce.h"), os.path.join(ROOT, "include", "flecsph_b200.h"), os.path.abspath(__file__)]
     objs, jobs = [], []
     for key, extra in SOURCES.items():
         src, _, tag = key.partition("@")

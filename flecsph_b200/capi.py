@@ -60,6 +60,14 @@ class Params(C.Structure):
         ("sph_viscosity_alpha_max", C.c_double), ("sph_viscosity_l", C.c_double), ("sph_viscosity_delta", C.c_double),
         ("poly_gamma2", C.c_double), ("ppt_density_thr", C.c_double), ("relaxation_beta", C.c_double),
         ("relaxation_gamma", C.c_double), ("relaxation_repulsion_radius", C.c_double), ("relaxation_repulsion_gamma", C.c_double),
+        # external forces (include/physics/eforce.h)
+        ("external_force_type", C.c_char * 64), ("density_profile", C.c_char * 32),
+        ("sphere_radius", C.c_double), ("extforce_wall_powerindex", C.c_double), ("extforce_wall_steepness", C.c_double),
+        ("gravity_acceleration_constant", C.c_double), ("zero_potential_poison_value", C.c_double),
+        ("mesa_rim_width", C.c_double), ("rho_initial", C.c_double), ("pressure_initial", C.c_double),
+        ("orbital_separation", C.c_double), ("mass_neutron_star", C.c_double), ("mass_white_dwarf", C.c_double),
+        ("airfoil_size", C.c_double), ("airfoil_thickness", C.c_double), ("airfoil_camber", C.c_double),
+        ("airfoil_anchor_x", C.c_double), ("airfoil_anchor_y", C.c_double), ("airfoil_attack_angle", C.c_double),
     ]
 
 
@@ -191,9 +199,16 @@ def default_params(dim=3, lib=None, **kw):
         p.sph_viscosity_alpha_max, p.sph_viscosity_l, p.sph_viscosity_delta = 1.0, 0.05, 1.0
         p.poly_gamma2, p.ppt_density_thr = 2.5, 5e14
         p.relaxation_beta, p.relaxation_gamma, p.relaxation_repulsion_radius, p.relaxation_repulsion_gamma = 1e-6, 0.0, 0.25, 0.0
+        p.external_force_type, p.density_profile = b"none", b"constant"
+        p.sphere_radius, p.extforce_wall_powerindex, p.extforce_wall_steepness = 1.0, 5.0, 1e12
+        p.gravity_acceleration_constant, p.mesa_rim_width, p.rho_initial, p.pressure_initial = 9.81, 0.25, 1.0, 1.0
+        p.orbital_separation, p.mass_neutron_star, p.mass_white_dwarf = 2.5e9, 1.26 * 1.988435e33, 1.10 * 1.988435e33
+        p.airfoil_size, p.airfoil_thickness, p.airfoil_camber, p.airfoil_anchor_x = 2.0, 0.05, 0.1, -1.0
     for k, v in kw.items():
         if k == "sph_kernel" and isinstance(v, str):
             v = KERNELS[v.lower()]
+        if isinstance(v, str):
+            v = v.encode()
         if not hasattr(p, k):
             raise AttributeError(k)
         setattr(p, k, v)

@@ -9,6 +9,7 @@
 //   compute_average_smoothinglength :879-898, check_nans :918-958, check_negativity :962-979
 //                                                                             include/physics/default_physics.h
 //   analysis::compute_total_{mass,energy,momentum}                            include/physics/analysis.h:56-150
+//   external_force::acceleration / potential where those functors call them    include/physics/eforce.h (fsph_eforce.h)
 #include <stdexcept>
 #include <cfloat>
 #include <cmath>
@@ -67,11 +68,13 @@ struct OpList {
 struct OpAccess { uint64_t rd, wr; };
 constexpr uint64_t fbit(int f) { return uint64_t(1) << f; }
 constexpr uint64_t vbit(int f) { return fbit(f) | fbit(f + 1) | fbit(f + 2); }
-static OpAccess op_access(int op, const PhysParams & pp) {
+static OpAccess op_access(int op, const PhysParams & pp, const ExtForce & ef) {
+  // functors that evaluate the external potential / force read the position as well
+  const uint64_t pot_in = ef.n > 0 ? vbit(F_POS) : 0;
   const uint64_t eos_in = fbit(F_RHO) | fbit(F_ADIA) | (pp.eos == FSPH_EOS_WD ? fbit(F_YE) : 0) | fbit(F_P) | fbit(F_CS);
   switch(op) {
     case FSPH_APPLY_EOS_INIT: return {fbit(F_RHO) | fbit(F_P) | (pp.eos == FSPH_EOS_WD ? fbit(F_YE) : 0), fbit(F_ADIA) | fbit(F_U)};
-    case FSPH_APPLY_SET_TOTAL_ENERGY: return {vbit(F_VEL) | fbit(F_U), fbit(F_E)};
+    case FSPH_APPLY_SET_TOTAL_ENERGY: return {vbit(F_VEL) | fbit(F_U) | pot_in, fbit(F_E)};
     case FSPH_APPLY_SAVE_VELOCITYHALF: return {vbit(F_VEL), vbit(F_VELH)};
     case FSPH_APPLY_LEAPFROG_KICK_V: return {vbit(F_VEL) | vbit(F_ACC) | vbit(F_GACC), vbit(F_VEL)};
     case FSPH_APPLY_LEAPFROG_KICK_U: return {fbit(F_U) | fbit(F_DUDT), fbit(F_U)};
@@ -79,8 +82,8 @@ static OpAccess op_access(int op, const PhysParams & pp) {
     case FSPH_APPLY_LEAPFROG_DRIFT: return {vbit(F_POS) | vbit(F_VEL), vbit(F_POS)};
     case FSPH_APPLY_RECOMPUTE_P_CS: return {fbit(F_U) | fbit(F_DUDT) | eos_in, fbit(F_P) | fbit(F_CS)};
     case FSPH_APPLY_RECOMPUTE_P_CS_THERMOKINETIC:
-      return {vbit(F_VEL) | vbit(F_ACC) | fbit(F_E) | fbit(F_DEDT) | eos_in, fbit(F_U) | fbit(F_P) | fbit(F_CS)};
-    case FSPH_APPLY_COMPUTE_DT: return {fbit(F_H) | vbit(F_VEL) | vbit(F_ACC) | vbit(F_GACC) | fbit(F_VSIG) | fbit(F_U), fbit(F_DT)};
+      return {vbit(F_VEL) | vbit(F_ACC) | fbit(F_E) | fbit(F_DEDT) | eos_in | pot_in, fbit(F_U) | fbit(F_P) | fbit(F_CS)};
+    case FSPH_APPLY_COMPUTE_DT: return {fbit(F_H) | vbit(F_VEL) | vbit(F_ACC) | vbit(F_GACC) | fbit(F_VSIG) | fbit(F_U) | pot_in, fbit(F_DT)};
     case FSPH_APPLY_CHECK_NANS:
       return {vbit(F_POS) | vbit(F_VEL) | vbit(F_VELH) | vbit(F_ACC) | vbit(F_GACC) | fbit(F_MASS) | fbit(F_GPOT) | fbit(F_RHO) | fbit(F_P) |
                 fbit(F_E) | fbit(F_DEDT) | fbit(F_DUDT) | fbit(F_ADIA) | fbit(F_VSIG) | fbit(F_U), 0};
@@ -91,15 +94,23 @@ static OpAccess op_access(int op, const PhysParams & pp) {
     case FSPH_APPLY_ADD_DRAG_DUDT: return {vbit(F_VEL) | fbit(F_DUDT), fbit(F_DUDT)};
     case 100: return {fbit(F_MASS) | fbit(F_RHO), fbit(F_H)};
     case 101: return {0, fbit(F_H)};
+    case 102: return {vbit(F_POS) | vbit(F_ACC), vbit(F_ACC)};
   }
   throw std::runtime_error("unknown apply op");
 }
 
 // One functor on the body's columns held in registers (v[f] = column f of this body): the statements of the reference's
 // functors, operation by operation (this file is compiled without FMA contraction).
-template<int D>
-__device__ __forceinline__ void apply_one(double * v, const int op, const PhysParams & pp, uint32_t * __restrict__ status) {
+// EF: the system has external force / potential terms (a separate instantiation: the common case without them keeps its
+// register budget); the position is copied out of the column registers so that the terms never index `v` dynamically
+template<int D, bool EF>
+__device__ __forceinline__ void apply_one(double * v, const int op, const PhysParams & pp, const ExtForce & ef, uint32_t * __restrict__ status) {
   const double dt = pp.dt;
+  double xp[3] = {0.0, 0.0, 0.0};
+  if(EF) {
+#pragma unroll
+    for(int d = 0; d < D; ++d) xp[d] = v[F_POS + d];
+  }
   switch(op) {
     case FSPH_APPLY_EOS_INIT: {
       // eos::init: adiabatic invariant (ideal / polytropic eos.h:68-83; piecewise polytrope :337-351: K1 of the first
@@ -125,7 +136,8 @@ __device__ __forceinline__ void apply_one(double * v, const int op, const PhysPa
       double v2 = 0.0;
 #pragma unroll
       for(int d = 0; d < D; ++d) v2 = v2 + v[F_VEL + d] * v[F_VEL + d];
-      v[F_E] = .5 * v2 + v[F_U] + 0.0;
+      // ekin + eint + epot, default_physics.h:330-334
+      v[F_E] = .5 * v2 + v[F_U] + (EF ? ef_potential<D>(ef, xp) : 0.0);
     } break;
     case FSPH_APPLY_SAVE_VELOCITYHALF:
 #pragma unroll
@@ -152,7 +164,8 @@ __device__ __forceinline__ void apply_one(double * v, const int op, const PhysPa
         v2 = v2 + v[F_VEL + d] * v[F_VEL + d];
         va = va + v[F_VEL + d] * v[F_ACC + d];
       }
-      const double eint = v[F_E] - .5 * v2 - 0.0;
+      // recover_internal_energy, default_physics.h:126-144
+      const double eint = v[F_E] - .5 * v2 - (EF ? ef_potential<D>(ef, xp) : 0.0);
       if(!(eint > 0)) atomicOr(status, (uint32_t)ERR_U_NONPOS);
       v[F_U] = eint;
       const double u = eint + 0.5 * dt * (v[F_DEDT] - va);
@@ -177,10 +190,19 @@ __device__ __forceinline__ void apply_one(double * v, const int op, const PhysPa
       double dtmin = pp.cfl * fmin(fmin(dt_v, dt_a), dt_c);
       if(pp.evolve_u && pp.thermokinetic) {
         const double eint = v[F_U];
+        const double epot = EF ? ef_potential<D>(ef, xp) : 0.0;
         if(!(eint > 0)) atomicOr(status, (uint32_t)ERR_U_NONPOS);
         int it;
         for(it = 0; it < 20; ++it) {
-          const double delta_epot = 0.0, delta_egrv = -dtmin * vg;
+          double delta_epot = 0.0;
+          if(EF) {
+            // external_force::potential(pos + dtmin*vel) - epot, default_physics.h:655
+            double xn[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for(int d = 0; d < D; ++d) xn[d] = xp[d] + dtmin * v[F_VEL + d];
+            delta_epot = ef_potential<D>(ef, xn) - epot;
+          }
+          const double delta_egrv = -dtmin * vg;
           if(delta_epot + delta_egrv < eint * 0.5) break;
           dtmin *= 0.25;
         }
@@ -229,6 +251,14 @@ __device__ __forceinline__ void apply_one(double * v, const int op, const PhysPa
       v[F_H] = r * pp.eta * pp.kernel_width;
     } break;
     case 101: v[F_H] = pp.dt; break;  // uniform h (value carried in pp.dt)
+    case 102: {  // acc_a += external_force::acceleration(particle), the last statement of compute_acceleration (default_physics.h:404)
+      if(EF) {
+        double a[3] = {0.0, 0.0, 0.0};
+        ef_acceleration<D>(ef, xp, a);
+#pragma unroll
+        for(int d = 0; d < D; ++d) v[F_ACC + d] = v[F_ACC + d] + a[d];
+      }
+    } break;
   }
 }
 
@@ -238,8 +268,8 @@ __device__ __forceinline__ void apply_one(double * v, const int op, const PhysPa
 #ifndef FSPH_APPLY_OCC
 #define FSPH_APPLY_OCC 4
 #endif
-template<int D>
-__global__ void __launch_bounds__(128, FSPH_APPLY_OCC) k_apply(Cols c, int64_t n, OpList ops, PhysParams pp, uint64_t need, uint64_t dirty,
+template<int D, bool EF>
+__global__ void __launch_bounds__(128, FSPH_APPLY_OCC) k_apply(Cols c, int64_t n, OpList ops, PhysParams pp, ExtForce ef, uint64_t need, uint64_t dirty,
   uint32_t * __restrict__ status) {
   // n = number of owned bodies, starting at c.own_lo (remote copies are refreshed from their owner: reset_ghosts)
   const int64_t i = c.own_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -251,7 +281,7 @@ __global__ void __launch_bounds__(128, FSPH_APPLY_OCC) k_apply(Cols c, int64_t n
     if(f < F_MASS && (f % 3) >= D) continue;   // unused vector components
     if((need >> f) & 1ull) v[f] = c.f[f][i];
   }
-  for(int k = 0; k < ops.n; ++k) apply_one<D>(v, ops.op[k], pp, status);
+  for(int k = 0; k < ops.n; ++k) apply_one<D, EF>(v, ops.op[k], pp, ef, status);
 #pragma unroll
   for(int f = 0; f < NF64; ++f) {
     if(f < F_MASS && (f % 3) >= D) continue;
@@ -271,15 +301,18 @@ void apply_fused(System & s, const int * op_list, int nops) {
   uint64_t need = 0, dirty = 0;
   for(int j = 0; j < 8; ++j) ops.op[j] = j < nops ? op_list[j] : -1;
   for(int k = 0; k < nops; ++k) {
-    const OpAccess a = op_access(op_list[k], pp);
+    const OpAccess a = op_access(op_list[k], pp, s.ef);
     need |= a.rd | a.wr;   // a functor may write a column only for some bodies (e.g. eos::init): keep the others' values
     dirty |= a.wr;
   }
   for(int f = 0; f < NF64; ++f)
     if(!s.col_used[f]) { need &= ~fbit(f); dirty &= ~fbit(f); }
-  if(s.dim == 1) FSPH_LAUNCH((k_apply<1>), nb, 128, s.stream, s.cols(), n_own, ops, pp, need, dirty, st);
-  else if(s.dim == 2) FSPH_LAUNCH((k_apply<2>), nb, 128, s.stream, s.cols(), n_own, ops, pp, need, dirty, st);
-  else FSPH_LAUNCH((k_apply<3>), nb, 128, s.stream, s.cols(), n_own, ops, pp, need, dirty, st);
+  const bool efo = s.ef.n > 0;
+#define FSPH_APPLY_GO(DD, EE) FSPH_LAUNCH((k_apply<DD, EE>), nb, 128, s.stream, s.cols(), n_own, ops, pp, s.ef, need, dirty, st)
+  if(s.dim == 1) { if(efo) FSPH_APPLY_GO(1, true); else FSPH_APPLY_GO(1, false); }
+  else if(s.dim == 2) { if(efo) FSPH_APPLY_GO(2, true); else FSPH_APPLY_GO(2, false); }
+  else { if(efo) FSPH_APPLY_GO(3, true); else FSPH_APPLY_GO(3, false); }
+#undef FSPH_APPLY_GO
   FSPH_CUDA_OK(cudaGetLastError());
   for(int k = 0; k < nops; ++k) {
     // the cached pair viscosities depend on v_1/2, rho and c_s (fsph_sweeps.cu)
@@ -309,7 +342,7 @@ __host__ __device__ inline double red_combine(int kind, int j, double a, double 
 }
 
 template<int D>
-__global__ void __launch_bounds__(256) k_reduce(Cols c, int64_t n, int kind, int thermokinetic, int fmm, double * __restrict__ part) {
+__global__ void __launch_bounds__(256) k_reduce(Cols c, int64_t n, int kind, int thermokinetic, int fmm, ExtForce ef, double * __restrict__ part) {
   double v[3] = {0, 0, 0};
   if(kind == RED_MIN_DT) v[0] = 1e24;
   if(kind == RED_MAX_H) v[0] = -DBL_MAX;
@@ -330,7 +363,15 @@ __global__ void __launch_bounds__(256) k_reduce(Cols c, int64_t n, int kind, int
             double v2 = 0.0;
 #pragma unroll
             for(int d = 0; d < D; ++d) v2 += c.f[F_VEL + d][i] * c.f[F_VEL + d][i];
-            v[0] += m * (c.f[F_U][i] + .5 * v2);
+            // m*(ekin + eint + epot), analysis.h:104-112
+            double epot = 0.0;
+            if(ef.n > 0) {
+              double x[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+              for(int d = 0; d < D; ++d) x[d] = c.f[F_POS + d][i];
+              epot = ef_potential<D>(ef, x);
+            }
+            v[0] += m * (.5 * v2 + c.f[F_U][i] + epot);
           }
           if(fmm) v[0] += .5 * m * c.f[F_GPOT][i];
         }
@@ -417,9 +458,9 @@ static void run_reduce_local(System & s, int kind, double out[3]) {
   }
   int nb = (int)std::min<int64_t>((s.n + 255) / 256, 148 * 4);
   double * part = reduce_scratch(s, (size_t)nb * 3 + 16);
-  if(s.dim == 1) FSPH_LAUNCH((k_reduce<1>), nb, 256, s.stream, s.cols(), s.n, kind, s.par.thermokinetic_formulation, s.par.enable_fmm, part);
-  else if(s.dim == 2) FSPH_LAUNCH((k_reduce<2>), nb, 256, s.stream, s.cols(), s.n, kind, s.par.thermokinetic_formulation, s.par.enable_fmm, part);
-  else FSPH_LAUNCH((k_reduce<3>), nb, 256, s.stream, s.cols(), s.n, kind, s.par.thermokinetic_formulation, s.par.enable_fmm, part);
+  if(s.dim == 1) FSPH_LAUNCH((k_reduce<1>), nb, 256, s.stream, s.cols(), s.n, kind, s.par.thermokinetic_formulation, s.par.enable_fmm, s.ef, part);
+  else if(s.dim == 2) FSPH_LAUNCH((k_reduce<2>), nb, 256, s.stream, s.cols(), s.n, kind, s.par.thermokinetic_formulation, s.par.enable_fmm, s.ef, part);
+  else FSPH_LAUNCH((k_reduce<3>), nb, 256, s.stream, s.cols(), s.n, kind, s.par.thermokinetic_formulation, s.par.enable_fmm, s.ef, part);
   FSPH_CUDA_OK(cudaGetLastError());
   std::vector<double> h((size_t)nb * 3);
   FSPH_CUDA_OK(cudaMemcpyAsync(h.data(), part, h.size() * 8, cudaMemcpyDeviceToHost, s.stream));

@@ -135,6 +135,8 @@ void do_sweep(System & s, int op) {
                   : op == FSPH_SWEEP_SHORT_RANGE_REPULSION ? "repulsion" : "neighbors";
   PhaseScope p(s, nm);
   sweep(s, op);
+  // the last statement of compute_acceleration: acc_a += external_force::acceleration(particle), default_physics.h:404
+  if((op == FSPH_SWEEP_ACCELERATION || op == 101) && s.ef.nacc > 0) apply(s, 102);
 }
 
 // device address and element size of one component of a C-ABI column
@@ -275,9 +277,9 @@ void do_step(System & s, int initial) {
     }
     stream_flush(s, cols_after_update, 3);
     do_sweep(s, 100);
-    // without gravity and relaxation terms nothing touches the acceleration between the sweep and the second kick: the
+    // without gravity, external forces and relaxation terms nothing touches the acceleration between the sweep and the second kick: the
     // sweep applies it to each body it finishes (one element-wise pass less)
-    const bool fuse_kick = !P.enable_fmm && !relaxing;
+    const bool fuse_kick = !P.enable_fmm && !relaxing && s.ef.nacc == 0;
     s.fuse_kick_v = fuse_kick;
     try { acceleration(); }
     catch(...) { s.fuse_kick_v = false; throw; }
@@ -368,6 +370,25 @@ void fsph_default_params(fsph_params * p, int32_t dim) {
   p->relaxation_gamma = 0.0;
   p->relaxation_repulsion_radius = 0.25;
   p->relaxation_repulsion_gamma = 0.0;
+  std::strcpy(p->external_force_type, "none");
+  std::strcpy(p->density_profile, "constant");
+  p->sphere_radius = 1.0;
+  p->extforce_wall_powerindex = 5.0;
+  p->extforce_wall_steepness = 1e12;
+  p->gravity_acceleration_constant = 9.81;
+  p->zero_potential_poison_value = 0.0;
+  p->mesa_rim_width = 0.25;
+  p->rho_initial = 1.0;
+  p->pressure_initial = 1.0;
+  p->orbital_separation = 2.5e9;
+  p->mass_neutron_star = 1.26 * 1.988435e33;
+  p->mass_white_dwarf = 1.10 * 1.988435e33;
+  p->airfoil_size = 2.0;
+  p->airfoil_thickness = 0.05;
+  p->airfoil_camber = 0.1;
+  p->airfoil_anchor_x = -1.0;
+  p->airfoil_anchor_y = 0.0;
+  p->airfoil_attack_angle = 0.0;
 }
 
 const char * fsph_backend(void) { return "cuda-sm100a"; }
@@ -391,6 +412,7 @@ fsph_system * fsph_create(const fsph_params * p, int32_t device) {
     s->dim = p->dim;
     s->device = device;
     s->dt = p->initial_dt;
+    s->ef = ef_parse(*p);   // external_force::select, eforce.h:358 (throws on a keyword the reference rejects)
     // optional columns
     for(int f = 0; f < F_FIRST_OPTIONAL; ++f) s->col_used[f] = true;
     s->col_used[F_YE] = p->eos_type == FSPH_EOS_WD;

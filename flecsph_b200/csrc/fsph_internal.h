@@ -13,6 +13,7 @@
 #include <utility>
 #include <stdexcept>
 #include "flecsph_b200.h"
+#include "fsph_eforce.h"
 
 namespace fsph {
 
@@ -219,6 +220,7 @@ struct Dist;
 
 struct System {
   fsph_params par;
+  ExtForce ef;   // external_force_type parsed (fsph_eforce.h)
   // domain decomposition (fsph_dist.cu); comm == nullptr: one rank owns everything
   Comm * comm = nullptr;
   Dist * dist = nullptr;

@@ -559,7 +559,7 @@ __device__ __forceinline__ void store_own(const Own<D> & o, const Cols & c, cons
   else if(OP == OP_ACC || OP == OP_ACCV) {
 #pragma unroll
     for(int d = 0; d < D; ++d) {
-      c.f[F_ACC + d][ia] = o.accv[d];  // + external_force::acceleration == 0 (external_force_type "none")
+      c.f[F_ACC + d][ia] = o.accv[d];  // external_force::acceleration is added by an element-wise pass right after (do_sweep)
       c.f[F_GACC + d][ia] = 0.0;
     }
     c.f[F_GPOT][ia] = 0.0;

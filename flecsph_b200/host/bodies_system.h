@@ -26,6 +26,7 @@
 #include <vector>
 #include <algorithm>
 #include <cstdint>
+#include <cstring>
 #include <cstdio>
 #include <cstdlib>
 #include <cstdio>
@@ -173,6 +174,28 @@ public:
     p.relaxation_gamma = relaxation_gamma;
     p.relaxation_repulsion_radius = relaxation_repulsion_radius;
     p.relaxation_repulsion_gamma = relaxation_repulsion_gamma;
+    // external forces (eforce.h): the keyword the driver hands to external_force::select and the parameters its terms read
+    std::snprintf(p.external_force_type, sizeof(p.external_force_type), "%s", external_force_type);
+    std::snprintf(p.density_profile, sizeof(p.density_profile), "%s", density_profile);
+    if(std::strlen(external_force_type) >= sizeof(p.external_force_type))
+      fsph_host::fail("external_force_type too long for the device path:", external_force_type);
+    p.sphere_radius = sphere_radius;
+    p.extforce_wall_powerindex = extforce_wall_powerindex;
+    p.extforce_wall_steepness = extforce_wall_steepness;
+    p.gravity_acceleration_constant = gravity_acceleration_constant;
+    p.zero_potential_poison_value = zero_potential_poison_value;
+    p.mesa_rim_width = mesa_rim_width;
+    p.rho_initial = rho_initial;
+    p.pressure_initial = pressure_initial;
+    p.orbital_separation = orbital_separation;
+    p.mass_neutron_star = mass_neutron_star;
+    p.mass_white_dwarf = mass_white_dwarf;
+    p.airfoil_size = airfoil_size;
+    p.airfoil_thickness = airfoil_thickness;
+    p.airfoil_camber = airfoil_camber;
+    p.airfoil_anchor_x = airfoil_anchor_x;
+    p.airfoil_anchor_y = airfoil_anchor_y;
+    p.airfoil_attack_angle = airfoil_attack_angle;
     int rank = 0;
     MPI_Comm_rank(MPI_COMM_WORLD, &rank);
     const char * dev = std::getenv("FSPH_DEVICE");

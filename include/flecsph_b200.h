@@ -90,6 +90,21 @@ typedef struct fsph_params {
   double relaxation_gamma;          /* params.h:572 */
   double relaxation_repulsion_radius; /* params.h:576 */
   double relaxation_repulsion_gamma;  /* params.h:580 */
+  /* external forces and potentials (include/physics/eforce.h): the keyword external_force::select parses
+   * (eforce.h:358-433; "none", or a comma-separated list of "spherical wall", "airfoil", "spherical density support",
+   * "gravity", "orbit", "walls:xyz", "poison"; an empty string means "none") and the parameters its terms read */
+  char external_force_type[64];       /* params.h:597 */
+  char density_profile[32];           /* params.h:671 ("constant", "parabolic", "mesa"; "from file" is refused) */
+  double sphere_radius;               /* params.h:270 */
+  double extforce_wall_powerindex;    /* params.h:608 */
+  double extforce_wall_steepness;     /* params.h:613 */
+  double gravity_acceleration_constant; /* params.h:623 */
+  double zero_potential_poison_value; /* params.h:603 */
+  double mesa_rim_width;              /* params.h:618 */
+  double rho_initial, pressure_initial; /* params.h:682,687 */
+  double orbital_separation, mass_neutron_star, mass_white_dwarf; /* params.h:637-647 */
+  double airfoil_size, airfoil_thickness, airfoil_camber;         /* params.h:761-769 */
+  double airfoil_anchor_x, airfoil_anchor_y, airfoil_attack_angle;/* params.h:773-781 */
 } fsph_params;
 
 /* Fill `p` with the reference's defaults (include/params.h) for `dim`. */

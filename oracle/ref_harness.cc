@@ -16,6 +16,7 @@
  * fsph_step(), which issues the calls of app/drivers/hydro/main_driver.cc:
  * 102-277 (and newtonian/main_driver.cc:218-222) in the driver's order.
  */
+#include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -95,6 +96,27 @@ install_params(const fsph_params & p) {
   _relaxation_gamma = p.relaxation_gamma;
   _relaxation_repulsion_radius = p.relaxation_repulsion_radius;
   _relaxation_repulsion_gamma = p.relaxation_repulsion_gamma;
+  // external forces.  NOTE: the terms of eforce.h latch most of these in function-level statics at their first call
+  // (e.g. `const static double box[3]`, eforce.h:51-55), so one process can exercise only one set of values per term.
+  std::snprintf(_external_force_type, sizeof(_external_force_type), "%s", p.external_force_type[0] ? p.external_force_type : "none");
+  std::snprintf(_density_profile, sizeof(_density_profile), "%s", p.density_profile[0] ? p.density_profile : "constant");
+  _sphere_radius = p.sphere_radius;
+  _extforce_wall_powerindex = p.extforce_wall_powerindex;
+  _extforce_wall_steepness = p.extforce_wall_steepness;
+  _gravity_acceleration_constant = p.gravity_acceleration_constant;
+  _zero_potential_poison_value = p.zero_potential_poison_value;
+  _mesa_rim_width = p.mesa_rim_width;
+  _rho_initial = p.rho_initial;
+  _pressure_initial = p.pressure_initial;
+  _orbital_separation = p.orbital_separation;
+  _mass_neutron_star = p.mass_neutron_star;
+  _mass_white_dwarf = p.mass_white_dwarf;
+  _airfoil_size = p.airfoil_size;
+  _airfoil_thickness = p.airfoil_thickness;
+  _airfoil_camber = p.airfoil_camber;
+  _airfoil_anchor_x = p.airfoil_anchor_x;
+  _airfoil_anchor_y = p.airfoil_anchor_y;
+  _airfoil_attack_angle = p.airfoil_attack_angle;
   // what set_derived_params does (app/drivers/hydro/main_driver.cc:52-74)
   kernels::select();
   viscosity::select();
@@ -142,6 +164,22 @@ fsph_default_params(fsph_params * p, int32_t dim) {
   p->ppt_density_thr = 5e14;
   p->relaxation_beta = 1e-6;
   p->relaxation_repulsion_radius = 0.25;
+  std::strcpy(p->external_force_type, "none");
+  std::strcpy(p->density_profile, "constant");
+  p->sphere_radius = 1.0;
+  p->extforce_wall_powerindex = 5.0;
+  p->extforce_wall_steepness = 1e12;
+  p->gravity_acceleration_constant = 9.81;
+  p->mesa_rim_width = 0.25;
+  p->rho_initial = 1.0;
+  p->pressure_initial = 1.0;
+  p->orbital_separation = 2.5e9;
+  p->mass_neutron_star = 1.26 * 1.988435e33;
+  p->mass_white_dwarf = 1.10 * 1.988435e33;
+  p->airfoil_size = 2.0;
+  p->airfoil_thickness = 0.05;
+  p->airfoil_camber = 0.1;
+  p->airfoil_anchor_x = -1.0;
 }
 
 const char *

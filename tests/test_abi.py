@@ -45,3 +45,18 @@ def test_params_struct_matches_header_defaults():
     q = capi.default_params(3)
     for name, _ in capi.Params._fields_:
         assert getattr(p, name) == getattr(q, name), name
+
+
+def test_params_layout_matches_header(tmp_path):
+    """The ctypes mirror of fsph_params has the layout the C compiler gives include/flecsph_b200.h."""
+    import ctypes as C
+    import subprocess
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "flecsph_b200.h"\n'
+                   'int main(){printf("%zu %zu %zu %zu\\n", sizeof(fsph_params), offsetof(fsph_params, sph_viscosity_alpha_max),'
+                   ' offsetof(fsph_params, external_force_type), offsetof(fsph_params, airfoil_attack_angle)); return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    P = capi.Params
+    assert got == [C.sizeof(P), P.sph_viscosity_alpha_max.offset, P.external_force_type.offset, P.airfoil_attack_angle.offset]

@@ -124,6 +124,9 @@ STEP_CASES = [
     # Cullen-Dehnen viscosity (remote copies need alpha and div v) and the relaxation phase on several ranks
     ("sedov", dict(nx=22, par=dict(sph_viscosity=1, sph_viscosity_alpha_max=1.5)), 3, "random", 4),
     ("random", dict(n=5000, seed=9, h_jitter=0.1, par=dict(relaxation_steps=2, relaxation_beta=0.3, relaxation_repulsion_gamma=1e-4)), 2, "random", 3),
+    # external forces (element-wise term after the acceleration sweep: no fused second kick) on several ranks
+    ("random", dict(n=5000, seed=10, h_jitter=0.1, par=dict(external_force_type="walls:xyz,gravity,poison", extforce_wall_powerindex=3.0,
+                                                            extforce_wall_steepness=40.0, gravity_acceleration_constant=0.7)), 3, "random", 3),
 ]
 
 
