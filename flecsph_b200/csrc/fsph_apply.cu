@@ -56,6 +56,7 @@ PhysParams System::phys() const {
   p.repulsion_radius = par.relaxation_repulsion_radius;
   p.repulsion_gamma = par.relaxation_repulsion_gamma;
   p.fuse_kick_v = fuse_kick_v ? 1 : 0;
+  p.ext_potential = ef.n > 0 ? 1 : 0;
   return p;
 }
 
@@ -95,6 +96,7 @@ static OpAccess op_access(int op, const PhysParams & pp, const ExtForce & ef) {
     case 100: return {fbit(F_MASS) | fbit(F_RHO), fbit(F_H)};
     case 101: return {0, fbit(F_H)};
     case 102: return {vbit(F_POS) | vbit(F_ACC), vbit(F_ACC)};
+    case 103: return {vbit(F_POS) | vbit(F_VEL) | fbit(F_E), fbit(F_U)};
   }
   throw std::runtime_error("unknown apply op");
 }
@@ -251,6 +253,16 @@ __device__ __forceinline__ void apply_one(double * v, const int op, const PhysPa
       v[F_H] = r * pp.eta * pp.kernel_width;
     } break;
     case 101: v[F_H] = pp.dt; break;  // uniform h (value carried in pp.dt)
+    case 103: {
+      // recover_internal_energy (default_physics.h:126-144) as compute_density_pressure_soundspeed calls it (:313-314) when
+      // there is an external potential: issued right before the density sweep, which then takes u as it finds it
+      double v2 = 0.0;
+#pragma unroll
+      for(int d = 0; d < D; ++d) v2 = v2 + v[F_VEL + d] * v[F_VEL + d];
+      const double eint = v[F_E] - .5 * v2 - (EF ? ef_potential<D>(ef, xp) : 0.0);
+      if(!(eint > 0)) atomicOr(status, (uint32_t)ERR_U_NONPOS);
+      v[F_U] = eint;
+    } break;
     case 102: {  // acc_a += external_force::acceleration(particle), the last statement of compute_acceleration (default_physics.h:404)
       if(EF) {
         double a[3] = {0.0, 0.0, 0.0};

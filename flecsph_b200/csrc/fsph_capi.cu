@@ -134,6 +134,10 @@ void do_sweep(System & s, int op) {
                   : op == FSPH_SWEEP_DUDT ? "dudt" : op == FSPH_SWEEP_DEDT ? "dedt" : op == FSPH_SWEEP_COMPUTE_ALPHA ? "viscosity_alpha"
                   : op == FSPH_SWEEP_SHORT_RANGE_REPULSION ? "repulsion" : "neighbors";
   PhaseScope p(s, nm);
+  // with an external potential the internal energy is recovered from e by an element-wise pass (the potential's terms
+  // stay out of the sweep kernels); without one the density sweep does it in its epilogue
+  if((op == FSPH_SWEEP_DENSITY_PRESSURE_SOUNDSPEED || op == 100) && s.ef.n > 0 && s.par.evolve_internal_energy && s.par.thermokinetic_formulation)
+    apply(s, 103);
   sweep(s, op);
   // the last statement of compute_acceleration: acc_a += external_force::acceleration(particle), default_physics.h:404
   if((op == FSPH_SWEEP_ACCELERATION || op == 101) && s.ef.nacc > 0) apply(s, 102);

@@ -174,6 +174,7 @@ struct PhysParams {
   double gamma2, rho_thr;                                    // piecewise polytrope
   double relax_beta, relax_gamma, repulsion_radius, repulsion_gamma;   // relaxation phase
   int fuse_kick_v;   // the acceleration sweep of fsph_step also applies the second velocity kick (integration.h:71-79)
+  int ext_potential; // external potential present: u is recovered from e by an element-wise pass before the density sweep
 };
 
 // eos::compute_pressure + compute_soundspeed (include/physics/eos/eos.h): ideal gas :166-183 from the specific internal

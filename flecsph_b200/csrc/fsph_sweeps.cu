@@ -493,8 +493,8 @@ __device__ __forceinline__ void store_own(const Own<D> & o, const Cols & c, cons
     if(!(rho > 0)) atomicOr(status, (uint32_t)ERR_RHO_NONPOS);
     c.f[F_RHO][ia] = rho;
     double u;
-    if(pp.evolve_u && pp.thermokinetic) {
-      // recover_internal_energy (no external potential)
+    if(pp.evolve_u && pp.thermokinetic && !pp.ext_potential) {
+      // recover_internal_energy without an external potential (with one: element-wise pass 103 before this sweep)
       double v2 = 0.0;
 #pragma unroll
       for(int d = 0; d < D; ++d) { const double v = c.f[F_VEL + d][ia]; v2 += v * v; }

@@ -35,6 +35,7 @@ def test_eforce_calls(name):
     assert_fields_close(G, R, ["e"], 1e-10)
     G.apply_in_smoothinglength(capi.SWEEP_DENSITY); R.apply_in_smoothinglength(capi.SWEEP_DENSITY)
     assert_neighbors_equal(G, R)
+    assert_fields_close(G, R, ["rho", "u", "P", "cs", "vsig"], 1e-10)   # u = e - ekin - epot inside the density functor
     for nm in ("rho", "P", "cs", "vsig"):   # identical inputs for the next calls
         G.set(capi.COL_NAMES.index(nm), R.get(capi.COL_NAMES.index(nm)))
     G.apply_all(capi.APPLY_SAVE_VELOCITYHALF); R.apply_all(capi.APPLY_SAVE_VELOCITYHALF)
