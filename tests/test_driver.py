@@ -60,7 +60,7 @@ def have(*paths):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,dim,iters", [("sedov", 3, 6), ("sod", 1, 8), ("collapse", 3, 4)])
+@pytest.mark.parametrize("name,dim,iters", [("sedov", 3, 6), ("sod", 1, 8), ("collapse", 3, 4), ("walls_gravity", 3, 5)])
 def test_unmodified_driver_on_gpu_matches_reference_build(tmp_path, name, dim, iters):
     drv = "newtonian" if name == "collapse" else "hydro"   # newtonian_3d: hydro + FMM gravity (newtonian/main_driver.cc)
     exe_g = os.path.join(B200, "%s_%dd_b200" % (drv, dim))
@@ -69,6 +69,14 @@ def test_unmodified_driver_on_gpu_matches_reference_build(tmp_path, name, dim, i
         pytest.skip("driver binaries not built (need the reference checkout: make -C flecsph_b200/host; make -C oracle drivers)")
     if name == "sedov":
         f, par = idata.sedov_3d(nx=14)
+    elif name == "walls_gravity":
+        # external forces through the .par file (data/RT_3d.par: external_force_type = "walls:xyz,gravity"): the blast sphere
+        # in a box whose walls cut into it, in a uniform field
+        f, par = idata.sedov_3d(nx=12)
+        f = dict(f, u=f["u"] + 0.5)   # warm ambient gas: the potential energy traded per step stays below u
+        f["P"] = (par["poly_gamma"] - 1.0) * f["rho"] * f["u"]
+        par = dict(par, external_force_type="walls:xyz,gravity", box_length=1.6, box_width=1.4, box_height=1.2,
+                   extforce_wall_powerindex=3.0, extforce_wall_steepness=50.0, gravity_acceleration_constant=0.5)
     elif name == "collapse":
         f, par = idata.collapse_3d(nx=11)
     else:
