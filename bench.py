@@ -10,9 +10,10 @@ drift, range, keys, sort, tree, neighbour search, density / acceleration / de/dt
 N=1: Sedov blast wave, FCC lattice in the unit sphere scaled to ~64 M particles (BASELINE.json configs[1]); inputs
 (~100 B/particle of live state, 6+ GB) are far larger than the 126 MB L2, so no explicit L2 flush is needed.
 `value` is timed with CUDA events inside the library on its own stream (fsph_phase_times "total"), inputs resident in
-HBM; `e2e` is the same step driven through the C ABI from pinned HOST buffers: the state is uploaded before every step and
-the results come back through fsph_step_streamed (device-to-host copies overlapped with the rest of the step), all
-inside the timed region.
+HBM; `e2e` is the same step driven through the C ABI from pinned HOST buffers (fsph_step_pipelined): every step its input
+state is copied host -> device and its results device -> host, all inside the timed region; the results leave on a side
+stream as soon as a column is final, and the uploads of the next step -- its inputs are the buffers this step filled, each
+upload ordered on the device after the download of the same buffer -- overlap the tail of this step's downloads.
 """
 import argparse
 import json
@@ -262,6 +263,7 @@ def main():
     ap.add_argument("--particles", type=float, default=64e6, help="target particle count per GPU")
     ap.add_argument("--cpu-nx", type=int, default=0, help="lattice_nx of the CPU sample (0: chosen from the time budget)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-serial", action="store_true", help="e2e with the uploads issued one by one before fsph_step_streamed (round-2 path) instead of fsph_step_pipelined")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE.json configurations / scaling sub-records")
     ap.add_argument("--host-ids", action="store_true", help="generate the initial data on the host (numpy) instead of on the device")
@@ -429,11 +431,23 @@ def main():
         # the iteration has written it for the last time (ids / masses / positions after update_iteration, ...), the call
         # returns when the last byte has arrived
         plan = [(col, c, bufs[col][c].data_ptr()) for col, nc in down for c in range(nc)]
-        for _ in range(a.steps):
-            upload()
-            if s.nbodies() > cap:
-                raise SystemExit("e2e staging buffers too small for this rank's share")
-            s.step_streamed(plan)
+        plan_in = [(col, c, bufs[col][c].data_ptr()) for col, nc in up for c in range(nc)]
+        if a.e2e_serial:
+            for _ in range(a.steps):
+                upload()
+                if s.nbodies() > cap:
+                    raise SystemExit("e2e staging buffers too small for this rank's share")
+                s.step_streamed(plan)
+        else:
+            # fsph_step_pipelined: the buffers step k filled are the inputs of step k+1; every byte goes host -> device ->
+            # host every step, the uploads of step k+1 (each ordered on the device after step k's copy of the same
+            # buffer) run while the tail of step k's results is still on its way down
+            for _ in range(a.steps):
+                if s.nbodies() > cap:
+                    raise SystemExit("e2e staging buffers too small for this rank's share")
+                s.step_pipelined(plan_in, plan)
+            s.stream_wait()
+        config["e2e_path"] = "fsph_step_streamed after serial uploads" if a.e2e_serial else "fsph_step_pipelined"
         barrier()
         te = time.perf_counter() - t0
         tte = torch.tensor([te], dtype=torch.float64, device="cuda")

@@ -81,6 +81,7 @@ SYMBOLS = [
     "fsph_nbodies", "fsph_set_column", "fsph_get_column", "fsph_set_component", "fsph_get_component", "fsph_launch_count", "fsph_upload_aos", "fsph_download_aos", "fsph_set_time",
     "fsph_get_time", "fsph_advance_time", "fsph_update_iteration", "fsph_reset_ghosts", "fsph_sweep", "fsph_apply",
     "fsph_reduce", "fsph_gravitation_fmm", "fsph_get_range", "fsph_get_smoothinglength", "fsph_step", "fsph_step_streamed",
+    "fsph_step_pipelined", "fsph_stream_wait",
     "fsph_tree_num_nodes", "fsph_tree_get_nodes", "fsph_tree_get_leaf_depth", "fsph_neighbor_lists",
     "fsph_phase_times", "fsph_set_time_state", "fsph_get_time_state", "fsph_tree_root",
     "fsph_comm_unique_id", "fsph_comm_init_nccl", "fsph_local_group_create", "fsph_local_group_destroy",
@@ -89,7 +90,7 @@ SYMBOLS = [
     "fsph_generate_lattice", "fsph_count_within", "fsph_id_fill",
 ]
 # entry points only the product library has to provide (the checkers under oracle/ may omit them)
-PRODUCT_ONLY = {"fsph_step_streamed", "fsph_set_time_state", "fsph_get_time_state", "fsph_tree_root", "fsph_comm_unique_id",
+PRODUCT_ONLY = {"fsph_step_streamed", "fsph_step_pipelined", "fsph_stream_wait", "fsph_set_time_state", "fsph_get_time_state", "fsph_tree_root", "fsph_comm_unique_id",
                 "fsph_comm_init_nccl", "fsph_local_group_create", "fsph_local_group_destroy", "fsph_comm_init_local",
                 "fsph_comm_rank", "fsph_comm_size", "fsph_nghosts", "fsph_dd_choose_splitters", "fsph_dd_align_splitter",
                 "fsph_measure_fp64_tflops", "fsph_measure_copy_gbs", "fsph_generate_lattice", "fsph_count_within",
@@ -150,6 +151,8 @@ def load(path):
         "fsph_get_smoothinglength": (dbl, [vp]),
         "fsph_step": (i32, [vp, i32]),
         "fsph_step_streamed": (i32, [vp, i32, vp, i32]),
+        "fsph_step_pipelined": (i32, [vp, i32, vp, i32, vp, i32]),
+        "fsph_stream_wait": (i32, [vp]),
         "fsph_tree_num_nodes": (i64, [vp]),
         "fsph_tree_get_nodes": (i32, [vp] + [vp] * 8),
         "fsph_tree_get_leaf_depth": (i32, [vp, vp]),
@@ -391,6 +394,20 @@ class BodySystem:
         for k, (col, comp, ptr) in enumerate(outputs):
             arr[k].col, arr[k].comp, arr[k].host = col, comp, ptr
         self._ck(self.lib.fsph_step_streamed(self.h, 1 if initial else 0, C.cast(arr, C.c_void_p), len(outputs)))
+
+    def step_pipelined(self, inputs, outputs, initial=False):
+        """fsph_step_pipelined: `inputs` / `outputs` = [(column, component, address of a pinned host buffer)]; returns when
+        the kernels are done -- stream_wait() before reading the output buffers."""
+        ain, aout = (StreamOut * max(len(inputs), 1))(), (StreamOut * max(len(outputs), 1))()   # fsph_stream_in has the same layout
+        for k, (col, comp, ptr) in enumerate(inputs):
+            ain[k].col, ain[k].comp, ain[k].host = col, comp, ptr
+        for k, (col, comp, ptr) in enumerate(outputs):
+            aout[k].col, aout[k].comp, aout[k].host = col, comp, ptr
+        self._ck(self.lib.fsph_step_pipelined(self.h, 1 if initial else 0, C.cast(ain, C.c_void_p), len(inputs),
+                                              C.cast(aout, C.c_void_p), len(outputs)))
+
+    def stream_wait(self):
+        self._ck(self.lib.fsph_stream_wait(self.h))
 
     # -- introspection ------------------------------------------------------
     def tree_nodes(self):

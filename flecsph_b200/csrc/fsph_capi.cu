@@ -177,6 +177,7 @@ static void stream_flush(System & s, const int * cols, int ncols) {
     const char * src = static_cast<const char *>(column_source(s, e.col, e.comp, esz));
     const int64_t first = s.has_ghosts ? s.own_begin : 0, cnt = s.n_owned_or_n();
     FSPH_CUDA_OK(cudaMemcpyAsync(e.host, src + (size_t)first * esz, (size_t)cnt * esz, cudaMemcpyDeviceToHost, s.side_stream));
+    if(e.ev) FSPH_CUDA_OK(cudaEventRecord(e.ev, s.side_stream));
     e.done = true;
   }
 }
@@ -328,6 +329,13 @@ int32_t guarded(fsph_system * s, F && f) {
   if(!s) return 1;
   try {
     FSPH_CUDA_OK(cudaSetDevice(s->device));
+    if(!s->in_pipelined_call && !s->prev_out.empty()) {
+      // copies of a pipelined step are still in flight and this is not the next pipelined step: let them land first
+      // (any other call may read or overwrite the columns they come from)
+      const cudaError_t e = cudaStreamSynchronize(s->side_stream);
+      s->prev_out.clear();
+      FSPH_CUDA_OK(e);
+    }
     f();
     return 0;
   }
@@ -445,8 +453,13 @@ void fsph_destroy(fsph_system * s) {
   delete s->comm;
   s->comm = nullptr;
   release_buffers(*s);
+  if(s->side_stream) cudaStreamSynchronize(s->side_stream);
+  if(s->up_stream) cudaStreamSynchronize(s->up_stream);
+  for(cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
   if(s->side_event) cudaEventDestroy(s->side_event);
+  if(s->up_event) cudaEventDestroy(s->up_event);
   if(s->side_stream) cudaStreamDestroy(s->side_stream);
+  if(s->up_stream) cudaStreamDestroy(s->up_stream);
   if(s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -716,25 +729,110 @@ int32_t fsph_step(fsph_system * s, int32_t initial) {
   return step_impl(s, initial);
 }
 
-int32_t fsph_step_streamed(fsph_system * s, int32_t initial, const fsph_stream_out * out, int32_t nout) {
+// device address and element size of one writable component (fsph_set_component)
+static void * column_dest(System & s, int col, int comp, size_t & esz) {
+  esz = 8;
+  if(col >= FSPH_COL_POS && col <= FSPH_COL_GACC) {
+    if(comp < 0 || comp >= s.dim) throw std::runtime_error("bad component");
+    return s.col[VEC_FIELD[col] + comp].p;
+  }
+  if(scalar_field(s, col) >= 0) return s.col[scalar_field(s, col)].p;
+  if(col == FSPH_COL_ID) return s.col_id.p;
+  if(col == FSPH_COL_TYPE) { esz = 4; return s.col_type.p; }
+  throw std::runtime_error("column not writable");
+}
+
+struct PipelinedScope {
+  fsph_system * s;
+  explicit PipelinedScope(fsph_system * sys) : s(sys) { s->in_pipelined_call = true; }
+  ~PipelinedScope() { s->in_pipelined_call = false; }
+};
+
+// One driver iteration with its host traffic pipelined against the neighbouring iterations (include/flecsph_b200.h):
+//   up_stream    host-to-device copies of this step's inputs; each waits for the end of the previous step's kernels and for
+//                the previous step's device-to-host copy of the same column / into the same host buffer
+//   stream       the step; waits for the inputs and for the previous step's copies (it overwrites what they read)
+//   side_stream  device-to-host copies of the results, each ordered after the last kernel that writes its column
+// Returns without waiting for the device-to-host copies: fsph_stream_wait, or the next pipelined step, orders after them.
+int32_t fsph_step_pipelined(fsph_system * s, int32_t initial, const fsph_stream_in * in, int32_t nin, const fsph_stream_out * out,
+  int32_t nout) {
   if(!s) return 1;
+  PipelinedScope scope(s);
   int32_t rc = guarded(s, [&]() {
-    if(nout < 0 || (nout > 0 && !out)) throw std::runtime_error("fsph_step_streamed: bad output list");
+    if(nout < 0 || (nout > 0 && !out)) throw std::runtime_error("fsph_step_pipelined: bad output list");
+    if(nin < 0 || (nin > 0 && !in)) throw std::runtime_error("fsph_step_pipelined: bad input list");
     if(!s->side_stream) {
       FSPH_CUDA_OK(cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking));
       FSPH_CUDA_OK(cudaEventCreateWithFlags(&s->side_event, cudaEventDisableTiming));
     }
+    if(!s->up_stream) {
+      FSPH_CUDA_OK(cudaStreamCreateWithFlags(&s->up_stream, cudaStreamNonBlocking));
+      FSPH_CUDA_OK(cudaEventCreateWithFlags(&s->up_event, cudaEventDisableTiming));
+    }
+    constexpr int HALF = 64;   // copies in flight per step; the events of consecutive steps come from alternate halves
+    if(nout > HALF) throw std::runtime_error("fsph_step_pipelined: more than 64 outputs");
+    while((int)s->ev_pool.size() < 2 * HALF) {
+      cudaEvent_t e;
+      FSPH_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      s->ev_pool.push_back(e);
+    }
+    if(nin > 0) {
+      // the host sees the owned bodies only (fsph_set_component drops the remote copies first; here they stay where
+      // they are -- the previous step's copies may still be reading the columns -- and the inputs go to the owned range)
+      const int64_t first = s->has_ghosts ? s->own_begin : 0, cnt = s->n_owned_or_n();
+      s->pair_pi_valid = false;
+      // the kernels of the previous step are done with the columns
+      FSPH_CUDA_OK(cudaEventRecord(s->up_event, s->stream));
+      FSPH_CUDA_OK(cudaStreamWaitEvent(s->up_stream, s->up_event, 0));
+      for(int k = 0; k < nin; ++k) {
+        size_t esz;
+        void * dst = column_dest(*s, in[k].col, in[k].comp, esz);
+        for(const auto & p : s->prev_out)
+          if(p.host == in[k].host || (p.col == in[k].col && p.comp == in[k].comp)) FSPH_CUDA_OK(cudaStreamWaitEvent(s->up_stream, p.ev, 0));
+        FSPH_CUDA_OK(cudaMemcpyAsync(static_cast<char *>(dst) + (size_t)first * esz, in[k].host, (size_t)cnt * esz, cudaMemcpyHostToDevice, s->up_stream));
+        if(in[k].col == FSPH_COL_POS || in[k].col == FSPH_COL_H || in[k].col == FSPH_COL_MASS) { s->tree_dirty = true; s->search_valid = false; }
+      }
+      FSPH_CUDA_OK(cudaEventRecord(s->up_event, s->up_stream));
+      FSPH_CUDA_OK(cudaStreamWaitEvent(s->stream, s->up_event, 0));
+    }
+    // this step overwrites columns the previous step's copies still read: the copies are in order on their stream, so the
+    // event of the last one covers them all
+    if(!s->prev_out.empty()) FSPH_CUDA_OK(cudaStreamWaitEvent(s->stream, s->prev_out.back().ev, 0));
+    const bool upper = !s->prev_out.empty() && s->prev_out.front().ev == s->ev_pool[0];
     s->stream_out.clear();
-    for(int k = 0; k < nout; ++k) s->stream_out.push_back({out[k].col, out[k].comp, out[k].host, false});
+    for(int k = 0; k < nout; ++k) s->stream_out.push_back({out[k].col, out[k].comp, out[k].host, false, s->ev_pool[(upper ? HALF : 0) + k]});
   });
   if(rc) return rc;
   rc = step_impl(s, initial);
   const int32_t rc2 = guarded(s, [&]() {
-    if(rc == 0) stream_flush(*s, nullptr, 0);
+    if(rc == 0) {
+      stream_flush(*s, nullptr, 0);
+      s->prev_out = s->stream_out;
+      s->stream_out.clear();
+      return;
+    }
     const cudaError_t e = cudaStreamSynchronize(s->side_stream);
     s->stream_out.clear();
+    s->prev_out.clear();
     FSPH_CUDA_OK(e);
   });
+  return rc ? rc : rc2;
+}
+
+int32_t fsph_stream_wait(fsph_system * s) {
+  if(!s) return 1;
+  PipelinedScope scope(s);
+  return guarded(s, [&]() {
+    cudaError_t e = cudaSuccess;
+    if(s->side_stream) e = cudaStreamSynchronize(s->side_stream);
+    s->prev_out.clear();
+    FSPH_CUDA_OK(e);
+  });
+}
+
+int32_t fsph_step_streamed(fsph_system * s, int32_t initial, const fsph_stream_out * out, int32_t nout) {
+  const int32_t rc = fsph_step_pipelined(s, initial, nullptr, 0, out, nout);
+  const int32_t rc2 = fsph_stream_wait(s);
   return rc ? rc : rc2;
 }
 

@@ -280,10 +280,17 @@ struct System {
   uint32_t host_err = 0;
 
   // fsph_step_streamed: results copied out on a side stream as soon as they are final
-  struct StreamOut { int col, comp; void * host; bool done; };
+  struct StreamOut { int col, comp; void * host; bool done; cudaEvent_t ev; };
   std::vector<StreamOut> stream_out;
   cudaStream_t side_stream = nullptr;
   cudaEvent_t side_event = nullptr;
+  // fsph_step_pipelined: device-to-host copies of the previous step still in flight when the call returned, the stream
+  // the next step's inputs arrive on, and a pool of (untimed) events, one per copy in flight
+  std::vector<StreamOut> prev_out;
+  cudaStream_t up_stream = nullptr;
+  cudaEvent_t up_event = nullptr;
+  std::vector<cudaEvent_t> ev_pool;
+  bool in_pipelined_call = false;
 
   // phase timing of the last fsph_step
   std::vector<Phase> phases;

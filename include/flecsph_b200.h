@@ -263,6 +263,25 @@ typedef struct fsph_stream_out {
 } fsph_stream_out;
 int32_t fsph_step_streamed(fsph_system * s, int32_t initial, const fsph_stream_out * out, int32_t nout);
 
+/* The same with the iteration's INPUTS coming from host buffers as well, pipelined against the neighbouring iterations:
+ * the reference's loop keeps the bodies in host memory (bodies_system.h:352-358), so a drop-in that is handed host
+ * buffers moves every field to the device before an iteration and back after it.  Component `comp` of column `col` of
+ * the owned bodies ([n] values, as fsph_set_component) is copied from `host` on an upload stream; each copy waits (on
+ * the device, with events) for the kernels of the previous iteration and for the previous iteration's device-to-host
+ * copy of the same column or into the same host buffer -- so with the buffers of iteration k handed back as the inputs
+ * of iteration k+1 the uploads of k+1 run while the tail of k's results is still on its way down (PCIe is full duplex),
+ * and every byte still goes host -> device -> host every iteration.  The call returns when the iteration's kernels are
+ * done, NOT when its results have arrived: call fsph_stream_wait before reading the host buffers (the next
+ * fsph_step_pipelined orders itself after the copies on the device; any other call on the system waits for them).
+ * Same results as fsph_set_component for every input, fsph_step, fsph_get_component for every output. */
+typedef struct fsph_stream_in {
+  int32_t col, comp;
+  const void * host;
+} fsph_stream_in;
+int32_t fsph_step_pipelined(fsph_system * s, int32_t initial, const fsph_stream_in * in, int32_t nin, const fsph_stream_out * out,
+  int32_t nout);
+int32_t fsph_stream_wait(fsph_system * s);
+
 /* --- introspection used by the parity tests ------------------------------- */
 /* Octree node table, sorted by key: tree_topology::cofm_ (tree_topology.h:2103)
  * with node fields of cofm_u (tree_types.h:51-141). */

@@ -242,3 +242,46 @@ def test_nccl_ranks():
     for which in ("sedov", "collapse"):
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, FSPH_CASE=which, FSPH_NX="32"))
         assert r.returncode == 0 and "NCCL DECOMPOSITION OK" in r.stdout, which + "\n" + r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_step_pipelined_on_ranks():
+    """fsph_step_pipelined on 2 ranks (the owned set of a rank changes from step to step; remote copies stay in place while
+    the inputs arrive in the owned range) == the same calls one by one."""
+    import torch
+    f, par, dim = case("sedov", nx=22)
+    n = len(f["mass"])
+    up = [(capi.COL_POS, 3), (capi.COL_VEL, 3), (capi.COL_ACC, 3), (capi.COL_GACC, 3), (capi.COL_MASS, 1), (capi.COL_H, 1), (capi.COL_E, 1),
+          (capi.COL_DEDT, 1), (capi.COL_CS, 1), (capi.COL_ID, 1)]
+    down = up + [(capi.COL_RHO, 1), (capi.COL_P, 1), (capi.COL_U, 1), (capi.COL_VSIG, 1), (capi.COL_DT, 1)]
+
+    def run(pipelined):
+        L = make_ranks(f, par, dim, 2, "random")
+
+        def body(r, s):
+            bufs = {(col, c): torch.empty(n, dtype=torch.int64 if col == capi.COL_ID else torch.float64).pin_memory() for col, nc in down for c in range(nc)}
+            plan_in = [(col, c, bufs[(col, c)].data_ptr()) for col, nc in up for c in range(nc)]
+            plan_out = [(col, c, bufs[(col, c)].data_ptr()) for col, nc in down for c in range(nc)]
+            s.step(initial=True)
+            for col, c, ptr in plan_out:
+                s.get_component(col, c, ptr)
+            for it in range(3):
+                if pipelined:
+                    s.step_pipelined(plan_in, plan_out)
+                else:
+                    for col, c, ptr in plan_in:
+                        s.set_component(col, c, ptr)
+                    s.step()
+                    for col, c, ptr in plan_out:
+                        s.get_component(col, c, ptr)
+            if pipelined:
+                s.stream_wait()
+            m = s.nbodies()
+            return {k: t[:m].numpy().copy() for k, t in bufs.items()}
+        try:
+            return L.call(body)
+        finally:
+            L.close()
+    a, b = run(False), run(True)
+    for r in range(2):
+        for k in a[r]:
+            assert np.array_equal(a[r][k], b[r][k]), (r, capi.COL_NAMES[k[0]], k[1])

@@ -230,3 +230,41 @@ def test_step_streamed_equals_step_then_download():
             ref = np.empty(n, np.int64 if col == capi.COL_ID else np.float64)
             A.get_component(col, c, ref.ctypes.data)
             assert np.array_equal(t.numpy(), ref), (it, capi.COL_NAMES[col], c)
+
+
+def test_step_pipelined_equals_upload_step_download():
+    """fsph_step_pipelined: the state goes host -> device -> host every iteration, the uploads of iteration k+1 overlapping
+    the tail of iteration k's downloads (ordered by events on the device) == fsph_set_component for every input,
+    fsph_step, fsph_get_component for every output.  The host buffers iteration k filled are iteration k+1's inputs."""
+    import torch
+    f, par, dim = case("sedov", nx=20)
+    A, B = make_system("cuda", f, par, dim), make_system("cuda", f, par, dim)
+    n = A.nbodies()
+    up = [(capi.COL_POS, 3), (capi.COL_VEL, 3), (capi.COL_ACC, 3), (capi.COL_GACC, 3), (capi.COL_MASS, 1), (capi.COL_H, 1), (capi.COL_E, 1),
+          (capi.COL_DEDT, 1), (capi.COL_CS, 1), (capi.COL_ID, 1)]
+    down = up + [(capi.COL_RHO, 1), (capi.COL_P, 1), (capi.COL_U, 1), (capi.COL_VSIG, 1), (capi.COL_DT, 1)]
+
+    def buffers():
+        return {(col, c): torch.empty(n, dtype=torch.int64 if col == capi.COL_ID else torch.float64).pin_memory() for col, nc in down for c in range(nc)}
+    ba, bb = buffers(), buffers()
+    plan_in = [(col, c, bb[(col, c)].data_ptr()) for col, nc in up for c in range(nc)]
+    plan_out = [(col, c, bb[(col, c)].data_ptr()) for col, nc in down for c in range(nc)]
+    A.step(initial=True); B.step(initial=True)
+    for S, bufs in ((A, ba), (B, bb)):
+        for (col, c), t in bufs.items():
+            S.get_component(col, c, t.data_ptr())
+    for it in range(4):
+        for col, nc in up:          # A: the calls one by one
+            for c in range(nc):
+                A.set_component(col, c, ba[(col, c)].data_ptr())
+        A.step()
+        for (col, c), t in ba.items():
+            A.get_component(col, c, t.data_ptr())
+        B.step_pipelined(plan_in, plan_out)   # B: returns with copies still in flight; the next call orders itself after them
+    B.stream_wait()
+    for k in ba:
+        assert np.array_equal(ba[k].numpy(), bb[k].numpy()), (capi.COL_NAMES[k[0]], k[1])
+    # another call on the system while copies are in flight waits for them
+    B.step_pipelined(plan_in, plan_out)
+    rho = B.get(capi.COL_RHO)
+    assert np.array_equal(rho, bb[(capi.COL_RHO, 0)].numpy())
