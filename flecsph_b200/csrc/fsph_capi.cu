@@ -236,7 +236,9 @@ void do_step(System & s, int initial) {
     }
   };
   static const int cols_after_update[] = {FSPH_COL_ID, FSPH_COL_MASS, FSPH_COL_POS};
-  static const int cols_after_acceleration[] = {FSPH_COL_ACC, FSPH_COL_GACC};
+  static const int cols_after_density[] = {FSPH_COL_RHO};   // P and c_s are recomputed at the end of the iteration
+  static const int cols_after_acceleration[] = {FSPH_COL_ACC, FSPH_COL_GACC, FSPH_COL_VSIG};
+  static const int cols_after_energy[] = {FSPH_COL_DEDT, FSPH_COL_DUDT};
   static const int cols_after_kick[] = {FSPH_COL_VEL};
   if(initial) {
     do_update_iteration(s);
@@ -245,13 +247,15 @@ void do_step(System & s, int initial) {
     if(P.thermokinetic_formulation) A(FSPH_APPLY_SET_TOTAL_ENERGY);
     if(cullen) A(FSPH_APPLY_INITIALIZE_ALPHA);
     do_sweep(s, 100);
+    stream_flush(s, cols_after_density, 1);
     A(FSPH_APPLY_SAVE_VELOCITYHALF);
     acceleration();
     gravity();
-    stream_flush(s, cols_after_acceleration, 2);
+    stream_flush(s, cols_after_acceleration, 3);
     stream_flush(s, cols_after_kick, 1);   // the first iteration does not kick
     timestep();
     if(P.evolve_internal_energy) energy_passes();
+    stream_flush(s, cols_after_energy, 2);
   }
   else {
     {
@@ -282,6 +286,7 @@ void do_step(System & s, int initial) {
     }
     stream_flush(s, cols_after_update, 3);
     do_sweep(s, 100);
+    stream_flush(s, cols_after_density, 1);
     // without gravity, external forces and relaxation terms nothing touches the acceleration between the sweep and the second kick: the
     // sweep applies it to each body it finishes (one element-wise pass less)
     const bool fuse_kick = !P.enable_fmm && !relaxing && s.ef.nacc == 0;
@@ -290,7 +295,7 @@ void do_step(System & s, int initial) {
     catch(...) { s.fuse_kick_v = false; throw; }
     s.fuse_kick_v = false;
     gravity();
-    stream_flush(s, cols_after_acceleration, 2);
+    stream_flush(s, cols_after_acceleration, 3);
     if(!fuse_kick) A(FSPH_APPLY_LEAPFROG_KICK_V);
     stream_flush(s, cols_after_kick, 1);
     do_reset_ghosts(s);
@@ -298,6 +303,7 @@ void do_step(System & s, int initial) {
       energy_passes();
       tail[ntail++] = kick_energy;
     }
+    stream_flush(s, cols_after_energy, 2);
   }
   {
     PhaseScope p(s, "elementwise");

@@ -63,6 +63,12 @@ class PortSystem:
 
     def __init__(self, params, backend=None, device=0):
         self.par = params
+        # the port restates the constant-viscosity / ideal-or-polytropic path without external forces; the other physics is
+        # checked against oracle/_ref only -- refuse rather than silently ignore a selector
+        if params.external_force_type.decode().strip().lower() not in ("", "none", "zero"):
+            raise NotImplementedError("oracle_port: external_force_type is not restated here (use oracle/_ref)")
+        if params.sph_viscosity != 0 or params.relaxation_steps > 0 or params.eos_type not in (0, 1):
+            raise NotImplementedError("oracle_port: Cullen-Dehnen viscosity / relaxation / ppt and wd EOS are not restated here (use oracle/_ref)")
         self.dim = D = params.dim
         self.B = 63 // D  # filling_curve.h:45-47
         self.n = 0
