@@ -87,19 +87,20 @@ def test_unmodified_driver_on_gpu_matches_reference_build(tmp_path, name, dim, i
 
 
 @pytest.mark.gpu
-def test_unmodified_tree_driver_on_gpu(tmp_path):
+@pytest.mark.parametrize("dim", [3, 2, 1])
+def test_unmodified_tree_driver_on_gpu(tmp_path, dim):
     """The neighbour-search micro-benchmark (app/drivers/tree/main.cc + main_driver.cc, unmodified) on the facade:
     update_iteration + the neighbour census on the device, iteration after iteration (the driver loops 5000 times; it is
     stopped after a few seconds).  The average neighbour count it prints must be that of the reference search."""
     from flecsph_b200 import capi
     from common import make_system
-    exe = os.path.join(B200, "tree_3d_b200")
+    exe = os.path.join(B200, "tree_%dd_b200" % dim)
     if not have(exe):
-        pytest.skip("tree_3d_b200 not built (need the reference checkout: make -C flecsph_b200/host)")
-    f, par = idata.sedov_3d(nx=20)
+        pytest.skip("tree_%dd_b200 not built (need the reference checkout: make -C flecsph_b200/host)" % dim)
+    f, par = idata.sedov_3d(nx=20) if dim == 3 else (idata.random_box(3000, dim=2, seed=4, h_jitter=0.1) if dim == 2 else idata.sodtube_1d(nx=200))
     wd = str(tmp_path / "tree")
     os.makedirs(wd, exist_ok=True)
-    fsphbin.write_initial_data(os.path.join(wd, "id.fsphbin"), f, 3)
+    fsphbin.write_initial_data(os.path.join(wd, "id.fsphbin"), f, dim)
     fsphbin.write_par(os.path.join(wd, "run.par"), par, initial_data_prefix="id", output_h5data_prefix="out", final_iteration=3)
     if not os.access(exe, os.X_OK):
         os.chmod(exe, 0o755)
@@ -109,7 +110,7 @@ def test_unmodified_tree_driver_on_gpu(tmp_path):
         out = (e.stdout or b"").decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
     avg = [int(l.split()[1]) for l in out.splitlines() if l.startswith("Average:")]
     assert len(avg) >= 3, out[-1000:]
-    S = make_system("cuda", f, par, 3)
+    S = make_system("cuda", f, par, dim)
     S.update_iteration()
     S.apply_in_smoothinglength(capi.SWEEP_NEIGHBORS_ONLY)
     nn = S.get(capi.COL_NNEIGH)
