@@ -1,0 +1,385 @@
+// hdf5.h -- the part of the HDF5 C API that the reference's particle I/O (mpisph/io.h) calls, implemented on h5mini.h.
+//
+// With this directory on the include path `#include <hdf5.h>` in the UNMODIFIED mpisph/io.h resolves here, and
+// io::inputDataHDF5 / io::outputDataHDF5 (mpisph/io.h:631,874) read and write H5part files in the library's own
+// on-disk format (see h5mini.h for the subset) on a machine without an HDF5 installation.  One process per file:
+// H5Pset_fapl_mpio / H5Pset_dxpl_mpio are accepted and ignored (a multi-rank run against a real parallel HDF5 simply
+// drops this directory from the include path).  Functions return what the library returns: an id >= 0 or a status 0 on
+// success, a negative value on failure (the reference tests `status != 0` and `H5Gget_objinfo == 0`).
+//
+// Entry points (call sites in mpisph/io.h): H5Fopen H5Fcreate H5Fclose :93-106, H5Gget_objinfo H5Gopen H5Gcreate H5Gclose
+// :105-131, H5Dcreate H5Dopen H5Dget_space H5Dwrite H5Dread H5Dclose :150-172,267-289,459-466, H5Screate_simple
+// H5Sselect_hyperslab H5Sget_simple_extent_dims/ndims H5Sclose :149-171,275-288,463, H5Acreate H5Aopen H5Awrite H5Aread
+// H5Aclose :184-231, H5Pcreate H5Pclose H5Pset_fapl_mpio H5Pset_dxpl_mpio :88-99,124-133, H5Eset_auto :112.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "h5mini.h"
+
+typedef int64_t hid_t;
+typedef int herr_t;
+typedef int htri_t;
+typedef unsigned long long hsize_t;
+typedef long long hssize_t;
+
+#define H5P_DEFAULT 0
+#define H5S_ALL 0
+#define H5F_ACC_RDONLY 0u
+#define H5F_ACC_RDWR 1u
+#define H5F_ACC_TRUNC 2u
+#define H5F_ACC_EXCL 4u
+#define H5P_FILE_ACCESS 1
+#define H5P_DATASET_XFER 2
+#define H5P_DATASET_CREATE 3
+#define H5FD_MPIO_INDEPENDENT 0
+#define H5FD_MPIO_COLLECTIVE 1
+enum H5S_seloper_t { H5S_SELECT_SET = 0 };
+// datatype ids: outside the range of object handles
+#define H5MINI_TYPE_BASE 0x70000000LL
+#define H5T_NATIVE_DOUBLE (H5MINI_TYPE_BASE + h5mini::T_F64)
+#define H5T_NATIVE_FLOAT (H5MINI_TYPE_BASE + h5mini::T_F32)
+#define H5T_NATIVE_LLONG (H5MINI_TYPE_BASE + h5mini::T_I64)
+#define H5T_NATIVE_ULLONG (H5MINI_TYPE_BASE + h5mini::T_U64)
+#define H5T_NATIVE_INT64 (H5MINI_TYPE_BASE + h5mini::T_I64)
+#define H5T_NATIVE_UINT64 (H5MINI_TYPE_BASE + h5mini::T_U64)
+#define H5T_NATIVE_LONG (H5MINI_TYPE_BASE + h5mini::T_I64)
+#define H5T_NATIVE_INT (H5MINI_TYPE_BASE + h5mini::T_I32)
+#define H5T_NATIVE_UINT (H5MINI_TYPE_BASE + h5mini::T_U32)
+
+namespace h5mini_api {
+
+enum Kind { K_FREE = 0, K_FILE, K_GROUP, K_DSET, K_SPACE, K_ATTR, K_PLIST };
+struct Obj {
+  Kind kind = K_FREE;
+  h5mini::File * file = nullptr;
+  h5mini::Group * group = nullptr;       // K_FILE (root), K_GROUP
+  h5mini::Dataset * dset = nullptr;      // K_DSET
+  std::vector<h5mini::Attr> * attrs = nullptr;   // K_ATTR: the list that holds it ...
+  size_t attr_idx = 0;                   // ... and its position (the list may grow)
+  uint64_t n = 0, sel_off = 0, sel_cnt = 0;   // K_SPACE
+  bool has_sel = false;
+};
+inline std::vector<Obj> & table() {
+  static std::vector<Obj> t(1);   // id 0 is H5P_DEFAULT / H5S_ALL
+  return t;
+}
+inline hid_t put(const Obj & o) {
+  auto & t = table();
+  for(size_t i = 1; i < t.size(); ++i)
+    if(t[i].kind == K_FREE) { t[i] = o; return (hid_t)i; }
+  t.push_back(o);
+  return (hid_t)(t.size() - 1);
+}
+inline Obj * get(hid_t id, Kind k) {
+  auto & t = table();
+  if(id <= 0 || (size_t)id >= t.size() || t[(size_t)id].kind != k) return nullptr;
+  return &t[(size_t)id];
+}
+// a location: a file (its root group) or a group
+inline Obj * loc(hid_t id) {
+  Obj * o = get(id, K_FILE);
+  return o ? o : get(id, K_GROUP);
+}
+inline herr_t release(hid_t id, Kind k) {
+  Obj * o = get(id, k);
+  if(!o) return -1;
+  *o = Obj();
+  return 0;
+}
+inline bool type_of(hid_t id, h5mini::TypeCode & t) {
+  if(id < H5MINI_TYPE_BASE || id >= H5MINI_TYPE_BASE + h5mini::T_NONE) return false;
+  t = (h5mini::TypeCode)(id - H5MINI_TYPE_BASE);
+  return true;
+}
+// the group a path leads to from `o` ('/'-separated; a leading '/' starts at the file's root); `leaf` receives the last
+// component when `parent_of_leaf` is set (the group that holds, or will hold, the named object)
+inline h5mini::Group * walk(Obj * o, const char * path, bool parent_of_leaf, std::string * leaf) {
+  if(!o || !path) return nullptr;
+  h5mini::Group * g = path[0] == '/' ? &o->file->root : o->group;
+  std::vector<std::string> parts;
+  std::string cur;
+  for(const char * p = path;; ++p) {
+    if(*p == '/' || *p == 0) {
+      if(!cur.empty()) parts.push_back(cur);
+      cur.clear();
+      if(*p == 0) break;
+    }
+    else cur.push_back(*p);
+  }
+  if(parent_of_leaf) {
+    if(parts.empty()) return nullptr;
+    *leaf = parts.back();
+    parts.pop_back();
+  }
+  for(const auto & s : parts) {
+    auto it = g->groups.find(s);
+    if(it == g->groups.end()) return nullptr;
+    g = &it->second;
+  }
+  return g;
+}
+// element-wise conversion between the numeric types (the library converts between memory and file types)
+inline void convert(h5mini::TypeCode st, const void * src, h5mini::TypeCode dt, void * dst, uint64_t n) {
+  using namespace h5mini;
+  if(st == dt || (type_compatible(st, dt) && !type_is_float(st))) { std::memcpy(dst, src, (size_t)n * type_size(st)); return; }
+  for(uint64_t i = 0; i < n; ++i) {
+    double f = 0; long long v = 0;
+    const char * s = static_cast<const char *>(src) + i * type_size(st);
+    switch(st) {
+      case T_F64: { double x; std::memcpy(&x, s, 8); f = x; v = (long long)x; } break;
+      case T_F32: { float x; std::memcpy(&x, s, 4); f = x; v = (long long)x; } break;
+      case T_I64: { int64_t x; std::memcpy(&x, s, 8); v = x; f = (double)x; } break;
+      case T_U64: { uint64_t x; std::memcpy(&x, s, 8); v = (long long)x; f = (double)x; } break;
+      case T_I32: { int32_t x; std::memcpy(&x, s, 4); v = x; f = (double)x; } break;
+      case T_U32: { uint32_t x; std::memcpy(&x, s, 4); v = x; f = (double)x; } break;
+      default: break;
+    }
+    char * d = static_cast<char *>(dst) + i * type_size(dt);
+    switch(dt) {
+      case T_F64: { double x = f; std::memcpy(d, &x, 8); } break;
+      case T_F32: { float x = (float)f; std::memcpy(d, &x, 4); } break;
+      case T_I64: { int64_t x = v; std::memcpy(d, &x, 8); } break;
+      case T_U64: { uint64_t x = (uint64_t)v; std::memcpy(d, &x, 8); } break;
+      case T_I32: { int32_t x = (int32_t)v; std::memcpy(d, &x, 4); } break;
+      case T_U32: { uint32_t x = (uint32_t)v; std::memcpy(d, &x, 4); } break;
+      default: break;
+    }
+  }
+}
+// [offset, count) of a selection on a 1-D space of n elements (id 0 = H5S_ALL)
+inline bool selection(hid_t space, uint64_t n_all, uint64_t & off, uint64_t & cnt) {
+  if(space == H5S_ALL) { off = 0; cnt = n_all; return true; }
+  Obj * s = get(space, K_SPACE);
+  if(!s) return false;
+  off = s->has_sel ? s->sel_off : 0;
+  cnt = s->has_sel ? s->sel_cnt : s->n;
+  return off + cnt <= s->n;
+}
+inline herr_t transfer(hid_t dset_id, hid_t mem_type, hid_t mem_space, hid_t file_space, void * rbuf, const void * wbuf) {
+  Obj * d = get(dset_id, K_DSET);
+  h5mini::TypeCode mt;
+  if(!d || !type_of(mem_type, mt)) return -1;
+  uint64_t foff, fcnt, moff, mcnt;
+  if(!selection(file_space, d->dset->n, foff, fcnt)) return -1;
+  if(mem_space == H5S_ALL) { moff = 0; mcnt = fcnt; }
+  else if(!selection(mem_space, 0, moff, mcnt)) return -1;
+  if(mcnt != fcnt || foff + fcnt > d->dset->n) return -1;
+  try {
+    const h5mini::TypeCode ft = d->dset->type;
+    const size_t ms = h5mini::type_size(mt);
+    if(wbuf) {
+      const char * src = static_cast<const char *>(wbuf) + moff * ms;
+      if(mt == ft) d->file->write_data(*d->dset, foff, fcnt, src);
+      else {
+        std::vector<char> tmp((size_t)fcnt * h5mini::type_size(ft));
+        convert(mt, src, ft, tmp.data(), fcnt);
+        d->file->write_data(*d->dset, foff, fcnt, tmp.data());
+      }
+    }
+    else {
+      char * dst = static_cast<char *>(rbuf) + moff * ms;
+      if(mt == ft) d->file->read_data(*d->dset, foff, fcnt, dst);
+      else {
+        std::vector<char> tmp((size_t)fcnt * h5mini::type_size(ft));
+        d->file->read_data(*d->dset, foff, fcnt, tmp.data());
+        convert(ft, tmp.data(), mt, dst, fcnt);
+      }
+    }
+    return 0;
+  }
+  catch(const std::exception & e) {
+    std::fprintf(stderr, "%s\n", e.what());
+    return -1;
+  }
+}
+
+}  // namespace h5mini_api
+
+// ---- files ---------------------------------------------------------------------------------------------------------
+inline hid_t H5Fopen(const char * name, unsigned flags, hid_t) {
+  h5mini::File * f = new h5mini::File;
+  try { f->open(name, (flags & H5F_ACC_RDWR) ? 'a' : 'r'); }
+  catch(const std::exception & e) { std::fprintf(stderr, "%s\n", e.what()); delete f; return -1; }
+  h5mini_api::Obj o;
+  o.kind = h5mini_api::K_FILE; o.file = f; o.group = &f->root;
+  return h5mini_api::put(o);
+}
+inline hid_t H5Fcreate(const char * name, unsigned, hid_t, hid_t) {
+  h5mini::File * f = new h5mini::File;
+  try { f->open(name, 'w'); }
+  catch(const std::exception & e) { std::fprintf(stderr, "%s\n", e.what()); delete f; return -1; }
+  h5mini_api::Obj o;
+  o.kind = h5mini_api::K_FILE; o.file = f; o.group = &f->root;
+  return h5mini_api::put(o);
+}
+inline herr_t H5Fclose(hid_t id) {
+  h5mini_api::Obj * o = h5mini_api::get(id, h5mini_api::K_FILE);
+  if(!o) return -1;
+  herr_t rc = 0;
+  try { o->file->close(); }
+  catch(const std::exception & e) { std::fprintf(stderr, "%s\n", e.what()); rc = -1; }
+  // handles into this file die with it
+  for(auto & x : h5mini_api::table())
+    if(x.file == o->file && &x != o) x = h5mini_api::Obj();
+  delete o->file;
+  *o = h5mini_api::Obj();
+  return rc;
+}
+
+// ---- groups --------------------------------------------------------------------------------------------------------
+inline herr_t H5Gget_objinfo(hid_t loc_id, const char * name, int, void *) {
+  std::string leaf;
+  h5mini::Group * g = h5mini_api::walk(h5mini_api::loc(loc_id), name, true, &leaf);
+  return g && (g->groups.count(leaf) || g->datasets.count(leaf)) ? 0 : -1;
+}
+inline hid_t H5Gopen(hid_t loc_id, const char * name, hid_t) {
+  h5mini_api::Obj * l = h5mini_api::loc(loc_id);
+  h5mini::Group * g = h5mini_api::walk(l, name, false, nullptr);
+  if(!g) return -1;
+  h5mini_api::Obj o;
+  o.kind = h5mini_api::K_GROUP; o.file = l->file; o.group = g;
+  return h5mini_api::put(o);
+}
+inline hid_t H5Gcreate(hid_t loc_id, const char * name, hid_t, hid_t, hid_t) {
+  h5mini_api::Obj * l = h5mini_api::loc(loc_id);
+  std::string leaf;
+  h5mini::Group * g = h5mini_api::walk(l, name, true, &leaf);
+  if(!g || !l->file->writable() || g->groups.count(leaf) || g->datasets.count(leaf)) return -1;
+  h5mini_api::Obj o;
+  o.kind = h5mini_api::K_GROUP; o.file = l->file; o.group = &g->groups[leaf];
+  l->file->touch();
+  return h5mini_api::put(o);
+}
+inline herr_t H5Gclose(hid_t id) { return h5mini_api::release(id, h5mini_api::K_GROUP); }
+
+// ---- dataspaces ----------------------------------------------------------------------------------------------------
+inline hid_t H5Screate_simple(int rank, const hsize_t * dims, const hsize_t *) {
+  if(rank != 1 || !dims) return -1;
+  h5mini_api::Obj o;
+  o.kind = h5mini_api::K_SPACE; o.n = dims[0];
+  return h5mini_api::put(o);
+}
+inline herr_t H5Sselect_hyperslab(hid_t id, H5S_seloper_t, const hsize_t * start, const hsize_t * stride, const hsize_t * count, const hsize_t * block) {
+  h5mini_api::Obj * s = h5mini_api::get(id, h5mini_api::K_SPACE);
+  if(!s || !start || !count || (stride && stride[0] != 1) || (block && block[0] != 1) || start[0] + count[0] > s->n) return -1;
+  s->has_sel = true; s->sel_off = start[0]; s->sel_cnt = count[0];
+  return 0;
+}
+inline int H5Sget_simple_extent_ndims(hid_t id) { return h5mini_api::get(id, h5mini_api::K_SPACE) ? 1 : -1; }
+inline int H5Sget_simple_extent_dims(hid_t id, hsize_t * dims, hsize_t * maxdims) {
+  h5mini_api::Obj * s = h5mini_api::get(id, h5mini_api::K_SPACE);
+  if(!s) return -1;
+  if(dims) dims[0] = s->n;
+  if(maxdims) maxdims[0] = s->n;
+  return 1;
+}
+inline herr_t H5Sclose(hid_t id) { return h5mini_api::release(id, h5mini_api::K_SPACE); }
+
+// ---- datasets ------------------------------------------------------------------------------------------------------
+inline hid_t H5Dcreate(hid_t loc_id, const char * name, hid_t type_id, hid_t space_id, hid_t, hid_t, hid_t) {
+  h5mini_api::Obj * l = h5mini_api::loc(loc_id);
+  h5mini_api::Obj * s = h5mini_api::get(space_id, h5mini_api::K_SPACE);
+  std::string leaf;
+  h5mini::Group * g = h5mini_api::walk(l, name, true, &leaf);
+  h5mini::TypeCode t;
+  if(!g || !s || !h5mini_api::type_of(type_id, t) || !l->file->writable() || g->groups.count(leaf) || g->datasets.count(leaf)) return -1;
+  h5mini::Dataset & d = g->datasets[leaf];
+  d.type = t; d.n = s->n;
+  l->file->touch();
+  h5mini_api::Obj o;
+  o.kind = h5mini_api::K_DSET; o.file = l->file; o.dset = &d;
+  return h5mini_api::put(o);
+}
+inline hid_t H5Dopen(hid_t loc_id, const char * name, hid_t) {
+  h5mini_api::Obj * l = h5mini_api::loc(loc_id);
+  std::string leaf;
+  h5mini::Group * g = h5mini_api::walk(l, name, true, &leaf);
+  if(!g) return -1;
+  auto it = g->datasets.find(leaf);
+  if(it == g->datasets.end()) return -1;
+  h5mini_api::Obj o;
+  o.kind = h5mini_api::K_DSET; o.file = l->file; o.dset = &it->second;
+  return h5mini_api::put(o);
+}
+inline hid_t H5Dget_space(hid_t id) {
+  h5mini_api::Obj * d = h5mini_api::get(id, h5mini_api::K_DSET);
+  if(!d) return -1;
+  h5mini_api::Obj o;
+  o.kind = h5mini_api::K_SPACE; o.n = d->dset->n;
+  return h5mini_api::put(o);
+}
+inline herr_t H5Dwrite(hid_t dset_id, hid_t mem_type, hid_t mem_space, hid_t file_space, hid_t, const void * buf) {
+  return h5mini_api::transfer(dset_id, mem_type, mem_space, file_space, nullptr, buf);
+}
+inline herr_t H5Dread(hid_t dset_id, hid_t mem_type, hid_t mem_space, hid_t file_space, hid_t, void * buf) {
+  return h5mini_api::transfer(dset_id, mem_type, mem_space, file_space, buf, nullptr);
+}
+inline herr_t H5Dclose(hid_t id) { return h5mini_api::release(id, h5mini_api::K_DSET); }
+
+// ---- attributes ----------------------------------------------------------------------------------------------------
+namespace h5mini_api {
+inline std::vector<h5mini::Attr> * attrs_of(hid_t loc_id, h5mini::File ** f) {
+  if(Obj * l = loc(loc_id)) { *f = l->file; return &l->group->attrs; }
+  if(Obj * d = get(loc_id, K_DSET)) { *f = d->file; return &d->dset->attrs; }
+  return nullptr;
+}
+}
+inline hid_t H5Acreate(hid_t loc_id, const char * name, hid_t type_id, hid_t space_id, hid_t, hid_t) {
+  h5mini::File * f = nullptr;
+  std::vector<h5mini::Attr> * v = h5mini_api::attrs_of(loc_id, &f);
+  h5mini_api::Obj * s = h5mini_api::get(space_id, h5mini_api::K_SPACE);
+  h5mini::TypeCode t;
+  if(!v || !s || !name || !h5mini_api::type_of(type_id, t) || !f->writable() || h5mini::find_attr(*v, name)) return -1;
+  h5mini::Attr a;
+  a.name = name; a.type = t; a.count = s->n;
+  a.data.assign((size_t)a.count * h5mini::type_size(t), 0);
+  v->push_back(a);
+  f->touch();
+  h5mini_api::Obj o;
+  o.kind = h5mini_api::K_ATTR; o.file = f; o.attrs = v; o.attr_idx = v->size() - 1;
+  return h5mini_api::put(o);
+}
+inline hid_t H5Aopen(hid_t loc_id, const char * name, hid_t) {
+  h5mini::File * f = nullptr;
+  std::vector<h5mini::Attr> * v = h5mini_api::attrs_of(loc_id, &f);
+  if(!v || !name) return -1;
+  for(size_t i = 0; i < v->size(); ++i)
+    if((*v)[i].name == name) {
+      h5mini_api::Obj o;
+      o.kind = h5mini_api::K_ATTR; o.file = f; o.attrs = v; o.attr_idx = i;
+      return h5mini_api::put(o);
+    }
+  return -1;
+}
+inline herr_t H5Awrite(hid_t id, hid_t mem_type, const void * buf) {
+  h5mini_api::Obj * o = h5mini_api::get(id, h5mini_api::K_ATTR);
+  h5mini::TypeCode mt;
+  if(!o || !buf || !h5mini_api::type_of(mem_type, mt) || !o->file->writable()) return -1;
+  h5mini::Attr & a = (*o->attrs)[o->attr_idx];
+  h5mini_api::convert(mt, buf, a.type, a.data.data(), a.count);
+  o->file->touch();
+  return 0;
+}
+inline herr_t H5Aread(hid_t id, hid_t mem_type, void * buf) {
+  h5mini_api::Obj * o = h5mini_api::get(id, h5mini_api::K_ATTR);
+  h5mini::TypeCode mt;
+  if(!o || !buf || !h5mini_api::type_of(mem_type, mt)) return -1;
+  const h5mini::Attr & a = (*o->attrs)[o->attr_idx];
+  h5mini_api::convert(a.type, a.data.data(), mt, buf, a.count);
+  return 0;
+}
+inline herr_t H5Aclose(hid_t id) { return h5mini_api::release(id, h5mini_api::K_ATTR); }
+
+// ---- property lists, error stack: accepted, nothing to configure ---------------------------------------------------
+inline hid_t H5Pcreate(hid_t) {
+  h5mini_api::Obj o;
+  o.kind = h5mini_api::K_PLIST;
+  return h5mini_api::put(o);
+}
+inline herr_t H5Pclose(hid_t id) { return h5mini_api::release(id, h5mini_api::K_PLIST); }
+template<typename C, typename I> inline herr_t H5Pset_fapl_mpio(hid_t, C, I) { return 0; }
+inline herr_t H5Pset_dxpl_mpio(hid_t, int) { return 0; }
+template<typename... A> inline herr_t H5Eset_auto(A...) { return 0; }
