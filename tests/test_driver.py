@@ -31,6 +31,33 @@ def run_driver(exe, workdir, fields, par, dim, iterations):
     return scal, diag, sets, hd
 
 
+def run_driver_h5(exe, workdir, fields, par, dim, iterations):
+    """The same run with H5part files on both sides of the driver: the initial data converted by h5tool, the snapshots
+    read back with the Python reader of tests/h5probe.py (the driver writes every step into <prefix>.h5part)."""
+    import h5probe
+    os.makedirs(workdir, exist_ok=True)
+    tool = os.path.join(B200, "h5tool")
+    fsphbin.write_initial_data(os.path.join(workdir, "id.fsphbin"), fields, dim)
+    subprocess.run([tool, "fromflat", os.path.join(workdir, "id.fsphbin"), os.path.join(workdir, "id.h5part")], check=True)
+    os.remove(os.path.join(workdir, "id.fsphbin"))
+    fsphbin.write_par(os.path.join(workdir, "run.par"), par, initial_data_prefix="id", output_h5data_prefix="out",
+                      final_iteration=iterations, out_screen_every=1, out_scalar_every=1, out_h5data_every=iterations,
+                      out_diagnostic_every=1)
+    for e in (exe, tool):
+        if not os.access(e, os.X_OK):
+            os.chmod(e, 0o755)
+    r = subprocess.run([exe, "run.par"], cwd=workdir, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    scal = np.loadtxt(os.path.join(workdir, "scalar_reductions.dat"), comments="#", ndmin=2)
+    diag = np.loadtxt(os.path.join(workdir, "diagnostic.dat"), comments="#", ndmin=2)
+    hf = h5probe.File(os.path.join(workdir, "out.h5part"))
+    assert hf.root.attrs["dimension"][0] == dim
+    last = max(hf.root.groups, key=lambda k: int(k.split("#")[1]))
+    st = hf.root.groups[last]
+    sets = {k: d.data for k, d in st.datasets.items()}
+    return scal, diag, sets, dict(iteration=int(st.attrs["iteration"][0]), time=float(st.attrs["time"][0]))
+
+
 def compare(a, b, iterations):
     (sa, da, fa, ha), (sb, db, fb, hb) = a, b
     assert sa.shape == sb.shape and sa.shape[0] == iterations + 1
@@ -136,3 +163,36 @@ def test_reference_driver_build_matches_reference_library(tmp_path):
     for k, col in (("x", capi.COL_POS), ("rho", capi.COL_RHO), ("u", capi.COL_U), ("h", capi.COL_H)):
         y = S.get(col).reshape(len(ids), -1)[:, 0][pb]
         assert np.abs(sets[k][pa] - y).max() <= 1e-12 * np.abs(y).max(), k
+
+
+def test_reference_driver_h5part_equals_flat(tmp_path):
+    """CPU: the reference driver with the reference's own mpisph/io.h (H5part files through the HDF5 stand-in of
+    flecsph_b200/host/h5mini) against the same driver with the flat container: identical bodies in, identical bodies out."""
+    exe_flat, exe_h5 = os.path.join(REF, "hydro_3d_ref"), os.path.join(REF, "hydro_3d_ref_h5")
+    if not have(exe_flat, exe_h5, os.path.join(B200, "h5tool")):
+        pytest.skip("driver binaries not built (make -C oracle drivers; make -C flecsph_b200/host)")
+    f, par = idata.sedov_3d(nx=10)
+    iters = 3
+    a = run_driver(exe_flat, str(tmp_path / "flat"), f, par, 3, iters)
+    b = run_driver_h5(exe_h5, str(tmp_path / "h5"), f, par, 3, iters)
+    assert np.array_equal(a[0], b[0])                       # scalar_reductions.dat
+    assert a[3]["iteration"] == b[3]["iteration"] == iters and a[3]["time"] == b[3]["time"]
+    pa, pb = np.argsort(a[2]["id"]), np.argsort(b[2]["id"])
+    common = sorted(set(a[2]) & set(b[2]))
+    assert {"x", "y", "z", "vx", "vy", "vz", "ax", "h", "rho", "u", "P", "m", "id", "dt"} <= set(common)
+    for k in common:
+        assert np.array_equal(a[2][k][pa], b[2][k][pb]), k
+
+
+@pytest.mark.gpu
+def test_unmodified_driver_with_h5part_io_on_gpu(tmp_path):
+    """The product build of the unmodified hydro_3d driver reading and writing H5part files (the reference's own io.h over
+    the HDF5 stand-in) against the reference build doing the same."""
+    exe_g, exe_r = os.path.join(B200, "hydro_3d_b200_h5"), os.path.join(REF, "hydro_3d_ref_h5")
+    if not have(exe_g, exe_r, os.path.join(B200, "h5tool")):
+        pytest.skip("driver binaries not built (need the reference checkout)")
+    f, par = idata.sedov_3d(nx=14)
+    g = run_driver_h5(exe_g, str(tmp_path / "gpu"), f, par, 3, 5)
+    r = run_driver_h5(exe_r, str(tmp_path / "ref"), f, par, 3, 5)
+    g[2].pop("neighbors", None); r[2].pop("neighbors", None)   # the reference's hydro drivers never fill body::neighbors_
+    compare(g, r, 5)
