@@ -319,8 +319,10 @@ class BodySystem:
         self._ck(self.lib.fsph_count_within(self.h, c.ctypes.data, float(radius), C.byref(n)))
         return n.value
 
-    def id_fill(self, mass, h, rho, u, u_blast_add=0.0, blast_radius=0.0, gamma=1.4, dt=0.0, radial_velocity=0.0):
-        f = np.array([mass, h, rho, u, u_blast_add, blast_radius, gamma, dt, radial_velocity], np.float64)
+    def id_fill(self, mass, h, rho, u, u_blast_add=0.0, blast_radius=0.0, gamma=1.4, dt=0.0, radial_velocity=0.0, rho_eos=None, pressure=None):
+        """rho_eos: the density P = rho_eos u (gamma - 1) is computed with (default: rho); pressure: a constant instead."""
+        f = np.array([mass, h, rho, u, u_blast_add, blast_radius, gamma, dt, radial_velocity, rho if rho_eos is None else rho_eos,
+                      float("nan") if pressure is None else pressure], np.float64)
         self._ck(self.lib.fsph_id_fill(self.h, f.ctypes.data))
 
     def snapshot(self, names=None):

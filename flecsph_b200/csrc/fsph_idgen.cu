@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) k_count_within(Cols c, int64_t n, double 
 }
 
 struct IdFill {
-  double mass, h, rho, u, u_blast_add, blast_radius, gamma, dt, radial_velocity;
+  double mass, h, rho, u, u_blast_add, blast_radius, gamma, dt, radial_velocity, rho_eos, pressure;
 };
 
 __global__ void __launch_bounds__(256) k_id_fill(Cols c, int64_t n, IdFill f) {
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) k_id_fill(Cols c, int64_t n, IdFill f) {
   // sedov/main.cc:297-304: the blast energy is shared by the bodies inside the blast radius
   const double u = f.u + (r < f.blast_radius ? f.u_blast_add : 0.0);
   c.f[F_U][i] = u;
-  c.f[F_P][i] = f.rho * u * (f.gamma - 1);
+  c.f[F_P][i] = isnan(f.pressure) ? f.rho_eos * u * (f.gamma - 1) : f.pressure;
   c.f[F_DT][i] = f.dt;
   // noh/main.cc:272-276: v = -v0 r / |r|
   const double rr = r > 0 ? r : 1.0, on = r > 0 ? 1.0 : 0.0;
@@ -239,13 +239,14 @@ int32_t fsph_count_within(fsph_system * s, const double * center, double radius,
   }
 }
 
-// uniform fields of a lattice body set: f = {mass, h, rho, u, u_blast_add, blast_radius, gamma, dt, radial_velocity};
-// P = rho u (gamma - 1), u += u_blast_add inside the blast radius, v = radial_velocity r / |r|
-int32_t fsph_id_fill(fsph_system * s, const double * f9) {
+// uniform fields of a lattice body set: f = {mass, h, rho, u, u_blast_add, blast_radius, gamma, dt, radial_velocity, rho_eos,
+// pressure}; P = rho_eos u (gamma - 1) or the constant `pressure` (when not NaN), u += u_blast_add inside the blast radius,
+// v = radial_velocity r / |r|
+int32_t fsph_id_fill(fsph_system * s, const double * f11) {
   if(!s) return 1;
   try {
     FSPH_CUDA_OK(cudaSetDevice(s->device));
-    IdFill f{f9[0], f9[1], f9[2], f9[3], f9[4], f9[5], f9[6], f9[7], f9[8]};
+    IdFill f{f11[0], f11[1], f11[2], f11[3], f11[4], f11[5], f11[6], f11[7], f11[8], f11[9], f11[10]};
     if(s->n > 0) FSPH_LAUNCH(k_id_fill, (unsigned)((s->n + 255) / 256), 256, s->stream, s->cols(), s->n, f);
     FSPH_CUDA_OK(cudaStreamSynchronize(s->stream));
     FSPH_CUDA_OK(cudaGetLastError());

@@ -85,35 +85,57 @@ def lattice_3d(lattice_type, domain_type, bmin, bmax, sep, slab=None):
     return np.concatenate(out, 0) if out else np.zeros((0, 3))
 
 
-def _sphere_common(nx, rho0, P0, gamma, eta, kernel_width, R=1.0, lattice_type=2, slab=None, allsum=None):
+def _sphere_common(kind, nx, rho0, P0, gamma, eta, kernel_width, R=1.0, lattice_type=2, slab=None, allsum=None):
     """slab / allsum: generate only this rank's layers; allsum(int) -> the sum over all ranks (global counts)."""
     sep = 2.0 * R / (nx - 1)
     pos = lattice_3d(lattice_type, 1, (-R,) * 3, (R,) * 3, sep, slab=slab)
     n_local = len(pos)
     n = allsum(n_local) if allsum else n_local
-    total_mass = rho0 * (4.0 * math.pi / 3.0) * R ** 3  # constant profile normalisation (sedov/main.cc:126-133)
-    m = total_mass / n
-    h = eta * kernel_width * (m / rho0) ** (1.0 / 3.0)
-    K0 = P0 / rho0 ** gamma
-    u = K0 * rho0 ** (gamma - 1) / (gamma - 1)
+    m, rho_st, rho_eos, h, u, P = sphere_scalars(kind, n, rho0, P0, gamma, eta, kernel_width, R)
     ids = np.arange(n_local, dtype=np.int64)
     if slab is not None:
         ids += np.int64(slab[0]) << np.int64(40)  # unique across ranks without a prefix sum of the counts
     n = n_local
-    f = dict(pos=pos, vel=np.zeros((n, 3)), mass=np.full(n, m), h=np.full(n, h), rho=np.full(n, rho0),
+    f = dict(pos=pos, vel=np.zeros((n, 3)), mass=np.full(n, m), h=np.full(n, h), rho=np.full(n, rho_st),
              u=np.full(n, u), id=ids)
-    return f, m
+    return f, m, rho_eos, P
+
+
+def sphere_scalars(kind, n, rho0, P0, gamma, eta, kernel_width, R=1.0):
+    """Per-body scalars of the constant-density sphere set-ups with each generator's own expressions:
+    (mass, stored density, density its pressure is computed with, smoothing length, internal energy, pressure).
+      sedov (sedov/main.cc:126-133,271-307) and noh (noh/main.cc:106-112,251-290): the density goes through the
+        renormalised profile, rho_initial / profile(0) * profile(r/R) -- one rounding away from rho_initial -- and h, u, P
+        follow from it; noh then stores rho_initial itself (noh/main.cc:260-261);
+      collapse (collapse/main.cc:94-113,183-190): rho_initial, pressure_initial and u = P / (rho (gamma - 1)) as they are."""
+    if kind == "collapse":
+        total_mass = rho0 * 4.0 / 3.0 * math.pi * (R * R * R)
+        m = total_mass / n
+        return m, rho0, rho0, eta * kernel_width * math.pow(m / rho0, 1.0 / 3), P0 / (rho0 * (gamma - 1.0)), P0
+    prof0 = 0.75 / math.pi                      # density_profiles::rho_constant_density, 3-D (density_profiles.h:69-81)
+    total_mass = rho0 * (R * R * R) / prof0     # "normalize mass such that central density is rho_initial"
+    m = total_mass / n
+    rho_a = rho0 / prof0 * prof0
+    h = eta * kernel_width * math.pow(m / rho_a, 1.0 / 3)
+    K0 = P0 / math.pow(rho0, gamma)
+    u = K0 * math.pow(rho_a, gamma - 1) / (gamma - 1)
+    return m, (rho0 if kind == "noh" else rho_a), rho_a, h, u, None
+
+
+def blast_energy_per_mass(blast_energy, m, nblast):
+    """sedov/main.cc:236-243,293: u_blast = E / mass_blast with the blast mass accumulated body by body."""
+    return blast_energy / float(np.cumsum(np.full(nblast, m))[-1])
 
 
 def sedov_3d(nx=20, eta=1.2, blast_energy=2e-7, blast_radius=0.06, P0=1e-7, gamma=1.4, slab=None, allsum=None):
     """Sedov blast wave, data/sedov_nx20.par semantics; nx scales the particle count (~0.74 nx^3)."""
-    f, m = _sphere_common(nx, 1.0, P0, gamma, eta, 2.0, slab=slab, allsum=allsum)
+    f, m, rho_eos, _ = _sphere_common("sedov", nx, 1.0, P0, gamma, eta, 2.0, slab=slab, allsum=allsum)
     r = np.sqrt((f["pos"] ** 2).sum(1))
     blast = r < blast_radius
     nblast = allsum(int(blast.sum())) if allsum else int(blast.sum())
     if nblast:
-        f["u"] = f["u"] + np.where(blast, blast_energy / (m * nblast), 0.0)
-    f["P"] = f["rho"] * f["u"] * (gamma - 1)
+        f["u"] = f["u"] + np.where(blast, blast_energy_per_mass(blast_energy, m, nblast), 0.0)
+    f["P"] = rho_eos * f["u"] * (gamma - 1)
     f["dt"] = np.full(len(r), 1e-4)
     par = dict(sph_kernel="wendland c4", sph_eta=eta, poly_gamma=gamma, initial_dt=1e-4, sph_variable_h=1,
                adaptive_timestep=1, timestep_cfl_factor=0.01)
@@ -122,11 +144,11 @@ def sedov_3d(nx=20, eta=1.2, blast_energy=2e-7, blast_radius=0.06, P0=1e-7, gamm
 
 def noh_3d(nx=20, eta=1.2, P0=1e-6, gamma=1.6666667, infall=0.1):
     """Noh implosion, data/noh_nx20.par semantics (noh/main.cc:236-292): radial inflow v = -0.1 r/|r|."""
-    f, m = _sphere_common(nx, 1.0, P0, gamma, eta, 2.0)
+    f, m, rho_eos, _ = _sphere_common("noh", nx, 1.0, P0, gamma, eta, 2.0)
     r = np.sqrt((f["pos"] ** 2).sum(1))
     rr = np.where(r > 0, r, 1.0)
     f["vel"] = -infall * f["pos"] / rr[:, None] * (r > 0)[:, None]
-    f["P"] = f["rho"] * f["u"] * (gamma - 1)
+    f["P"] = rho_eos * f["u"] * (gamma - 1)
     f["dt"] = np.full(len(r), 2e-3)
     par = dict(sph_kernel="wendland c4", sph_eta=eta, poly_gamma=gamma, initial_dt=2e-3, sph_variable_h=1,
                adaptive_timestep=1, timestep_cfl_factor=0.25)
@@ -135,8 +157,8 @@ def noh_3d(nx=20, eta=1.2, P0=1e-6, gamma=1.6666667, infall=0.1):
 
 def collapse_3d(nx=10, eta=1.2, P0=1e-10, gamma=1.4):
     """Self-gravitating cold sphere, data/collapse_nx10.par semantics: quintic spline, du/dt path, FMM gravity."""
-    f, m = _sphere_common(nx, 1.0, P0, gamma, eta, 3.0)
-    f["P"] = f["rho"] * f["u"] * (gamma - 1)
+    f, m, _, P = _sphere_common("collapse", nx, 1.0, P0, gamma, eta, 3.0)
+    f["P"] = np.full(len(f["mass"]), P)
     f["dt"] = np.full(len(f["mass"]), 5e-4)
     par = dict(sph_kernel="quintic spline", sph_eta=eta, poly_gamma=gamma, initial_dt=5e-4, sph_variable_h=0,
                adaptive_timestep=0, thermokinetic_formulation=0, enable_fmm=1, fmm_macangle=0.8,
@@ -267,18 +289,14 @@ def sphere_on_device(system, kind, nx, slab=None, allsum=None, eta=1.2, R=1.0, *
     slab = slab or (0, 1)
     n_local = system.generate_lattice(2, 1, (-R,) * 3, (R,) * 3, sep, slab=slab, id_offset=(slab[0] << 40) if slab[1] > 1 else 0)
     n = allsum(n_local) if allsum else n_local
-    total_mass = rho0 * (4.0 * math.pi / 3.0) * R ** 3
-    m = total_mass / n
-    h = eta * spec["kw_"] * (m / rho0) ** (1.0 / 3.0)
-    K0 = P0 / rho0 ** gamma
-    u = K0 * rho0 ** (gamma - 1) / (gamma - 1)
+    m, rho_st, rho_eos, h, u, P_const = sphere_scalars(kind, n, rho0, P0, gamma, eta, spec["kw_"], R)
     add, rb = 0.0, 0.0
     if spec["blast"]:
         e_blast, rb = spec["blast"]
         nb = system.count_within((0.0, 0.0, 0.0), rb)
         nb = allsum(nb) if allsum else nb
-        add = e_blast / (m * nb) if nb else 0.0
-    system.id_fill(m, h, rho0, u, add, rb, gamma, spec["dt"], spec["v"])
+        add = blast_energy_per_mass(e_blast, m, nb) if nb else 0.0
+    system.id_fill(m, h, rho_st, u, add, rb, gamma, spec["dt"], spec["v"], rho_eos=rho_eos, pressure=P_const)
     par = {"sedov": sedov_3d, "noh": noh_3d, "collapse": collapse_3d}[kind](nx=4)[1]
     return n_local, par
 

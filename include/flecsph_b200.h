@@ -306,13 +306,16 @@ int32_t fsph_neighbor_lists(fsph_system * s, int64_t * offsets, int64_t * ids);
  *                          generation order, ids = id_offset + index.  slab_k of slab_K selects one contiguous group of
  *                          z layers (one per rank of a multi-GPU run).  Resizes the system; *n_out = bodies made.
  *   fsph_count_within      bodies with |x - c| < radius (blast region, sedov/main.cc:283-295).
- *   fsph_id_fill           f = {mass, h, rho, u, u_blast_add, blast_radius, gamma, dt, radial_velocity}: uniform
- *                          mass / h / rho / dt, u (+ u_blast_add inside the blast radius, sedov/main.cc:297-304),
- *                          P = rho u (gamma - 1), v = radial_velocity r / |r| (noh/main.cc:272-276). */
+ *   fsph_id_fill           f = {mass, h, rho, u, u_blast_add, blast_radius, gamma, dt, radial_velocity, rho_eos, pressure}:
+ *                          uniform mass / h / rho / dt, u (+ u_blast_add inside the blast radius, sedov/main.cc:297-304),
+ *                          P = rho_eos u (gamma - 1) -- the generators compute it with the renormalised profile density,
+ *                          which noh then replaces by rho_initial in the stored column (noh/main.cc:251-261,290) -- or the
+ *                          constant `pressure` when that is not NaN (collapse/main.cc:186), v = radial_velocity r / |r|
+ *                          (noh/main.cc:272-276). */
 int32_t fsph_generate_lattice(fsph_system * s, int32_t lattice_type, int32_t domain_type, const double * bmin, const double * bmax,
   double sep, int32_t slab_k, int32_t slab_K, int64_t id_offset, int64_t * n_out);
 int32_t fsph_count_within(fsph_system * s, const double * center, double radius, int64_t * out);
-int32_t fsph_id_fill(fsph_system * s, const double * f9);
+int32_t fsph_id_fill(fsph_system * s, const double * f11);
 
 /* Device micro-benchmarks (roofline denominators measured on the GPU the run uses; SURVEY.md 8d asks for the fp64
  * one because MEASURED_PEAKS.json has none): sustained DFMA rate in TFLOP/s and 128-bit copy bandwidth in GB/s
