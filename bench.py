@@ -475,16 +475,26 @@ def main():
                               "phases_ms_rank0": ph, "n_gpus": world}
         if world == 1:
             # BASELINE.json configs[3] and [4] at full size on one GPU (KH: periodic box, eta 1.5; collapse: quintic, FMM)
-            f, par = idata.kh_3d(nx=310)
-            ss = make_cuda_system(f, par, local_rank)
-            nb = len(f["mass"])
-            del f
-            ms, ph = time_steps(ss, 3, 2)
-            configs["kelvin_helmholtz_3d"] = {"bodies": nb, "bodies_with_periodic_copies": ss.nbodies(), "ms_per_step": ms,
-                                              "updates_per_s": nb / (ms * 1e-3), "phases_ms_rank0": ph, "n_gpus": 1}
-            ss.close()
-            sub("collapse", 32e6, "collapse_newtonian_3d")
-            sub("sedov", 16e6, "sedov_3d_16M")
+            # a sub-record that fails (these are not the headline) is reported as such instead of taking the line with it
+            def guarded_sub(label, fn):
+                try:
+                    fn()
+                except Exception as e:      # noqa: BLE001
+                    configs[label] = {"error": str(e)[:300]}
+
+            def kh():
+                # app/id_generators/KH/main.cc with data/KH_3d.par semantics (HCP blocks, density ratio 2), lattice_nx for ~32 M bodies
+                f, par = idata.kh_3d_reference(nx=328)
+                ss = make_cuda_system(f, par, local_rank)
+                nb = len(f["mass"])
+                del f
+                ms, ph = time_steps(ss, 3, 2)
+                configs["kelvin_helmholtz_3d"] = {"bodies": nb, "bodies_with_periodic_copies": ss.nbodies(), "lattice_nx": 328, "ms_per_step": ms,
+                                                  "updates_per_s": nb / (ms * 1e-3), "phases_ms_rank0": ph, "n_gpus": 1}
+                ss.close()
+            guarded_sub("kelvin_helmholtz_3d", kh)
+            guarded_sub("collapse_newtonian_3d", lambda: sub("collapse", 32e6, "collapse_newtonian_3d"))
+            guarded_sub("sedov_3d_16M", lambda: sub("sedov", 16e6, "sedov_3d_16M"))
         else:
             sub("sedov", 64e6, "sedov_3d_64M_strong_scaling")     # the metric as BASELINE.json quotes it: 64 M bodies in total
             sub("noh", 128e6, "noh_3d_128M")

@@ -8,7 +8,10 @@ generators produce, so that no HDF5 file is needed:
   * Sedov blast:  app/id_generators/sedov/main.cc:68-312 with data/sedov_nx20.par;
   * Noh implosion: app/id_generators/noh/main.cc:236-292 with data/noh_nx20.par;
   * Sod tube 1-D: app/id_generators/sodtube/main.cc with data/sodtube_t1_n100.par
-    (equal-mass variant, test #1).
+    (equal-mass variant, test #1);
+  * Kelvin-Helmholtz 3-D: app/id_generators/KH/main.cc with data/KH_3d.par.
+The sphere set-ups and Kelvin-Helmholtz are bit-equal to the H5part files the reference's own generators write
+(tests/test_generators.py).
 Every function returns (fields, params_overrides): a dict of column-name ->
 numpy array in generation order (ids 0..N-1) and the `.par` values of the run.
 """
@@ -231,47 +234,84 @@ def periodic_box(n, dim=3, seed=0, h_jitter=0.0, eta=1.2, vel_amp=0.1, box=(1.0,
     return f, par
 
 
-def kh_3d(nx=20, eta=1.5, gamma=1.4, density_ratio=2.0, flow_velocity=1.0, P0=2.5, A=0.025, lam=1.0 / 6.0, L=1.0):
-    """Kelvin-Helmholtz shear layer in a fully periodic unit box, data/KH_3d.par semantics (app/id_generators/KH/main.cc):
-    a dense middle slab |y| < L/4 moving at +v/2 between two slabs of half the density moving at -v/2, equal-mass
-    particles (so the outer slabs are coarser by cbrt(density_ratio)), eta = 1.5, velocity perturbation a la Price
-    (2008) at the interfaces (main.cc:352-356).  Simplification: rectangular lattices that tile the periodic box exactly
-    (the reference builds HCP lattices and stretches the outer blocks to fit, main.cc:296-326)."""
-    s = L / nx
-    def block(n_x, n_y, n_z, y_lo, y_hi):
-        xs = -0.5 * L + (np.arange(n_x) + 0.5) * (L / n_x)
-        ys = y_lo + (np.arange(n_y) + 0.5) * ((y_hi - y_lo) / n_y)
-        zs = -0.5 * L + (np.arange(n_z) + 0.5) * (L / n_z)
-        Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
-        vol = (L / n_x) * ((y_hi - y_lo) / n_y) * (L / n_z)
-        return np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1), vol
-    n_mid_y = max(nx // 2, 1)
-    n_out = max(int(round(nx / density_ratio ** (1.0 / 3.0))), 1)
-    n_out_y = max(int(round(n_out / 4.0)), 1)
-    pm, vol_m = block(nx, n_mid_y, nx, -0.25 * L, 0.25 * L)
-    pt, vol_t = block(n_out, n_out_y, n_out, 0.25 * L, 0.5 * L)
-    pb, _ = block(n_out, n_out_y, n_out, -0.5 * L, -0.25 * L)
-    rho_m = density_ratio
-    m = rho_m * vol_m                     # equal masses
-    rho_t = m / vol_t
-    pos = np.concatenate([pm, pt, pb])
-    n, nm = len(pos), len(pm)
-    mid = np.arange(n) < nm
+def kh_blocks(nx, lattice_type=1, density_ratio=2.0, box=(1.0, 1.0, 1.0)):
+    """set_derived_params of app/id_generators/KH/main.cc:58-226 (3-D): the three lattice blocks (middle, top, bottom) as
+    (bmin, bmax, separation), and the lengths the stretching step needs."""
+    L, W, H = box
+    sep = L / nx
+    sep_t = sep * math.cbrt(density_ratio)
+    dx_m = dy_m = dY_m = dz_m = dZ_m = sep
+    dx_t = dy_t = dY_t = dz_t = dZ_t = sep_t
+    if lattice_type in (1, 2):
+        dy_m *= math.sqrt(3.) / 2.; dY_m = 2. * dy_m
+        dy_t *= math.sqrt(3.) / 2.; dY_t = 2. * dy_t
+        dz_m *= math.sqrt(2. / 3.); dz_t *= math.sqrt(2. / 3.)
+        dZ_m = (2. if lattice_type == 1 else 3.) * dz_m
+        dZ_t = (2. if lattice_type == 1 else 3.) * dz_t
+    w_m = math.floor(W / (3. * dY_m)) * dY_m
+    gap = min(dY_m, dY_t) / 2.
+    w_t = math.floor((W / 2. - w_m / 2. - gap) / dY_t) * dY_t
+    Nx_t = int(math.floor(L / dx_t + 0.1))
+    q = 2. if lattice_type == 0 else 4.
+    mx = (-L / 2. + dx_m / q, L / 2.)
+    tx = (-Nx_t * dx_t / 2. + dx_t / q, Nx_t * dx_t / 2.)
+    h_m = int(math.floor(H / dZ_m)) * dZ_m
+    h_t = int(math.floor(H / dZ_t)) * dZ_t
+    mid = ((mx[0], -0.5 * w_m, -h_m / 2.), (mx[1], 0.5 * w_m + 0.01 * dy_m, h_m / 2.), sep)
+    top = ((tx[0], 0.5 * w_m + gap, -h_t / 2.), (tx[1], 0.5 * w_m + gap + w_t, h_t / 2.), sep_t)
+    bot = ((tx[0], -0.5 * w_m - gap - w_t, -h_t / 2.), (tx[1], -0.5 * w_m - gap + 0.01 * dy_t, h_t / 2.), sep_t)
+    return dict(blocks=(mid, top, bot), sep=sep, dx_t=dx_t, w_m=w_m, gap=gap, h_m=h_m, h_t=h_t)
+
+
+def kh_3d_reference(nx=30, lattice_type=1, eta=1.5, gamma=1.4, density_ratio=2.0, flow_velocity=1.0, rho_initial=1.0,
+                    pressure_initial=1.0, A=0.025, lam=0.1666, box=(1.0, 1.0, 1.0), cfl=0.25, kernel_width=2.0):
+    """Kelvin-Helmholtz initial data as app/id_generators/KH/main.cc builds it (data/KH_3d.par): an HCP (or FCC /
+    rectangular) block of density rho * ratio moving at +v/2 between two coarser blocks of density rho moving at -v/2,
+    equal masses; the outer blocks are stretched to fit the periodic box (main.cc:296-326), a velocity perturbation a la
+    Price (2008) sits at the interfaces (:352-356).  Statement by statement; bit-equal to the generator's H5part file
+    (tests/test_generators.py).  Returns (fields, par); the generator's suggested time step is par["initial_dt"]."""
+    L, W, H = box
+    g = kh_blocks(nx, lattice_type, density_ratio, box)
+    parts = [lattice_3d(lattice_type, 0, bmin, bmax, sp) for bmin, bmax, sp in g["blocks"]]
+    npm, npt = len(parts[0]), len(parts[1])
+    pos = np.concatenate(parts, 0)
+    n = len(pos)
+    x, y, z = pos[:, 0].copy(), pos[:, 1].copy(), pos[:, 2].copy()
+    rho_t, rho_m = rho_initial, rho_initial * density_ratio
+    pmass = rho_m * g["sep"] * g["sep"] * g["sep"]
+    if lattice_type in (1, 2):
+        pmass *= 1. / math.sqrt(2.)
+    # stretch the top and bottom blocks to the box (main.cc:296-326)
+    yx = math.floor(L / g["dx_t"] + 0.1) * g["dx_t"] / L
+    yz = g["h_t"] / g["h_m"]
+    y0 = g["w_m"] / 2. + g["gap"]
+    o = slice(npm, n)
+    y[o] = np.where(y[o] > 0, y0 + yx * yz * (y[o] - y0), -y0 + yx * yz * (y[o] + y0))
+    x[o] = x[o] / yx
+    z[o] = z[o] / yz
+    ys = .5 * W / abs(y[npm + npt])
+    y = y * ys
+    pmass *= ys
+    zs = .5 * H / abs(z[npm + npt])
+    z = z * zs
+    pmass *= zs
+    mid = np.arange(n) < npm
     rho = np.where(mid, rho_m, rho_t)
     vel = np.zeros((n, 3))
-    vel[:, 0] = np.where(mid, 0.5 * flow_velocity, -0.5 * flow_velocity)
-    x, y = pos[:, 0], pos[:, 1]
-    up = (y < 0.25 * L) & (y > 0.25 * L - 0.025)
-    dn = (y > -0.25 * L) & (y < -0.25 * L + 0.025)
-    vel[:, 1] = np.where(up, A * np.sin(-2 * np.pi * (x + 0.5) / lam), 0.0) + np.where(dn, A * np.sin(2 * np.pi * (x + 0.5) / lam), 0.0)
-    u = P0 / (gamma - 1.0) / rho
-    h = eta * 2.0 * (m / rho) ** (1.0 / 3.0)
-    cs = math.sqrt(gamma * P0 / rho_t)
-    dt0 = 0.25 * s / max(cs, flow_velocity)
-    f = dict(pos=pos, vel=vel, mass=np.full(n, m), h=h, rho=rho, u=u, P=np.full(n, P0), id=np.arange(n, dtype=np.int64),
+    vel[:, 0] = np.where(mid, flow_velocity / 2.0, -flow_velocity / 2.0)
+    up = np.nonzero((y < 0.25) & (y > 0.25 - 0.025))[0]
+    dn = np.nonzero((y > -0.25) & (y < -0.25 + 0.025))[0]
+    vel[up, 1] = [A * math.sin(-2 * math.pi * (xx + .5) / lam) for xx in x[up]]     # libm sin, as the generator's
+    vel[dn, 1] = [A * math.sin(2 * math.pi * (xx + .5) / lam) for xx in x[dn]]
+    P = np.full(n, pressure_initial)
+    u = P / (gamma - 1.) / rho
+    h = np.where(mid, eta * kernel_width * math.pow(pmass / rho_m, 1. / 3), eta * kernel_width * math.pow(pmass / rho_t, 1. / 3))
+    cs = math.sqrt(gamma * max(pressure_initial / rho_m, pressure_initial / rho_t))
+    dt0 = cfl * g["sep"] / max(cs, flow_velocity)
+    f = dict(pos=np.stack([x, y, z], 1), vel=vel, mass=np.full(n, pmass), h=h, rho=rho, u=u, P=P, id=np.arange(n, dtype=np.int64),
              dt=np.full(n, dt0))
     par = dict(sph_kernel="wendland c4", sph_eta=eta, poly_gamma=gamma, initial_dt=dt0, sph_variable_h=1, adaptive_timestep=1,
-               timestep_cfl_factor=0.25, box_length=L, box_width=L, box_height=L, periodic_boundary_x=1, periodic_boundary_y=1,
+               timestep_cfl_factor=cfl, box_length=L, box_width=W, box_height=H, periodic_boundary_x=1, periodic_boundary_y=1,
                periodic_boundary_z=1)
     return f, par
 

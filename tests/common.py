@@ -44,7 +44,7 @@ def case(name, **kw):
         par = dict(par, **kw.get("par", {}))
         return f, par, dim
     if name == "kh":
-        f, par = idata.kh_3d(nx=kw.get("nx", 20))
+        f, par = idata.kh_3d_reference(nx=kw.get("nx", 20))
         return f, par, 3
     if name == "periodic":
         dim = kw.get("dim", 3)

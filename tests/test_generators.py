@@ -85,3 +85,46 @@ def test_numpy_generators_equal_the_reference_generators(tmp_path, kind, nx, ext
         assert np.array_equal(st[k].data, v), "%s: max abs diff %g" % (k, np.abs(st[k].data - v).max())
     if kind == "sedov":
         assert (f["u"] > f["u"].min()).sum() >= 1   # the blast region is populated
+
+
+KH_PAR = """
+  initial_data_prefix = "id"
+  lattice_nx = %d
+  poly_gamma = 1.4
+  KH_A = 0.025
+  KH_lambda = 0.1666
+  density_ratio = %g
+  equal_mass = yes
+  lattice_type = %d
+  domain_type = 0
+  flow_velocity = 1
+  sph_kernel = "Wendland C4"
+  sph_eta = 1.5
+  initial_dt = 1.0
+  timestep_cfl_factor = 0.25
+  box_width = 1.
+  box_length = 1.
+  box_height = 1.
+"""
+
+
+@pytest.mark.parametrize("nx,lattice_type,ratio", [(30, 1, 2.0), (22, 2, 2.0), (41, 0, 2.0), (26, 1, 3.0)])
+def test_kelvin_helmholtz_equals_the_reference_generator(tmp_path, nx, lattice_type, ratio):
+    """app/id_generators/KH/main.cc (data/KH_3d.par: HCP; also FCC / rectangular and another density ratio)."""
+    exe = os.path.join(REF, "KH_3d_generator")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/KH_3d_generator not built (make -C oracle generators; needs the reference checkout)")
+    if not os.access(exe, os.X_OK):
+        os.chmod(exe, 0o755)
+    (tmp_path / "id.par").write_text(KH_PAR % (nx, ratio, lattice_type))
+    r = subprocess.run([exe, "id.par"], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    hf = h5probe.File(str(tmp_path / "id.h5part"))
+    st = hf.root.groups["Step#0"].datasets
+    f, par = idata.kh_3d_reference(nx=nx, lattice_type=lattice_type, density_ratio=ratio)
+    assert hf.root.attrs["nparticles"][0] == len(f["mass"]) and hf.root.attrs["timestep"][0] == par["initial_dt"]
+    want = dict(x=f["pos"][:, 0], y=f["pos"][:, 1], z=f["pos"][:, 2], vx=f["vel"][:, 0], vy=f["vel"][:, 1], m=f["mass"], h=f["h"], rho=f["rho"],
+                u=f["u"], P=f["P"], id=f["id"])
+    for k, v in want.items():
+        assert np.array_equal(st[k].data, v), "%s: max abs diff %g" % (k, np.abs(st[k].data - v).max())
+    assert (f["vel"][:, 1] != 0).sum() > 0 and (f["rho"] == ratio).any() and (f["rho"] == 1.0).any()
