@@ -45,6 +45,12 @@ def case(name, **kw):
         return f, par, dim
     if name == "kh":
         f, par = idata.kh_3d_reference(nx=kw.get("nx", 20))
+        # off the exact lattice: the generator puts bodies exactly on faces of the periodic box and on key-cell boundaries, where
+        # a last-bit difference of a (1e-10-tolerance) acceleration changes a key digit after the drift -- the storage order,
+        # the numbering of the periodic copies that follows it (boundary.h:218-243) and the traversal-order-dependent signal
+        # speed then differ between two correct implementations.  The generator itself is pinned in tests/test_generators.py.
+        nx = kw.get("nx", 20)
+        f["pos"] = f["pos"] + (1e-3 / nx) * np.random.default_rng(5).standard_normal(f["pos"].shape)
         return f, par, 3
     if name == "periodic":
         dim = kw.get("dim", 3)
