@@ -128,3 +128,22 @@ def test_kelvin_helmholtz_equals_the_reference_generator(tmp_path, nx, lattice_t
     for k, v in want.items():
         assert np.array_equal(st[k].data, v), "%s: max abs diff %g" % (k, np.abs(st[k].data - v).max())
     assert (f["vel"][:, 1] != 0).sum() > 0 and (f["rho"] == ratio).any() and (f["rho"] == 1.0).any()
+
+
+@pytest.mark.parametrize("nx", [100, 400])
+def test_sod_tube_equals_the_reference_generator(tmp_path, nx):
+    """app/id_generators/sodtube/main.cc, 1-D, test #1, equal masses (data/sodtube_t1_n100.par)."""
+    exe = os.path.join(REF, "sodtube_1d_generator")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/sodtube_1d_generator not built (make -C oracle generators; needs the reference checkout)")
+    if not os.access(exe, os.X_OK):
+        os.chmod(exe, 0o755)
+    (tmp_path / "id.par").write_text('  initial_data_prefix = "id"\n  lattice_nx = %d\n  poly_gamma = 1.4\n  sodtest_num = 1\n  equal_mass = yes\n'
+                                     '  sph_eta = 1.2\n  lattice_type = 1\n  sph_kernel = "Wendland C4"\n  initial_dt = 0.001\n' % nx)
+    r = subprocess.run([exe, "id.par"], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    st = h5probe.File(str(tmp_path / "id.h5part")).root.groups["Step#0"].datasets
+    f, _ = idata.sodtube_1d(nx=nx)
+    want = dict(x=f["pos"][:, 0], vx=f["vel"][:, 0], m=f["mass"], h=f["h"], rho=f["rho"], u=f["u"], P=f["P"], id=f["id"])
+    for k, v in want.items():
+        assert np.array_equal(st[k].data, v), "%s: max abs diff %g" % (k, np.abs(st[k].data - v).max())
