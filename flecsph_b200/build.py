@@ -71,7 +71,7 @@ def build_cuda(verbose=False, force=False):
 def build_oracle():
     """oracle/_ref from /root/reference when it is present (dev container); prebuilt files travel to the GPU box."""
     if os.path.isdir("/root/reference/include"):
-        r = subprocess.run(["make", "-j4", "-C", os.path.join(ROOT, "oracle"), "ref", "ref_fast", "drivers", "h5part", "generators"], capture_output=True, text=True)
+        r = subprocess.run(["make", "-j4", "-C", os.path.join(ROOT, "oracle"), "ref", "ref_fast", "drivers", "h5part", "generators", "unit_tests"], capture_output=True, text=True)
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("oracle/_ref build failed")
