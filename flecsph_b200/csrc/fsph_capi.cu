@@ -714,9 +714,34 @@ int32_t fsph_gravitation_fmm(fsph_system * s) {
   return guarded(s, [&]() { gravitation_fmm(*s); check_status(*s); });
 }
 int32_t fsph_get_range(fsph_system * s, double * lo, double * hi) {
-  if(!s) return 1;
-  for(int d = 0; d < s->dim; ++d) { lo[d] = s->lo[d]; hi[d] = s->hi[d]; }
-  return 0;
+  // body_system::getRange (bodies_system.h:131-138) is mpi_compute_range of the bodies as they are NOW -- not the range of
+  // the last update_iteration (mpisph/test/bs.cc:29-35 asks for it right after read_bodies).  While positions and h are
+  // those of the last update_iteration the stored range is that very result.
+  return guarded(s, [&]() {
+    if(!(s->tree_valid && !s->tree_dirty) && s->n_owned_or_n() > 0) {
+      double keep_lo[3], keep_hi[3];
+      for(int d = 0; d < 3; ++d) { keep_lo[d] = s->lo[d]; keep_hi[d] = s->hi[d]; }
+      compute_range(*s);
+      if(s->comm) {
+        // MPI_Allreduce MIN / MAX of the ranks' ranges (bodies_system.h:255-262)
+        const int P = s->comm->nranks;
+        double mine[6] = {s->lo[0], s->lo[1], s->lo[2], s->hi[0], s->hi[1], s->hi[2]};
+        std::vector<double> all((size_t)6 * P);
+        dist_all_gather_host(*s, mine, all.data(), sizeof(mine));
+        for(int q = 0; q < P; ++q)
+          for(int d = 0; d < s->dim; ++d) {
+            s->lo[d] = std::min(s->lo[d], all[(size_t)6 * q + d]);
+            s->hi[d] = std::max(s->hi[d], all[(size_t)6 * q + 3 + d]);
+          }
+      }
+      for(int d = 0; d < s->dim; ++d) { lo[d] = s->lo[d]; hi[d] = s->hi[d]; }
+      // the keys of a still valid tree belong to the range they were made with
+      if(s->tree_valid)
+        for(int d = 0; d < 3; ++d) { s->lo[d] = keep_lo[d]; s->hi[d] = keep_hi[d]; }
+      return;
+    }
+    for(int d = 0; d < s->dim; ++d) { lo[d] = s->lo[d]; hi[d] = s->hi[d]; }
+  });
 }
 double fsph_get_smoothinglength(fsph_system * s) {
   double r = 0;

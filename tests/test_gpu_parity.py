@@ -268,3 +268,20 @@ def test_step_pipelined_equals_upload_step_download():
     B.step_pipelined(plan_in, plan_out)
     rho = B.get(capi.COL_RHO)
     assert np.array_equal(rho, bb[(capi.COL_RHO, 0)].numpy())
+
+
+def test_get_range_is_the_range_of_the_bodies_as_they_are():
+    """body_system::getRange (bodies_system.h:131-138) recomputes mpi_compute_range from the current bodies: right after the
+    bodies were loaded (mpisph/test/bs.cc:29-35), and after positions changed behind the tree's back."""
+    f, par, dim = case("random", n=1500, seed=77, h_jitter=0.2)
+    if not have_ref(dim):
+        pytest.skip("oracle/_ref not shipped")
+    G, R = make_system("cuda", f, par, dim), make_system("ref", f, par, dim)
+    for S in (G, R):
+        lo, hi = S.get_range()
+        assert np.array_equal(lo, (f["pos"] - f["h"][:, None]).min(0)) and np.array_equal(hi, (f["pos"] + f["h"][:, None]).max(0))
+    G.update_iteration(); R.update_iteration()
+    moved = R.get(capi.COL_POS) * 1.5 - 0.1
+    G.set(capi.COL_POS, moved); R.set(capi.COL_POS, moved)
+    (gl, gh), (rl, rh) = G.get_range(), R.get_range()
+    assert np.array_equal(gl, rl) and np.array_equal(gh, rh)
