@@ -1,0 +1,67 @@
+"""The reference's own end-to-end flow, nothing modified: its Sedov generator (app/id_generators/sedov/main.cc) writes
+sedov_nx20.h5part from data/sedov_nx20.par (copied as tests/golden/sedov_nx20.par), its hydro_3d driver
+(app/drivers/hydro/main.cc + main_driver.cc) reads that file and the same .par, runs the 50 iterations the file asks for and
+writes sedov_evolution.h5part every 10 -- what the reference's CMake tests do (app/id_generators/CMakeLists.txt:81,
+app/drivers/CMakeLists.txt).  HDF5 is the stand-in of flecsph_b200/host/h5mini.
+  CPU: generator + driver on the reference's own body_system (oracle/_ref/hydro_3d_ref_h5)
+  GPU: generator + the same driver sources on the facade (flecsph_b200/host/bin/hydro_3d_b200_h5), against the CPU run:
+       conserved sums to 1e-9, every particle field of the last output step to 1e-7 after 50 adaptive steps."""
+import os
+import shutil
+import subprocess
+import numpy as np
+import pytest
+import h5probe
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref")
+B200 = os.path.join(ROOT, "flecsph_b200", "host", "bin")
+PAR = os.path.join(ROOT, "tests", "golden", "sedov_nx20.par")
+
+
+def run_flow(driver, workdir):
+    gen = os.path.join(REF, "sedov_3d_generator")
+    for exe in (gen, driver):
+        if not os.path.exists(exe):
+            pytest.skip("%s not built (needs the reference checkout)" % os.path.basename(exe))
+        if not os.access(exe, os.X_OK):
+            os.chmod(exe, 0o755)
+    os.makedirs(workdir, exist_ok=True)
+    shutil.copy(PAR, os.path.join(workdir, "sedov_nx20.par"))
+    for exe in (gen, driver):
+        r = subprocess.run([exe, "sedov_nx20.par"], cwd=workdir, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    scal = np.loadtxt(os.path.join(workdir, "scalar_reductions.dat"), comments="#", ndmin=2)
+    hf = h5probe.File(os.path.join(workdir, "sedov_evolution.h5part"))
+    return scal, hf
+
+
+def check_run(scal, hf):
+    assert scal[-1, 0] == 50                                   # final_iteration = 50, out_scalar_every = 10
+    assert sorted(hf.root.groups, key=lambda k: int(k[5:])) == ["Step#%d" % k for k in range(6)]   # out_h5data_every = 10
+    assert [int(hf.root.groups["Step#%d" % k].attrs["iteration"][0]) for k in range(6)] == [0, 10, 20, 30, 40, 50]
+    e = scal[:, 4]
+    assert np.abs(e - e[0]).max() <= 1e-6 * abs(e[0])          # total energy over the 50 steps
+    assert np.abs(scal[:, 3] - scal[0, 3]).max() <= 1e-12 * scal[0, 3]   # mass
+
+
+def test_reference_generator_and_driver_flow_on_cpu(tmp_path):
+    scal, hf = run_flow(os.path.join(REF, "hydro_3d_ref_h5"), str(tmp_path / "ref"))
+    check_run(scal, hf)
+    assert len(hf.root.groups["Step#5"].datasets["x"].data) == 5069
+
+
+@pytest.mark.gpu
+def test_reference_flow_on_the_gpu_facade(tmp_path):
+    sg, hg = run_flow(os.path.join(B200, "hydro_3d_b200_h5"), str(tmp_path / "gpu"))
+    sr, hr = run_flow(os.path.join(REF, "hydro_3d_ref_h5"), str(tmp_path / "ref"))
+    check_run(sg, hg)
+    assert sg.shape == sr.shape
+    assert np.allclose(sg[:, :7], sr[:, :7], rtol=1e-9, atol=0)          # iteration, time, dt, mass, energies
+    a, b = hg.root.groups["Step#5"].datasets, hr.root.groups["Step#5"].datasets
+    pa, pb = np.argsort(a["id"].data), np.argsort(b["id"].data)
+    assert np.array_equal(a["id"].data[pa], b["id"].data[pb])
+    for k in ("x", "y", "z", "vx", "vy", "vz", "ax", "ay", "az", "h", "rho", "u", "P", "m", "dt"):
+        x, y = a[k].data[pa], b[k].data[pb]
+        scale = max(np.abs(b[c].data).max() for c in (("ax", "ay", "az") if k[0] == "a" else ("vx", "vy", "vz") if k[0] == "v" and len(k) == 2 else (k,)))
+        assert np.abs(x - y).max() <= 1e-7 * scale, (k, np.abs(x - y).max(), scale)
