@@ -19,8 +19,8 @@ B200 = os.path.join(ROOT, "flecsph_b200", "host", "bin")
 PAR = os.path.join(ROOT, "tests", "golden", "sedov_nx20.par")
 
 
-def run_flow(driver, workdir):
-    gen = os.path.join(REF, "sedov_3d_generator")
+def run_flow(driver, workdir, dim=3):
+    gen = os.path.join(REF, "sedov_%dd_generator" % dim)
     for exe in (gen, driver):
         if not os.path.exists(exe):
             pytest.skip("%s not built (needs the reference checkout)" % os.path.basename(exe))
@@ -45,16 +45,19 @@ def check_run(scal, hf):
     assert np.abs(scal[:, 3] - scal[0, 3]).max() <= 1e-12 * scal[0, 3]   # mass
 
 
-def test_reference_generator_and_driver_flow_on_cpu(tmp_path):
-    scal, hf = run_flow(os.path.join(REF, "hydro_3d_ref_h5"), str(tmp_path / "ref"))
+@pytest.mark.parametrize("dim", [3, 2])
+def test_reference_generator_and_driver_flow_on_cpu(tmp_path, dim):
+    scal, hf = run_flow(os.path.join(REF, "hydro_%dd_ref_h5" % dim), str(tmp_path / "ref"), dim)
     check_run(scal, hf)
-    assert len(hf.root.groups["Step#5"].datasets["x"].data) == 5069
+    assert len(hf.root.groups["Step#5"].datasets["x"].data) == (5069 if dim == 3 else 313)
 
 
 @pytest.mark.gpu
-def test_reference_flow_on_the_gpu_facade(tmp_path):
-    sg, hg = run_flow(os.path.join(B200, "hydro_3d_b200_h5"), str(tmp_path / "gpu"))
-    sr, hr = run_flow(os.path.join(REF, "hydro_3d_ref_h5"), str(tmp_path / "ref"))
+@pytest.mark.parametrize("dim", [3, 2])
+def test_reference_flow_on_the_gpu_facade(tmp_path, dim):
+    """dim = 2: the same .par through sedov_2d_generator and hydro_2d, as app/id_generators/CMakeLists.txt:81 does."""
+    sg, hg = run_flow(os.path.join(B200, "hydro_%dd_b200_h5" % dim), str(tmp_path / "gpu"), dim)
+    sr, hr = run_flow(os.path.join(REF, "hydro_%dd_ref_h5" % dim), str(tmp_path / "ref"), dim)
     check_run(sg, hg)
     assert sg.shape == sr.shape
     assert np.allclose(sg[:, :7], sr[:, :7], rtol=1e-9, atol=0)          # iteration, time, dt, mass, energies
