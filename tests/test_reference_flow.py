@@ -1,5 +1,5 @@
 """The reference's own end-to-end flow, nothing modified: its Sedov generator (app/id_generators/sedov/main.cc) writes
-sedov_nx20.h5part from data/sedov_nx20.par (copied as tests/golden/sedov_nx20.par), its hydro_3d driver
+sedov_nx20.h5part from the settings of data/sedov_nx20.par, its hydro_3d driver
 (app/drivers/hydro/main.cc + main_driver.cc) reads that file and the same .par, runs the 50 iterations the file asks for and
 writes sedov_evolution.h5part every 10 -- what the reference's CMake tests do (app/id_generators/CMakeLists.txt:81,
 app/drivers/CMakeLists.txt).  HDF5 is the stand-in of flecsph_b200/host/h5mini.
@@ -7,7 +7,6 @@ app/drivers/CMakeLists.txt).  HDF5 is the stand-in of flecsph_b200/host/h5mini.
   GPU: generator + the same driver sources on the facade (flecsph_b200/host/bin/hydro_3d_b200_h5), against the CPU run:
        conserved sums to 1e-9, every particle field of the last output step to 1e-7 after 50 adaptive steps."""
 import os
-import shutil
 import subprocess
 import numpy as np
 import pytest
@@ -16,7 +15,12 @@ import h5probe
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref")
 B200 = os.path.join(ROOT, "flecsph_b200", "host", "bin")
-PAR = os.path.join(ROOT, "tests", "golden", "sedov_nx20.par")
+# the settings of the reference's data/sedov_nx20.par, value for value (the file itself stays in the reference checkout)
+SEDOV_NX20 = dict(
+    initial_data_prefix='"sedov_nx20"', lattice_nx=20, poly_gamma=1.4, rho_initial=1.0, pressure_initial=1.0e-7, sphere_radius=1.0,
+    sph_eta=1.2, sedov_blast_energy=2.e-7, sedov_blast_radius=0.06, lattice_type=2, domain_type=1, sph_kernel='"Wendland C4"',
+    initial_dt=1.e-4, final_iteration=50, out_screen_every=1, out_scalar_every=10, out_h5data_every=10,
+    output_h5data_prefix='"sedov_evolution"', sph_variable_h="yes", adaptive_timestep="yes", timestep_cfl_factor=0.01)
 
 
 def run_flow(driver, workdir, dim=3):
@@ -27,7 +31,8 @@ def run_flow(driver, workdir, dim=3):
         if not os.access(exe, os.X_OK):
             os.chmod(exe, 0o755)
     os.makedirs(workdir, exist_ok=True)
-    shutil.copy(PAR, os.path.join(workdir, "sedov_nx20.par"))
+    with open(os.path.join(workdir, "sedov_nx20.par"), "w") as f:
+        f.write("".join("  %s = %s\n" % (k, v if isinstance(v, str) else repr(v)) for k, v in SEDOV_NX20.items()))
     for exe in (gen, driver):
         r = subprocess.run([exe, "sedov_nx20.par"], cwd=workdir, capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
