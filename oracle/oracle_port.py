@@ -15,7 +15,10 @@ golden vectors for this path; its behavioural pins
 (neighbour set == brute force for uniform h, mpisph/test/tree3d.cc:87-108;
 self in neighbours, app/drivers/tree/main_driver.cc:108-113; root mass == sum m,
 tree3d.cc:85; key round trip, tree_topology/test/filling_curves.cc:202-241)
-are asserted in tests/test_oracle.py as well.
+are asserted in tests/test_oracle.py as well.  Restated: the constant-viscosity /
+ideal-or-polytropic hydro path of the drivers with external forces and potentials
+(eforce.h; tests/test_eforce.py); not restated (oracle/_ref only): Cullen-Dehnen
+viscosity, the relaxation phase, the piecewise-polytropic and white-dwarf EOS, FMM.
 
 Each function cites the reference file:line it follows (paths relative to
 /root/reference).  Bit-exact parts (range, keys, order, tree, node summaries,
@@ -58,15 +61,171 @@ def _clz64(x):
     return n
 
 
+class ExternalForce:
+    """external_force::select / acceleration / potential (include/physics/eforce.h:330-433) with the terms of :46-330 and the
+    constant / parabolic / mesa profiles of include/physics/density_profiles.h:69-221,355-396, vectorised over the bodies.
+    The terms are added in the order of the keyword, starting from zero."""
+
+    def __init__(self, par, dim):
+        self.par, self.dim, self.terms = par, dim, []
+        kw = par.external_force_type.decode().strip()
+        if kw.lower() in ("", "none", "zero"):
+            return
+        for it in kw.split(","):
+            low = it.lower()
+            if low in ("spherical wall", "airfoil", "spherical density support", "gravity", "orbit", "poison"):
+                self.terms.append(low)
+            elif low.startswith("walls:"):
+                self.terms += ["wall" + str("xyz".index(ch)) for ch in low[6:9]]
+            else:
+                raise ValueError("bad external_force_type: " + it)
+        if "spherical density support" in self.terms:
+            prof = par.density_profile.decode().strip().lower() or "constant"
+            if prof not in ("constant", "parabolic", "mesa"):
+                raise NotImplementedError("density_profile " + prof)
+            self.prof = prof
+            if prof == "mesa":
+                q = par.mesa_rim_width
+                self.mesa_rho0 = {1: .5 / (1. - q / 3.), 2: 1. / (np.pi * self._mesa_helper(1.)), 3: 1. / (4. * np.pi * self._mesa_helper(1.))}[dim]
+            self.K0 = par.pressure_initial / par.rho_initial ** par.poly_gamma
+            self.rho0 = float(self._rho(np.zeros(1))[0])
+
+    def _mesa_helper(self, r):
+        dr = self.par.mesa_rim_width
+        r0 = 1. - dr
+        if self.dim == 2:
+            return r ** 2 * (1. - (.5 * r ** 2 + r0 ** 2) / dr ** 2) + (.5 * r0 ** 3 + 4. * r ** 3) * r0 / (3. * dr ** 2)
+        return r0 ** 3 / 3. + (r ** 3 - r0 ** 3) / 3. * (1. - r0 ** 2 / dr ** 2) + r0 * (r ** 2 - r0 ** 2) * (r ** 2 + r0 ** 2) / (2. * dr ** 2) \
+            - (r ** 5 - r0 ** 5) / (5 * dr ** 2)
+
+    def _rho(self, r):
+        D = self.dim
+        if self.prof == "parabolic":
+            return {1: 0.75, 2: 2. / np.pi, 3: 15. / (8. * np.pi)}[D] * (1. - r * r)
+        if self.prof == "mesa":
+            q = self.par.mesa_rim_width
+            return np.where(r < 1. - q, self.mesa_rho0, np.where(r < .9999, self.mesa_rho0 * (1. - (r - (1. - q)) ** 2 / q ** 2), 0.0))
+        return np.full(len(r), {1: 0.5, 2: 1.0 / np.pi, 3: 0.75 / np.pi}[D])
+
+    def _drhodr(self, r):
+        D = self.dim
+        if self.prof == "parabolic":
+            return {1: -1.5, 2: -4. / np.pi, 3: -15. / (4. * np.pi)}[D] * r
+        if self.prof == "mesa":
+            q = self.par.mesa_rim_width
+            return np.where((r > 1. - q) & (r < .9999), -2. * self.mesa_rho0 * (r - (1. - q)) / q ** 2, 0.0)
+        return np.zeros(len(r))
+
+    def _box(self):
+        return (.5 * self.par.box_length, .5 * self.par.box_width, .5 * self.par.box_height)
+
+    def _airfoil(self, x):
+        p = self.par
+        al = p.airfoil_attack_angle * np.pi / 180.0
+        x1, y1 = x[:, 0] - p.airfoil_anchor_x, x[:, 1] - p.airfoil_anchor_y
+        xx, yy = x1 * np.cos(al) + y1 * np.sin(al), -x1 * np.sin(al) + y1 * np.cos(al)
+        inside = (np.abs(yy) < 5.0 * p.airfoil_thickness) & (xx > -p.airfoil_size * 0.02) & (xx < p.airfoil_size * 1.02)
+        with np.errstate(invalid="ignore"):
+            upper = p.airfoil_thickness * xx * np.sqrt(p.airfoil_size ** 2 - xx * xx)
+        camber = p.airfoil_camber * np.sin(np.pi * xx / 2.)
+        phi = upper ** 2 - (yy - camber) ** 2 + 0.002
+        return al, xx, yy, camber, phi, inside & (phi > 0.0)
+
+    def acceleration(self, x):
+        p, D, n = self.par, self.dim, len(x)
+        a = np.zeros((n, D))
+        pn, pa = p.extforce_wall_powerindex, p.extforce_wall_steepness
+        r = np.sqrt((x * x).sum(1))
+
+        def sphere_wall():
+            t = np.zeros((n, D))
+            out = r > p.sphere_radius
+            with np.errstate(invalid="ignore", divide="ignore"):
+                ar = pn * pa * np.power(np.where(out, r - p.sphere_radius, 0.0), pn - 1)
+                t[out] = (-x / r[:, None] * ar[:, None])[out]
+            return t
+        for term in self.terms:
+            t = np.zeros((n, D))
+            if term == "spherical wall":
+                t = sphere_wall()
+            elif term == "airfoil":
+                al, xx, yy, camber, phi, on = self._airfoil(x)
+                with np.errstate(invalid="ignore"):
+                    pw = pn * pa * np.power(np.where(on, phi, 1.0), pn - 1)
+                a0 = pw * (2. * (yy - camber) * (-p.airfoil_camber * np.pi / 2. * np.cos(np.pi / 2. * xx))
+                           - p.airfoil_thickness ** 2 * 2 * xx * (p.airfoil_size ** 2 - 2 * xx * xx))
+                a1 = pw * 2. * (yy - camber)
+                t[:, 0] = np.where(on, a0 * np.cos(al) - a1 * np.sin(al), 0.0)
+                t[:, 1] = np.where(on, a0 * np.sin(al) + a1 * np.cos(al), 0.0)
+            elif term == "spherical density support":
+                q = r / p.sphere_radius
+                rho = p.rho_initial / self.rho0 * self._rho(q)
+                drho = p.rho_initial / (self.rho0 * p.sphere_radius) * self._drhodr(q)
+                with np.errstate(invalid="ignore", divide="ignore"):
+                    a_r = np.where(rho > 0, self.K0 * p.poly_gamma * np.power(np.where(rho > 0, rho, 1.0), p.poly_gamma - 2) * drho, 0.0)
+                    t = np.where((q > 1e-12)[:, None], a_r[:, None] * x / r[:, None], 0.0)
+                t = t + sphere_wall()
+            elif term == "gravity":
+                t[:, 1 if D > 1 else 0] = -p.gravity_acceleration_constant
+            elif term == "orbit":
+                m_t = p.mass_neutron_star + p.mass_white_dwarf
+                d2 = (x[:, 0] - p.orbital_separation) ** 2 + x[:, 1] ** 2 + x[:, 2] ** 2
+                t1 = -p.gravitational_constant * p.mass_neutron_star / np.sqrt(d2 ** 3)
+                t2 = p.gravitational_constant * m_t / p.orbital_separation ** 3
+                t[:, 0] = t1 * (x[:, 0] - p.orbital_separation) + t2 * (x[:, 0] - p.orbital_separation * p.mass_neutron_star / m_t)
+                t[:, 1] = t1 * x[:, 1] + t2 * x[:, 1]
+                t[:, 2] = t1 * x[:, 2]
+            elif term.startswith("wall"):
+                i = int(term[4])
+                b, xi = self._box()[i], x[:, i]
+                t[:, i] = (np.where(xi < -b, np.power(np.where(xi < -b, -xi - b, 0.0), pn - 1), 0.0)
+                           - np.where(xi > b, np.power(np.where(xi > b, xi - b, 0.0), pn - 1), 0.0)) * pn * pa
+            else:
+                continue   # poison: potential only
+            a = a + t
+        return a
+
+    def potential(self, x):
+        p, D, n = self.par, self.dim, len(x)
+        phi = np.zeros(n)
+        pn, pa = p.extforce_wall_powerindex, p.extforce_wall_steepness
+        r = np.sqrt((x * x).sum(1))
+        sphere = np.where(r > p.sphere_radius, pa * np.power(np.where(r > p.sphere_radius, r - p.sphere_radius, 0.0), pn), 0.0)
+        for term in self.terms:
+            if term == "spherical wall":
+                t = sphere
+            elif term == "airfoil":
+                _, _, _, _, aux, on = self._airfoil(x)
+                t = np.where(on, pa * np.power(np.where(on, aux, 1.0), pn), 0.0)
+            elif term == "spherical density support":
+                rho = p.rho_initial / self.rho0 * self._rho(r / p.sphere_radius)
+                t = np.where(rho > 0, -self.K0 * p.poly_gamma * np.power(np.where(rho > 0, rho, 1.0), p.poly_gamma - 1.) / (p.poly_gamma - 1.), 0.0) + sphere
+            elif term == "gravity":
+                t = x[:, 1 if D > 1 else 0] * p.gravity_acceleration_constant
+            elif term == "orbit":
+                m_t = p.mass_neutron_star + p.mass_white_dwarf
+                t1 = -p.gravitational_constant * p.mass_neutron_star / np.sqrt((x[:, 0] - p.orbital_separation) ** 2 + x[:, 1] ** 2 + x[:, 2] ** 2)
+                t2 = -0.5 * p.gravitational_constant * m_t / p.orbital_separation ** 3
+                t = t1 + t2 * ((x[:, 0] - p.orbital_separation * p.mass_neutron_star / m_t) ** 2 + x[:, 1] ** 2)
+            elif term.startswith("wall"):
+                i = int(term[4])
+                b, xi = self._box()[i], x[:, i]
+                t = (np.where(xi < -b, np.power(np.where(xi < -b, -xi - b, 0.0), pn), 0.0)
+                     + np.where(xi > b, np.power(np.where(xi > b, xi - b, 0.0), pn), 0.0)) * pa
+            else:
+                t = np.full(n, p.zero_potential_poison_value)
+            phi = phi + t
+        return phi
+
+
 class PortSystem:
     backend = "oracle-port"
 
     def __init__(self, params, backend=None, device=0):
         self.par = params
-        # the port restates the constant-viscosity / ideal-or-polytropic path without external forces; the other physics is
+        # the port restates the constant-viscosity / ideal-or-polytropic path (with external forces); the other physics is
         # checked against oracle/_ref only -- refuse rather than silently ignore a selector
-        if params.external_force_type.decode().strip().lower() not in ("", "none", "zero"):
-            raise NotImplementedError("oracle_port: external_force_type is not restated here (use oracle/_ref)")
+        self.ef = ExternalForce(params, params.dim)
         if params.sph_viscosity != 0 or params.relaxation_steps > 0 or params.eos_type not in (0, 1):
             raise NotImplementedError("oracle_port: Cullen-Dehnen viscosity / relaxation / ppt and wd EOS are not restated here (use oracle/_ref)")
         self.dim = D = params.dim
@@ -471,9 +630,9 @@ class PortSystem:
         c["cs"][idx] = np.sqrt(g * (g - 1.) * c["u"][idx])
 
     def _recover_u(self):
-        """physics::recover_internal_energy, default_physics.h:126-145 (no external potential)."""
+        """physics::recover_internal_energy, default_physics.h:126-145."""
         c = self.c
-        eint = c["e"] - .5 * (c["vel"] * c["vel"]).sum(1) - 0.0
+        eint = c["e"] - .5 * (c["vel"] * c["vel"]).sum(1) - self.ef.potential(c["pos"])
         if not (eint > 0).all():
             raise RuntimeError("internal energy non-positive")
         c["u"] = eint
@@ -514,6 +673,7 @@ class PortSystem:
             # compute_acceleration, default_physics.h:348-408
             coef = -mt * (Pa[a] + Pa[b] + Pi) * F
             acc = np.stack([self._sum(a, coef * rab[:, d]) for d in range(self.dim)], 1)
+            acc = acc + self.ef.acceleration(c["pos"])     # default_physics.h:404
             c["acc"] = acc
             c["gacc"] = np.zeros_like(acc)
             c["gpot"] = np.zeros(self.n)
@@ -538,7 +698,7 @@ class PortSystem:
         if op == 0:    # eos::init -> compute_adiabatic, eos/eos.h:68-83,157-159
             c["adiabatic"] = c["P"] / np.power(c["rho"], p.poly_gamma)
         elif op == 1:  # set_total_energy, default_physics.h:327-335
-            c["e"] = .5 * (c["vel"] * c["vel"]).sum(1) + c["u"] + 0.0
+            c["e"] = .5 * (c["vel"] * c["vel"]).sum(1) + c["u"] + self.ef.potential(c["pos"])
         elif op == 2:  # save_velocityhalf, integration.h:52
             c["velhalf"] = c["vel"].copy()
         elif op == 3:  # leapfrog_kick_v, integration.h:65
@@ -573,9 +733,11 @@ class PortSystem:
                 if not (c["u"] > 0).all():
                     raise RuntimeError("internal energy non-positive")
                 vg = (c["vel"] * c["gacc"]).sum(1)
+                epot = self.ef.potential(c["pos"])
                 done = np.zeros(self.n, bool)
                 for _ in range(20):
-                    done |= (0.0 + (-dtmin * vg)) < c["u"] * 0.5
+                    depot = self.ef.potential(c["pos"] + dtmin[:, None] * c["vel"]) - epot if self.ef.terms else 0.0
+                    done |= (depot + (-dtmin * vg)) < c["u"] * 0.5
                     dtmin = np.where(done, dtmin, dtmin * 0.25)
                 if not done.all():
                     raise RuntimeError("eint-based dt estimator did not converge")
@@ -628,7 +790,7 @@ class PortSystem:
             if p.thermokinetic_formulation:
                 out[0] = (c["mass"] * c["e"])[m].sum()
             else:
-                out[0] = (c["mass"] * (c["u"] + .5 * (c["vel"] * c["vel"]).sum(1)))[m].sum()
+                out[0] = (c["mass"] * (.5 * (c["vel"] * c["vel"]).sum(1) + c["u"] + self.ef.potential(c["pos"])))[m].sum()
             if p.enable_fmm:
                 out[0] += .5 * (c["mass"] * c["gpot"])[m].sum()
         elif op == 5:  # analysis::compute_total_momentum, analysis.h:56-67

@@ -75,3 +75,25 @@ def test_keyword_parser(shim):
         assert rc == 1, kw
     assert host_eval(shim, dict(external_force_type="walls:y"), 1, points(1, 4, seed=1))[0] == 1   # axis beyond the dimension
     assert host_eval(shim, dict(external_force_type="spherical density support", density_profile="from file"), 3, x)[0] == 1
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("thermokinetic", [1, 0])
+def test_numpy_port_with_external_forces_matches_reference(name, thermokinetic):
+    """oracle/oracle_port.py restates eforce.h as well: three driver iterations against the reference headers."""
+    from common import case, assert_fields_close
+    dim, keyword, extra = CASES[name]
+    if not have_ref(dim):
+        pytest.skip("oracle/_ref not built")
+    f, par, _ = case("random", n={1: 200, 2: 500, 3: 700}[dim], dim=dim, seed=90 + dim, h_jitter=0.1)
+    f = dict(f)
+    f["pos"] = (f["pos"] - 0.5) * 1.3
+    f["h"] = f["h"] * 1.3
+    par = dict(par, **EF_PARAMS, external_force_type=keyword, thermokinetic_formulation=thermokinetic, **extra)
+    P, R = make_system("port", f, par, dim), make_system("ref", f, par, dim)
+    names = ["pos", "vel", "rho", "P", "u", "cs", "acc", "h", "vsig", "dt"] + (["dedt", "e"] if thermokinetic else ["dudt"])
+    for it in range(3):
+        P.step(initial=(it == 0)); R.step(initial=(it == 0))
+        assert_fields_close(P, R, names, 1e-10 if it < 2 else 1e-9)
+        ep, er = P.get_all(capi.GET_TOTAL_ENERGY, 1)[0], R.get_all(capi.GET_TOTAL_ENERGY, 1)[0]
+        assert abs(ep - er) <= 1e-10 * abs(er)
