@@ -17,8 +17,8 @@ self in neighbours, app/drivers/tree/main_driver.cc:108-113; root mass == sum m,
 tree3d.cc:85; key round trip, tree_topology/test/filling_curves.cc:202-241)
 are asserted in tests/test_oracle.py as well.  Restated: the constant-viscosity /
 ideal-or-polytropic hydro path of the drivers with external forces and potentials
-(eforce.h; tests/test_eforce.py); not restated (oracle/_ref only): Cullen-Dehnen
-viscosity, the relaxation phase, the piecewise-polytropic and white-dwarf EOS, FMM.
+(eforce.h; tests/test_eforce.py) and all four equations of state; not restated
+(oracle/_ref only): Cullen-Dehnen viscosity, the relaxation phase, FMM gravity.
 
 Each function cites the reference file:line it follows (paths relative to
 /root/reference).  Bit-exact parts (range, keys, order, tree, node summaries,
@@ -33,7 +33,7 @@ SUB_ENTITIES = 128                       # tree_topology.h:2121
 TOL = np.finfo(np.float64).eps * 10.0    # tree_geometry.h:57
 
 VEC = ("pos", "vel", "velhalf", "acc", "gacc")
-SCAL = ("mass", "h", "rho", "P", "u", "e", "cs", "dudt", "dedt", "dt", "alpha", "vsig", "gpot", "adiabatic")
+SCAL = ("mass", "h", "rho", "P", "u", "e", "cs", "dudt", "dedt", "dt", "alpha", "vsig", "gpot", "adiabatic", "ye")
 
 # sigma tables, kernels.h:40-47
 SIGMA = {
@@ -226,8 +226,8 @@ class PortSystem:
         # the port restates the constant-viscosity / ideal-or-polytropic path (with external forces); the other physics is
         # checked against oracle/_ref only -- refuse rather than silently ignore a selector
         self.ef = ExternalForce(params, params.dim)
-        if params.sph_viscosity != 0 or params.relaxation_steps > 0 or params.eos_type not in (0, 1):
-            raise NotImplementedError("oracle_port: Cullen-Dehnen viscosity / relaxation / ppt and wd EOS are not restated here (use oracle/_ref)")
+        if params.sph_viscosity != 0 or params.relaxation_steps > 0 or params.enable_fmm:
+            raise NotImplementedError("oracle_port: Cullen-Dehnen viscosity / relaxation / FMM gravity are not restated here (use oracle/_ref)")
         self.dim = D = params.dim
         self.B = 63 // D  # filling_curve.h:45-47
         self.n = 0
@@ -624,10 +624,33 @@ class PortSystem:
         return (-p.sph_viscosity_alpha * c_ab + p.sph_viscosity_beta * mu) * mu / rho_ab
 
     def _eos(self, idx=slice(None)):
-        """eos_t<eos_ideal>::compute_pressure / compute_soundspeed, eos/eos.h:166-183."""
-        c, g = self.c, self.par.poly_gamma
-        c["P"][idx] = (g - 1.) * c["rho"][idx] * c["u"][idx]
-        c["cs"][idx] = np.sqrt(g * (g - 1.) * c["u"][idx])
+        """eos::compute_pressure + compute_soundspeed (eos/eos.h): ideal gas :166-183 from u, polytropic :100-118 from the
+        body's adiabatic invariant K = P / rho^gamma, piecewise polytrope :365-394 (K = K1 of the first segment), cold
+        white dwarf :254-275 from the electron fraction; eos_type none :425-432 leaves P and cs as they are."""
+        c, p = self.c, self.par
+        g = p.poly_gamma
+        rho = c["rho"][idx]
+        if p.eos_type == 0:
+            c["P"][idx] = (g - 1.) * rho * c["u"][idx]
+            c["cs"][idx] = np.sqrt(g * (g - 1.) * c["u"][idx])
+        elif p.eos_type == 1:
+            K = c["adiabatic"][idx]
+            c["P"][idx] = K * np.power(rho, g)
+            c["cs"][idx] = np.sqrt(K * g * np.power(rho, g - 1.))
+        elif p.eos_type == 3:
+            K, g2, thr = c["adiabatic"][idx], p.poly_gamma2, p.ppt_density_thr
+            K2 = K * thr ** (g - g2)
+            lo = rho < thr
+            c["P"][idx] = np.where(lo, K * np.power(rho, g), K2 * np.power(rho, g2))
+            c["cs"][idx] = np.where(lo, np.sqrt(K * g * np.power(rho, g - 1.)), np.sqrt(K2 * g2 * np.power(rho, g2 - 1.)))
+        elif p.eos_type == 2:
+            A_wd, B_wd, C_LIGHT = 6.00233181e22, 9.73932099e5, 2.99792458e10
+            x = np.cbrt(rho * c["ye"][idx] / B_wd)
+            x2 = x * x
+            c["P"][idx] = A_wd * (x * (2. * x2 - 3.) * np.sqrt(x2 + 1.) + 3. * np.arcsinh(x))
+            numer = (1. + x2) * (6. * x2 - 3.) + 3. + x2 * (2. * x2 - 3.)
+            denom = (1. + x2) * (6. * x2 + 1.) - 1. + x2 * (2. * x2 + 1.)
+            c["cs"][idx] = np.sqrt(numer / (3. * denom)) * C_LIGHT
 
     def _recover_u(self):
         """physics::recover_internal_energy, default_physics.h:126-145."""
@@ -695,8 +718,18 @@ class PortSystem:
     # ---- apply_all / get_all ---------------------------------------------------
     def apply_all(self, op):
         c, p, dt = self.c, self.par, self.dt_
-        if op == 0:    # eos::init -> compute_adiabatic, eos/eos.h:68-83,157-159
-            c["adiabatic"] = c["P"] / np.power(c["rho"], p.poly_gamma)
+        if op == 0:    # eos::init: adiabatic invariant (eos/eos.h:68-83,157-159; ppt :337-351), internal energy of the white dwarf :292-302
+            if p.eos_type in (0, 1):
+                c["adiabatic"] = c["P"] / np.power(c["rho"], p.poly_gamma)
+            elif p.eos_type == 3:
+                K2 = c["P"] / np.power(c["rho"], p.poly_gamma2)
+                c["adiabatic"] = np.where(c["rho"] < p.ppt_density_thr, c["P"] / np.power(c["rho"], p.poly_gamma),
+                                          K2 * p.ppt_density_thr ** (p.poly_gamma2 - p.poly_gamma))
+            elif p.eos_type == 2:
+                A_wd, B_wd = 6.00233181e22, 9.73932099e5
+                x = np.cbrt(c["rho"] * c["ye"] / B_wd)
+                x2, x3 = x * x, x * x * x
+                c["u"] = A_wd / c["rho"] * (8. * x3 * (np.sqrt(x2 + 1.) - 1.) - (x * (2. * x2 - 3.) * np.sqrt(x2 + 1.) + 3. * np.arcsinh(x)))
         elif op == 1:  # set_total_energy, default_physics.h:327-335
             c["e"] = .5 * (c["vel"] * c["vel"]).sum(1) + c["u"] + self.ef.potential(c["pos"])
         elif op == 2:  # save_velocityhalf, integration.h:52

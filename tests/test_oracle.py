@@ -71,3 +71,25 @@ def test_key_round_trip():
                 c[d] |= ((k >> (b * 3 + d)) & 1) << b
         x = lo + (np.array(c) + 0.5) / (1 << B) * (hi - lo)
         assert np.abs(x - f["pos"][i]).max() < 1e-4
+
+
+@pytest.mark.parametrize("eos", ["polytropic", "ppt", "wd"])
+def test_port_equations_of_state_match_reference(eos):
+    """eos_type polytropic / piecewise polytrope / cold white dwarf (eos/eos.h:57-419): eos::init and three driver iterations."""
+    from flecsph_b200 import capi
+    f, par, dim = case("random", n=600, seed=61, h_jitter=0.15)
+    if not have_ref(dim):
+        pytest.skip("oracle/_ref not built")
+    f = dict(f)
+    if eos == "polytropic":
+        par = dict(par, eos_type=capi.EOS_POLYTROPIC, poly_gamma=1.7, thermokinetic_formulation=0)
+    elif eos == "ppt":
+        par = dict(par, eos_type=capi.EOS_PPT, poly_gamma=1.6, poly_gamma2=2.4, ppt_density_thr=1.0, thermokinetic_formulation=0)
+    else:
+        f["mass"], f["rho"], f["ye"] = f["mass"] * 3e6, f["rho"] * 3e6, np.full(len(f["mass"]), 0.5)
+        par = dict(par, eos_type=capi.EOS_WD, thermokinetic_formulation=0, adaptive_timestep=0, initial_dt=1e-12)
+    P, R = make_system("port", f, par, dim), make_system("ref", f, par, dim)
+    names = ["pos", "vel", "rho", "P", "u", "cs", "acc", "h", "vsig", "dudt"] + ([] if eos == "wd" else ["adiabatic", "dt"])
+    for it in range(3):
+        P.step(initial=(it == 0)); R.step(initial=(it == 0))
+        assert_fields_close(P, R, names, 1e-10 if it < 2 else 1e-9)
