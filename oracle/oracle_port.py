@@ -17,8 +17,8 @@ self in neighbours, app/drivers/tree/main_driver.cc:108-113; root mass == sum m,
 tree3d.cc:85; key round trip, tree_topology/test/filling_curves.cc:202-241)
 are asserted in tests/test_oracle.py as well.  Restated: the constant-viscosity /
 ideal-or-polytropic hydro path of the drivers with external forces and potentials
-(eforce.h; tests/test_eforce.py) and all four equations of state; not restated
-(oracle/_ref only): Cullen-Dehnen viscosity, the relaxation phase, FMM gravity.
+(eforce.h; tests/test_eforce.py), all four equations of state and the relaxation phase
+(drag, short-range repulsion); not restated (oracle/_ref only): Cullen-Dehnen viscosity, FMM gravity.
 
 Each function cites the reference file:line it follows (paths relative to
 /root/reference).  Bit-exact parts (range, keys, order, tree, node summaries,
@@ -226,8 +226,8 @@ class PortSystem:
         # the port restates the constant-viscosity / ideal-or-polytropic path (with external forces); the other physics is
         # checked against oracle/_ref only -- refuse rather than silently ignore a selector
         self.ef = ExternalForce(params, params.dim)
-        if params.sph_viscosity != 0 or params.relaxation_steps > 0 or params.enable_fmm:
-            raise NotImplementedError("oracle_port: Cullen-Dehnen viscosity / relaxation / FMM gravity are not restated here (use oracle/_ref)")
+        if params.sph_viscosity != 0 or params.enable_fmm:
+            raise NotImplementedError("oracle_port: Cullen-Dehnen viscosity / FMM gravity are not restated here (use oracle/_ref)")
         self.dim = D = params.dim
         self.B = 63 // D  # filling_curve.h:45-47
         self.n = 0
@@ -688,6 +688,15 @@ class PortSystem:
             np.maximum.at(vs, a, val)
             c["vsig"] = vs
             return
+        if op == 6:
+            # add_short_range_repulsion, default_physics.h:718-754: neighbours other than the body itself within
+            # relaxation_repulsion_radius * h_ab
+            take = (c["id"][a] != c["id"][b]) & ~(r > hab * p.relaxation_repulsion_radius)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                w = np.where(take, c["mass"][b] / (r * r * r), 0.0)
+            acc_r = np.stack([self._sum(a, np.where(take, w * rab[:, d], 0.0)) for d in range(self.dim)], 1)
+            c["acc"] = c["acc"] + acc_r * p.relaxation_repulsion_gamma
+            return
         F = self.gradW_over_r(r, hab)
         mt = c["mass"][b] * (rab != 0).any(1)
         Pi = self._visc(a, b, rab, hab)
@@ -775,6 +784,15 @@ class PortSystem:
                 if not done.all():
                     raise RuntimeError("eint-based dt estimator did not converge")
             c["dt"] = dtmin
+        elif op in (13, 14, 15):  # add_drag_acceleration :702-709, add_drag_dedt :573-581, add_drag_dudt :587-595
+            v2 = (c["vel"] * c["vel"]).sum(1)
+            drag = 0.0 - (p.relaxation_beta + p.relaxation_gamma * v2)[:, None] * c["vel"]     # external_force::acceleration_drag, eforce.h:441-451
+            if op == 13:
+                c["acc"] = c["acc"] + drag
+            elif op == 14:
+                c["dedt"] = c["dedt"] + (c["vel"] * drag).sum(1)
+            else:
+                c["dudt"] = c["dudt"] + (c["vel"] * drag).sum(1)
         elif op == 10:  # check_nans, default_physics.h:918-958
             for k in VEC + SCAL:
                 if np.isnan(c[k]).any():
@@ -842,12 +860,25 @@ class PortSystem:
         p = self.par
         S, A, G = self.apply_in_smoothinglength, self.apply_all, self.get_all
 
+        relaxing = self.iteration < p.relaxation_steps     # hydro/main_driver.cc:128-133,152,165,205-206,221,235
+
+        def acceleration():
+            S(1)
+            if relaxing:
+                A(13); S(6)
+
         def energy():
             for m in range(1, p.pressure_updates_number + 1):
                 if p.thermokinetic_formulation:
-                    S(3); A(8)
+                    S(3)
+                    if relaxing:
+                        A(14)
+                    A(8)
                 else:
-                    S(2); A(7)
+                    S(2)
+                    if relaxing:
+                        A(15)
+                    A(7)
                 if m < p.pressure_updates_number:
                     self.reset_ghosts()
         if initial:
@@ -855,7 +886,7 @@ class PortSystem:
             A(0)
             if p.thermokinetic_formulation:
                 A(1)
-            S(0); A(2); self.reset_ghosts(); S(1)
+            S(0); A(2); self.reset_ghosts(); acceleration()
             if p.adaptive_timestep:
                 A(9); G(0)
             if p.evolve_internal_energy:
@@ -865,7 +896,7 @@ class PortSystem:
                 A(5 if p.thermokinetic_formulation else 4)
             A(3); A(2); A(6)
             self.update_iteration()
-            S(0); self.reset_ghosts(); S(1)
+            S(0); self.reset_ghosts(); acceleration()
             A(3); self.reset_ghosts()
             if p.evolve_internal_energy:
                 energy()

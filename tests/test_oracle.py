@@ -93,3 +93,19 @@ def test_port_equations_of_state_match_reference(eos):
     for it in range(3):
         P.step(initial=(it == 0)); R.step(initial=(it == 0))
         assert_fields_close(P, R, names, 1e-10 if it < 2 else 1e-9)
+
+
+@pytest.mark.parametrize("dim,thermokinetic", [(3, 1), (2, 0), (1, 1)])
+def test_port_relaxation_phase_matches_reference(dim, thermokinetic):
+    """relaxation_steps = 2 (hydro/main_driver.cc:128-133,152,165): drag on the acceleration and the energy rate, short-range
+    repulsion, du/dt held at zero; two iterations inside the phase and two after it."""
+    f, par, _ = case("random", n={1: 150, 2: 500, 3: 700}[dim], dim=dim, seed=71, h_jitter=0.1)
+    if not have_ref(dim):
+        pytest.skip("oracle/_ref not built")
+    par = dict(par, relaxation_steps=2, relaxation_beta=0.3, relaxation_gamma=0.7, relaxation_repulsion_radius=0.6,
+               relaxation_repulsion_gamma=1e-4, thermokinetic_formulation=thermokinetic)
+    P, R = make_system("port", f, par, dim), make_system("ref", f, par, dim)
+    names = ["pos", "vel", "rho", "P", "u", "cs", "acc", "h", "vsig", "dt"] + (["dedt", "e"] if thermokinetic else ["dudt"])
+    for it in range(4):
+        P.step(initial=(it == 0)); R.step(initial=(it == 0))
+        assert_fields_close(P, R, names, 1e-10 if it < 2 else 1e-9)
