@@ -17,8 +17,8 @@ self in neighbours, app/drivers/tree/main_driver.cc:108-113; root mass == sum m,
 tree3d.cc:85; key round trip, tree_topology/test/filling_curves.cc:202-241)
 are asserted in tests/test_oracle.py as well.  Restated: the constant-viscosity /
 ideal-or-polytropic hydro path of the drivers with external forces and potentials
-(eforce.h; tests/test_eforce.py), all four equations of state and the relaxation phase
-(drag, short-range repulsion); not restated (oracle/_ref only): Cullen-Dehnen viscosity, FMM gravity.
+(eforce.h; tests/test_eforce.py), all four equations of state, the relaxation phase
+(drag, short-range repulsion) and the Cullen-Dehnen viscosity; not restated (oracle/_ref only): FMM gravity.
 
 Each function cites the reference file:line it follows (paths relative to
 /root/reference).  Bit-exact parts (range, keys, order, tree, node summaries,
@@ -33,7 +33,8 @@ SUB_ENTITIES = 128                       # tree_topology.h:2121
 TOL = np.finfo(np.float64).eps * 10.0    # tree_geometry.h:57
 
 VEC = ("pos", "vel", "velhalf", "acc", "gacc")
-SCAL = ("mass", "h", "rho", "P", "u", "e", "cs", "dudt", "dedt", "dt", "alpha", "vsig", "gpot", "adiabatic", "ye")
+SCAL = ("mass", "h", "rho", "P", "u", "e", "cs", "dudt", "dedt", "dt", "alpha", "vsig", "gpot", "adiabatic", "ye",
+        "divv", "ddivvdt", "trigger", "xi", "tracess", "gradv")
 
 # sigma tables, kernels.h:40-47
 SIGMA = {
@@ -226,8 +227,8 @@ class PortSystem:
         # the port restates the constant-viscosity / ideal-or-polytropic path (with external forces); the other physics is
         # checked against oracle/_ref only -- refuse rather than silently ignore a selector
         self.ef = ExternalForce(params, params.dim)
-        if params.sph_viscosity != 0 or params.enable_fmm:
-            raise NotImplementedError("oracle_port: Cullen-Dehnen viscosity / FMM gravity are not restated here (use oracle/_ref)")
+        if params.enable_fmm:
+            raise NotImplementedError("oracle_port: FMM gravity is not restated here (use oracle/_ref)")
         self.dim = D = params.dim
         self.B = 63 // D  # filling_curve.h:45-47
         self.n = 0
@@ -613,7 +614,7 @@ class PortSystem:
         return np.bincount(a, weights=w, minlength=self.n)
 
     def _visc(self, a, b, rab, hab):
-        """viscosity::mu, viscosity.h:81-93 and viscosity_function<visc_constant>, :128-137."""
+        """viscosity::mu, viscosity.h:81-93, viscosity_function<visc_constant> :128-137 and <visc_cullen> :150-157."""
         c, p = self.c, self.par
         v12 = c["velhalf"][a] - c["velhalf"][b]
         dot = (v12 * rab).sum(1)
@@ -621,6 +622,9 @@ class PortSystem:
         mu = hab * dot / (d2 + p.sph_viscosity_epsilon * hab * hab + TINY) * (dot < 0.0)
         rho_ab = .5 * (c["rho"][a] + c["rho"][b])
         c_ab = .5 * (c["cs"][a] + c["cs"][b])
+        if p.sph_viscosity == 1:
+            alpha_ab = .5 * (c["alpha"][a] + c["alpha"][b])
+            return -alpha_ab * (c_ab - 2.0 * mu) * mu / rho_ab
         return (-p.sph_viscosity_alpha * c_ab + p.sph_viscosity_beta * mu) * mu / rho_ab
 
     def _eos(self, idx=slice(None)):
@@ -687,6 +691,45 @@ class PortSystem:
             vs = np.zeros(self.n)
             np.maximum.at(vs, a, val)
             c["vsig"] = vs
+            if p.sph_viscosity == 1:
+                # compute_divv, default_physics.h:273-300: div v = (v_a . sum_b m_b grad W_ab) / rho_a and its rate of change
+                F = self.gradW_over_r(r, hab)
+                dv = self._sum(a, c["mass"][b] * (c["vel"][a] * rab).sum(1) * F) / c["rho"]
+                c["ddivvdt"] = (dv - c["divv"]) / self.dt_
+                c["divv"] = dv
+            return
+        if op == 5:
+            # viscosity::compute_alpha, viscosity.h:310-363 (A_trigger :283-308, compute_xi :193-272)
+            vab = c["vel"][a] - c["vel"][b]
+            cab = np.maximum(c["cs"][a], c["cs"][b])
+            with np.errstate(invalid="ignore", divide="ignore"):
+                val = cab - np.minimum((vab * (rab / r[:, None])).sum(1), 0.0)
+            vs = np.zeros(self.n)
+            np.maximum.at(vs, a, np.where(np.isnan(val), 0.0, val))    # the body itself (0/0) never wins the max
+            F = self.gradW_over_r(r, hab)
+            R = self._sum(a, np.sign(c["divv"][b]) * c["mass"][b] * self.W(r, hab)) / c["rho"]
+            D = self.dim
+            g = np.zeros((self.n, D, D))
+            for i in range(D):
+                for j in range(D):
+                    g[:, i, j] = self._sum(a, c["mass"][b] * (-vab[:, i]) * rab[:, j] * F) / c["rho"]
+            c["gradv"] = g[:, 0, 0].copy()
+            sym = 0.5 * (g + g.transpose(0, 2, 1))
+            for i in range(D):
+                sym[:, i, i] -= c["divv"] / D
+            tss = (sym * sym).sum((1, 2))
+            c["tracess"] = tss
+            res = (2.0 * (1.0 - R) ** 4 * c["divv"]) ** 2
+            with np.errstate(invalid="ignore", divide="ignore"):
+                xi = np.where(res < 1e-16, 0.0, res / (res + tss))
+            trig = np.maximum(-c["ddivvdt"], 0.0)
+            c["xi"], c["trigger"] = xi, trig
+            At = xi * trig
+            with np.errstate(invalid="ignore", divide="ignore"):
+                aloc = p.sph_viscosity_alpha_max * At / (p.sph_viscosity_delta * (vs / c["h"]) ** 2 + At)
+                decay = c["h"] / (2.0 * p.sph_viscosity_l * vs)
+                damp = c["alpha"] * np.exp(-((c["alpha"] - aloc) / decay) * self.dt_)
+            c["alpha"] = np.where(c["alpha"] <= aloc, aloc, damp)
             return
         if op == 6:
             # add_short_range_repulsion, default_physics.h:718-754: neighbours other than the body itself within
@@ -784,6 +827,8 @@ class PortSystem:
                 if not done.all():
                     raise RuntimeError("eint-based dt estimator did not converge")
             c["dt"] = dtmin
+        elif op == 12:  # viscosity::initialize_alpha, viscosity.h:172-180
+            c["alpha"] = np.full(self.n, p.sph_viscosity_alpha if p.sph_viscosity == 0 else 0.0)
         elif op in (13, 14, 15):  # add_drag_acceleration :702-709, add_drag_dedt :573-581, add_drag_dudt :587-595
             v2 = (c["vel"] * c["vel"]).sum(1)
             drag = 0.0 - (p.relaxation_beta + p.relaxation_gamma * v2)[:, None] * c["vel"]     # external_force::acceleration_drag, eforce.h:441-451
@@ -863,6 +908,9 @@ class PortSystem:
         relaxing = self.iteration < p.relaxation_steps     # hydro/main_driver.cc:128-133,152,165,205-206,221,235
 
         def acceleration():
+            if p.sph_viscosity != 0:       # hydro/main_driver.cc:121-124,195-198
+                S(5)
+            self.reset_ghosts()
             S(1)
             if relaxing:
                 A(13); S(6)
@@ -886,7 +934,9 @@ class PortSystem:
             A(0)
             if p.thermokinetic_formulation:
                 A(1)
-            S(0); A(2); self.reset_ghosts(); acceleration()
+            if p.sph_viscosity != 0:
+                A(12)
+            S(0); A(2); acceleration()
             if p.adaptive_timestep:
                 A(9); G(0)
             if p.evolve_internal_energy:
@@ -896,7 +946,7 @@ class PortSystem:
                 A(5 if p.thermokinetic_formulation else 4)
             A(3); A(2); A(6)
             self.update_iteration()
-            S(0); self.reset_ghosts(); acceleration()
+            S(0); acceleration()
             A(3); self.reset_ghosts()
             if p.evolve_internal_energy:
                 energy()

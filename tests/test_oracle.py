@@ -109,3 +109,21 @@ def test_port_relaxation_phase_matches_reference(dim, thermokinetic):
     for it in range(4):
         P.step(initial=(it == 0)); R.step(initial=(it == 0))
         assert_fields_close(P, R, names, 1e-10 if it < 2 else 1e-9)
+
+
+@pytest.mark.parametrize("name,kw", [("sedov", dict(nx=10)), ("random", dict(n=500, dim=2, seed=7, h_jitter=0.1)), ("sod", dict(nx=100)),
+                                     ("random", dict(n=600, dim=3, seed=8, par=dict(thermokinetic_formulation=0)))])
+def test_port_cullen_dehnen_viscosity_matches_reference(name, kw):
+    """sph_viscosity = cullen (viscosity.h:150-157,172-363; compute_divv default_physics.h:273-300): the per-body alpha, its
+    trigger and limiter, and the fields they feed, through four driver iterations."""
+    f, par, dim = case(name, **kw)
+    if not have_ref(dim):
+        pytest.skip("oracle/_ref not built")
+    par = dict(par, sph_viscosity=capi.VISC_CULLEN, sph_viscosity_alpha_max=1.5, sph_viscosity_l=0.1, sph_viscosity_delta=0.7)
+    P, R = make_system("port", f, par, dim), make_system("ref", f, par, dim)
+    thermo = par.get("thermokinetic_formulation", 1)
+    names = ["pos", "vel", "rho", "P", "u", "cs", "acc", "h", "vsig", "dt", "alpha", "divv", "ddivvdt", "xi", "trigger", "tracess", "gradv"] + \
+            (["dedt", "e"] if thermo else ["dudt"])
+    for it in range(4):
+        P.step(initial=(it == 0)); R.step(initial=(it == 0))
+        assert_fields_close(P, R, names, 1e-10 if it < 2 else 1e-9)
