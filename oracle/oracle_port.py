@@ -18,7 +18,7 @@ tree3d.cc:85; key round trip, tree_topology/test/filling_curves.cc:202-241)
 are asserted in tests/test_oracle.py as well.  Restated: the constant-viscosity /
 ideal-or-polytropic hydro path of the drivers with external forces and potentials
 (eforce.h; tests/test_eforce.py), all four equations of state, the relaxation phase
-(drag, short-range repulsion) and the Cullen-Dehnen viscosity; not restated (oracle/_ref only): FMM gravity.
+(drag, short-range repulsion), the Cullen-Dehnen viscosity and FMM gravity (monopole dual tree walk).
 
 Each function cites the reference file:line it follows (paths relative to
 /root/reference).  Bit-exact parts (range, keys, order, tree, node summaries,
@@ -227,8 +227,6 @@ class PortSystem:
         # the port restates the constant-viscosity / ideal-or-polytropic path (with external forces); the other physics is
         # checked against oracle/_ref only -- refuse rather than silently ignore a selector
         self.ef = ExternalForce(params, params.dim)
-        if params.enable_fmm:
-            raise NotImplementedError("oracle_port: FMM gravity is not restated here (use oracle/_ref)")
         self.dim = D = params.dim
         self.B = 63 // D  # filling_curve.h:45-47
         self.n = 0
@@ -414,6 +412,77 @@ class PortSystem:
                 r = max(r, dist + radius[c]); lp = max(lp, dist + radius[c] + lap[c])
             mass[nd] = M; com[nd] = X; radius[nd] = r; lap[nd] = lp; bmin[nd] = mn; bmax[nd] = mx; sub[nd] = S
         t.update(mass=mass, com=com, radius=radius, lap=lap, bmin=bmin, bmax=bmax, sub=sub)
+
+    def gravitation_fmm(self):
+        """body_system::gravitation_fmm (bodies_system.h:282-288): tree_topology::traversal_fmm (tree_topology.h:448-795) with the
+        functors of include/physics/fmm.h (taylor_c2c / taylor_p2c :146-159, fmm_p2p :113-143, fmm_c2p :103-111) and
+        fmm_sub_entities_ = 0.  A dual walk over (sink cell, source cell) pairs from (root, root): two bodies -> direct term;
+        the same node -> all ordered pairs of its children; r1 + r2 < theta |X1 - X2| (tree_geometry.h:343-350) -> the source's
+        monopole goes to the sink (a node accumulates it at its centre of mass in (pc, fc), a body takes it directly);
+        otherwise the cell with the larger radius is split.  Afterwards every body adds pc - (x - X).fc and fc of each
+        ancestor node that was a sink (interaction_c2p, fmm.h:80-97).  Accumulates into gpot / gacc (3-D only)."""
+        assert self.dim == 3
+        t, c, par = self.t, self.c, self.par
+        cs, isleaf, cnode = t["cell_start"], t["cell_isleaf"], t["cell_node"]
+        cb, ce = t["child_begin"], t["child_end"]
+        mass, com, radius = t["mass"], t["com"], t["radius"]
+        pos, m, ids = c["pos"], c["mass"], c["id"]
+        gc, theta = par.gravitational_constant, par.fmm_macangle
+        pc, fc, hit = np.zeros(t["nn"]), np.zeros((t["nn"], 3)), np.zeros(t["nn"], bool)
+        gpot, gacc = c["gpot"].copy(), c["gacc"].copy()
+
+        def monopole(x, X, M):
+            d = self._distance(x, X)
+            return -gc * M / d, -gc * M * (x - X) / (d * d * d)
+        queue = [(0, 0)]
+        while queue:
+            nxt = []
+            for c1, c2 in queue:
+                l1, l2 = isleaf[c1], isleaf[c2]
+                if l1 and l2:
+                    i, j = cs[c1], cs[c2]
+                    if ids[i] != ids[j]:
+                        dp, da = monopole(pos[i], pos[j], m[j])
+                        gpot[i] += dp
+                        gacc[i] = gacc[i] + da
+                    continue
+                if c1 == c2:
+                    kids = range(cb[cnode[c1]], ce[cnode[c1]])
+                    for k1 in kids:
+                        nxt.append((k1, k1))
+                        for k2 in range(k1 + 1, kids.stop):
+                            nxt.append((k1, k2))
+                            nxt.append((k2, k1))
+                    continue
+                X1, r1 = (pos[cs[c1]], 0.0) if l1 else (com[cnode[c1]], radius[cnode[c1]])
+                X2, r2, M2 = (pos[cs[c2]], 0.0, m[cs[c2]]) if l2 else (com[cnode[c2]], radius[cnode[c2]], mass[cnode[c2]])
+                if r1 + r2 < theta * self._distance(X1, X2):
+                    dp, da = monopole(X1, X2, M2)
+                    if l1:
+                        gpot[cs[c1]] += dp
+                        gacc[cs[c1]] = gacc[cs[c1]] + da
+                    else:
+                        pc[cnode[c1]] += dp
+                        fc[cnode[c1]] = fc[cnode[c1]] + da
+                        hit[cnode[c1]] = True
+                elif r1 > r2:
+                    nxt += [(k, c2) for k in range(cb[cnode[c1]], ce[cnode[c1]])]
+                else:
+                    nxt += [(c1, k) for k in range(cb[cnode[c2]], ce[cnode[c2]])]
+            queue = nxt
+        # c2p: the bodies below every node that was a sink
+        for nd in np.nonzero(hit)[0]:
+            stack = [t["node_cell"][nd]]
+            while stack:
+                cell = stack.pop()
+                if isleaf[cell]:
+                    i = cs[cell]
+                    r = pos[i] - com[nd]
+                    gpot[i] += pc[nd] - (r * fc[nd]).sum()
+                    gacc[i] = gacc[i] + fc[nd]
+                else:
+                    stack += list(range(cb[cnode[cell]], ce[cnode[cell]]))
+        c["gpot"], c["gacc"] = gpot, gacc
 
     def _distance(self, a, b):
         """flecsi::distance, space_vector.h:46-58."""
@@ -901,7 +970,7 @@ class PortSystem:
         return float(self.c["h"].max())
 
     def step(self, initial=False):
-        """One iteration of app/drivers/hydro/main_driver.cc:102-277 (no FMM in the port)."""
+        """One iteration of app/drivers/hydro/main_driver.cc:102-277 (+ newtonian/main_driver.cc:218-222 with enable_fmm)."""
         p = self.par
         S, A, G = self.apply_in_smoothinglength, self.apply_all, self.get_all
 
@@ -914,6 +983,8 @@ class PortSystem:
             S(1)
             if relaxing:
                 A(13); S(6)
+            if p.enable_fmm:               # newtonian/main_driver.cc:218-222
+                self.gravitation_fmm()
 
         def energy():
             for m in range(1, p.pressure_updates_number + 1):

@@ -127,3 +127,21 @@ def test_port_cullen_dehnen_viscosity_matches_reference(name, kw):
     for it in range(4):
         P.step(initial=(it == 0)); R.step(initial=(it == 0))
         assert_fields_close(P, R, names, 1e-10 if it < 2 else 1e-9)
+
+
+def test_port_fmm_gravity_matches_reference():
+    """body_system::gravitation_fmm: the monopole dual tree walk alone, and through newtonian driver iterations (collapse)."""
+    f, par, dim = case("collapse", nx=8, fmm=1)
+    if not have_ref(dim):
+        pytest.skip("oracle/_ref not built")
+    P, R = make_system("port", f, par, dim), make_system("ref", f, par, dim)
+    P.update_iteration(); R.update_iteration()
+    P.gravitation_fmm(); R.gravitation_fmm()
+    assert np.abs(R.get(capi.COL_GACC)).max() > 0
+    assert_fields_close(P, R, ["gacc", "gpot"], 1e-10)
+    P2, R2 = make_system("port", f, par, dim), make_system("ref", f, par, dim)
+    for it in range(3):
+        P2.step(initial=(it == 0)); R2.step(initial=(it == 0))
+        assert_fields_close(P2, R2, ["pos", "vel", "rho", "P", "u", "acc", "gacc", "gpot", "dudt", "h"], 1e-10 if it < 2 else 1e-9)
+        ep, er = P2.get_all(capi.GET_TOTAL_ENERGY, 1)[0], R2.get_all(capi.GET_TOTAL_ENERGY, 1)[0]
+        assert abs(ep - er) <= 1e-10 * abs(er)
