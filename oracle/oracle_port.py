@@ -227,6 +227,8 @@ class PortSystem:
         # the port restates the constant-viscosity / ideal-or-polytropic path (with external forces); the other physics is
         # checked against oracle/_ref only -- refuse rather than silently ignore a selector
         self.ef = ExternalForce(params, params.dim)
+        if params.periodic_boundary_x or params.periodic_boundary_y or params.periodic_boundary_z:
+            raise NotImplementedError("oracle_port: periodic boundaries (boundary.h) are not restated here (use oracle/_ref)")
         self.dim = D = params.dim
         self.B = 63 // D  # filling_curve.h:45-47
         self.n = 0
