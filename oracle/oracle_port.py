@@ -18,7 +18,8 @@ tree3d.cc:85; key round trip, tree_topology/test/filling_curves.cc:202-241)
 are asserted in tests/test_oracle.py as well.  Restated: the constant-viscosity /
 ideal-or-polytropic hydro path of the drivers with external forces and potentials
 (eforce.h; tests/test_eforce.py), all four equations of state, the relaxation phase
-(drag, short-range repulsion), the Cullen-Dehnen viscosity and FMM gravity (monopole dual tree walk).
+(drag, short-range repulsion), the Cullen-Dehnen viscosity, FMM gravity (monopole dual tree walk) and the periodic
+boundaries (WALL copies); one rank.
 
 Each function cites the reference file:line it follows (paths relative to
 /root/reference).  Bit-exact parts (range, keys, order, tree, node summaries,
@@ -227,8 +228,6 @@ class PortSystem:
         # the port restates the constant-viscosity / ideal-or-polytropic path (with external forces); the other physics is
         # checked against oracle/_ref only -- refuse rather than silently ignore a selector
         self.ef = ExternalForce(params, params.dim)
-        if params.periodic_boundary_x or params.periodic_boundary_y or params.periodic_boundary_z:
-            raise NotImplementedError("oracle_port: periodic boundaries (boundary.h) are not restated here (use oracle/_ref)")
         self.dim = D = params.dim
         self.B = 63 // D  # filling_curve.h:45-47
         self.n = 0
@@ -504,8 +503,57 @@ class PortSystem:
     def leaf_depth(self):
         return self.leaf_depth_.copy()
 
+    def periodic_walls(self):
+        """boundary::pboundary_clean + pboundary_generate (include/physics/boundary.h:45-248) as update_iteration calls them
+        (bodies_system.h:160-168): the WALL copies of the previous iteration go (stable), bodies outside the box re-enter on the
+        other side, and every body within halo = 2.5 max h of a periodic face gets one copy per such axis plus the xy / xz / zy
+        edge and the xyz corner copies, appended body by body in that order and numbered from the real-body count upwards."""
+        c, p, D = self.c, self.par, self.dim
+        keep = c["type"] != 1
+        for k in list(c):
+            c[k] = c[k][keep]
+        self.n = n0 = int(keep.sum())
+        halo = 2.5 * float(c["h"].max())
+        periodic = (p.periodic_boundary_x, p.periodic_boundary_y, p.periodic_boundary_z)
+        lo = np.array([-0.5 * p.box_length, -0.5 * p.box_width, -0.5 * p.box_height])[:D]
+        hi = np.array([0.5 * p.box_length, 0.5 * p.box_width, 0.5 * p.box_height])[:D]
+        pos = c["pos"]
+        for d in range(D):
+            if periodic[d]:
+                x = pos[:, d]
+                pos[:, d] = np.where(x > hi[d], x - (hi[d] - lo[d]), np.where(x <= lo[d], x + (hi[d] - lo[d]), x))
+        src, newpos = [], []
+        corners = {2: [(0, 1)], 3: [(0, 1), (0, 2), (2, 1), (0, 1, 2)]}.get(D, [])
+        for i in range(n0):
+            x = pos[i]
+            up = [periodic[d] and bool(x[d] + halo > hi[d]) for d in range(D)]
+            on = [periodic[d] and (up[d] or bool(x[d] - halo <= lo[d])) for d in range(D)]
+            for d in range(D):
+                if on[d]:
+                    y = x.copy()
+                    y[d] = y[d] - (hi[d] - lo[d]) if up[d] else y[d] + (hi[d] - lo[d])
+                    src.append(i); newpos.append(y)
+            for axes in corners:
+                if all(on[d] for d in axes):
+                    y = x.copy()
+                    for d in axes:   # add_corner_XX / _XXX: the reference's own expressions
+                        y[d] = lo[d] - abs(x[d] + lo[d]) if up[d] else hi[d] + abs(x[d] + hi[d])
+                    src.append(i); newpos.append(y)
+        if src:
+            src = np.array(src)
+            for k in list(c):
+                c[k] = np.concatenate([c[k], c[k][src]])
+            m = len(src)
+            c["pos"][n0:] = np.array(newpos)
+            c["type"][n0:] = 1
+            c["id"][n0:] = n0 + np.arange(m)
+            self.n = n0 + m
+
     def update_iteration(self):
-        """body_system::update_iteration, bodies_system.h:152-229 (non-periodic, one rank)."""
+        """body_system::update_iteration, bodies_system.h:152-229 (one rank)."""
+        p = self.par
+        if p.periodic_boundary_x or p.periodic_boundary_y or p.periodic_boundary_z:
+            self.periodic_walls()
         self.compute_range()
         self.compute_keys()
         self.sort_bodies()

@@ -145,3 +145,26 @@ def test_port_fmm_gravity_matches_reference():
         assert_fields_close(P2, R2, ["pos", "vel", "rho", "P", "u", "acc", "gacc", "gpot", "dudt", "h"], 1e-10 if it < 2 else 1e-9)
         ep, er = P2.get_all(capi.GET_TOTAL_ENERGY, 1)[0], R2.get_all(capi.GET_TOTAL_ENERGY, 1)[0]
         assert abs(ep - er) <= 1e-10 * abs(er)
+
+
+@pytest.mark.parametrize("dim,periodic", [(3, (1, 1, 1)), (3, (1, 0, 1)), (2, (1, 1, 0)), (1, (1, 0, 0))])
+def test_port_periodic_boundaries_match_reference(dim, periodic):
+    """boundary.h:45-248: the WALL copies (count, positions, ids, order), the tree and neighbour sets over them bit for bit,
+    and four driver iterations (copies are regenerated every iteration; strays re-enter the box)."""
+    f, par, _ = case("periodic", n={1: 120, 2: 400, 3: 500}[dim], dim=dim, seed=13, h_jitter=0.1, box=(1.0, 0.8, 0.6), periodic=periodic, stray=0.02)
+    if not have_ref(dim):
+        pytest.skip("oracle/_ref not built")
+    P, R = make_system("port", f, par, dim), make_system("ref", f, par, dim)
+    P.update_iteration(); R.update_iteration()
+    assert P.nbodies() == R.nbodies() > len(f["mass"])
+    assert np.array_equal(P.get(capi.COL_TYPE), R.get(capi.COL_TYPE)) and np.array_equal(P.get(capi.COL_POS), R.get(capi.COL_POS))
+    assert_tree_equal(P, R)
+    P.apply_in_smoothinglength(capi.SWEEP_NEIGHBORS_ONLY); R.apply_in_smoothinglength(capi.SWEEP_NEIGHBORS_ONLY)
+    assert_neighbors_equal(P, R)
+    P2, R2 = make_system("port", f, par, dim), make_system("ref", f, par, dim)
+    for it in range(4):
+        P2.step(initial=(it == 0)); R2.step(initial=(it == 0))
+        assert P2.nbodies() == R2.nbodies()
+        assert_fields_close(P2, R2, ["pos", "vel", "rho", "P", "u", "acc", "dedt", "h", "vsig", "dt"], 1e-10 if it < 2 else 1e-9)
+    for op in (capi.GET_TOTAL_MASS, capi.GET_TOTAL_ENERGY, capi.GET_TOTAL_MOMENTUM):
+        assert np.allclose(P2.get_all(op), R2.get_all(op), rtol=1e-11, atol=1e-14)
