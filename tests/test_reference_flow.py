@@ -23,7 +23,20 @@ SEDOV_NX20 = dict(
     output_h5data_prefix='"sedov_evolution"', sph_variable_h="yes", adaptive_timestep="yes", timestep_cfl_factor=0.01)
 
 
-def run_flow(driver, workdir, dim=3):
+# the settings of data/mesa_nx20.par (the reference's mesa_relaxation_test, app/drivers/CMakeLists.txt:139-143: the Sedov
+# generator on an icosahedral lattice with perturbed positions, then 10 iterations of the relaxation phase with the
+# "spherical density support" external force of a mesa density profile, polytropic EOS, internal energy not evolved)
+MESA_NX20 = dict(
+    initial_data_prefix='"mesa_nx20"', domain_type=1, sphere_radius=1.0, density_profile='"mesa"',
+    external_force_type='"spherical density support"', lattice_nx=20, lattice_type=3, lattice_perturbation_amplitude=0.15,
+    eos_type='"polytropic"', poly_gamma=1.4, rho_initial=1.0, pressure_initial=0.1, sedov_blast_energy=0.0, relaxation_steps=200,
+    relaxation_beta=1.0, relaxation_gamma=0.0001, out_screen_every=1, out_scalar_every=1, out_h5data_every=10,
+    output_h5data_prefix='"mesa_3d"', sph_eta=1.6, sph_kernel='"Wendland C4"', initial_dt=1.e-4, thermokinetic_formulation="yes",
+    final_iteration=10, adaptive_timestep="yes", sph_variable_h="yes", timestep_cfl_factor=0.25, evolve_internal_energy="no")
+
+
+def run_flow(driver, workdir, dim=3, settings=None, par_name="sedov_nx20.par", out_name="sedov_evolution.h5part"):
+    settings = settings or SEDOV_NX20
     gen = os.path.join(REF, "sedov_%dd_generator" % dim)
     for exe in (gen, driver):
         if not os.path.exists(exe):
@@ -31,13 +44,13 @@ def run_flow(driver, workdir, dim=3):
         if not os.access(exe, os.X_OK):
             os.chmod(exe, 0o755)
     os.makedirs(workdir, exist_ok=True)
-    with open(os.path.join(workdir, "sedov_nx20.par"), "w") as f:
-        f.write("".join("  %s = %s\n" % (k, v if isinstance(v, str) else repr(v)) for k, v in SEDOV_NX20.items()))
+    with open(os.path.join(workdir, par_name), "w") as f:
+        f.write("".join("  %s = %s\n" % (k, v if isinstance(v, str) else repr(v)) for k, v in settings.items()))
     for exe in (gen, driver):
-        r = subprocess.run([exe, "sedov_nx20.par"], cwd=workdir, capture_output=True, text=True, timeout=900)
+        r = subprocess.run([exe, par_name], cwd=workdir, capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
     scal = np.loadtxt(os.path.join(workdir, "scalar_reductions.dat"), comments="#", ndmin=2)
-    hf = h5probe.File(os.path.join(workdir, "sedov_evolution.h5part"))
+    hf = h5probe.File(os.path.join(workdir, out_name))
     return scal, hf
 
 
@@ -70,6 +83,38 @@ def test_reference_flow_on_the_gpu_facade(tmp_path, dim):
     pa, pb = np.argsort(a["id"].data), np.argsort(b["id"].data)
     assert np.array_equal(a["id"].data[pa], b["id"].data[pb])
     for k in ("x", "y", "z", "vx", "vy", "vz", "ax", "ay", "az", "h", "rho", "u", "P", "m", "dt"):
+        x, y = a[k].data[pa], b[k].data[pb]
+        scale = max(np.abs(b[c].data).max() for c in (("ax", "ay", "az") if k[0] == "a" else ("vx", "vy", "vz") if k[0] == "v" and len(k) == 2 else (k,)))
+        assert np.abs(x - y).max() <= 1e-7 * scale, (k, np.abs(x - y).max(), scale)
+
+
+MESA = dict(settings=MESA_NX20, par_name="mesa_nx20.par", out_name="mesa_3d.h5part")
+
+
+def check_mesa(scal, hf):
+    assert scal[-1, 0] == 10 and sorted(hf.root.groups) == ["Step#0", "Step#1"]
+    assert int(hf.root.groups["Step#1"].attrs["iteration"][0]) == 10
+    assert np.abs(scal[:, 3] - scal[0, 3]).max() <= 1e-12 * scal[0, 3]   # mass
+
+
+def test_reference_mesa_relaxation_flow_on_cpu(tmp_path):
+    scal, hf = run_flow(os.path.join(REF, "hydro_3d_ref_h5"), str(tmp_path / "ref"), 3, **MESA)
+    check_mesa(scal, hf)
+
+
+@pytest.mark.gpu
+def test_reference_mesa_relaxation_flow_on_the_gpu_facade(tmp_path):
+    """External force "spherical density support" (mesa profile), relaxation drag, polytropic EOS, internal energy not
+    evolved: the reference's mesa_relaxation_test on the facade against the reference build."""
+    sg, hg = run_flow(os.path.join(B200, "hydro_3d_b200_h5"), str(tmp_path / "gpu"), 3, **MESA)
+    sr, hr = run_flow(os.path.join(REF, "hydro_3d_ref_h5"), str(tmp_path / "ref"), 3, **MESA)
+    check_mesa(sg, hg)
+    assert sg.shape == sr.shape
+    assert np.allclose(sg[:, :7], sr[:, :7], rtol=1e-8, atol=0)
+    a, b = hg.root.groups["Step#1"].datasets, hr.root.groups["Step#1"].datasets
+    pa, pb = np.argsort(a["id"].data), np.argsort(b["id"].data)
+    assert np.array_equal(a["id"].data[pa], b["id"].data[pb])
+    for k in ("x", "y", "z", "vx", "vy", "vz", "ax", "ay", "az", "h", "rho", "P", "m", "dt"):
         x, y = a[k].data[pa], b[k].data[pb]
         scale = max(np.abs(b[c].data).max() for c in (("ax", "ay", "az") if k[0] == "a" else ("vx", "vy", "vz") if k[0] == "v" and len(k) == 2 else (k,)))
         assert np.abs(x - y).max() <= 1e-7 * scale, (k, np.abs(x - y).max(), scale)
