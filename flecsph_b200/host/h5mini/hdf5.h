@@ -383,3 +383,11 @@ inline herr_t H5Pclose(hid_t id) { return h5mini_api::release(id, h5mini_api::K_
 template<typename C, typename I> inline herr_t H5Pset_fapl_mpio(hid_t, C, I) { return 0; }
 inline herr_t H5Pset_dxpl_mpio(hid_t, int) { return 0; }
 template<typename... A> inline herr_t H5Eset_auto(A...) { return 0; }
+
+// the versioned names the library's H5Xcreate / H5Xopen macros expand to (H5version.h)
+inline hid_t H5Gcreate2(hid_t l, const char * n, hid_t a, hid_t b, hid_t c) { return H5Gcreate(l, n, a, b, c); }
+inline hid_t H5Gopen2(hid_t l, const char * n, hid_t a) { return H5Gopen(l, n, a); }
+inline hid_t H5Dcreate2(hid_t l, const char * n, hid_t t, hid_t s, hid_t a, hid_t b, hid_t c) { return H5Dcreate(l, n, t, s, a, b, c); }
+inline hid_t H5Dopen2(hid_t l, const char * n, hid_t a) { return H5Dopen(l, n, a); }
+inline hid_t H5Acreate2(hid_t l, const char * n, hid_t t, hid_t s, hid_t a, hid_t b) { return H5Acreate(l, n, t, s, a, b); }
+template<typename... A> inline herr_t H5Eset_auto2(A...) { return 0; }
