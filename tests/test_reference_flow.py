@@ -118,3 +118,27 @@ def test_reference_mesa_relaxation_flow_on_the_gpu_facade(tmp_path):
         x, y = a[k].data[pa], b[k].data[pb]
         scale = max(np.abs(b[c].data).max() for c in (("ax", "ay", "az") if k[0] == "a" else ("vx", "vy", "vz") if k[0] == "v" and len(k) == 2 else (k,)))
         assert np.abs(x - y).max() <= 1e-7 * scale, (k, np.abs(x - y).max(), scale)
+
+
+def test_reference_restart_from_a_snapshot_on_cpu(tmp_path):
+    """Checkpoint / resume as the reference does it (mpisph/io.h:663-777: initial_iteration != 0 looks the iteration up among
+    the steps of <prefix>.h5part, reads its time and time step back): 20 iterations in one go against 10 + a restart from
+    the step written at iteration 10, on the reference's classes over the HDF5 stand-in."""
+    drv = os.path.join(REF, "hydro_3d_ref_h5")
+    base = dict(SEDOV_NX20, lattice_nx=14, sedov_blast_radius=0.15, final_iteration=20, out_scalar_every=1, output_h5data_prefix='"ev"')
+    scal_a, hf_a = run_flow(drv, str(tmp_path), 3, settings=base, par_name="a.par", out_name="ev.h5part")
+    assert [int(hf_a.root.groups["Step#%d" % k].attrs["iteration"][0]) for k in range(3)] == [0, 10, 20]
+    os.rename(str(tmp_path / "scalar_reductions.dat"), str(tmp_path / "scalar_a.dat"))
+    again = dict(base, initial_data_prefix='"ev"', initial_iteration=10, output_h5data_prefix='"ev_restart"')
+    with open(str(tmp_path / "b.par"), "w") as f:
+        f.write("".join("  %s = %s\n" % (k, v if isinstance(v, str) else repr(v)) for k, v in again.items()))
+    r = subprocess.run([drv, "b.par"], cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    hf_b = h5probe.File(str(tmp_path / "ev_restart.h5part"))
+    sa, sb = hf_a.root.groups["Step#2"], hf_b.root.groups["Step#1"]
+    assert int(sb.attrs["iteration"][0]) == 20 and int(hf_b.root.groups["Step#0"].attrs["iteration"][0]) == 10
+    assert abs(sb.attrs["time"][0] - sa.attrs["time"][0]) <= 1e-12 * sa.attrs["time"][0]
+    scal_b = np.loadtxt(str(tmp_path / "scalar_reductions.dat"), comments="#", ndmin=2)
+    assert scal_b[0, 0] == 10 and scal_b[-1, 0] == 20
+    assert abs(scal_b[-1, 4] - scal_a[-1, 4]) <= 1e-6 * abs(scal_a[-1, 4])      # total energy at iteration 20
+    assert np.array_equal(np.sort(sa.datasets["id"].data), np.sort(sb.datasets["id"].data))
